@@ -1,0 +1,17 @@
+// api.cu -- error reporting and version for the libst3d C ABI.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void st3d_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* st3d_last_error(void) { return g_err; }
+extern "C" int st3d_version(void) { return 100; }

@@ -1,0 +1,257 @@
+// gram.cu -- Gram-matrix style loss: G = F F^T (style_transfer.py:31-35), the per-layer loss
+// mean((G - Gs)^2) / (C^2 H^2) of losses.py:35-39 fused into the split-K finalize, and the backward
+// dF = (dG + dG^T) F.  SURVEY.md section 8 rows a11, a12, a17.
+//
+// Two arithmetic modes behind one ABI:
+//   ST3D_GRAM_TF32  tcgen05.mma kind::tf32 with TMEM accumulators, TMA-fed (gram_tc.cuh); the product path
+//   ST3D_GRAM_FP32  FFMA tiles, exact fp32 products; any C / HW; used for odd shapes and as the
+//                   on-device cross-check of the tensor-core path
+// Both write split-K partial sums to the workspace; k_gram_finalize adds them in a fixed order
+// (deterministic result) and applies the MSE-vs-target epilogue.
+#include "gram_common.cuh"
+#include "gram_tc.cuh"
+
+namespace st3d {
+
+// -------------------------------------------------------------------------------------------------
+// FP32 FFMA forward: one 64x64 tile of one split of one image per CTA (lower-triangular tiles only)
+// -------------------------------------------------------------------------------------------------
+constexpr int kST = 64, kSK = 16;
+
+__global__ void __launch_bounds__(256)
+k_gram_simt(const float* __restrict__ feat, int C, int64_t HW, int splits, int64_t k_chunk,
+            float* __restrict__ partials) {
+    __shared__ float sA[kSK][kST + 4], sB[kSK][kST + 4];
+    // blockIdx.x enumerates tile pairs (ti >= tj)
+    int ti = 0, rem = blockIdx.x;
+    while (rem > ti) { rem -= ti + 1; ++ti; }
+    const int tj = rem;
+    const int split = blockIdx.y, b = blockIdx.z;
+    const float* F = feat + (int64_t)b * C * HW;
+    const int64_t k0 = (int64_t)split * k_chunk, k1 = min(HW, k0 + k_chunk);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    for (int64_t k = k0; k < k1; k += kSK) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int r = (threadIdx.x >> 4) + 16 * m, kk = threadIdx.x & 15;
+            const int64_t x = k + kk;
+            const int ra = ti * kST + r, rb = tj * kST + r;
+            sA[kk][r] = (ra < C && x < k1) ? F[(int64_t)ra * HW + x] : 0.0f;
+            sB[kk][r] = (rb < C && x < k1) ? F[(int64_t)rb * HW + x] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kSK; ++kk) {
+            float a[4], bb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = sA[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bb[j] = sB[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* P = partials + ((int64_t)b * splits + split) * C * C;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = ti * kST + ty * 4 + i, c = tj * kST + tx * 4 + j;
+            if (r < C && c < C) {
+                P[(int64_t)r * C + c] = acc[i][j];
+                if (ti != tj) P[(int64_t)c * C + r] = acc[i][j];
+            }
+        }
+}
+
+// -------------------------------------------------------------------------------------------------
+// finalize: G = sum over splits (fixed order); optional gram / MSE-vs-target / dgram outputs
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_gram_finalize(const float* __restrict__ partials, int splits, int B, int Bt, int C,
+                const float* __restrict__ target, float scale, float* __restrict__ gram, float* __restrict__ dgram,
+                float* __restrict__ loss_out) {
+    const int64_t cc = (int64_t)C * C, total = (int64_t)B * cc;
+    float acc = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / cc, e = i % cc;
+        const float* p = partials + b * splits * cc + e;
+        float g = 0.0f;
+        for (int s = 0; s < splits; ++s) g += p[(int64_t)s * cc];
+        if (gram) gram[i] = g;
+        if (target) {
+            const float d = g - target[(Bt == 1 ? 0 : b) * cc + e];
+            acc += d * d;
+            if (dgram) dgram[i] = 2.0f * scale * d;
+        }
+    }
+    if (!target || !loss_out) return;
+    __shared__ float s_part[8];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < 8 ? s_part[threadIdx.x] : 0.0f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) atomicAdd(loss_out, v * scale);
+    }
+}
+
+// S = gs * (dG + dG^T)
+__global__ void k_gram_symmetrize(const float* __restrict__ dgram, int B, int C, float gs, float* __restrict__ sym) {
+    const int64_t cc = (int64_t)C * C, i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * cc) return;
+    const int64_t b = i / cc, e = i % cc;
+    const int r = (int)(e / C), c = (int)(e % C);
+    sym[i] = gs * (dgram[i] + dgram[b * cc + (int64_t)c * C + r]);
+}
+
+// -------------------------------------------------------------------------------------------------
+// FP32 FFMA backward: dF[b, c, x] = sum_j S[b, c, j] F[b, j, x];  64 (c) x 64 (x) tile per CTA
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_gram_bwd_simt(const float* __restrict__ feat, const float* __restrict__ sym, int C, int64_t HW, int accumulate,
+                float* __restrict__ grad_feat) {
+    __shared__ float sS[kSK][kST + 4];  // [j][c]
+    __shared__ float sF[kSK][kST + 4];  // [j][x]
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * kST;
+    const int64_t x0 = (int64_t)blockIdx.x * kST;
+    const float* F = feat + (int64_t)b * C * HW;
+    const float* S = sym + (int64_t)b * C * C;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    for (int j0 = 0; j0 < C; j0 += kSK) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            {   // S tile: c = tid/16 + 16 m, j = tid%16 (j contiguous in memory)
+                const int c = (threadIdx.x >> 4) + 16 * m, jj = threadIdx.x & 15;
+                sS[jj][c] = (c0 + c < C && j0 + jj < C) ? S[(int64_t)(c0 + c) * C + j0 + jj] : 0.0f;
+            }
+            {   // F tile: j = tid/64 + 4 m, x = tid%64 (x contiguous)
+                const int jj = (threadIdx.x >> 6) + 4 * m, x = threadIdx.x & 63;
+                sF[jj][x] = (j0 + jj < C && x0 + x < HW) ? F[(int64_t)(j0 + jj) * HW + x0 + x] : 0.0f;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kSK; ++kk) {
+            float a[4], bb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = sS[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bb[j] = sF[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* G = grad_feat + (int64_t)b * C * HW;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + ty * 4 + i;
+            const int64_t x = x0 + tx * 4 + j;
+            if (c < C && x < HW) {
+                const int64_t o = (int64_t)c * HW + x;
+                G[o] = accumulate ? G[o] + acc[i][j] : acc[i][j];
+            }
+        }
+}
+
+static int check_common(const char* what, const float* feat, int B, int C, int64_t HW, int precision) {
+    ST3D_REQUIRE(B >= 0 && C >= 1 && HW >= 1, "%s: bad sizes B=%d C=%d HW=%lld", what, B, C, (long long)HW);
+    ST3D_REQUIRE(B == 0 || feat, "%s: null feat", what);
+    ST3D_REQUIRE(precision == ST3D_GRAM_TF32 || precision == ST3D_GRAM_FP32, "%s: unknown precision %d", what,
+                 precision);
+    if (precision == ST3D_GRAM_TF32 && !gram_tc_supported(C, HW)) {
+        st3d_set_error("%s: the tcgen05 path needs C in {64,128,256,512} and HW %% 4 == 0 (got C=%d HW=%lld); "
+                       "use ST3D_GRAM_FP32", what, C, (long long)HW);
+        return ST3D_ERR_UNSUPPORTED;
+    }
+    return ST3D_OK;
+}
+
+static int gram_partials(const float* feat, const GramPlan& p, int precision, cudaStream_t s) {
+    if (precision == ST3D_GRAM_TF32) return gram_tc_forward(feat, p, s);
+    const int T = cdiv(p.C, kST);
+    k_gram_simt<<<dim3(T * (T + 1) / 2, p.splits, p.B), 256, 0, s>>>(feat, p.C, p.HW, p.splits, p.k_chunk, p.partials);
+    ST3D_LAUNCH_OK("k_gram_simt");
+    return ST3D_OK;
+}
+
+}  // namespace st3d
+
+using namespace st3d;
+
+extern "C" size_t st3d_gram_workspace_size(int B, int C, int64_t HW) {
+    if (B <= 0 || C <= 0 || HW <= 0) return 256;
+    return gram_plan(nullptr, B, C, HW, gram_panels(C)).bytes;
+}
+
+extern "C" int st3d_gram_mse_forward(const float* feat, const float* target, int B, int Bt, int C, int64_t HW,
+                                     float scale, float* gram, float* dgram, float* loss_out, void* workspace,
+                                     size_t workspace_bytes, int precision, st3d_stream_t stream) {
+    int rc = check_common("gram_forward", feat, B, C, HW, precision);
+    if (rc != ST3D_OK) return rc;
+    if (B == 0) return ST3D_OK;
+    ST3D_REQUIRE(!target || Bt == 1 || Bt == B, "gram_mse_forward: target batch %d is neither 1 nor %d", Bt, B);
+    ST3D_REQUIRE(!target || loss_out, "gram_mse_forward: loss_out is required with a target");
+    ST3D_REQUIRE(workspace, "gram_forward: null workspace");
+    const GramPlan p = gram_plan(workspace, B, C, HW, gram_panels(C));
+    if (workspace_bytes < p.bytes) {
+        st3d_set_error("gram_forward: workspace %zu < required %zu bytes", workspace_bytes, p.bytes);
+        return ST3D_ERR_WORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    rc = gram_partials(feat, p, precision, s);
+    if (rc != ST3D_OK) return rc;
+    const int64_t total = (int64_t)B * C * C;
+    const int grid = (int)std::min<int64_t>(cdiv(total, 256), 148 * 4);
+    k_gram_finalize<<<grid, 256, 0, s>>>(p.partials, p.splits, B, Bt, C, target, scale, gram, dgram, loss_out);
+    ST3D_LAUNCH_OK("k_gram_finalize");
+    return ST3D_OK;
+}
+
+extern "C" int st3d_gram_forward(const float* feat, int B, int C, int64_t HW, float* gram, void* workspace,
+                                 size_t workspace_bytes, int precision, st3d_stream_t stream) {
+    ST3D_REQUIRE(B == 0 || gram, "gram_forward: null output");
+    return st3d_gram_mse_forward(feat, nullptr, B, 1, C, HW, 0.0f, gram, nullptr, nullptr, workspace, workspace_bytes,
+                                 precision, stream);
+}
+
+extern "C" int st3d_gram_backward(const float* feat, const float* dgram, int B, int C, int64_t HW, float grad_scale,
+                                  int accumulate, float* grad_feat, void* workspace, size_t workspace_bytes,
+                                  int precision, st3d_stream_t stream) {
+    int rc = check_common("gram_backward", feat, B, C, HW, precision);
+    if (rc != ST3D_OK) return rc;
+    if (B == 0) return ST3D_OK;
+    ST3D_REQUIRE(dgram && grad_feat && workspace, "gram_backward: null pointer");
+    const GramPlan p = gram_plan(workspace, B, C, HW, gram_panels(C));
+    if (workspace_bytes < p.bytes) {
+        st3d_set_error("gram_backward: workspace %zu < required %zu bytes", workspace_bytes, p.bytes);
+        return ST3D_ERR_WORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    k_gram_symmetrize<<<cdiv((int64_t)B * C * C, 256), 256, 0, s>>>(dgram, B, C, grad_scale, p.sym);
+    ST3D_LAUNCH_OK("k_gram_symmetrize");
+    if (precision == ST3D_GRAM_TF32) return gram_tc_backward(feat, p, accumulate, grad_feat, s);
+    k_gram_bwd_simt<<<dim3(cdiv(HW, kST), cdiv(C, kST), B), 256, 0, s>>>(feat, p.sym, C, HW, accumulate, grad_feat);
+    ST3D_LAUNCH_OK("k_gram_bwd_simt");
+    return ST3D_OK;
+}

@@ -1,0 +1,485 @@
+// gram_tc.cuh -- tcgen05 / TMEM / TMA kernels of the Gram path (sm_100a only).
+//
+//   forward   G_b = F_b F_b^T          (style_transfer.py:31-35)   both operands K-major (HW contiguous)
+//   backward  dF_b = S_b F_b           (autograd of the above)     A = F^T tile (MN-major), B = S (K-major)
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA
+// issuer, warps 2-5 = epilogue (TMEM -> registers -> global).  Operands are fp32 in shared memory,
+// 128-byte swizzled exactly as TMA writes them, consumed by tcgen05.mma kind::tf32; accumulation is
+// fp32 in TMEM.  Every mbarrier wait is bounded: a protocol bug traps instead of hanging the GPU.
+#pragma once
+#include <cuda.h>
+
+#include "gram_common.cuh"
+
+namespace st3d {
+namespace tc {
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    long long start = 0;
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        const long long now = clock64();
+        if (start == 0) start = now;
+        if (now - start > 4000000000ll) __trap();  // ~2 s: protocol error, fail loudly
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "n"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, fp32 operands read as tf32
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive columns: r[j] = TMEM[lane_base + laneid][col + j]
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&r)[32]) {
+    uint32_t* u = reinterpret_cast<uint32_t*>(r);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+          "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+          "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+          "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- descriptors (bit layout: PTX ISA "tcgen05 shared memory / instruction descriptor") ---------------
+// 128-byte swizzled operand tile.  lbo / sbo in bytes.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46) /* sm_100 descriptor version */ |
+           (2ull << 61) /* SWIZZLE_128B */;
+}
+// kind::tf32, fp32 accumulate; a_mn / b_mn = 1 selects the MN-major operand layout
+constexpr uint32_t instr_desc(int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int kThreads = 192;
+constexpr int kScratchFloats = 4 * 32 * 33;  // one padded 32x32 transpose tile per epilogue warp
+
+// =====================================================================================================
+// forward
+// =====================================================================================================
+template <int C>
+struct FwdCfg {
+    static constexpr int M = C == 64 ? 64 : 128;
+    static constexpr int PANELS = C == 256 ? 2 : 1;  // row panels accumulated by one CTA
+    static constexpr int GROUPS = C == 512 ? 4 : 1;  // CTAs per (image, split)
+    static constexpr int NHALF = C == 512 ? 2 : 1;   // an MMA covers at most N = 256 columns
+    static constexpr int NMMA = C / NHALF;
+    static constexpr int TMEM_COLS = C == 64 ? 64 : (C == 128 ? 128 : 512);
+    static constexpr int STAGE_BYTES = C * 128;      // C rows x 32 fp32
+    static constexpr int STAGES = C == 64 ? 16 : (C == 128 ? 10 : (C == 256 ? 6 : 3));
+    static constexpr int BOX_ROWS = C < 256 ? C : 256;
+    static constexpr int BOXES = C / BOX_ROWS;
+    static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + kScratchFloats * 4 + (2 * STAGES + 2) * 8 + 16;
+};
+
+// grid (GROUPS, splits, B).  partials [B][splits][C][C].
+template <int C>
+__global__ void __launch_bounds__(kThreads, 1)
+k_gram_tc_fwd(const __grid_constant__ CUtensorMap map, float* __restrict__ partials, int splits, int64_t k_chunk,
+              int64_t HW) {
+    using Cfg = FwdCfg<C>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* stages = smem;
+    float* scratch = reinterpret_cast<float*>(smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + kScratchFloats);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 1);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + Cfg::STAGES),
+                   tmem_full = smem_u32(bars + 2 * Cfg::STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x, s = blockIdx.y, b = blockIdx.z;
+    const int64_t k0 = (int64_t)s * k_chunk, k1 = min(HW, k0 + k_chunk);
+    const int nkb = (int)((k1 - k0 + 31) / 32);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < Cfg::STAGES; ++i) {
+            mbar_init(full0 + 8 * i, 1);
+            mbar_init(empty0 + 8 * i, 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&map);
+    }
+    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(smem_u32(tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % Cfg::STAGES;
+                const uint32_t ph = (kb / Cfg::STAGES) & 1;
+                mbar_wait(empty0 + 8 * st, ph ^ 1);
+                mbar_arrive_expect_tx(full0 + 8 * st, Cfg::STAGE_BYTES);
+                const uint32_t dst = smem_u32(stages + (size_t)st * Cfg::STAGE_BYTES);
+#pragma unroll
+                for (int bx = 0; bx < Cfg::BOXES; ++bx)
+                    tma_load_2d(dst + bx * Cfg::BOX_ROWS * 128, &map, full0 + 8 * st, (int)(k0 + (int64_t)kb * 32),
+                                b * C + bx * Cfg::BOX_ROWS);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = instr_desc(Cfg::M, Cfg::NMMA, 0, 0);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % Cfg::STAGES;
+                const uint32_t ph = (kb / Cfg::STAGES) & 1;
+                mbar_wait(full0 + 8 * st, ph);
+                tc_fence_after();
+                const uint32_t sbase = smem_u32(stages + (size_t)st * Cfg::STAGE_BYTES);
+#pragma unroll
+                for (int p = 0; p < Cfg::PANELS; ++p) {
+                    const uint32_t row_a = (C == 512 ? g : p) * 128;  // 0 when C <= 128
+#pragma unroll
+                    for (int h = 0; h < Cfg::NHALF; ++h) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t ad = smem_desc(sbase + row_a * 128 + k * 32, 16, 1024);
+                            const uint64_t bd = smem_desc(sbase + h * 256 * 128 + k * 32, 16, 1024);
+                            mma_tf32(tmem_base + p * 256 + h * 256, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        }
+                    }
+                }
+                mma_commit(empty0 + 8 * st);  // frees the smem slot once these MMAs have read it
+            }
+            mma_commit(tmem_full);
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;  // TMEM lane quarter this warp may read
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        float* P = partials + ((int64_t)b * splits + s) * C * C;
+        float* sc = scratch + q * 32 * 33;
+        float r[32];
+#pragma unroll 1
+        for (int p = 0; p < Cfg::PANELS; ++p) {
+            const int panel_row0 = (C == 512 ? g : p) * 128;
+#pragma unroll 1
+            for (int c0 = 0; c0 < C; c0 += 32) {
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p * 256 + c0), r);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sc[lane * 33 + j] = r[j];
+                __syncwarp();
+                // M = 128: TMEM lane = row.  M = 64: rows 16q..16q+15 live in lanes 32q..32q+15.
+                const int rows = Cfg::M == 128 ? 32 : 16;
+                const int row0 = Cfg::M == 128 ? panel_row0 + q * 32 : q * 16;
+                for (int t = 0; t < rows; ++t) P[(int64_t)(row0 + t) * C + c0 + lane] = sc[t * 33 + lane];
+                __syncwarp();
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// =====================================================================================================
+// backward: D[x (128 lanes)][c (C columns)] = sum_j F[j][x] S[c][j]
+// =====================================================================================================
+template <int C>
+struct BwdCfg {
+    static constexpr int NHALF = C == 512 ? 2 : 1;
+    static constexpr int NMMA = C / NHALF;
+    static constexpr int ACC = C <= 256 ? 2 : 1;  // TMEM accumulator buffers (epilogue overlaps the next chunk)
+    static constexpr int TMEM_COLS = C * ACC < 32 ? 32 : C * ACC;  // 128, 256, 512, 512
+    static constexpr int F_BYTES = 4 * 4096;      // four [32 j][32 x] boxes = 128 x's
+    static constexpr int S_BYTES = C * 128;       // [C rows c][32 j]
+    static constexpr int STAGE_BYTES = F_BYTES + S_BYTES;
+    static constexpr int STAGES = C == 64 ? 8 : (C == 128 ? 6 : (C == 256 ? 4 : 2));
+    static constexpr int KB = C / 32;             // k-blocks (32 channels j each) per chunk
+    static constexpr int S_BOX_ROWS = C < 256 ? C : 256;
+    static constexpr int S_BOXES = C / S_BOX_ROWS;
+    static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 2 * ACC) * 8 + 16;
+};
+
+template <int C>
+__global__ void __launch_bounds__(kThreads, 1)
+k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__ CUtensorMap map_s,
+              float* __restrict__ grad_feat, int B, int64_t HW, int accumulate) {
+    using Cfg = BwdCfg<C>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* stages = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 2 * Cfg::ACC);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + Cfg::STAGES),
+                   accf0 = smem_u32(bars + 2 * Cfg::STAGES), acce0 = smem_u32(bars + 2 * Cfg::STAGES + Cfg::ACC);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t chunks = (HW + 127) / 128, items = (int64_t)B * chunks;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < Cfg::STAGES; ++i) {
+            mbar_init(full0 + 8 * i, 1);
+            mbar_init(empty0 + 8 * i, 1);
+        }
+        for (int i = 0; i < Cfg::ACC; ++i) {
+            mbar_init(accf0 + 8 * i, 1);
+            mbar_init(acce0 + 8 * i, 4);  // one arrival per epilogue warp
+        }
+        fence_barrier_init();
+        tma_prefetch_desc(&map_f);
+        tma_prefetch_desc(&map_s);
+    }
+    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(smem_u32(tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+                const int b = (int)(item / chunks);
+                const int x0 = (int)(item % chunks) * 128;
+                for (int kb = 0; kb < Cfg::KB; ++kb, ++it) {
+                    const int st = it % Cfg::STAGES;
+                    const uint32_t ph = (it / Cfg::STAGES) & 1;
+                    mbar_wait(empty0 + 8 * st, ph ^ 1);
+                    mbar_arrive_expect_tx(full0 + 8 * st, Cfg::STAGE_BYTES);
+                    const uint32_t dst = smem_u32(stages + (size_t)st * Cfg::STAGE_BYTES);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        tma_load_2d(dst + i * 4096, &map_f, full0 + 8 * st, x0 + 32 * i, b * C + kb * 32);
+#pragma unroll
+                    for (int bx = 0; bx < Cfg::S_BOXES; ++bx)
+                        tma_load_2d(dst + Cfg::F_BYTES + bx * Cfg::S_BOX_ROWS * 128, &map_s, full0 + 8 * st, kb * 32,
+                                    b * C + bx * Cfg::S_BOX_ROWS);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = instr_desc(128, Cfg::NMMA, 1, 0);  // A = F^T tile: MN-major
+            uint32_t it = 0, li = 0;
+            for (int64_t item = blockIdx.x; item < items; item += gridDim.x, ++li) {
+                const uint32_t a = li % Cfg::ACC, aph = (li / Cfg::ACC) & 1;
+                mbar_wait(acce0 + 8 * a, aph ^ 1);  // epilogue has drained this accumulator
+                tc_fence_after();
+                for (int kb = 0; kb < Cfg::KB; ++kb, ++it) {
+                    const int st = it % Cfg::STAGES;
+                    const uint32_t ph = (it / Cfg::STAGES) & 1;
+                    mbar_wait(full0 + 8 * st, ph);
+                    tc_fence_after();
+                    const uint32_t sF = smem_u32(stages + (size_t)st * Cfg::STAGE_BYTES), sS = sF + Cfg::F_BYTES;
+#pragma unroll
+                    for (int kg = 0; kg < 4; ++kg) {  // 8 channels j per MMA
+                        const uint64_t ad = smem_desc(sF + kg * 1024, 4096, 1024);
+#pragma unroll
+                        for (int h = 0; h < Cfg::NHALF; ++h) {
+                            const uint64_t bd = smem_desc(sS + h * 256 * 128 + kg * 32, 16, 1024);
+                            mma_tf32(tmem_base + a * C + h * 256, ad, bd, idesc, (kb > 0 || kg > 0) ? 1u : 0u);
+                        }
+                    }
+                    mma_commit(empty0 + 8 * st);
+                }
+                mma_commit(accf0 + 8 * a);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        uint32_t li = 0;
+        float r[32];
+        for (int64_t item = blockIdx.x; item < items; item += gridDim.x, ++li) {
+            const uint32_t a = li % Cfg::ACC, aph = (li / Cfg::ACC) & 1;
+            const int b = (int)(item / chunks);
+            const int64_t x = (item % chunks) * 128 + q * 32 + lane;
+            mbar_wait(accf0 + 8 * a, aph);
+            tc_fence_after();
+            float* out = grad_feat + (int64_t)b * C * HW + x;
+#pragma unroll 1
+            for (int c0 = 0; c0 < C; c0 += 32) {
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * C + c0), r);
+                if (x < HW) {
+                    if (accumulate) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) out[(int64_t)(c0 + j) * HW] += r[j];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) out[(int64_t)(c0 + j) * HW] = r[j];
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acce0 + 8 * a);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ---- host side -----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static inline EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// 2D fp32 tensor [rows][cols] (cols contiguous), box [box_rows][32 cols], 128-byte swizzle, zero fill
+static inline int make_map(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        st3d_set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return ST3D_ERR_CUDA;
+    }
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * sizeof(float)};
+    const cuuint32_t box[2] = {32, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        st3d_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu)", (int)r,
+                       (unsigned long long)rows, (unsigned long long)cols);
+        return ST3D_ERR_CUDA;
+    }
+    return ST3D_OK;
+}
+
+template <int C>
+static int launch_fwd(const float* feat, const GramPlan& p, cudaStream_t s) {
+    using Cfg = FwdCfg<C>;
+    CUtensorMap map;
+    int rc = make_map(&map, feat, (uint64_t)p.B * C, (uint64_t)p.HW, Cfg::BOX_ROWS);
+    if (rc != ST3D_OK) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        ST3D_CUDA_OK(cudaFuncSetAttribute(k_gram_tc_fwd<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        attr_done = true;
+    }
+    k_gram_tc_fwd<C><<<dim3(Cfg::GROUPS, p.splits, p.B), kThreads, Cfg::SMEM, s>>>(map, p.partials, p.splits, p.k_chunk,
+                                                                                  p.HW);
+    ST3D_LAUNCH_OK("k_gram_tc_fwd");
+    return ST3D_OK;
+}
+
+template <int C>
+static int launch_bwd(const float* feat, const GramPlan& p, int accumulate, float* grad_feat, cudaStream_t s) {
+    using Cfg = BwdCfg<C>;
+    CUtensorMap map_f, map_s;
+    int rc = make_map(&map_f, feat, (uint64_t)p.B * C, (uint64_t)p.HW, 32);
+    if (rc != ST3D_OK) return rc;
+    rc = make_map(&map_s, p.sym, (uint64_t)p.B * C, (uint64_t)C, Cfg::S_BOX_ROWS);
+    if (rc != ST3D_OK) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        ST3D_CUDA_OK(cudaFuncSetAttribute(k_gram_tc_bwd<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        attr_done = true;
+    }
+    const int64_t items = (int64_t)p.B * ((p.HW + 127) / 128);
+    const int grid = (int)std::min<int64_t>(items, 148);
+    k_gram_tc_bwd<C><<<grid, kThreads, Cfg::SMEM, s>>>(map_f, map_s, grad_feat, p.B, p.HW, accumulate);
+    ST3D_LAUNCH_OK("k_gram_tc_bwd");
+    return ST3D_OK;
+}
+
+}  // namespace tc
+
+static inline bool gram_tc_supported(int C, int64_t HW) {
+    return (C == 64 || C == 128 || C == 256 || C == 512) && HW % 4 == 0 && HW >= 32;
+}
+
+static inline int gram_tc_forward(const float* feat, const GramPlan& p, cudaStream_t s) {
+    switch (p.C) {
+        case 64: return tc::launch_fwd<64>(feat, p, s);
+        case 128: return tc::launch_fwd<128>(feat, p, s);
+        case 256: return tc::launch_fwd<256>(feat, p, s);
+        case 512: return tc::launch_fwd<512>(feat, p, s);
+    }
+    return ST3D_ERR_UNSUPPORTED;
+}
+
+static inline int gram_tc_backward(const float* feat, const GramPlan& p, int accumulate, float* grad_feat,
+                                   cudaStream_t s) {
+    switch (p.C) {
+        case 64: return tc::launch_bwd<64>(feat, p, accumulate, grad_feat, s);
+        case 128: return tc::launch_bwd<128>(feat, p, accumulate, grad_feat, s);
+        case 256: return tc::launch_bwd<256>(feat, p, accumulate, grad_feat, s);
+        case 512: return tc::launch_bwd<512>(feat, p, accumulate, grad_feat, s);
+    }
+    return ST3D_ERR_UNSUPPORTED;
+}
+
+}  // namespace st3d

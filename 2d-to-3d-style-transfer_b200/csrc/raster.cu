@@ -1,0 +1,461 @@
+// raster.cu -- tile-binned multi-view rasterizer with fused texture / shade / blend epilogue.
+//
+// Replaces PyTorch3D's MeshRasterizer.transform, rasterize_meshes
+// (coarse + fine kernels), interpolate_face_attributes, TexturesUV/TexturesVertex.sample_textures,
+// phong_shading with AmbientLights and softmax_rgb_blend as reached from the reference through
+// utils.py:65-77 (render_meshes) / first_approach.py:106-114.  Not a port: one setup pass builds a
+// 48-byte record per (view, face) and exact-size 16x16-pixel tile bins; one fine pass stages each
+// tile's faces in shared memory, tests them with one-rounding fp32 edge functions (bit-identical to
+// oracle/raster_oracle.c) and shades the winning face in the same kernel.
+#include <float.h>
+
+#include <type_traits>
+
+#include "common.cuh"
+#include "shade.cuh"
+
+namespace st3d {
+
+// -------------------------------------------------------------------------------------------------
+// 1. vertex transform (same operation order as oracle_transform_verts)
+// -------------------------------------------------------------------------------------------------
+__global__ void k_transform(const float* __restrict__ verts, const float* __restrict__ R,
+                            const float* __restrict__ T, float k00, float k11, int64_t V,
+                            float4* __restrict__ out4, float* __restrict__ out3) {
+    const int n = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float sR[9], sT[3];
+    if (threadIdx.x < 9) sR[threadIdx.x] = R[n * 9 + threadIdx.x];
+    if (threadIdx.x < 3) sT[threadIdx.x] = T[n * 3 + threadIdx.x];
+    __syncthreads();
+    if (i >= V) return;
+    const float x = verts[3 * i], y = verts[3 * i + 1], z = verts[3 * i + 2];
+    const float xv = fadd(fadd(fadd(fmul(x, sR[0]), fmul(y, sR[3])), fmul(z, sR[6])), sT[0]);
+    const float yv = fadd(fadd(fadd(fmul(x, sR[1]), fmul(y, sR[4])), fmul(z, sR[7])), sT[1]);
+    const float zv = fadd(fadd(fadd(fmul(x, sR[2]), fmul(y, sR[5])), fmul(z, sR[8])), sT[2]);
+    const float xn = fdiv(fmul(xv, k00), zv), yn = fdiv(fmul(yv, k11), zv);
+    const int64_t o = (int64_t)n * V + i;
+    if (out4) out4[o] = make_float4(xn, yn, zv, 0.0f);
+    if (out3) {
+        out3[3 * o] = xn;
+        out3[3 * o + 1] = yn;
+        out3[3 * o + 2] = zv;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// 2. face setup + tile count
+// -------------------------------------------------------------------------------------------------
+// Inclusive range [lo, hi] of NDC-ordered pixel indices j in [0, S1) whose centre c(j) satisfies
+// lo_v <= c(j) <= hi_v, evaluated with exactly the oracle's float comparisons.
+__device__ __forceinline__ void ndc_pixel_range(float lo_v, float hi_v, int S1, int S2, int& jlo, int& jhi) {
+    float range = 2.0f;
+    if (S1 > S2) range = fdiv(fmul((float)S1, range), (float)S2);
+    const float off = range * 0.5f;
+    // estimate j = ((v + off) * S1 - off) / range, then fix up with the exact centre values
+    const float el = ((lo_v + off) * (float)S1 - off) / range;
+    const float eh = ((hi_v + off) * (float)S1 - off) / range;
+    jlo = (int)fminf(fmaxf(ceilf(el), 0.0f), (float)S1);
+    jhi = (int)fminf(fmaxf(floorf(eh), -1.0f), (float)(S1 - 1));
+    while (jlo > 0 && pix_to_ndc(jlo - 1, S1, S2) >= lo_v) --jlo;
+    while (jlo < S1 && pix_to_ndc(jlo, S1, S2) < lo_v) ++jlo;
+    while (jhi < S1 - 1 && pix_to_ndc(jhi + 1, S1, S2) <= hi_v) ++jhi;
+    while (jhi >= 0 && pix_to_ndc(jhi, S1, S2) > hi_v) --jhi;
+}
+
+template <bool GATHER>
+__global__ void k_setup(const float* __restrict__ face_verts, const float4* __restrict__ verts_ndc,
+                        const int32_t* __restrict__ faces, const int64_t* __restrict__ first_idx,
+                        const int64_t* __restrict__ num_faces, int64_t F_per_mesh, int64_t V, int H, int W,
+                        float blur_radius, int cull_backfaces, int TX, int TY, FaceRec* __restrict__ rec,
+                        int* __restrict__ tile_count) {
+    const int n = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t first = first_idx ? first_idx[n] : (int64_t)n * F_per_mesh;
+    const int64_t cnt = num_faces ? num_faces[n] : F_per_mesh;
+    if (i >= cnt) return;
+    const int64_t f = first + i;
+    FaceVerts v;
+    if (GATHER) {
+        const int i0 = faces[3 * i], i1 = faces[3 * i + 1], i2 = faces[3 * i + 2];
+        const float4 p0 = verts_ndc[(int64_t)n * V + i0];
+        const float4 p1 = verts_ndc[(int64_t)n * V + i1];
+        const float4 p2 = verts_ndc[(int64_t)n * V + i2];
+        v = FaceVerts{p0.x, p0.y, p0.z, p1.x, p1.y, p1.z, p2.x, p2.y, p2.z};
+    } else {
+        const float* p = face_verts + 9 * f;
+        v = FaceVerts{p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8]};
+    }
+    const float area = edge_fn(v.x2, v.y2, v.x0, v.y0, v.x1, v.y1);
+    bool valid = fabsf(area) > kEps;                       // also false for NaN
+    if (cull_backfaces && area < 0.0f) valid = false;
+    if (fmaxf(v.z0, fmaxf(v.z1, v.z2)) < 0.0f) valid = false;
+    const float radius = __fsqrt_rn(blur_radius);
+    const float xmin = fsub(fminf(v.x0, fminf(v.x1, v.x2)), radius);
+    const float xmax = fadd(fmaxf(v.x0, fmaxf(v.x1, v.x2)), radius);
+    const float ymin = fsub(fminf(v.y0, fminf(v.y1, v.y2)), radius);
+    const float ymax = fadd(fmaxf(v.y0, fmaxf(v.y1, v.y2)), radius);
+    if (!(isfinite(xmin) && isfinite(xmax) && isfinite(ymin) && isfinite(ymax))) valid = false;
+    int xi0 = 1, xi1 = 0, yi0 = 1, yi1 = 0;
+    if (valid) {
+        int jlo, jhi, klo, khi;
+        ndc_pixel_range(xmin, xmax, W, H, jlo, jhi);
+        ndc_pixel_range(ymin, ymax, H, W, klo, khi);
+        if (jlo <= jhi && klo <= khi) {
+            xi0 = W - 1 - jhi;  // image x runs opposite to NDC x (A.3)
+            xi1 = W - 1 - jlo;
+            yi0 = H - 1 - khi;
+            yi1 = H - 1 - klo;
+        } else {
+            valid = false;
+        }
+    }
+    FaceRec r;
+    r.a = make_float4(v.x0, v.y0, v.z0, v.x1);
+    r.b = make_float4(v.y1, v.z1, v.x2, v.y2);
+    r.c = make_float4(v.z2, area, __int_as_float(xi0 | (xi1 << 16)), __int_as_float(yi0 | (yi1 << 16)));
+    rec[f] = r;
+    if (!valid) return;
+    const int tx0 = xi0 / kTile, tx1 = xi1 / kTile, ty0 = yi0 / kTile, ty1 = yi1 / kTile;
+    for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&tile_count[(n * TY + ty) * TX + tx], 1);
+}
+
+// 3. carve each tile's list out of the pair buffer (order of tiles in the buffer is irrelevant)
+__global__ void k_alloc(const int* __restrict__ tile_count, int* __restrict__ tile_offset, int* __restrict__ hdr,
+                        int NT) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= NT) return;
+    const int c = tile_count[t];
+    tile_offset[t] = c > 0 ? atomicAdd(&hdr[0], c) : 0;
+}
+
+// 4. fill the tile lists with packed face ids
+__global__ void k_fill(const FaceRec* __restrict__ rec, const int64_t* __restrict__ first_idx,
+                       const int64_t* __restrict__ num_faces, int64_t F_per_mesh, int TX, int TY,
+                       const int* __restrict__ tile_offset, int* __restrict__ tile_cursor, int* __restrict__ list,
+                       int64_t capacity, int* __restrict__ hdr) {
+    const int n = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t first = first_idx ? first_idx[n] : (int64_t)n * F_per_mesh;
+    const int64_t cnt = num_faces ? num_faces[n] : F_per_mesh;
+    if (i >= cnt) return;
+    const int64_t f = first + i;
+    const float4 c = rec[f].c;
+    const int xr = __float_as_int(c.z), yr = __float_as_int(c.w);
+    const int xi0 = xr & 0xffff, xi1 = xr >> 16, yi0 = yr & 0xffff, yi1 = yr >> 16;
+    if (xi0 > xi1) return;
+    const int tx0 = xi0 / kTile, tx1 = xi1 / kTile, ty0 = yi0 / kTile, ty1 = yi1 / kTile;
+    for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tx = tx0; tx <= tx1; ++tx) {
+            const int t = (n * TY + ty) * TX + tx;
+            const int64_t slot = (int64_t)tile_offset[t] + atomicAdd(&tile_cursor[t], 1);
+            if (slot < capacity)
+                list[slot] = (int)f;
+            else
+                hdr[1] = 1;
+        }
+}
+
+// -------------------------------------------------------------------------------------------------
+// 5. fine raster (+ fused shade)
+// -------------------------------------------------------------------------------------------------
+constexpr int kChunk = 256;  // faces staged in shared memory per round (one per thread)
+
+struct FragOut {  // MODE 0: _C.rasterize_meshes outputs
+    int64_t* pix_to_face;
+    float* zbuf;
+    float* bary;
+    float* dists;
+};
+
+struct KBest1 {  // K = 1: everything in registers
+    float z = FLT_MAX;
+    int f = 0x7fffffff;
+    float b0, b1, b2, dist;
+    __device__ __forceinline__ void offer(const Hit& h, int face) {
+        if (h.z < z || (h.z == z && face < f)) {
+            z = h.z; f = face; b0 = h.b0; b1 = h.b1; b2 = h.b2; dist = h.dist;
+        }
+    }
+};
+
+template <int K>
+struct KBest {  // ascending (z, face); empty slots hold (FLT_MAX, INT_MAX)
+    float z[K], b0[K], b1[K], b2[K], dist[K];
+    int f[K];
+    __device__ __forceinline__ KBest() {
+#pragma unroll
+        for (int k = 0; k < K; ++k) { z[k] = FLT_MAX; f[k] = 0x7fffffff; b0[k] = b1[k] = b2[k] = dist[k] = -1.0f; }
+    }
+    __device__ __forceinline__ static bool less(float za, int fa, float zb, int fb) {
+        return za < zb || (za == zb && fa < fb);
+    }
+    __device__ __forceinline__ void offer(const Hit& h, int face) {
+        if (!less(h.z, face, z[K - 1], f[K - 1])) return;
+        z[K - 1] = h.z; f[K - 1] = face; b0[K - 1] = h.b0; b1[K - 1] = h.b1; b2[K - 1] = h.b2; dist[K - 1] = h.dist;
+#pragma unroll
+        for (int s = K - 1; s > 0; --s) {
+            if (less(z[s], f[s], z[s - 1], f[s - 1])) {
+                float t;
+                int ti;
+                t = z[s]; z[s] = z[s - 1]; z[s - 1] = t;
+                ti = f[s]; f[s] = f[s - 1]; f[s - 1] = ti;
+                t = b0[s]; b0[s] = b0[s - 1]; b0[s - 1] = t;
+                t = b1[s]; b1[s] = b1[s - 1]; b1[s - 1] = t;
+                t = b2[s]; b2[s] = b2[s - 1]; b2[s - 1] = t;
+                t = dist[s]; dist[s] = dist[s - 1]; dist[s - 1] = t;
+            }
+        }
+    }
+};
+
+// MODE 0: fragments out (K >= 1).  MODE 1: fused shade (K == 1).
+template <int MODE, int K>
+__global__ void __launch_bounds__(256)
+k_fine(const FaceRec* __restrict__ rec, const int* __restrict__ tile_count, const int* __restrict__ tile_offset,
+       const int* __restrict__ list, int64_t capacity, int H, int W, int TX, int TY, float blur_radius, int persp,
+       int clip, FragOut fo, ShadeParams sp) {
+    __shared__ float4 s_e0[kChunk], s_e1[kChunk], s_e2[kChunk];
+    __shared__ int4 s_misc[kChunk];
+
+    const int t = blockIdx.x;
+    const int n = t / (TX * TY);
+    const int ty = (t / TX) % TY, tx = t % TX;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp = 8x4 pixel block; 2 x 4 blocks per tile
+    const int wx0 = tx * kTile + (warp & 1) * 8, wy0 = ty * kTile + (warp >> 1) * 4;
+    const int xi = wx0 + (lane & 7), yi = wy0 + (lane >> 3);
+    const bool active = xi < W && yi < H;
+    const float px = pix_to_ndc(W - 1 - xi, W, H), py = pix_to_ndc(H - 1 - yi, H, W);
+    const bool soft = blur_radius > 0.0f;
+
+    typename std::conditional<K == 1, KBest1, KBest<K>>::type best;
+
+    const int base = tile_offset[t];
+    // on bin overflow (hdr[1] set, results invalid) never read past the pair buffer
+    const int count = (int)max((int64_t)0, min((int64_t)tile_count[t], capacity - base));
+    for (int c0 = 0; c0 < count; c0 += kChunk) {
+        const int nc = min(kChunk, count - c0);
+        __syncthreads();
+        if (threadIdx.x < nc) {
+            const int f = list[base + c0 + threadIdx.x];
+            const FaceRec r = rec[f];
+            const FaceVerts v = unpack(r);
+            // edge i of the barycentric numerators: b0 <- (v1,v2), b1 <- (v2,v0), b2 <- (v0,v1)
+            s_e0[threadIdx.x] = make_float4(v.x1, v.y1, fsub(v.y2, v.y1), fsub(v.x2, v.x1));
+            s_e1[threadIdx.x] = make_float4(v.x2, v.y2, fsub(v.y0, v.y2), fsub(v.x0, v.x2));
+            s_e2[threadIdx.x] = make_float4(v.x0, v.y0, fsub(v.y1, v.y0), fsub(v.x1, v.x0));
+            const int zpos = (v.z0 > 0.0f && v.z1 > 0.0f && v.z2 > 0.0f) ? 1 : 0;
+            s_misc[threadIdx.x] = make_int4(f, __float_as_int(r.c.z), __float_as_int(r.c.w), zpos);
+        }
+        __syncthreads();
+        for (int j = 0; j < nc; ++j) {
+            const int4 m = s_misc[j];
+            const int fx0 = m.y & 0xffff, fx1 = m.y >> 16, fy0 = m.z & 0xffff, fy1 = m.z >> 16;
+            // warp-uniform reject: face's pixel range misses this warp's 8x4 block
+            if (fx1 < wx0 || fx0 > wx0 + 7 || fy1 < wy0 || fy0 > wy0 + 3) continue;
+            const float4 e0 = s_e0[j], e1 = s_e1[j], e2 = s_e2[j];
+            const float w0 = fsub(fmul(fsub(px, e0.x), e0.z), fmul(fsub(py, e0.y), e0.w));
+            const float w1 = fsub(fmul(fsub(px, e1.x), e1.z), fmul(fsub(py, e1.y), e1.w));
+            const float w2 = fsub(fmul(fsub(px, e2.x), e2.z), fmul(fsub(py, e2.y), e2.w));
+            // exact bbox test of the oracle == pixel-range membership
+            bool cand = active && xi >= fx0 && xi <= fx1 && yi >= fy0 && yi <= fy1;
+            // necessary condition for "inside" when all z > 0 and blur == 0: the three edge values
+            // share one strict sign (then every barycentric coordinate can be > 0)
+            if (!soft && m.w)
+                cand = cand && ((w0 > 0.0f && w1 > 0.0f && w2 > 0.0f) || (w0 < 0.0f && w1 < 0.0f && w2 < 0.0f));
+            if (cand) {
+                const FaceRec r = rec[m.x];
+                Hit h;
+                if (eval_face(px, py, unpack(r), r.c.y, blur_radius, persp != 0, clip != 0, h)) best.offer(h, m.x);
+            }
+        }
+    }
+    if (!active) return;
+    const int64_t pix = ((int64_t)n * H + yi) * W + xi;
+    if (MODE == 0) {
+        if constexpr (K == 1) {
+            const bool hit = best.f != 0x7fffffff;
+            fo.pix_to_face[pix] = hit ? best.f : -1;
+            fo.zbuf[pix] = hit ? best.z : -1.0f;
+            fo.dists[pix] = hit ? best.dist : -1.0f;
+            fo.bary[3 * pix] = hit ? best.b0 : -1.0f;
+            fo.bary[3 * pix + 1] = hit ? best.b1 : -1.0f;
+            fo.bary[3 * pix + 2] = hit ? best.b2 : -1.0f;
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const bool hit = best.f[k] != 0x7fffffff;
+                const int64_t o = pix * K + k;
+                fo.pix_to_face[o] = hit ? best.f[k] : -1;
+                fo.zbuf[o] = hit ? best.z[k] : -1.0f;
+                fo.dists[o] = hit ? best.dist[k] : -1.0f;
+                fo.bary[3 * o] = hit ? best.b0[k] : -1.0f;
+                fo.bary[3 * o + 1] = hit ? best.b1[k] : -1.0f;
+                fo.bary[3 * o + 2] = hit ? best.b2[k] : -1.0f;
+            }
+        }
+    } else {
+        if constexpr (K == 1) {
+            const bool hit = best.f != 0x7fffffff;
+            float rgba[4];
+            if (hit) {
+                const int fl = best.f - n * (int)sp.F;
+                float texel[3];
+                sample_texel(sp, fl, best.b0, best.b1, best.b2, texel);
+                blend_k1(sp, texel, best.dist, best.z, rgba);
+            } else {
+                rgba[0] = sp.bg[0]; rgba[1] = sp.bg[1]; rgba[2] = sp.bg[2]; rgba[3] = 0.0f;
+            }
+            sp.pix_to_face[pix] = hit ? best.f : -1;
+            if (sp.out_layout == ST3D_LAYOUT_NHWC_RGBA) {
+                reinterpret_cast<float4*>(sp.out_image)[pix] = make_float4(rgba[0], rgba[1], rgba[2], rgba[3]);
+            } else {
+                const int64_t hw = (int64_t)H * W, o = (int64_t)n * 3 * hw + (int64_t)yi * W + xi;
+                sp.out_image[o] = rgba[0];
+                sp.out_image[o + hw] = rgba[1];
+                sp.out_image[o + 2 * hw] = rgba[2];
+                if (sp.out_mask) sp.out_mask[pix] = rgba[3] > 0.0f ? 1.0f : 0.0f;
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------
+static int run_bins(const RasterWs& ws, const float* face_verts, const int32_t* faces, const int64_t* first_idx,
+                    const int64_t* num_faces, int N, int64_t F_per_mesh, int64_t V, int H, int W, float blur_radius,
+                    int cull_backfaces, bool gather, cudaStream_t s) {
+    ST3D_CUDA_OK(cudaMemsetAsync(ws.hdr, 0, ws.zero_bytes, s));
+    if (F_per_mesh > 0 && N > 0) {
+        dim3 grid(cdiv(F_per_mesh, 256), N);
+        if (gather)
+            k_setup<true><<<grid, 256, 0, s>>>(nullptr, ws.verts_ndc, faces, first_idx, num_faces, F_per_mesh, V, H, W,
+                                               blur_radius, cull_backfaces, ws.TX, ws.TY, ws.rec, ws.tile_count);
+        else
+            k_setup<false><<<grid, 256, 0, s>>>(face_verts, nullptr, nullptr, first_idx, num_faces, F_per_mesh, V, H, W,
+                                                blur_radius, cull_backfaces, ws.TX, ws.TY, ws.rec, ws.tile_count);
+        ST3D_LAUNCH_OK("k_setup");
+        k_alloc<<<cdiv(ws.NT, 256), 256, 0, s>>>(ws.tile_count, ws.tile_offset, ws.hdr, ws.NT);
+        ST3D_LAUNCH_OK("k_alloc");
+        k_fill<<<grid, 256, 0, s>>>(ws.rec, first_idx, num_faces, F_per_mesh, ws.TX, ws.TY, ws.tile_offset,
+                                    ws.tile_cursor, ws.list, ws.capacity, ws.hdr);
+        ST3D_LAUNCH_OK("k_fill");
+    }
+    return ST3D_OK;
+}
+
+}  // namespace st3d
+
+using namespace st3d;
+
+extern "C" size_t st3d_raster_workspace_size(int N, int64_t F_total, int H, int W, int64_t list_capacity) {
+    return raster_ws_layout(nullptr, N, F_total, H, W, list_capacity, 0).total_bytes;
+}
+
+extern "C" size_t st3d_render_workspace_size(int N, int64_t V, int64_t F, int H, int W, int64_t list_capacity) {
+    return raster_ws_layout(nullptr, N, (int64_t)N * F, H, W, list_capacity, (int64_t)N * V).total_bytes;
+}
+
+extern "C" int st3d_transform_verts_forward(const float* verts, const float* R, const float* T, float k00, float k11,
+                                            int N, int64_t V, float* verts_ndc, st3d_stream_t stream) {
+    ST3D_REQUIRE(verts && R && T && verts_ndc, "transform_verts_forward: null pointer");
+    ST3D_REQUIRE(N >= 0 && V >= 0, "transform_verts_forward: negative size");
+    if (N == 0 || V == 0) return ST3D_OK;
+    k_transform<<<dim3(cdiv(V, 256), N), 256, 0, (cudaStream_t)stream>>>(verts, R, T, k00, k11, V, nullptr, verts_ndc);
+    ST3D_LAUNCH_OK("k_transform");
+    return ST3D_OK;
+}
+
+extern "C" int st3d_rasterize_meshes_forward(const float* face_verts, const int64_t* mesh_to_face_first_idx,
+                                             const int64_t* num_faces_per_mesh, int N, int64_t F_total,
+                                             int64_t max_faces_in_mesh, int H, int W, float blur_radius,
+                                             int faces_per_pixel, int bin_size, int max_faces_per_bin,
+                                             int perspective_correct, int clip_barycentric_coords, int cull_backfaces,
+                                             void* workspace, size_t workspace_bytes, int64_t* pix_to_face, float* zbuf,
+                                             float* bary, float* dists, st3d_stream_t stream) {
+    (void)bin_size;
+    (void)max_faces_per_bin;
+    ST3D_REQUIRE(N >= 0 && F_total >= 0 && H > 0 && W > 0, "rasterize_meshes: bad sizes N=%d F=%lld H=%d W=%d", N,
+                 (long long)F_total, H, W);
+    ST3D_REQUIRE(H <= 32768 && W <= 32768, "rasterize_meshes: image side > 32768");
+    ST3D_REQUIRE(F_total < (1ll << 31), "rasterize_meshes: more than 2^31 faces");
+    ST3D_REQUIRE(faces_per_pixel >= 1 && faces_per_pixel <= ST3D_MAX_FACES_PER_PIXEL,
+                 "rasterize_meshes: faces_per_pixel=%d outside [1,%d]", faces_per_pixel, ST3D_MAX_FACES_PER_PIXEL);
+    ST3D_REQUIRE(blur_radius >= 0.0f, "rasterize_meshes: negative blur_radius");
+    ST3D_REQUIRE(pix_to_face && zbuf && bary && dists && workspace, "rasterize_meshes: null pointer");
+    ST3D_REQUIRE(N == 0 || (mesh_to_face_first_idx && num_faces_per_mesh && (face_verts || F_total == 0)),
+                 "rasterize_meshes: null input");
+    if (N == 0) return ST3D_OK;
+    const int64_t cap = ((int64_t)workspace_bytes - (int64_t)raster_ws_layout(nullptr, N, F_total, H, W, 1, 0).total_bytes) /
+                            (int64_t)sizeof(int) - 64;
+    if (cap < 1) {
+        st3d_set_error("rasterize_meshes: workspace of %zu bytes too small", workspace_bytes);
+        return ST3D_ERR_WORKSPACE;
+    }
+    const RasterWs ws = raster_ws_layout(workspace, N, F_total, H, W, cap, 0);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = run_bins(ws, face_verts, nullptr, mesh_to_face_first_idx, num_faces_per_mesh, N, max_faces_in_mesh, 0, H, W,
+                      blur_radius, cull_backfaces, false, s);
+    if (rc != ST3D_OK) return rc;
+    FragOut fo{pix_to_face, zbuf, bary, dists};
+    ShadeParams sp{};
+    const int K = faces_per_pixel;
+#define ST3D_FINE(KK)                                                                                            \
+    k_fine<0, KK><<<ws.NT, 256, 0, s>>>(ws.rec, ws.tile_count, ws.tile_offset, ws.list, ws.capacity, H, W, ws.TX,  \
+                                        ws.TY, blur_radius, perspective_correct, clip_barycentric_coords, fo, sp)
+    if (K == 1) ST3D_FINE(1);
+    else if (K == 2) ST3D_FINE(2);
+    else if (K <= 4) {
+        // K in {3,4}: run with 4 slots into a temp layout is not possible without scratch; instantiate exactly
+        if (K == 3) ST3D_FINE(3); else ST3D_FINE(4);
+    } else if (K == 5) ST3D_FINE(5);
+    else if (K == 6) ST3D_FINE(6);
+    else if (K == 7) ST3D_FINE(7);
+    else ST3D_FINE(8);
+#undef ST3D_FINE
+    ST3D_LAUNCH_OK("k_fine");
+    return ST3D_OK;
+}
+
+extern "C" int st3d_render_forward(const st3d_render_args* a, st3d_stream_t stream) {
+    ST3D_REQUIRE(a, "render_forward: null args");
+    ST3D_REQUIRE(a->N >= 0 && a->V > 0 && a->F >= 0 && a->H > 0 && a->W > 0, "render_forward: bad sizes");
+    ST3D_REQUIRE(a->H <= 32768 && a->W <= 32768, "render_forward: image side > 32768");
+    ST3D_REQUIRE((int64_t)a->N * a->F < (1ll << 31), "render_forward: N*F >= 2^31");
+    ST3D_REQUIRE(a->verts && a->faces && a->R && a->T, "render_forward: null mesh/camera pointer");
+    ST3D_REQUIRE(a->out_image && a->pix_to_face && a->workspace, "render_forward: null output/workspace");
+    ST3D_REQUIRE(a->blur_radius >= 0.0f && a->sigma > 0.0f && a->gamma > 0.0f, "render_forward: bad blur/sigma/gamma");
+    ST3D_REQUIRE(a->zfar > a->znear, "render_forward: zfar <= znear");
+    if (a->tex_mode == ST3D_TEX_UV)
+        ST3D_REQUIRE(a->face_uvs && a->texture && a->Ht > 0 && a->Wt > 0, "render_forward: UV texture inputs missing");
+    else if (a->tex_mode == ST3D_TEX_VERTEX)
+        ST3D_REQUIRE(a->verts_rgb, "render_forward: verts_rgb missing");
+    else
+        ST3D_REQUIRE(false, "render_forward: unknown tex_mode %d", a->tex_mode);
+    ST3D_REQUIRE(a->out_layout == ST3D_LAYOUT_NHWC_RGBA || a->out_layout == ST3D_LAYOUT_PLANAR,
+                 "render_forward: unknown out_layout %d", a->out_layout);
+    const size_t need = st3d_render_workspace_size(a->N, a->V, a->F, a->H, a->W, a->list_capacity);
+    if (a->workspace_bytes < need) {
+        st3d_set_error("render_forward: workspace %zu < required %zu bytes", a->workspace_bytes, need);
+        return ST3D_ERR_WORKSPACE;
+    }
+    if (a->N == 0) return ST3D_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const RasterWs ws = raster_ws_layout(a->workspace, a->N, (int64_t)a->N * a->F, a->H, a->W, a->list_capacity,
+                                         (int64_t)a->N * a->V);
+    k_transform<<<dim3(cdiv(a->V, 256), a->N), 256, 0, s>>>(a->verts, a->R, a->T, a->k00, a->k11, a->V, ws.verts_ndc,
+                                                            nullptr);
+    ST3D_LAUNCH_OK("k_transform");
+    int rc = run_bins(ws, nullptr, a->faces, nullptr, nullptr, a->N, a->F, a->V, a->H, a->W, a->blur_radius,
+                      a->cull_backfaces, true, s);
+    if (rc != ST3D_OK) return rc;
+    const ShadeParams sp = make_shade_params(*a);
+    FragOut fo{};
+    k_fine<1, 1><<<ws.NT, 256, 0, s>>>(ws.rec, ws.tile_count, ws.tile_offset, ws.list, ws.capacity, a->H, a->W, ws.TX,
+                                       ws.TY, a->blur_radius, 1, a->blur_radius > 0.0f ? 1 : 0, fo, sp);
+    ST3D_LAUNCH_OK("k_fine");
+    return ST3D_OK;
+}

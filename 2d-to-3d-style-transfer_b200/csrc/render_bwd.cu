@@ -1,0 +1,207 @@
+// render_bwd.cu -- fused backward of st3d_render_forward.
+//
+// Replaces the autograd chain the reference triggers with loss.backward() (first_approach.py:211 /
+// second_approach.py:188): softmax_rgb_blend backward -> shading ->
+// grid_sample backward (bilinear scatter into the texture) -> interpolate_face_attributes backward
+// -> rasterize_meshes_backward -> verts[faces] gather backward -> camera transform backward.
+// One pass per pixel; barycentrics are recomputed from the per-face records the forward pass left
+// in the workspace (same one-rounding arithmetic, so the texel footprint is identical); vertex
+// gradients are summed across the lanes of a warp that hit the same face before any atomic.
+#include "common.cuh"
+#include "face_grad.cuh"
+#include "shade.cuh"
+
+namespace st3d {
+
+template <int TEX_MODE, bool NEED_GEOM>
+__global__ void __launch_bounds__(256)
+k_render_bwd(const FaceRec* __restrict__ rec, const float* __restrict__ grad_image, int N, int H, int W, int TX,
+             int TY, int clip, ShadeParams sp, float* __restrict__ grad_texture, float* __restrict__ grad_ndc,
+             float* __restrict__ grad_verts_rgb) {
+    const int t = blockIdx.x;
+    const int n = t / (TX * TY);
+    const int ty = (t / TX) % TY, tx = t % TX;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int xi = tx * kTile + (warp & 1) * 8 + (lane & 7), yi = ty * kTile + (warp >> 1) * 4 + (lane >> 3);
+    const bool active = xi < W && yi < H;
+    const int64_t pix = ((int64_t)n * H + yi) * W + xi;
+    const int f = active ? sp.pix_to_face[pix] : -1;
+    const bool hit = f >= 0;
+    if (!__any_sync(0xffffffffu, hit)) return;  // warp-uniform: nothing covered in this 8x4 block
+
+    float gv[9];    // d loss / d NDC face verts
+    float gcol[9];  // d loss / d vertex colours of the face (vertex-colour mode)
+#pragma unroll
+    for (int i = 0; i < 9; ++i) gv[i] = gcol[i] = 0.0f;
+    const int fl = hit ? f - n * (int)sp.F : 0;
+
+    if (hit) {
+        const float px = pix_to_ndc(W - 1 - xi, W, H), py = pix_to_ndc(H - 1 - yi, H, W);
+        const FaceVerts v = unpack(rec[f]);
+        float b0, b1, b2, pz, dist;
+        face_recompute(px, py, v, true, clip != 0, b0, b1, b2, pz, dist);
+
+        // upstream gradient
+        float g_rgb[3], g_alpha = 0.0f;
+        if (sp.out_layout == ST3D_LAYOUT_NHWC_RGBA) {
+            const float4 g = reinterpret_cast<const float4*>(grad_image)[pix];
+            g_rgb[0] = g.x; g_rgb[1] = g.y; g_rgb[2] = g.z; g_alpha = g.w;
+        } else {
+            const int64_t hw = (int64_t)H * W, o = (int64_t)n * 3 * hw + (int64_t)yi * W + xi;
+            g_rgb[0] = grad_image[o]; g_rgb[1] = grad_image[o + hw]; g_rgb[2] = grad_image[o + 2 * hw];
+        }
+
+        // forward recompute of texel / blend
+        float texel[3];
+        TexTaps tp{};
+        float t00[3], t01[3], t10[3], t11[3];
+        float2 uv0, uv1, uv2;
+        int vi0 = 0, vi1 = 0, vi2 = 0;
+        if (TEX_MODE == ST3D_TEX_UV) {
+            const float2* fuv = reinterpret_cast<const float2*>(sp.face_uvs) + 3 * (int64_t)fl;
+            uv0 = __ldg(fuv); uv1 = __ldg(fuv + 1); uv2 = __ldg(fuv + 2);
+            const float u = b0 * uv0.x + b1 * uv1.x + b2 * uv2.x;
+            const float vv = b0 * uv0.y + b1 * uv1.y + b2 * uv2.y;
+            tp = tex_taps(u, vv, sp.Ht, sp.Wt);
+            const bool x1ok = tp.x1 < sp.Wt, y1ok = tp.y1 < sp.Ht;
+            const float* p00 = sp.texture + 3 * ((int64_t)tp.y0 * sp.Wt + tp.x0);
+            const float* p10 = p00 + 3 * (int64_t)sp.Wt;
+            const float wx0 = 1.0f - tp.wx1, wy0 = 1.0f - tp.wy1;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                t00[c] = __ldg(p00 + c);
+                t01[c] = x1ok ? __ldg(p00 + 3 + c) : 0.0f;
+                t10[c] = y1ok ? __ldg(p10 + c) : 0.0f;
+                t11[c] = (x1ok && y1ok) ? __ldg(p10 + 3 + c) : 0.0f;
+                texel[c] = t00[c] * (wx0 * wy0) + t01[c] * (tp.wx1 * wy0) + t10[c] * (wx0 * tp.wy1) +
+                           t11[c] * (tp.wx1 * tp.wy1);
+            }
+        } else {
+            const int32_t* fi = sp.faces + 3 * (int64_t)fl;
+            vi0 = __ldg(fi); vi1 = __ldg(fi + 1); vi2 = __ldg(fi + 2);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                t00[c] = __ldg(sp.verts_rgb + 3 * (int64_t)vi0 + c);
+                t01[c] = __ldg(sp.verts_rgb + 3 * (int64_t)vi1 + c);
+                t10[c] = __ldg(sp.verts_rgb + 3 * (int64_t)vi2 + c);
+                texel[c] = b0 * t00[c] + b1 * t01[c] + b2 * t10[c];
+            }
+        }
+        const BlendK1 bl = blend_terms(sp, dist, pz);
+        float g_w = 0.0f, g_delta = 0.0f, g_texel[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float color = sp.ambient[c] * texel[c];
+            const float rgb = (bl.w * color + bl.delta * sp.bg[c]) / bl.denom;
+            g_w += g_rgb[c] * (color - rgb) / bl.denom;
+            g_delta += g_rgb[c] * (sp.bg[c] - rgb) / bl.denom;
+            g_texel[c] = g_rgb[c] * (bl.w / bl.denom) * sp.ambient[c];
+        }
+        // w = prob * e ; alpha = prob
+        const float e = bl.prob > 0.0f ? bl.w / bl.prob : 0.0f;
+        const float g_prob = g_w * e + g_alpha;
+        const float g_dist = g_prob * (-bl.prob * (1.0f - bl.prob) / sp.sigma);
+        const float g_zinv = g_w * bl.dw_dzinv + g_delta * bl.ddelta_dzinv;
+        const float g_pz = -g_zinv / (sp.zfar - sp.znear);
+
+        float gb0, gb1, gb2;
+        if (TEX_MODE == ST3D_TEX_UV) {
+            const float wx0 = 1.0f - tp.wx1, wy0 = 1.0f - tp.wy1;
+            float g_ix = 0.0f, g_iy = 0.0f;
+            const bool x1ok = tp.x1 < sp.Wt, y1ok = tp.y1 < sp.Ht;
+            float* q00 = grad_texture ? grad_texture + 3 * ((int64_t)tp.y0 * sp.Wt + tp.x0) : nullptr;
+            float* q10 = q00 ? q00 + 3 * (int64_t)sp.Wt : nullptr;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float g = g_texel[c];
+                g_ix += g * ((t01[c] - t00[c]) * wy0 + (t11[c] - t10[c]) * tp.wy1);
+                g_iy += g * ((t10[c] - t00[c]) * wx0 + (t11[c] - t01[c]) * tp.wx1);
+                if (q00 && g != 0.0f) {
+                    atomicAdd(q00 + c, g * (wx0 * wy0));
+                    if (x1ok) atomicAdd(q00 + 3 + c, g * (tp.wx1 * wy0));
+                    if (y1ok) atomicAdd(q10 + c, g * (wx0 * tp.wy1));
+                    if (x1ok && y1ok) atomicAdd(q10 + 3 + c, g * (tp.wx1 * tp.wy1));
+                }
+            }
+            const float g_u = g_ix * tp.gx, g_v = g_iy * tp.gy;
+            gb0 = g_u * uv0.x + g_v * uv0.y;
+            gb1 = g_u * uv1.x + g_v * uv1.y;
+            gb2 = g_u * uv2.x + g_v * uv2.y;
+        } else {
+            gb0 = gb1 = gb2 = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                gb0 += g_texel[c] * t00[c];
+                gb1 += g_texel[c] * t01[c];
+                gb2 += g_texel[c] * t10[c];
+                gcol[c] = b0 * g_texel[c];
+                gcol[3 + c] = b1 * g_texel[c];
+                gcol[6 + c] = b2 * g_texel[c];
+            }
+        }
+        if (NEED_GEOM) {
+            const FaceGrad fg = face_backward(px, py, v, true, clip != 0, gb0, gb1, gb2, g_pz, g_dist);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) gv[i] = fg.g[i];
+        }
+    }
+
+    if (NEED_GEOM) {
+        // per-face accumulation: lanes that hit the same face are summed before the atomics
+        const int32_t* faces = sp.faces;
+        const int64_t nV = (int64_t)n * sp.V;
+        warp_aggregate_add<9>(hit, fl, gv, [&](int key, int i) {
+            const int vert = __ldg(faces + 3 * (int64_t)key + i / 3);
+            return grad_ndc + 3 * (nV + vert) + i % 3;
+        });
+    }
+    if (TEX_MODE == ST3D_TEX_VERTEX && grad_verts_rgb) {
+        const int32_t* faces = sp.faces;
+        warp_aggregate_add<9>(hit, fl, gcol, [&](int key, int i) {
+            const int vert = __ldg(faces + 3 * (int64_t)key + i / 3);
+            return grad_verts_rgb + 3 * (int64_t)vert + i % 3;
+        });
+    }
+}
+
+}  // namespace st3d
+
+using namespace st3d;
+
+extern "C" int st3d_render_backward(const st3d_render_args* a, const float* grad_image, float* grad_texture,
+                                    float* grad_verts, float* grad_verts_rgb, st3d_stream_t stream) {
+    ST3D_REQUIRE(a && grad_image, "render_backward: null args");
+    ST3D_REQUIRE(a->workspace && a->pix_to_face, "render_backward: forward state missing");
+    ST3D_REQUIRE(a->tex_mode == ST3D_TEX_UV || a->tex_mode == ST3D_TEX_VERTEX, "render_backward: unknown tex_mode");
+    const size_t need = st3d_render_workspace_size(a->N, a->V, a->F, a->H, a->W, a->list_capacity);
+    if (a->workspace_bytes < need) {
+        st3d_set_error("render_backward: workspace %zu < required %zu bytes", a->workspace_bytes, need);
+        return ST3D_ERR_WORKSPACE;
+    }
+    if (a->N == 0 || a->F == 0) return ST3D_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const RasterWs ws = raster_ws_layout(a->workspace, a->N, (int64_t)a->N * a->F, a->H, a->W, a->list_capacity,
+                                         (int64_t)a->N * a->V);
+    const ShadeParams sp = make_shade_params(*a);
+    const int clip = a->blur_radius > 0.0f ? 1 : 0;
+    const bool geom = grad_verts != nullptr;
+    if (geom) ST3D_CUDA_OK(cudaMemsetAsync(ws.grad_ndc, 0, (size_t)a->N * a->V * 3 * sizeof(float), s));
+    float* g_tex = a->tex_mode == ST3D_TEX_UV ? grad_texture : nullptr;
+    float* g_rgb = a->tex_mode == ST3D_TEX_VERTEX ? grad_verts_rgb : nullptr;
+#define ST3D_BWD(MODE, GEOM)                                                                                   \
+    k_render_bwd<MODE, GEOM><<<ws.NT, 256, 0, s>>>(ws.rec, grad_image, a->N, a->H, a->W, ws.TX, ws.TY, clip, sp, \
+                                                   g_tex, ws.grad_ndc, g_rgb)
+    if (a->tex_mode == ST3D_TEX_UV) {
+        if (geom) ST3D_BWD(ST3D_TEX_UV, true); else ST3D_BWD(ST3D_TEX_UV, false);
+    } else {
+        if (geom) ST3D_BWD(ST3D_TEX_VERTEX, true); else ST3D_BWD(ST3D_TEX_VERTEX, false);
+    }
+#undef ST3D_BWD
+    ST3D_LAUNCH_OK("k_render_bwd");
+    if (geom) {
+        const int rc = st3d_transform_verts_backward(a->verts, a->R, a->T, a->k00, a->k11, a->N, a->V, ws.grad_ndc,
+                                                     grad_verts, stream);
+        if (rc != ST3D_OK) return rc;
+    }
+    return ST3D_OK;
+}

@@ -1,0 +1,380 @@
+"""Thin tensor-level wrappers over the libst3d C ABI (include/st3d.h).
+
+Every function takes CUDA fp32 tensors, passes raw device pointers plus the current torch stream
+and raises on a non-zero return code.  Nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+
+from ._lib import RenderArgs, St3dError, check, lib
+
+TEX_UV, TEX_VERTEX = 0, 1
+LAYOUT_NHWC_RGBA, LAYOUT_PLANAR = 0, 1
+MAX_FACES_PER_PIXEL = 8
+WS_HEADER_INTS = 16
+
+
+def _p(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _cuda_f32(name: str, t: torch.Tensor, *shape_tail):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise St3dError(f"{name}: expected a CUDA tensor (st3d has no CPU path; the CPU oracle is test-only)")
+    if t.dtype != torch.float32:
+        raise ValueError(f"{name}: expected float32, got {t.dtype}")
+    if shape_tail and tuple(t.shape[-len(shape_tail):]) != tuple(shape_tail):
+        raise ValueError(f"{name}: expected trailing shape {shape_tail}, got {tuple(t.shape)}")
+    return t.contiguous()
+
+
+def _cuda_int(name: str, t: torch.Tensor, dtype):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise St3dError(f"{name}: expected a CUDA tensor (st3d has no CPU path)")
+    return t.to(dtype).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# deferred bin-overflow checks (the library never synchronises; see st3d.h workspace header)
+# ------------------------------------------------------------------------------------------------
+_pending: list = []
+_capacity_hint: dict = {}
+
+
+def _watch_header(ws: torch.Tensor, key) -> None:
+    host = torch.empty(WS_HEADER_INTS, dtype=torch.int32, pin_memory=True)
+    host.copy_(ws[: WS_HEADER_INTS * 4].view(torch.int32), non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    _pending.append((ev, host, key))
+
+
+def poll_overflow(block: bool = False) -> None:
+    """Raise if an earlier raster call overflowed its tile-bin pair buffer."""
+    keep = []
+    for ev, host, key in _pending:
+        if block:
+            ev.synchronize()
+        if ev.query():
+            needed, overflow = int(host[0]), int(host[1])
+            _capacity_hint[key] = max(_capacity_hint.get(key, 0), needed)
+            if overflow:
+                _pending.clear()
+                raise St3dError(f"tile bins overflowed: {needed} (face,tile) pairs needed; results of that call are "
+                                "invalid. Re-run: the capacity hint has been raised.")
+        else:
+            keep.append((ev, host, key))
+    _pending[:] = keep
+
+
+def _capacity(key, total_faces: int) -> int:
+    hint = _capacity_hint.get(key)
+    if hint is None:
+        return 8 * total_faces + 4096
+    return max(2 * hint, total_faces) + 4096
+
+
+# ------------------------------------------------------------------------------------------------
+# operator boundary (mirrors pytorch3d._C)
+# ------------------------------------------------------------------------------------------------
+def transform_verts(verts, R, T, k00: float, k11: float):
+    verts = _cuda_f32("verts", verts, 3)
+    R = _cuda_f32("R", R, 3, 3).reshape(-1, 3, 3)
+    T = _cuda_f32("T", T, 3).reshape(-1, 3)
+    N, V = R.shape[0], verts.shape[0]
+    out = torch.empty((N, V, 3), device=verts.device, dtype=torch.float32)
+    check(lib().st3d_transform_verts_forward(_p(verts), _p(R), _p(T), k00, k11, N, V, _p(out), _stream()),
+          "st3d_transform_verts_forward")
+    return out
+
+
+def transform_verts_backward(verts, R, T, k00, k11, grad_ndc):
+    verts = _cuda_f32("verts", verts, 3)
+    R = _cuda_f32("R", R, 3, 3).reshape(-1, 3, 3)
+    T = _cuda_f32("T", T, 3).reshape(-1, 3)
+    grad_ndc = _cuda_f32("grad_ndc", grad_ndc, 3)
+    g = torch.zeros_like(verts)
+    check(lib().st3d_transform_verts_backward(_p(verts), _p(R), _p(T), k00, k11, R.shape[0], verts.shape[0],
+                                              _p(grad_ndc), _p(g), _stream()), "st3d_transform_verts_backward")
+    return g
+
+
+def rasterize_meshes(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, image_size, blur_radius=0.0,
+                     faces_per_pixel=1, bin_size=0, max_faces_per_bin=0, perspective_correct=False,
+                     clip_barycentric_coords=False, cull_backfaces=False):
+    """Signature of pytorch3d._C.rasterize_meshes.  Returns (pix_to_face i64, zbuf, bary, dists)."""
+    poll_overflow()
+    face_verts = _cuda_f32("face_verts", face_verts, 3, 3)
+    first = _cuda_int("mesh_to_face_first_idx", mesh_to_face_first_idx, torch.int64)
+    num = _cuda_int("num_faces_per_mesh", num_faces_per_mesh, torch.int64)
+    H, W = (image_size, image_size) if isinstance(image_size, int) else tuple(image_size)
+    N, Ft, K = first.numel(), face_verts.shape[0], int(faces_per_pixel)
+    if num.numel() != N:
+        raise ValueError("mesh_to_face_first_idx and num_faces_per_mesh differ in length")
+    dev = face_verts.device
+    p2f = torch.empty((N, H, W, K), device=dev, dtype=torch.int64)
+    zbuf = torch.empty((N, H, W, K), device=dev, dtype=torch.float32)
+    bary = torch.empty((N, H, W, K, 3), device=dev, dtype=torch.float32)
+    dists = torch.empty((N, H, W, K), device=dev, dtype=torch.float32)
+    if N == 0:
+        return p2f, zbuf, bary, dists
+    max_f = int(num.max().item()) if N > 1 else Ft
+    key = ("raster", N, Ft, H, W)
+    nbytes = lib().st3d_raster_workspace_size(N, Ft, H, W, _capacity(key, Ft))
+    ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    check(lib().st3d_rasterize_meshes_forward(_p(face_verts), _p(first), _p(num), N, Ft, max_f, H, W, float(blur_radius),
+                                              K, int(bin_size or 0), int(max_faces_per_bin or 0), int(perspective_correct),
+                                              int(clip_barycentric_coords), int(cull_backfaces), _p(ws), nbytes,
+                                              _p(p2f), _p(zbuf), _p(bary), _p(dists), _stream()),
+          "st3d_rasterize_meshes_forward")
+    _watch_header(ws, key)
+    return p2f, zbuf, bary, dists
+
+
+def rasterize_meshes_backward(face_verts, pix_to_face, grad_zbuf, grad_bary, grad_dists, perspective_correct,
+                              clip_barycentric_coords):
+    face_verts = _cuda_f32("face_verts", face_verts, 3, 3)
+    p2f = _cuda_int("pix_to_face", pix_to_face, torch.int64)
+    N, H, W, K = p2f.shape
+    gz = _cuda_f32("grad_zbuf", grad_zbuf)
+    gb = _cuda_f32("grad_bary", grad_bary, 3)
+    gd = _cuda_f32("grad_dists", grad_dists)
+    out = torch.zeros_like(face_verts)
+    check(lib().st3d_rasterize_meshes_backward(_p(face_verts), _p(p2f), _p(gz), _p(gb), _p(gd), N, H, W, K,
+                                               face_verts.shape[0], int(perspective_correct),
+                                               int(clip_barycentric_coords), _p(out), _stream()),
+          "st3d_rasterize_meshes_backward")
+    return out
+
+
+def interp_face_attrs_forward(pix_to_face, bary, face_attrs):
+    p2f = _cuda_int("pix_to_face", pix_to_face, torch.int64).reshape(-1)
+    bary = _cuda_f32("bary", bary, 3).reshape(-1, 3)
+    fa = _cuda_f32("face_attrs", face_attrs)
+    if fa.dim() != 3 or fa.shape[1] != 3:
+        raise ValueError("face_attrs must be (F,3,D)")
+    P, F, D = p2f.numel(), fa.shape[0], fa.shape[2]
+    out = torch.empty((P, D), device=fa.device, dtype=torch.float32)
+    check(lib().st3d_interp_face_attrs_forward(_p(p2f), _p(bary), _p(fa), P, F, D, _p(out), _stream()),
+          "st3d_interp_face_attrs_forward")
+    return out
+
+
+def interp_face_attrs_backward(pix_to_face, bary, face_attrs, grad_out):
+    p2f = _cuda_int("pix_to_face", pix_to_face, torch.int64).reshape(-1)
+    bary = _cuda_f32("bary", bary, 3).reshape(-1, 3)
+    fa = _cuda_f32("face_attrs", face_attrs)
+    go = _cuda_f32("grad_out", grad_out).reshape(p2f.numel(), -1)
+    P, F, D = p2f.numel(), fa.shape[0], fa.shape[2]
+    g_bary = torch.empty((P, 3), device=fa.device, dtype=torch.float32)
+    g_attrs = torch.zeros_like(fa)
+    check(lib().st3d_interp_face_attrs_backward(_p(p2f), _p(bary), _p(fa), _p(go), P, F, D, _p(g_bary), _p(g_attrs),
+                                                _stream()), "st3d_interp_face_attrs_backward")
+    return g_bary, g_attrs
+
+
+# ------------------------------------------------------------------------------------------------
+# fused multi-view renderer
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class RenderSpec:
+    """Non-tensor settings of one fused render call (cameras' fov folded into k00/k11)."""
+    image_size: tuple
+    k00: float
+    k11: float
+    znear: float = 1.0
+    zfar: float = 100.0
+    blur_radius: float = 0.0
+    cull_backfaces: bool = False
+    ambient: tuple = (1.0, 1.0, 1.0)
+    background: tuple = (1.0, 1.0, 1.0)
+    sigma: float = 1e-4
+    gamma: float = 1e-4
+    layout: int = LAYOUT_NHWC_RGBA
+
+
+@dataclass
+class RenderState:
+    """Everything backward needs; tensors are kept alive here."""
+    args: RenderArgs
+    keep: list = field(default_factory=list)
+    workspace: Optional[torch.Tensor] = None
+
+
+def render_forward(spec: RenderSpec, verts, faces, R, T, *, face_uvs=None, texture=None, verts_rgb=None):
+    """One launch sequence for N views of one mesh.  Returns (image, mask|None, pix_to_face i32, state)."""
+    poll_overflow()
+    verts = _cuda_f32("verts", verts, 3)
+    faces = _cuda_int("faces", faces, torch.int32)
+    R = _cuda_f32("R", R, 3, 3).reshape(-1, 3, 3)
+    T = _cuda_f32("T", T, 3).reshape(-1, 3)
+    if R.shape[0] != T.shape[0]:
+        raise ValueError("R and T describe different numbers of cameras")
+    if faces.dim() != 2 or faces.shape[1] != 3:
+        raise ValueError("faces must be (F,3)")
+    N, V, F = R.shape[0], verts.shape[0], faces.shape[0]
+    H, W = spec.image_size
+    dev = verts.device
+    a = RenderArgs()
+    a.verts, a.faces, a.V, a.F = _p(verts), _p(faces), V, F
+    a.R, a.T, a.N = _p(R), _p(T), N
+    a.k00, a.k11, a.znear, a.zfar = spec.k00, spec.k11, spec.znear, spec.zfar
+    a.H, a.W, a.blur_radius, a.cull_backfaces = H, W, spec.blur_radius, int(spec.cull_backfaces)
+    keep = [verts, faces, R, T]
+    if texture is not None:
+        texture = _cuda_f32("texture", texture, 3)
+        texture = texture.reshape(texture.shape[-3], texture.shape[-2], 3)
+        face_uvs = _cuda_f32("face_uvs", face_uvs, 3, 2)
+        if face_uvs.shape[0] != F:
+            raise ValueError("face_uvs must be (F,3,2)")
+        a.tex_mode, a.face_uvs, a.texture = TEX_UV, _p(face_uvs), _p(texture)
+        a.Ht, a.Wt = texture.shape[0], texture.shape[1]
+        keep += [texture, face_uvs]
+    elif verts_rgb is not None:
+        verts_rgb = _cuda_f32("verts_rgb", verts_rgb, 3)
+        if verts_rgb.shape[0] != V:
+            raise ValueError("verts_rgb must be (V,3)")
+        a.tex_mode, a.verts_rgb = TEX_VERTEX, _p(verts_rgb)
+        keep += [verts_rgb]
+    else:
+        raise ValueError("render_forward needs either texture+face_uvs or verts_rgb")
+    a.ambient = (ctypes.c_float * 3)(*spec.ambient)
+    a.background = (ctypes.c_float * 3)(*spec.background)
+    a.sigma, a.gamma, a.out_layout = spec.sigma, spec.gamma, spec.layout
+    if spec.layout == LAYOUT_NHWC_RGBA:
+        image = torch.empty((N, H, W, 4), device=dev, dtype=torch.float32)
+        mask = None
+    else:
+        image = torch.empty((N, 3, H, W), device=dev, dtype=torch.float32)
+        mask = torch.empty((N, 1, H, W), device=dev, dtype=torch.float32)
+    p2f = torch.empty((N, H, W), device=dev, dtype=torch.int32)
+    a.out_image, a.out_mask, a.pix_to_face = _p(image), _p(mask), _p(p2f)
+    key = ("render", N, F, H, W)
+    cap = _capacity(key, N * F)
+    nbytes = lib().st3d_render_workspace_size(N, V, F, H, W, cap)
+    ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    a.workspace, a.workspace_bytes, a.list_capacity = _p(ws), nbytes, cap
+    check(lib().st3d_render_forward(ctypes.byref(a), _stream()), "st3d_render_forward")
+    if N > 0:
+        _watch_header(ws, key)
+    return image, mask, p2f, RenderState(args=a, keep=keep + [image, mask, p2f], workspace=ws)
+
+
+def render_backward(state: RenderState, grad_image, need_texture=True, need_verts=False, need_verts_rgb=False):
+    """Returns (grad_texture|None, grad_verts|None, grad_verts_rgb|None)."""
+    a = state.args
+    grad_image = _cuda_f32("grad_image", grad_image)
+    dev = grad_image.device
+    g_tex = torch.zeros((a.Ht, a.Wt, 3), device=dev, dtype=torch.float32) if (need_texture and a.tex_mode == TEX_UV) else None
+    g_verts = torch.zeros((a.V, 3), device=dev, dtype=torch.float32) if need_verts else None
+    g_rgb = torch.zeros((a.V, 3), device=dev, dtype=torch.float32) if (need_verts_rgb and a.tex_mode == TEX_VERTEX) else None
+    check(lib().st3d_render_backward(ctypes.byref(a), _p(grad_image), _p(g_tex), _p(g_verts), _p(g_rgb), _stream()),
+          "st3d_render_backward")
+    return g_tex, g_verts, g_rgb
+
+
+# ------------------------------------------------------------------------------------------------
+# Gram / MSE losses (style_transfer.py:31-35, losses.py:31-39, losses.py:71-75)
+# ------------------------------------------------------------------------------------------------
+GRAM_TF32, GRAM_FP32 = 0, 1
+_PRECISIONS = {"tf32": GRAM_TF32, "fp32": GRAM_FP32, GRAM_TF32: GRAM_TF32, GRAM_FP32: GRAM_FP32}
+
+
+def gram_tc_supported(C: int, HW: int) -> bool:
+    """Shapes the tcgen05 (kind::tf32) Gram kernels accept; mirrors gram_tc_supported() in csrc."""
+    return C in (64, 128, 256, 512) and HW % 4 == 0 and HW >= 32
+
+
+def _precision(precision, C: int, HW: int) -> int:
+    if precision is None:
+        return GRAM_TF32 if gram_tc_supported(C, HW) else GRAM_FP32
+    try:
+        return _PRECISIONS[precision]
+    except KeyError:
+        raise ValueError(f"precision must be 'tf32', 'fp32' or None, got {precision!r}") from None
+
+
+def _feat3(name, feat):
+    feat = _cuda_f32(name, feat)
+    if feat.dim() == 4:
+        feat = feat.reshape(feat.shape[0], feat.shape[1], -1)
+    if feat.dim() != 3:
+        raise ValueError(f"{name}: expected (B,C,H,W) or (B,C,HW)")
+    return feat
+
+
+def _gram_ws(B, C, HW, device):
+    nbytes = lib().st3d_gram_workspace_size(B, C, HW)
+    return torch.empty(nbytes, device=device, dtype=torch.uint8), nbytes
+
+
+def gram_forward(feat, precision=None):
+    """(B,C,H,W) -> (B,C,C) = F F^T."""
+    f = _feat3("feat", feat)
+    B, C, HW = f.shape
+    out = torch.empty((B, C, C), device=f.device, dtype=torch.float32)
+    if B == 0:
+        return out
+    ws, nbytes = _gram_ws(B, C, HW, f.device)
+    check(lib().st3d_gram_forward(_p(f), B, C, HW, _p(out), _p(ws), nbytes, _precision(precision, C, HW), _stream()),
+          "st3d_gram_forward")
+    return out
+
+
+def gram_mse_forward(feat, target, scale: float, loss_out, want_gram=False, precision=None):
+    """loss_out[0] += scale * sum((F F^T - target)^2); returns (dgram, gram|None)."""
+    f = _feat3("feat", feat)
+    B, C, HW = f.shape
+    target = _cuda_f32("target", target, C, C).reshape(-1, C, C)
+    if target.shape[0] not in (1, B):
+        raise ValueError(f"target batch {target.shape[0]} is neither 1 nor {B}")
+    if loss_out.dtype != torch.float32 or not loss_out.is_cuda:
+        raise ValueError("loss_out must be a CUDA float32 tensor")
+    dgram = torch.empty((B, C, C), device=f.device, dtype=torch.float32)
+    gram = torch.empty((B, C, C), device=f.device, dtype=torch.float32) if want_gram else None
+    ws, nbytes = _gram_ws(B, C, HW, f.device)
+    check(lib().st3d_gram_mse_forward(_p(f), _p(target), B, target.shape[0], C, HW, float(scale), _p(gram), _p(dgram),
+                                      _p(loss_out), _p(ws), nbytes, _precision(precision, C, HW), _stream()),
+          "st3d_gram_mse_forward")
+    return dgram, gram
+
+
+def gram_backward(feat, dgram, grad_scale: float = 1.0, out=None, accumulate=False, precision=None):
+    """grad_feat = grad_scale * (dG + dG^T) F, shaped like feat."""
+    f = _feat3("feat", feat)
+    B, C, HW = f.shape
+    dgram = _cuda_f32("dgram", dgram, C, C).reshape(B, C, C)
+    if out is None:
+        out = torch.empty_like(f)
+        accumulate = False
+    ws, nbytes = _gram_ws(B, C, HW, f.device)
+    check(lib().st3d_gram_backward(_p(f), _p(dgram), B, C, HW, float(grad_scale), int(accumulate), _p(out), _p(ws),
+                                   nbytes, _precision(precision, C, HW), _stream()), "st3d_gram_backward")
+    return out.reshape(feat.shape)
+
+
+def mse_forward(a, b, scale: float, loss_out, mask=None, want_grad=True):
+    """loss_out[0] += scale * sum(m (a-b)^2); returns grad wrt a (or None).  mask: (B,1,H,W) for a (B,Cm,H,W)."""
+    a = _cuda_f32("a", a)
+    b = _cuda_f32("b", b)
+    if a.shape != b.shape:
+        raise ValueError(f"shape mismatch {tuple(a.shape)} vs {tuple(b.shape)}")
+    inner, mask_ch = 1, 1
+    if mask is not None:
+        mask = _cuda_f32("mask", mask)
+        if a.dim() != 4 or mask.shape != (a.shape[0], 1, a.shape[2], a.shape[3]):
+            raise ValueError("mask must be (B,1,H,W) for a (B,C,H,W) input")
+        inner, mask_ch = a.shape[2] * a.shape[3], a.shape[1]
+    grad = torch.empty_like(a) if want_grad else None
+    check(lib().st3d_mse_forward(_p(a), _p(b), _p(mask), a.numel(), inner, mask_ch, float(scale), _p(loss_out),
+                                 _p(grad), _stream()), "st3d_mse_forward")
+    return grad

@@ -1,0 +1,193 @@
+/*
+ * st3d.h -- C ABI of libst3d.so, the B200-native (sm_100a) implementation of the per-iteration
+ * style-transfer hot path of EmaMule/2D-to-3D-Style-Transfer.
+ *
+ * The reference has no FFI of its own: its hot path calls the third-party PyTorch3D extension
+ * (`pytorch3d._C`, absent from /root/reference) and torch.  Each entry point below names the
+ * reference call site / upstream operator it replaces.  INTEGRATION.md shows the ctypes stubs a
+ * maintainer would add.
+ *
+ * Conventions:
+ *  - every function returns 0 on success or a negative ST3D_ERR_* code and never throws;
+ *    `st3d_last_error()` returns a thread-local message for the last failure on this thread;
+ *  - the caller owns ALL memory (inputs, outputs, workspace); pointers are device pointers on the
+ *    current device unless marked "host"; tensors are contiguous, row-major;
+ *  - work is enqueued on `stream` (a cudaStream_t); no call synchronises the device or the host;
+ *  - re-entrant: no global mutable state.
+ */
+#ifndef ST3D_H_
+#define ST3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* st3d_stream_t; /* cudaStream_t */
+
+#define ST3D_OK 0
+#define ST3D_ERR_ARG (-1)
+#define ST3D_ERR_CUDA (-2)
+#define ST3D_ERR_WORKSPACE (-3)
+#define ST3D_ERR_UNSUPPORTED (-4)
+
+#define ST3D_MAX_FACES_PER_PIXEL 8
+#define ST3D_TILE 16 /* raster tile edge in pixels */
+
+const char* st3d_last_error(void);
+int st3d_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Vertex transform: world -> view -> NDC with z kept as view depth.
+ * Replaces PyTorch3D MeshRasterizer.transform as invoked by utils.py:69:
+ *   view = X . R + T (row vectors);  ndc.xy = (view.xy * k) / view.z;  ndc.z = view.z
+ * verts (V,3); R (N,3,3); T (N,3); out verts_ndc (N,V,3).
+ * Backward: grad_verts (V,3) += sum over views of J^T grad_ndc (caller zero-fills).
+ * ---------------------------------------------------------------------------------------------- */
+int st3d_transform_verts_forward(const float* verts, const float* R, const float* T, float k00, float k11,
+                                 int N, int64_t V, float* verts_ndc, st3d_stream_t stream);
+int st3d_transform_verts_backward(const float* verts, const float* R, const float* T, float k00, float k11,
+                                  int N, int64_t V, const float* grad_ndc, float* grad_verts,
+                                  st3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Operator boundary mirroring pytorch3d._C (upstream csrc/rasterize_meshes, csrc/interp_face_attrs;
+ * reached from the reference through first_approach.py:107-114 / utils.py:69).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Bytes of workspace for a raster call.  list_capacity = max (face,tile) pairs the tile bins may
+ * hold; 0 selects the default 8*F_total + 4096. */
+size_t st3d_raster_workspace_size(int N, int64_t F_total, int H, int W, int64_t list_capacity);
+
+/* Workspace header, readable by the host AFTER the stream has been synchronised:
+ * [0] = (face,tile) pairs needed by the last call, [1] = 1 if the bins overflowed (results invalid,
+ * re-run with a larger list_capacity), [2] = capacity in pairs. */
+#define ST3D_WS_HEADER_INTS 16
+
+/* _C.rasterize_meshes: face_verts (F_total,3,3) in NDC (z = view depth); mesh n owns faces
+ * [first[n], first[n]+num[n]).  Outputs (N,H,W,K): pix_to_face int64 (-1 = empty, packed face
+ * index), zbuf, dists; bary (N,H,W,K,3).  K <= ST3D_MAX_FACES_PER_PIXEL.  bin_size and
+ * max_faces_per_bin are accepted for signature parity and ignored: bins are 16x16-pixel tiles with
+ * exact-size face lists (no silent face drop, SURVEY section 7 "max_faces_per_bin overflow"). */
+int st3d_rasterize_meshes_forward(const float* face_verts, const int64_t* mesh_to_face_first_idx,
+                                  const int64_t* num_faces_per_mesh, int N, int64_t F_total, int64_t max_faces_in_mesh,
+                                  int H, int W, float blur_radius, int faces_per_pixel, int bin_size,
+                                  int max_faces_per_bin, int perspective_correct, int clip_barycentric_coords,
+                                  int cull_backfaces, void* workspace, size_t workspace_bytes,
+                                  int64_t* pix_to_face, float* zbuf, float* bary, float* dists,
+                                  st3d_stream_t stream);
+
+/* _C.rasterize_meshes_backward: grad_face_verts (F_total,3,3) += ... (caller zero-fills). */
+int st3d_rasterize_meshes_backward(const float* face_verts, const int64_t* pix_to_face, const float* grad_zbuf,
+                                   const float* grad_bary, const float* grad_dists, int N, int H, int W, int K,
+                                   int64_t F_total, int perspective_correct, int clip_barycentric_coords,
+                                   float* grad_face_verts, st3d_stream_t stream);
+
+/* _C.interp_face_attrs_forward/backward: pix_to_face (P) int64, bary (P,3), face_attrs (F,3,D),
+ * out (P,D).  Backward: grad_bary (P,3) overwritten; grad_face_attrs (F,3,D) += (caller zero-fills). */
+int st3d_interp_face_attrs_forward(const int64_t* pix_to_face, const float* bary, const float* face_attrs,
+                                   int64_t P, int64_t F, int D, float* out, st3d_stream_t stream);
+int st3d_interp_face_attrs_backward(const int64_t* pix_to_face, const float* bary, const float* face_attrs,
+                                    const float* grad_out, int64_t P, int64_t F, int D, float* grad_bary,
+                                    float* grad_face_attrs, st3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused multi-view renderer = MeshRenderer(MeshRasterizer, SoftPhongShader) with AmbientLights,
+ * faces_per_pixel = 1, for N cameras of ONE mesh in one call.  Replaces the per-view loop of
+ * utils.py:65-77 (render_meshes) and everything beneath it:
+ * transform -> tile bins -> fine raster -> UV / vertex-colour sample -> ambient shade ->
+ * softmax_rgb_blend, one pass, fragments never materialised.
+ * ---------------------------------------------------------------------------------------------- */
+#define ST3D_TEX_UV 0
+#define ST3D_TEX_VERTEX 1
+#define ST3D_LAYOUT_NHWC_RGBA 0 /* (N,H,W,4), what renderer(...) returns (utils.py:69)              */
+#define ST3D_LAYOUT_PLANAR 1    /* (N,3,H,W) image + (N,1,H,W) mask, what render_meshes returns     */
+
+typedef struct st3d_render_args {
+    /* mesh */
+    const float* verts;     /* (V,3) world space */
+    const int32_t* faces;   /* (F,3) */
+    int64_t V, F;
+    /* cameras: FoVPerspectiveCameras(R, T), fov/aspect folded into k00/k11 */
+    const float* R;         /* (N,3,3) */
+    const float* T;         /* (N,3) */
+    int N;
+    float k00, k11, znear, zfar;
+    /* RasterizationSettings(image_size, blur_radius, faces_per_pixel=1) */
+    int H, W;
+    float blur_radius;
+    int cull_backfaces;
+    /* textures */
+    int tex_mode;           /* ST3D_TEX_UV | ST3D_TEX_VERTEX */
+    const float* face_uvs;  /* (F,3,2) = verts_uvs[faces_uvs]            (UV mode)     */
+    const float* texture;   /* (Ht,Wt,3) one map shared by all views      (UV mode)     */
+    int Ht, Wt;
+    const float* verts_rgb; /* (V,3)                                     (vertex mode) */
+    /* AmbientLights x Materials.ambient, BlendParams */
+    float ambient[3];
+    float background[3];
+    float sigma, gamma;
+    /* outputs */
+    int out_layout;
+    float* out_image;       /* NHWC_RGBA: (N,H,W,4); PLANAR: (N,3,H,W) */
+    float* out_mask;        /* PLANAR only: (N,1,H,W) = (alpha > 0) */
+    int32_t* pix_to_face;   /* (N,H,W) packed face index n*F+f or -1; saved for backward */
+    /* scratch */
+    void* workspace;        /* >= st3d_render_workspace_size(...) bytes; forward fills it, backward reads it */
+    size_t workspace_bytes;
+    int64_t list_capacity;  /* must match the value given to st3d_render_workspace_size */
+} st3d_render_args;
+
+size_t st3d_render_workspace_size(int N, int64_t V, int64_t F, int H, int W, int64_t list_capacity);
+int st3d_render_forward(const st3d_render_args* args, st3d_stream_t stream);
+
+/* Backward of st3d_render_forward (autograd of loss.backward(), first_approach.py:211 /
+ * second_approach.py:188).  grad_image has the layout of out_image
+ * (the alpha channel of NHWC_RGBA carries a gradient; the PLANAR mask does not).
+ * grad_texture (Ht,Wt,3), grad_verts (V,3), grad_verts_rgb (V,3): accumulated (+=), may be NULL when
+ * not required; the caller zero-fills. */
+int st3d_render_backward(const st3d_render_args* args, const float* grad_image, float* grad_texture,
+                         float* grad_verts, float* grad_verts_rgb, st3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Style / content losses (style_transfer.py:31-35 gram_matrix; losses.py:31-39 loss body).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Arithmetic of the Gram products.  ST3D_GRAM_TF32: tcgen05.mma kind::tf32 fed by TMA with fp32
+ * accumulation in TMEM (C in {64,128,256,512}, HW % 4 == 0, HW >= 32; anything else returns
+ * ST3D_ERR_UNSUPPORTED).  ST3D_GRAM_FP32: exact fp32 FFMA tiles, any shape. */
+#define ST3D_GRAM_TF32 0
+#define ST3D_GRAM_FP32 1
+
+/* gram_matrix (style_transfer.py:31-35): feat (B,C,HW) fp32 -> gram (B,C,C) = F F^T, split-K with a
+ * deterministic fixed-order reduction of the partial sums held in the workspace. */
+size_t st3d_gram_workspace_size(int B, int C, int64_t HW);
+int st3d_gram_forward(const float* feat, int B, int C, int64_t HW, float* gram, void* workspace,
+                      size_t workspace_bytes, int precision, st3d_stream_t stream);
+
+/* One style layer of losses.py:35-39 fused: G = F F^T, loss_out[0] += scale * sum((G - G_target)^2),
+ * dgram (B,C,C) = 2 * scale * (G - G_target).  scale = weight / (B*C*C) / (C*C*H*H) is supplied by
+ * the caller; target (Bt,C,C) with Bt in {1,B} (broadcast).  gram and dgram may be NULL. */
+int st3d_gram_mse_forward(const float* feat, const float* target, int B, int Bt, int C, int64_t HW,
+                          float scale, float* gram, float* dgram, float* loss_out, void* workspace,
+                          size_t workspace_bytes, int precision, st3d_stream_t stream);
+
+/* Backward of gram_matrix: grad_feat (B,C,HW) = grad_scale * (dG + dG^T) F; when accumulate != 0 the
+ * result is added to grad_feat.  The workspace is the one sized by st3d_gram_workspace_size. */
+int st3d_gram_backward(const float* feat, const float* dgram, int B, int C, int64_t HW, float grad_scale,
+                       int accumulate, float* grad_feat, void* workspace, size_t workspace_bytes,
+                       int precision, st3d_stream_t stream);
+
+/* mean((a-b)^2) family (losses.py:31 content loss; losses.py:71-75 masked MSE):
+ * loss_out[0] += scale * sum(m*(a-b)^2); grad_a = 2*scale*m*(a-b) (NULL to skip).
+ * mask may be NULL; otherwise mask has n/mask_div elements broadcast over `inner` contiguous
+ * elements: m[i] = mask[(i / (inner*mask_ch)) * inner + i % inner]  (mask (B,1,H,W) vs (B,3,H,W)). */
+int st3d_mse_forward(const float* a, const float* b, const float* mask, int64_t n, int64_t inner, int mask_ch,
+                     float scale, float* loss_out, float* grad_a, st3d_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ST3D_H_ */

@@ -1,0 +1,161 @@
+"""GPU parity tests of the loss half (Gram / style loss / content + masked MSE) through st3d.ops.
+
+Bar (BASELINE.json north_star): fp32 path within 1e-4 relative; the tensor-core Gram (tcgen05
+kind::tf32, i.e. at least bf16-grade operands) within 2e-3 relative.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import loss_oracle as lo
+
+pytestmark = pytest.mark.gpu
+TOL_FP32, TOL_TC = 1e-4, 2e-3
+
+
+def _ops():
+    import st3d
+    return st3d.ops
+
+
+def _relerr(got, want):
+    got, want = got.detach().double().cpu(), want.detach().double().cpu()
+    return ((got - want).abs().max() / want.abs().max().clamp(min=1e-30)).item()
+
+
+def _features(B, C, H, W, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.relu(torch.randn(B, C, H, W, generator=g)) * 1.7  # post-ReLU like the VGG taps
+
+
+def test_gram_matches_reference_golden(golden_dir):
+    import sys
+    sys.path.insert(0, golden_dir)
+    import make_golden as mg
+    ops = _ops()
+    g = np.load(os.path.join(golden_dir, "loss_golden.npz"))
+    _, _, _, feat, _ = mg.loss_inputs()          # (2,8,5,7): odd shape -> fp32 FFMA path
+    got = ops.gram_forward(feat.cuda())
+    np.testing.assert_allclose(got.cpu().numpy(), g["gram"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 8, 5, 7), (1, 64, 16, 16), (3, 96, 9, 13), (2, 128, 24, 20)])
+def test_gram_fp32(B, C, H, W):
+    ops = _ops()
+    f = _features(B, C, H, W, 1)
+    want = lo.gram_matrix(f.double())
+    got = ops.gram_forward(f.cuda(), precision="fp32")
+    assert _relerr(got, want) <= TOL_FP32
+
+
+@pytest.mark.parametrize("B,C,H,W", [(1, 64, 16, 16), (2, 64, 64, 64), (2, 128, 32, 32), (3, 128, 24, 20),
+                                       (2, 256, 16, 16), (1, 256, 36, 28), (2, 512, 8, 8), (1, 512, 32, 32),
+                                       (8, 64, 20, 12), (1, 64, 6, 6)])
+def test_gram_tcgen05(B, C, H, W):
+    ops = _ops()
+    f = _features(B, C, H, W, 2)
+    want = lo.gram_matrix(f.double())
+    got = ops.gram_forward(f.cuda(), precision="tf32")
+    torch.cuda.synchronize()
+    err = _relerr(got, want)
+    assert err <= TOL_TC, f"tcgen05 Gram error {err:.3e}"
+    # determinism: fixed-order split-K reduction
+    assert torch.equal(got, ops.gram_forward(f.cuda(), precision="tf32"))
+    # against the exact-fp32 device path too
+    assert _relerr(got, ops.gram_forward(f.cuda(), precision="fp32")) <= TOL_TC
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", TOL_FP32), ("tf32", TOL_TC)])
+@pytest.mark.parametrize("B,Bt,C,H,W", [(2, 1, 64, 32, 32), (2, 2, 128, 16, 16), (1, 1, 256, 16, 16), (2, 1, 512, 8, 8)])
+def test_gram_mse_and_backward(precision, tol, B, Bt, C, H, W):
+    ops = _ops()
+    f = _features(B, C, H, W, 3)
+    style = _features(Bt, C, H, W, 4)
+    target = lo.gram_matrix(style.double())
+    f64 = f.double().requires_grad_(True)
+    scale = 1e6 / (B * C * C) / (C * C * H * H)   # style_weight * mean / (C^2 H^2), losses.py:35-39
+    want = 1e6 * lo.style_layer_loss(f64, target)
+    want.backward()
+    loss = torch.zeros(1, device="cuda")
+    dgram, gram = ops.gram_mse_forward(f.cuda(), target.float().cuda(), scale, loss, want_gram=True, precision=precision)
+    grad = ops.gram_backward(f.cuda(), dgram, 1.0, precision=precision)
+    torch.cuda.synchronize()
+    assert _relerr(gram, lo.gram_matrix(f.double())) <= tol
+    assert abs(loss.item() - want.item()) <= 2 * tol * abs(want.item()), (loss.item(), want.item())
+    assert grad.shape == f.shape
+    assert _relerr(grad, f64.grad) <= 2 * tol, f"grad error {_relerr(grad, f64.grad):.3e}"
+
+
+@pytest.mark.parametrize("C,H,W", [(64, 40, 40), (128, 12, 20), (256, 16, 8), (512, 8, 12)])
+def test_gram_backward_general_dgram(C, H, W):
+    """dG need not be symmetric: grad = (dG + dG^T) F; accumulate adds into an existing buffer."""
+    ops = _ops()
+    B = 2
+    f = _features(B, C, H, W, 5)
+    g = torch.Generator().manual_seed(6)
+    dG = torch.randn(B, C, C, generator=g)
+    f64 = f.double().requires_grad_(True)
+    (lo.gram_matrix(f64) * dG.double()).sum().backward()
+    for precision, tol in (("fp32", TOL_FP32), ("tf32", TOL_TC)):
+        got = ops.gram_backward(f.cuda(), dG.cuda(), 0.5, precision=precision)
+        assert _relerr(got, 0.5 * f64.grad) <= tol, precision
+        base = torch.ones_like(f).cuda()
+        got2 = ops.gram_backward(f.cuda(), dG.cuda(), 0.5, out=base.reshape(B, C, -1), accumulate=True, precision=precision)
+        assert _relerr(got2, 0.5 * f64.grad + 1.0) <= tol, precision
+
+
+def test_gram_unsupported_shape_fails_loudly():
+    ops = _ops()
+    with pytest.raises(Exception):
+        ops.gram_forward(torch.rand(1, 8, 5, 7, device="cuda"), precision="tf32")
+    with pytest.raises(Exception):
+        ops.gram_forward(torch.rand(1, 64, 8, 8), precision="fp32")   # CPU tensor: no CPU path
+
+
+def test_mse_and_masked_mse(golden_dir):
+    import sys
+    sys.path.insert(0, golden_dir)
+    import make_golden as mg
+    ops = _ops()
+    g = np.load(os.path.join(golden_dir, "loss_golden.npz"))
+    cur, con, _, _, masks = mg.loss_inputs()
+    loss = torch.zeros(1, device="cuda")
+    grad = ops.mse_forward(cur.cuda(), con.cuda(), 1.0 / cur.numel(), loss, mask=masks.cuda())
+    np.testing.assert_allclose(loss.item(), g["first"], rtol=1e-5)
+    np.testing.assert_allclose(grad.cpu().numpy(), g["first_grad"], rtol=1e-4, atol=1e-9)
+    # unmasked, odd length (scalar path) and large (vector path)
+    for n in (1001, 1 << 20):
+        gen = torch.Generator().manual_seed(n)
+        a, b = torch.randn(n, generator=gen), torch.randn(n, generator=gen)
+        loss.zero_()
+        gr = ops.mse_forward(a.cuda(), b.cuda(), 1.0 / n, loss)
+        want = ((a.double() - b.double()) ** 2).mean()
+        assert abs(loss.item() - want.item()) <= 1e-5 * want.item()
+        assert _relerr(gr, 2 * (a.double() - b.double()) / n) <= 1e-6
+
+
+def test_gram_full_size_properties():
+    """BASELINE configs[1] layer sizes (8 images at 512^2): properties instead of a CPU oracle run."""
+    ops = _ops()
+    for C, S in ((64, 512), (128, 256), (256, 128), (512, 64), (512, 32)):
+        B = 8
+        g = torch.Generator(device="cuda").manual_seed(C + S)
+        f = torch.relu(torch.randn(B, C, S, S, device="cuda", generator=g))
+        G = ops.gram_forward(f, precision="tf32")
+        torch.cuda.synchronize()
+        assert torch.allclose(G, G.transpose(1, 2), rtol=1e-5, atol=1e-3 * G.abs().max().item())
+        # diagonal = squared row norms; trace check against an fp64 reduction
+        tr = (f.double() ** 2).sum(dim=(1, 2, 3))
+        assert ((torch.diagonal(G, dim1=1, dim2=2).double().sum(1) - tr).abs() / tr).max() <= TOL_TC
+        # checksum: 1^T G 1 = || sum_c F_c ||^2
+        cs = (f.double().sum(1) ** 2).sum(dim=(1, 2))
+        assert ((G.double().sum(dim=(1, 2)) - cs).abs() / cs).max() <= TOL_TC
+        # homogeneity: G(2F) = 4 G(F) exactly (power-of-two scaling is exact in tf32/fp32)
+        assert torch.equal(ops.gram_forward(2 * f, precision="tf32"), 4 * G)
+        # backward: <dF, X> = <dG + dG^T, F X^T> for a random probe X (adjoint identity), via fp32 path
+        dG = torch.randn(B, C, C, device="cuda", generator=g)
+        dF = ops.gram_backward(f, dG, 1.0, precision="tf32")
+        dF32 = ops.gram_backward(f, dG, 1.0, precision="fp32")
+        assert _relerr(dF, dF32) <= TOL_TC

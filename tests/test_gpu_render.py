@@ -1,0 +1,252 @@
+"""GPU parity tests of the render half (C ABI of include/st3d.h via st3d.ops) against the CPU oracle.
+
+Bar (BASELINE.json north_star): pix_to_face bit-exact; images / fragments / gradients within 1e-4
+relative (fp32).  Gradients are compared against float64 autograd through the oracle restatement.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import render_oracle as ro
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _ops():
+    import st3d
+    return st3d.ops
+
+
+def _close(got, want, tol=TOL, what=""):
+    got, want = got.detach().double().cpu(), want.detach().double().cpu()
+    scale = want.abs().max().clamp(min=1e-30)
+    err = (got - want).abs().max() / scale
+    assert err <= tol, f"{what}: max error {err:.3e} of the largest magnitude (tolerance {tol:g})"
+
+
+def _face_verts(cow, R, T):
+    k00, k11 = ro.fov_scales(60.0)
+    ndc = ro.transform_verts_exact(cow["verts"], R, T, k00, k11)
+    N, Fn = R.shape[0], cow["faces"].shape[0]
+    fv = ndc[:, cow["faces"]].reshape(N * Fn, 3, 3).contiguous()
+    first = torch.arange(N, dtype=torch.int64) * Fn
+    num = torch.full((N,), Fn, dtype=torch.int64)
+    return fv, first, num, (k00, k11)
+
+
+@pytest.mark.parametrize("S,K,blur", [(64, 1, 0.0), ((48, 80), 1, 0.0), (64, 3, 0.0), (40, 4, 2e-4), (33, 8, 1e-3)])
+def test_rasterize_meshes_matches_oracle(cow, S, K, blur):
+    ops = _ops()
+    R, T = ro.random_cameras(2, generator=torch.Generator().manual_seed(11))
+    fv, first, num, _ = _face_verts(cow, R, T)
+    clip = blur > 0
+    want = ro.rasterize_naive(fv, first, num, S, blur, K, True, clip, False, nthreads=8)
+    got = ops.rasterize_meshes(fv.cuda(), first.cuda(), num.cuda(), S, blur, K, 0, 0, True, clip, False)
+    torch.cuda.synchronize()
+    ops.poll_overflow(block=True)
+    assert torch.equal(got[0].cpu(), want[0]), "pix_to_face differs from the oracle"
+    for g, w, name in zip(got[1:], want[1:], ("zbuf", "bary", "dists")):
+        _close(g, w, what=name)
+    assert (got[0] >= 0).float().mean() > 0.05
+
+
+def test_rasterize_transform_bit_exact(cow):
+    ops = _ops()
+    R, T = ro.random_cameras(3, generator=torch.Generator().manual_seed(5))
+    k00, k11 = ro.fov_scales(60.0)
+    want = ro.transform_verts_exact(cow["verts"], R, T, k00, k11)
+    got = ops.transform_verts(cow["verts"].cuda(), R.cuda(), T.cuda(), k00, k11)
+    assert torch.equal(got.cpu(), want), "vertex transform is not bit-identical to the oracle"
+
+
+def test_rasterize_edge_cases():
+    ops = _ops()
+    # shared-edge hole, back faces drawn, z tie -> lower face index, degenerate and behind-camera faces
+    x = 0.125
+    tris = torch.tensor([[x, -1, 1.0], [x, 1, 1.0], [1, 0, 1.0], [x, 1, 1.0], [x, -1, 1.0], [-1, 0, 1.0],
+                         [0.0, 0.0, 1.0], [0.5, 0.5, 1.0], [1.0, 1.0, 1.0],
+                         [-0.9, -0.9, -1.0], [0.9, -0.9, -1.0], [0.0, 0.9, -1.0],
+                         [-0.9, -0.9, 3.0], [0.0, 0.9, 3.0], [0.9, -0.9, 3.0],
+                         [-0.9, -0.9, 3.0], [0.0, 0.9, 3.0], [0.9, -0.9, 3.0]]).reshape(-1, 3, 3)
+    first, num = torch.zeros(1, dtype=torch.int64), torch.tensor([tris.shape[0]])
+    for K in (1, 2, 5):
+        for cull in (False, True):
+            want = ro.rasterize_naive(tris, first, num, 8, 0.0, K, True, False, cull)
+            got = ops.rasterize_meshes(tris.cuda(), first.cuda(), num.cuda(), 8, 0.0, K, 0, 0, True, False, cull)
+            assert torch.equal(got[0].cpu(), want[0])
+            _close(got[1], want[1], what="zbuf")
+    # empty inputs
+    e = ops.rasterize_meshes(torch.zeros((0, 3, 3), device="cuda"), torch.zeros(1, dtype=torch.int64, device="cuda"),
+                             torch.zeros(1, dtype=torch.int64, device="cuda"), 16, 0.0, 1, 0, 0, True, False, False)
+    assert (e[0] == -1).all() and (e[1] == -1).all()
+
+
+def test_render_forward_matches_golden(golden_dir, cow):
+    ops = _ops()
+    g = np.load(os.path.join(golden_dir, "render_golden.npz"))
+    k00, k11 = ro.fov_scales(60.0)
+    for sfx, S in (("", 64), ("2", 96)):
+        R, T = torch.from_numpy(g["R" + sfx]), torch.from_numpy(g["T" + sfx])
+        spec = ops.RenderSpec(image_size=(S, S), k00=k00, k11=k11)
+        fuv = cow["verts_uvs"][cow["faces_uvs"]]
+        img, _, p2f, _ = ops.render_forward(spec, cow["verts"].cuda(), cow["faces"].cuda(), R.cuda(), T.cuda(),
+                                            face_uvs=fuv.cuda(), texture=cow["texture"].cuda())
+        torch.cuda.synchronize()
+        ops.poll_overflow(block=True)
+        assert np.array_equal(p2f.cpu().numpy(), g["p2f" + sfx][..., 0]), "pix_to_face differs from the golden"
+        np.testing.assert_allclose(img.cpu().numpy(), g["rgba" + sfx].astype(np.float32), atol=2e-3)  # fp16 fixture
+        want = ro.render_views(cow["verts"], cow["faces"], R, T, S, texture=cow["texture"],
+                               verts_uvs=cow["verts_uvs"], faces_uvs=cow["faces_uvs"], nthreads=8)
+        _close(img, want, what="rgba")
+
+
+@pytest.mark.parametrize("layout", ["nhwc", "planar"])
+@pytest.mark.parametrize("mode", ["uv", "vertex"])
+def test_render_backward_matches_oracle_autograd(cow, layout, mode):
+    ops = _ops()
+    S, N = 72, 3
+    gen = torch.Generator().manual_seed(21)
+    R, T = ro.random_cameras(N, generator=gen)
+    k00, k11 = ro.fov_scales(60.0)
+    verts64 = cow["verts"].double().requires_grad_(True)
+    tex = torch.rand(40, 56, 3, generator=gen)
+    vrgb = torch.rand(cow["verts"].shape[0], 3, generator=gen)
+    tex64, vrgb64 = tex.double().requires_grad_(True), vrgb.double().requires_grad_(True)
+    kw = dict(texture=tex64, verts_uvs=cow["verts_uvs"].double(), faces_uvs=cow["faces_uvs"]) if mode == "uv" \
+        else dict(verts_rgb=vrgb64)
+    # coverage must come from the fp32 positions: render_views rasterizes verts.float() exactly
+    rgba = ro.render_views(verts64, cow["faces"], R, T, S, nthreads=8, **kw)
+    wgt = torch.randn(N, S, S, 4, generator=gen).double()
+    if layout == "planar":
+        wgt[..., 3] = 0.0
+    (rgba * wgt).sum().backward()
+
+    lay = ops.LAYOUT_NHWC_RGBA if layout == "nhwc" else ops.LAYOUT_PLANAR
+    spec = ops.RenderSpec(image_size=(S, S), k00=k00, k11=k11, layout=lay)
+    gkw = dict(face_uvs=cow["verts_uvs"][cow["faces_uvs"]].cuda(), texture=tex.cuda()) if mode == "uv" \
+        else dict(verts_rgb=vrgb.cuda())
+    img, mask, p2f, state = ops.render_forward(spec, cow["verts"].cuda(), cow["faces"].cuda(), R.cuda(), T.cuda(), **gkw)
+    if layout == "planar":
+        want_img, want_mask = ro.images_and_masks(rgba.detach())
+        _close(img, want_img, what="planar image")
+        assert torch.equal(mask.cpu().double(), want_mask)
+        gimg = wgt[..., :3].permute(0, 3, 1, 2).contiguous().float().cuda()
+    else:
+        _close(img, rgba, what="rgba")
+        gimg = wgt.float().cuda()
+    g_tex, g_verts, g_rgb = ops.render_backward(state, gimg, need_texture=True, need_verts=True, need_verts_rgb=True)
+    torch.cuda.synchronize()
+    if mode == "uv":
+        _close(g_tex, tex64.grad, what="grad_texture")
+        assert g_rgb is None
+    else:
+        _close(g_rgb, vrgb64.grad, what="grad_verts_rgb")
+        assert g_tex is None
+    _close(g_verts, verts64.grad, tol=2e-4, what="grad_verts")
+
+
+@pytest.mark.parametrize("K,blur", [(1, 0.0), (3, 5e-4)])
+def test_rasterize_meshes_backward_matches_autograd(cow, K, blur):
+    ops = _ops()
+    S = 56
+    gen = torch.Generator().manual_seed(3)
+    R, T = ro.random_cameras(2, generator=gen)
+    fv, first, num, _ = _face_verts(cow, R, T)
+    clip = blur > 0
+    p2f, *_ = ro.rasterize_naive(fv, first, num, S, blur, K, True, clip, False, nthreads=8)
+    fv64 = fv.double().requires_grad_(True)
+    zbuf, bary, dists = ro.fragments_from_faces(fv64, p2f, True, clip)
+    gz, gb, gd = (torch.randn(t.shape, generator=gen).double() for t in (zbuf, bary, dists))
+    (zbuf * gz).sum().backward(retain_graph=True)
+    g_z = fv64.grad.clone(); fv64.grad = None
+    (bary * gb).sum().backward(retain_graph=True)
+    g_b = fv64.grad.clone(); fv64.grad = None
+    (dists * gd).sum().backward()
+    g_d = fv64.grad.clone()
+    zero = lambda t: torch.zeros_like(t).float().cuda()
+    fvc, p2fc = fv.cuda(), p2f.cuda()
+    got_z = ops.rasterize_meshes_backward(fvc, p2fc, gz.float().cuda(), zero(gb), zero(gd), True, clip)
+    got_b = ops.rasterize_meshes_backward(fvc, p2fc, zero(gz), gb.float().cuda(), zero(gd), True, clip)
+    got_d = ops.rasterize_meshes_backward(fvc, p2fc, zero(gz), zero(gb), gd.float().cuda(), True, clip)
+    _close(got_z, g_z, tol=2e-4, what="grad via zbuf")
+    _close(got_b, g_b, tol=2e-4, what="grad via bary")
+    _close(got_d, g_d, tol=2e-4, what="grad via dists")
+
+
+def test_interp_face_attrs(cow):
+    ops = _ops()
+    gen = torch.Generator().manual_seed(9)
+    Fn, P, D = 50, 4000, 5
+    p2f = torch.randint(-1, Fn, (P,), generator=gen)
+    bary = torch.rand(P, 3, generator=gen)
+    attrs = torch.randn(Fn, 3, D, generator=gen).double().requires_grad_(True)
+    bary64 = bary.double().requires_grad_(True)
+    want = ro.interpolate_face_attributes(p2f, bary64, attrs)
+    go = torch.randn(P, D, generator=gen).double()
+    (want * go).sum().backward()
+    got = ops.interp_face_attrs_forward(p2f.cuda(), bary.cuda(), attrs.detach().float().cuda())
+    _close(got, want, what="interp forward")
+    g_bary, g_attrs = ops.interp_face_attrs_backward(p2f.cuda(), bary.cuda(), attrs.detach().float().cuda(), go.float().cuda())
+    mask = (p2f >= 0)[:, None].double()
+    _close(g_bary, bary64.grad * mask, what="grad_bary")
+    _close(g_attrs, attrs.grad, what="grad_attrs")
+
+
+def test_transform_backward(cow):
+    ops = _ops()
+    gen = torch.Generator().manual_seed(2)
+    R, T = ro.random_cameras(4, generator=gen)
+    k00, k11 = ro.fov_scales(60.0)
+    v64 = cow["verts"].double().requires_grad_(True)
+    ndc = ro.transform_verts_torch(v64, R, T, k00, k11)
+    g = torch.randn(ndc.shape, generator=gen).double()
+    (ndc * g).sum().backward()
+    got = ops.transform_verts_backward(cow["verts"].cuda(), R.cuda(), T.cuda(), k00, k11, g.float().cuda())
+    _close(got, v64.grad, what="transform backward")
+
+
+def test_full_size_properties(cow):
+    """BASELINE configs[1] size (8 x 512^2): size-independent properties instead of an oracle run."""
+    ops = _ops()
+    S, N = 512, 8
+    R, T = ro.random_cameras(N, generator=torch.Generator().manual_seed(0))
+    k00, k11 = ro.fov_scales(60.0)
+    fuv = cow["verts_uvs"][cow["faces_uvs"]].cuda()
+    tex = torch.nn.functional.interpolate(cow["texture"].permute(2, 0, 1)[None], size=(512, 512), mode="bilinear",
+                                          align_corners=False)[0].permute(1, 2, 0).contiguous().cuda()
+    spec = ops.RenderSpec(image_size=(S, S), k00=k00, k11=k11)
+    args = (spec, cow["verts"].cuda(), cow["faces"].cuda(), R.cuda(), T.cuda())
+    img, _, p2f, state = ops.render_forward(*args, face_uvs=fuv, texture=tex)
+    img2, _, p2f2, _ = ops.render_forward(*args, face_uvs=fuv, texture=tex)
+    torch.cuda.synchronize()
+    ops.poll_overflow(block=True)
+    assert torch.equal(p2f, p2f2) and torch.equal(img, img2), "forward is not deterministic"
+    cov = p2f >= 0
+    assert 0.1 < cov.float().mean().item() < 0.6
+    assert torch.equal(img[..., 3] > 0, cov)                      # mask == coverage (utils.py:71-72)
+    assert torch.equal(img[..., :3][~cov], torch.ones_like(img[..., :3][~cov]))  # exact white background
+    Fn = cow["faces"].shape[0]
+    view = torch.arange(N, device="cuda")[:, None, None].expand_as(p2f)
+    assert ((p2f[cov] // Fn) == view[cov]).all()                  # packed indices stay inside their view
+    # same coverage through the operator boundary (fragments) as through the fused path
+    fv = ops.transform_verts(*args[1:2], R.cuda(), T.cuda(), k00, k11)[:, cow["faces"].cuda()].reshape(N * Fn, 3, 3)
+    first = torch.arange(N, device="cuda") * Fn
+    frag = ops.rasterize_meshes(fv, first, torch.full((N,), Fn, device="cuda"), S, 0.0, 1, 0, 0, True, False, False)
+    assert torch.equal(frag[0][..., 0], p2f.long())
+    inside = frag[2][..., 0, :][cov]
+    assert (inside > 0).all() and torch.allclose(inside.sum(-1), torch.ones_like(inside[:, 0]), atol=1e-4)
+    assert (frag[3][..., 0][cov] <= 0).all()
+    # linearity of the backward in the upstream gradient and in the texture
+    g1 = torch.randn_like(img); g2 = torch.randn_like(img)
+    t1, _, _ = ops.render_backward(state, g1)
+    t2, _, _ = ops.render_backward(state, g2)
+    t12, _, _ = ops.render_backward(state, g1 + 2 * g2)
+    _close(t12, t1 + 2 * t2, tol=1e-4, what="backward linearity")
+    # <render(tex), g> == <tex, backward(g)> up to the (constant) background term: rgb is affine in tex
+    img0, *_ = ops.render_forward(*args, face_uvs=fuv, texture=torch.zeros_like(tex))
+    lhs = ((img - img0)[..., :3].double() * g1[..., :3].double()).sum()
+    rhs = (tex.double() * t1.double()).sum()
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), abs(rhs)), (lhs.item(), rhs.item())
