@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -15,3 +17,8 @@ void st3d_set_error(const char* fmt, ...) {
 
 extern "C" const char* st3d_last_error(void) { return g_err; }
 extern "C" int st3d_version(void) { return 100; }
+
+// Kernel launches issued by this library in this process (a statistic, never read by the kernels).
+static std::atomic<unsigned long long> g_launches{0};
+void st3d_count_launch(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" unsigned long long st3d_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -7,6 +7,7 @@
 #include "../../include/st3d.h"
 
 void st3d_set_error(const char* fmt, ...);
+void st3d_count_launch(void);  // bumps the counter st3d_launch_count() reports
 
 #define ST3D_REQUIRE(cond, ...)             \
     do {                                    \
@@ -32,6 +33,7 @@ void st3d_set_error(const char* fmt, ...);
             st3d_set_error("launch of %s: %s", name, cudaGetErrorString(e_));     \
             return ST3D_ERR_CUDA;                                                 \
         }                                                                         \
+        st3d_count_launch();                                                      \
     } while (0)
 
 namespace st3d {

@@ -106,9 +106,11 @@ k_gram_finalize(const float* __restrict__ partials, int splits, int B, int Bt, i
 }
 
 // S = gs * (dG + dG^T)
-__global__ void k_gram_symmetrize(const float* __restrict__ dgram, int B, int C, float gs, float* __restrict__ sym) {
+__global__ void k_gram_symmetrize(const float* __restrict__ dgram, int B, int C, float gs,
+                                  const float* __restrict__ gs_dev, float* __restrict__ sym) {
     const int64_t cc = (int64_t)C * C, i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)B * cc) return;
+    if (gs_dev) gs *= __ldg(gs_dev);
     const int64_t b = i / cc, e = i % cc;
     const int r = (int)(e / C), c = (int)(e % C);
     sym[i] = gs * (dgram[i] + dgram[b * cc + (int64_t)c * C + r]);
@@ -236,8 +238,8 @@ extern "C" int st3d_gram_forward(const float* feat, int B, int C, int64_t HW, fl
 }
 
 extern "C" int st3d_gram_backward(const float* feat, const float* dgram, int B, int C, int64_t HW, float grad_scale,
-                                  int accumulate, float* grad_feat, void* workspace, size_t workspace_bytes,
-                                  int precision, st3d_stream_t stream) {
+                                  const float* grad_scale_dev, int accumulate, float* grad_feat, void* workspace,
+                                  size_t workspace_bytes, int precision, st3d_stream_t stream) {
     int rc = check_common("gram_backward", feat, B, C, HW, precision);
     if (rc != ST3D_OK) return rc;
     if (B == 0) return ST3D_OK;
@@ -248,7 +250,7 @@ extern "C" int st3d_gram_backward(const float* feat, const float* dgram, int B, 
         return ST3D_ERR_WORKSPACE;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    k_gram_symmetrize<<<cdiv((int64_t)B * C * C, 256), 256, 0, s>>>(dgram, B, C, grad_scale, p.sym);
+    k_gram_symmetrize<<<cdiv((int64_t)B * C * C, 256), 256, 0, s>>>(dgram, B, C, grad_scale, grad_scale_dev, p.sym);
     ST3D_LAUNCH_OK("k_gram_symmetrize");
     if (precision == ST3D_GRAM_TF32) return gram_tc_backward(feat, p, accumulate, grad_feat, s);
     k_gram_bwd_simt<<<dim3(cdiv(HW, kST), cdiv(C, kST), B), 256, 0, s>>>(feat, p.sym, C, HW, accumulate, grad_feat);

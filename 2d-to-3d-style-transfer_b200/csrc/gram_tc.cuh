@@ -9,6 +9,7 @@
 // fp32 in TMEM.  Every mbarrier wait is bounded: a protocol bug traps instead of hanging the GPU.
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "gram_common.cuh"
 
@@ -100,11 +101,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&r)[32]) {
 }
 
 // ---- descriptors (bit layout: PTX ISA "tcgen05 shared memory / instruction descriptor") ---------------
-// 128-byte swizzled operand tile.  lbo / sbo in bytes.
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+// 128-byte swizzled operand tile.  lbo / sbo in bytes.  layout: 2 = SWIZZLE_128B (16-byte chunks, the
+// K-major operands), 1 = SWIZZLE_128B_BASE32B (32-byte chunks; the only layout tcgen05 accepts for an
+// MN-major tf32 operand; TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo, uint64_t layout = 2) {
     return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46) /* sm_100 descriptor version */ |
-           (2ull << 61) /* SWIZZLE_128B */;
+           (layout << 61);
 }
 // kind::tf32, fp32 accumulate; a_mn / b_mn = 1 selects the MN-major operand layout
 constexpr uint32_t instr_desc(int M, int N, int a_mn, int b_mn) {
@@ -332,7 +335,8 @@ k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__
                     const uint32_t sF = smem_u32(stages + (size_t)st * Cfg::STAGE_BYTES), sS = sF + Cfg::F_BYTES;
 #pragma unroll
                     for (int kg = 0; kg < 4; ++kg) {  // 8 channels j per MMA
-                        const uint64_t ad = smem_desc(sF + kg * 1024, 4096, 1024);
+                        // A: 4 M-atoms (32 x's) 4096 B apart; each MMA spans two 4-row K-atoms 512 B apart
+                        const uint64_t ad = smem_desc(sF + kg * 1024, 4096, 512, 1);
 #pragma unroll
                         for (int h = 0; h < Cfg::NHALF; ++h) {
                             const uint64_t bd = smem_desc(sS + h * 256 * 128 + kg * 32, 16, 1024);
@@ -397,7 +401,8 @@ static inline EncodeTiledFn encode_fn() {
 }
 
 // 2D fp32 tensor [rows][cols] (cols contiguous), box [box_rows][32 cols], 128-byte swizzle, zero fill
-static inline int make_map(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+static inline int make_map(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                           CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         st3d_set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -407,8 +412,13 @@ static inline int make_map(CUtensorMap* m, const float* base, uint64_t rows, uin
     const cuuint64_t strides[1] = {cols * sizeof(float)};
     const cuuint32_t box[2] = {32, box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    // TFLOAT32: the TMA unit rounds each fp32 value to tf32 (round-to-nearest) while it copies, so the
+    // tensor core's operand truncation introduces no systematic bias (plain FLOAT32 would leave the low
+    // 13 mantissa bits to be chopped: a -5e-4 relative bias per operand, fatal in G - G_target).
+    static const bool plain = [] { const char* e = getenv("ST3D_TMA_PLAIN_FP32"); return e && e[0] == '1'; }();
+    const CUresult r = fn(m, plain ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2,
+                          const_cast<float*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         st3d_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu)", (int)r,
@@ -439,7 +449,7 @@ template <int C>
 static int launch_bwd(const float* feat, const GramPlan& p, int accumulate, float* grad_feat, cudaStream_t s) {
     using Cfg = BwdCfg<C>;
     CUtensorMap map_f, map_s;
-    int rc = make_map(&map_f, feat, (uint64_t)p.B * C, (uint64_t)p.HW, 32);
+    int rc = make_map(&map_f, feat, (uint64_t)p.B * C, (uint64_t)p.HW, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc != ST3D_OK) return rc;
     rc = make_map(&map_s, p.sym, (uint64_t)p.B * C, (uint64_t)C, Cfg::S_BOX_ROWS);
     if (rc != ST3D_OK) return rc;

@@ -37,6 +37,7 @@ class RenderArgs(ctypes.Structure):
 SIGNATURES = {
     "st3d_last_error": (ctypes.c_char_p, []),
     "st3d_version": (c_i, []),
+    "st3d_launch_count": (ctypes.c_ulonglong, []),
     "st3d_transform_verts_forward": (c_i, [c_p, c_p, c_p, c_f, c_f, c_i, c_i64, c_p, c_p]),
     "st3d_transform_verts_backward": (c_i, [c_p, c_p, c_p, c_f, c_f, c_i, c_i64, c_p, c_p, c_p]),
     "st3d_raster_workspace_size": (c_sz, [c_i, c_i64, c_i, c_i, c_i64]),
@@ -51,7 +52,7 @@ SIGNATURES = {
     "st3d_gram_workspace_size": (c_sz, [c_i, c_i, c_i64]),
     "st3d_gram_forward": (c_i, [c_p, c_i, c_i, c_i64, c_p, c_p, c_sz, c_i, c_p]),
     "st3d_gram_mse_forward": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i64, c_f, c_p, c_p, c_p, c_p, c_sz, c_i, c_p]),
-    "st3d_gram_backward": (c_i, [c_p, c_p, c_i, c_i, c_i64, c_f, c_i, c_p, c_p, c_sz, c_i, c_p]),
+    "st3d_gram_backward": (c_i, [c_p, c_p, c_i, c_i, c_i64, c_f, c_p, c_i, c_p, c_p, c_sz, c_i, c_p]),
     "st3d_mse_forward": (c_i, [c_p, c_p, c_p, c_i64, c_i64, c_i, c_f, c_p, c_p, c_p]),
 }
 

@@ -1,0 +1,67 @@
+"""Fused-kernel versions of the reference's loss bodies (losses.py:12-44, 68-98; style_transfer.py:10-35).
+
+The VGG-19 convolutions stay on torch/cuDNN (out of scope per BASELINE.json); everything after the
+feature taps -- Gram products, the MSE against the style Grams, the content MSE, the masked image MSE
+and all their backwards -- runs in libst3d kernels."""
+from __future__ import annotations
+
+import torch
+
+from . import functional as Fn
+
+# VGG-19 `.features` taps of style_transfer.py:12-19.  The ReLUs are in-place, so every tapped tensor is
+# the post-ReLU activation by the time it is used.
+VGG_TAPS = {"0": "conv1_1", "5": "conv2_1", "10": "conv3_1", "19": "conv4_1", "21": "conv4_2", "28": "conv5_1"}
+CONTENT_LAYER = "conv4_2"
+LAST_TAP = 28
+
+
+def get_features(image: torch.Tensor, model, layers=None, stop_after_last_tap: bool = True):
+    """style_transfer.py:10-27.  Walks `model` (VGG-19 `.features`) and returns {layer name: activation}.
+    The reference keeps walking modules 29-36 whose outputs nobody reads; this stops after the last tap."""
+    layers = VGG_TAPS if layers is None else layers
+    last = max((int(k) for k in layers if str(k).isdigit()), default=None)
+    feats, x = {}, image
+    for name, module in model._modules.items():
+        x = module(x)
+        if name in layers:
+            feats[layers[name]] = x
+        if stop_after_last_tap and last is not None and name == str(last):
+            break
+    return feats
+
+
+def style_targets(style_imgs: torch.Tensor, model, precision=None):
+    """Gram matrices of the style image's features (losses.py:19-25), conv4_2 excluded."""
+    with torch.no_grad():
+        feats = get_features(style_imgs, model)
+        return {k: Fn.gram_matrix(v, precision) for k, v in feats.items() if k != CONTENT_LAYER}
+
+
+def perceptual_loss_from_features(cur_feats, content_feat, style_grams, style_weight=1e6, content_weight=1.0,
+                                  precision=None):
+    """losses.py:28-42 given the three sets of features."""
+    content_loss = Fn.mse_loss(cur_feats[CONTENT_LAYER], content_feat)
+    style_loss = None
+    for layer, target in style_grams.items():
+        term = Fn.style_layer_loss(cur_feats[layer], target, 1.0, precision)
+        style_loss = term if style_loss is None else style_loss + term
+    return content_weight * content_loss + style_weight * style_loss
+
+
+def compute_perceptual_loss(current_imgs, content_imgs, style_imgs, model, style_weight=1e6, content_weight=1,
+                            precision=None):
+    """losses.py:12-44.  `style_imgs` may have batch 1 (the reference repeats one image B times,
+    second_approach.py:157; a single copy gives the same target Gram for every view)."""
+    B = current_imgs.shape[0]
+    assert content_imgs.shape[0] == B and style_imgs.shape[0] in (1, B)
+    with torch.no_grad():
+        content_feat = get_features(content_imgs, model, {"21": CONTENT_LAYER})[CONTENT_LAYER]
+    grams = style_targets(style_imgs, model, precision)
+    cur = get_features(current_imgs, model)
+    return perceptual_loss_from_features(cur, content_feat, grams, style_weight, content_weight, precision)
+
+
+def compute_first_approach_image_loss(rendered, masks, target_rendered):
+    """losses.py:71-75 (`texture` target): mse_loss(rendered * masks, target * masks)."""
+    return Fn.masked_mse_loss(rendered, target_rendered, masks)

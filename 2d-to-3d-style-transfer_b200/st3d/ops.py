@@ -348,8 +348,8 @@ def gram_mse_forward(feat, target, scale: float, loss_out, want_gram=False, prec
     return dgram, gram
 
 
-def gram_backward(feat, dgram, grad_scale: float = 1.0, out=None, accumulate=False, precision=None):
-    """grad_feat = grad_scale * (dG + dG^T) F, shaped like feat."""
+def gram_backward(feat, dgram, grad_scale: float = 1.0, out=None, accumulate=False, precision=None, scale_tensor=None):
+    """grad_feat = grad_scale * [scale_tensor] * (dG + dG^T) F, shaped like feat (scale_tensor: 1-element CUDA tensor)."""
     f = _feat3("feat", feat)
     B, C, HW = f.shape
     dgram = _cuda_f32("dgram", dgram, C, C).reshape(B, C, C)
@@ -357,8 +357,10 @@ def gram_backward(feat, dgram, grad_scale: float = 1.0, out=None, accumulate=Fal
         out = torch.empty_like(f)
         accumulate = False
     ws, nbytes = _gram_ws(B, C, HW, f.device)
-    check(lib().st3d_gram_backward(_p(f), _p(dgram), B, C, HW, float(grad_scale), int(accumulate), _p(out), _p(ws),
-                                   nbytes, _precision(precision, C, HW), _stream()), "st3d_gram_backward")
+    if scale_tensor is not None:
+        scale_tensor = _cuda_f32("scale_tensor", scale_tensor).reshape(1)
+    check(lib().st3d_gram_backward(_p(f), _p(dgram), B, C, HW, float(grad_scale), _p(scale_tensor), int(accumulate),
+                                   _p(out), _p(ws), nbytes, _precision(precision, C, HW), _stream()), "st3d_gram_backward")
     return out.reshape(feat.shape)
 
 

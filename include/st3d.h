@@ -38,6 +38,8 @@ typedef void* st3d_stream_t; /* cudaStream_t */
 
 const char* st3d_last_error(void);
 int st3d_version(void);
+/* Number of kernels this library has launched in this process so far (all threads). */
+unsigned long long st3d_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Vertex transform: world -> view -> NDC with z kept as view depth.
@@ -174,11 +176,13 @@ int st3d_gram_mse_forward(const float* feat, const float* target, int B, int Bt,
                           float scale, float* gram, float* dgram, float* loss_out, void* workspace,
                           size_t workspace_bytes, int precision, st3d_stream_t stream);
 
-/* Backward of gram_matrix: grad_feat (B,C,HW) = grad_scale * (dG + dG^T) F; when accumulate != 0 the
- * result is added to grad_feat.  The workspace is the one sized by st3d_gram_workspace_size. */
+/* Backward of gram_matrix: grad_feat (B,C,HW) = s * (dG + dG^T) F with s = grad_scale, times the device
+ * scalar *grad_scale_dev when that pointer is not NULL (autograd's upstream gradient, applied without
+ * a host read); when accumulate != 0 the result is added to grad_feat.  The workspace is the one sized
+ * by st3d_gram_workspace_size. */
 int st3d_gram_backward(const float* feat, const float* dgram, int B, int C, int64_t HW, float grad_scale,
-                       int accumulate, float* grad_feat, void* workspace, size_t workspace_bytes,
-                       int precision, st3d_stream_t stream);
+                       const float* grad_scale_dev, int accumulate, float* grad_feat, void* workspace,
+                       size_t workspace_bytes, int precision, st3d_stream_t stream);
 
 /* mean((a-b)^2) family (losses.py:31 content loss; losses.py:71-75 masked MSE):
  * loss_out[0] += scale * sum(m*(a-b)^2); grad_a = 2*scale*m*(a-b) (NULL to skip).
