@@ -73,35 +73,79 @@ k_gram_simt(const float* __restrict__ feat, int C, int64_t HW, int splits, int64
 }
 
 // -------------------------------------------------------------------------------------------------
-// finalize: G = sum over splits (fixed order); optional gram / MSE-vs-target / dgram outputs
+// finalize: G = sum over splits (fixed order); optional gram / MSE-vs-target / dgram outputs.
+// A block is SP split-lanes x (256 / SP) element-lanes; an element-lane owns VEC consecutive elements.
+// Split-lane j adds splits j, j + SP, ... in order; lane 0 then adds the SP partial sums in order, so
+// the result does not depend on scheduling (deterministic split-K).
 // -------------------------------------------------------------------------------------------------
+template <int VEC>
 __global__ void __launch_bounds__(256)
-k_gram_finalize(const float* __restrict__ partials, int splits, int B, int Bt, int C,
+k_gram_finalize(const float* __restrict__ partials, int splits, int sp, int B, int Bt, int C,
                 const float* __restrict__ target, float scale, float* __restrict__ gram, float* __restrict__ dgram,
                 float* __restrict__ loss_out) {
+    __shared__ float s_acc[256 * VEC];
+    __shared__ float s_part[8];
     const int64_t cc = (int64_t)C * C, total = (int64_t)B * cc;
-    float acc = 0.0f;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t b = i / cc, e = i % cc;
+    const int lanes = 256 / sp;
+    const int lane = threadIdx.x % lanes, sl = threadIdx.x / lanes;
+    const int64_t e0 = ((int64_t)blockIdx.x * lanes + lane) * VEC;  // first element of this lane (VEC | cc)
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.0f;
+    const bool in_range = e0 < total;
+    int64_t b = 0, e = 0;
+    if (in_range) {
+        b = e0 / cc;
+        e = e0 % cc;
         const float* p = partials + b * splits * cc + e;
-        float g = 0.0f;
-        for (int s = 0; s < splits; ++s) g += p[(int64_t)s * cc];
-        if (gram) gram[i] = g;
+        for (int s = sl; s < splits; s += sp) {
+            if (VEC == 4) {
+                const float4 t = *reinterpret_cast<const float4*>(p + (int64_t)s * cc);
+                acc[0] += t.x; acc[1 % VEC] += t.y; acc[2 % VEC] += t.z; acc[3 % VEC] += t.w;
+            } else {
+                acc[0] += p[(int64_t)s * cc];
+            }
+        }
+    }
+    if (sp > 1) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) s_acc[threadIdx.x * VEC + v] = acc[v];
+        __syncthreads();
+        if (sl == 0)
+            for (int j = 1; j < sp; ++j)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) acc[v] += s_acc[(j * lanes + lane) * VEC + v];
+    }
+    float lsum = 0.0f;
+    if (in_range && sl == 0) {
+        float d[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) d[v] = 0.0f;
         if (target) {
-            const float d = g - target[(Bt == 1 ? 0 : b) * cc + e];
-            acc += d * d;
-            if (dgram) dgram[i] = 2.0f * scale * d;
+            const float* tg = target + (Bt == 1 ? 0 : b) * cc + e;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                d[v] = acc[v] - tg[v];
+                lsum += d[v] * d[v];
+                d[v] *= 2.0f * scale;
+            }
+        }
+        if (VEC == 4) {
+            if (gram) *reinterpret_cast<float4*>(gram + e0) = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
+            if (target && dgram) *reinterpret_cast<float4*>(dgram + e0) = make_float4(d[0], d[1 % VEC], d[2 % VEC], d[3 % VEC]);
+        } else {
+            if (gram) gram[e0] = acc[0];
+            if (target && dgram) dgram[e0] = d[0];
         }
     }
     if (!target || !loss_out) return;
-    __shared__ float s_part[8];
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    lsum = warp_sum(lsum);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = lsum;
     __syncthreads();
     if (threadIdx.x < 32) {
         float v = threadIdx.x < 8 ? s_part[threadIdx.x] : 0.0f;
         v = warp_sum(v);
-        if (threadIdx.x == 0) atomicAdd(loss_out, v * scale);
+        if (threadIdx.x == 0 && v != 0.0f) atomicAdd(loss_out, v * scale);
     }
 }
 
@@ -224,8 +268,16 @@ extern "C" int st3d_gram_mse_forward(const float* feat, const float* target, int
     rc = gram_partials(feat, p, precision, s);
     if (rc != ST3D_OK) return rc;
     const int64_t total = (int64_t)B * C * C;
-    const int grid = (int)std::min<int64_t>(cdiv(total, 256), 148 * 4);
-    k_gram_finalize<<<grid, 256, 0, s>>>(p.partials, p.splits, B, Bt, C, target, scale, gram, dgram, loss_out);
+    const int sp = p.splits >= 8 ? 8 : (p.splits >= 4 ? 4 : (p.splits >= 2 ? 2 : 1));
+    const int lanes = 256 / sp;
+    const bool vec = ((int64_t)C * C) % 4 == 0 &&
+                     ((((uintptr_t)gram) | ((uintptr_t)dgram) | ((uintptr_t)target) | ((uintptr_t)p.partials)) & 15) == 0;
+    if (vec)
+        k_gram_finalize<4><<<cdiv(total, (int64_t)lanes * 4), 256, 0, s>>>(p.partials, p.splits, sp, B, Bt, C, target,
+                                                                         scale, gram, dgram, loss_out);
+    else
+        k_gram_finalize<1><<<cdiv(total, lanes), 256, 0, s>>>(p.partials, p.splits, sp, B, Bt, C, target, scale, gram,
+                                                             dgram, loss_out);
     ST3D_LAUNCH_OK("k_gram_finalize");
     return ST3D_OK;
 }

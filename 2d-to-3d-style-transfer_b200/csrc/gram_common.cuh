@@ -25,8 +25,10 @@ static inline GramPlan gram_plan(void* base, int B, int C, int64_t HW, int ctas_
     p.HW = HW;
     const int64_t kblocks = (HW + 31) / 32;
     int64_t want = 148 / ((int64_t)B * ctas_per_image_unsplit);
+    // a CTA flushes a (128 x C) partial tile per split: give it at least 16 k-blocks to amortise that
+    const int64_t min_kb = 16;
+    if (want > kblocks / min_kb) want = kblocks / min_kb;
     if (want < 1) want = 1;
-    if (want > kblocks) want = kblocks;
     const int64_t per = (kblocks + want - 1) / want;  // k-blocks per split
     p.splits = (int)((kblocks + per - 1) / per);
     p.k_chunk = per * 32;

@@ -18,16 +18,20 @@ LAST_TAP = 28
 
 def get_features(image: torch.Tensor, model, layers=None, stop_after_last_tap: bool = True):
     """style_transfer.py:10-27.  Walks `model` (VGG-19 `.features`) and returns {layer name: activation}.
-    The reference keeps walking modules 29-36 whose outputs nobody reads; this stops after the last tap."""
+    The reference keeps walking modules 30-36 whose outputs nobody reads; this stops after the last tap
+    and the in-place ReLU that follows it (that ReLU rewrites the tapped tensor, so it is part of the tap)."""
     layers = VGG_TAPS if layers is None else layers
     last = max((int(k) for k in layers if str(k).isdigit()), default=None)
-    feats, x = {}, image
+    feats, x, done = {}, image, False
     for name, module in model._modules.items():
+        if done and not (isinstance(module, torch.nn.ReLU) and module.inplace):
+            break
         x = module(x)
+        if done:
+            break
         if name in layers:
             feats[layers[name]] = x
-        if stop_after_last_tap and last is not None and name == str(last):
-            break
+        done = stop_after_last_tap and last is not None and name == str(last)
     return feats
 
 

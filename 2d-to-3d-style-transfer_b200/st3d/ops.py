@@ -19,6 +19,51 @@ MAX_FACES_PER_PIXEL = 8
 WS_HEADER_INTS = 16
 
 
+# ------------------------------------------------------------------------------------------------
+# optional per-op CUDA-event timing (bench.py): events go on the launching stream, nothing synchronises
+# ------------------------------------------------------------------------------------------------
+_profile: Optional[list] = None
+
+
+def start_profile() -> None:
+    global _profile
+    _profile = []
+
+
+def stop_profile():
+    """Returns {(op, key): [ms, ...]} for every op call since start_profile(); synchronises once."""
+    global _profile
+    rec, _profile = _profile or [], None
+    torch.cuda.synchronize()
+    out: dict = {}
+    for name, key, e0, e1 in rec:
+        out.setdefault((name, key), []).append(e0.elapsed_time(e1))
+    return out
+
+
+class _timed:
+    def __init__(self, name, key=None):
+        self.name, self.key = name, key
+
+    def __enter__(self):
+        if _profile is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _profile is not None and exc[0] is None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _profile.append((self.name, self.key, self.e0, e1))
+        return False
+
+
+def launch_count() -> int:
+    """Kernels launched by libst3d in this process so far."""
+    return int(lib().st3d_launch_count())
+
+
 def _p(t: Optional[torch.Tensor]):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -263,7 +308,8 @@ def render_forward(spec: RenderSpec, verts, faces, R, T, *, face_uvs=None, textu
     nbytes = lib().st3d_render_workspace_size(N, V, F, H, W, cap)
     ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
     a.workspace, a.workspace_bytes, a.list_capacity = _p(ws), nbytes, cap
-    check(lib().st3d_render_forward(ctypes.byref(a), _stream()), "st3d_render_forward")
+    with _timed("render_forward", (N, H, W, F)):
+        check(lib().st3d_render_forward(ctypes.byref(a), _stream()), "st3d_render_forward")
     if N > 0:
         _watch_header(ws, key)
     return image, mask, p2f, RenderState(args=a, keep=keep + [image, mask, p2f], workspace=ws)
@@ -277,8 +323,9 @@ def render_backward(state: RenderState, grad_image, need_texture=True, need_vert
     g_tex = torch.zeros((a.Ht, a.Wt, 3), device=dev, dtype=torch.float32) if (need_texture and a.tex_mode == TEX_UV) else None
     g_verts = torch.zeros((a.V, 3), device=dev, dtype=torch.float32) if need_verts else None
     g_rgb = torch.zeros((a.V, 3), device=dev, dtype=torch.float32) if (need_verts_rgb and a.tex_mode == TEX_VERTEX) else None
-    check(lib().st3d_render_backward(ctypes.byref(a), _p(grad_image), _p(g_tex), _p(g_verts), _p(g_rgb), _stream()),
-          "st3d_render_backward")
+    with _timed("render_backward", (a.N, a.H, a.W, a.F)):
+        check(lib().st3d_render_backward(ctypes.byref(a), _p(grad_image), _p(g_tex), _p(g_verts), _p(g_rgb), _stream()),
+              "st3d_render_backward")
     return g_tex, g_verts, g_rgb
 
 
@@ -325,8 +372,9 @@ def gram_forward(feat, precision=None):
     if B == 0:
         return out
     ws, nbytes = _gram_ws(B, C, HW, f.device)
-    check(lib().st3d_gram_forward(_p(f), B, C, HW, _p(out), _p(ws), nbytes, _precision(precision, C, HW), _stream()),
-          "st3d_gram_forward")
+    with _timed("gram_forward", (B, C, HW)):
+        check(lib().st3d_gram_forward(_p(f), B, C, HW, _p(out), _p(ws), nbytes, _precision(precision, C, HW), _stream()),
+              "st3d_gram_forward")
     return out
 
 
@@ -342,9 +390,10 @@ def gram_mse_forward(feat, target, scale: float, loss_out, want_gram=False, prec
     dgram = torch.empty((B, C, C), device=f.device, dtype=torch.float32)
     gram = torch.empty((B, C, C), device=f.device, dtype=torch.float32) if want_gram else None
     ws, nbytes = _gram_ws(B, C, HW, f.device)
-    check(lib().st3d_gram_mse_forward(_p(f), _p(target), B, target.shape[0], C, HW, float(scale), _p(gram), _p(dgram),
-                                      _p(loss_out), _p(ws), nbytes, _precision(precision, C, HW), _stream()),
-          "st3d_gram_mse_forward")
+    with _timed("gram_mse_forward", (B, C, HW)):
+        check(lib().st3d_gram_mse_forward(_p(f), _p(target), B, target.shape[0], C, HW, float(scale), _p(gram), _p(dgram),
+                                          _p(loss_out), _p(ws), nbytes, _precision(precision, C, HW), _stream()),
+              "st3d_gram_mse_forward")
     return dgram, gram
 
 
@@ -359,8 +408,10 @@ def gram_backward(feat, dgram, grad_scale: float = 1.0, out=None, accumulate=Fal
     ws, nbytes = _gram_ws(B, C, HW, f.device)
     if scale_tensor is not None:
         scale_tensor = _cuda_f32("scale_tensor", scale_tensor).reshape(1)
-    check(lib().st3d_gram_backward(_p(f), _p(dgram), B, C, HW, float(grad_scale), _p(scale_tensor), int(accumulate),
-                                   _p(out), _p(ws), nbytes, _precision(precision, C, HW), _stream()), "st3d_gram_backward")
+    with _timed("gram_backward", (B, C, HW)):
+        check(lib().st3d_gram_backward(_p(f), _p(dgram), B, C, HW, float(grad_scale), _p(scale_tensor), int(accumulate),
+                                       _p(out), _p(ws), nbytes, _precision(precision, C, HW), _stream()),
+              "st3d_gram_backward")
     return out.reshape(feat.shape)
 
 
@@ -377,6 +428,7 @@ def mse_forward(a, b, scale: float, loss_out, mask=None, want_grad=True):
             raise ValueError("mask must be (B,1,H,W) for a (B,C,H,W) input")
         inner, mask_ch = a.shape[2] * a.shape[3], a.shape[1]
     grad = torch.empty_like(a) if want_grad else None
-    check(lib().st3d_mse_forward(_p(a), _p(b), _p(mask), a.numel(), inner, mask_ch, float(scale), _p(loss_out),
-                                 _p(grad), _stream()), "st3d_mse_forward")
+    with _timed("mse_forward", (a.numel(),)):
+        check(lib().st3d_mse_forward(_p(a), _p(b), _p(mask), a.numel(), inner, mask_ch, float(scale), _p(loss_out),
+                                     _p(grad), _stream()), "st3d_mse_forward")
     return grad

@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- style-optimisation iterations/sec on B200 (BASELINE.json metric, configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (libst3d kernels)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+One step = one optimisation iteration of second_approach.py:147-190 (`texture` target) over the views a
+rank holds: render content mesh -> render current mesh -> VGG-19 features (torch/cuDNN, out of scope but
+inside the timed step) -> content MSE + Gram style loss -> backward -> [NCCL all-reduce] -> Adam step.
+Weak scaling: every GPU holds `--views` (default 8) views at `--size`^2 (default 512); `value` is the
+whole-job throughput in 8-view-iteration equivalents per second (= iterations/sec at N = 1).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "2d-to-3d-style-transfer_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "style-opt iters/sec (render+loss fwd/bwd)"
+UNIT = "it/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="st3d", choices=["st3d", "reference"])
+    ap.add_argument("--views", type=int, default=8, help="views per GPU")
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the e2e / cached-constants legs")
+    ap.add_argument("--profile-run", action="store_true",
+                    help="for ncu captures only: honour --warmup < 3 (a number from such a run is never reported)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# workload (shared by both arms): cow mesh, synthetic style image, seeded random-init VGG-19
+# ------------------------------------------------------------------------------------------------
+def load_workload(size):
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    d = np.load(os.path.join(ROOT, "tests", "golden", "cow_mesh.npz"))
+    verts = torch.from_numpy(d["verts"]).float()
+    faces = torch.from_numpy(d["faces"]).long()
+    uvs = torch.from_numpy(d["verts_uvs"]).float()
+    fuvs = torch.from_numpy(d["faces_uvs"]).long()
+    tex = torch.from_numpy(d["texture"]).float() / 255.0
+    # first_approach.py:90-100 / second_approach.py: the texture is resized to size x size (bilinear)
+    tex = F.interpolate(tex.permute(2, 0, 1)[None], size=(size, size), mode="bilinear", align_corners=False)[0]
+    tex = tex.permute(1, 2, 0).contiguous()
+    g = torch.Generator().manual_seed(0)
+    low = torch.rand(1, 3, size // 16, size // 16, generator=g)
+    style = F.interpolate(low, size=(size, size), mode="bicubic", align_corners=False).clamp(0, 1).contiguous()
+    return dict(verts=verts, faces=faces, verts_uvs=uvs, faces_uvs=fuvs, texture=tex, style=style)
+
+
+def seeded_vgg():
+    import torch
+    import torchvision
+    torch.manual_seed(0)
+    vgg = torchvision.models.vgg19(weights=None).features.eval()
+    for p in vgg.parameters():
+        p.requires_grad_(False)
+    return vgg
+
+
+def cameras(n_total):
+    import torch
+    from st3d import cameras as cm
+    return cm.random_view_cameras(n_total, generator=torch.Generator().manual_seed(0))
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"cow_mesh texture optimisation, {args.views} views x {args.size}^2 per GPU (BASELINE configs[1])",
+        "views_per_gpu": args.views, "global_views": args.views * world, "image_size": args.size,
+        "faces": 5856, "verts": 2930, "texture": f"{args.size}x{args.size}x3", "target": "texture",
+        "style_weight": 1e6, "content_weight": 1, "lr": 0.01, "parallelism": f"view-sharded dp{world}",
+        "vgg": "torchvision VGG-19 .features, seeded random init (ImageNet weights unavailable offline), fp32 cuDNN "
+               "(torch default allow_tf32), inside the timed step",
+        "l2": "per-step working set (VGG activations of 8 x 512^2 images, > 4 GB) exceeds the 126 MB L2; no explicit flush",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's CPU path (oracle port; PyTorch3D itself is not installable here)
+# ------------------------------------------------------------------------------------------------
+def cpu_one_view_iterations(args, n_timed, n_warm):
+    """Times `n_timed` one-view optimisation iterations on the host cores; returns seconds per one-view step."""
+    import torch
+    from oracle import loss_oracle as lo
+    from oracle import render_oracle as ro
+    w = load_workload(args.size)
+    vgg = seeded_vgg()
+    R, T = cameras(args.views)
+    tex0 = w["texture"]
+    tex = tex0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([tex], lr=0.01)
+    threads = os.cpu_count() or 1
+    kw = dict(verts_uvs=w["verts_uvs"], faces_uvs=w["faces_uvs"], nthreads=threads)
+    times = []
+    for i in range(n_warm + n_timed):
+        v = i % args.views
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        with torch.no_grad():
+            content, _ = ro.images_and_masks(ro.render_views(w["verts"], w["faces"], R[v:v + 1], T[v:v + 1], args.size,
+                                                             texture=tex0, **kw))
+        current, _ = ro.images_and_masks(ro.render_views(w["verts"], w["faces"], R[v:v + 1], T[v:v + 1], args.size,
+                                                         texture=tex, **kw))
+        loss = lo.perceptual_loss(current, content, w["style"], vgg, 1e6, 1.0)
+        loss.backward()
+        opt.step()
+        float(loss)
+        if i >= n_warm:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), threads
+
+
+def cpu_baseline_dict(args, sec_per_view, threads, n_timed):
+    return {"value": 1.0 / (sec_per_view * args.views), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n_timed} one-view iterations at {args.size}^2 (1 of {args.views} views per step); an "
+                      f"{args.views}-view iteration costs {args.views}x (every stage is per-view); CPU restatement of the "
+                      "PyTorch3D path (library unavailable) + the reference's loss arithmetic, all host threads",
+            "sec_per_view_iteration": sec_per_view}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sec, threads = cpu_one_view_iterations(args, max(args.steps, 1), max(args.warmup, 0))
+    value = 1.0 / (sec * args.views)
+    cb = cpu_baseline_dict(args, sec, threads, args.steps)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * args.views * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "cow mesh fixture + synthetic style image + random-init VGG-19",
+        "config": workload_config(args, 1), "cpu_baseline": cb,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(op, key, tex=512):
+    """SURVEY.md section 8(d) / DESIGN.md: bytes one call of `op` must move."""
+    if op == "render_forward":      # face records + (pix_to_face i32, rgb, mask) per pixel + texture once
+        N, H, W, F = key
+        return N * F * 36 + N * H * W * (4 + 16) + tex * tex * 12
+    if op == "render_backward":     # grad rgb + saved pix_to_face per pixel + face records + grad_texture
+        N, H, W, F = key
+        return N * H * W * (12 + 4) + N * F * 48 + tex * tex * 12
+    if op == "gram_backward":       # read F, write dF
+        B, C, HW = key
+        return 2 * B * C * HW * 4
+    if op in ("gram_forward", "gram_mse_forward"):   # read F, write G (+dG)
+        B, C, HW = key
+        return B * C * HW * 4 + B * C * C * 4
+    if op == "mse_forward":         # read a, b, write grad
+        return 3 * key[0] * 4
+    return None
+
+
+def run_st3d(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import st3d
+    from st3d import ops
+    from st3d.optimize import TextureStyleOptimizer
+
+    w = load_workload(args.size)
+    vgg = seeded_vgg().to(dev)
+    R_all, T_all = cameras(args.views * world)
+    sl = slice(rank * args.views, (rank + 1) * args.views)
+    R, T = R_all[sl].contiguous().to(dev), T_all[sl].contiguous().to(dev)
+    style = w["style"].to(dev)
+
+    def make(cache):
+        return TextureStyleOptimizer(w["verts"].to(dev), w["faces"].to(dev), w["verts_uvs"].to(dev),
+                                     w["faces_uvs"].to(dev), w["texture"].to(dev), vgg, args.size, lr=0.01,
+                                     precision=args.precision, cache_constants=cache, world_size=world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timed region --------------------------------------------------------------
+    opt = make(False)
+    warm = args.warmup if args.profile_run else max(args.warmup, 3)
+    for _ in range(warm):
+        opt.step(R, T, style)
+    ops.poll_overflow(block=True)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = ops.launch_count()
+    ops.start_profile()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = opt.step(R, T, style)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    prof = ops.stop_profile()
+    launches = ops.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    ops.poll_overflow(block=True)
+    ms_step = ms_total / args.steps
+    value = world / (ms_step * 1e-3)          # 8-view-iteration equivalents per second over all ranks
+    final_loss = float(loss)
+
+    # per-op breakdown (rank 0)
+    stages, mine_ms = {}, 0.0
+    for (op, key), v in sorted(prof.items()):
+        per_step = sum(v) / args.steps
+        mine_ms += per_step
+        name = op + ("" if key is None else "_" + "x".join(str(k) for k in key))
+        stages[name] = round(per_step, 4)
+    # dominant kernel -> roofline
+    dom = max(((op, key, sum(v) / len(v)) for (op, key), v in prof.items() if algorithmic_bytes(op, key)),
+              key=lambda t: t[2] * len(prof[(t[0], t[1])]), default=None)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except OSError:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    roofline = None
+    if dom:
+        op, key, avg_ms = dom
+        nbytes = algorithmic_bytes(op, key)
+        ach = nbytes / (avg_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                    "traffic": None, "kernel": f"{op} {key}",
+                    "algorithmic_bytes": nbytes, "avg_ms": avg_ms,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (Gram products tf32 on tcgen05, fp32 accumulate)" if args.precision == "tf32" else "f32",
+        "data": "cow mesh fixture (reference objects/cow_mesh) + synthetic style image + seeded random-init VGG-19",
+        "config": workload_config(args, world), "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roofline, "final_loss": final_loss,
+        "stages_ms_per_step": stages,
+        "render_loss_only": {"ms_per_step": mine_ms, "it_per_s": (world / (mine_ms * 1e-3)) if mine_ms > 0 else None,
+                             "note": "sum of libst3d op times (CUDA events) per step; VGG-19 / Adam / autograd glue excluded"},
+    }
+
+    if not args.no_extras:
+        # ---- end-to-end: host buffers in, loss + rendered views out, every step --------------------------
+        opt2 = make(False)
+        h_style = w["style"].pin_memory()
+        h_R, h_T = R_all[sl].contiguous().pin_memory(), T_all[sl].contiguous().pin_memory()
+        h_img = torch.empty((args.views, 3, args.size, args.size), dtype=torch.float32).pin_memory()
+        d_style, d_R, d_T = torch.empty_like(style), torch.empty_like(R), torch.empty_like(T)
+
+        def e2e_step():
+            d_style.copy_(h_style, non_blocking=True)
+            d_R.copy_(h_R, non_blocking=True)
+            d_T.copy_(h_T, non_blocking=True)
+            l = opt2.step(d_R, d_T, d_style)
+            h_img.copy_(opt2.last_images, non_blocking=True)     # the reference dumps every view every step
+            return float(l)                                      # loss.item(): second_approach.py:190
+
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+        h2d = h_style.numel() * 4 + h_R.numel() * 4 + h_T.numel() * 4
+        d2h = h_img.numel() * 4 + 4
+        out["e2e"] = {"value": world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                      "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
+                      "api": "st3d.optimize.TextureStyleOptimizer.step(R, T, style) with pinned host inputs"}
+        # ---- variant: constant content/style features cached (loop hygiene the reference lacks) ---------
+        opt3 = make(True)
+        for _ in range(3):
+            opt3.step(R, T, style)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(args.steps):
+            opt3.step(R, T, style)
+        c1.record()
+        barrier()
+        cms = max_over_ranks(c0.elapsed_time(c1)) / args.steps
+        out["cached_constants"] = {"value": world / (cms * 1e-3), "unit": UNIT, "ms_per_step": cms,
+                                   "note": "content render + content/style VGG features computed once (they are "
+                                           "constants of the loop); not the headline"}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n = 2
+        sec, threads = cpu_one_view_iterations(args, n, 1)
+        out["cpu_baseline"] = cpu_baseline_dict(args, sec, threads, n)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        out["lib"] = st3d.library_path()
+        print(json.dumps(out))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_st3d(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,89 @@
+"""Host-side logic that needs no GPU: camera math, projection constants, the VGG feature walk and the
+view-sharded gradient all-reduce (gloo, world_size 2)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import loss_oracle as lo
+from oracle import render_oracle as ro
+
+
+def test_cameras_match_oracle():
+    from st3d import cameras as cm
+    for seed in (0, 3):
+        R, T = cm.random_view_cameras(6, generator=torch.Generator().manual_seed(seed))
+        R2, T2 = ro.random_cameras(6, generator=torch.Generator().manual_seed(seed))
+        assert torch.equal(R, R2) and torch.equal(T, T2)
+    for axis in "XYZ":
+        assert torch.equal(cm.rotate_axis_angle_matrix(37.0, axis)[0, :3, :3], ro.rotate_axis_angle_R(37.0, axis))
+    R, T = cm.look_at_view_transform(2.7, 90.0, 10.0)       # looking straight down: degenerate x axis branch
+    R2, T2 = ro.look_at_view_transform(2.7, 90.0, 10.0)
+    assert torch.allclose(R, R2) and torch.allclose(T, T2)
+    assert torch.allclose(R[0] @ R[0].t(), torch.eye(3), atol=1e-6)
+
+
+def test_fov_scales_bit_identical():
+    from st3d.functional import fov_scales
+    for fov in (60.0, 45.0, 90.0):
+        assert fov_scales(fov) == ro.fov_scales(fov)
+
+
+def test_get_features_walk():
+    import torchvision
+    from st3d import losses
+    torch.manual_seed(0)
+    vgg = torchvision.models.vgg19(weights=None).features.eval()
+    x = torch.rand(1, 3, 32, 32)
+    with torch.no_grad():
+        a = losses.get_features(x, vgg)
+        b = lo.get_features(x.clone(), vgg)
+    assert list(a) == list(b) == ["conv1_1", "conv2_1", "conv3_1", "conv4_1", "conv4_2", "conv5_1"]
+    for k in a:
+        assert torch.equal(a[k], b[k])
+        assert (a[k] >= 0).all()                 # in-place ReLU: every tap is post-ReLU
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from st3d.optimize import allreduce_gradients
+    tex = torch.zeros(4, 4, 3, requires_grad=True)
+    verts = torch.zeros(5, 3, requires_grad=True)
+    unused = torch.zeros(2, requires_grad=True)
+    # per-rank "view shard" gradients: the sharded result must equal the sum over shards
+    g = torch.Generator().manual_seed(100 + rank)
+    tex.grad = torch.rand(4, 4, 3, generator=g)
+    verts.grad = torch.rand(5, 3, generator=g)
+    allreduce_gradients([tex, verts, unused])
+    q.put((rank, tex.grad.clone(), verts.grad.clone(), unused.grad is None))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_view_sharded_gradient_allreduce_gloo():
+    world, port = 2, 29641
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    want_tex = sum(torch.rand(4, 4, 3, generator=torch.Generator().manual_seed(100 + r)) for r in range(world))
+    for rank, tex, verts, unused_none in out:
+        assert torch.allclose(tex, want_tex) and unused_none
+    assert torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
+
+
+def test_allreduce_is_noop_single_process():
+    from st3d.optimize import allreduce_gradients
+    p = torch.ones(3, requires_grad=True)
+    p.grad = torch.full((3,), 2.0)
+    allreduce_gradients([p])
+    assert torch.equal(p.grad, torch.full((3,), 2.0))
