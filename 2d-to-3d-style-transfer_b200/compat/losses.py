@@ -1,0 +1,61 @@
+"""Drop-in for the reference's losses.py (same names, same arguments); the image-space and feature-space
+reductions and their backward passes run in libst3d kernels.
+
+    compute_perceptual_loss        losses.py:12-44
+    rgb_range_loss                 losses.py:48-51   (unused by the scripts)
+    compute_tv_loss                losses.py:55-65   (unused by the scripts)
+    compute_first_approach_loss    losses.py:68-98
+    compute_second_approach_loss   losses.py:101-126
+"""
+import torch
+from pytorch3d.loss import mesh_edge_loss, mesh_laplacian_smoothing, mesh_normal_consistency
+
+from st3d import functional as _fn
+from st3d import losses as _losses
+from style_transfer import *  # noqa: F401,F403  (the reference re-exports these names too)
+
+device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+
+
+def compute_perceptual_loss(current_imgs, content_imgs, style_imgs, model, style_weight=1e6, content_weight=1):
+    assert current_imgs.shape[0] == content_imgs.shape[0] == style_imgs.shape[0]
+    return _losses.compute_perceptual_loss(current_imgs, content_imgs, style_imgs, model, style_weight, content_weight)
+
+
+def rgb_range_loss(mesh):
+    texture = mesh.textures.maps_padded()
+    return (torch.relu(texture - 1) + torch.relu(-texture)).sum()
+
+
+def compute_tv_loss(images, masks):
+    dh = (images[..., :-1, :] - images[..., 1:, :]).abs() * (masks[..., :-1, :] * masks[..., 1:, :])
+    dw = (images[..., :, :-1] - images[..., :, 1:]).abs() * (masks[..., :, :-1] * masks[..., :, 1:])
+    return (dh.sum() + dw.sum()) / masks.sum()
+
+
+def _geometry_terms(verts, target_verts, mesh, weights):
+    """The regularisers shared by the `mesh` and `both` targets (losses.py:84-87, 113-115)."""
+    return (weights["mesh_verts_weight"] * _fn.mse_loss(verts, target_verts)
+            + weights["mesh_edge_loss_weight"] * mesh_edge_loss(mesh)
+            + weights["mesh_laplacian_smoothing_weight"] * mesh_laplacian_smoothing(mesh)
+            + weights["mesh_normal_consistency_weight"] * mesh_normal_consistency(mesh))
+
+
+def compute_first_approach_loss(rendered, masks, target_rendered, verts, target_verts, mesh, weights, opt_type):
+    image_term = _fn.masked_mse_loss(rendered, target_rendered, masks)
+    if opt_type == "texture":
+        return image_term
+    if opt_type in ("mesh", "both"):
+        return weights["main_loss_weight"] * image_term + _geometry_terms(verts, target_verts, mesh, weights)
+    raise ValueError(f"unknown optimisation target {opt_type!r}")
+
+
+def compute_second_approach_loss(current, content, style, model, style_weight, content_weight, verts, target_verts,
+                                 mesh, weights, opt_type):
+    perceptual = compute_perceptual_loss(current, content, style, model, style_weight=style_weight,
+                                         content_weight=content_weight)
+    if opt_type == "texture":
+        return perceptual
+    if opt_type in ("mesh", "both"):
+        return weights["main_loss_weight"] * perceptual + _geometry_terms(verts, target_verts, mesh, weights)
+    raise ValueError(f"unknown optimisation target {opt_type!r}")

@@ -1,0 +1,312 @@
+"""Renderer surface used by the reference (first_approach.py:106-114, utils.py:69, 149, 168, 208):
+cameras, rasterization settings, rasterizer, shader, renderer, textures.
+
+`MeshRenderer(...)(meshes_world=, cameras=)` runs the FUSED libst3d path (vertex transform -> tile bins
+-> fine raster -> texture sample -> ambient shade -> soft blend in one launch sequence) for every camera
+passed, whether that is one camera (the reference's per-view loop, utils.py:68-69) or a whole batch.
+`MeshRasterizer(...)(meshes)` alone returns Fragments through the operator-boundary kernels.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import NamedTuple, Optional, Sequence, Union
+
+import torch
+
+from st3d import cameras as _cam
+from st3d import functional as _fn
+
+from ..structures import Meshes
+from .cameras import FoVPerspectiveCameras, look_at_view_transform  # noqa: F401  (re-exported)
+
+
+# ------------------------------------------------------------------------------------------------
+# textures
+# ------------------------------------------------------------------------------------------------
+def _stack(x, name):
+    if isinstance(x, (list, tuple)):
+        if len(x) != 1:
+            raise NotImplementedError(f"{name}: one mesh per batch (views are batched, not meshes)")
+        return x[0][None]
+    return x
+
+
+class TexturesUV:
+    """maps (N,H,W,C), faces_uvs (N,F,3) int64, verts_uvs (N,V,2); bilinear, border padding,
+    align_corners=True, v flipped.  `maps_padded()` returns the tensor that was passed in,
+    so a leaf texture keeps receiving gradients (utils.py:177-185)."""
+
+    def __init__(self, maps, faces_uvs, verts_uvs, padding_mode: str = "border", align_corners: bool = True,
+                 sampling_mode: str = "bilinear"):
+        if (padding_mode, align_corners, sampling_mode) != ("border", True, "bilinear"):
+            raise NotImplementedError("TexturesUV: only bilinear / border / align_corners=True sampling is implemented")
+        self._maps = _stack(maps, "maps")
+        self._faces_uvs = _stack(faces_uvs, "faces_uvs")
+        self._verts_uvs = _stack(verts_uvs, "verts_uvs")
+        if self._maps.dim() != 4 or self._faces_uvs.dim() != 3 or self._verts_uvs.dim() != 3:
+            raise ValueError("TexturesUV expects maps (N,H,W,C), faces_uvs (N,F,3), verts_uvs (N,V,2)")
+        if not (self._maps.shape[0] == self._faces_uvs.shape[0] == self._verts_uvs.shape[0]):
+            raise ValueError("TexturesUV: batch sizes differ")
+        self.device = self._maps.device
+
+    def maps_padded(self):
+        return self._maps
+
+    def faces_uvs_padded(self):
+        return self._faces_uvs
+
+    def verts_uvs_padded(self):
+        return self._verts_uvs
+
+    def maps_list(self):
+        return [m for m in self._maps]
+
+    def faces_verts_uvs(self):
+        """(F,3,2) per-face UVs of mesh 0."""
+        return self._verts_uvs[0][self._faces_uvs[0].long()]
+
+    def clone(self):
+        return TexturesUV(self._maps.clone(), self._faces_uvs.clone(), self._verts_uvs.clone())
+
+    def detach(self):
+        return TexturesUV(self._maps.detach(), self._faces_uvs.detach(), self._verts_uvs.detach())
+
+    def to(self, device):
+        return TexturesUV(self._maps.to(device), self._faces_uvs.to(device), self._verts_uvs.to(device))
+
+
+class TexturesVertex:
+    """verts_features (N,V,C): one colour per vertex, interpolated with the barycentrics."""
+
+    def __init__(self, verts_features):
+        self._feats = _stack(verts_features, "verts_features")
+        if self._feats.dim() != 3:
+            raise ValueError("TexturesVertex expects verts_features (N,V,C)")
+        self.device = self._feats.device
+
+    def verts_features_padded(self):
+        return self._feats
+
+    def verts_features_packed(self):
+        return self._feats[0]
+
+    def clone(self):
+        return TexturesVertex(self._feats.clone())
+
+    def detach(self):
+        return TexturesVertex(self._feats.detach())
+
+    def to(self, device):
+        return TexturesVertex(self._feats.to(device))
+
+
+# ------------------------------------------------------------------------------------------------
+# settings, lights, materials, blending
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class RasterizationSettings:
+    image_size: Union[int, Sequence[int]] = 256
+    blur_radius: float = 0.0
+    faces_per_pixel: int = 1
+    bin_size: Optional[int] = None            # accepted, unused: libst3d bins into 16x16 tiles with exact lists
+    max_faces_per_bin: Optional[int] = None   # accepted, unused: no fixed per-bin capacity, no dropped faces
+    perspective_correct: Optional[bool] = None
+    clip_barycentric_coords: Optional[bool] = None
+    cull_backfaces: bool = False
+    z_clip_value: Optional[float] = None
+    cull_to_frustum: bool = False
+
+
+@dataclass
+class BlendParams:
+    sigma: float = 1e-4
+    gamma: float = 1e-4
+    background_color: Sequence[float] = (1.0, 1.0, 1.0)
+
+
+def _color(c):
+    t = torch.as_tensor(c, dtype=torch.float32).reshape(-1)
+    if t.numel() != 3:
+        raise ValueError("colours are RGB triples")
+    return tuple(float(v) for v in t)
+
+
+class Materials:
+    def __init__(self, ambient_color=((1, 1, 1),), diffuse_color=((1, 1, 1),), specular_color=((1, 1, 1),),
+                 shininess=64, device="cpu"):
+        self.ambient_color, self.diffuse_color = _color(ambient_color), _color(diffuse_color)
+        self.specular_color, self.shininess, self.device = _color(specular_color), float(shininess), device
+
+
+class AmbientLights:
+    """Ambient-only lighting: diffuse = specular = 0, so pixel colour = ambient * texel (A.5)."""
+
+    def __init__(self, ambient_color=((1.0, 1.0, 1.0),), device="cpu"):
+        self.ambient_color, self.device = _color(ambient_color), device
+
+    def to(self, device):
+        self.device = device
+        return self
+
+
+class _DirectionalOrPoint:
+    def __init__(self, *a, **k):
+        raise NotImplementedError(f"{type(self).__name__}: only AmbientLights (the reference's lighting, "
+                                  "first_approach.py:108) is implemented by the fused libst3d shader")
+
+
+class PointLights(_DirectionalOrPoint):
+    pass
+
+
+class DirectionalLights(_DirectionalOrPoint):
+    pass
+
+
+class Fragments(NamedTuple):
+    pix_to_face: torch.Tensor
+    zbuf: torch.Tensor
+    bary_coords: torch.Tensor
+    dists: torch.Tensor
+
+
+# ------------------------------------------------------------------------------------------------
+# rasterizer / shader / renderer
+# ------------------------------------------------------------------------------------------------
+def _image_hw(size):
+    return (int(size), int(size)) if isinstance(size, int) else (int(size[0]), int(size[1]))
+
+
+def _one_mesh(meshes: Meshes):
+    if not isinstance(meshes, Meshes):
+        raise ValueError("meshes_world must be a pytorch3d.structures.Meshes")
+    if len(meshes) != 1:
+        raise NotImplementedError("one mesh per call: libst3d batches camera VIEWS of a single mesh")
+    verts, faces = meshes.verts_packed(), meshes.faces_packed()
+    if not verts.is_cuda:
+        raise RuntimeError("this renderer runs on CUDA only (libst3d has no CPU path): move the mesh to a cuda device")
+    return verts, faces
+
+
+def _camera_params(cameras):
+    if cameras is None:
+        raise ValueError("cameras must be given to the rasterizer / renderer, at construction or per call")
+    if isinstance(cameras, (list, tuple)):
+        cameras = FoVPerspectiveCameras.join(cameras)
+    if not isinstance(cameras, FoVPerspectiveCameras):
+        raise NotImplementedError("only FoVPerspectiveCameras is implemented")
+    return cameras, cameras.uniform_intrinsics()
+
+
+class MeshRasterizer(torch.nn.Module):
+    def __init__(self, cameras=None, raster_settings: Optional[RasterizationSettings] = None):
+        super().__init__()
+        self.cameras = cameras
+        self.raster_settings = raster_settings if raster_settings is not None else RasterizationSettings()
+
+    def to(self, device):
+        if self.cameras is not None:
+            self.cameras = self.cameras.to(device)
+        return self
+
+    def _settings(self, kwargs):
+        return kwargs.get("raster_settings", self.raster_settings)
+
+    def forward(self, meshes_world, **kwargs) -> Fragments:
+        cams, (fov, aspect, znear, zfar) = _camera_params(kwargs.get("cameras", self.cameras))
+        rs = self._settings(kwargs)
+        if rs.cull_to_frustum:
+            raise NotImplementedError("cull_to_frustum is not implemented")
+        verts, faces = _one_mesh(meshes_world)
+        R, T = cams.R.to(verts.device), cams.T.to(verts.device)
+        N, Fn = R.shape[0], faces.shape[0]
+        ndc = _fn.transform_verts(verts, R, T, fov, aspect, znear)                    # (N,V,3)
+        z_clip = rs.z_clip_value if rs.z_clip_value is not None else znear / 2.0
+        if bool((ndc[..., 2].detach() < z_clip).any()):
+            raise NotImplementedError("a vertex lies in front of the near clipping plane (z < znear / 2): "
+                                      "near-plane face clipping is not implemented")
+        face_verts = ndc[:, faces.long()].reshape(N * Fn, 3, 3)
+        first = torch.arange(N, device=verts.device, dtype=torch.int64) * Fn
+        num = torch.full((N,), Fn, device=verts.device, dtype=torch.int64)
+        clip_bary = rs.clip_barycentric_coords if rs.clip_barycentric_coords is not None else rs.blur_radius > 0.0
+        persp = rs.perspective_correct if rs.perspective_correct is not None else True
+        p2f, zbuf, bary, dists = _fn.rasterize_meshes(face_verts, first, num, _image_hw(rs.image_size), rs.blur_radius,
+                                                      rs.faces_per_pixel, persp, clip_bary, rs.cull_backfaces)
+        return Fragments(p2f, zbuf, bary, dists)
+
+
+class SoftPhongShader(torch.nn.Module):
+    def __init__(self, device="cpu", cameras=None, lights=None, materials=None, blend_params=None):
+        super().__init__()
+        self.lights = lights if lights is not None else AmbientLights(device=device)
+        self.materials = materials if materials is not None else Materials(device=device)
+        self.cameras = cameras
+        self.blend_params = blend_params if blend_params is not None else BlendParams()
+
+    def to(self, device):
+        return self
+
+    def forward(self, fragments, meshes, **kwargs):
+        raise NotImplementedError("SoftPhongShader is fused into the rasterizer epilogue: call it through "
+                                  "MeshRenderer(rasterizer, shader)(meshes_world=..., cameras=...)")
+
+
+class MeshRenderer(torch.nn.Module):
+    """renderer(meshes_world=mesh, cameras=camera) -> (N,H,W,4) RGBA, N = number of cameras."""
+
+    def __init__(self, rasterizer: MeshRasterizer, shader: SoftPhongShader):
+        super().__init__()
+        self.rasterizer, self.shader = rasterizer, shader
+
+    def to(self, device):
+        self.rasterizer.to(device)
+        return self
+
+    def _fused_args(self, meshes_world, kwargs):
+        cams, (fov, aspect, znear, zfar) = _camera_params(kwargs.get("cameras", self.rasterizer.cameras))
+        rs = kwargs.get("raster_settings", self.rasterizer.raster_settings)
+        lights = kwargs.get("lights", self.shader.lights)
+        materials = kwargs.get("materials", self.shader.materials)
+        blend = kwargs.get("blend_params", self.shader.blend_params)
+        if not isinstance(lights, AmbientLights):
+            raise NotImplementedError("only AmbientLights is implemented by the fused shader")
+        if rs.faces_per_pixel != 1:
+            raise NotImplementedError("the fused renderer implements faces_per_pixel=1 (what the reference uses); "
+                                      "use MeshRasterizer for K > 1 fragments")
+        if rs.cull_to_frustum or (rs.perspective_correct is False):
+            raise NotImplementedError("cull_to_frustum / perspective_correct=False are not implemented in the fused path")
+        verts, faces = _one_mesh(meshes_world)
+        tex = meshes_world.textures
+        ambient = tuple(l * m for l, m in zip(lights.ambient_color, materials.ambient_color))
+        common = dict(fov=fov, aspect=aspect, znear=znear, zfar=zfar, blur_radius=rs.blur_radius,
+                      cull_backfaces=rs.cull_backfaces, ambient=ambient, background=_color(blend.background_color),
+                      sigma=blend.sigma, gamma=blend.gamma,
+                      z_clip=rs.z_clip_value if rs.z_clip_value is not None else znear / 2.0)
+        R, T = cams.R.to(verts.device).float(), cams.T.to(verts.device).float()
+        if isinstance(tex, TexturesUV):
+            maps = tex.maps_padded()
+            if maps.shape[0] != 1 or maps.shape[-1] != 3:
+                raise NotImplementedError("one RGB texture map per mesh")
+            tex_kw = dict(texture=maps, face_uvs=tex.faces_verts_uvs())
+        elif isinstance(tex, TexturesVertex):
+            tex_kw = dict(verts_rgb=tex.verts_features_packed())
+        else:
+            raise ValueError("meshes_world.textures must be TexturesUV or TexturesVertex")
+        return verts, faces, R, T, _image_hw(rs.image_size), tex_kw, common
+
+    def forward(self, meshes_world, **kwargs):
+        verts, faces, R, T, size, tex_kw, common = self._fused_args(meshes_world, kwargs)
+        rgba, _ = _fn.render_views(verts, faces, R, T, size, planar=False, **tex_kw, **common)
+        return rgba
+
+    def render_planar(self, meshes_world, **kwargs):
+        """Batched fast path used by this repo's `utils.render_meshes`: ((N,3,H,W) images, (N,1,H,W) masks)
+        straight from the kernel epilogue -- no permute / compare / stack passes."""
+        verts, faces, R, T, size, tex_kw, common = self._fused_args(meshes_world, kwargs)
+        images, masks, _ = _fn.render_views(verts, faces, R, T, size, planar=True, **tex_kw, **common)
+        return images, masks
+
+
+__all__ = ["FoVPerspectiveCameras", "look_at_view_transform", "TexturesUV", "TexturesVertex", "RasterizationSettings",
+           "BlendParams", "Materials", "AmbientLights", "PointLights", "DirectionalLights", "Fragments",
+           "MeshRasterizer", "SoftPhongShader", "MeshRenderer"]

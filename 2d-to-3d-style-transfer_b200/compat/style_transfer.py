@@ -1,0 +1,40 @@
+"""Drop-in for the reference's style_transfer.py (same names, same arguments), with the Gram products,
+the style MSE and the content MSE running in libst3d kernels.  VGG-19 stays on torch/cuDNN.
+
+    get_features    style_transfer.py:10-27
+    gram_matrix     style_transfer.py:31-35
+    style_transfer  style_transfer.py:38-84   (2D neural style transfer of a batch of images)
+"""
+import torch
+from tqdm import tqdm
+
+from st3d import functional as _fn
+from st3d import losses as _losses
+
+device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+
+
+def get_features(image, model, layers=None):
+    return _losses.get_features(image, model, layers)
+
+
+def gram_matrix(tensor):
+    return _fn.gram_matrix(tensor)
+
+
+def style_transfer(initial_optimized_imgs, content_imgs, style_imgs, model, steps=2000, style_weight=1e6,
+                   content_weight=1, lr=0.003):
+    assert initial_optimized_imgs.shape[0] == content_imgs.shape[0] == style_imgs.shape[0]
+    # constants of the loop: content features and style Grams (one Gram per image, as in the reference)
+    with torch.no_grad():
+        content_feat = _losses.get_features(content_imgs, model, {"21": _losses.CONTENT_LAYER})[_losses.CONTENT_LAYER]
+    grams = _losses.style_targets(style_imgs, model)
+    images = initial_optimized_imgs.clone().detach().to(device).requires_grad_(True)
+    optimizer = torch.optim.Adam([images], lr=lr)
+    for _ in tqdm(range(steps), desc="2D Style Transfer"):
+        feats = _losses.get_features(images, model)
+        loss = _losses.perceptual_loss_from_features(feats, content_feat, grams, style_weight, content_weight)
+        optimizer.zero_grad()
+        loss.backward()
+        optimizer.step()
+    return images

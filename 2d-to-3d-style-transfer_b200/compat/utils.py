@@ -1,0 +1,115 @@
+"""Drop-in for the reference's utils.py (same names, same arguments).  `render_meshes` renders ALL the
+cameras it is given in one fused libst3d launch sequence instead of one renderer call per view
+(utils.py:65-77); everything else is setup / I/O glue around the hot path."""
+import os
+import random
+
+import torch
+from PIL import Image
+from pytorch3d.renderer import FoVPerspectiveCameras, TexturesUV
+from pytorch3d.renderer.cameras import look_at_view_transform
+from pytorch3d.structures import Meshes
+from pytorch3d.transforms import RotateAxisAngle
+from torchvision import models, transforms
+
+from style_transfer import *  # noqa: F401,F403
+
+device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+
+
+def apply_background(tensors, masks, background_type="noise", background=None):
+    """utils.py:19-30: composite the render over fresh uniform noise / the style image / nothing."""
+    if background_type == "white":
+        return tensors                      # the shader's background is already white
+    if background_type == "noise":
+        fill = torch.rand(tensors.shape, device=tensors.device)
+    elif background_type == "style":
+        fill = background
+    else:
+        return None
+    return tensors * masks + fill * (1 - masks)
+
+
+def load_as_tensor(image_path, size=512):
+    """utils.py:34-44: RGB image squashed to size x size, (3,size,size) in [0,1]."""
+    with Image.open(image_path) as im:
+        im = im.convert("RGB")
+        tensor = transforms.ToTensor()(transforms.Resize((size, size))(im))
+    return tensor[:3].to(device)
+
+
+def get_vgg():
+    """utils.py:48-52: frozen VGG-19 `.features` with ImageNet weights."""
+    vgg = models.vgg19(weights=models.VGG19_Weights.IMAGENET1K_V1).features.to(device)
+    for p in vgg.parameters():
+        p.requires_grad_(False)
+    return vgg
+
+
+def tensor_to_image(tensor):
+    return transforms.ToPILImage()(tensor.detach().clone().squeeze(0).clamp(0, 1).cpu())
+
+
+def render_meshes(renderer, meshes, cameras):
+    """-> ((B,3,H,W) images, (B,1,H,W) masks).  `cameras` is a list of camera objects or a camera batch."""
+    if not isinstance(cameras, FoVPerspectiveCameras):
+        cameras = FoVPerspectiveCameras.join(list(cameras))
+    return renderer.render_planar(meshes, cameras=cameras)
+
+
+def save_render(renderer, meshes, cameras, path):
+    os.makedirs(path, exist_ok=True)
+    tensors, _ = render_meshes(renderer, meshes, cameras)
+    for i, t in enumerate(tensors):
+        tensor_to_image(t).save(f"{path}/view_{i}.png")
+
+
+def finalize_tensor(tensor):
+    return tensor.clamp(0.0, 1.0).detach()
+
+
+def finalize_mesh(mesh):
+    """utils.py:94-113: same geometry, texture clamped to [0,1]."""
+    tex = mesh.textures
+    clamped = TexturesUV(verts_uvs=tex.verts_uvs_padded(), faces_uvs=tex.faces_uvs_padded(),
+                         maps=finalize_tensor(tex.maps_padded()))
+    return Meshes(verts=mesh.verts_padded(), faces=mesh.faces_padded(), textures=clamped)
+
+
+def build_fixed_cameras(n_views, dist=3.0, shuffle=True):
+    """utils.py:121-151: views on two great circles (about X, then about Y) at distance `dist`."""
+    n_x = n_views // 2
+    views = [(a.item(), "X") for a in torch.linspace(0, 315, n_x)]
+    views += [(a.item(), "Y") for a in torch.linspace(45, 315, n_views - n_x)]
+    if shuffle:
+        random.shuffle(views)
+    R = torch.stack([RotateAxisAngle(a, axis=ax, device=device).get_matrix()[0, :3, :3] for a, ax in views], dim=0)
+    T = torch.tensor([0.0, 0.0, dist], device=device).repeat(len(views), 1)
+    return FoVPerspectiveCameras(R=R, T=T, device=device)
+
+
+def build_random_cameras(n_views, dist=2.10):
+    """utils.py:154-170: uniform directions on the sphere (cos-elevation and azimuth uniform)."""
+    elev = torch.acos(torch.rand(n_views) * 2 - 1) * 180 / torch.pi - 90
+    azim = torch.rand(n_views) * 360 - 180
+    R, T = look_at_view_transform(dist=dist, elev=elev, azim=azim, at=((0, 0.10, 0.25),))
+    return FoVPerspectiveCameras(R=R, T=T, device=device)
+
+
+def setup_optimizations(optimization_target, mesh, lr):
+    """utils.py:173-204: clone the mesh, mark the chosen leaves, build Adam."""
+    work = mesh.clone()
+    leaves = {"texture_map": work.textures.maps_padded(), "verts": work.verts_packed()}
+    chosen = {"texture": ["texture_map"], "mesh": ["verts"], "both": ["verts", "texture_map"]}[optimization_target]
+    for name in chosen:
+        leaves[name].requires_grad_(True)
+    optimizer = torch.optim.Adam([leaves[name] for name in chosen], lr=lr)
+    return {"optimizable_mesh": work, "optimizer": optimizer, "texture_map": leaves["texture_map"],
+            "verts": leaves["verts"], "faces": work.faces_packed(),
+            "verts_uvs": work.textures.verts_uvs_padded(), "faces_uvs": work.textures.faces_uvs_padded()}
+
+
+def build_mesh(verts_uvs, faces_uvs, texture_map, verts, faces):
+    """utils.py:207-210."""
+    return Meshes(verts=[verts], faces=[faces],
+                  textures=TexturesUV(verts_uvs=verts_uvs, faces_uvs=faces_uvs, maps=texture_map))

@@ -67,8 +67,8 @@ template <bool GATHER>
 __global__ void k_setup(const float* __restrict__ face_verts, const float4* __restrict__ verts_ndc,
                         const int32_t* __restrict__ faces, const int64_t* __restrict__ first_idx,
                         const int64_t* __restrict__ num_faces, int64_t F_per_mesh, int64_t V, int H, int W,
-                        float blur_radius, int cull_backfaces, int TX, int TY, FaceRec* __restrict__ rec,
-                        int* __restrict__ tile_count) {
+                        float blur_radius, int cull_backfaces, int TX, int TY, float z_clip, FaceRec* __restrict__ rec,
+                        int* __restrict__ tile_count, int* __restrict__ hdr) {
     const int n = blockIdx.y;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t first = first_idx ? first_idx[n] : (int64_t)n * F_per_mesh;
@@ -86,6 +86,7 @@ __global__ void k_setup(const float* __restrict__ face_verts, const float4* __re
         const float* p = face_verts + 9 * f;
         v = FaceVerts{p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8]};
     }
+    if (fminf(v.z0, fminf(v.z1, v.z2)) < z_clip) hdr[4] = 1;  // would need near-plane clipping (A.2 clip_faces)
     const float area = edge_fn(v.x2, v.y2, v.x0, v.y0, v.x1, v.y1);
     bool valid = fabsf(area) > kEps;                       // also false for NaN
     if (cull_backfaces && area < 0.0f) valid = false;
@@ -457,16 +458,18 @@ k_fine_hard(const FaceRec* __restrict__ rec, const int* __restrict__ tile_count,
 // -------------------------------------------------------------------------------------------------
 static int run_bins(const RasterWs& ws, const float* face_verts, const int32_t* faces, const int64_t* first_idx,
                     const int64_t* num_faces, int N, int64_t F_per_mesh, int64_t V, int H, int W, float blur_radius,
-                    int cull_backfaces, bool gather, cudaStream_t s) {
+                    int cull_backfaces, bool gather, float z_clip, cudaStream_t s) {
     ST3D_CUDA_OK(cudaMemsetAsync(ws.hdr, 0, ws.zero_bytes, s));
     if (F_per_mesh > 0 && N > 0) {
         dim3 grid(cdiv(F_per_mesh, 256), N);
         if (gather)
             k_setup<true><<<grid, 256, 0, s>>>(nullptr, ws.verts_ndc, faces, first_idx, num_faces, F_per_mesh, V, H, W,
-                                               blur_radius, cull_backfaces, ws.TX, ws.TY, ws.rec, ws.tile_count);
+                                               blur_radius, cull_backfaces, ws.TX, ws.TY, z_clip, ws.rec, ws.tile_count,
+                                               ws.hdr);
         else
             k_setup<false><<<grid, 256, 0, s>>>(face_verts, nullptr, nullptr, first_idx, num_faces, F_per_mesh, V, H, W,
-                                                blur_radius, cull_backfaces, ws.TX, ws.TY, ws.rec, ws.tile_count);
+                                                blur_radius, cull_backfaces, ws.TX, ws.TY, z_clip, ws.rec, ws.tile_count,
+                                               ws.hdr);
         ST3D_LAUNCH_OK("k_setup");
         k_alloc<<<cdiv(ws.NT, 256), 256, 0, s>>>(ws.tile_count, ws.tile_offset, ws.hdr, ws.NT);
         ST3D_LAUNCH_OK("k_alloc");
@@ -528,7 +531,7 @@ extern "C" int st3d_rasterize_meshes_forward(const float* face_verts, const int6
     const RasterWs ws = raster_ws_layout(workspace, N, F_total, H, W, cap, 0);
     cudaStream_t s = (cudaStream_t)stream;
     int rc = run_bins(ws, face_verts, nullptr, mesh_to_face_first_idx, num_faces_per_mesh, N, max_faces_in_mesh, 0, H, W,
-                      blur_radius, cull_backfaces, false, s);
+                      blur_radius, cull_backfaces, false, -INFINITY, s);
     if (rc != ST3D_OK) return rc;
     FragOut fo{pix_to_face, zbuf, bary, dists};
     ShadeParams sp{};
@@ -584,7 +587,7 @@ extern "C" int st3d_render_forward(const st3d_render_args* a, st3d_stream_t stre
                                                             nullptr);
     ST3D_LAUNCH_OK("k_transform");
     int rc = run_bins(ws, nullptr, a->faces, nullptr, nullptr, a->N, a->F, a->V, a->H, a->W, a->blur_radius,
-                      a->cull_backfaces, true, s);
+                      a->cull_backfaces, true, a->z_clip > 0.0f ? a->z_clip : -INFINITY, s);
     if (rc != ST3D_OK) return rc;
     const ShadeParams sp = make_shade_params(*a);
     FragOut fo{};

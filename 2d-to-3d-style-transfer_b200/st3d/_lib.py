@@ -29,7 +29,7 @@ class RenderArgs(ctypes.Structure):
         ("tex_mode", c_i), ("face_uvs", c_p), ("texture", c_p), ("Ht", c_i), ("Wt", c_i), ("verts_rgb", c_p),
         ("ambient", c_f * 3), ("background", c_f * 3), ("sigma", c_f), ("gamma", c_f),
         ("out_layout", c_i), ("out_image", c_p), ("out_mask", c_p), ("pix_to_face", c_p),
-        ("workspace", c_p), ("workspace_bytes", c_sz), ("list_capacity", c_i64),
+        ("workspace", c_p), ("workspace_bytes", c_sz), ("list_capacity", c_i64), ("z_clip", c_f),
     ]
 
 

@@ -64,7 +64,7 @@ def render_views(verts: torch.Tensor, faces: torch.Tensor, R: torch.Tensor, T: t
                  verts_rgb: Optional[torch.Tensor] = None, fov: float = 60.0, aspect: float = 1.0,
                  znear: float = 1.0, zfar: float = 100.0, blur_radius: float = 0.0, cull_backfaces: bool = False,
                  ambient: Sequence[float] = (1.0, 1.0, 1.0), background: Sequence[float] = (1.0, 1.0, 1.0),
-                 sigma: float = 1e-4, gamma: float = 1e-4, planar: bool = True):
+                 sigma: float = 1e-4, gamma: float = 1e-4, planar: bool = True, z_clip: Optional[float] = None):
     """Render N camera views of one mesh in one launch sequence (faces_per_pixel = 1, ambient light).
 
     planar=True  -> (images (N,3,H,W), masks (N,1,H,W), pix_to_face (N,H,W) int32): what
@@ -76,7 +76,7 @@ def render_views(verts: torch.Tensor, faces: torch.Tensor, R: torch.Tensor, T: t
     k00, k11 = fov_scales(fov, aspect, znear)
     spec = ops.RenderSpec(image_size=(H, W), k00=k00, k11=k11, znear=znear, zfar=zfar, blur_radius=blur_radius,
                           cull_backfaces=cull_backfaces, ambient=tuple(ambient), background=tuple(background),
-                          sigma=sigma, gamma=gamma,
+                          sigma=sigma, gamma=gamma, z_clip=z_clip,
                           layout=ops.LAYOUT_PLANAR if planar else ops.LAYOUT_NHWC_RGBA)
     if texture is not None:
         if face_uvs is None:
@@ -211,3 +211,25 @@ def mse_loss(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 def masked_mse_loss(a: torch.Tensor, b: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     """F.mse_loss(a * mask, b * mask) of losses.py:71-75: the mean runs over ALL elements."""
     return _MseFn.apply(a, b, mask)
+
+
+# ------------------------------------------------------------------------------------------------
+# camera transform with autograd (MeshRasterizer.transform of the unfused, Fragments-returning path)
+# ------------------------------------------------------------------------------------------------
+class _TransformFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, verts, R, T, k00, k11):
+        ctx.save_for_backward(verts.detach(), R, T)
+        ctx.k = (k00, k11)
+        return ops.transform_verts(verts.detach(), R, T, k00, k11)
+
+    @staticmethod
+    def backward(ctx, grad_ndc):
+        verts, R, T = ctx.saved_tensors
+        return ops.transform_verts_backward(verts, R, T, ctx.k[0], ctx.k[1], grad_ndc.contiguous()), None, None, None, None
+
+
+def transform_verts(verts, R, T, fov: float = 60.0, aspect: float = 1.0, znear: float = 1.0):
+    """(V,3) world -> (N,V,3) [x_ndc, y_ndc, z_view] for N FoV-perspective cameras (row-vector R, T)."""
+    k00, k11 = fov_scales(fov, aspect, znear)
+    return _TransformFn.apply(verts, R.reshape(-1, 3, 3), T.reshape(-1, 3), k00, k11)

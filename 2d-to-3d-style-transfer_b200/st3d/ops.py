@@ -112,6 +112,11 @@ def poll_overflow(block: bool = False) -> None:
         if ev.query():
             needed, overflow = int(host[0]), int(host[1])
             _capacity_hint[key] = max(_capacity_hint.get(key, 0), needed)
+            if int(host[4]):
+                _pending.clear()
+                raise NotImplementedError("a face has a vertex in front of the near clipping plane (z < z_clip): "
+                                          "near-plane face clipping (PyTorch3D clip_faces) is not implemented; the "
+                                          "images of that render call must not be used")
             if overflow:
                 _pending.clear()
                 raise St3dError(f"tile bins overflowed: {needed} (face,tile) pairs needed; results of that call are "
@@ -245,6 +250,7 @@ class RenderSpec:
     sigma: float = 1e-4
     gamma: float = 1e-4
     layout: int = LAYOUT_NHWC_RGBA
+    z_clip: Optional[float] = None      # None -> znear / 2 (PyTorch3D's default for perspective cameras)
 
 
 @dataclass
@@ -308,6 +314,7 @@ def render_forward(spec: RenderSpec, verts, faces, R, T, *, face_uvs=None, textu
     nbytes = lib().st3d_render_workspace_size(N, V, F, H, W, cap)
     ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
     a.workspace, a.workspace_bytes, a.list_capacity = _p(ws), nbytes, cap
+    a.z_clip = spec.znear / 2.0 if spec.z_clip is None else float(spec.z_clip)
     with _timed("render_forward", (N, H, W, F)):
         check(lib().st3d_render_forward(ctypes.byref(a), _stream()), "st3d_render_forward")
     if N > 0:

@@ -65,7 +65,9 @@ size_t st3d_raster_workspace_size(int N, int64_t F_total, int H, int W, int64_t 
 
 /* Workspace header, readable by the host AFTER the stream has been synchronised:
  * [0] = (face,tile) pairs needed by the last call, [1] = 1 if the bins overflowed (results invalid,
- * re-run with a larger list_capacity), [2] = capacity in pairs. */
+ * re-run with a larger list_capacity), [2] = capacity in pairs, [4] = 1 if some face has a vertex nearer
+ * than st3d_render_args.z_clip (PyTorch3D would clip such faces against the near plane, clip.py; that
+ * path is not implemented, so the caller must treat the render as unsupported rather than trust it). */
 #define ST3D_WS_HEADER_INTS 16
 
 /* _C.rasterize_meshes: face_verts (F_total,3,3) in NDC (z = view depth); mesh n owns faces
@@ -140,6 +142,7 @@ typedef struct st3d_render_args {
     void* workspace;        /* >= st3d_render_workspace_size(...) bytes; forward fills it, backward reads it */
     size_t workspace_bytes;
     int64_t list_capacity;  /* must match the value given to st3d_render_workspace_size */
+    float z_clip;           /* near-plane clip depth (PyTorch3D: znear / 2); <= 0 disables the check */
 } st3d_render_args;
 
 size_t st3d_render_workspace_size(int N, int64_t V, int64_t F, int H, int W, int64_t list_capacity);

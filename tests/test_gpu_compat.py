@@ -1,0 +1,211 @@
+"""GPU integration tests of the drop-in surface: the calls second_approach.py:147-190 and
+first_approach.py:191-213 make, through the `pytorch3d`-named package and the utils / losses modules of
+compat/, against the CPU oracle on the same inputs."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "2d-to-3d-style-transfer_b200")
+COMPAT = os.path.join(PKG, "compat")
+if COMPAT not in sys.path:
+    sys.path.insert(0, COMPAT)
+
+from oracle import loss_oracle as lo  # noqa: E402
+from oracle import render_oracle as ro  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+S = 64
+WEIGHTS = {"mesh_edge_loss_weight": 1.0, "mesh_laplacian_smoothing_weight": 1.0, "mesh_normal_consistency_weight": 1.0,
+           "mesh_verts_weight": 1.0, "main_loss_weight": 3.0}
+
+
+def _vgg(device):
+    import torchvision
+    torch.manual_seed(0)
+    vgg = torchvision.models.vgg19(weights=None).features.eval().to(device)
+    for p in vgg.parameters():
+        p.requires_grad_(False)
+    return vgg
+
+
+@pytest.fixture(scope="module")
+def scene(tmp_path_factory, cow):
+    """The cow written to OBJ/MTL/PNG and loaded back the way the scripts do (first_approach.py:83-103)."""
+    from pytorch3d.io import load_obj, save_obj
+    from pytorch3d.renderer import (AmbientLights, FoVPerspectiveCameras, MeshRasterizer, MeshRenderer,
+                                    RasterizationSettings, SoftPhongShader)
+    import utils
+    d = tmp_path_factory.mktemp("cow")
+    save_obj(str(d / "cow.obj"), cow["verts"], cow["faces"], cow["verts_uvs"], cow["faces_uvs"], cow["texture"])
+    dev = torch.device("cuda:0")
+    verts, faces, aux = load_obj(str(d / "cow.obj"))
+    verts_uvs, faces_uvs = aux.verts_uvs[None].to(dev), faces.textures_idx[None].to(dev)
+    tex = list(aux.texture_images.values())[0][None].to(dev)
+    tex = F.interpolate(tex.permute(0, 3, 1, 2), size=S, mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+    mesh = utils.build_mesh(verts_uvs, faces_uvs, tex, verts.to(dev), faces.verts_idx.to(dev))
+    cams = FoVPerspectiveCameras(device=dev)
+    renderer = MeshRenderer(rasterizer=MeshRasterizer(cameras=cams, raster_settings=RasterizationSettings(
+        image_size=S, blur_radius=0.0, faces_per_pixel=1)), shader=SoftPhongShader(device=dev, cameras=cams,
+                                                                               lights=AmbientLights(device=dev)))
+    torch.manual_seed(3)
+    cameras = utils.build_random_cameras(3)
+    return dict(mesh=mesh, renderer=renderer, cameras=cameras, verts=verts, faces=faces.verts_idx, tex=tex.cpu(),
+                verts_uvs=aux.verts_uvs, faces_uvs=faces.textures_idx, dev=dev)
+
+
+def _oracle_images(sc, verts, tex):
+    rgba = ro.render_views(verts, sc["faces"], sc["cameras"].R.cpu(), sc["cameras"].T.cpu(), S, texture=tex,
+                           verts_uvs=sc["verts_uvs"].to(verts.dtype), faces_uvs=sc["faces_uvs"], nthreads=8)
+    return ro.images_and_masks(rgba)
+
+
+def test_per_view_calls_equal_batched_render_and_oracle(scene):
+    import utils
+    sc = scene
+    per_view = [sc["renderer"](meshes_world=sc["mesh"], cameras=cam) for cam in sc["cameras"]]   # utils.py:68-69
+    assert all(o.shape == (1, S, S, 4) for o in per_view)
+    rgba = torch.cat(per_view, dim=0)
+    images, masks = utils.render_meshes(sc["renderer"], sc["mesh"], [sc["cameras"][i] for i in range(3)])
+    assert torch.equal(images, rgba[..., :3].permute(0, 3, 1, 2))
+    assert torch.equal(masks[:, 0], (rgba[..., 3] > 0).float())
+    want_img, want_mask = _oracle_images(sc, sc["verts"], sc["tex"][0])
+    assert torch.equal(masks.cpu(), want_mask)
+    assert (images.cpu() - want_img).abs().max() <= 1e-4
+
+
+def test_rasterizer_fragments_match_oracle(scene):
+    from pytorch3d.renderer import MeshRasterizer, RasterizationSettings
+    sc = scene
+    rast = MeshRasterizer(cameras=sc["cameras"], raster_settings=RasterizationSettings(image_size=S, faces_per_pixel=2))
+    frag = rast(sc["mesh"])
+    k00, k11 = ro.fov_scales(60.0)
+    ndc = ro.transform_verts_exact(sc["verts"], sc["cameras"].R.cpu(), sc["cameras"].T.cpu(), k00, k11)
+    Fn = sc["faces"].shape[0]
+    fv = ndc[:, sc["faces"]].reshape(3 * Fn, 3, 3)
+    want = ro.rasterize_naive(fv, torch.arange(3) * Fn, torch.full((3,), Fn), S, 0.0, 2, True, False, False, nthreads=8)
+    assert frag.pix_to_face.dtype == torch.int64 and torch.equal(frag.pix_to_face.cpu(), want[0])
+    assert (frag.zbuf.cpu() - want[1]).abs().max() <= 1e-4 and (frag.bary_coords.cpu() - want[2]).abs().max() <= 1e-4
+
+
+@pytest.mark.parametrize("target", ["texture", "both"])
+def test_second_approach_iteration_matches_oracle(scene, target):
+    """One iteration of second_approach.py:147-190, then two more Adam steps."""
+    import losses
+    import utils
+    sc = scene
+    dev = sc["dev"]
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False          # compare against CPU fp32 convolutions
+    try:
+        vgg = _vgg(dev)
+        style = torch.rand(1, 3, S, S, generator=torch.Generator().manual_seed(4)).repeat(3, 1, 1, 1)
+        out = utils.setup_optimizations(target, sc["mesh"], 0.01)
+        texture_map, verts, faces = out["texture_map"], out["verts"], out["faces"]
+        cams = [sc["cameras"][i] for i in range(3)]
+        hist = []
+        for step in range(3):
+            out["optimizer"].zero_grad()
+            content, cmask = utils.render_meshes(sc["renderer"], sc["mesh"], cams)
+            content = utils.apply_background(content, cmask, "white", style.to(dev))
+            current_mesh = utils.build_mesh(out["verts_uvs"], out["faces_uvs"], texture_map, verts, faces)
+            current, mask = utils.render_meshes(sc["renderer"], current_mesh, cams)
+            current = utils.apply_background(current, mask, "white", style.to(dev))
+            loss = losses.compute_second_approach_loss(current=current, content=content, style=style.to(dev), model=vgg,
+                                                       style_weight=1e6, content_weight=1.0, verts=verts,
+                                                       target_verts=sc["mesh"].verts_packed(), mesh=current_mesh,
+                                                       weights=WEIGHTS, opt_type=target)
+            loss.backward()
+            if step == 0:
+                g_tex = texture_map.grad.detach().cpu().clone()
+                g_verts = verts.grad.detach().cpu().clone() if target == "both" else None
+                first = loss.item()
+            out["optimizer"].step()
+            hist.append(loss.item())
+        assert hist[-1] < hist[0], hist
+        # oracle, same first iteration on the CPU
+        vgg_cpu = _vgg("cpu")
+        tex_o = sc["tex"][0].clone().requires_grad_(True)
+        verts_o = sc["verts"].clone().requires_grad_(target == "both")
+        with torch.no_grad():
+            content_o, _ = _oracle_images(sc, sc["verts"], sc["tex"][0])
+        current_o, _ = _oracle_images(sc, verts_o, tex_o)
+        want = lo.second_approach_loss(current_o, content_o, style, vgg_cpu, 1e6, 1.0, verts_o, sc["verts"], sc["faces"],
+                                       WEIGHTS, target)
+        want.backward()
+        assert abs(first - want.item()) <= 2e-3 * abs(want.item()), (first, want.item())
+        rel = lambda a, b: ((a - b).abs().max() / b.abs().max()).item()
+        assert rel(g_tex[0], tex_o.grad) <= 5e-3, rel(g_tex[0], tex_o.grad)
+        if target == "both":
+            assert rel(g_verts, verts_o.grad) <= 5e-3, rel(g_verts, verts_o.grad)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+
+
+@pytest.mark.parametrize("target", ["texture", "mesh"])
+def test_first_approach_mse_fit_matches_oracle(scene, target):
+    """The MSE-fit loop body of first_approach.py:191-213."""
+    import losses
+    import utils
+    sc = scene
+    dev = sc["dev"]
+    goal = torch.rand(3, 3, S, S, generator=torch.Generator().manual_seed(8))
+    out = utils.setup_optimizations(target, sc["mesh"], 0.01)
+    cams = [sc["cameras"][i] for i in range(3)]
+    hist = []
+    for step in range(4):
+        out["optimizer"].zero_grad()
+        cur = utils.build_mesh(out["verts_uvs"], out["faces_uvs"], out["texture_map"], out["verts"], out["faces"])
+        rendered, masks = utils.render_meshes(sc["renderer"], cur, cams)
+        loss = losses.compute_first_approach_loss(rendered=rendered, masks=masks, target_rendered=goal.to(dev),
+                                                  verts=out["verts"], target_verts=sc["mesh"].verts_packed(), mesh=cur,
+                                                  weights=WEIGHTS, opt_type=target)
+        loss.backward()
+        if step == 0:
+            first = loss.item()
+            g = (out["texture_map"].grad if target == "texture" else out["verts"].grad).detach().cpu().clone()
+        out["optimizer"].step()
+        hist.append(loss.item())
+    assert hist[-1] < hist[0], hist
+    tex_o = sc["tex"][0].double().requires_grad_(target == "texture")
+    verts_o = sc["verts"].double().requires_grad_(target == "mesh")
+    img_o, mask_o = _oracle_images(sc, verts_o, tex_o)
+    want = lo.first_approach_loss(img_o, mask_o, goal.double(), verts_o, sc["verts"].double(), sc["faces"], WEIGHTS, target)
+    want.backward()
+    assert abs(first - want.item()) <= 1e-4 * abs(want.item())
+    ref = tex_o.grad if target == "texture" else verts_o.grad
+    got = g[0] if target == "texture" else g
+    assert ((got.double() - ref).abs().max() / ref.abs().max()).item() <= 2e-4
+
+
+def test_near_plane_violation_is_reported(scene):
+    """A camera inside the mesh needs near-plane clipping, which is not implemented: fail loudly."""
+    from pytorch3d.renderer import FoVPerspectiveCameras
+    from st3d import ops
+    sc = scene
+    inside = FoVPerspectiveCameras(R=torch.eye(3)[None], T=torch.tensor([[0.0, 0.0, 0.2]]), device=sc["dev"])
+    sc["renderer"](meshes_world=sc["mesh"], cameras=inside)
+    torch.cuda.synchronize()
+    with pytest.raises(NotImplementedError):
+        ops.poll_overflow(block=True)
+
+
+def test_runner_resolves_modules_to_compat(tmp_path):
+    script = tmp_path / "probe.py"
+    script.write_text(
+        "from style_transfer import *\nfrom utils import *\nfrom losses import *\n"
+        "from pytorch3d.io import load_obj, IO\n"
+        "from pytorch3d.renderer import FoVPerspectiveCameras, RasterizationSettings, MeshRenderer, MeshRasterizer, "
+        "SoftPhongShader, AmbientLights\n"
+        "import pytorch3d, utils, losses, style_transfer\n"
+        "print('OK', pytorch3d.__version__, utils.__file__, losses.__file__, style_transfer.__file__)\n")
+    env = dict(os.environ, PYTHONPATH=PKG)
+    out = subprocess.run([sys.executable, "-m", "st3d.run", str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("OK")][0]
+    assert "st3d" in line and line.count(os.path.join("compat", "")) == 3
