@@ -43,17 +43,25 @@ def loss_inputs():
 
 
 def import_reference():
+    """Imports the LIVE reference modules (style_transfer.py, losses.py) without disturbing same-named
+    modules that may already be loaded (this repo ships drop-in modules with those names)."""
     stub = types.ModuleType("pytorch3d.loss")
     for n in ("mesh_edge_loss", "mesh_laplacian_smoothing", "mesh_normal_consistency"):
         setattr(stub, n, lambda *a, **k: 0.0)
     pkg = types.ModuleType("pytorch3d")
     pkg.loss = stub
-    sys.modules.setdefault("pytorch3d", pkg)
-    sys.modules.setdefault("pytorch3d.loss", stub)
+    names = ("pytorch3d", "pytorch3d.loss", "style_transfer", "losses")
+    saved = {n: sys.modules.pop(n) for n in names if n in sys.modules}
+    sys.modules["pytorch3d"], sys.modules["pytorch3d.loss"] = pkg, stub
     sys.path.insert(0, REF)
-    import style_transfer as ref_st
-    import losses as ref_losses
-    sys.path.remove(REF)
+    try:
+        import style_transfer as ref_st
+        import losses as ref_losses
+    finally:
+        sys.path.remove(REF)
+        for n in names:
+            sys.modules.pop(n, None)
+        sys.modules.update(saved)
     return ref_st, ref_losses
 
 
