@@ -188,17 +188,17 @@ def cpu_baseline_dict(args, sec_per_view, threads, n_timed):
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     sec, threads = cpu_one_view_iterations(args, max(args.steps, 1), max(args.warmup, 0))
     value = 1.0 / (sec * args.views)
     cb = cpu_baseline_dict(args, sec, threads, args.steps)
-    print(json.dumps({
+    return json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * args.views * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "cow mesh fixture + synthetic style image + random-init VGG-19",
         "config": workload_config(args, 1), "cpu_baseline": cb,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------------
@@ -381,15 +381,33 @@ def run_st3d(args):
         dist.destroy_process_group()
     if rank == 0:
         out["lib"] = st3d.library_path()
-        print(json.dumps(out))
+        return json.dumps(out)
+    return None
+
+
+class _QuietStdout:
+    """Routes fd 1 to stderr while the benchmark runs (NCCL / cuDNN may print to stdout) and restores it for
+    the single JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
 
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_st3d(args)
+    with _QuietStdout():
+        line = run_reference(args) if args.impl == "reference" else run_st3d(args)
+    if line is not None:
+        print(line, flush=True)
 
 
 if __name__ == "__main__":
