@@ -182,7 +182,11 @@ struct RasterWs {
     int* tile_cursor;  // NT
     int* tile_offset;  // NT
     FaceRec* rec;      // F_total
-    int* list;         // capacity
+    int* list;         // capacity: face id of every (face, tile) pair, grouped by tile
+    int* list_tile;    // capacity: tile id of the same pair (for the pair-parallel z-buffer pass)
+    unsigned long long* zkey;  // N*H*W: (depth bits << 32 | face id) z-buffer of the hard rasterizer
+    float* ndc_x;      // W: NDC x of every pixel column (exact oracle arithmetic)
+    float* ndc_y;      // H
     float4* verts_ndc; // N*V (render only)
     float* grad_ndc;   // N*V*3 (render backward scratch)
     size_t zero_bytes; // hdr + tile_count + tile_cursor (contiguous) cleared every call
@@ -217,6 +221,17 @@ static inline RasterWs raster_ws_layout(void* base, int N, int64_t F_total, int 
     off = align_up(off, 256);
     w.list = (int*)(p + off);
     off += (size_t)w.capacity * sizeof(int);
+    off = align_up(off, 256);
+    w.list_tile = (int*)(p + off);
+    off += (size_t)w.capacity * sizeof(int);
+    off = align_up(off, 256);
+    w.zkey = (unsigned long long*)(p + off);
+    off += (size_t)N * H * W * sizeof(unsigned long long);
+    off = align_up(off, 256);
+    w.ndc_x = (float*)(p + off);
+    off += (size_t)W * sizeof(float);
+    w.ndc_y = (float*)(p + off);
+    off += (size_t)H * sizeof(float);
     off = align_up(off, 256);
     w.verts_ndc = (float4*)(p + off);
     off += (size_t)NV * sizeof(float4);

@@ -29,7 +29,8 @@ static inline GramPlan gram_plan(void* base, int B, int C, int64_t HW, int ctas_
     const int64_t min_kb = 16;
     if (want > kblocks / min_kb) want = kblocks / min_kb;
     if (want < 1) want = 1;
-    const int64_t per = (kblocks + want - 1) / want;  // k-blocks per split
+    int64_t per = (kblocks + want - 1) / want;  // k-blocks per split
+    per = (per + 3) / 4 * 4;  // whole pipeline stages (up to 4 k-blocks each): a split never reads its neighbour's columns
     p.splits = (int)((kblocks + per - 1) / per);
     p.k_chunk = per * 32;
     char* c = (char*)base;

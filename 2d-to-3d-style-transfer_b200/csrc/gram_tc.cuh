@@ -129,8 +129,12 @@ struct FwdCfg {
     static constexpr int NHALF = C == 512 ? 2 : 1;   // an MMA covers at most N = 256 columns
     static constexpr int NMMA = C / NHALF;
     static constexpr int TMEM_COLS = C == 64 ? 64 : (C == 128 ? 128 : 512);
-    static constexpr int STAGE_BYTES = C * 128;      // C rows x 32 fp32
-    static constexpr int STAGES = C == 64 ? 16 : (C == 128 ? 10 : (C == 256 ? 6 : 3));
+    // k-blocks (32 fp32 columns) per pipeline stage: the boxes of one stage are issued back to back, so DRAM
+    // sees KPS*128 contiguous bytes per feature row instead of isolated 128-byte bursts 4*HW bytes apart
+    static constexpr int KPS = C == 64 ? 4 : (C == 128 ? 2 : 1);
+    static constexpr int SLAB_BYTES = C * 128;       // C rows x 32 fp32
+    static constexpr int STAGE_BYTES = KPS * SLAB_BYTES;
+    static constexpr int STAGES = C == 64 ? 5 : (C == 128 ? 5 : (C == 256 ? 6 : 3));
     static constexpr int BOX_ROWS = C < 256 ? C : 256;
     static constexpr int BOXES = C / BOX_ROWS;
     static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + kScratchFloats * 4 + (2 * STAGES + 2) * 8 + 16;
@@ -155,6 +159,7 @@ k_gram_tc_fwd(const __grid_constant__ CUtensorMap map, float* __restrict__ parti
     const int g = blockIdx.x, s = blockIdx.y, b = blockIdx.z;
     const int64_t k0 = (int64_t)s * k_chunk, k1 = min(HW, k0 + k_chunk);
     const int nkb = (int)((k1 - k0 + 31) / 32);
+    const int nst = (nkb + Cfg::KPS - 1) / Cfg::KPS;  // pipeline stages (KPS k-blocks each)
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < Cfg::STAGES; ++i) {
@@ -173,38 +178,48 @@ k_gram_tc_fwd(const __grid_constant__ CUtensorMap map, float* __restrict__ parti
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int st = kb % Cfg::STAGES;
-                const uint32_t ph = (kb / Cfg::STAGES) & 1;
+            for (int it = 0; it < nst; ++it) {
+                const int st = it % Cfg::STAGES;
+                const uint32_t ph = (it / Cfg::STAGES) & 1;
                 mbar_wait(empty0 + 8 * st, ph ^ 1);
                 mbar_arrive_expect_tx(full0 + 8 * st, Cfg::STAGE_BYTES);
                 const uint32_t dst = smem_u32(stages + (size_t)st * Cfg::STAGE_BYTES);
 #pragma unroll
-                for (int bx = 0; bx < Cfg::BOXES; ++bx)
-                    tma_load_2d(dst + bx * Cfg::BOX_ROWS * 128, &map, full0 + 8 * st, (int)(k0 + (int64_t)kb * 32),
-                                b * C + bx * Cfg::BOX_ROWS);
+                for (int kk = 0; kk < Cfg::KPS; ++kk) {
+                    // k-blocks past the end of this split's range read zero-filled (out of bounds) or are
+                    // cancelled by x >= HW; the split owns [k0, k1) and k1 - k0 is a multiple of 32 * KPS
+                    // except for the last split, whose tail boxes fall beyond HW and come back as zeros
+                    const int x = (int)(k0 + ((int64_t)it * Cfg::KPS + kk) * 32);
+#pragma unroll
+                    for (int bx = 0; bx < Cfg::BOXES; ++bx)
+                        tma_load_2d(dst + kk * Cfg::SLAB_BYTES + bx * Cfg::BOX_ROWS * 128, &map, full0 + 8 * st, x,
+                                    b * C + bx * Cfg::BOX_ROWS);
+                }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = instr_desc(Cfg::M, Cfg::NMMA, 0, 0);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int st = kb % Cfg::STAGES;
-                const uint32_t ph = (kb / Cfg::STAGES) & 1;
+            for (int it = 0; it < nst; ++it) {
+                const int st = it % Cfg::STAGES;
+                const uint32_t ph = (it / Cfg::STAGES) & 1;
                 mbar_wait(full0 + 8 * st, ph);
                 tc_fence_after();
-                const uint32_t sbase = smem_u32(stages + (size_t)st * Cfg::STAGE_BYTES);
 #pragma unroll
-                for (int p = 0; p < Cfg::PANELS; ++p) {
-                    const uint32_t row_a = (C == 512 ? g : p) * 128;  // 0 when C <= 128
+                for (int kk = 0; kk < Cfg::KPS; ++kk) {
+                    const uint32_t sbase = smem_u32(stages + (size_t)st * Cfg::STAGE_BYTES) + kk * Cfg::SLAB_BYTES;
 #pragma unroll
-                    for (int h = 0; h < Cfg::NHALF; ++h) {
+                    for (int p = 0; p < Cfg::PANELS; ++p) {
+                        const uint32_t row_a = (C == 512 ? g : p) * 128;  // 0 when C <= 128
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t ad = smem_desc(sbase + row_a * 128 + k * 32, 16, 1024);
-                            const uint64_t bd = smem_desc(sbase + h * 256 * 128 + k * 32, 16, 1024);
-                            mma_tf32(tmem_base + p * 256 + h * 256, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        for (int h = 0; h < Cfg::NHALF; ++h) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t ad = smem_desc(sbase + row_a * 128 + k * 32, 16, 1024);
+                                const uint64_t bd = smem_desc(sbase + h * 256 * 128 + k * 32, 16, 1024);
+                                mma_tf32(tmem_base + p * 256 + h * 256, ad, bd, idesc, (it > 0 || kk > 0 || k > 0) ? 1u : 0u);
+                            }
                         }
                     }
                 }

@@ -124,8 +124,11 @@ __global__ void k_setup(const float* __restrict__ face_verts, const float4* __re
 
 // 3. carve each tile's list out of the pair buffer (order of tiles in the buffer is irrelevant)
 __global__ void k_alloc(const int* __restrict__ tile_count, int* __restrict__ tile_offset, int* __restrict__ hdr,
-                        int NT) {
+                        int NT, int H, int W, float* __restrict__ ndc_x, float* __restrict__ ndc_y) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    // pixel-centre NDC tables (image x / y run opposite to NDC x / y)
+    for (int i = t; i < W; i += gridDim.x * blockDim.x) ndc_x[i] = pix_to_ndc(W - 1 - i, W, H);
+    for (int i = t; i < H; i += gridDim.x * blockDim.x) ndc_y[i] = pix_to_ndc(H - 1 - i, H, W);
     if (t >= NT) return;
     const int c = tile_count[t];
     tile_offset[t] = c > 0 ? atomicAdd(&hdr[0], c) : 0;
@@ -135,7 +138,7 @@ __global__ void k_alloc(const int* __restrict__ tile_count, int* __restrict__ ti
 __global__ void k_fill(const FaceRec* __restrict__ rec, const int64_t* __restrict__ first_idx,
                        const int64_t* __restrict__ num_faces, int64_t F_per_mesh, int TX, int TY,
                        const int* __restrict__ tile_offset, int* __restrict__ tile_cursor, int* __restrict__ list,
-                       int64_t capacity, int* __restrict__ hdr) {
+                       int* __restrict__ list_tile, int64_t capacity, int* __restrict__ hdr) {
     const int n = blockIdx.y;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t first = first_idx ? first_idx[n] : (int64_t)n * F_per_mesh;
@@ -151,9 +154,10 @@ __global__ void k_fill(const FaceRec* __restrict__ rec, const int64_t* __restric
         for (int tx = tx0; tx <= tx1; ++tx) {
             const int t = (n * TY + ty) * TX + tx;
             const int64_t slot = (int64_t)tile_offset[t] + atomicAdd(&tile_cursor[t], 1);
-            if (slot < capacity)
+            if (slot < capacity) {
                 list[slot] = (int)f;
-            else
+                list_tile[slot] = t;
+            } else
                 hdr[1] = 1;
         }
 }
@@ -324,105 +328,83 @@ k_fine(const FaceRec* __restrict__ rec, const int* __restrict__ tile_count, cons
 }
 
 // -------------------------------------------------------------------------------------------------
-// 5b. hard rasterization (blur_radius == 0, faces_per_pixel == 1): face-parallel tile z-buffer
+// 5b. hard rasterization (blur_radius == 0, faces_per_pixel == 1): pair-parallel global z-buffer
 // -------------------------------------------------------------------------------------------------
-// One CTA per 16x16 tile.  Each WARP takes one face of the tile's list at a time and sweeps the
-// face's pixel box (clipped to the tile) in 8x4 steps; lanes that are strictly inside compute the
-// oracle's exact depth and race with a 64-bit atomicMin on (depth bits, face id) in shared memory --
-// the same lexicographic (z, face) order the oracle uses, so the winner does not depend on timing.
-// The winner's barycentrics / distance / shading are then evaluated once per pixel.
-template <int MODE>
+// Phase A (k_zbuf_pairs): one WARP per (face, tile) pair of the bins -- a unit of at most 16x16 pixels,
+// so the load is balanced whatever the distribution of faces over the image.  The warp sweeps the
+// face's pixel box (clipped to the tile) in 8x4 steps; lanes strictly inside the face compute the
+// oracle's exact depth and issue one 64-bit atomicMin on (depth bits << 32 | face id) into a global
+// z-buffer.  That key order IS the oracle's lexicographic (z, face) order, so the winner does not depend
+// on timing.  Phase B (k_resolve): one thread per pixel, row-major (128-byte coalesced stores), evaluates
+// its winner once (barycentrics, edge distance) and runs the fused texture / shade / blend epilogue.
 __global__ void __launch_bounds__(256)
-k_fine_hard(const FaceRec* __restrict__ rec, const int* __restrict__ tile_count, const int* __restrict__ tile_offset,
-            const int* __restrict__ list, int64_t capacity, int H, int W, int persp, FragOut fo, ShadeParams sp) {
-    __shared__ FaceRec s_rec[kChunk];
-    __shared__ int s_id[kChunk];
-    __shared__ unsigned long long s_best[kTile * kTile];
-    __shared__ float s_px[kTile], s_py[kTile];
-
-    const int tx = blockIdx.x, ty = blockIdx.y, n = blockIdx.z;
-    const int TX = gridDim.x, TY = gridDim.y;
-    const int t = (n * TY + ty) * TX + tx;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile_x0 = tx * kTile, tile_y0 = ty * kTile;
-    // this thread's output pixel: warp = 8x4 block, 2 x 4 blocks per tile
-    const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
-    const int xi = tile_x0 + lx, yi = tile_y0 + ly;
-    const bool active = xi < W && yi < H;
-    const int64_t pix = ((int64_t)n * H + yi) * W + xi;
-
-    const int base = tile_offset[t];
-    const int count = (int)max((int64_t)0, min((int64_t)tile_count[t], capacity - base));
-
-    unsigned long long key = ~0ull;
-    if (count > 0) {
-        s_best[threadIdx.x] = ~0ull;
-        if (threadIdx.x < kTile) s_px[threadIdx.x] = pix_to_ndc(W - 1 - (tile_x0 + threadIdx.x), W, H);
-        else if (threadIdx.x < 2 * kTile) s_py[threadIdx.x - kTile] = pix_to_ndc(H - 1 - (tile_y0 + threadIdx.x - kTile), H, W);
-        for (int c0 = 0; c0 < count; c0 += kChunk) {
-            const int nc = min(kChunk, count - c0);
-            __syncthreads();
-            if (threadIdx.x < nc) {
-                const int f = list[base + c0 + threadIdx.x];
-                s_rec[threadIdx.x] = rec[f];
-                s_id[threadIdx.x] = f;
-            }
-            __syncthreads();
-            for (int j = warp; j < nc; j += 8) {
-                const float4 ra = s_rec[j].a, rb = s_rec[j].b, rc = s_rec[j].c;
-                const FaceVerts v{ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w, rc.x};
-                const int xr = __float_as_int(rc.z), yr = __float_as_int(rc.w);
-                const int x0 = max(xr & 0xffff, tile_x0), x1 = min(xr >> 16, tile_x0 + kTile - 1);
-                const int y0 = max(yr & 0xffff, tile_y0), y1 = min(yr >> 16, tile_y0 + kTile - 1);
-                const bool zpos = v.z0 > 0.0f && v.z1 > 0.0f && v.z2 > 0.0f;
-                const float denom = fadd(rc.y, kEps);
-                const unsigned fid = (unsigned)s_id[j];
-                // edge i of the barycentric numerators: w0 <- (v1,v2), w1 <- (v2,v0), w2 <- (v0,v1)
-                const float e0y = fsub(v.y2, v.y1), e0x = fsub(v.x2, v.x1);
-                const float e1y = fsub(v.y0, v.y2), e1x = fsub(v.x0, v.x2);
-                const float e2y = fsub(v.y1, v.y0), e2x = fsub(v.x1, v.x0);
-                for (int by = y0; by <= y1; by += 4) {
-                    for (int bx = x0; bx <= x1; bx += 8) {
-                        const int qx = bx + (lane & 7), qy = by + (lane >> 3);
-                        if (qx > x1 || qy > y1) continue;
-                        const float px = s_px[qx - tile_x0], py = s_py[qy - tile_y0];
-                        const float w0 = fsub(fmul(fsub(px, v.x1), e0y), fmul(fsub(py, v.y1), e0x));
-                        const float w1 = fsub(fmul(fsub(px, v.x2), e1y), fmul(fsub(py, v.y2), e1x));
-                        const float w2 = fsub(fmul(fsub(px, v.x0), e2y), fmul(fsub(py, v.y0), e2x));
-                        // necessary for "inside" when every z > 0: the three edge values share one strict sign
-                        if (zpos && !((w0 > 0.0f && w1 > 0.0f && w2 > 0.0f) || (w0 < 0.0f && w1 < 0.0f && w2 < 0.0f)))
-                            continue;
-                        float b0 = fdiv(w0, denom), b1 = fdiv(w1, denom), b2 = fdiv(w2, denom);
-                        if (persp) {
-                            const float t0 = fmul(fmul(b0, v.z1), v.z2);
-                            const float t1 = fmul(fmul(v.z0, b1), v.z2);
-                            const float t2 = fmul(fmul(v.z0, v.z1), b2);
-                            const float d = fmaxf(fadd(fadd(t0, t1), t2), kEps);
-                            b0 = fdiv(t0, d);
-                            b1 = fdiv(t1, d);
-                            b2 = fdiv(t2, d);
-                        }
-                        if (!(b0 > 0.0f && b1 > 0.0f && b2 > 0.0f)) continue;
-                        const float pz = fadd(fadd(fmul(b0, v.z0), fmul(b1, v.z1)), fmul(b2, v.z2));
-                        if (!(pz >= 0.0f)) continue;
-                        const unsigned long long k =
-                            ((unsigned long long)__float_as_uint(fadd(pz, 0.0f)) << 32) | (unsigned long long)fid;
-                        atomicMin(&s_best[(qy - tile_y0) * kTile + (qx - tile_x0)], k);
-                    }
+k_zbuf_pairs(const FaceRec* __restrict__ rec, const int* __restrict__ list, const int* __restrict__ list_tile,
+             const int* __restrict__ hdr, int64_t capacity, int H, int W, int TX, int TY, int persp,
+             const float* __restrict__ ndc_x, const float* __restrict__ ndc_y, unsigned long long* __restrict__ zkey) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t total = min((int64_t)hdr[0], capacity);
+    for (int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < total; p += nwarps) {
+        const int f = __ldg(list + p), t = __ldg(list_tile + p);
+        const int n = t / (TX * TY), tile_y0 = ((t / TX) % TY) * kTile, tile_x0 = (t % TX) * kTile;
+        const float4 ra = __ldg(&rec[f].a), rb = __ldg(&rec[f].b), rc = __ldg(&rec[f].c);
+        const FaceVerts v{ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w, rc.x};
+        const int xr = __float_as_int(rc.z), yr = __float_as_int(rc.w);
+        const int x0 = max(xr & 0xffff, tile_x0), x1 = min(xr >> 16, tile_x0 + kTile - 1);
+        const int y0 = max(yr & 0xffff, tile_y0), y1 = min(yr >> 16, tile_y0 + kTile - 1);
+        const bool zpos = v.z0 > 0.0f && v.z1 > 0.0f && v.z2 > 0.0f;
+        const float denom = fadd(rc.y, kEps);
+        // edge i of the barycentric numerators: w0 <- (v1,v2), w1 <- (v2,v0), w2 <- (v0,v1)
+        const float e0y = fsub(v.y2, v.y1), e0x = fsub(v.x2, v.x1);
+        const float e1y = fsub(v.y0, v.y2), e1x = fsub(v.x0, v.x2);
+        const float e2y = fsub(v.y1, v.y0), e2x = fsub(v.x1, v.x0);
+        unsigned long long* zview = zkey + (int64_t)n * H * W;
+        for (int by = y0; by <= y1; by += 4) {
+            for (int bx = x0; bx <= x1; bx += 8) {
+                const int qx = bx + (lane & 7), qy = by + (lane >> 3);
+                if (qx > x1 || qy > y1) continue;
+                const float px = __ldg(ndc_x + qx), py = __ldg(ndc_y + qy);
+                const float w0 = fsub(fmul(fsub(px, v.x1), e0y), fmul(fsub(py, v.y1), e0x));
+                const float w1 = fsub(fmul(fsub(px, v.x2), e1y), fmul(fsub(py, v.y2), e1x));
+                const float w2 = fsub(fmul(fsub(px, v.x0), e2y), fmul(fsub(py, v.y0), e2x));
+                // necessary for "inside" when every z > 0: the three edge values share one strict sign
+                if (zpos && !((w0 > 0.0f && w1 > 0.0f && w2 > 0.0f) || (w0 < 0.0f && w1 < 0.0f && w2 < 0.0f)))
+                    continue;
+                float b0 = fdiv(w0, denom), b1 = fdiv(w1, denom), b2 = fdiv(w2, denom);
+                if (persp) {
+                    const float t0 = fmul(fmul(b0, v.z1), v.z2);
+                    const float t1 = fmul(fmul(v.z0, b1), v.z2);
+                    const float t2 = fmul(fmul(v.z0, v.z1), b2);
+                    const float d = fmaxf(fadd(fadd(t0, t1), t2), kEps);
+                    b0 = fdiv(t0, d);
+                    b1 = fdiv(t1, d);
+                    b2 = fdiv(t2, d);
                 }
+                if (!(b0 > 0.0f && b1 > 0.0f && b2 > 0.0f)) continue;
+                const float pz = fadd(fadd(fmul(b0, v.z0), fmul(b1, v.z1)), fmul(b2, v.z2));
+                if (!(pz >= 0.0f)) continue;
+                const unsigned long long k =
+                    ((unsigned long long)__float_as_uint(fadd(pz, 0.0f)) << 32) | (unsigned long long)(unsigned)f;
+                atomicMin(zview + (int64_t)qy * W + qx, k);
             }
         }
-        __syncthreads();
-        key = s_best[ly * kTile + lx];
     }
-    if (!active) return;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_resolve(const FaceRec* __restrict__ rec, const unsigned long long* __restrict__ zkey, int H, int W, int persp,
+          const float* __restrict__ ndc_x, const float* __restrict__ ndc_y, FragOut fo, ShadeParams sp) {
+    const int xi = blockIdx.x * blockDim.x + threadIdx.x, yi = blockIdx.y, n = blockIdx.z;
+    if (xi >= W) return;
+    const int64_t pix = ((int64_t)n * H + yi) * W + xi;
+    const unsigned long long key = zkey[pix];
     const bool hit = key != ~0ull;
     const int f = (int)(unsigned)(key & 0xffffffffull);
     Hit h{};
     if (hit) {
-        const float px = pix_to_ndc(W - 1 - xi, W, H), py = pix_to_ndc(H - 1 - yi, H, W);
         const FaceRec r = rec[f];
-        eval_face(px, py, unpack(r), r.c.y, 0.0f, persp != 0, false, h);
+        eval_face(__ldg(ndc_x + xi), __ldg(ndc_y + yi), unpack(r), r.c.y, 0.0f, persp != 0, false, h);
     }
     if (MODE == 0) {
         fo.pix_to_face[pix] = hit ? f : -1;
@@ -453,6 +435,18 @@ k_fine_hard(const FaceRec* __restrict__ rec, const int* __restrict__ tile_count,
     }
 }
 
+template <int MODE>
+static int run_hard(const RasterWs& ws, int N, int H, int W, int persp, const FragOut& fo, const ShadeParams& sp,
+                    cudaStream_t s) {
+    ST3D_CUDA_OK(cudaMemsetAsync(ws.zkey, 0xFF, (size_t)N * H * W * sizeof(unsigned long long), s));
+    k_zbuf_pairs<<<148 * 8, 256, 0, s>>>(ws.rec, ws.list, ws.list_tile, ws.hdr, ws.capacity, H, W, ws.TX, ws.TY, persp,
+                                         ws.ndc_x, ws.ndc_y, ws.zkey);
+    ST3D_LAUNCH_OK("k_zbuf_pairs");
+    k_resolve<MODE><<<dim3(cdiv(W, 256), H, N), 256, 0, s>>>(ws.rec, ws.zkey, H, W, persp, ws.ndc_x, ws.ndc_y, fo, sp);
+    ST3D_LAUNCH_OK("k_resolve");
+    return ST3D_OK;
+}
+
 // -------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------
@@ -471,10 +465,10 @@ static int run_bins(const RasterWs& ws, const float* face_verts, const int32_t* 
                                                 blur_radius, cull_backfaces, ws.TX, ws.TY, z_clip, ws.rec, ws.tile_count,
                                                ws.hdr);
         ST3D_LAUNCH_OK("k_setup");
-        k_alloc<<<cdiv(ws.NT, 256), 256, 0, s>>>(ws.tile_count, ws.tile_offset, ws.hdr, ws.NT);
+        k_alloc<<<cdiv(ws.NT, 256), 256, 0, s>>>(ws.tile_count, ws.tile_offset, ws.hdr, ws.NT, H, W, ws.ndc_x, ws.ndc_y);
         ST3D_LAUNCH_OK("k_alloc");
         k_fill<<<grid, 256, 0, s>>>(ws.rec, first_idx, num_faces, F_per_mesh, ws.TX, ws.TY, ws.tile_offset,
-                                    ws.tile_cursor, ws.list, ws.capacity, ws.hdr);
+                                    ws.tile_cursor, ws.list, ws.list_tile, ws.capacity, ws.hdr);
         ST3D_LAUNCH_OK("k_fill");
     }
     return ST3D_OK;
@@ -523,7 +517,7 @@ extern "C" int st3d_rasterize_meshes_forward(const float* face_verts, const int6
                  "rasterize_meshes: null input");
     if (N == 0) return ST3D_OK;
     const int64_t cap = ((int64_t)workspace_bytes - (int64_t)raster_ws_layout(nullptr, N, F_total, H, W, 1, 0).total_bytes) /
-                            (int64_t)sizeof(int) - 64;
+                            (int64_t)(2 * sizeof(int)) - 128;  // two int arrays (face id, tile id) per pair
     if (cap < 1) {
         st3d_set_error("rasterize_meshes: workspace of %zu bytes too small", workspace_bytes);
         return ST3D_ERR_WORKSPACE;
@@ -539,11 +533,9 @@ extern "C" int st3d_rasterize_meshes_forward(const float* face_verts, const int6
 #define ST3D_FINE(KK)                                                                                            \
     k_fine<0, KK><<<ws.NT, 256, 0, s>>>(ws.rec, ws.tile_count, ws.tile_offset, ws.list, ws.capacity, H, W, ws.TX,  \
                                         ws.TY, blur_radius, perspective_correct, clip_barycentric_coords, fo, sp)
-    if (K == 1 && blur_radius == 0.0f && !clip_barycentric_coords) {
-        const int TN = ws.NT / (ws.TX * ws.TY);
-        k_fine_hard<0><<<dim3(ws.TX, ws.TY, TN), 256, 0, s>>>(ws.rec, ws.tile_count, ws.tile_offset, ws.list, ws.capacity,
-                                                              H, W, perspective_correct, fo, sp);
-    } else if (K == 1) ST3D_FINE(1);
+    if (K == 1 && blur_radius == 0.0f && !clip_barycentric_coords)
+        return run_hard<0>(ws, N, H, W, perspective_correct, fo, sp, s);
+    if (K == 1) ST3D_FINE(1);
     else if (K == 2) ST3D_FINE(2);
     else if (K <= 4) {
         // K in {3,4}: run with 4 slots into a temp layout is not possible without scratch; instantiate exactly
@@ -591,11 +583,8 @@ extern "C" int st3d_render_forward(const st3d_render_args* a, st3d_stream_t stre
     if (rc != ST3D_OK) return rc;
     const ShadeParams sp = make_shade_params(*a);
     FragOut fo{};
-    if (a->blur_radius == 0.0f)
-        k_fine_hard<1><<<dim3(ws.TX, ws.TY, a->N), 256, 0, s>>>(ws.rec, ws.tile_count, ws.tile_offset, ws.list, ws.capacity,
-                                                                a->H, a->W, 1, fo, sp);
-    else
-        k_fine<1, 1><<<ws.NT, 256, 0, s>>>(ws.rec, ws.tile_count, ws.tile_offset, ws.list, ws.capacity, a->H, a->W,
+    if (a->blur_radius == 0.0f) return run_hard<1>(ws, a->N, a->H, a->W, 1, fo, sp, s);
+    k_fine<1, 1><<<ws.NT, 256, 0, s>>>(ws.rec, ws.tile_count, ws.tile_offset, ws.list, ws.capacity, a->H, a->W,
                                            ws.TX, ws.TY, a->blur_radius, 1, 1, fo, sp);
     ST3D_LAUNCH_OK("k_fine");
     return ST3D_OK;
