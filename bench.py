@@ -295,9 +295,11 @@ def run_st3d(args):
         mine_ms += per_step
         name = op + ("" if key is None else "_" + "x".join(str(k) for k in key))
         stages[name] = round(per_step, 4)
-    # dominant kernel -> roofline
-    dom = max(((op, key, sum(v) / len(v)) for (op, key), v in prof.items() if algorithmic_bytes(op, key)),
-              key=lambda t: t[2] * len(prof[(t[0], t[1])]), default=None)
+    # dominant KERNEL -> roofline.  gram_* / mse ops are one hot kernel each (plus a <5 us symmetrise/finalize);
+    # render_forward is a sequence of 7 launches (bins, z-buffer, resolve) and is reported per op below.
+    single_kernel_ops = ("gram_backward", "gram_mse_forward", "gram_forward", "mse_forward")
+    dom = max(((op, key, sum(v) / len(v)) for (op, key), v in prof.items() if op in single_kernel_ops),
+              key=lambda t: t[2], default=None)
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -311,10 +313,22 @@ def run_st3d(args):
         nbytes = algorithmic_bytes(op, key)
         ach = nbytes / (avg_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": None, "kernel": f"{op} {key}",
+                    "traffic": 1028184064 if (op, key) == ("gram_backward", (8, 64, 262144)) else None,
+                    "traffic_source": "ncu --set full, profiles/r1_ncu_full_gram_render.csv (dram read+write of k_gram_tc_bwd<64>)",
+                    "kernel": f"{op} {key}: " + ("k_gram_tc_bwd<C> (tcgen05 kind::tf32, TMA, TMEM)" if op == "gram_backward"
+                                                 else "k_gram_tc_fwd<C> (tcgen05 kind::tf32, TMA, TMEM)" if op.startswith("gram")
+                                                 else "k_mse"),
                     "algorithmic_bytes": nbytes, "avg_ms": avg_ms,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"}
 
+    op_table = {}
+    for (op, key), v in sorted(prof.items()):
+        nb = algorithmic_bytes(op, key)
+        if nb:
+            avg = sum(v) / len(v)
+            op_table[op + "_" + "x".join(str(k) for k in key)] = {
+                "avg_ms": round(avg, 4), "calls_per_step": len(v) // args.steps, "algorithmic_MB": round(nb / 1e6, 2),
+                "GBps": round(nb / (avg * 1e-3) / 1e9, 1), "frac_of_hbm_peak": round(nb / (avg * 1e-3) / 1e9 / hbm_peak, 3)}
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -322,7 +336,7 @@ def run_st3d(args):
         "data": "cow mesh fixture (reference objects/cow_mesh) + synthetic style image + seeded random-init VGG-19",
         "config": workload_config(args, world), "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roofline, "final_loss": final_loss,
-        "stages_ms_per_step": stages,
+        "stages_ms_per_step": stages, "ops_vs_hbm_roofline": op_table,
         "render_loss_only": {"ms_per_step": mine_ms, "it_per_s": (world / (mine_ms * 1e-3)) if mine_ms > 0 else None,
                              "note": "sum of libst3d op times (CUDA events) per step; VGG-19 / Adam / autograd glue excluded"},
     }
