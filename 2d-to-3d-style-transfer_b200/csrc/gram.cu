@@ -19,8 +19,8 @@ namespace st3d {
 constexpr int kST = 64, kSK = 16;
 
 __global__ void __launch_bounds__(256)
-k_gram_simt(const float* __restrict__ feat, int C, int64_t HW, int splits, int64_t k_chunk,
-            float* __restrict__ partials) {
+k_gram_simt(const float* __restrict__ feat, int C, int64_t HW, int64_t sc, int64_t sx, int splits, int64_t k_chunk,
+            float* __restrict__ partials) {  // element (c, x) of an image lives at c * sc + x * sx
     __shared__ float sA[kSK][kST + 4], sB[kSK][kST + 4];
     // blockIdx.x enumerates tile pairs (ti >= tj)
     int ti = 0, rem = blockIdx.x;
@@ -41,8 +41,8 @@ k_gram_simt(const float* __restrict__ feat, int C, int64_t HW, int splits, int64
             const int r = (threadIdx.x >> 4) + 16 * m, kk = threadIdx.x & 15;
             const int64_t x = k + kk;
             const int ra = ti * kST + r, rb = tj * kST + r;
-            sA[kk][r] = (ra < C && x < k1) ? F[(int64_t)ra * HW + x] : 0.0f;
-            sB[kk][r] = (rb < C && x < k1) ? F[(int64_t)rb * HW + x] : 0.0f;
+            sA[kk][r] = (ra < C && x < k1) ? F[(int64_t)ra * sc + x * sx] : 0.0f;
+            sB[kk][r] = (rb < C && x < k1) ? F[(int64_t)rb * sc + x * sx] : 0.0f;
         }
         __syncthreads();
 #pragma unroll
@@ -164,8 +164,8 @@ __global__ void k_gram_symmetrize(const float* __restrict__ dgram, int B, int C,
 // FP32 FFMA backward: dF[b, c, x] = sum_j S[b, c, j] F[b, j, x];  64 (c) x 64 (x) tile per CTA
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_gram_bwd_simt(const float* __restrict__ feat, const float* __restrict__ sym, int C, int64_t HW, int accumulate,
-                float* __restrict__ grad_feat) {
+k_gram_bwd_simt(const float* __restrict__ feat, const float* __restrict__ sym, int C, int64_t HW, int64_t sc,
+                int64_t sx, int accumulate, float* __restrict__ grad_feat) {
     __shared__ float sS[kSK][kST + 4];  // [j][c]
     __shared__ float sF[kSK][kST + 4];  // [j][x]
     const int b = blockIdx.z;
@@ -188,7 +188,7 @@ k_gram_bwd_simt(const float* __restrict__ feat, const float* __restrict__ sym, i
             }
             {   // F tile: j = tid/64 + 4 m, x = tid%64 (x contiguous)
                 const int jj = (threadIdx.x >> 6) + 4 * m, x = threadIdx.x & 63;
-                sF[jj][x] = (j0 + jj < C && x0 + x < HW) ? F[(int64_t)(j0 + jj) * HW + x0 + x] : 0.0f;
+                sF[jj][x] = (j0 + jj < C && x0 + x < HW) ? F[(int64_t)(j0 + jj) * sc + (x0 + x) * sx] : 0.0f;
             }
         }
         __syncthreads();
@@ -214,13 +214,14 @@ k_gram_bwd_simt(const float* __restrict__ feat, const float* __restrict__ sym, i
             const int c = c0 + ty * 4 + i;
             const int64_t x = x0 + tx * 4 + j;
             if (c < C && x < HW) {
-                const int64_t o = (int64_t)c * HW + x;
+                const int64_t o = (int64_t)c * sc + x * sx;
                 G[o] = accumulate ? G[o] + acc[i][j] : acc[i][j];
             }
         }
 }
 
-static int check_common(const char* what, const float* feat, int B, int C, int64_t HW, int precision) {
+static int check_common(const char* what, const float* feat, int B, int C, int64_t HW, int precision, int layout) {
+    ST3D_REQUIRE(layout == ST3D_FEAT_NCHW || layout == ST3D_FEAT_NHWC, "%s: unknown feature layout %d", what, layout);
     ST3D_REQUIRE(B >= 0 && C >= 1 && HW >= 1, "%s: bad sizes B=%d C=%d HW=%lld", what, B, C, (long long)HW);
     ST3D_REQUIRE(B == 0 || feat, "%s: null feat", what);
     ST3D_REQUIRE(precision == ST3D_GRAM_TF32 || precision == ST3D_GRAM_FP32, "%s: unknown precision %d", what,
@@ -233,10 +234,12 @@ static int check_common(const char* what, const float* feat, int B, int C, int64
     return ST3D_OK;
 }
 
-static int gram_partials(const float* feat, const GramPlan& p, int precision, cudaStream_t s) {
-    if (precision == ST3D_GRAM_TF32) return gram_tc_forward(feat, p, s);
+static int gram_partials(const float* feat, const GramPlan& p, int precision, int layout, cudaStream_t s) {
+    const bool nhwc = layout == ST3D_FEAT_NHWC;
+    if (precision == ST3D_GRAM_TF32) return gram_tc_forward(feat, p, nhwc, s);
     const int T = cdiv(p.C, kST);
-    k_gram_simt<<<dim3(T * (T + 1) / 2, p.splits, p.B), 256, 0, s>>>(feat, p.C, p.HW, p.splits, p.k_chunk, p.partials);
+    k_gram_simt<<<dim3(T * (T + 1) / 2, p.splits, p.B), 256, 0, s>>>(feat, p.C, p.HW, nhwc ? 1 : p.HW, nhwc ? p.C : 1,
+                                                                     p.splits, p.k_chunk, p.partials);
     ST3D_LAUNCH_OK("k_gram_simt");
     return ST3D_OK;
 }
@@ -252,8 +255,8 @@ extern "C" size_t st3d_gram_workspace_size(int B, int C, int64_t HW) {
 
 extern "C" int st3d_gram_mse_forward(const float* feat, const float* target, int B, int Bt, int C, int64_t HW,
                                      float scale, float* gram, float* dgram, float* loss_out, void* workspace,
-                                     size_t workspace_bytes, int precision, st3d_stream_t stream) {
-    int rc = check_common("gram_forward", feat, B, C, HW, precision);
+                                     size_t workspace_bytes, int precision, int layout, st3d_stream_t stream) {
+    int rc = check_common("gram_forward", feat, B, C, HW, precision, layout);
     if (rc != ST3D_OK) return rc;
     if (B == 0) return ST3D_OK;
     ST3D_REQUIRE(!target || Bt == 1 || Bt == B, "gram_mse_forward: target batch %d is neither 1 nor %d", Bt, B);
@@ -265,7 +268,7 @@ extern "C" int st3d_gram_mse_forward(const float* feat, const float* target, int
         return ST3D_ERR_WORKSPACE;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    rc = gram_partials(feat, p, precision, s);
+    rc = gram_partials(feat, p, precision, layout, s);
     if (rc != ST3D_OK) return rc;
     const int64_t total = (int64_t)B * C * C;
     const int sp = p.splits >= 8 ? 8 : (p.splits >= 4 ? 4 : (p.splits >= 2 ? 2 : 1));
@@ -283,16 +286,16 @@ extern "C" int st3d_gram_mse_forward(const float* feat, const float* target, int
 }
 
 extern "C" int st3d_gram_forward(const float* feat, int B, int C, int64_t HW, float* gram, void* workspace,
-                                 size_t workspace_bytes, int precision, st3d_stream_t stream) {
+                                 size_t workspace_bytes, int precision, int layout, st3d_stream_t stream) {
     ST3D_REQUIRE(B == 0 || gram, "gram_forward: null output");
     return st3d_gram_mse_forward(feat, nullptr, B, 1, C, HW, 0.0f, gram, nullptr, nullptr, workspace, workspace_bytes,
-                                 precision, stream);
+                                 precision, layout, stream);
 }
 
 extern "C" int st3d_gram_backward(const float* feat, const float* dgram, int B, int C, int64_t HW, float grad_scale,
                                   const float* grad_scale_dev, int accumulate, float* grad_feat, void* workspace,
-                                  size_t workspace_bytes, int precision, st3d_stream_t stream) {
-    int rc = check_common("gram_backward", feat, B, C, HW, precision);
+                                  size_t workspace_bytes, int precision, int layout, st3d_stream_t stream) {
+    int rc = check_common("gram_backward", feat, B, C, HW, precision, layout);
     if (rc != ST3D_OK) return rc;
     if (B == 0) return ST3D_OK;
     ST3D_REQUIRE(dgram && grad_feat && workspace, "gram_backward: null pointer");
@@ -304,8 +307,10 @@ extern "C" int st3d_gram_backward(const float* feat, const float* dgram, int B, 
     cudaStream_t s = (cudaStream_t)stream;
     k_gram_symmetrize<<<cdiv((int64_t)B * C * C, 256), 256, 0, s>>>(dgram, B, C, grad_scale, grad_scale_dev, p.sym);
     ST3D_LAUNCH_OK("k_gram_symmetrize");
-    if (precision == ST3D_GRAM_TF32) return gram_tc_backward(feat, p, accumulate, grad_feat, s);
-    k_gram_bwd_simt<<<dim3(cdiv(HW, kST), cdiv(C, kST), B), 256, 0, s>>>(feat, p.sym, C, HW, accumulate, grad_feat);
+    const bool nhwc = layout == ST3D_FEAT_NHWC;
+    if (precision == ST3D_GRAM_TF32) return gram_tc_backward(feat, p, nhwc, accumulate, grad_feat, s);
+    k_gram_bwd_simt<<<dim3(cdiv(HW, kST), cdiv(C, kST), B), 256, 0, s>>>(feat, p.sym, C, HW, nhwc ? 1 : HW, nhwc ? C : 1,
+                                                                         accumulate, grad_feat);
     ST3D_LAUNCH_OK("k_gram_bwd_simt");
     return ST3D_OK;
 }

@@ -54,6 +54,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, int z) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z)
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -141,7 +147,12 @@ struct FwdCfg {
 };
 
 // grid (GROUPS, splits, B).  partials [B][splits][C][C].
-template <int C>
+// NHWC = false: features (B, C, HW), HW contiguous  -> both operands K-major, plain 128-byte swizzle.
+// NHWC = true : features (B, HW, C), C contiguous (torch channels_last, what cuDNN's tensor-core convolutions
+//               produce) -> the contraction runs over the row index, both operands are MN-major and use the
+//               32-byte-atom swizzle; a stage is ROWS = 32*KPS pixel rows, stored as C/32 boxes of
+//               [ROWS][32 channels] (one fully contiguous ROWS*C*4-byte region of DRAM).
+template <int C, bool NHWC>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gram_tc_fwd(const __grid_constant__ CUtensorMap map, float* __restrict__ partials, int splits, int64_t k_chunk,
               int64_t HW) {
@@ -184,41 +195,67 @@ k_gram_tc_fwd(const __grid_constant__ CUtensorMap map, float* __restrict__ parti
                 mbar_wait(empty0 + 8 * st, ph ^ 1);
                 mbar_arrive_expect_tx(full0 + 8 * st, Cfg::STAGE_BYTES);
                 const uint32_t dst = smem_u32(stages + (size_t)st * Cfg::STAGE_BYTES);
+                if (NHWC) {
+                    constexpr int ROWS = 32 * Cfg::KPS;
+                    const int x = (int)(k0 + (int64_t)it * ROWS);  // rows >= HW are zero-filled by the 3D map
 #pragma unroll
-                for (int kk = 0; kk < Cfg::KPS; ++kk) {
-                    // k-blocks past the end of this split's range read zero-filled (out of bounds) or are
-                    // cancelled by x >= HW; the split owns [k0, k1) and k1 - k0 is a multiple of 32 * KPS
-                    // except for the last split, whose tail boxes fall beyond HW and come back as zeros
-                    const int x = (int)(k0 + ((int64_t)it * Cfg::KPS + kk) * 32);
+                    for (int cg = 0; cg < C / 32; ++cg)
+                        tma_load_3d(dst + cg * ROWS * 128, &map, full0 + 8 * st, cg * 32, x, b);
+                } else {
 #pragma unroll
-                    for (int bx = 0; bx < Cfg::BOXES; ++bx)
-                        tma_load_2d(dst + kk * Cfg::SLAB_BYTES + bx * Cfg::BOX_ROWS * 128, &map, full0 + 8 * st, x,
-                                    b * C + bx * Cfg::BOX_ROWS);
+                    for (int kk = 0; kk < Cfg::KPS; ++kk) {
+                        // the split owns [k0, k1), a whole number of stages except for the last split of an
+                        // image, whose tail boxes lie beyond HW and come back zero-filled
+                        const int x = (int)(k0 + ((int64_t)it * Cfg::KPS + kk) * 32);
+#pragma unroll
+                        for (int bx = 0; bx < Cfg::BOXES; ++bx)
+                            tma_load_2d(dst + kk * Cfg::SLAB_BYTES + bx * Cfg::BOX_ROWS * 128, &map, full0 + 8 * st, x,
+                                        b * C + bx * Cfg::BOX_ROWS);
+                    }
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = instr_desc(Cfg::M, Cfg::NMMA, 0, 0);
+            constexpr uint32_t idesc = instr_desc(Cfg::M, Cfg::NMMA, NHWC ? 1 : 0, NHWC ? 1 : 0);
             for (int it = 0; it < nst; ++it) {
                 const int st = it % Cfg::STAGES;
                 const uint32_t ph = (it / Cfg::STAGES) & 1;
                 mbar_wait(full0 + 8 * st, ph);
                 tc_fence_after();
+                if (NHWC) {
+                    constexpr uint32_t BOX = 32 * Cfg::KPS * 128;  // one [ROWS][32 channels] box
+                    const uint32_t sbase = smem_u32(stages + (size_t)st * Cfg::STAGE_BYTES);
 #pragma unroll
-                for (int kk = 0; kk < Cfg::KPS; ++kk) {
-                    const uint32_t sbase = smem_u32(stages + (size_t)st * Cfg::STAGE_BYTES) + kk * Cfg::SLAB_BYTES;
+                    for (int kg = 0; kg < 4 * Cfg::KPS; ++kg) {  // 8 pixel rows per MMA
 #pragma unroll
-                    for (int p = 0; p < Cfg::PANELS; ++p) {
-                        const uint32_t row_a = (C == 512 ? g : p) * 128;  // 0 when C <= 128
+                        for (int p = 0; p < Cfg::PANELS; ++p) {
+                            const uint32_t grp_a = (C == 512 ? g : p) * 4;  // first 32-channel group of the panel
+                            const uint64_t ad = smem_desc(sbase + grp_a * BOX + kg * 1024, BOX, 512, 1);
 #pragma unroll
-                        for (int h = 0; h < Cfg::NHALF; ++h) {
+                            for (int h = 0; h < Cfg::NHALF; ++h) {
+                                const uint64_t bd = smem_desc(sbase + h * 8 * BOX + kg * 1024, BOX, 512, 1);
+                                mma_tf32(tmem_base + p * 256 + h * 256, ad, bd, idesc, (it > 0 || kg > 0) ? 1u : 0u);
+                            }
+                        }
+                    }
+                } else {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const uint64_t ad = smem_desc(sbase + row_a * 128 + k * 32, 16, 1024);
-                                const uint64_t bd = smem_desc(sbase + h * 256 * 128 + k * 32, 16, 1024);
-                                mma_tf32(tmem_base + p * 256 + h * 256, ad, bd, idesc, (it > 0 || kk > 0 || k > 0) ? 1u : 0u);
+                    for (int kk = 0; kk < Cfg::KPS; ++kk) {
+                        const uint32_t sbase = smem_u32(stages + (size_t)st * Cfg::STAGE_BYTES) + kk * Cfg::SLAB_BYTES;
+#pragma unroll
+                        for (int p = 0; p < Cfg::PANELS; ++p) {
+                            const uint32_t row_a = (C == 512 ? g : p) * 128;  // 0 when C <= 128
+#pragma unroll
+                            for (int h = 0; h < Cfg::NHALF; ++h) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint64_t ad = smem_desc(sbase + row_a * 128 + k * 32, 16, 1024);
+                                    const uint64_t bd = smem_desc(sbase + h * 256 * 128 + k * 32, 16, 1024);
+                                    mma_tf32(tmem_base + p * 256 + h * 256, ad, bd, idesc,
+                                             (it > 0 || kk > 0 || k > 0) ? 1u : 0u);
+                                }
                             }
                         }
                     }
@@ -276,7 +313,10 @@ struct BwdCfg {
     static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 2 * ACC) * 8 + 16;
 };
 
-template <int C>
+// NHWC = false: A = F^T tile from rows j of (B, C, HW): MN-major, 32-byte-atom swizzle, four [32 j][32 x] boxes.
+// NHWC = true : A = F tile [128 x rows][32 j] of (B, HW, C): K-major, plain 128-byte swizzle, one box; the
+//               epilogue thread owns one pixel row and stores 32 consecutive channels (128 contiguous bytes).
+template <int C, bool NHWC>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__ CUtensorMap map_s,
               float* __restrict__ grad_feat, int B, int64_t HW, int accumulate) {
@@ -323,9 +363,13 @@ k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__
                     mbar_wait(empty0 + 8 * st, ph ^ 1);
                     mbar_arrive_expect_tx(full0 + 8 * st, Cfg::STAGE_BYTES);
                     const uint32_t dst = smem_u32(stages + (size_t)st * Cfg::STAGE_BYTES);
+                    if (NHWC) {
+                        tma_load_3d(dst, &map_f, full0 + 8 * st, kb * 32, x0, b);  // [128 x][32 j], rows >= HW zero
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        tma_load_2d(dst + i * 4096, &map_f, full0 + 8 * st, x0 + 32 * i, b * C + kb * 32);
+                        for (int i = 0; i < 4; ++i)
+                            tma_load_2d(dst + i * 4096, &map_f, full0 + 8 * st, x0 + 32 * i, b * C + kb * 32);
+                    }
 #pragma unroll
                     for (int bx = 0; bx < Cfg::S_BOXES; ++bx)
                         tma_load_2d(dst + Cfg::F_BYTES + bx * Cfg::S_BOX_ROWS * 128, &map_s, full0 + 8 * st, kb * 32,
@@ -336,7 +380,7 @@ k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = instr_desc(128, Cfg::NMMA, 1, 0);  // A = F^T tile: MN-major
+            constexpr uint32_t idesc = instr_desc(128, Cfg::NMMA, NHWC ? 0 : 1, 0);  // NCHW: A = F^T tile, MN-major
             uint32_t it = 0, li = 0;
             for (int64_t item = blockIdx.x; item < items; item += gridDim.x, ++li) {
                 const uint32_t a = li % Cfg::ACC, aph = (li / Cfg::ACC) & 1;
@@ -350,8 +394,9 @@ k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__
                     const uint32_t sF = smem_u32(stages + (size_t)st * Cfg::STAGE_BYTES), sS = sF + Cfg::F_BYTES;
 #pragma unroll
                     for (int kg = 0; kg < 4; ++kg) {  // 8 channels j per MMA
-                        // A: 4 M-atoms (32 x's) 4096 B apart; each MMA spans two 4-row K-atoms 512 B apart
-                        const uint64_t ad = smem_desc(sF + kg * 1024, 4096, 512, 1);
+                        // NCHW: 4 M-atoms (32 x's) 4096 B apart; each MMA spans two 4-row K-atoms 512 B apart
+                        // NHWC: K-major rows of 128 B, 8 channels (32 B) per MMA
+                        const uint64_t ad = NHWC ? smem_desc(sF + kg * 32, 16, 1024) : smem_desc(sF + kg * 1024, 4096, 512, 1);
 #pragma unroll
                         for (int h = 0; h < Cfg::NHALF; ++h) {
                             const uint64_t bd = smem_desc(sS + h * 256 * 128 + kg * 32, 16, 1024);
@@ -374,12 +419,23 @@ k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__
             const int64_t x = (item % chunks) * 128 + q * 32 + lane;
             mbar_wait(accf0 + 8 * a, aph);
             tc_fence_after();
-            float* out = grad_feat + (int64_t)b * C * HW + x;
+            float* out = NHWC ? grad_feat + ((int64_t)b * HW + x) * C : grad_feat + (int64_t)b * C * HW + x;
 #pragma unroll 1
             for (int c0 = 0; c0 < C; c0 += 32) {
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * C + c0), r);
                 if (x < HW) {
-                    if (accumulate) {
+                    if (NHWC) {
+                        float4* o4 = reinterpret_cast<float4*>(out + c0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 v = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                            if (accumulate) {
+                                const float4 o = o4[j];
+                                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                            }
+                            o4[j] = v;
+                        }
+                    } else if (accumulate) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) out[(int64_t)(c0 + j) * HW] += r[j];
                     } else {
@@ -443,39 +499,67 @@ static inline int make_map(CUtensorMap* m, const float* base, uint64_t rows, uin
     return ST3D_OK;
 }
 
-template <int C>
+// 3D fp32 tensor [B][HW][C] (C contiguous), box [1][box_rows][32 channels]; rows past HW read as zeros
+static inline int make_map_nhwc(CUtensorMap* m, const float* base, uint64_t B, uint64_t HW, uint64_t C, uint32_t box_rows,
+                                CUtensorMapSwizzle swizzle) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        st3d_set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return ST3D_ERR_CUDA;
+    }
+    const cuuint64_t dims[3] = {C, HW, B};
+    const cuuint64_t strides[2] = {C * sizeof(float), HW * C * sizeof(float)};
+    const cuuint32_t box[3] = {32, box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    static const bool plain = [] { const char* e = getenv("ST3D_TMA_PLAIN_FP32"); return e && e[0] == '1'; }();
+    const CUresult r = fn(m, plain ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 3,
+                          const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        st3d_set_error("cuTensorMapEncodeTiled (NHWC) failed with CUresult %d (B=%llu HW=%llu C=%llu)", (int)r,
+                       (unsigned long long)B, (unsigned long long)HW, (unsigned long long)C);
+        return ST3D_ERR_CUDA;
+    }
+    return ST3D_OK;
+}
+
+template <int C, bool NHWC>
 static int launch_fwd(const float* feat, const GramPlan& p, cudaStream_t s) {
     using Cfg = FwdCfg<C>;
     CUtensorMap map;
-    int rc = make_map(&map, feat, (uint64_t)p.B * C, (uint64_t)p.HW, Cfg::BOX_ROWS);
+    int rc = NHWC ? make_map_nhwc(&map, feat, p.B, p.HW, C, 32 * Cfg::KPS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+                  : make_map(&map, feat, (uint64_t)p.B * C, (uint64_t)p.HW, Cfg::BOX_ROWS);
     if (rc != ST3D_OK) return rc;
     static bool attr_done = false;
     if (!attr_done) {
-        ST3D_CUDA_OK(cudaFuncSetAttribute(k_gram_tc_fwd<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        ST3D_CUDA_OK(cudaFuncSetAttribute(k_gram_tc_fwd<C, NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)Cfg::SMEM));
         attr_done = true;
     }
-    k_gram_tc_fwd<C><<<dim3(Cfg::GROUPS, p.splits, p.B), kThreads, Cfg::SMEM, s>>>(map, p.partials, p.splits, p.k_chunk,
-                                                                                  p.HW);
+    k_gram_tc_fwd<C, NHWC><<<dim3(Cfg::GROUPS, p.splits, p.B), kThreads, Cfg::SMEM, s>>>(map, p.partials, p.splits,
+                                                                                        p.k_chunk, p.HW);
     ST3D_LAUNCH_OK("k_gram_tc_fwd");
     return ST3D_OK;
 }
 
-template <int C>
+template <int C, bool NHWC>
 static int launch_bwd(const float* feat, const GramPlan& p, int accumulate, float* grad_feat, cudaStream_t s) {
     using Cfg = BwdCfg<C>;
     CUtensorMap map_f, map_s;
-    int rc = make_map(&map_f, feat, (uint64_t)p.B * C, (uint64_t)p.HW, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    int rc = NHWC ? make_map_nhwc(&map_f, feat, p.B, p.HW, C, 128, CU_TENSOR_MAP_SWIZZLE_128B)
+                  : make_map(&map_f, feat, (uint64_t)p.B * C, (uint64_t)p.HW, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc != ST3D_OK) return rc;
     rc = make_map(&map_s, p.sym, (uint64_t)p.B * C, (uint64_t)C, Cfg::S_BOX_ROWS);
     if (rc != ST3D_OK) return rc;
     static bool attr_done = false;
     if (!attr_done) {
-        ST3D_CUDA_OK(cudaFuncSetAttribute(k_gram_tc_bwd<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        ST3D_CUDA_OK(cudaFuncSetAttribute(k_gram_tc_bwd<C, NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)Cfg::SMEM));
         attr_done = true;
     }
     const int64_t items = (int64_t)p.B * ((p.HW + 127) / 128);
     const int grid = (int)std::min<int64_t>(items, 148);
-    k_gram_tc_bwd<C><<<grid, kThreads, Cfg::SMEM, s>>>(map_f, map_s, grad_feat, p.B, p.HW, accumulate);
+    k_gram_tc_bwd<C, NHWC><<<grid, kThreads, Cfg::SMEM, s>>>(map_f, map_s, grad_feat, p.B, p.HW, accumulate);
     ST3D_LAUNCH_OK("k_gram_tc_bwd");
     return ST3D_OK;
 }
@@ -486,24 +570,29 @@ static inline bool gram_tc_supported(int C, int64_t HW) {
     return (C == 64 || C == 128 || C == 256 || C == 512) && HW % 4 == 0 && HW >= 32;
 }
 
-static inline int gram_tc_forward(const float* feat, const GramPlan& p, cudaStream_t s) {
+static inline int gram_tc_forward(const float* feat, const GramPlan& p, bool nhwc, cudaStream_t s) {
+#define ST3D_FWD(CC) return nhwc ? tc::launch_fwd<CC, true>(feat, p, s) : tc::launch_fwd<CC, false>(feat, p, s)
     switch (p.C) {
-        case 64: return tc::launch_fwd<64>(feat, p, s);
-        case 128: return tc::launch_fwd<128>(feat, p, s);
-        case 256: return tc::launch_fwd<256>(feat, p, s);
-        case 512: return tc::launch_fwd<512>(feat, p, s);
+        case 64: ST3D_FWD(64);
+        case 128: ST3D_FWD(128);
+        case 256: ST3D_FWD(256);
+        case 512: ST3D_FWD(512);
     }
+#undef ST3D_FWD
     return ST3D_ERR_UNSUPPORTED;
 }
 
-static inline int gram_tc_backward(const float* feat, const GramPlan& p, int accumulate, float* grad_feat,
+static inline int gram_tc_backward(const float* feat, const GramPlan& p, bool nhwc, int accumulate, float* grad_feat,
                                    cudaStream_t s) {
+#define ST3D_BWD(CC) \
+    return nhwc ? tc::launch_bwd<CC, true>(feat, p, accumulate, grad_feat, s) : tc::launch_bwd<CC, false>(feat, p, accumulate, grad_feat, s)
     switch (p.C) {
-        case 64: return tc::launch_bwd<64>(feat, p, accumulate, grad_feat, s);
-        case 128: return tc::launch_bwd<128>(feat, p, accumulate, grad_feat, s);
-        case 256: return tc::launch_bwd<256>(feat, p, accumulate, grad_feat, s);
-        case 512: return tc::launch_bwd<512>(feat, p, accumulate, grad_feat, s);
+        case 64: ST3D_BWD(64);
+        case 128: ST3D_BWD(128);
+        case 256: ST3D_BWD(256);
+        case 512: ST3D_BWD(512);
     }
+#undef ST3D_BWD
     return ST3D_ERR_UNSUPPORTED;
 }
 

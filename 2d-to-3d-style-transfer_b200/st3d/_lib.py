@@ -50,9 +50,9 @@ SIGNATURES = {
     "st3d_render_forward": (c_i, [ctypes.POINTER(RenderArgs), c_p]),
     "st3d_render_backward": (c_i, [ctypes.POINTER(RenderArgs), c_p, c_p, c_p, c_p, c_p]),
     "st3d_gram_workspace_size": (c_sz, [c_i, c_i, c_i64]),
-    "st3d_gram_forward": (c_i, [c_p, c_i, c_i, c_i64, c_p, c_p, c_sz, c_i, c_p]),
-    "st3d_gram_mse_forward": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i64, c_f, c_p, c_p, c_p, c_p, c_sz, c_i, c_p]),
-    "st3d_gram_backward": (c_i, [c_p, c_p, c_i, c_i, c_i64, c_f, c_p, c_i, c_p, c_p, c_sz, c_i, c_p]),
+    "st3d_gram_forward": (c_i, [c_p, c_i, c_i, c_i64, c_p, c_p, c_sz, c_i, c_i, c_p]),
+    "st3d_gram_mse_forward": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i64, c_f, c_p, c_p, c_p, c_p, c_sz, c_i, c_i, c_p]),
+    "st3d_gram_backward": (c_i, [c_p, c_p, c_i, c_i, c_i64, c_f, c_p, c_i, c_p, c_p, c_sz, c_i, c_i, c_p]),
     "st3d_mse_forward": (c_i, [c_p, c_p, c_p, c_i64, c_i64, c_i, c_f, c_p, c_p, c_p]),
 }
 

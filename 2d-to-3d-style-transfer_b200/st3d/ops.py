@@ -357,13 +357,24 @@ def _precision(precision, C: int, HW: int) -> int:
         raise ValueError(f"precision must be 'tf32', 'fp32' or None, got {precision!r}") from None
 
 
+FEAT_NCHW, FEAT_NHWC = 0, 1
+
+
 def _feat3(name, feat):
-    feat = _cuda_f32(name, feat)
+    """-> (tensor whose storage the kernel reads, layout, (B, C, HW)).  A channels_last (B,C,H,W) tensor is
+    passed as is (its storage is (B, HW, C)); anything else is made (B, C, HW)-contiguous."""
+    if not isinstance(feat, torch.Tensor) or not feat.is_cuda:
+        raise St3dError(f"{name}: expected a CUDA tensor (st3d has no CPU path; the CPU oracle is test-only)")
+    if feat.dtype != torch.float32:
+        raise ValueError(f"{name}: expected float32, got {feat.dtype}")
     if feat.dim() == 4:
-        feat = feat.reshape(feat.shape[0], feat.shape[1], -1)
+        B, C, H, W = feat.shape
+        if C > 1 and H * W > 1 and feat.is_contiguous(memory_format=torch.channels_last) and not feat.is_contiguous():
+            return feat, FEAT_NHWC, (B, C, H * W)
+        return feat.contiguous().reshape(B, C, H * W), FEAT_NCHW, (B, C, H * W)
     if feat.dim() != 3:
         raise ValueError(f"{name}: expected (B,C,H,W) or (B,C,HW)")
-    return feat
+    return feat.contiguous(), FEAT_NCHW, tuple(feat.shape)
 
 
 def _gram_ws(B, C, HW, device):
@@ -372,23 +383,21 @@ def _gram_ws(B, C, HW, device):
 
 
 def gram_forward(feat, precision=None):
-    """(B,C,H,W) -> (B,C,C) = F F^T."""
-    f = _feat3("feat", feat)
-    B, C, HW = f.shape
+    """(B,C,H,W) -> (B,C,C) = F F^T.  NCHW-contiguous and channels_last inputs are both read in place."""
+    f, layout, (B, C, HW) = _feat3("feat", feat)
     out = torch.empty((B, C, C), device=f.device, dtype=torch.float32)
     if B == 0:
         return out
     ws, nbytes = _gram_ws(B, C, HW, f.device)
     with _timed("gram_forward", (B, C, HW)):
-        check(lib().st3d_gram_forward(_p(f), B, C, HW, _p(out), _p(ws), nbytes, _precision(precision, C, HW), _stream()),
-              "st3d_gram_forward")
+        check(lib().st3d_gram_forward(_p(f), B, C, HW, _p(out), _p(ws), nbytes, _precision(precision, C, HW), layout,
+                                      _stream()), "st3d_gram_forward")
     return out
 
 
 def gram_mse_forward(feat, target, scale: float, loss_out, want_gram=False, precision=None):
     """loss_out[0] += scale * sum((F F^T - target)^2); returns (dgram, gram|None)."""
-    f = _feat3("feat", feat)
-    B, C, HW = f.shape
+    f, layout, (B, C, HW) = _feat3("feat", feat)
     target = _cuda_f32("target", target, C, C).reshape(-1, C, C)
     if target.shape[0] not in (1, B):
         raise ValueError(f"target batch {target.shape[0]} is neither 1 nor {B}")
@@ -399,35 +408,42 @@ def gram_mse_forward(feat, target, scale: float, loss_out, want_gram=False, prec
     ws, nbytes = _gram_ws(B, C, HW, f.device)
     with _timed("gram_mse_forward", (B, C, HW)):
         check(lib().st3d_gram_mse_forward(_p(f), _p(target), B, target.shape[0], C, HW, float(scale), _p(gram), _p(dgram),
-                                          _p(loss_out), _p(ws), nbytes, _precision(precision, C, HW), _stream()),
+                                          _p(loss_out), _p(ws), nbytes, _precision(precision, C, HW), layout, _stream()),
               "st3d_gram_mse_forward")
     return dgram, gram
 
 
 def gram_backward(feat, dgram, grad_scale: float = 1.0, out=None, accumulate=False, precision=None, scale_tensor=None):
-    """grad_feat = grad_scale * [scale_tensor] * (dG + dG^T) F, shaped like feat (scale_tensor: 1-element CUDA tensor)."""
-    f = _feat3("feat", feat)
-    B, C, HW = f.shape
+    """grad_feat = grad_scale * [scale_tensor] * (dG + dG^T) F, with the shape AND memory layout of feat
+    (scale_tensor: 1-element CUDA tensor).  `out`, when given, must have feat's layout."""
+    f, layout, (B, C, HW) = _feat3("feat", feat)
     dgram = _cuda_f32("dgram", dgram, C, C).reshape(B, C, C)
     if out is None:
-        out = torch.empty_like(f)
+        out = torch.empty_like(f)           # preserve_format: channels_last stays channels_last
         accumulate = False
+    else:
+        if out.shape != f.shape or out.stride() != f.stride() or out.dtype != torch.float32 or not out.is_cuda:
+            raise ValueError("gram_backward: `out` must match the (normalised) feature tensor in shape and strides")
     ws, nbytes = _gram_ws(B, C, HW, f.device)
     if scale_tensor is not None:
         scale_tensor = _cuda_f32("scale_tensor", scale_tensor).reshape(1)
     with _timed("gram_backward", (B, C, HW)):
         check(lib().st3d_gram_backward(_p(f), _p(dgram), B, C, HW, float(grad_scale), _p(scale_tensor), int(accumulate),
-                                       _p(out), _p(ws), nbytes, _precision(precision, C, HW), _stream()),
+                                       _p(out), _p(ws), nbytes, _precision(precision, C, HW), layout, _stream()),
               "st3d_gram_backward")
-    return out.reshape(feat.shape)
+    return out if layout == FEAT_NHWC else out.reshape(feat.shape)
 
 
 def mse_forward(a, b, scale: float, loss_out, mask=None, want_grad=True):
     """loss_out[0] += scale * sum(m (a-b)^2); returns grad wrt a (or None).  mask: (B,1,H,W) for a (B,Cm,H,W)."""
-    a = _cuda_f32("a", a)
-    b = _cuda_f32("b", b)
     if a.shape != b.shape:
         raise ValueError(f"shape mismatch {tuple(a.shape)} vs {tuple(b.shape)}")
+    same_dense_layout = (mask is None and isinstance(a, torch.Tensor) and isinstance(b, torch.Tensor) and a.dim() == 4
+                         and a.is_cuda and b.is_cuda and a.dtype == b.dtype == torch.float32 and a.stride() == b.stride()
+                         and a.is_contiguous(memory_format=torch.channels_last))
+    if not same_dense_layout:       # an elementwise reduction does not care about the order of a dense layout
+        a = _cuda_f32("a", a)
+        b = _cuda_f32("b", b)
     inner, mask_ch = 1, 1
     if mask is not None:
         mask = _cuda_f32("mask", mask)

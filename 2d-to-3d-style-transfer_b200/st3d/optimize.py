@@ -39,7 +39,7 @@ class TextureStyleOptimizer:
 
     def __init__(self, verts, faces, verts_uvs, faces_uvs, texture, vgg, image_size, lr: float = 0.01,
                  style_weight: float = 1e6, content_weight: float = 1.0, precision=None,
-                 cache_constants: bool = False, world_size: int = 1, group=None):
+                 cache_constants: bool = False, world_size: int = 1, group=None, channels_last: bool = True):
         dev = verts.device
         if dev.type != "cuda":
             raise RuntimeError("TextureStyleOptimizer needs CUDA tensors: libst3d has no CPU path")
@@ -48,7 +48,10 @@ class TextureStyleOptimizer:
         self.face_uvs = verts_uvs.float()[faces_uvs.long()].contiguous()          # (F,3,2)
         self.content_texture = texture.detach().clone().float().contiguous()     # the mesh as loaded
         self.texture = texture.detach().clone().float().contiguous().requires_grad_(True)
-        self.vgg = vgg
+        # cuDNN's tensor-core convolutions are NHWC kernels: with NCHW tensors torch wraps every conv in
+        # nchw<->nhwc transposes (~20 % of a step).  channels_last keeps activations NHWC end to end.
+        self.channels_last = channels_last
+        self.vgg = vgg.to(memory_format=torch.channels_last) if channels_last else vgg
         self.image_size = image_size
         self.style_weight, self.content_weight = style_weight, content_weight
         self.precision = precision
@@ -57,6 +60,9 @@ class TextureStyleOptimizer:
         self.optimizer = torch.optim.Adam([self.texture], lr=lr)
         self._cache = {}
         self.last_images: Optional[torch.Tensor] = None
+
+    def _nn_input(self, images):
+        return images.contiguous(memory_format=torch.channels_last) if self.channels_last else images
 
     def _render(self, texture, R, T):
         images, masks, _ = Fn.render_views(self.verts, self.faces, R, T, self.image_size, texture=texture,
@@ -72,12 +78,13 @@ class TextureStyleOptimizer:
         else:
             with torch.no_grad():
                 content_imgs, _ = self._render(self.content_texture, R, T)                     # second_approach.py:160
-                content_feat = losses.get_features(content_imgs, self.vgg, {"21": losses.CONTENT_LAYER})[losses.CONTENT_LAYER]
-            grams = losses.style_targets(style_img, self.vgg, self.precision)                   # losses.py:19-25
+                content_feat = losses.get_features(self._nn_input(content_imgs), self.vgg,
+                                                   {"21": losses.CONTENT_LAYER})[losses.CONTENT_LAYER]
+            grams = losses.style_targets(self._nn_input(style_img), self.vgg, self.precision)                   # losses.py:19-25
             if self.cache_constants:
                 self._cache = dict(key=key, content_feat=content_feat, grams=grams)
         current_imgs, _ = self._render(self.texture, R, T)                                      # :165
-        cur = losses.get_features(current_imgs, self.vgg)
+        cur = losses.get_features(self._nn_input(current_imgs), self.vgg)
         loss = losses.perceptual_loss_from_features(cur, content_feat, grams, self.style_weight, self.content_weight,
                                                     self.precision)
         (loss / self.world_size).backward()                                                     # :188

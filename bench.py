@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument("--views", type=int, default=8, help="views per GPU")
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--nchw", action="store_true", help="keep VGG activations NCHW (torch default) instead of channels_last")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the e2e / cached-constants legs")
     ap.add_argument("--profile-run", action="store_true",
@@ -92,7 +93,8 @@ def workload_config(args, world):
         "faces": 5856, "verts": 2930, "texture": f"{args.size}x{args.size}x3", "target": "texture",
         "style_weight": 1e6, "content_weight": 1, "lr": 0.01, "parallelism": f"view-sharded dp{world}",
         "vgg": "torchvision VGG-19 .features, seeded random init (ImageNet weights unavailable offline), fp32 cuDNN "
-               "(torch default allow_tf32), inside the timed step",
+               "(torch default allow_tf32), activations " + ("NCHW" if args.nchw else "channels_last (NHWC)") +
+               ", inside the timed step",
         "l2": "per-step working set (VGG activations of 8 x 512^2 images, > 4 GB) exceeds the 126 MB L2; no explicit flush",
     }
 
@@ -249,7 +251,8 @@ def run_st3d(args):
     def make(cache):
         return TextureStyleOptimizer(w["verts"].to(dev), w["faces"].to(dev), w["verts_uvs"].to(dev),
                                      w["faces_uvs"].to(dev), w["texture"].to(dev), vgg, args.size, lr=0.01,
-                                     precision=args.precision, cache_constants=cache, world_size=world)
+                                     precision=args.precision, cache_constants=cache, world_size=world,
+                                     channels_last=not args.nchw)
 
     def barrier():
         if world > 1:

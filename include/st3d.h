@@ -166,18 +166,24 @@ int st3d_render_backward(const st3d_render_args* args, const float* grad_image, 
 #define ST3D_GRAM_TF32 0
 #define ST3D_GRAM_FP32 1
 
+/* Memory layout of a feature map `feat` / `grad_feat` with B images, C channels and HW pixels:
+ * ST3D_FEAT_NCHW: (B, C, HW), pixels contiguous (torch default);  ST3D_FEAT_NHWC: (B, HW, C), channels
+ * contiguous (torch channels_last -- what cuDNN's tensor-core convolutions produce without transposes). */
+#define ST3D_FEAT_NCHW 0
+#define ST3D_FEAT_NHWC 1
+
 /* gram_matrix (style_transfer.py:31-35): feat (B,C,HW) fp32 -> gram (B,C,C) = F F^T, split-K with a
  * deterministic fixed-order reduction of the partial sums held in the workspace. */
 size_t st3d_gram_workspace_size(int B, int C, int64_t HW);
 int st3d_gram_forward(const float* feat, int B, int C, int64_t HW, float* gram, void* workspace,
-                      size_t workspace_bytes, int precision, st3d_stream_t stream);
+                      size_t workspace_bytes, int precision, int layout, st3d_stream_t stream);
 
 /* One style layer of losses.py:35-39 fused: G = F F^T, loss_out[0] += scale * sum((G - G_target)^2),
  * dgram (B,C,C) = 2 * scale * (G - G_target).  scale = weight / (B*C*C) / (C*C*H*H) is supplied by
  * the caller; target (Bt,C,C) with Bt in {1,B} (broadcast).  gram and dgram may be NULL. */
 int st3d_gram_mse_forward(const float* feat, const float* target, int B, int Bt, int C, int64_t HW,
                           float scale, float* gram, float* dgram, float* loss_out, void* workspace,
-                          size_t workspace_bytes, int precision, st3d_stream_t stream);
+                          size_t workspace_bytes, int precision, int layout, st3d_stream_t stream);
 
 /* Backward of gram_matrix: grad_feat (B,C,HW) = s * (dG + dG^T) F with s = grad_scale, times the device
  * scalar *grad_scale_dev when that pointer is not NULL (autograd's upstream gradient, applied without
@@ -185,7 +191,7 @@ int st3d_gram_mse_forward(const float* feat, const float* target, int B, int Bt,
  * by st3d_gram_workspace_size. */
 int st3d_gram_backward(const float* feat, const float* dgram, int B, int C, int64_t HW, float grad_scale,
                        const float* grad_scale_dev, int accumulate, float* grad_feat, void* workspace,
-                       size_t workspace_bytes, int precision, st3d_stream_t stream);
+                       size_t workspace_bytes, int precision, int layout, st3d_stream_t stream);
 
 /* mean((a-b)^2) family (losses.py:31 content loss; losses.py:71-75 masked MSE):
  * loss_out[0] += scale * sum(m*(a-b)^2); grad_a = 2*scale*m*(a-b) (NULL to skip).

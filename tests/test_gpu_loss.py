@@ -159,3 +159,53 @@ def test_gram_full_size_properties():
         dF = ops.gram_backward(f, dG, 1.0, precision="tf32")
         dF32 = ops.gram_backward(f, dG, 1.0, precision="fp32")
         assert _relerr(dF, dF32) <= TOL_TC
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", TOL_FP32), ("tf32", TOL_TC)])
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 32, 32), (3, 64, 20, 12), (2, 128, 16, 24), (1, 256, 16, 16), (2, 256, 12, 20),
+                                       (2, 512, 8, 8), (1, 512, 16, 12), (8, 64, 24, 24)])
+def test_gram_channels_last_features(precision, tol, B, C, H, W):
+    """channels_last (NHWC) feature maps -- what a channels_last VGG hands over -- are read in place:
+    MN-major tcgen05 operands forward, K-major backward, gradient returned channels_last."""
+    ops = _ops()
+    f = _features(B, C, H, W, 11)
+    fcl = f.cuda().contiguous(memory_format=torch.channels_last)
+    assert not fcl.is_contiguous()
+    style = lo.gram_matrix(_features(1, C, H, W, 12).double())
+    f64 = f.double().requires_grad_(True)
+    scale = 1e6 / (B * C * C) / (C * C * H * H)
+    want = 1e6 * lo.style_layer_loss(f64, style)
+    want.backward()
+    G = ops.gram_forward(fcl, precision=precision)
+    assert _relerr(G, lo.gram_matrix(f.double())) <= tol
+    assert torch.equal(G, ops.gram_forward(fcl, precision=precision))            # deterministic
+    loss = torch.zeros(1, device="cuda")
+    dgram, _ = ops.gram_mse_forward(fcl, style.float().cuda(), scale, loss, precision=precision)
+    assert abs(loss.item() - want.item()) <= 2 * tol * abs(want.item())
+    grad = ops.gram_backward(fcl, dgram, 1.0, precision=precision)
+    assert grad.shape == f.shape and grad.is_contiguous(memory_format=torch.channels_last)
+    assert _relerr(grad, f64.grad) <= 2 * tol, _relerr(grad, f64.grad)
+    # same numbers as the NCHW path up to the arithmetic mode
+    grad_nchw = ops.gram_backward(f.cuda(), dgram, 1.0, precision=precision)
+    assert _relerr(grad, grad_nchw.double()) <= 2 * tol
+    # accumulate into an existing channels_last buffer
+    base = torch.ones_like(fcl)
+    got = ops.gram_backward(fcl, dgram, 0.5, out=base, accumulate=True, precision=precision)
+    assert _relerr(got, 0.5 * f64.grad + 1.0) <= 2 * tol
+
+
+def test_channels_last_autograd_and_mse():
+    import st3d.functional as Fn
+    B, C, H, W = 2, 64, 16, 16
+    f = _features(B, C, H, W, 13)
+    fcl = f.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    tgt = lo.gram_matrix(_features(1, C, H, W, 14).double())
+    loss = 1e6 * Fn.style_layer_loss(fcl, tgt.float().cuda())
+    other = _features(B, C, H, W, 15).cuda().contiguous(memory_format=torch.channels_last)
+    loss = loss + 3.0 * Fn.mse_loss(fcl, other)
+    loss.backward()
+    f64 = f.double().requires_grad_(True)
+    want = 1e6 * lo.style_layer_loss(f64, tgt) + 3.0 * ((f64 - other.cpu().double()) ** 2).mean()
+    want.backward()
+    assert abs(loss.item() - want.item()) <= 4e-3 * abs(want.item())
+    assert _relerr(fcl.grad, f64.grad) <= 4e-3
