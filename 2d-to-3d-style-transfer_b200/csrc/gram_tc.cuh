@@ -310,7 +310,8 @@ struct BwdCfg {
     static constexpr int KB = C / 32;             // k-blocks (32 channels j each) per chunk
     static constexpr int S_BOX_ROWS = C < 256 ? C : 256;
     static constexpr int S_BOXES = C / S_BOX_ROWS;
-    static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 2 * ACC) * 8 + 16;
+    static constexpr int TR_FLOATS = 4 * 32 * 36;  // NHWC epilogue transpose tiles (one per epilogue warp)
+    static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + TR_FLOATS * 4 + (2 * STAGES + 2 * ACC) * 8 + 16;
 };
 
 // NHWC = false: A = F^T tile from rows j of (B, C, HW): MN-major, 32-byte-atom swizzle, four [32 j][32 x] boxes.
@@ -324,7 +325,8 @@ k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* stages = smem;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES);
+    float* tr_scratch = reinterpret_cast<float*>(smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tr_scratch + Cfg::TR_FLOATS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 2 * Cfg::ACC);
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + Cfg::STAGES),
                    accf0 = smem_u32(bars + 2 * Cfg::STAGES), acce0 = smem_u32(bars + 2 * Cfg::STAGES + Cfg::ACC);
@@ -423,19 +425,33 @@ k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__
 #pragma unroll 1
             for (int c0 = 0; c0 < C; c0 += 32) {
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * C + c0), r);
-                if (x < HW) {
-                    if (NHWC) {
-                        float4* o4 = reinterpret_cast<float4*>(out + c0);
+                if (NHWC) {
+                    // r[j] = D[pixel row = lane][channel c0 + j].  Transpose through padded shared memory so that
+                    // one warp store covers 4 pixel rows x 128 contiguous bytes instead of 32 rows x 16 bytes.
+                    float* sc = tr_scratch + q * 32 * 36;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float4 v = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(sc + lane * 36 + 4 * j) =
+                            make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                    __syncwarp();
+                    const int64_t xw = (item % chunks) * 128 + q * 32;  // first pixel row of this warp
+                    float* ow = grad_feat + ((int64_t)b * HW + xw) * C + c0 + 4 * (lane & 7);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int t = 4 * i + (lane >> 3);
+                        if (xw + t < HW) {
+                            float4 v = *reinterpret_cast<const float4*>(sc + t * 36 + 4 * (lane & 7));
+                            float4* o = reinterpret_cast<float4*>(ow + (int64_t)t * C);
                             if (accumulate) {
-                                const float4 o = o4[j];
-                                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                                const float4 old = *o;
+                                v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
                             }
-                            o4[j] = v;
+                            *o = v;
                         }
-                    } else if (accumulate) {
+                    }
+                    __syncwarp();
+                } else if (x < HW) {
+                    if (accumulate) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) out[(int64_t)(c0 + j) * HW] += r[j];
                     } else {

@@ -34,6 +34,9 @@ res["render_backward_tex_us"] = timeit(lambda: ops.render_backward(state["o"][3]
 res["render_backward_tex_verts_us"] = timeit(lambda: ops.render_backward(state["o"][3], g, need_verts=True))
 for C, HW in ((64, S * S), (128, S * S // 4), (256, S * S // 16), (512, S * S // 64), (512, S * S // 256)):
     f = torch.relu(torch.randn(N, C, HW, device=dev))
+    if os.environ.get("NHWC") == "1":
+        side = int(HW ** 0.5)
+        f = f.reshape(N, C, side, HW // side).contiguous(memory_format=torch.channels_last)
     tgt = torch.randn(1, C, C, device=dev); loss = torch.zeros(1, device=dev)
     dg = torch.randn(N, C, C, device=dev)
     t1 = timeit(lambda: ops.gram_mse_forward(f, tgt, 1e-9, loss))
