@@ -4,7 +4,8 @@ cameras, rasterization settings, rasterizer, shader, renderer, textures.
 `MeshRenderer(...)(meshes_world=, cameras=)` runs the FUSED libst3d path (vertex transform -> tile bins
 -> fine raster -> texture sample -> ambient shade -> soft blend in one launch sequence) for every camera
 passed, whether that is one camera (the reference's per-view loop, utils.py:68-69) or a whole batch.
-`MeshRasterizer(...)(meshes)` alone returns Fragments through the operator-boundary kernels.
+`MeshRasterizer(...)(meshes)` alone returns Fragments through the operator-boundary kernels; Point /
+Directional lights and faces_per_pixel > 1 take the general path (Fragments + shading.py).
 """
 from __future__ import annotations
 
@@ -141,6 +142,8 @@ class Materials:
 class AmbientLights:
     """Ambient-only lighting: diffuse = specular = 0, so pixel colour = ambient * texel (A.5)."""
 
+    kind = "ambient"
+
     def __init__(self, ambient_color=((1.0, 1.0, 1.0),), device="cpu"):
         self.ambient_color, self.device = _color(ambient_color), device
 
@@ -149,18 +152,30 @@ class AmbientLights:
         return self
 
 
-class _DirectionalOrPoint:
-    def __init__(self, *a, **k):
-        raise NotImplementedError(f"{type(self).__name__}: only AmbientLights (the reference's lighting, "
-                                  "first_approach.py:108) is implemented by the fused libst3d shader")
+class PointLights:
+    kind = "point"
+
+    def __init__(self, ambient_color=((0.5, 0.5, 0.5),), diffuse_color=((0.3, 0.3, 0.3),),
+                 specular_color=((0.2, 0.2, 0.2),), location=((0, 1, 0),), device="cpu"):
+        self.ambient_color, self.diffuse_color = _color(ambient_color), _color(diffuse_color)
+        self.specular_color, self.location, self.device = _color(specular_color), _color(location), device
+
+    def to(self, device):
+        self.device = device
+        return self
 
 
-class PointLights(_DirectionalOrPoint):
-    pass
+class DirectionalLights:
+    kind = "directional"
 
+    def __init__(self, ambient_color=((0.5, 0.5, 0.5),), diffuse_color=((0.3, 0.3, 0.3),),
+                 specular_color=((0.2, 0.2, 0.2),), direction=((0, 1, 0),), device="cpu"):
+        self.ambient_color, self.diffuse_color = _color(ambient_color), _color(diffuse_color)
+        self.specular_color, self.direction, self.device = _color(specular_color), _color(direction), device
 
-class DirectionalLights(_DirectionalOrPoint):
-    pass
+    def to(self, device):
+        self.device = device
+        return self
 
 
 class Fragments(NamedTuple):
@@ -247,8 +262,23 @@ class SoftPhongShader(torch.nn.Module):
         return self
 
     def forward(self, fragments, meshes, **kwargs):
-        raise NotImplementedError("SoftPhongShader is fused into the rasterizer epilogue: call it through "
-                                  "MeshRenderer(rasterizer, shader)(meshes_world=..., cameras=...)")
+        """General path (any lights, any faces_per_pixel) on top of Fragments; see shading.py."""
+        from . import shading
+        cams, (fov, aspect, znear, zfar) = _camera_params(kwargs.get("cameras", self.cameras))
+        lights = kwargs.get("lights", self.lights)
+        materials = kwargs.get("materials", self.materials)
+        blend = kwargs.get("blend_params", self.blend_params)
+        verts, faces = _one_mesh(meshes)
+        tex = meshes.textures
+        if isinstance(tex, TexturesUV):
+            texels = shading.sample_textures_uv(fragments, tex, faces.shape[0])
+        elif isinstance(tex, TexturesVertex):
+            texels = shading.sample_textures_vertex(fragments, tex, faces, faces.shape[0])
+        else:
+            raise ValueError("meshes.textures must be TexturesUV or TexturesVertex")
+        colors = shading.phong_shading(fragments, verts, faces, texels, lights, materials,
+                                       cams.get_camera_center().to(verts.device))
+        return shading.softmax_rgb_blend(colors, fragments, blend, znear, zfar)
 
 
 class MeshRenderer(torch.nn.Module):
@@ -294,7 +324,16 @@ class MeshRenderer(torch.nn.Module):
             raise ValueError("meshes_world.textures must be TexturesUV or TexturesVertex")
         return verts, faces, R, T, _image_hw(rs.image_size), tex_kw, common
 
+    def _can_fuse(self, kwargs):
+        rs = kwargs.get("raster_settings", self.rasterizer.raster_settings)
+        lights = kwargs.get("lights", self.shader.lights)
+        return (isinstance(lights, AmbientLights) and rs.faces_per_pixel == 1 and not rs.cull_to_frustum
+                and rs.perspective_correct is not False and rs.clip_barycentric_coords in (None, rs.blur_radius > 0.0))
+
     def forward(self, meshes_world, **kwargs):
+        if not self._can_fuse(kwargs):       # Phong lights / K > 1: Fragments + general shader
+            fragments = self.rasterizer(meshes_world, **kwargs)
+            return self.shader(fragments, meshes_world, **kwargs)
         verts, faces, R, T, size, tex_kw, common = self._fused_args(meshes_world, kwargs)
         rgba, _ = _fn.render_views(verts, faces, R, T, size, planar=False, **tex_kw, **common)
         return rgba
@@ -302,6 +341,9 @@ class MeshRenderer(torch.nn.Module):
     def render_planar(self, meshes_world, **kwargs):
         """Batched fast path used by this repo's `utils.render_meshes`: ((N,3,H,W) images, (N,1,H,W) masks)
         straight from the kernel epilogue -- no permute / compare / stack passes."""
+        if not self._can_fuse(kwargs):
+            rgba = self.forward(meshes_world, **kwargs)
+            return rgba[..., :3].permute(0, 3, 1, 2).contiguous(), (rgba[..., 3:4] > 0).to(rgba.dtype).permute(0, 3, 1, 2)
         verts, faces, R, T, size, tex_kw, common = self._fused_args(meshes_world, kwargs)
         images, masks, _ = _fn.render_views(verts, faces, R, T, size, planar=True, **tex_kw, **common)
         return images, masks

@@ -152,5 +152,4 @@ def test_renderer_fails_loudly_on_cpu():
     mesh = utils.build_mesh(torch.rand(1, 3, 2), faces[None], torch.rand(1, 4, 4, 3), torch.rand(3, 3), faces)
     with pytest.raises(RuntimeError):
         renderer(meshes_world=mesh, cameras=cams)
-    with pytest.raises(NotImplementedError):
-        PointLights()
+    assert PointLights().kind == "point"

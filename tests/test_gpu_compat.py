@@ -211,3 +211,41 @@ def test_runner_resolves_modules_to_compat(tmp_path):
     assert out.returncode == 0, out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("OK")][0]
     assert "st3d" in line and line.count(os.path.join("compat", "")) == 3
+
+
+def test_general_shader_path_matches_fused_and_oracle(scene):
+    """PointLights / faces_per_pixel > 1 go through Fragments + the general shader (operator-boundary kernels +
+    elementwise torch): must equal the fused path where both apply, and the oracle's Phong + K-face blend."""
+    from pytorch3d.renderer import (AmbientLights, BlendParams, MeshRasterizer, MeshRenderer, PointLights,
+                                    RasterizationSettings, SoftPhongShader)
+    sc = scene
+    dev, cams = sc["dev"], sc["cameras"]
+    # (1) ambient, K = 1 through the general path == fused path
+    rs = RasterizationSettings(image_size=S, blur_radius=0.0, faces_per_pixel=1)
+    rast = MeshRasterizer(cameras=cams, raster_settings=rs)
+    shader = SoftPhongShader(device=dev, cameras=cams, lights=AmbientLights(device=dev))
+    general = shader(rast(sc["mesh"]), sc["mesh"], cameras=cams)
+    fused = MeshRenderer(rast, shader)(meshes_world=sc["mesh"], cameras=cams)
+    assert (general - fused).abs().max() <= 1e-5
+    # (2) point light, K = 3, soft blend: against the oracle
+    rs3 = RasterizationSettings(image_size=S, blur_radius=2e-4, faces_per_pixel=3)
+    lights = PointLights(location=((1.0, 2.0, -2.0),), device=dev)
+    blend = BlendParams(sigma=1e-4, gamma=1e-4, background_color=(0.2, 0.4, 0.6))
+    renderer = MeshRenderer(MeshRasterizer(cameras=cams, raster_settings=rs3),
+                            SoftPhongShader(device=dev, cameras=cams, lights=lights, blend_params=blend))
+    tex = sc["mesh"].textures.maps_padded().clone().requires_grad_(True)
+    import utils
+    mesh = utils.build_mesh(sc["mesh"].textures.verts_uvs_padded(), sc["mesh"].textures.faces_uvs_padded(), tex,
+                            sc["mesh"].verts_packed(), sc["mesh"].faces_packed())
+    rgba = renderer(meshes_world=mesh, cameras=cams)
+    wgt = torch.randn(rgba.shape, generator=torch.Generator().manual_seed(5)).to(dev)
+    (rgba * wgt).sum().backward()
+    tex_o = sc["tex"][0].clone().requires_grad_(True)
+    want = ro.render_views(sc["verts"], sc["faces"], cams.R.cpu(), cams.T.cpu(), S, texture=tex_o,
+                           verts_uvs=sc["verts_uvs"], faces_uvs=sc["faces_uvs"], blur_radius=2e-4, faces_per_pixel=3,
+                           background=(0.2, 0.4, 0.6), nthreads=8,
+                           lights=dict(kind="point", ambient=(0.5,) * 3, diffuse=(0.3,) * 3, specular=(0.2,) * 3,
+                                       location=(1.0, 2.0, -2.0)))
+    assert (rgba.detach().cpu() - want.detach()).abs().max() <= 2e-4
+    (want * wgt.cpu()).sum().backward()
+    assert ((tex.grad[0].cpu() - tex_o.grad).abs().max() / tex_o.grad.abs().max()).item() <= 1e-3

@@ -312,3 +312,33 @@ def test_dense_mesh_two_algorithms_agree(cow):
     g = torch.randn_like(img)
     g_tex, g_verts, _ = ops.render_backward(state, g, need_verts=True)
     assert torch.isfinite(g_tex).all() and torch.isfinite(g_verts).all() and g_tex.abs().sum() > 0
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_random_triangle_soups_bit_exact(seed):
+    """Random triangle soups incl. slivers, huge and off-screen triangles, faces crossing z = 0 and exact
+    duplicates (z ties): pix_to_face must match the oracle bit for bit for K = 1 (z-buffer path) and K = 4
+    (K-best scan), hard and soft, square and non-square images."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(100 + seed)
+    n = 300
+    centre = torch.rand(n, 1, 2, generator=g) * 2.4 - 1.2
+    size = torch.rand(n, 1, 1, generator=g) ** 3 * 1.5 + 0.01
+    xy = centre + (torch.rand(n, 3, 2, generator=g) - 0.5) * size
+    z = torch.rand(n, 1, 1, generator=g) * 4 + 0.5 + (torch.rand(n, 3, 1, generator=g) - 0.5) * 0.8
+    tris = torch.cat([xy, z], dim=-1)
+    tris[:10, :, 2] -= 3.0                                   # some faces behind / straddling the camera plane
+    tris[10:20, 2] = tris[10:20, 0] * 0.5 + tris[10:20, 1] * 0.5   # degenerate (zero area)
+    tris[20:30] = tris[30:40]                                # exact duplicates: z ties -> lower index wins
+    tris[40:45, :, :2] *= 20.0                               # huge triangles covering the whole image
+    first, num = torch.tensor([0, 150]), torch.tensor([150, 150])   # two "meshes" (views) in one call
+    for size_hw, K, blur in (((64, 64), 1, 0.0), ((40, 72), 1, 0.0), ((48, 48), 4, 0.0), ((32, 56), 3, 1e-3)):
+        clip = blur > 0
+        want = ro.rasterize_naive(tris, first, num, size_hw, blur, K, True, clip, False, nthreads=8)
+        got = ops.rasterize_meshes(tris.cuda(), first.cuda(), num.cuda(), size_hw, blur, K, 0, 0, True, clip, False)
+        torch.cuda.synchronize()
+        ops.poll_overflow(block=True)
+        assert torch.equal(got[0].cpu(), want[0]), (seed, size_hw, K, blur)
+        m = want[0] >= 0
+        assert torch.allclose(got[1].cpu()[m], want[1][m], rtol=1e-5, atol=1e-6)
+        assert torch.allclose(got[2].cpu()[m], want[2][m], rtol=1e-4, atol=1e-5)
