@@ -24,7 +24,7 @@ def get_features(image: torch.Tensor, model, layers=None, stop_after_last_tap: b
     last = max((int(k) for k in layers if str(k).isdigit()), default=None)
     feats, x, done = {}, image, False
     for name, module in model._modules.items():
-        if done and not (isinstance(module, torch.nn.ReLU) and module.inplace):
+        if done and not ((isinstance(module, torch.nn.ReLU) and module.inplace) or isinstance(module, torch.nn.Identity)):
             break
         x = module(x)
         if done:
@@ -40,6 +40,16 @@ def style_targets(style_imgs: torch.Tensor, model, precision=None):
     with torch.no_grad():
         feats = get_features(style_imgs, model)
         return {k: Fn.gram_matrix(v, precision) for k, v in feats.items() if k != CONTENT_LAYER}
+
+
+def blended_style_targets(style_imgs, weights, model, precision=None):
+    """Multi-style targets (BASELINE configs[3]): Gs = sum_j w_j * Gram(style_j) per layer, as (1,C,C) tensors.
+    `style_imgs` is (J,3,H,W); the reference itself uses a single style image (second_approach.py:157)."""
+    w = torch.as_tensor(weights, dtype=torch.float32, device=style_imgs.device).reshape(-1, 1, 1)
+    if w.shape[0] != style_imgs.shape[0]:
+        raise ValueError("one weight per style image")
+    grams = style_targets(style_imgs, model, precision)              # layer -> (J,C,C)
+    return {k: (g * w).sum(dim=0, keepdim=True) for k, g in grams.items()}
 
 
 def perceptual_loss_from_features(cur_feats, content_feat, style_grams, style_weight=1e6, content_weight=1.0,

@@ -39,7 +39,8 @@ class TextureStyleOptimizer:
 
     def __init__(self, verts, faces, verts_uvs, faces_uvs, texture, vgg, image_size, lr: float = 0.01,
                  style_weight: float = 1e6, content_weight: float = 1.0, precision=None,
-                 cache_constants: bool = False, world_size: int = 1, group=None, channels_last: bool = True):
+                 cache_constants: bool = False, world_size: int = 1, group=None, channels_last: bool = True,
+                 fuse_conv_relu: bool = True):
         dev = verts.device
         if dev.type != "cuda":
             raise RuntimeError("TextureStyleOptimizer needs CUDA tensors: libst3d has no CPU path")
@@ -51,7 +52,11 @@ class TextureStyleOptimizer:
         # cuDNN's tensor-core convolutions are NHWC kernels: with NCHW tensors torch wraps every conv in
         # nchw<->nhwc transposes (~20 % of a step).  channels_last keeps activations NHWC end to end.
         self.channels_last = channels_last
-        self.vgg = vgg.to(memory_format=torch.channels_last) if channels_last else vgg
+        if fuse_conv_relu:          # cuDNN's fused conv + bias + ReLU entry point (same numbers, fewer kernels)
+            from .vgg import fuse_vgg_features
+            self.vgg = fuse_vgg_features(vgg, channels_last)
+        else:
+            self.vgg = vgg.to(memory_format=torch.channels_last) if channels_last else vgg
         self.image_size = image_size
         self.style_weight, self.content_weight = style_weight, content_weight
         self.precision = precision

@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
     ap.add_argument("--nchw", action="store_true", help="keep VGG activations NCHW (torch default) instead of channels_last")
+    ap.add_argument("--unfused-vgg", action="store_true", help="conv, bias add and ReLU as separate torch kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the e2e / cached-constants legs")
     ap.add_argument("--profile-run", action="store_true",
@@ -94,7 +95,7 @@ def workload_config(args, world):
         "style_weight": 1e6, "content_weight": 1, "lr": 0.01, "parallelism": f"view-sharded dp{world}",
         "vgg": "torchvision VGG-19 .features, seeded random init (ImageNet weights unavailable offline), fp32 cuDNN "
                "(torch default allow_tf32), activations " + ("NCHW" if args.nchw else "channels_last (NHWC)") +
-               ", inside the timed step",
+               (", conv+bias+ReLU as cuDNN's fused call" if not args.unfused_vgg else "") + ", inside the timed step",
         "l2": "per-step working set (VGG activations of 8 x 512^2 images, > 4 GB) exceeds the 126 MB L2; no explicit flush",
     }
 
@@ -225,6 +226,64 @@ def algorithmic_bytes(op, key, tex=512):
     return None
 
 
+def c1_first_approach(dev, steps=50, size=256, run_cpu=True):
+    """BASELINE configs[0]: cow texture fit, 1 view 256x256, 50 Adam steps of the masked-MSE loop of
+    first_approach.py:191-213 (render -> masked MSE -> backward -> Adam; no VGG on this path)."""
+    import torch
+    from st3d import functional as Fn
+    w = load_workload(size)
+    R, T = cameras(1)
+    target = torch.rand(1, 3, size, size, generator=torch.Generator().manual_seed(3))
+    verts, faces = w["verts"].to(dev), w["faces"].int().to(dev)
+    fuv = w["verts_uvs"][w["faces_uvs"]].to(dev)
+    tex = w["texture"].to(dev).clone().requires_grad_(True)
+    opt = torch.optim.Adam([tex], lr=0.01)
+    Rd, Td, tgt = R.to(dev), T.to(dev), target.to(dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        img, mask, _ = Fn.render_views(verts, faces, Rd, Td, size, texture=tex, face_uvs=fuv)
+        loss = Fn.masked_mse_loss(img, tgt, mask)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    gpu_ms = e0.elapsed_time(e1) / steps
+    res = {"workload": "cow texture fit, 1 view x 256^2, masked-MSE loop (first_approach.py:191-213), 50 Adam steps",
+           "gpu_ms_per_step": gpu_ms, "gpu_it_per_s": 1e3 / gpu_ms, "final_loss": float(loss)}
+    if run_cpu:
+        from oracle import loss_oracle as lo
+        from oracle import render_oracle as ro
+        texc = w["texture"].clone().requires_grad_(True)
+        optc = torch.optim.Adam([texc], lr=0.01)
+        threads = os.cpu_count() or 1
+        ts = []
+        for i in range(4):
+            t0 = time.perf_counter()
+            optc.zero_grad()
+            img, mask = ro.images_and_masks(ro.render_views(w["verts"], w["faces"], R, T, size, texture=texc,
+                                                            verts_uvs=w["verts_uvs"], faces_uvs=w["faces_uvs"],
+                                                            nthreads=threads))
+            l = lo.first_approach_loss(img, mask, target, None, None, None, {}, "texture")
+            l.backward()
+            optc.step()
+            if i:
+                ts.append(time.perf_counter() - t0)
+        cpu_ms = 1e3 * sum(ts) / len(ts)
+        res.update({"cpu_ms_per_step": cpu_ms, "cpu_it_per_s": 1e3 / cpu_ms, "cpu_threads": threads,
+                    "speedup": cpu_ms / gpu_ms})
+    return res
+
+
 def run_st3d(args):
     import torch
     import torch.distributed as dist
@@ -252,7 +311,7 @@ def run_st3d(args):
         return TextureStyleOptimizer(w["verts"].to(dev), w["faces"].to(dev), w["verts_uvs"].to(dev),
                                      w["faces_uvs"].to(dev), w["texture"].to(dev), vgg, args.size, lr=0.01,
                                      precision=args.precision, cache_constants=cache, world_size=world,
-                                     channels_last=not args.nchw)
+                                     channels_last=not args.nchw, fuse_conv_relu=not args.unfused_vgg)
 
     def barrier():
         if world > 1:
@@ -389,6 +448,8 @@ def run_st3d(args):
                                    "note": "content render + content/style VGG features computed once (they are "
                                            "constants of the loop); not the headline"}
 
+    if rank == 0 and world == 1 and not args.no_extras:
+        out["c1_first_approach"] = c1_first_approach(dev, run_cpu=not args.no_cpu_baseline)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n = 2
         sec, threads = cpu_one_view_iterations(args, n, 1)

@@ -209,3 +209,57 @@ def test_channels_last_autograd_and_mse():
     want.backward()
     assert abs(loss.item() - want.item()) <= 4e-3 * abs(want.item())
     assert _relerr(fcl.grad, f64.grad) <= 4e-3
+
+
+def test_blended_multi_style_targets():
+    """configs[3]: Gs = sum_j w_j Gram(style_j); the fused loss against the blended target equals the oracle's."""
+    import torchvision
+    from st3d import losses
+    torch.manual_seed(0)
+    vgg = torchvision.models.vgg19(weights=None).features.eval()
+    for p in vgg.parameters():
+        p.requires_grad_(False)
+    g = torch.Generator().manual_seed(9)
+    styles = torch.rand(4, 3, 64, 64, generator=g)
+    cur = torch.rand(2, 3, 64, 64, generator=g)
+    wts = [0.25, 0.25, 0.25, 0.25]
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        targets = losses.blended_style_targets(styles.cuda(), wts, vgg.cuda())
+        feats = losses.get_features(cur.cuda(), vgg)
+        got = sum(losses.Fn.style_layer_loss(feats[k], t) for k, t in targets.items())
+        vgg_cpu = vgg.cpu()
+        sf = lo.get_features(styles, vgg_cpu)
+        cf = lo.get_features(cur, vgg_cpu)
+        want = 0.0
+        for k in lo.STYLE_LAYERS:
+            tgt = (lo.gram_matrix(sf[k]) * torch.tensor(wts).reshape(-1, 1, 1)).sum(0, keepdim=True)
+            want = want + lo.style_layer_loss(cf[k], tgt)
+        assert abs(got.item() - want.item()) <= 3e-3 * abs(want.item()), (got.item(), want.item())
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+
+
+def test_fused_vgg_forward_backward_equal_unfused():
+    """cuDNN's fused conv+bias+ReLU entry point: same taps, same input gradient as the stock module walk."""
+    import torchvision
+    from st3d import losses
+    from st3d.vgg import fuse_vgg_features
+    torch.manual_seed(0)
+    vgg = torchvision.models.vgg19(weights=None).features.eval().cuda()
+    for p in vgg.parameters():
+        p.requires_grad_(False)
+    fused = fuse_vgg_features(vgg, channels_last=True)
+    plain = vgg.to(memory_format=torch.channels_last)
+    x = torch.rand(2, 3, 64, 64, device="cuda").contiguous(memory_format=torch.channels_last)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    fa, fb = losses.get_features(xa, fused), lo.get_features(xb, plain)
+    assert list(fa) == list(fb)
+    la = sum((f ** 2).mean() for f in fa.values())
+    lb = sum((f ** 2).mean() for f in fb.values())
+    la.backward()
+    lb.backward()
+    for k in fb:
+        assert torch.allclose(fa[k], fb[k], rtol=1e-4, atol=1e-6), k
+    assert _relerr(xa.grad, xb.grad) <= 1e-3

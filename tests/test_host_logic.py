@@ -87,3 +87,22 @@ def test_allreduce_is_noop_single_process():
     p.grad = torch.full((3,), 2.0)
     allreduce_gradients([p])
     assert torch.equal(p.grad, torch.full((3,), 2.0))
+
+
+def test_fused_vgg_keeps_names_and_values_on_cpu():
+    """fuse_vgg_features keeps the module names get_features taps; on CPU the fused module falls back to
+    conv + relu_ (the cuDNN entry point is CUDA-only), so values must be identical to the plain walk."""
+    import torchvision
+    from st3d import losses
+    from st3d.vgg import FusedConvReLU, fuse_vgg_features
+    torch.manual_seed(0)
+    vgg = torchvision.models.vgg19(weights=None).features.eval()
+    fused = fuse_vgg_features(vgg, channels_last=False)
+    assert list(fused._modules) == list(vgg._modules)
+    assert isinstance(fused._modules["0"], FusedConvReLU) and isinstance(fused._modules["1"], torch.nn.Identity)
+    assert fused._modules["0"].conv.weight is vgg._modules["0"].weight
+    x = torch.rand(1, 3, 32, 32)
+    with torch.no_grad():
+        a, b = losses.get_features(x, fused), lo.get_features(x.clone(), vgg)
+    for k in b:
+        assert torch.equal(a[k], b[k])
