@@ -8,6 +8,7 @@ Mirrors, batched over views, what the reference reaches through `render_meshes` 
 """
 from __future__ import annotations
 
+import functools
 import math
 from typing import Optional, Sequence
 
@@ -17,6 +18,7 @@ import torch
 from . import ops
 
 
+@functools.lru_cache(maxsize=64)
 def fov_scales(fov_deg: float = 60.0, aspect: float = 1.0, znear: float = 1.0):
     """K00, K11 of FoVPerspectiveCameras' projection, rounded to fp32 step by step so the
     projected vertices are bit-identical to the oracle's."""

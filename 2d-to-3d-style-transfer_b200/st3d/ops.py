@@ -95,12 +95,17 @@ _pending: list = []
 _capacity_hint: dict = {}
 
 
+_free_hosts: list = []      # recycled pinned header buffers (cudaHostAlloc costs milliseconds; never allocate per call)
+
+
 def _watch_header(ws: torch.Tensor, key) -> None:
-    host = torch.empty(WS_HEADER_INTS, dtype=torch.int32, pin_memory=True)
+    host = _free_hosts.pop() if _free_hosts else torch.empty(WS_HEADER_INTS, dtype=torch.int32, pin_memory=True)
     host.copy_(ws[: WS_HEADER_INTS * 4].view(torch.int32), non_blocking=True)
     ev = torch.cuda.Event()
     ev.record()
     _pending.append((ev, host, key))
+    if len(_pending) > 64:      # bound the backlog when the caller never polls
+        poll_overflow()
 
 
 def poll_overflow(block: bool = False) -> None:
@@ -110,9 +115,10 @@ def poll_overflow(block: bool = False) -> None:
         if block:
             ev.synchronize()
         if ev.query():
-            needed, overflow = int(host[0]), int(host[1])
+            needed, overflow, clip = int(host[0]), int(host[1]), int(host[4])
+            _free_hosts.append(host)
             _capacity_hint[key] = max(_capacity_hint.get(key, 0), needed)
-            if int(host[4]):
+            if clip:
                 _pending.clear()
                 raise NotImplementedError("a face has a vertex in front of the near clipping plane (z < z_clip): "
                                           "near-plane face clipping (PyTorch3D clip_faces) is not implemented; the "
