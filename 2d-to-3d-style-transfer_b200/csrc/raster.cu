@@ -337,60 +337,6 @@ k_fine(const FaceRec* __restrict__ rec, const int* __restrict__ tile_count, cons
 // z-buffer.  That key order IS the oracle's lexicographic (z, face) order, so the winner does not depend
 // on timing.  Phase B (k_resolve): one thread per pixel, row-major (128-byte coalesced stores), evaluates
 // its winner once (barycentrics, edge distance) and runs the fused texture / shade / blend epilogue.
-__global__ void __launch_bounds__(256)
-k_zbuf_pairs(const FaceRec* __restrict__ rec, const int* __restrict__ list, const int* __restrict__ list_tile,
-             const int* __restrict__ hdr, int64_t capacity, int H, int W, int TX, int TY, int persp,
-             const float* __restrict__ ndc_x, const float* __restrict__ ndc_y, unsigned long long* __restrict__ zkey) {
-    const int lane = threadIdx.x & 31;
-    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    const int64_t total = min((int64_t)hdr[0], capacity);
-    for (int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < total; p += nwarps) {
-        const int f = __ldg(list + p), t = __ldg(list_tile + p);
-        const int n = t / (TX * TY), tile_y0 = ((t / TX) % TY) * kTile, tile_x0 = (t % TX) * kTile;
-        const float4 ra = __ldg(&rec[f].a), rb = __ldg(&rec[f].b), rc = __ldg(&rec[f].c);
-        const FaceVerts v{ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w, rc.x};
-        const int xr = __float_as_int(rc.z), yr = __float_as_int(rc.w);
-        const int x0 = max(xr & 0xffff, tile_x0), x1 = min(xr >> 16, tile_x0 + kTile - 1);
-        const int y0 = max(yr & 0xffff, tile_y0), y1 = min(yr >> 16, tile_y0 + kTile - 1);
-        const bool zpos = v.z0 > 0.0f && v.z1 > 0.0f && v.z2 > 0.0f;
-        const float denom = fadd(rc.y, kEps);
-        // edge i of the barycentric numerators: w0 <- (v1,v2), w1 <- (v2,v0), w2 <- (v0,v1)
-        const float e0y = fsub(v.y2, v.y1), e0x = fsub(v.x2, v.x1);
-        const float e1y = fsub(v.y0, v.y2), e1x = fsub(v.x0, v.x2);
-        const float e2y = fsub(v.y1, v.y0), e2x = fsub(v.x1, v.x0);
-        unsigned long long* zview = zkey + (int64_t)n * H * W;
-        for (int by = y0; by <= y1; by += 4) {
-            for (int bx = x0; bx <= x1; bx += 8) {
-                const int qx = bx + (lane & 7), qy = by + (lane >> 3);
-                if (qx > x1 || qy > y1) continue;
-                const float px = __ldg(ndc_x + qx), py = __ldg(ndc_y + qy);
-                const float w0 = fsub(fmul(fsub(px, v.x1), e0y), fmul(fsub(py, v.y1), e0x));
-                const float w1 = fsub(fmul(fsub(px, v.x2), e1y), fmul(fsub(py, v.y2), e1x));
-                const float w2 = fsub(fmul(fsub(px, v.x0), e2y), fmul(fsub(py, v.y0), e2x));
-                // necessary for "inside" when every z > 0: the three edge values share one strict sign
-                if (zpos && !((w0 > 0.0f && w1 > 0.0f && w2 > 0.0f) || (w0 < 0.0f && w1 < 0.0f && w2 < 0.0f)))
-                    continue;
-                float b0 = fdiv(w0, denom), b1 = fdiv(w1, denom), b2 = fdiv(w2, denom);
-                if (persp) {
-                    const float t0 = fmul(fmul(b0, v.z1), v.z2);
-                    const float t1 = fmul(fmul(v.z0, b1), v.z2);
-                    const float t2 = fmul(fmul(v.z0, v.z1), b2);
-                    const float d = fmaxf(fadd(fadd(t0, t1), t2), kEps);
-                    b0 = fdiv(t0, d);
-                    b1 = fdiv(t1, d);
-                    b2 = fdiv(t2, d);
-                }
-                if (!(b0 > 0.0f && b1 > 0.0f && b2 > 0.0f)) continue;
-                const float pz = fadd(fadd(fmul(b0, v.z0), fmul(b1, v.z1)), fmul(b2, v.z2));
-                if (!(pz >= 0.0f)) continue;
-                const unsigned long long k =
-                    ((unsigned long long)__float_as_uint(fadd(pz, 0.0f)) << 32) | (unsigned long long)(unsigned)f;
-                atomicMin(zview + (int64_t)qy * W + qx, k);
-            }
-        }
-    }
-}
-
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_resolve(const FaceRec* __restrict__ rec, const unsigned long long* __restrict__ zkey, int H, int W, int persp,
@@ -435,21 +381,228 @@ k_resolve(const FaceRec* __restrict__ rec, const unsigned long long* __restrict_
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// 5c. hard rasterization without bins: k_prepare -> k_face_zbuf -> k_big_faces -> k_resolve
+// -------------------------------------------------------------------------------------------------
+// k_prepare: z-buffer keys := all ones, header := 0, pixel-centre NDC tables (one launch instead of
+// two memsets and a table pass).
+__global__ void __launch_bounds__(256)
+k_prepare(unsigned long long* __restrict__ zkey, int64_t nkeys, int* __restrict__ hdr, int H, int W,
+          float* __restrict__ ndc_x, float* __restrict__ ndc_y) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    ulonglong2* z2 = reinterpret_cast<ulonglong2*>(zkey);
+    for (int64_t i = tid; i < nkeys / 2; i += nth) z2[i] = make_ulonglong2(~0ull, ~0ull);
+    if (tid == 0 && (nkeys & 1)) zkey[nkeys - 1] = ~0ull;
+    if (tid < ST3D_WS_HEADER_INTS) hdr[tid] = 0;
+    for (int64_t i = tid; i < W; i += nth) ndc_x[i] = pix_to_ndc(W - 1 - (int)i, W, H);
+    for (int64_t i = tid; i < H; i += nth) ndc_y[i] = pix_to_ndc(H - 1 - (int)i, H, W);
+}
+
+// Exact depth test of one pixel against one face + z-buffer update (the oracle's arithmetic)
+__device__ __forceinline__ void zbuf_test_pixel(float px, float py, const FaceVerts& v, float denom, bool zpos, bool persp,
+                                                float e0x, float e0y, float e1x, float e1y, float e2x, float e2y,
+                                                unsigned fid, unsigned long long* slot) {
+    const float w0 = fsub(fmul(fsub(px, v.x1), e0y), fmul(fsub(py, v.y1), e0x));
+    const float w1 = fsub(fmul(fsub(px, v.x2), e1y), fmul(fsub(py, v.y2), e1x));
+    const float w2 = fsub(fmul(fsub(px, v.x0), e2y), fmul(fsub(py, v.y0), e2x));
+    // necessary for "inside" when every z > 0: the three edge values share one strict sign
+    if (zpos && !((w0 > 0.0f && w1 > 0.0f && w2 > 0.0f) || (w0 < 0.0f && w1 < 0.0f && w2 < 0.0f))) return;
+    float b0 = fdiv(w0, denom), b1 = fdiv(w1, denom), b2 = fdiv(w2, denom);
+    if (persp) {
+        const float t0 = fmul(fmul(b0, v.z1), v.z2);
+        const float t1 = fmul(fmul(v.z0, b1), v.z2);
+        const float t2 = fmul(fmul(v.z0, v.z1), b2);
+        const float d = fmaxf(fadd(fadd(t0, t1), t2), kEps);
+        b0 = fdiv(t0, d);
+        b1 = fdiv(t1, d);
+        b2 = fdiv(t2, d);
+    }
+    if (!(b0 > 0.0f && b1 > 0.0f && b2 > 0.0f)) return;
+    const float pz = fadd(fadd(fmul(b0, v.z0), fmul(b1, v.z1)), fmul(b2, v.z2));
+    if (!(pz >= 0.0f)) return;
+    atomicMin(slot, ((unsigned long long)__float_as_uint(fadd(pz, 0.0f)) << 32) | (unsigned long long)fid);
+}
+
+constexpr int kUnitSide = 64;  // work units of the sweep pass cover at most 64 x 64 pixels
+
+// One thread per (view, face): builds the face record (optionally projecting the three vertices itself),
+// then rasterizes it straight into the global z-buffer -- no bins on this path:
+//   box of <= 16 pixels  : the thread tests its pixels itself (dense meshes: faces smaller than a pixel)
+//   larger               : queued as work units of <= 64 x 64 pixels for k_sweep_units (one warp per unit)
+// SRC = 0: face_verts (F_total,3,3) already in NDC (operator boundary); SRC = 1: world verts + faces + cameras.
+template <int SRC>
+__global__ void __launch_bounds__(256)
+k_face_zbuf(const float* __restrict__ face_verts, const int64_t* __restrict__ first_idx,
+            const int64_t* __restrict__ num_faces, const float* __restrict__ verts, const int32_t* __restrict__ faces,
+            const float* __restrict__ Rm, const float* __restrict__ Tv, float k00, float k11, int64_t F_per_mesh,
+            int H, int W, int cull_backfaces, float z_clip, int persp, const float* __restrict__ ndc_x,
+            const float* __restrict__ ndc_y, FaceRec* __restrict__ rec, unsigned long long* __restrict__ zkey,
+            int* __restrict__ unit_face, int* __restrict__ unit_block, int64_t unit_capacity, int* __restrict__ hdr) {
+    const int n = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t first = SRC == 0 ? first_idx[n] : (int64_t)n * F_per_mesh;
+    const int64_t cnt = SRC == 0 ? num_faces[n] : F_per_mesh;
+    const bool live = i < cnt;
+    const int64_t f = first + (live ? i : 0);
+    __shared__ float sR[9], sT[3];
+    if (SRC == 1) {
+        if (threadIdx.x < 9) sR[threadIdx.x] = Rm[n * 9 + threadIdx.x];
+        if (threadIdx.x < 3) sT[threadIdx.x] = Tv[n * 3 + threadIdx.x];
+        __syncthreads();
+    }
+    FaceVerts v{};
+    float area = 0.0f;
+    int x0 = 1, x1 = 0, y0 = 1, y1 = 0;
+    bool valid = false;
+    if (live) {
+        if (SRC == 1) {
+            float c[9];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {  // same operation order as k_transform / oracle_transform_verts
+                const float* p = verts + 3 * (int64_t)__ldg(faces + 3 * i + k);
+                const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+                const float xv = fadd(fadd(fadd(fmul(x, sR[0]), fmul(y, sR[3])), fmul(z, sR[6])), sT[0]);
+                const float yv = fadd(fadd(fadd(fmul(x, sR[1]), fmul(y, sR[4])), fmul(z, sR[7])), sT[1]);
+                const float zv = fadd(fadd(fadd(fmul(x, sR[2]), fmul(y, sR[5])), fmul(z, sR[8])), sT[2]);
+                c[3 * k] = fdiv(fmul(xv, k00), zv);
+                c[3 * k + 1] = fdiv(fmul(yv, k11), zv);
+                c[3 * k + 2] = zv;
+            }
+            v = FaceVerts{c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8]};
+        } else {
+            const float* p = face_verts + 9 * f;
+            v = FaceVerts{p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8]};
+        }
+        if (fminf(v.z0, fminf(v.z1, v.z2)) < z_clip) hdr[4] = 1;  // would need near-plane clipping (A.2 clip_faces)
+        area = edge_fn(v.x2, v.y2, v.x0, v.y0, v.x1, v.y1);
+        valid = fabsf(area) > kEps;
+        if (cull_backfaces && area < 0.0f) valid = false;
+        if (fmaxf(v.z0, fmaxf(v.z1, v.z2)) < 0.0f) valid = false;
+        const float xmin = fminf(v.x0, fminf(v.x1, v.x2)), xmax = fmaxf(v.x0, fmaxf(v.x1, v.x2));
+        const float ymin = fminf(v.y0, fminf(v.y1, v.y2)), ymax = fmaxf(v.y0, fmaxf(v.y1, v.y2));
+        if (!(isfinite(xmin) && isfinite(xmax) && isfinite(ymin) && isfinite(ymax))) valid = false;
+        if (valid) {
+            int jlo, jhi, klo, khi;
+            ndc_pixel_range(xmin, xmax, W, H, jlo, jhi);
+            ndc_pixel_range(ymin, ymax, H, W, klo, khi);
+            if (jlo <= jhi && klo <= khi) {
+                x0 = W - 1 - jhi;  // image x runs opposite to NDC x (A.3)
+                x1 = W - 1 - jlo;
+                y0 = H - 1 - khi;
+                y1 = H - 1 - klo;
+            } else {
+                valid = false;
+            }
+        }
+        FaceRec r;
+        r.a = make_float4(v.x0, v.y0, v.z0, v.x1);
+        r.b = make_float4(v.y1, v.z1, v.x2, v.y2);
+        r.c = make_float4(v.z2, area, __int_as_float(x0 | (x1 << 16)), __int_as_float(y0 | (y1 << 16)));
+        rec[f] = r;
+    }
+    const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
+    const bool small = valid && bw * bh <= 16;
+    unsigned long long* zview = zkey + (int64_t)n * H * W;
+    if (valid && !small) {
+        // queue the face as ceil(bw/64) x ceil(bh/64) work units of at most 64 x 64 pixels for k_sweep_units
+        const int ux = (bw + kUnitSide - 1) / kUnitSide, uy = (bh + kUnitSide - 1) / kUnitSide;
+        const int slot0 = atomicAdd(&hdr[5], ux * uy);
+        for (int u = 0; u < ux * uy; ++u) {
+            if (slot0 + u < unit_capacity) {
+                unit_face[slot0 + u] = (int)f;
+                unit_block[slot0 + u] = (n << 20) | ((u / ux) << 10) | (u % ux);
+            } else {
+                hdr[1] = 1;
+            }
+        }
+    }
+    if (small) {
+        const bool zpos = v.z0 > 0.0f && v.z1 > 0.0f && v.z2 > 0.0f;
+        const float denom = fadd(area, kEps);
+        const float e0y = fsub(v.y2, v.y1), e0x = fsub(v.x2, v.x1), e1y = fsub(v.y0, v.y2), e1x = fsub(v.x0, v.x2);
+        const float e2y = fsub(v.y1, v.y0), e2x = fsub(v.x1, v.x0);
+        for (int qy = y0; qy <= y1; ++qy)
+            for (int qx = x0; qx <= x1; ++qx)
+                zbuf_test_pixel(__ldg(ndc_x + qx), __ldg(ndc_y + qy), v, denom, zpos, persp != 0, e0x, e0y, e1x, e1y, e2x,
+                                e2y, (unsigned)f, zview + (int64_t)qy * W + qx);
+    }
+}
+
+// One WARP per queued unit (a face, or a 64 x 64-pixel block of a large face): sweeps the unit's pixel box in
+// 8x4 steps.  Units are balanced by construction, so neither one huge triangle nor one crowded image region
+// can stall the pass.
+__global__ void __launch_bounds__(256)
+k_sweep_units(const FaceRec* __restrict__ rec, const int* __restrict__ unit_face, const int* __restrict__ unit_block,
+              const int* __restrict__ hdr, int64_t unit_capacity, int H, int W, int persp,
+              const float* __restrict__ ndc_x, const float* __restrict__ ndc_y, unsigned long long* __restrict__ zkey) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t total = min((int64_t)hdr[5], unit_capacity);
+    for (int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < total; p += nwarps) {
+        const int f = __ldg(unit_face + p), blk = __ldg(unit_block + p);
+        const int n = blk >> 20, uy = (blk >> 10) & 1023, ux = blk & 1023;
+        const float4 ra = __ldg(&rec[f].a), rb = __ldg(&rec[f].b), rc = __ldg(&rec[f].c);
+        const FaceVerts v{ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w, rc.x};
+        const int xr = __float_as_int(rc.z), yr = __float_as_int(rc.w);
+        const int x0 = (xr & 0xffff) + ux * kUnitSide, x1 = min(xr >> 16, x0 + kUnitSide - 1);
+        const int y0 = (yr & 0xffff) + uy * kUnitSide, y1 = min(yr >> 16, y0 + kUnitSide - 1);
+        const bool zpos = v.z0 > 0.0f && v.z1 > 0.0f && v.z2 > 0.0f;
+        const float denom = fadd(rc.y, kEps);
+        const float e0y = fsub(v.y2, v.y1), e0x = fsub(v.x2, v.x1), e1y = fsub(v.y0, v.y2), e1x = fsub(v.x0, v.x2);
+        const float e2y = fsub(v.y1, v.y0), e2x = fsub(v.x1, v.x0);
+        unsigned long long* zview = zkey + (int64_t)n * H * W;
+        for (int by = y0; by <= y1; by += 4) {
+            for (int bx = x0; bx <= x1; bx += 8) {
+                const int qx = bx + (lane & 7), qy = by + (lane >> 3);
+                if (qx > x1 || qy > y1) continue;
+                zbuf_test_pixel(__ldg(ndc_x + qx), __ldg(ndc_y + qy), v, denom, zpos, persp != 0, e0x, e0y, e1x, e1y, e2x,
+                                e2y, (unsigned)f, zview + (int64_t)qy * W + qx);
+            }
+        }
+    }
+}
+
+struct HardSrc {  // where the faces of the hard path come from
+    const float* face_verts = nullptr;      // SRC 0
+    const int64_t* first_idx = nullptr;
+    const int64_t* num_faces = nullptr;
+    const float* verts = nullptr;           // SRC 1
+    const int32_t* faces = nullptr;
+    const float* R = nullptr;
+    const float* T = nullptr;
+    float k00 = 0, k11 = 0;
+    int64_t F_per_mesh = 0;                 // faces per view (SRC 1) or the largest mesh (SRC 0)
+    int cull_backfaces = 0;
+    float z_clip = -INFINITY;
+};
+
 template <int MODE>
-static int run_hard(const RasterWs& ws, int N, int H, int W, int persp, const FragOut& fo, const ShadeParams& sp,
-                    cudaStream_t s) {
-    ST3D_CUDA_OK(cudaMemsetAsync(ws.zkey, 0xFF, (size_t)N * H * W * sizeof(unsigned long long), s));
-    k_zbuf_pairs<<<148 * 8, 256, 0, s>>>(ws.rec, ws.list, ws.list_tile, ws.hdr, ws.capacity, H, W, ws.TX, ws.TY, persp,
-                                         ws.ndc_x, ws.ndc_y, ws.zkey);
-    ST3D_LAUNCH_OK("k_zbuf_pairs");
+static int run_hard(const RasterWs& ws, const HardSrc& h, int N, int H, int W, int persp, const FragOut& fo,
+                    const ShadeParams& sp, cudaStream_t s) {
+    ST3D_REQUIRE(N < 2048, "hard rasterization packs the view index into 11 bits: at most 2047 views per call (got %d)", N);
+    k_prepare<<<148 * 4, 256, 0, s>>>(ws.zkey, (int64_t)N * H * W, ws.hdr, H, W, ws.ndc_x, ws.ndc_y);
+    ST3D_LAUNCH_OK("k_prepare");
+    if (h.F_per_mesh > 0) {
+        const dim3 grid(cdiv(h.F_per_mesh, 256), N);
+        if (h.verts)
+            k_face_zbuf<1><<<grid, 256, 0, s>>>(nullptr, nullptr, nullptr, h.verts, h.faces, h.R, h.T, h.k00, h.k11,
+                                                h.F_per_mesh, H, W, h.cull_backfaces, h.z_clip, persp, ws.ndc_x, ws.ndc_y,
+                                                ws.rec, ws.zkey, ws.list, ws.list_tile, ws.capacity, ws.hdr);
+        else
+            k_face_zbuf<0><<<grid, 256, 0, s>>>(h.face_verts, h.first_idx, h.num_faces, nullptr, nullptr, nullptr, nullptr,
+                                                0.0f, 0.0f, h.F_per_mesh, H, W, h.cull_backfaces, h.z_clip, persp,
+                                                ws.ndc_x, ws.ndc_y, ws.rec, ws.zkey, ws.list, ws.list_tile, ws.capacity,
+                                                ws.hdr);
+        ST3D_LAUNCH_OK("k_face_zbuf");
+        k_sweep_units<<<148 * 8, 256, 0, s>>>(ws.rec, ws.list, ws.list_tile, ws.hdr, ws.capacity, H, W, persp, ws.ndc_x,
+                                              ws.ndc_y, ws.zkey);
+        ST3D_LAUNCH_OK("k_sweep_units");
+    }
     k_resolve<MODE><<<dim3(cdiv(W, 256), H, N), 256, 0, s>>>(ws.rec, ws.zkey, H, W, persp, ws.ndc_x, ws.ndc_y, fo, sp);
     ST3D_LAUNCH_OK("k_resolve");
     return ST3D_OK;
 }
 
-// -------------------------------------------------------------------------------------------------
-// host side
-// -------------------------------------------------------------------------------------------------
 static int run_bins(const RasterWs& ws, const float* face_verts, const int32_t* faces, const int64_t* first_idx,
                     const int64_t* num_faces, int N, int64_t F_per_mesh, int64_t V, int H, int W, float blur_radius,
                     int cull_backfaces, bool gather, float z_clip, cudaStream_t s) {
@@ -524,17 +677,24 @@ extern "C" int st3d_rasterize_meshes_forward(const float* face_verts, const int6
     }
     const RasterWs ws = raster_ws_layout(workspace, N, F_total, H, W, cap, 0);
     cudaStream_t s = (cudaStream_t)stream;
-    int rc = run_bins(ws, face_verts, nullptr, mesh_to_face_first_idx, num_faces_per_mesh, N, max_faces_in_mesh, 0, H, W,
-                      blur_radius, cull_backfaces, false, -INFINITY, s);
-    if (rc != ST3D_OK) return rc;
     FragOut fo{pix_to_face, zbuf, bary, dists};
     ShadeParams sp{};
     const int K = faces_per_pixel;
+    if (K == 1 && blur_radius == 0.0f && !clip_barycentric_coords) {
+        HardSrc h;
+        h.face_verts = face_verts;
+        h.first_idx = mesh_to_face_first_idx;
+        h.num_faces = num_faces_per_mesh;
+        h.F_per_mesh = max_faces_in_mesh;
+        h.cull_backfaces = cull_backfaces;
+        return run_hard<0>(ws, h, N, H, W, perspective_correct, fo, sp, s);
+    }
+    int rc = run_bins(ws, face_verts, nullptr, mesh_to_face_first_idx, num_faces_per_mesh, N, max_faces_in_mesh, 0, H, W,
+                      blur_radius, cull_backfaces, false, -INFINITY, s);
+    if (rc != ST3D_OK) return rc;
 #define ST3D_FINE(KK)                                                                                            \
     k_fine<0, KK><<<ws.NT, 256, 0, s>>>(ws.rec, ws.tile_count, ws.tile_offset, ws.list, ws.capacity, H, W, ws.TX,  \
                                         ws.TY, blur_radius, perspective_correct, clip_barycentric_coords, fo, sp)
-    if (K == 1 && blur_radius == 0.0f && !clip_barycentric_coords)
-        return run_hard<0>(ws, N, H, W, perspective_correct, fo, sp, s);
     if (K == 1) ST3D_FINE(1);
     else if (K == 2) ST3D_FINE(2);
     else if (K <= 4) {
@@ -575,15 +735,28 @@ extern "C" int st3d_render_forward(const st3d_render_args* a, st3d_stream_t stre
     cudaStream_t s = (cudaStream_t)stream;
     const RasterWs ws = raster_ws_layout(a->workspace, a->N, (int64_t)a->N * a->F, a->H, a->W, a->list_capacity,
                                          (int64_t)a->N * a->V);
+    const ShadeParams sp = make_shade_params(*a);
+    FragOut fo{};
+    const float z_clip = a->z_clip > 0.0f ? a->z_clip : -INFINITY;
+    if (a->blur_radius == 0.0f) {  // the reference's configuration: no bins, faces go straight to the z-buffer
+        HardSrc h;
+        h.verts = a->verts;
+        h.faces = a->faces;
+        h.R = a->R;
+        h.T = a->T;
+        h.k00 = a->k00;
+        h.k11 = a->k11;
+        h.F_per_mesh = a->F;
+        h.cull_backfaces = a->cull_backfaces;
+        h.z_clip = z_clip;
+        return run_hard<1>(ws, h, a->N, a->H, a->W, 1, fo, sp, s);
+    }
     k_transform<<<dim3(cdiv(a->V, 256), a->N), 256, 0, s>>>(a->verts, a->R, a->T, a->k00, a->k11, a->V, ws.verts_ndc,
                                                             nullptr);
     ST3D_LAUNCH_OK("k_transform");
     int rc = run_bins(ws, nullptr, a->faces, nullptr, nullptr, a->N, a->F, a->V, a->H, a->W, a->blur_radius,
-                      a->cull_backfaces, true, a->z_clip > 0.0f ? a->z_clip : -INFINITY, s);
+                      a->cull_backfaces, true, z_clip, s);
     if (rc != ST3D_OK) return rc;
-    const ShadeParams sp = make_shade_params(*a);
-    FragOut fo{};
-    if (a->blur_radius == 0.0f) return run_hard<1>(ws, a->N, a->H, a->W, 1, fo, sp, s);
     k_fine<1, 1><<<ws.NT, 256, 0, s>>>(ws.rec, ws.tile_count, ws.tile_offset, ws.list, ws.capacity, a->H, a->W,
                                            ws.TX, ws.TY, a->blur_radius, 1, 1, fo, sp);
     ST3D_LAUNCH_OK("k_fine");
