@@ -175,6 +175,25 @@ __device__ __forceinline__ bool eval_face(float px, float py, const FaceVerts& v
     return true;
 }
 
+// barycentrics + depth only (the same arithmetic as eval_face, without the edge distance)
+__device__ __forceinline__ void face_bary(float px, float py, const FaceVerts& v, float area, bool persp, float& b0,
+                                          float& b1, float& b2, float& pz) {
+    const float denom = fadd(area, kEps);
+    b0 = fdiv(edge_fn(px, py, v.x1, v.y1, v.x2, v.y2), denom);
+    b1 = fdiv(edge_fn(px, py, v.x2, v.y2, v.x0, v.y0), denom);
+    b2 = fdiv(edge_fn(px, py, v.x0, v.y0, v.x1, v.y1), denom);
+    if (persp) {
+        const float t0 = fmul(fmul(b0, v.z1), v.z2);
+        const float t1 = fmul(fmul(v.z0, b1), v.z2);
+        const float t2 = fmul(fmul(v.z0, v.z1), b2);
+        const float d = fmaxf(fadd(fadd(t0, t1), t2), kEps);
+        b0 = fdiv(t0, d);
+        b1 = fdiv(t1, d);
+        b2 = fdiv(t2, d);
+    }
+    pz = fadd(fadd(fmul(b0, v.z0), fmul(b1, v.z1)), fmul(b2, v.z2));
+}
+
 // ---- raster workspace ---------------------------------------------------------------------------
 struct RasterWs {
     int* hdr;          // ST3D_WS_HEADER_INTS ints: [0] pairs needed, [1] overflow, [2] capacity

@@ -348,9 +348,20 @@ k_resolve(const FaceRec* __restrict__ rec, const unsigned long long* __restrict_
     const bool hit = key != ~0ull;
     const int f = (int)(unsigned)(key & 0xffffffffull);
     Hit h{};
+    // Planar output carries no alpha channel, and for a covered pixel rgb = w c / (w + 1e-10) with w = prob in
+    // [0.5, 1]: the edge distance changes rgb by <= 2e-10 relative (below one fp32 ulp), so it is not computed.
+    const bool need_dist = MODE == 0 || sp.out_layout == ST3D_LAYOUT_NHWC_RGBA;
     if (hit) {
         const FaceRec r = rec[f];
-        eval_face(__ldg(ndc_x + xi), __ldg(ndc_y + yi), unpack(r), r.c.y, 0.0f, persp != 0, false, h);
+        const float px = __ldg(ndc_x + xi), py = __ldg(ndc_y + yi);
+        if (need_dist) {
+            eval_face(px, py, unpack(r), r.c.y, 0.0f, persp != 0, false, h);
+        } else {
+            float dist_unused;
+            face_bary(px, py, unpack(r), r.c.y, persp != 0, h.b0, h.b1, h.b2, h.z);
+            h.dist = -1.0f;  // any negative value: prob = sigmoid(1e4) = 1
+            (void)dist_unused;
+        }
     }
     if (MODE == 0) {
         fo.pix_to_face[pix] = hit ? f : -1;
@@ -431,7 +442,7 @@ constexpr int kUnitSide = 64;  // work units of the sweep pass cover at most 64 
 //   larger               : queued as work units of <= 64 x 64 pixels for k_sweep_units (one warp per unit)
 // SRC = 0: face_verts (F_total,3,3) already in NDC (operator boundary); SRC = 1: world verts + faces + cameras.
 template <int SRC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 k_face_zbuf(const float* __restrict__ face_verts, const int64_t* __restrict__ first_idx,
             const int64_t* __restrict__ num_faces, const float* __restrict__ verts, const int32_t* __restrict__ faces,
             const float* __restrict__ Rm, const float* __restrict__ Tv, float k00, float k11, int64_t F_per_mesh,
@@ -503,11 +514,24 @@ k_face_zbuf(const float* __restrict__ face_verts, const int64_t* __restrict__ fi
     const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
     const bool small = valid && bw * bh <= 16;
     unsigned long long* zview = zkey + (int64_t)n * H * W;
-    if (valid && !small) {
-        // queue the face as ceil(bw/64) x ceil(bh/64) work units of at most 64 x 64 pixels for k_sweep_units
-        const int ux = (bw + kUnitSide - 1) / kUnitSide, uy = (bh + kUnitSide - 1) / kUnitSide;
-        const int slot0 = atomicAdd(&hdr[5], ux * uy);
-        for (int u = 0; u < ux * uy; ++u) {
+    {
+        // queue the face as ceil(bw/64) x ceil(bh/64) work units of at most 64 x 64 pixels for k_sweep_units;
+        // one atomicAdd per WARP (prefix sum over the lanes' unit counts), not one per face
+        const int ux = (valid && !small) ? (bw + kUnitSide - 1) / kUnitSide : 0;
+        const int nu = (valid && !small) ? ux * ((bh + kUnitSide - 1) / kUnitSide) : 0;
+        const int lane = threadIdx.x & 31;
+        int incl = nu;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+        int base = 0;
+        if (lane == 31 && warp_total > 0) base = atomicAdd(&hdr[5], warp_total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        const int slot0 = base + incl - nu;
+        for (int u = 0; u < nu; ++u) {
             if (slot0 + u < unit_capacity) {
                 unit_face[slot0 + u] = (int)f;
                 unit_block[slot0 + u] = (n << 20) | ((u / ux) << 10) | (u % ux);
@@ -583,13 +607,13 @@ static int run_hard(const RasterWs& ws, const HardSrc& h, int N, int H, int W, i
     k_prepare<<<148 * 4, 256, 0, s>>>(ws.zkey, (int64_t)N * H * W, ws.hdr, H, W, ws.ndc_x, ws.ndc_y);
     ST3D_LAUNCH_OK("k_prepare");
     if (h.F_per_mesh > 0) {
-        const dim3 grid(cdiv(h.F_per_mesh, 256), N);
+        const dim3 grid(cdiv(h.F_per_mesh, 128), N);
         if (h.verts)
-            k_face_zbuf<1><<<grid, 256, 0, s>>>(nullptr, nullptr, nullptr, h.verts, h.faces, h.R, h.T, h.k00, h.k11,
+            k_face_zbuf<1><<<grid, 128, 0, s>>>(nullptr, nullptr, nullptr, h.verts, h.faces, h.R, h.T, h.k00, h.k11,
                                                 h.F_per_mesh, H, W, h.cull_backfaces, h.z_clip, persp, ws.ndc_x, ws.ndc_y,
                                                 ws.rec, ws.zkey, ws.list, ws.list_tile, ws.capacity, ws.hdr);
         else
-            k_face_zbuf<0><<<grid, 256, 0, s>>>(h.face_verts, h.first_idx, h.num_faces, nullptr, nullptr, nullptr, nullptr,
+            k_face_zbuf<0><<<grid, 128, 0, s>>>(h.face_verts, h.first_idx, h.num_faces, nullptr, nullptr, nullptr, nullptr,
                                                 0.0f, 0.0f, h.F_per_mesh, H, W, h.cull_backfaces, h.z_clip, persp,
                                                 ws.ndc_x, ws.ndc_y, ws.rec, ws.zkey, ws.list, ws.list_tile, ws.capacity,
                                                 ws.hdr);

@@ -39,7 +39,15 @@ k_render_bwd(const FaceRec* __restrict__ rec, const float* __restrict__ grad_ima
         const float px = pix_to_ndc(W - 1 - xi, W, H), py = pix_to_ndc(H - 1 - yi, H, W);
         const FaceVerts v = unpack(rec[f]);
         float b0, b1, b2, pz, dist;
-        face_recompute(px, py, v, true, clip != 0, b0, b1, b2, pz, dist);
+        // planar layout + hard rasterization: no alpha gradient comes in and d(rgb)/d(dist) is ~1e-10 relative,
+        // so the edge distance (three point-segment distances) is neither recomputed nor differentiated
+        const bool skip_dist = sp.out_layout == ST3D_LAYOUT_PLANAR && clip == 0;
+        if (skip_dist) {
+            face_bary(px, py, v, edge_fn(v.x2, v.y2, v.x0, v.y0, v.x1, v.y1), true, b0, b1, b2, pz);
+            dist = -1.0f;
+        } else {
+            face_recompute(px, py, v, true, clip != 0, b0, b1, b2, pz, dist);
+        }
 
         // upstream gradient
         float g_rgb[3], g_alpha = 0.0f;
@@ -100,7 +108,7 @@ k_render_bwd(const FaceRec* __restrict__ rec, const float* __restrict__ grad_ima
         // w = prob * e ; alpha = prob
         const float e = bl.prob > 0.0f ? bl.w / bl.prob : 0.0f;
         const float g_prob = g_w * e + g_alpha;
-        const float g_dist = g_prob * (-bl.prob * (1.0f - bl.prob) / sp.sigma);
+        const float g_dist = skip_dist ? 0.0f : g_prob * (-bl.prob * (1.0f - bl.prob) / sp.sigma);
         const float g_zinv = g_w * bl.dw_dzinv + g_delta * bl.ddelta_dzinv;
         const float g_pz = -g_zinv / (sp.zfar - sp.znear);
 

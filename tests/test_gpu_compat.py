@@ -72,7 +72,8 @@ def test_per_view_calls_equal_batched_render_and_oracle(scene):
     assert all(o.shape == (1, S, S, 4) for o in per_view)
     rgba = torch.cat(per_view, dim=0)
     images, masks = utils.render_meshes(sc["renderer"], sc["mesh"], [sc["cameras"][i] for i in range(3)])
-    assert torch.equal(images, rgba[..., :3].permute(0, 3, 1, 2))
+    # the planar path skips the edge distance (rgb = w c / (w + 1e-10), w in [0.5, 1]): equal to one fp32 ulp
+    assert (images - rgba[..., :3].permute(0, 3, 1, 2)).abs().max() <= 2.5e-7
     assert torch.equal(masks[:, 0], (rgba[..., 3] > 0).float())
     want_img, want_mask = _oracle_images(sc, sc["verts"], sc["tex"][0])
     assert torch.equal(masks.cpu(), want_mask)
