@@ -528,7 +528,7 @@ k_face_zbuf(const float* __restrict__ face_verts, const int64_t* __restrict__ fi
         }
         const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
         int base = 0;
-        if (lane == 31 && warp_total > 0) base = atomicAdd(&hdr[5], warp_total);
+        if (lane == 31 && warp_total > 0) base = atomicAdd(&hdr[0], warp_total);  // hdr[0] = units needed
         base = __shfl_sync(0xffffffffu, base, 31);
         const int slot0 = base + incl - nu;
         for (int u = 0; u < nu; ++u) {
@@ -561,7 +561,7 @@ k_sweep_units(const FaceRec* __restrict__ rec, const int* __restrict__ unit_face
               const float* __restrict__ ndc_x, const float* __restrict__ ndc_y, unsigned long long* __restrict__ zkey) {
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    const int64_t total = min((int64_t)hdr[5], unit_capacity);
+    const int64_t total = min((int64_t)hdr[0], unit_capacity);
     for (int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < total; p += nwarps) {
         const int f = __ldg(unit_face + p), blk = __ldg(unit_block + p);
         const int n = blk >> 20, uy = (blk >> 10) & 1023, ux = blk & 1023;

@@ -226,7 +226,7 @@ def algorithmic_bytes(op, key, tex=512):
     return None
 
 
-def c1_first_approach(dev, steps=50, size=256, run_cpu=True):
+def c1_first_approach(dev, steps=200, size=256, run_cpu=True):
     """BASELINE configs[0]: cow texture fit, 1 view 256x256, 50 Adam steps of the masked-MSE loop of
     first_approach.py:191-213 (render -> masked MSE -> backward -> Adam; no VGG on this path)."""
     import torch
@@ -248,7 +248,7 @@ def c1_first_approach(dev, steps=50, size=256, run_cpu=True):
         opt.step()
         return loss
 
-    for _ in range(5):
+    for _ in range(20):
         step()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -258,7 +258,7 @@ def c1_first_approach(dev, steps=50, size=256, run_cpu=True):
     e1.record()
     torch.cuda.synchronize()
     gpu_ms = e0.elapsed_time(e1) / steps
-    res = {"workload": "cow texture fit, 1 view x 256^2, masked-MSE loop (first_approach.py:191-213), 50 Adam steps",
+    res = {"workload": "cow texture fit, 1 view x 256^2, masked-MSE loop (first_approach.py:191-213), 200 timed Adam steps",
            "gpu_ms_per_step": gpu_ms, "gpu_it_per_s": 1e3 / gpu_ms, "final_loss": float(loss)}
     if run_cpu:
         from oracle import loss_oracle as lo
@@ -449,6 +449,10 @@ def run_st3d(args):
                                            "constants of the loop); not the headline"}
 
     if rank == 0 and world == 1 and not args.no_extras:
+        import gc
+        opt = opt2 = opt3 = None          # release the 8 x 512^2 iteration state before the small workload
+        gc.collect()
+        torch.cuda.empty_cache()
         out["c1_first_approach"] = c1_first_approach(dev, run_cpu=not args.no_cpu_baseline)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n = 2
