@@ -375,8 +375,9 @@ def run_st3d(args):
         nbytes = algorithmic_bytes(op, key)
         ach = nbytes / (avg_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": 1028184064 if (op, key) == ("gram_backward", (8, 64, 262144)) else None,
-                    "traffic_source": "ncu --set full, profiles/r1_ncu_full_gram_render.csv (dram read+write of k_gram_tc_bwd<64>)",
+                    "traffic": 1026100000 if (op, key) == ("gram_backward", (8, 64, 262144)) else None,
+                    "traffic_source": "ncu --set full, profiles/r1_ncu_full_final.csv: dram read 537.0 MB + write 489.1 MB of "
+                                      "k_gram_tc_bwd<64, NHWC> (per launch)",
                     "kernel": f"{op} {key}: " + ("k_gram_tc_bwd<C> (tcgen05 kind::tf32, TMA, TMEM)" if op == "gram_backward"
                                                  else "k_gram_tc_fwd<C> (tcgen05 kind::tf32, TMA, TMEM)" if op.startswith("gram")
                                                  else "k_mse"),
