@@ -1,0 +1,48 @@
+// Does q = fma(fma(-b, a*r, a), r, a*r) with r = __frcp_rn(b) reproduce __fdiv_rn(a, b) bit for bit?
+// (Markstein-style correction from a correctly rounded reciprocal.)  Counts mismatches over random inputs.
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+__device__ __forceinline__ uint32_t rng(uint64_t& s) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (uint32_t)(s >> 16); }
+__global__ void probe(unsigned long long* mism, unsigned long long* first_a_b, int mode, uint64_t seed, int iters) {
+    uint64_t s = seed * 0x9E3779B97F4A7C15ull + (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 0xD1B54A32D192ED03ull + 1;
+    unsigned long long local = 0;
+    for (int i = 0; i < iters; ++i) {
+        float a, b;
+        if (mode == 0) {          // arbitrary normal floats with exponents in [-40, 40]
+            a = __uint_as_float((rng(s) & 0x807FFFFFu) | (((rng(s) % 81) + 87) << 23));
+            b = __uint_as_float((rng(s) & 0x807FFFFFu) | (((rng(s) % 81) + 87) << 23));
+        } else {                  // workload-like: a = small edge value, b = area-like or depth-like
+            a = (float)((int)(rng(s) % 2000001) - 1000000) * 1e-9f * (float)(1 + rng(s) % 1000);
+            b = ((rng(s) & 1) ? 1.0f : -1.0f) * (1e-7f + (float)(rng(s) % 1000000) * 1e-8f * (float)(1 + rng(s) % 100));
+        }
+        const float want = __fdiv_rn(a, b);
+        const float r = __frcp_rn(b);
+        const float q0 = __fmul_rn(a, r);
+        const float rem = __fmaf_rn(-b, q0, a);
+        const float got = __fmaf_rn(rem, r, q0);
+        if (__float_as_uint(want) != __float_as_uint(got) && !(want != want && got != got)) {
+            if (local == 0 && atomicCAS(&first_a_b[0], 0ull, 1ull) == 0ull) {
+                first_a_b[1] = __float_as_uint(a); first_a_b[2] = __float_as_uint(b);
+                first_a_b[3] = __float_as_uint(want); first_a_b[4] = __float_as_uint(got);
+            }
+            ++local;
+        }
+    }
+    if (local) atomicAdd(mism, local);
+}
+int main() {
+    unsigned long long *d_m, *d_f, h_m, h_f[5];
+    cudaMalloc(&d_m, 8); cudaMalloc(&d_f, 40);
+    for (int mode = 0; mode < 2; ++mode) {
+        cudaMemset(d_m, 0, 8); cudaMemset(d_f, 0, 40);
+        const int blocks = 148 * 16, threads = 256, iters = 4096, rounds = 8;
+        for (int r = 0; r < rounds; ++r) probe<<<blocks, threads>>>(d_m, d_f, mode, 1234 + r, iters);
+        cudaDeviceSynchronize();
+        cudaMemcpy(&h_m, d_m, 8, cudaMemcpyDeviceToHost); cudaMemcpy(h_f, d_f, 40, cudaMemcpyDeviceToHost);
+        printf("mode %d: %llu mismatches in %.3g divisions", mode, h_m, (double)blocks * threads * iters * rounds);
+        if (h_m) printf("  first: a=%08llx b=%08llx want=%08llx got=%08llx", h_f[1], h_f[2], h_f[3], h_f[4]);
+        printf("\n");
+    }
+    return 0;
+}
