@@ -3,8 +3,8 @@
 kernels, with view-sharded data parallelism over NCCL (one process per GPU).
 
 One iteration = render the content mesh (no grad) -> render the current mesh -> VGG features of
-content / style / current -> content MSE + Gram style loss -> backward into the texture -> (all-reduce
-of the texture gradient when sharded) -> Adam step.
+content / style / current -> content MSE + Gram style loss (+ mesh regularisers) -> backward into the
+texture / vertices -> (all-reduce of the flat gradient when sharded) -> Adam step.
 """
 from __future__ import annotations
 
@@ -34,21 +34,50 @@ def allreduce_gradients(params, group=None) -> None:
         off += n
 
 
-class TextureStyleOptimizer:
-    """Optimises the UV texture of a mesh so that its renders match a style image (Approach 2)."""
+DEFAULT_WEIGHTS = {"main_loss_weight": 3.0, "mesh_verts_weight": 1.0, "mesh_edge_loss_weight": 1.0,
+                   "mesh_laplacian_smoothing_weight": 1.0, "mesh_normal_consistency_weight": 1.0}
 
-    def __init__(self, verts, faces, verts_uvs, faces_uvs, texture, vgg, image_size, lr: float = 0.01,
-                 style_weight: float = 1e6, content_weight: float = 1.0, precision=None,
-                 cache_constants: bool = False, world_size: int = 1, group=None, channels_last: bool = True,
-                 fuse_conv_relu: bool = True):
+
+class StyleOptimizer:
+    """"Approach 2" of the reference (second_approach.py): optimise the texture and / or the vertices of a mesh so
+    that its renders match a style image under a VGG perceptual loss.
+
+    target   'texture' | 'mesh' | 'both'  (utils.py:173-204, losses.py:101-126)
+    texture  UV map (T,T,3) with verts_uvs / faces_uvs, or per-vertex colours via `verts_rgb` (V,3)
+    style    one image (1,3,H,W), or J images with `style_weights` -> blended Gram targets (BASELINE configs[3])
+    """
+
+    def __init__(self, verts, faces, vgg, image_size, *, verts_uvs=None, faces_uvs=None, texture=None, verts_rgb=None,
+                 target: str = "texture", lr: float = 0.01, style_weight: float = 1e6, content_weight: float = 1.0,
+                 weights=None, style_weights=None, precision=None, cache_constants: bool = False, world_size: int = 1,
+                 group=None, channels_last: bool = True, fuse_conv_relu: bool = True):
         dev = verts.device
         if dev.type != "cuda":
-            raise RuntimeError("TextureStyleOptimizer needs CUDA tensors: libst3d has no CPU path")
-        self.verts = verts.detach().float().contiguous()
+            raise RuntimeError("StyleOptimizer needs CUDA tensors: libst3d has no CPU path")
+        if target not in ("texture", "mesh", "both"):
+            raise ValueError(f"unknown optimisation target {target!r}")
+        if (texture is None) == (verts_rgb is None):
+            raise ValueError("give either texture (+ verts_uvs, faces_uvs) or verts_rgb")
+        self.target = target
+        self.verts0 = verts.detach().float().contiguous()                       # content geometry / regulariser anchor
         self.faces = faces.to(torch.int32).contiguous()
-        self.face_uvs = verts_uvs.float()[faces_uvs.long()].contiguous()          # (F,3,2)
-        self.content_texture = texture.detach().clone().float().contiguous()     # the mesh as loaded
-        self.texture = texture.detach().clone().float().contiguous().requires_grad_(True)
+        self.uv_mode = texture is not None
+        if self.uv_mode:
+            self.face_uvs = verts_uvs.float()[faces_uvs.long()].contiguous()    # (F,3,2)
+            colour0 = texture
+        else:
+            self.face_uvs = None
+            colour0 = verts_rgb
+        self.content_colour = colour0.detach().clone().float().contiguous()     # the mesh as loaded
+        self.colour = colour0.detach().clone().float().contiguous()
+        self.verts = self.verts0.clone()
+        params = []
+        if target in ("mesh", "both"):
+            params.append(self.verts.requires_grad_(True))
+        if target in ("texture", "both"):
+            params.append(self.colour.requires_grad_(True))
+        self.params = params
+        self.weights = dict(DEFAULT_WEIGHTS, **(weights or {}))
         # cuDNN's tensor-core convolutions are NHWC kernels: with NCHW tensors torch wraps every conv in
         # nchw<->nhwc transposes (~20 % of a step).  channels_last keeps activations NHWC end to end.
         self.channels_last = channels_last
@@ -59,20 +88,43 @@ class TextureStyleOptimizer:
             self.vgg = vgg.to(memory_format=torch.channels_last) if channels_last else vgg
         self.image_size = image_size
         self.style_weight, self.content_weight = style_weight, content_weight
+        self.style_weights = style_weights
         self.precision = precision
         self.cache_constants = cache_constants
         self.world_size, self.group = world_size, group
-        self.optimizer = torch.optim.Adam([self.texture], lr=lr)
+        self.optimizer = torch.optim.Adam(params, lr=lr)
         self._cache = {}
+        self._edges = None
         self.last_images: Optional[torch.Tensor] = None
+
+    # kept for the first API of this module
+    @property
+    def texture(self):
+        return self.colour
 
     def _nn_input(self, images):
         return images.contiguous(memory_format=torch.channels_last) if self.channels_last else images
 
-    def _render(self, texture, R, T):
-        images, masks, _ = Fn.render_views(self.verts, self.faces, R, T, self.image_size, texture=texture,
-                                           face_uvs=self.face_uvs)
+    def _render(self, verts, colour, R, T):
+        kw = dict(texture=colour, face_uvs=self.face_uvs) if self.uv_mode else dict(verts_rgb=colour)
+        images, masks, _ = Fn.render_views(verts, self.faces, R, T, self.image_size, **kw)
         return images, masks
+
+    def _style_targets(self, style_img):
+        x = self._nn_input(style_img)
+        if self.style_weights is not None:
+            return losses.blended_style_targets(x, self.style_weights, self.vgg, self.precision)
+        return losses.style_targets(x, self.vgg, self.precision)
+
+    def _regularisers(self):
+        from . import mesh_losses as ml
+        if self._edges is None:
+            self._edges = ml.unique_edges(self.faces)
+        w = self.weights
+        return (w["mesh_verts_weight"] * Fn.mse_loss(self.verts, self.verts0)
+                + w["mesh_edge_loss_weight"] * ml.edge_loss(self.verts, self.faces, edges=self._edges)
+                + w["mesh_laplacian_smoothing_weight"] * ml.laplacian_smoothing(self.verts, self.faces, edges=self._edges)
+                + w["mesh_normal_consistency_weight"] * ml.normal_consistency(self.verts, self.faces))
 
     def step(self, R: torch.Tensor, T: torch.Tensor, style_img: torch.Tensor) -> torch.Tensor:
         """One optimisation iteration over the views (R, T) held by this rank; returns the loss (device scalar)."""
@@ -82,18 +134,38 @@ class TextureStyleOptimizer:
             content_feat, grams = self._cache["content_feat"], self._cache["grams"]
         else:
             with torch.no_grad():
-                content_imgs, _ = self._render(self.content_texture, R, T)                     # second_approach.py:160
+                content_imgs, _ = self._render(self.verts0, self.content_colour, R, T)         # second_approach.py:160
                 content_feat = losses.get_features(self._nn_input(content_imgs), self.vgg,
                                                    {"21": losses.CONTENT_LAYER})[losses.CONTENT_LAYER]
-            grams = losses.style_targets(self._nn_input(style_img), self.vgg, self.precision)                   # losses.py:19-25
+            grams = self._style_targets(style_img)                                              # losses.py:19-25
             if self.cache_constants:
                 self._cache = dict(key=key, content_feat=content_feat, grams=grams)
-        current_imgs, _ = self._render(self.texture, R, T)                                      # :165
+        current_imgs, _ = self._render(self.verts, self.colour, R, T)                           # :165
         cur = losses.get_features(self._nn_input(current_imgs), self.vgg)
         loss = losses.perceptual_loss_from_features(cur, content_feat, grams, self.style_weight, self.content_weight,
                                                     self.precision)
+        if self.target != "texture":                                                            # losses.py:108-124
+            # the perceptual term is a mean over views (sharded: scale by 1/world); the regularisers are
+            # view-independent and identical on every rank, so they are added once, after the all-reduce
+            loss = self.weights["main_loss_weight"] * loss
         (loss / self.world_size).backward()                                                     # :188
-        allreduce_gradients([self.texture], self.group)
+        allreduce_gradients(self.params, self.group)
+        if self.target != "texture":
+            reg = self._regularisers()
+            reg.backward()
+            loss = loss + reg
         self.optimizer.step()                                                                   # :189
         self.last_images = current_imgs.detach()
         return loss.detach()
+
+
+class TextureStyleOptimizer(StyleOptimizer):
+    """Texture-only optimisation of a UV-mapped mesh (the `texture` target, BASELINE configs[1])."""
+
+    def __init__(self, verts, faces, verts_uvs, faces_uvs, texture, vgg, image_size, lr: float = 0.01,
+                 style_weight: float = 1e6, content_weight: float = 1.0, precision=None, cache_constants: bool = False,
+                 world_size: int = 1, group=None, channels_last: bool = True, fuse_conv_relu: bool = True):
+        super().__init__(verts, faces, vgg, image_size, verts_uvs=verts_uvs, faces_uvs=faces_uvs, texture=texture,
+                         target="texture", lr=lr, style_weight=style_weight, content_weight=content_weight,
+                         precision=precision, cache_constants=cache_constants, world_size=world_size, group=group,
+                         channels_last=channels_last, fuse_conv_relu=fuse_conv_relu)

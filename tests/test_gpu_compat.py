@@ -250,3 +250,39 @@ def test_general_shader_path_matches_fused_and_oracle(scene):
     assert (rgba.detach().cpu() - want.detach()).abs().max() <= 2e-4
     (want * wgt.cpu()).sum().backward()
     assert ((tex.grad[0].cpu() - tex_o.grad).abs().max() / tex_o.grad.abs().max()).item() <= 1e-3
+
+
+@pytest.mark.parametrize("target,mode", [("both", "uv"), ("texture", "vertex"), ("mesh", "uv")])
+def test_style_optimizer_targets(cow, target, mode):
+    """st3d.optimize.StyleOptimizer: every target / texture kind steps, stays finite and matches the oracle's first loss."""
+    from st3d.optimize import StyleOptimizer
+    dev = torch.device("cuda:0")
+    vgg = _vgg(dev)
+    R, T = ro.random_cameras(2, generator=torch.Generator().manual_seed(6))
+    style = torch.rand(3, 3, S, S, generator=torch.Generator().manual_seed(7))
+    tex = F.interpolate(cow["texture"].permute(2, 0, 1)[None], size=S, mode="bilinear", align_corners=False)[0].permute(1, 2, 0)
+    vrgb = torch.rand(cow["verts"].shape[0], 3, generator=torch.Generator().manual_seed(8))
+    kw = dict(verts_uvs=cow["verts_uvs"].to(dev), faces_uvs=cow["faces_uvs"].to(dev), texture=tex.to(dev)) if mode == "uv" \
+        else dict(verts_rgb=vrgb.to(dev))
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        opt = StyleOptimizer(cow["verts"].to(dev), cow["faces"].to(dev), vgg, S, target=target, weights=WEIGHTS,
+                             style_weights=[0.5, 0.3, 0.2], **kw)
+        hist = [opt.step(R.to(dev), T.to(dev), style.to(dev)).item() for _ in range(3)]
+        assert all(np.isfinite(hist))
+        if target == "texture":
+            assert hist[-1] < hist[0]
+        # oracle: same first iteration
+        vgg_cpu = _vgg("cpu")
+        okw = dict(texture=tex, verts_uvs=cow["verts_uvs"], faces_uvs=cow["faces_uvs"]) if mode == "uv" else dict(verts_rgb=vrgb)
+        img = ro.images_and_masks(ro.render_views(cow["verts"], cow["faces"], R, T, S, nthreads=8, **okw))[0]
+        sf, cf = lo.get_features(style, vgg_cpu), lo.get_features(img, vgg_cpu)
+        wts = torch.tensor([0.5, 0.3, 0.2]).reshape(-1, 1, 1)
+        want = sum(1e6 * lo.style_layer_loss(cf[k], (lo.gram_matrix(sf[k]) * wts).sum(0, keepdim=True)) for k in lo.STYLE_LAYERS)
+        # content term is zero at the first iteration (current == content); regularisers at the initial mesh
+        if target != "texture":
+            want = WEIGHTS["main_loss_weight"] * want + lo._regularisers(cow["verts"], cow["verts"], cow["faces"], WEIGHTS)
+        assert abs(hist[0] - want.item()) <= 3e-3 * abs(want.item()), (hist[0], want.item())
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
