@@ -153,6 +153,8 @@ def cpu_one_view_iterations(args, n_timed, n_warm):
     import torch
     from oracle import loss_oracle as lo
     from oracle import render_oracle as ro
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
+    torch.set_num_threads(os.cpu_count() or 1)
     w = load_workload(args.size)
     vgg = seeded_vgg()
     R, T = cameras(args.views)
@@ -174,7 +176,7 @@ def cpu_one_view_iterations(args, n_timed, n_warm):
         loss = lo.perceptual_loss(current, content, w["style"], vgg, 1e6, 1.0)
         loss.backward()
         opt.step()
-        float(loss)
+        float(loss.detach())
         if i >= n_warm:
             times.append(time.perf_counter() - t0)
     return sum(times) / len(times), threads
@@ -259,10 +261,11 @@ def c1_first_approach(dev, steps=200, size=256, run_cpu=True):
     torch.cuda.synchronize()
     gpu_ms = e0.elapsed_time(e1) / steps
     res = {"workload": "cow texture fit, 1 view x 256^2, masked-MSE loop (first_approach.py:191-213), 200 timed Adam steps",
-           "gpu_ms_per_step": gpu_ms, "gpu_it_per_s": 1e3 / gpu_ms, "final_loss": float(loss)}
+           "gpu_ms_per_step": gpu_ms, "gpu_it_per_s": 1e3 / gpu_ms, "final_loss": float(loss.detach())}
     if run_cpu:
         from oracle import loss_oracle as lo
         from oracle import render_oracle as ro
+        torch.set_num_threads(os.cpu_count() or 1)
         texc = w["texture"].clone().requires_grad_(True)
         optc = torch.optim.Adam([texc], lr=0.01)
         threads = os.cpu_count() or 1
