@@ -39,10 +39,14 @@ def load_as_tensor(image_path, size=512):
 
 
 def get_vgg():
-    """utils.py:48-52: frozen VGG-19 `.features` with ImageNet weights."""
+    """utils.py:48-52: frozen VGG-19 `.features` with ImageNet weights.  On CUDA the module is returned with
+    cuDNN's fused conv+bias+ReLU calls and channels_last weights (same module names, same tapped values)."""
     vgg = models.vgg19(weights=models.VGG19_Weights.IMAGENET1K_V1).features.to(device)
     for p in vgg.parameters():
         p.requires_grad_(False)
+    if device.type == "cuda":
+        from st3d.vgg import fuse_vgg_features
+        vgg = fuse_vgg_features(vgg, channels_last=True)
     return vgg
 
 

@@ -22,6 +22,8 @@ def get_features(image: torch.Tensor, model, layers=None, stop_after_last_tap: b
     and the in-place ReLU that follows it (that ReLU rewrites the tapped tensor, so it is part of the tap)."""
     layers = VGG_TAPS if layers is None else layers
     last = max((int(k) for k in layers if str(k).isdigit()), default=None)
+    if getattr(model, "_st3d_channels_last", False) and image.dim() == 4 and image.is_cuda:
+        image = image.contiguous(memory_format=torch.channels_last)
     feats, x, done = {}, image, False
     for name, module in model._modules.items():
         if done and not ((isinstance(module, torch.nn.ReLU) and module.inplace) or isinstance(module, torch.nn.Identity)):

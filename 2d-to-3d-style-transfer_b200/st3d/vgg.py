@@ -75,4 +75,5 @@ def fuse_vgg_features(features: nn.Sequential, channels_last: bool = True) -> nn
     fused = nn.Sequential(out).eval()
     if channels_last:
         fused = fused.to(memory_format=torch.channels_last)
+    fused._st3d_channels_last = bool(channels_last)     # get_features converts its input accordingly
     return fused
