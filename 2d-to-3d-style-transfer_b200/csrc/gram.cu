@@ -149,15 +149,25 @@ k_gram_finalize(const float* __restrict__ partials, int splits, int sp, int B, i
     }
 }
 
-// S = gs * (dG + dG^T)
-__global__ void k_gram_symmetrize(const float* __restrict__ dgram, int B, int C, float gs,
-                                  const float* __restrict__ gs_dev, float* __restrict__ sym) {
-    const int64_t cc = (int64_t)C * C, i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)B * cc) return;
+// S = gs * (dG + dG^T): 32x32 tiles, the transposed operand goes through shared memory so both global reads
+// are coalesced
+__global__ void __launch_bounds__(256)
+k_gram_symmetrize(const float* __restrict__ dgram, int B, int C, float gs, const float* __restrict__ gs_dev,
+                  float* __restrict__ sym) {
+    __shared__ float tile[32][33];
     if (gs_dev) gs *= __ldg(gs_dev);
-    const int64_t b = i / cc, e = i % cc;
-    const int r = (int)(e / C), c = (int)(e % C);
-    sym[i] = gs * (dgram[i] + dgram[b * cc + (int64_t)c * C + r]);
+    const int b = blockIdx.z, r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const float* G = dgram + (int64_t)b * C * C;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int k = ty; k < 32; k += 8) {  // tile of dG at (c0.., r0..): read rows c0+k, columns r0+tx
+        const int rr = c0 + k, cc = r0 + tx;
+        tile[k][tx] = (rr < C && cc < C) ? G[(int64_t)rr * C + cc] : 0.0f;
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        const int rr = r0 + k, cc = c0 + tx;
+        if (rr < C && cc < C) sym[(int64_t)b * C * C + (int64_t)rr * C + cc] = gs * (G[(int64_t)rr * C + cc] + tile[tx][k]);
+    }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -305,7 +315,7 @@ extern "C" int st3d_gram_backward(const float* feat, const float* dgram, int B, 
         return ST3D_ERR_WORKSPACE;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    k_gram_symmetrize<<<cdiv((int64_t)B * C * C, 256), 256, 0, s>>>(dgram, B, C, grad_scale, grad_scale_dev, p.sym);
+    k_gram_symmetrize<<<dim3(cdiv(C, 32), cdiv(C, 32), B), 256, 0, s>>>(dgram, B, C, grad_scale, grad_scale_dev, p.sym);
     ST3D_LAUNCH_OK("k_gram_symmetrize");
     const bool nhwc = layout == ST3D_FEAT_NHWC;
     if (precision == ST3D_GRAM_TF32) return gram_tc_backward(feat, p, nhwc, accumulate, grad_feat, s);

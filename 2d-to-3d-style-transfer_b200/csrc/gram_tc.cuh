@@ -60,6 +60,31 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z)
         : "memory");
 }
+// multicast variants: the box lands at the same shared-memory offset of every CTA in `mask`, and signals the
+// mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, int z,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -122,7 +147,7 @@ constexpr uint32_t instr_desc(int M, int N, int a_mn, int b_mn) {
 }
 
 constexpr int kThreads = 192;
-constexpr int kScratchFloats = 4 * 32 * 33;  // one padded 32x32 transpose tile per epilogue warp
+constexpr int kScratchFloats = 4 * 32 * 36;  // one padded (16-byte aligned rows) 32x32 transpose tile per epilogue warp
 
 // =====================================================================================================
 // forward
@@ -141,7 +166,10 @@ struct FwdCfg {
     static constexpr int SLAB_BYTES = C * 128;       // C rows x 32 fp32
     static constexpr int STAGE_BYTES = KPS * SLAB_BYTES;
     static constexpr int STAGES = C == 64 ? 5 : (C == 128 ? 5 : (C == 256 ? 6 : 3));
-    static constexpr int BOX_ROWS = C < 256 ? C : 256;
+    // C = 512: the four panel CTAs of one (image, split) form a thread-block cluster; each loads its own quarter of
+    // the slab (its 128 channels) and TMA-multicasts it to all four, so the slab leaves L2 once instead of four times
+    static constexpr bool CLUSTER = C == 512;
+    static constexpr int BOX_ROWS = CLUSTER ? 128 : (C < 256 ? C : 256);
     static constexpr int BOXES = C / BOX_ROWS;
     static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + kScratchFloats * 4 + (2 * STAGES + 2) * 8 + 16;
 };
@@ -175,7 +203,7 @@ k_gram_tc_fwd(const __grid_constant__ CUtensorMap map, float* __restrict__ parti
     if (threadIdx.x == 0) {
         for (int i = 0; i < Cfg::STAGES; ++i) {
             mbar_init(full0 + 8 * i, 1);
-            mbar_init(empty0 + 8 * i, 1);
+            mbar_init(empty0 + 8 * i, Cfg::CLUSTER ? 4 : 1);  // cluster: every CTA's MMAs must have released the slot
         }
         mbar_init(tmem_full, 1);
         fence_barrier_init();
@@ -184,6 +212,7 @@ k_gram_tc_fwd(const __grid_constant__ CUtensorMap map, float* __restrict__ parti
     if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(smem_u32(tmem_slot));
     tc_fence_before();
     __syncthreads();
+    if (Cfg::CLUSTER) cluster_sync_all();  // peers' barriers are initialised before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -198,19 +227,30 @@ k_gram_tc_fwd(const __grid_constant__ CUtensorMap map, float* __restrict__ parti
                 if (NHWC) {
                     constexpr int ROWS = 32 * Cfg::KPS;
                     const int x = (int)(k0 + (int64_t)it * ROWS);  // rows >= HW are zero-filled by the 3D map
+                    if (Cfg::CLUSTER) {
 #pragma unroll
-                    for (int cg = 0; cg < C / 32; ++cg)
-                        tma_load_3d(dst + cg * ROWS * 128, &map, full0 + 8 * st, cg * 32, x, b);
+                        for (int cg = 4 * g; cg < 4 * g + 4; ++cg)
+                            tma_load_3d_mc(dst + cg * ROWS * 128, &map, full0 + 8 * st, cg * 32, x, b, 0xF);
+                    } else {
+#pragma unroll
+                        for (int cg = 0; cg < C / 32; ++cg)
+                            tma_load_3d(dst + cg * ROWS * 128, &map, full0 + 8 * st, cg * 32, x, b);
+                    }
                 } else {
 #pragma unroll
                     for (int kk = 0; kk < Cfg::KPS; ++kk) {
                         // the split owns [k0, k1), a whole number of stages except for the last split of an
                         // image, whose tail boxes lie beyond HW and come back zero-filled
                         const int x = (int)(k0 + ((int64_t)it * Cfg::KPS + kk) * 32);
+                        if (Cfg::CLUSTER) {
+                            tma_load_2d_mc(dst + kk * Cfg::SLAB_BYTES + g * Cfg::BOX_ROWS * 128, &map, full0 + 8 * st, x,
+                                           b * C + g * Cfg::BOX_ROWS, 0xF);
+                        } else {
 #pragma unroll
-                        for (int bx = 0; bx < Cfg::BOXES; ++bx)
-                            tma_load_2d(dst + kk * Cfg::SLAB_BYTES + bx * Cfg::BOX_ROWS * 128, &map, full0 + 8 * st, x,
-                                        b * C + bx * Cfg::BOX_ROWS);
+                            for (int bx = 0; bx < Cfg::BOXES; ++bx)
+                                tma_load_2d(dst + kk * Cfg::SLAB_BYTES + bx * Cfg::BOX_ROWS * 128, &map, full0 + 8 * st, x,
+                                            b * C + bx * Cfg::BOX_ROWS);
+                        }
                     }
                 }
             }
@@ -260,7 +300,8 @@ k_gram_tc_fwd(const __grid_constant__ CUtensorMap map, float* __restrict__ parti
                         }
                     }
                 }
-                mma_commit(empty0 + 8 * st);  // frees the smem slot once these MMAs have read it
+                // frees the smem slot once these MMAs have read it (in every CTA of the cluster when multicasting)
+                if (Cfg::CLUSTER) mma_commit_mc(empty0 + 8 * st, 0xF); else mma_commit(empty0 + 8 * st);
             }
             mma_commit(tmem_full);
         }
@@ -270,27 +311,38 @@ k_gram_tc_fwd(const __grid_constant__ CUtensorMap map, float* __restrict__ parti
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         float* P = partials + ((int64_t)b * splits + s) * C * C;
-        float* sc = scratch + q * 32 * 33;
+        float* sc = scratch + q * 32 * 36;
         float r[32];
 #pragma unroll 1
         for (int p = 0; p < Cfg::PANELS; ++p) {
             const int panel_row0 = (C == 512 ? g : p) * 128;
+            // M = 128: TMEM lane = row.  M = 64: rows 16q..16q+15 live in lanes 32q..32q+15.
+            const int rows = Cfg::M == 128 ? 32 : 16;
+            const int row0 = Cfg::M == 128 ? panel_row0 + q * 32 : q * 16;
 #pragma unroll 1
             for (int c0 = 0; c0 < C; c0 += 32) {
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p * 256 + c0), r);
+                // transpose through padded shared memory with 128-bit accesses: one warp store then covers
+                // 4 rows x 128 contiguous bytes of the partial tile
 #pragma unroll
-                for (int j = 0; j < 32; ++j) sc[lane * 33 + j] = r[j];
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(sc + lane * 36 + 4 * j) =
+                        make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
                 __syncwarp();
-                // M = 128: TMEM lane = row.  M = 64: rows 16q..16q+15 live in lanes 32q..32q+15.
-                const int rows = Cfg::M == 128 ? 32 : 16;
-                const int row0 = Cfg::M == 128 ? panel_row0 + q * 32 : q * 16;
-                for (int t = 0; t < rows; ++t) P[(int64_t)(row0 + t) * C + c0 + lane] = sc[t * 33 + lane];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int t = 4 * i + (lane >> 3);
+                    if (t < rows)
+                        *reinterpret_cast<float4*>(P + (int64_t)(row0 + t) * C + c0 + 4 * (lane & 7)) =
+                            *reinterpret_cast<const float4*>(sc + t * 36 + 4 * (lane & 7));
+                }
                 __syncwarp();
             }
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (Cfg::CLUSTER) cluster_sync_all();  // no CTA leaves while peers may still multicast into it / arrive on its barriers
     if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
@@ -552,8 +604,27 @@ static int launch_fwd(const float* feat, const GramPlan& p, cudaStream_t s) {
                                           (int)Cfg::SMEM));
         attr_done = true;
     }
-    k_gram_tc_fwd<C, NHWC><<<dim3(Cfg::GROUPS, p.splits, p.B), kThreads, Cfg::SMEM, s>>>(map, p.partials, p.splits,
-                                                                                        p.k_chunk, p.HW);
+    if (Cfg::CLUSTER) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(Cfg::GROUPS, p.splits, p.B);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = Cfg::SMEM;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = Cfg::GROUPS;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        float* partials = p.partials;
+        int splits = p.splits;
+        int64_t k_chunk = p.k_chunk, HW = p.HW;
+        ST3D_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gram_tc_fwd<C, NHWC>, map, partials, splits, k_chunk, HW));
+    } else {
+        k_gram_tc_fwd<C, NHWC><<<dim3(Cfg::GROUPS, p.splits, p.B), kThreads, Cfg::SMEM, s>>>(map, p.partials, p.splits,
+                                                                                            p.k_chunk, p.HW);
+    }
     ST3D_LAUNCH_OK("k_gram_tc_fwd");
     return ST3D_OK;
 }
