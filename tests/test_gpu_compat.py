@@ -286,3 +286,38 @@ def test_style_optimizer_targets(cow, target, mode):
         assert abs(hist[0] - want.item()) <= 3e-3 * abs(want.item()), (hist[0], want.item())
     finally:
         torch.backends.cudnn.allow_tf32 = prev
+
+
+def test_loss_trajectory_matches_oracle_loop(cow):
+    """Four Adam iterations of the texture optimisation: the loss trajectory of the CUDA path follows the CPU
+    oracle loop (same VGG weights, same cameras, same style image) -- forward, backward and the update compose."""
+    from st3d.optimize import TextureStyleOptimizer
+    dev = torch.device("cuda:0")
+    R, T = ro.random_cameras(2, generator=torch.Generator().manual_seed(12))
+    style = torch.rand(1, 3, S, S, generator=torch.Generator().manual_seed(13))
+    tex0 = F.interpolate(cow["texture"].permute(2, 0, 1)[None], size=S, mode="bilinear", align_corners=False)[0].permute(1, 2, 0).contiguous()
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        opt = TextureStyleOptimizer(cow["verts"].to(dev), cow["faces"].to(dev), cow["verts_uvs"].to(dev),
+                                    cow["faces_uvs"].to(dev), tex0.to(dev), _vgg(dev), S, lr=0.01)
+        got = [opt.step(R.to(dev), T.to(dev), style.to(dev)).item() for _ in range(4)]
+        vgg_cpu = _vgg("cpu")
+        tex = tex0.clone().requires_grad_(True)
+        adam = torch.optim.Adam([tex], lr=0.01)
+        kw = dict(verts_uvs=cow["verts_uvs"], faces_uvs=cow["faces_uvs"], nthreads=8)
+        with torch.no_grad():
+            content = ro.images_and_masks(ro.render_views(cow["verts"], cow["faces"], R, T, S, texture=tex0, **kw))[0]
+        want = []
+        for _ in range(4):
+            adam.zero_grad()
+            cur = ro.images_and_masks(ro.render_views(cow["verts"], cow["faces"], R, T, S, texture=tex, **kw))[0]
+            loss = lo.perceptual_loss(cur, content, style.repeat(2, 1, 1, 1), vgg_cpu, 1e6, 1.0)
+            loss.backward()
+            adam.step()
+            want.append(loss.item())
+        assert want[-1] < want[0]
+        for g, w in zip(got, want):
+            assert abs(g - w) <= 5e-3 * abs(w), (got, want)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
