@@ -413,20 +413,24 @@ k_prepare(unsigned long long* __restrict__ zkey, int64_t nkeys, int* __restrict_
 __device__ __forceinline__ void zbuf_test_pixel(float px, float py, const FaceVerts& v, float denom, bool zpos, bool persp,
                                                 float e0x, float e0y, float e1x, float e1y, float e2x, float e2y,
                                                 unsigned fid, unsigned long long* slot) {
+    const float rden = __frcp_rn(denom);  // loop-invariant per face: hoisted by the compiler out of the pixel sweep
+    const bool den_ok = exp_safe(denom);
     const float w0 = fsub(fmul(fsub(px, v.x1), e0y), fmul(fsub(py, v.y1), e0x));
     const float w1 = fsub(fmul(fsub(px, v.x2), e1y), fmul(fsub(py, v.y2), e1x));
     const float w2 = fsub(fmul(fsub(px, v.x0), e2y), fmul(fsub(py, v.y0), e2x));
     // necessary for "inside" when every z > 0: the three edge values share one strict sign
     if (zpos && !((w0 > 0.0f && w1 > 0.0f && w2 > 0.0f) || (w0 < 0.0f && w1 < 0.0f && w2 < 0.0f))) return;
-    float b0 = fdiv(w0, denom), b1 = fdiv(w1, denom), b2 = fdiv(w2, denom);
+    float b0 = fdiv_r(w0, denom, rden, den_ok), b1 = fdiv_r(w1, denom, rden, den_ok), b2 = fdiv_r(w2, denom, rden, den_ok);
     if (persp) {
         const float t0 = fmul(fmul(b0, v.z1), v.z2);
         const float t1 = fmul(fmul(v.z0, b1), v.z2);
         const float t2 = fmul(fmul(v.z0, v.z1), b2);
         const float d = fmaxf(fadd(fadd(t0, t1), t2), kEps);
-        b0 = fdiv(t0, d);
-        b1 = fdiv(t1, d);
-        b2 = fdiv(t2, d);
+        const float rd = __frcp_rn(d);
+        const bool d_ok = exp_safe(d);
+        b0 = fdiv_r(t0, d, rd, d_ok);
+        b1 = fdiv_r(t1, d, rd, d_ok);
+        b2 = fdiv_r(t2, d, rd, d_ok);
     }
     if (!(b0 > 0.0f && b1 > 0.0f && b2 > 0.0f)) return;
     const float pz = fadd(fadd(fmul(b0, v.z0), fmul(b1, v.z1)), fmul(b2, v.z2));

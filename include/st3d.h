@@ -64,8 +64,9 @@ int st3d_transform_verts_backward(const float* verts, const float* R, const floa
 size_t st3d_raster_workspace_size(int N, int64_t F_total, int H, int W, int64_t list_capacity);
 
 /* Workspace header, readable by the host AFTER the stream has been synchronised:
- * [0] = (face,tile) pairs needed by the last call, [1] = 1 if the bins overflowed (results invalid,
- * re-run with a larger list_capacity), [2] = capacity in pairs, [4] = 1 if some face has a vertex nearer
+ * [0] = work-list entries needed by the last call ((face,tile) pairs of the binned path, face units of the
+ * hard path), [1] = 1 if that list overflowed (results invalid, re-run with a larger list_capacity),
+ * [2] = capacity in entries, [4] = 1 if some face has a vertex nearer
  * than st3d_render_args.z_clip (PyTorch3D would clip such faces against the near plane, clip.py; that
  * path is not implemented, so the caller must treat the render as unsupported rather than trust it). */
 #define ST3D_WS_HEADER_INTS 16
@@ -73,8 +74,10 @@ size_t st3d_raster_workspace_size(int N, int64_t F_total, int H, int W, int64_t 
 /* _C.rasterize_meshes: face_verts (F_total,3,3) in NDC (z = view depth); mesh n owns faces
  * [first[n], first[n]+num[n]).  Outputs (N,H,W,K): pix_to_face int64 (-1 = empty, packed face
  * index), zbuf, dists; bary (N,H,W,K,3).  K <= ST3D_MAX_FACES_PER_PIXEL.  bin_size and
- * max_faces_per_bin are accepted for signature parity and ignored: bins are 16x16-pixel tiles with
- * exact-size face lists (no silent face drop, SURVEY section 7 "max_faces_per_bin overflow"). */
+ * max_faces_per_bin are accepted for signature parity and ignored: hard rasterization (blur 0, K = 1)
+ * uses no bins at all (faces go straight to a 64-bit z-buffer), the general path bins into 16x16-pixel
+ * tiles with exact-size face lists -- no silent face drop either way (SURVEY section 7
+ * "max_faces_per_bin overflow"). */
 int st3d_rasterize_meshes_forward(const float* face_verts, const int64_t* mesh_to_face_first_idx,
                                   const int64_t* num_faces_per_mesh, int N, int64_t F_total, int64_t max_faces_in_mesh,
                                   int H, int W, float blur_radius, int faces_per_pixel, int bin_size,
@@ -101,8 +104,8 @@ int st3d_interp_face_attrs_backward(const int64_t* pix_to_face, const float* bar
  * Fused multi-view renderer = MeshRenderer(MeshRasterizer, SoftPhongShader) with AmbientLights,
  * faces_per_pixel = 1, for N cameras of ONE mesh in one call.  Replaces the per-view loop of
  * utils.py:65-77 (render_meshes) and everything beneath it:
- * transform -> tile bins -> fine raster -> UV / vertex-colour sample -> ambient shade ->
- * softmax_rgb_blend, one pass, fragments never materialised.
+ * transform + face setup -> z-buffer rasterization -> per-pixel resolve with UV / vertex-colour sample ->
+ * ambient shade -> softmax_rgb_blend; fragments are never materialised.
  * ---------------------------------------------------------------------------------------------- */
 #define ST3D_TEX_UV 0
 #define ST3D_TEX_VERTEX 1

@@ -9,9 +9,9 @@ __global__ void probe(unsigned long long* mism, unsigned long long* first_a_b, i
     unsigned long long local = 0;
     for (int i = 0; i < iters; ++i) {
         float a, b;
-        if (mode == 0) {          // arbitrary normal floats with exponents in [-40, 40]
-            a = __uint_as_float((rng(s) & 0x807FFFFFu) | (((rng(s) % 81) + 87) << 23));
-            b = __uint_as_float((rng(s) & 0x807FFFFFu) | (((rng(s) % 81) + 87) << 23));
+        if (mode == 0) {          // arbitrary normal floats with biased exponents in [70, 184] (the guard window of fdiv_r)
+            a = __uint_as_float((rng(s) & 0x807FFFFFu) | (((rng(s) % 115) + 70) << 23));
+            b = __uint_as_float((rng(s) & 0x807FFFFFu) | (((rng(s) % 115) + 70) << 23));
         } else {                  // workload-like: a = small edge value, b = area-like or depth-like
             a = (float)((int)(rng(s) % 2000001) - 1000000) * 1e-9f * (float)(1 + rng(s) % 1000);
             b = ((rng(s) & 1) ? 1.0f : -1.0f) * (1e-7f + (float)(rng(s) % 1000000) * 1e-8f * (float)(1 + rng(s) % 100));
