@@ -236,17 +236,16 @@ class MeshRasterizer(torch.nn.Module):
         R, T = cams.R.to(verts.device), cams.T.to(verts.device)
         N, Fn = R.shape[0], faces.shape[0]
         ndc = _fn.transform_verts(verts, R, T, fov, aspect, znear)                    # (N,V,3)
-        z_clip = rs.z_clip_value if rs.z_clip_value is not None else znear / 2.0
-        if bool((ndc[..., 2].detach() < z_clip).any()):
-            raise NotImplementedError("a vertex lies in front of the near clipping plane (z < znear / 2): "
-                                      "near-plane face clipping is not implemented")
         face_verts = ndc[:, faces.long()].reshape(N * Fn, 3, 3)
         first = torch.arange(N, device=verts.device, dtype=torch.int64) * Fn
         num = torch.full((N,), Fn, device=verts.device, dtype=torch.int64)
         clip_bary = rs.clip_barycentric_coords if rs.clip_barycentric_coords is not None else rs.blur_radius > 0.0
         persp = rs.perspective_correct if rs.perspective_correct is not None else True
+        # upstream: z_clip = znear / 2 for perspective-correct rasterization unless given
+        z_clip = rs.z_clip_value if rs.z_clip_value is not None else (znear / 2.0 if persp else None)
         p2f, zbuf, bary, dists = _fn.rasterize_meshes(face_verts, first, num, _image_hw(rs.image_size), rs.blur_radius,
-                                                      rs.faces_per_pixel, persp, clip_bary, rs.cull_backfaces)
+                                                      rs.faces_per_pixel, persp, clip_bary, rs.cull_backfaces,
+                                                      z_clip_value=z_clip)
         return Fragments(p2f, zbuf, bary, dists)
 
 

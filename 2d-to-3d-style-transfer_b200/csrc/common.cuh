@@ -63,6 +63,21 @@ __device__ __forceinline__ float fdiv_r(float a, float b, float r, bool b_safe) 
     }
     return __fdiv_rn(a, b);
 }
+// Three quotients over one denominator: one range check for the lot (|a| in [2^-57, 2^57] is inside the
+// exp_safe window; NaN numerators give NaN on either path), then 3 instructions per quotient.
+__device__ __forceinline__ void fdiv3_r(float& a0, float& a1, float& a2, float b, float r, bool b_safe) {
+    const float lo = fminf(fminf(fabsf(a0), fabsf(a1)), fabsf(a2)), hi = fmaxf(fmaxf(fabsf(a0), fabsf(a1)), fabsf(a2));
+    if (b_safe && lo >= 0x1p-57f && hi <= 0x1p57f) {
+        const float q0 = __fmul_rn(a0, r), q1 = __fmul_rn(a1, r), q2 = __fmul_rn(a2, r);
+        a0 = __fmaf_rn(__fmaf_rn(-b, q0, a0), r, q0);
+        a1 = __fmaf_rn(__fmaf_rn(-b, q1, a1), r, q1);
+        a2 = __fmaf_rn(__fmaf_rn(-b, q2, a2), r, q2);
+    } else {
+        a0 = __fdiv_rn(a0, b);
+        a1 = __fdiv_rn(a1, b);
+        a2 = __fdiv_rn(a2, b);
+    }
+}
 __device__ __forceinline__ float clamp01(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -72,30 +87,32 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // Warp-aggregated scatter: lanes that hit the same key (face) are summed with shuffles and one lane
-// issues the atomics.  NV values per lane; dst(key) gives the destination of value i.
+// issues the atomics.  NV values per lane; dst(key) gives the destination of value i.  Keys are >= 0.
+// One MATCH.ANY finds the groups: a lane alone with its key (every lane, on a mesh denser than the pixel
+// grid) goes straight to its atomics; only keys shared by several lanes take the shuffle reduction.
 template <int NV, class DstFn>
 __device__ __forceinline__ void warp_aggregate_add(bool valid, int key, const float (&vals)[NV], DstFn dst) {
     const unsigned lane = threadIdx.x & 31;
-    unsigned remaining = __ballot_sync(0xffffffffu, valid);
+    if (!__any_sync(0xffffffffu, valid)) return;
+    const unsigned grp = __match_any_sync(0xffffffffu, valid ? key : (int)(0x80000000u | lane));
+    const bool shared_key = valid && (grp & (grp - 1)) != 0;
+    if (valid && !shared_key) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            if (vals[i] != 0.0f) atomicAdd(dst(key, i), vals[i]);
+    }
+    unsigned remaining = __ballot_sync(0xffffffffu, shared_key && lane == (unsigned)(__ffs(grp) - 1));  // group leaders
     while (remaining) {
         const int leader = __ffs(remaining) - 1;
+        const unsigned g = __shfl_sync(0xffffffffu, grp, leader);
         const int lk = __shfl_sync(0xffffffffu, key, leader);
-        const bool mine = valid && key == lk;
-        const unsigned grp = __ballot_sync(0xffffffffu, mine);
-        if (__popc(grp) == 1) {
-            if (mine) {
+        const bool mine = (g >> lane) & 1u;
 #pragma unroll
-                for (int i = 0; i < NV; ++i)
-                    if (vals[i] != 0.0f) atomicAdd(dst(lk, i), vals[i]);
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const float s = warp_sum(mine ? vals[i] : 0.0f);
-                if (lane == (unsigned)leader && s != 0.0f) atomicAdd(dst(lk, i), s);
-            }
+        for (int i = 0; i < NV; ++i) {
+            const float s = warp_sum(mine ? vals[i] : 0.0f);
+            if (lane == (unsigned)leader && s != 0.0f) atomicAdd(dst(lk, i), s);
         }
-        remaining &= ~grp;
+        remaining &= remaining - 1;
     }
 }
 

@@ -63,6 +63,22 @@ __device__ __forceinline__ void ndc_pixel_range(float lo_v, float hi_v, int S1, 
     while (jhi >= 0 && pix_to_ndc(jhi, S1, S2) > hi_v) --jhi;
 }
 
+// The same ranges in IMAGE order from the pixel-centre table k_prepare wrote (tab[i] = NDC coordinate of the
+// centre of image column / row i, strictly decreasing in i): [i0, i1] = {i : lo_v <= tab[i] <= hi_v}.  The
+// estimate j = a v + b (a = S / range, b = off (S - 1) / range, from the host) only seeds the search; membership
+// is decided by comparisons against the exact table values, so the result equals ndc_pixel_range's.
+__device__ __forceinline__ void table_pixel_range(const float* __restrict__ tab, int S, float a, float b, float lo_v,
+                                                  float hi_v, int& i0, int& i1) {
+    const int jhi = (int)fminf(fmaxf(floorf(fmaf(hi_v, a, b)), -1.0f), (float)(S - 1));
+    const int jlo = (int)fminf(fmaxf(ceilf(fmaf(lo_v, a, b)), 0.0f), (float)S);
+    i0 = S - 1 - jhi;  // first i with tab[i] <= hi_v
+    i1 = S - 1 - jlo;  // last i with tab[i] >= lo_v
+    while (i0 > 0 && __ldg(tab + i0 - 1) <= hi_v) --i0;
+    while (i0 < S && __ldg(tab + i0) > hi_v) ++i0;
+    while (i1 < S - 1 && __ldg(tab + i1 + 1) >= lo_v) ++i1;
+    while (i1 >= 0 && __ldg(tab + i1) < lo_v) --i1;
+}
+
 template <bool GATHER>
 __global__ void k_setup(const float* __restrict__ face_verts, const float4* __restrict__ verts_ndc,
                         const int32_t* __restrict__ faces, const int64_t* __restrict__ first_idx,
@@ -409,28 +425,27 @@ k_prepare(unsigned long long* __restrict__ zkey, int64_t nkeys, int* __restrict_
     for (int64_t i = tid; i < H; i += nth) ndc_y[i] = pix_to_ndc(H - 1 - (int)i, H, W);
 }
 
-// Exact depth test of one pixel against one face + z-buffer update (the oracle's arithmetic)
-__device__ __forceinline__ void zbuf_test_pixel(float px, float py, const FaceVerts& v, float denom, bool zpos, bool persp,
-                                                float e0x, float e0y, float e1x, float e1y, float e2x, float e2y,
-                                                unsigned fid, unsigned long long* slot) {
-    const float rden = __frcp_rn(denom);  // loop-invariant per face: hoisted by the compiler out of the pixel sweep
-    const bool den_ok = exp_safe(denom);
+// Exact depth test of one pixel against one face + z-buffer update (the oracle's arithmetic).
+// rden = __frcp_rn(denom), den_ok = exp_safe(denom): per face, computed by the caller.
+__device__ __forceinline__ void zbuf_test_pixel(float px, float py, const FaceVerts& v, float denom, float rden, bool den_ok,
+                                                bool zpos, bool persp, float e0x, float e0y, float e1x, float e1y,
+                                                float e2x, float e2y, unsigned fid, unsigned long long* slot) {
     const float w0 = fsub(fmul(fsub(px, v.x1), e0y), fmul(fsub(py, v.y1), e0x));
     const float w1 = fsub(fmul(fsub(px, v.x2), e1y), fmul(fsub(py, v.y2), e1x));
     const float w2 = fsub(fmul(fsub(px, v.x0), e2y), fmul(fsub(py, v.y0), e2x));
     // necessary for "inside" when every z > 0: the three edge values share one strict sign
     if (zpos && !((w0 > 0.0f && w1 > 0.0f && w2 > 0.0f) || (w0 < 0.0f && w1 < 0.0f && w2 < 0.0f))) return;
-    float b0 = fdiv_r(w0, denom, rden, den_ok), b1 = fdiv_r(w1, denom, rden, den_ok), b2 = fdiv_r(w2, denom, rden, den_ok);
+    float b0 = w0, b1 = w1, b2 = w2;
+    fdiv3_r(b0, b1, b2, denom, rden, den_ok);
     if (persp) {
-        const float t0 = fmul(fmul(b0, v.z1), v.z2);
-        const float t1 = fmul(fmul(v.z0, b1), v.z2);
-        const float t2 = fmul(fmul(v.z0, v.z1), b2);
+        float t0 = fmul(fmul(b0, v.z1), v.z2);
+        float t1 = fmul(fmul(v.z0, b1), v.z2);
+        float t2 = fmul(fmul(v.z0, v.z1), b2);
         const float d = fmaxf(fadd(fadd(t0, t1), t2), kEps);
-        const float rd = __frcp_rn(d);
-        const bool d_ok = exp_safe(d);
-        b0 = fdiv_r(t0, d, rd, d_ok);
-        b1 = fdiv_r(t1, d, rd, d_ok);
-        b2 = fdiv_r(t2, d, rd, d_ok);
+        fdiv3_r(t0, t1, t2, d, __frcp_rn(d), exp_safe(d));
+        b0 = t0;
+        b1 = t1;
+        b2 = t2;
     }
     if (!(b0 > 0.0f && b1 > 0.0f && b2 > 0.0f)) return;
     const float pz = fadd(fadd(fmul(b0, v.z0), fmul(b1, v.z1)), fmul(b2, v.z2));
@@ -450,7 +465,7 @@ __global__ void __launch_bounds__(128)
 k_face_zbuf(const float* __restrict__ face_verts, const int64_t* __restrict__ first_idx,
             const int64_t* __restrict__ num_faces, const float* __restrict__ verts, const int32_t* __restrict__ faces,
             const float* __restrict__ Rm, const float* __restrict__ Tv, float k00, float k11, int64_t F_per_mesh,
-            int H, int W, int cull_backfaces, float z_clip, int persp, const float* __restrict__ ndc_x,
+            int H, int W, float4 est, int cull_backfaces, float z_clip, int persp, const float* __restrict__ ndc_x,
             const float* __restrict__ ndc_y, FaceRec* __restrict__ rec, unsigned long long* __restrict__ zkey,
             int* __restrict__ unit_face, int* __restrict__ unit_block, int64_t unit_capacity, int* __restrict__ hdr) {
     const int n = blockIdx.y;
@@ -479,8 +494,10 @@ k_face_zbuf(const float* __restrict__ face_verts, const int64_t* __restrict__ fi
                 const float xv = fadd(fadd(fadd(fmul(x, sR[0]), fmul(y, sR[3])), fmul(z, sR[6])), sT[0]);
                 const float yv = fadd(fadd(fadd(fmul(x, sR[1]), fmul(y, sR[4])), fmul(z, sR[7])), sT[1]);
                 const float zv = fadd(fadd(fadd(fmul(x, sR[2]), fmul(y, sR[5])), fmul(z, sR[8])), sT[2]);
-                c[3 * k] = fdiv(fmul(xv, k00), zv);
-                c[3 * k + 1] = fdiv(fmul(yv, k11), zv);
+                const float rz = __frcp_rn(zv);  // two quotients over zv: corrected-reciprocal division (common.cuh)
+                const bool z_ok = exp_safe(zv);
+                c[3 * k] = fdiv_r(fmul(xv, k00), zv, rz, z_ok);
+                c[3 * k + 1] = fdiv_r(fmul(yv, k11), zv, rz, z_ok);
                 c[3 * k + 2] = zv;
             }
             v = FaceVerts{c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8]};
@@ -497,23 +514,21 @@ k_face_zbuf(const float* __restrict__ face_verts, const int64_t* __restrict__ fi
         const float ymin = fminf(v.y0, fminf(v.y1, v.y2)), ymax = fmaxf(v.y0, fmaxf(v.y1, v.y2));
         if (!(isfinite(xmin) && isfinite(xmax) && isfinite(ymin) && isfinite(ymax))) valid = false;
         if (valid) {
-            int jlo, jhi, klo, khi;
-            ndc_pixel_range(xmin, xmax, W, H, jlo, jhi);
-            ndc_pixel_range(ymin, ymax, H, W, klo, khi);
-            if (jlo <= jhi && klo <= khi) {
-                x0 = W - 1 - jhi;  // image x runs opposite to NDC x (A.3)
-                x1 = W - 1 - jlo;
-                y0 = H - 1 - khi;
-                y1 = H - 1 - klo;
-            } else {
+            table_pixel_range(ndc_x, W, est.x, est.y, xmin, xmax, x0, x1);  // image x runs opposite to NDC x (A.3)
+            table_pixel_range(ndc_y, H, est.z, est.w, ymin, ymax, y0, y1);
+            if (x0 > x1 || y0 > y1) {
                 valid = false;
+                x0 = y0 = 1;
+                x1 = y1 = 0;
             }
         }
-        FaceRec r;
-        r.a = make_float4(v.x0, v.y0, v.z0, v.x1);
-        r.b = make_float4(v.y1, v.z1, v.x2, v.y2);
-        r.c = make_float4(v.z2, area, __int_as_float(x0 | (x1 << 16)), __int_as_float(y0 | (y1 << 16)));
-        rec[f] = r;
+        if (valid) {  // only a face that covers a pixel centre can win one: nothing else ever reads the record
+            FaceRec r;
+            r.a = make_float4(v.x0, v.y0, v.z0, v.x1);
+            r.b = make_float4(v.y1, v.z1, v.x2, v.y2);
+            r.c = make_float4(v.z2, area, __int_as_float(x0 | (x1 << 16)), __int_as_float(y0 | (y1 << 16)));
+            rec[f] = r;
+        }
     }
     const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
     const bool small = valid && bw * bh <= 16;
@@ -523,36 +538,39 @@ k_face_zbuf(const float* __restrict__ face_verts, const int64_t* __restrict__ fi
         // one atomicAdd per WARP (prefix sum over the lanes' unit counts), not one per face
         const int ux = (valid && !small) ? (bw + kUnitSide - 1) / kUnitSide : 0;
         const int nu = (valid && !small) ? ux * ((bh + kUnitSide - 1) / kUnitSide) : 0;
-        const int lane = threadIdx.x & 31;
-        int incl = nu;
+        if (__any_sync(0xffffffffu, nu > 0)) {  // (on meshes denser than the pixel grid most warps queue nothing)
+            const int lane = threadIdx.x & 31;
+            int incl = nu;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
-        int base = 0;
-        if (lane == 31 && warp_total > 0) base = atomicAdd(&hdr[0], warp_total);  // hdr[0] = units needed
-        base = __shfl_sync(0xffffffffu, base, 31);
-        const int slot0 = base + incl - nu;
-        for (int u = 0; u < nu; ++u) {
-            if (slot0 + u < unit_capacity) {
-                unit_face[slot0 + u] = (int)f;
-                unit_block[slot0 + u] = (n << 20) | ((u / ux) << 10) | (u % ux);
-            } else {
-                hdr[1] = 1;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+            int base = 0;
+            if (lane == 31) base = atomicAdd(&hdr[0], warp_total);  // hdr[0] = units needed
+            base = __shfl_sync(0xffffffffu, base, 31);
+            const int slot0 = base + incl - nu;
+            for (int u = 0; u < nu; ++u) {
+                if (slot0 + u < unit_capacity) {
+                    unit_face[slot0 + u] = (int)f;
+                    unit_block[slot0 + u] = (n << 20) | ((u / ux) << 10) | (u % ux);
+                } else {
+                    hdr[1] = 1;
+                }
             }
         }
     }
     if (small) {
         const bool zpos = v.z0 > 0.0f && v.z1 > 0.0f && v.z2 > 0.0f;
-        const float denom = fadd(area, kEps);
+        const float denom = fadd(area, kEps), rden = __frcp_rn(denom);
+        const bool den_ok = exp_safe(denom);
         const float e0y = fsub(v.y2, v.y1), e0x = fsub(v.x2, v.x1), e1y = fsub(v.y0, v.y2), e1x = fsub(v.x0, v.x2);
         const float e2y = fsub(v.y1, v.y0), e2x = fsub(v.x1, v.x0);
         for (int qy = y0; qy <= y1; ++qy)
             for (int qx = x0; qx <= x1; ++qx)
-                zbuf_test_pixel(__ldg(ndc_x + qx), __ldg(ndc_y + qy), v, denom, zpos, persp != 0, e0x, e0y, e1x, e1y, e2x,
-                                e2y, (unsigned)f, zview + (int64_t)qy * W + qx);
+                zbuf_test_pixel(__ldg(ndc_x + qx), __ldg(ndc_y + qy), v, denom, rden, den_ok, zpos, persp != 0, e0x, e0y,
+                                e1x, e1y, e2x, e2y, (unsigned)f, zview + (int64_t)qy * W + qx);
     }
 }
 
@@ -575,7 +593,8 @@ k_sweep_units(const FaceRec* __restrict__ rec, const int* __restrict__ unit_face
         const int x0 = (xr & 0xffff) + ux * kUnitSide, x1 = min(xr >> 16, x0 + kUnitSide - 1);
         const int y0 = (yr & 0xffff) + uy * kUnitSide, y1 = min(yr >> 16, y0 + kUnitSide - 1);
         const bool zpos = v.z0 > 0.0f && v.z1 > 0.0f && v.z2 > 0.0f;
-        const float denom = fadd(rc.y, kEps);
+        const float denom = fadd(rc.y, kEps), rden = __frcp_rn(denom);
+        const bool den_ok = exp_safe(denom);
         const float e0y = fsub(v.y2, v.y1), e0x = fsub(v.x2, v.x1), e1y = fsub(v.y0, v.y2), e1x = fsub(v.x0, v.x2);
         const float e2y = fsub(v.y1, v.y0), e2x = fsub(v.x1, v.x0);
         unsigned long long* zview = zkey + (int64_t)n * H * W;
@@ -583,8 +602,8 @@ k_sweep_units(const FaceRec* __restrict__ rec, const int* __restrict__ unit_face
             for (int bx = x0; bx <= x1; bx += 8) {
                 const int qx = bx + (lane & 7), qy = by + (lane >> 3);
                 if (qx > x1 || qy > y1) continue;
-                zbuf_test_pixel(__ldg(ndc_x + qx), __ldg(ndc_y + qy), v, denom, zpos, persp != 0, e0x, e0y, e1x, e1y, e2x,
-                                e2y, (unsigned)f, zview + (int64_t)qy * W + qx);
+                zbuf_test_pixel(__ldg(ndc_x + qx), __ldg(ndc_y + qy), v, denom, rden, den_ok, zpos, persp != 0, e0x, e0y,
+                                e1x, e1y, e2x, e2y, (unsigned)f, zview + (int64_t)qy * W + qx);
             }
         }
     }
@@ -612,13 +631,17 @@ static int run_hard(const RasterWs& ws, const HardSrc& h, int N, int H, int W, i
     ST3D_LAUNCH_OK("k_prepare");
     if (h.F_per_mesh > 0) {
         const dim3 grid(cdiv(h.F_per_mesh, 128), N);
+        // seeds of the pixel-range search: NDC-ordered pixel index j(v) = a v + b (A.3 PixToNonSquareNdc inverted)
+        const double rx = W > H ? 2.0 * W / H : 2.0, ry = H > W ? 2.0 * H / W : 2.0;
+        const float4 est = make_float4((float)(W / rx), (float)(0.5 * rx * (W - 1) / rx), (float)(H / ry),
+                                       (float)(0.5 * ry * (H - 1) / ry));
         if (h.verts)
             k_face_zbuf<1><<<grid, 128, 0, s>>>(nullptr, nullptr, nullptr, h.verts, h.faces, h.R, h.T, h.k00, h.k11,
-                                                h.F_per_mesh, H, W, h.cull_backfaces, h.z_clip, persp, ws.ndc_x, ws.ndc_y,
-                                                ws.rec, ws.zkey, ws.list, ws.list_tile, ws.capacity, ws.hdr);
+                                                h.F_per_mesh, H, W, est, h.cull_backfaces, h.z_clip, persp, ws.ndc_x,
+                                                ws.ndc_y, ws.rec, ws.zkey, ws.list, ws.list_tile, ws.capacity, ws.hdr);
         else
             k_face_zbuf<0><<<grid, 128, 0, s>>>(h.face_verts, h.first_idx, h.num_faces, nullptr, nullptr, nullptr, nullptr,
-                                                0.0f, 0.0f, h.F_per_mesh, H, W, h.cull_backfaces, h.z_clip, persp,
+                                                0.0f, 0.0f, h.F_per_mesh, H, W, est, h.cull_backfaces, h.z_clip, persp,
                                                 ws.ndc_x, ws.ndc_y, ws.rec, ws.zkey, ws.list, ws.list_tile, ws.capacity,
                                                 ws.hdr);
         ST3D_LAUNCH_OK("k_face_zbuf");

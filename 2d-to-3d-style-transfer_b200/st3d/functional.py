@@ -111,10 +111,21 @@ class _RasterizeFn(torch.autograd.Function):
 
 
 def rasterize_meshes(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, image_size, blur_radius=0.0,
-                     faces_per_pixel=1, perspective_correct=True, clip_barycentric_coords=False, cull_backfaces=False):
-    return _RasterizeFn.apply(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, image_size, float(blur_radius),
-                              int(faces_per_pixel), bool(perspective_correct), bool(clip_barycentric_coords),
-                              bool(cull_backfaces))
+                     faces_per_pixel=1, perspective_correct=True, clip_barycentric_coords=False, cull_backfaces=False,
+                     z_clip_value: Optional[float] = None):
+    """Upstream `rasterize_meshes` from packed face vertices on: optional near-plane clipping (torch ops, as
+    upstream's clip.py) -> `_C.rasterize_meshes` (libst3d kernels) -> indices / barycentrics mapped back to the
+    unclipped faces.  Differentiable w.r.t. face_verts."""
+    args = (image_size, float(blur_radius), int(faces_per_pixel), bool(perspective_correct),
+            bool(clip_barycentric_coords), bool(cull_backfaces))
+    if z_clip_value is None:
+        return _RasterizeFn.apply(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, *args)
+    from . import clip as _clip
+    cl = _clip.clip_faces(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, float(z_clip_value),
+                          bool(perspective_correct))
+    p2f, zbuf, bary, dists = _RasterizeFn.apply(cl.face_verts, cl.mesh_to_face_first_idx, cl.num_faces_per_mesh, *args)
+    p2f, bary = _clip.convert_clipped_rasterization_to_original_faces(p2f, bary, cl)
+    return p2f, zbuf, bary, dists
 
 
 class _InterpFn(torch.autograd.Function):

@@ -245,6 +245,95 @@ def fragments_from_faces(face_verts, pix_to_face, perspective_correct=True, clip
 
 
 # --------------------------------------------------------------------------------------------
+# A.2 near-plane clipping (upstream renderer/mesh/clip.py: clip_faces +
+# convert_clipped_rasterization_to_original_faces; reached from the reference through the
+# MeshRasterizer built at first_approach.py:107-111 with z_clip_value = znear / 2)
+# --------------------------------------------------------------------------------------------
+def _plane_crossings(tri, i1, z_clip, perspective_correct):
+    """tri (3,3) rows = vertices [x_ndc, y_ndc, z_view]; i1 = index of the vertex that is alone on its
+    side of the plane.  p2 is the PREVIOUS vertex, p3 the NEXT one.  Returns the crossing points p4 (on
+    p1-p2), p5 (on p1-p3) and the barycentric coordinates of p4, p5 w.r.t. the unclipped face."""
+    i2, i3 = (i1 - 1) % 3, (i1 + 1) % 3
+    p1, p2, p3 = tri[i1], tri[i2], tri[i3]
+    w2 = (p1[2] - z_clip) / (p1[2] - p2[2])
+    w3 = (p1[2] - z_clip) / (p1[2] - p3[2])
+    if perspective_correct:      # interpolate in view space (x_ndc * z), then divide again
+        def unproject(p):
+            return torch.stack([p[0] * p[2], p[1] * p[2], p[2]])
+
+        def project(q):
+            return torch.stack([q[0] / q[2], q[1] / q[2], q[2]])
+        q1, q2, q3 = unproject(p1), unproject(p2), unproject(p3)
+        p4 = project(q1 * (1 - w2) + q2 * w2)
+        p5 = project(q1 * (1 - w3) + q3 * w3)
+    else:
+        p4 = p1 * (1 - w2) + p2 * w2
+        p5 = p1 * (1 - w3) + p3 * w3
+    zero = torch.zeros((), dtype=tri.dtype)
+    b4, b5 = [zero, zero, zero], [zero, zero, zero]
+    b4[i1], b4[i2] = 1 - w2, w2
+    b5[i1], b5[i3] = 1 - w3, w3
+    return p4, p5, torch.stack(b4), torch.stack(b5), i2, i3
+
+
+def clip_faces(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, z_clip, perspective_correct=True):
+    """Clip every face against the plane z = z_clip.  Per face, by the number of vertices
+    with z < z_clip:  0 -> kept;  3 -> removed;  2 (p1 in front) -> the triangle (p4, p5, p1);
+    1 (p1 behind) -> the quad split into (p4, p2, p5) and (p5, p2, p3), linked as neighbours.
+    Differentiable in the dtype of face_verts.  Returns a dict:
+      face_verts (Fc,3,3), first (N), num (N), to_unclipped (Fc) i64, conversion (Fc,3,3) whose COLUMN k
+      holds the unclipped-face barycentrics of clipped vertex k (identity for kept faces),
+      was_clipped (Fc) bool, neighbor (Fc) i64 (-1 = none)."""
+    dt = face_verts.dtype
+    first = mesh_to_face_first_idx.tolist()
+    num = num_faces_per_mesh.tolist()
+    behind = (face_verts[:, :, 2].detach() < z_clip)
+    out_fv, to_unc, conv, was, neigh, new_first, new_num = [], [], [], [], [], [], []
+    eye = torch.eye(3, dtype=dt)
+    for n in range(len(first)):
+        new_first.append(len(out_fv))
+        for f in range(first[n], first[n] + num[n]):
+            nb = int(behind[f].sum())
+            tri = face_verts[f]
+            if nb == 0:
+                out_fv.append(tri); to_unc.append(f); conv.append(eye); was.append(False); neigh.append(-1)
+            elif nb == 2:
+                i1 = int((~behind[f]).nonzero()[0])
+                p4, p5, b4, b5, i2, i3 = _plane_crossings(tri, i1, z_clip, perspective_correct)
+                out_fv.append(torch.stack([p4, p5, tri[i1]]))
+                conv.append(torch.stack([b4, b5, eye[i1]], dim=1))
+                to_unc.append(f); was.append(True); neigh.append(-1)
+            elif nb == 1:
+                i1 = int(behind[f].nonzero()[0])
+                p4, p5, b4, b5, i2, i3 = _plane_crossings(tri, i1, z_clip, perspective_correct)
+                k = len(out_fv)
+                out_fv.append(torch.stack([p4, tri[i2], p5]))
+                conv.append(torch.stack([b4, eye[i2], b5], dim=1))
+                out_fv.append(torch.stack([p5, tri[i2], tri[i3]]))
+                conv.append(torch.stack([b5, eye[i2], eye[i3]], dim=1))
+                to_unc += [f, f]; was += [True, True]; neigh += [k + 1, k]
+        new_num.append(len(out_fv) - new_first[-1])
+    Fc = len(out_fv)
+    return dict(face_verts=torch.stack(out_fv) if Fc else face_verts.new_zeros((0, 3, 3)),
+                first=torch.tensor(new_first, dtype=torch.int64), num=torch.tensor(new_num, dtype=torch.int64),
+                to_unclipped=torch.tensor(to_unc, dtype=torch.int64),
+                conversion=torch.stack(conv) if Fc else face_verts.new_zeros((0, 3, 3)),
+                was_clipped=torch.tensor(was, dtype=torch.bool), neighbor=torch.tensor(neigh, dtype=torch.int64))
+
+
+def convert_clipped_to_unclipped(pix_to_face, bary, clipped):
+    """pix_to_face -> indices of the unclipped faces; barycentrics of clipped faces -> barycentrics of
+    the unclipped face: b_unclipped = conversion @ b_clipped."""
+    mask = pix_to_face >= 0
+    idx = pix_to_face.clamp(min=0)
+    p2f = torch.where(mask, clipped["to_unclipped"][idx], pix_to_face)
+    conv = clipped["conversion"].to(bary.dtype)[idx]                     # (...,3,3)
+    b = (conv * bary[..., None, :]).sum(dim=-1)
+    use = (mask & clipped["was_clipped"][idx])[..., None]
+    return p2f, torch.where(use, b, bary)
+
+
+# --------------------------------------------------------------------------------------------
 # A.4 texture sampling
 # --------------------------------------------------------------------------------------------
 def interpolate_face_attributes(pix_to_face, bary, face_attrs):
@@ -352,8 +441,9 @@ DEFAULT_MATERIALS = dict(ambient=(1.0, 1.0, 1.0), diffuse=(1.0, 1.0, 1.0), specu
 def render_views(verts, faces, R, T, image_size, texture=None, verts_uvs=None, faces_uvs=None,
                  verts_rgb=None, blur_radius=0.0, faces_per_pixel=1, fov=60.0, znear=1.0, zfar=100.0,
                  sigma=1e-4, gamma=1e-4, background=(1.0, 1.0, 1.0), lights=None, materials=None,
-                 nthreads=1, return_fragments=False):
+                 nthreads=1, return_fragments=False, z_clip=None):
     """Render N views of one mesh.  Differentiable w.r.t. verts / texture / verts_rgb.
+    z_clip: near-plane clip depth (None = znear / 2, what MeshRasterizer infers for perspective cameras).
 
     Coverage (pix_to_face) comes from the exact C rasterizer on exactly-transformed fp32 verts;
     zbuf/bary/dists are then recomputed differentiably in the dtype of `verts`.
@@ -369,11 +459,23 @@ def render_views(verts, faces, R, T, image_size, texture=None, verts_uvs=None, f
     fv_exact = ndc_exact[:, faces].reshape(N * Fn, 3, 3)
     first = torch.arange(N, dtype=torch.int64) * Fn
     num = torch.full((N,), Fn, dtype=torch.int64)
-    p2f, zbuf_x, bary_x, dists_x = rasterize_naive(fv_exact, first, num, (H, W), blur_radius, faces_per_pixel,
-                                                    True, blur_radius > 0, False, nthreads)
+    z_clip = znear / 2.0 if z_clip is None else z_clip
     ndc = transform_verts_torch(verts, R, T, k00, k11)
     fv = ndc[:, faces].reshape(N * Fn, 3, 3)
-    zbuf, bary, dists = fragments_from_faces(fv, p2f, True, blur_radius > 0)
+    if bool((fv_exact[:, :, 2] < z_clip).any()):    # A.2: some face crosses (or lies behind) the clip plane
+        cl_x = clip_faces(fv_exact, first, num, np.float32(z_clip).item(), True)
+        p2f_c, zbuf_x, bary_x, dists_x = rasterize_naive(cl_x["face_verts"], cl_x["first"], cl_x["num"], (H, W),
+                                                          blur_radius, faces_per_pixel, True, blur_radius > 0, False,
+                                                          nthreads)
+        cl = clip_faces(fv, first, num, z_clip, True)
+        assert torch.equal(cl["to_unclipped"], cl_x["to_unclipped"])
+        zbuf, bary_c, dists = fragments_from_faces(cl["face_verts"], p2f_c, True, blur_radius > 0)
+        p2f, bary = convert_clipped_to_unclipped(p2f_c, bary_c, cl)
+        _, bary_x = convert_clipped_to_unclipped(p2f_c, bary_x, cl_x)
+    else:
+        p2f, zbuf_x, bary_x, dists_x = rasterize_naive(fv_exact, first, num, (H, W), blur_radius, faces_per_pixel,
+                                                        True, blur_radius > 0, False, nthreads)
+        zbuf, bary, dists = fragments_from_faces(fv, p2f, True, blur_radius > 0)
     local = torch.where(p2f >= 0, p2f % Fn, p2f)
     if texture is not None:
         fuv = verts_uvs.to(verts.dtype)[faces_uvs.to(torch.int64)]

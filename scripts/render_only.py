@@ -6,8 +6,21 @@ import numpy as np, torch
 from st3d import ops, functional as Fn, cameras as cm
 d = np.load(os.path.join(ROOT, "tests/golden/cow_mesh.npz"))
 dev = "cuda"
-verts = torch.from_numpy(d["verts"]).to(dev); faces = torch.from_numpy(d["faces"]).int().to(dev)
-fuv = torch.from_numpy(d["verts_uvs"])[torch.from_numpy(d["faces_uvs"]).long()].to(dev)
+verts, faces = torch.from_numpy(d["verts"]), torch.from_numpy(d["faces"]).long()
+uvs, fuvs = torch.from_numpy(d["verts_uvs"]), torch.from_numpy(d["faces_uvs"]).long()
+def subdivide(verts, faces):
+    e = torch.cat([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]], dim=0)
+    uniq, inv = torch.unique(torch.sort(e, dim=1).values, dim=0, return_inverse=True)
+    mid = 0.5 * (verts[uniq[:, 0]] + verts[uniq[:, 1]])
+    V, F_ = verts.shape[0], faces.shape[0]
+    m01, m12, m20 = V + inv[:F_], V + inv[F_:2 * F_], V + inv[2 * F_:]
+    a, b, c = faces[:, 0], faces[:, 1], faces[:, 2]
+    nf = torch.cat([torch.stack([a, m01, m20], 1), torch.stack([m01, b, m12], 1), torch.stack([m20, m12, c], 1),
+                    torch.stack([m01, m12, m20], 1)], dim=0)
+    return torch.cat([verts, mid], dim=0), nf
+for _ in range(int(os.environ.get("SUBDIV", 0))):      # SUBDIV=4: 1.5 M faces (BASELINE configs[4] scale)
+    verts, faces = subdivide(verts, faces); uvs, fuvs = subdivide(uvs, fuvs)
+fuv = uvs[fuvs].to(dev); verts = verts.to(dev); faces = faces.int().to(dev)
 S = int(os.environ.get("SIZE", 512)); N = int(os.environ.get("VIEWS", 8))
 tex = torch.rand(S, S, 3, device=dev)
 R, T = cm.random_view_cameras(N, generator=torch.Generator().manual_seed(0)); R, T = R.to(dev), T.to(dev)
@@ -16,6 +29,6 @@ spec = ops.RenderSpec(image_size=(S, S), k00=k00, k11=k11, layout=ops.LAYOUT_PLA
 g = torch.randn(N, 3, S, S, device=dev)
 for i in range(int(os.environ.get("REPS", 3))):
     out = ops.render_forward(spec, verts, faces, R, T, face_uvs=fuv, texture=tex)
-    ops.render_backward(out[3], g, need_verts=True)
+    ops.render_backward(out[3], g, need_verts=os.environ.get("NEED_VERTS", "1") == "1")
 torch.cuda.synchronize(); ops.poll_overflow(block=True)
 print("ok", float((out[2] >= 0).float().mean()))
