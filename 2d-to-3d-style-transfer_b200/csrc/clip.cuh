@@ -111,7 +111,7 @@ __device__ __forceinline__ void clip_convert_bary(const ClipTri& t, float b0, fl
 
 // Backward of clip_triangle: gt[9] = d loss / d clipped-triangle vertices, gcv[9] = d loss / d cv
 // -> accumulated into g[9] = d loss / d unclipped NDC vertices (x0,y0,z0,x1,...).
-__device__ __noinline__ void clip_triangle_backward(const FaceVerts& v, float zc, int t, const float* gt, const float* gcv,
+static __device__ __noinline__ void clip_triangle_backward(const FaceVerts& v, float zc, int t, const float* gt, const float* gcv,
                                                     float* g) {
     ClipFrame c;
     clip_frame(v, zc, c);

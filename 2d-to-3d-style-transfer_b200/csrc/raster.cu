@@ -11,6 +11,7 @@
 
 #include <type_traits>
 
+#include "clip.cuh"
 #include "common.cuh"
 #include "shade.cuh"
 
@@ -344,19 +345,90 @@ k_fine(const FaceRec* __restrict__ rec, const int* __restrict__ tile_count, cons
 }
 
 // -------------------------------------------------------------------------------------------------
-// 5b. hard rasterization (blur_radius == 0, faces_per_pixel == 1): pair-parallel global z-buffer
+// 5b. hard rasterization (blur_radius == 0, faces_per_pixel == 1) without bins:
+//     k_prepare -> k_face_zbuf -> k_sweep_units -> k_resolve
 // -------------------------------------------------------------------------------------------------
-// Phase A (k_zbuf_pairs): one WARP per (face, tile) pair of the bins -- a unit of at most 16x16 pixels,
-// so the load is balanced whatever the distribution of faces over the image.  The warp sweeps the
-// face's pixel box (clipped to the tile) in 8x4 steps; lanes strictly inside the face compute the
-// oracle's exact depth and issue one 64-bit atomicMin on (depth bits << 32 | face id) into a global
-// z-buffer.  That key order IS the oracle's lexicographic (z, face) order, so the winner does not depend
-// on timing.  Phase B (k_resolve): one thread per pixel, row-major (128-byte coalesced stores), evaluates
-// its winner once (barycentrics, edge distance) and runs the fused texture / shade / blend epilogue.
+// Every candidate (face, pixel) pair computes the oracle's exact depth and issues one 64-bit atomicMin on
+// (depth bits << 32 | face id) into a global z-buffer.  That key order IS the oracle's lexicographic (z, face)
+// order, so the winner does not depend on timing.  k_resolve (one thread per pixel, row-major, 128-byte
+// coalesced stores) evaluates its winner once and runs the fused texture / shade / blend epilogue.
+
+// Sub-triangle of a near-plane-clipped face for the sweep (clip.cuh); by-value in and out so the caller's
+// hot-path variables stay in registers.
+struct TriBox {
+    int x0, x1, y0, y1;  // inclusive pixel ranges, image order; x0 > x1 when no pixel centre is covered
+    float area;
+    bool valid;
+};
+
+// Area, culling and the exact pixel ranges of one projected triangle
+__device__ __forceinline__ TriBox tri_box(const FaceVerts& v, int H, int W, float4 est, int cull_backfaces,
+                                          const float* __restrict__ ndc_x, const float* __restrict__ ndc_y) {
+    TriBox b{1, 0, 1, 0, 0.0f, false};
+    b.area = edge_fn(v.x2, v.y2, v.x0, v.y0, v.x1, v.y1);
+    bool valid = fabsf(b.area) > kEps;  // also false for NaN
+    if (cull_backfaces && b.area < 0.0f) valid = false;
+    if (fmaxf(v.z0, fmaxf(v.z1, v.z2)) < 0.0f) valid = false;
+    const float xmin = fminf(v.x0, fminf(v.x1, v.x2)), xmax = fmaxf(v.x0, fmaxf(v.x1, v.x2));
+    const float ymin = fminf(v.y0, fminf(v.y1, v.y2)), ymax = fmaxf(v.y0, fmaxf(v.y1, v.y2));
+    if (!(isfinite(xmin) && isfinite(xmax) && isfinite(ymin) && isfinite(ymax))) valid = false;
+    if (valid) {
+        table_pixel_range(ndc_x, W, est.x, est.y, xmin, xmax, b.x0, b.x1);  // image x runs opposite to NDC x (A.3)
+        table_pixel_range(ndc_y, H, est.z, est.w, ymin, ymax, b.y0, b.y1);
+        if (b.x0 > b.x1 || b.y0 > b.y1) {
+            valid = false;
+            b.x0 = b.y0 = 1;
+            b.x1 = b.y1 = 0;
+        }
+    }
+    b.valid = valid;
+    return b;
+}
+
+struct ClipUnit {
+    FaceVerts v;
+    TriBox box;
+};
+
+static __device__ __noinline__ ClipUnit clipped_unit(FaceVerts v, float z_clip, int t, int H, int W, float4 est,
+                                              int cull_backfaces, const float* ndc_x, const float* ndc_y) {
+    ClipTri ct;
+    clip_triangle(v, z_clip, t, ct);
+    ClipUnit u;
+    u.v = ct.v;
+    u.box = tri_box(ct.v, H, W, est, cull_backfaces, ndc_x, ndc_y);
+    return u;
+}
+
+// The winning pixel of a clipped face: find the sub-triangle that produced the z-buffer key, evaluate it
+// and convert its barycentrics to the unclipped face (convert_clipped_rasterization_to_original_faces).
+static __device__ __noinline__ Hit resolve_clipped(FaceVerts v, float z_clip, float px, float py, unsigned depth_bits, bool persp) {
+    Hit best{};
+    best.z = -1.0f;
+    best.b0 = best.b1 = best.b2 = best.dist = -1.0f;
+    bool have = false;
+    const int nt = count_behind(v, z_clip) == 2 ? 1 : 2;
+    for (int t = 0; t < nt; ++t) {
+        ClipTri ct;
+        clip_triangle(v, z_clip, t, ct);
+        const float area = edge_fn(ct.v.x2, ct.v.y2, ct.v.x0, ct.v.y0, ct.v.x1, ct.v.y1);
+        Hit h;
+        if (!(fabsf(area) > kEps) || !eval_face(px, py, ct.v, area, 0.0f, persp, false, h)) continue;
+        const bool exact = __float_as_uint(fadd(h.z, 0.0f)) == depth_bits;
+        if (have && !exact) continue;
+        float u0, u1, u2;
+        clip_convert_bary(ct, h.b0, h.b1, h.b2, u0, u1, u2);
+        best = Hit{h.z, u0, u1, u2, h.dist};
+        have = true;
+        if (exact) break;
+    }
+    return best;
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 k_resolve(const FaceRec* __restrict__ rec, const unsigned long long* __restrict__ zkey, int H, int W, int persp,
-          const float* __restrict__ ndc_x, const float* __restrict__ ndc_y, FragOut fo, ShadeParams sp) {
+          float z_clip, const float* __restrict__ ndc_x, const float* __restrict__ ndc_y, FragOut fo, ShadeParams sp) {
     const int xi = blockIdx.x * blockDim.x + threadIdx.x, yi = blockIdx.y, n = blockIdx.z;
     if (xi >= W) return;
     const int64_t pix = ((int64_t)n * H + yi) * W + xi;
@@ -370,13 +442,13 @@ k_resolve(const FaceRec* __restrict__ rec, const unsigned long long* __restrict_
     if (hit) {
         const FaceRec r = rec[f];
         const float px = __ldg(ndc_x + xi), py = __ldg(ndc_y + yi);
-        if (need_dist) {
+        if (__float_as_int(r.c.z) < 0) {  // near-plane-clipped face
+            h = resolve_clipped(unpack(r), z_clip, px, py, (unsigned)(key >> 32), persp != 0);
+        } else if (need_dist) {
             eval_face(px, py, unpack(r), r.c.y, 0.0f, persp != 0, false, h);
         } else {
-            float dist_unused;
             face_bary(px, py, unpack(r), r.c.y, persp != 0, h.b0, h.b1, h.b2, h.z);
             h.dist = -1.0f;  // any negative value: prob = sigmoid(1e4) = 1
-            (void)dist_unused;
         }
     }
     if (MODE == 0) {
@@ -408,14 +480,13 @@ k_resolve(const FaceRec* __restrict__ rec, const unsigned long long* __restrict_
     }
 }
 
-// -------------------------------------------------------------------------------------------------
-// 5c. hard rasterization without bins: k_prepare -> k_face_zbuf -> k_big_faces -> k_resolve
-// -------------------------------------------------------------------------------------------------
-// k_prepare: z-buffer keys := all ones, header := 0, pixel-centre NDC tables (one launch instead of
-// two memsets and a table pass).
+// k_prepare: z-buffer keys := all ones, header := 0, pixel-centre NDC tables and (fused renderer) the projection
+// of every vertex for every view -- one launch instead of two memsets, a table pass and a transform pass.
 __global__ void __launch_bounds__(256)
 k_prepare(unsigned long long* __restrict__ zkey, int64_t nkeys, int* __restrict__ hdr, int H, int W,
-          float* __restrict__ ndc_x, float* __restrict__ ndc_y) {
+          float* __restrict__ ndc_x, float* __restrict__ ndc_y, const float* __restrict__ verts,
+          const float* __restrict__ Rm, const float* __restrict__ Tv, float k00, float k11, int N, int64_t V,
+          float4* __restrict__ verts_ndc) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
     ulonglong2* z2 = reinterpret_cast<ulonglong2*>(zkey);
     for (int64_t i = tid; i < nkeys / 2; i += nth) z2[i] = make_ulonglong2(~0ull, ~0ull);
@@ -423,6 +494,21 @@ k_prepare(unsigned long long* __restrict__ zkey, int64_t nkeys, int* __restrict_
     if (tid < ST3D_WS_HEADER_INTS) hdr[tid] = 0;
     for (int64_t i = tid; i < W; i += nth) ndc_x[i] = pix_to_ndc(W - 1 - (int)i, W, H);
     for (int64_t i = tid; i < H; i += nth) ndc_y[i] = pix_to_ndc(H - 1 - (int)i, H, W);
+    if (verts == nullptr || tid >= V) return;
+    for (int n = 0; n < N; ++n) {  // same operation order as k_transform / oracle_transform_verts
+        const float* R = Rm + 9 * n;
+        const float* T = Tv + 3 * n;
+        const float r0 = __ldg(R), r1 = __ldg(R + 1), r2 = __ldg(R + 2), r3 = __ldg(R + 3), r4 = __ldg(R + 4);
+        const float r5 = __ldg(R + 5), r6 = __ldg(R + 6), r7 = __ldg(R + 7), r8 = __ldg(R + 8);
+        const float t0 = __ldg(T), t1 = __ldg(T + 1), t2 = __ldg(T + 2);
+        for (int64_t i = tid; i < V; i += nth) {
+            const float x = __ldg(verts + 3 * i), y = __ldg(verts + 3 * i + 1), z = __ldg(verts + 3 * i + 2);
+            const float xv = fadd(fadd(fadd(fmul(x, r0), fmul(y, r3)), fmul(z, r6)), t0);
+            const float yv = fadd(fadd(fadd(fmul(x, r1), fmul(y, r4)), fmul(z, r7)), t1);
+            const float zv = fadd(fadd(fadd(fmul(x, r2), fmul(y, r5)), fmul(z, r8)), t2);
+            verts_ndc[(int64_t)n * V + i] = make_float4(fdiv(fmul(xv, k00), zv), fdiv(fmul(yv, k11), zv), zv, 0.0f);
+        }
+    }
 }
 
 // Exact depth test of one pixel against one face + z-buffer update (the oracle's arithmetic).
@@ -453,19 +539,62 @@ __device__ __forceinline__ void zbuf_test_pixel(float px, float py, const FaceVe
     atomicMin(slot, ((unsigned long long)__float_as_uint(fadd(pz, 0.0f)) << 32) | (unsigned long long)fid);
 }
 
-constexpr int kUnitSide = 64;  // work units of the sweep pass cover at most 64 x 64 pixels
+constexpr int kUnitSide = 64;   // work units of the sweep pass cover at most 64 x 64 pixels
+constexpr int kSmallBox = 16;   // faces whose pixel box holds at most this many centres never reach the queue
 
-// One thread per (view, face): builds the face record (optionally projecting the three vertices itself),
-// then rasterizes it straight into the global z-buffer -- no bins on this path:
-//   box of <= 16 pixels  : the thread tests its pixels itself (dense meshes: faces smaller than a pixel)
-//   larger               : queued as work units of <= 64 x 64 pixels for k_sweep_units (one warp per unit)
-// SRC = 0: face_verts (F_total,3,3) already in NDC (operator boundary); SRC = 1: world verts + faces + cameras.
+// A face crossing the near plane (1 or 2 vertices with z < z_clip): its one or two sub-triangles are queued as
+// sweep units (bit 31 of the unit word = sub-triangle index); the record keeps the UNCLIPPED coordinates and
+// carries the "clipped" flag in bit 31 of its x range, so sweep / resolve / backward recompute the sub-triangles.
+static __device__ __noinline__ void setup_clipped_face(FaceVerts v, float z_clip, int n, int f, int H, int W, float4 est,
+                                                int cull_backfaces, const float* ndc_x, const float* ndc_y,
+                                                FaceRec* rec, int* unit_face, int* unit_block, int64_t unit_capacity,
+                                                int* hdr) {
+    const int nt = count_behind(v, z_clip) == 2 ? 1 : 2;
+    int nu[2] = {0, 0}, ux[2] = {1, 1};
+    int X0 = 0x7fff, X1 = 0, Y0 = 0x7fff, Y1 = 0;
+    for (int t = 0; t < nt; ++t) {
+        const ClipUnit u = clipped_unit(v, z_clip, t, H, W, est, cull_backfaces, ndc_x, ndc_y);
+        if (!u.box.valid) continue;
+        ux[t] = (u.box.x1 - u.box.x0 + kUnitSide) / kUnitSide;
+        nu[t] = ux[t] * ((u.box.y1 - u.box.y0 + kUnitSide) / kUnitSide);
+        X0 = min(X0, u.box.x0); X1 = max(X1, u.box.x1); Y0 = min(Y0, u.box.y0); Y1 = max(Y1, u.box.y1);
+    }
+    const int total = nu[0] + nu[1];
+    if (total == 0) return;
+    FaceRec r;
+    r.a = make_float4(v.x0, v.y0, v.z0, v.x1);
+    r.b = make_float4(v.y1, v.z1, v.x2, v.y2);
+    r.c = make_float4(v.z2, 0.0f, __int_as_float((int)(0x80000000u | (unsigned)X0 | ((unsigned)X1 << 16))),
+                      __int_as_float(Y0 | (Y1 << 16)));
+    rec[f] = r;
+    hdr[5] = 1;  // informational: this call clipped faces against the near plane
+    const int base = atomicAdd(&hdr[0], total);
+    for (int u = 0; u < total; ++u) {
+        if (base + u >= unit_capacity) {
+            hdr[1] = 1;
+            break;
+        }
+        const int t = u < nu[0] ? 0 : 1, l = u - (t ? nu[0] : 0);
+        unit_face[base + u] = f;
+        unit_block[base + u] = (int)(((unsigned)t << 31) | ((unsigned)n << 20) | ((unsigned)(l / ux[t]) << 10) |
+                                     (unsigned)(l % ux[t]));
+    }
+}
+
+// One thread per (view, face): builds the face record, then rasterizes it straight into the global z-buffer --
+// no bins on this path:
+//   box of <= 16 pixels  : tested here.  The (face, pixel) candidates of the 32 faces of a warp are compacted
+//                          with a prefix sum, so one pass tests 32 candidates whatever the spread of box sizes
+//                          (on a mesh denser than the pixel grid most boxes hold 0 or 1 centre);
+//   larger               : queued as work units of <= 64 x 64 pixels for k_sweep_units (one warp per unit).
+// SRC = 0: face_verts (F_total,3,3) already in NDC (operator boundary); SRC = 1: faces + the vertices k_prepare
+// projected (world verts + cameras).
 template <int SRC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 10)
 k_face_zbuf(const float* __restrict__ face_verts, const int64_t* __restrict__ first_idx,
-            const int64_t* __restrict__ num_faces, const float* __restrict__ verts, const int32_t* __restrict__ faces,
-            const float* __restrict__ Rm, const float* __restrict__ Tv, float k00, float k11, int64_t F_per_mesh,
-            int H, int W, float4 est, int cull_backfaces, float z_clip, int persp, const float* __restrict__ ndc_x,
+            const int64_t* __restrict__ num_faces, const float4* __restrict__ verts_ndc,
+            const int32_t* __restrict__ faces, int64_t V, int64_t F_per_mesh, int H, int W, float4 est,
+            int cull_backfaces, float z_clip, int persp, const float* __restrict__ ndc_x,
             const float* __restrict__ ndc_y, FaceRec* __restrict__ rec, unsigned long long* __restrict__ zkey,
             int* __restrict__ unit_face, int* __restrict__ unit_block, int64_t unit_capacity, int* __restrict__ hdr) {
     const int n = blockIdx.y;
@@ -474,72 +603,42 @@ k_face_zbuf(const float* __restrict__ face_verts, const int64_t* __restrict__ fi
     const int64_t cnt = SRC == 0 ? num_faces[n] : F_per_mesh;
     const bool live = i < cnt;
     const int64_t f = first + (live ? i : 0);
-    __shared__ float sR[9], sT[3];
-    if (SRC == 1) {
-        if (threadIdx.x < 9) sR[threadIdx.x] = Rm[n * 9 + threadIdx.x];
-        if (threadIdx.x < 3) sT[threadIdx.x] = Tv[n * 3 + threadIdx.x];
-        __syncthreads();
-    }
+    const int lane = threadIdx.x & 31;
     FaceVerts v{};
-    float area = 0.0f;
-    int x0 = 1, x1 = 0, y0 = 1, y1 = 0;
-    bool valid = false;
+    TriBox box{1, 0, 1, 0, 0.0f, false};
     if (live) {
         if (SRC == 1) {
-            float c[9];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {  // same operation order as k_transform / oracle_transform_verts
-                const float* p = verts + 3 * (int64_t)__ldg(faces + 3 * i + k);
-                const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
-                const float xv = fadd(fadd(fadd(fmul(x, sR[0]), fmul(y, sR[3])), fmul(z, sR[6])), sT[0]);
-                const float yv = fadd(fadd(fadd(fmul(x, sR[1]), fmul(y, sR[4])), fmul(z, sR[7])), sT[1]);
-                const float zv = fadd(fadd(fadd(fmul(x, sR[2]), fmul(y, sR[5])), fmul(z, sR[8])), sT[2]);
-                const float rz = __frcp_rn(zv);  // two quotients over zv: corrected-reciprocal division (common.cuh)
-                const bool z_ok = exp_safe(zv);
-                c[3 * k] = fdiv_r(fmul(xv, k00), zv, rz, z_ok);
-                c[3 * k + 1] = fdiv_r(fmul(yv, k11), zv, rz, z_ok);
-                c[3 * k + 2] = zv;
-            }
-            v = FaceVerts{c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8]};
+            const float4* vn = verts_ndc + (int64_t)n * V;
+            const float4 p0 = __ldg(vn + __ldg(faces + 3 * i)), p1 = __ldg(vn + __ldg(faces + 3 * i + 1));
+            const float4 p2 = __ldg(vn + __ldg(faces + 3 * i + 2));
+            v = FaceVerts{p0.x, p0.y, p0.z, p1.x, p1.y, p1.z, p2.x, p2.y, p2.z};
         } else {
             const float* p = face_verts + 9 * f;
             v = FaceVerts{p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8]};
         }
-        if (fminf(v.z0, fminf(v.z1, v.z2)) < z_clip) hdr[4] = 1;  // would need near-plane clipping (A.2 clip_faces)
-        area = edge_fn(v.x2, v.y2, v.x0, v.y0, v.x1, v.y1);
-        valid = fabsf(area) > kEps;
-        if (cull_backfaces && area < 0.0f) valid = false;
-        if (fmaxf(v.z0, fmaxf(v.z1, v.z2)) < 0.0f) valid = false;
-        const float xmin = fminf(v.x0, fminf(v.x1, v.x2)), xmax = fmaxf(v.x0, fmaxf(v.x1, v.x2));
-        const float ymin = fminf(v.y0, fminf(v.y1, v.y2)), ymax = fmaxf(v.y0, fmaxf(v.y1, v.y2));
-        if (!(isfinite(xmin) && isfinite(xmax) && isfinite(ymin) && isfinite(ymax))) valid = false;
-        if (valid) {
-            table_pixel_range(ndc_x, W, est.x, est.y, xmin, xmax, x0, x1);  // image x runs opposite to NDC x (A.3)
-            table_pixel_range(ndc_y, H, est.z, est.w, ymin, ymax, y0, y1);
-            if (x0 > x1 || y0 > y1) {
-                valid = false;
-                x0 = y0 = 1;
-                x1 = y1 = 0;
-            }
-        }
-        if (valid) {  // only a face that covers a pixel centre can win one: nothing else ever reads the record
+        const int nb = count_behind(v, z_clip);  // z_clip = -inf: clipping off (operator boundary: done upstream)
+        if (nb == 0)
+            box = tri_box(v, H, W, est, cull_backfaces, ndc_x, ndc_y);
+        else if (nb < 3)
+            setup_clipped_face(v, z_clip, n, (int)f, H, W, est, cull_backfaces, ndc_x, ndc_y, rec, unit_face, unit_block,
+                               unit_capacity, hdr);
+        if (box.valid) {  // only a face that covers a pixel centre can win one: nothing else ever reads the record
             FaceRec r;
             r.a = make_float4(v.x0, v.y0, v.z0, v.x1);
             r.b = make_float4(v.y1, v.z1, v.x2, v.y2);
-            r.c = make_float4(v.z2, area, __int_as_float(x0 | (x1 << 16)), __int_as_float(y0 | (y1 << 16)));
+            r.c = make_float4(v.z2, box.area, __int_as_float(box.x0 | (box.x1 << 16)),
+                              __int_as_float(box.y0 | (box.y1 << 16)));
             rec[f] = r;
         }
     }
-    const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
-    const bool small = valid && bw * bh <= 16;
-    unsigned long long* zview = zkey + (int64_t)n * H * W;
+    const int bw = box.x1 - box.x0 + 1, bh = box.y1 - box.y0 + 1;
+    const bool small = box.valid && bw * bh <= kSmallBox;
     {
         // queue the face as ceil(bw/64) x ceil(bh/64) work units of at most 64 x 64 pixels for k_sweep_units;
         // one atomicAdd per WARP (prefix sum over the lanes' unit counts), not one per face
-        const int ux = (valid && !small) ? (bw + kUnitSide - 1) / kUnitSide : 0;
-        const int nu = (valid && !small) ? ux * ((bh + kUnitSide - 1) / kUnitSide) : 0;
+        const int ux = (box.valid && !small) ? (bw + kUnitSide - 1) / kUnitSide : 0;
+        const int nu = (box.valid && !small) ? ux * ((bh + kUnitSide - 1) / kUnitSide) : 0;
         if (__any_sync(0xffffffffu, nu > 0)) {  // (on meshes denser than the pixel grid most warps queue nothing)
-            const int lane = threadIdx.x & 31;
             int incl = nu;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -561,16 +660,47 @@ k_face_zbuf(const float* __restrict__ face_verts, const int64_t* __restrict__ fi
             }
         }
     }
-    if (small) {
-        const bool zpos = v.z0 > 0.0f && v.z1 > 0.0f && v.z2 > 0.0f;
-        const float denom = fadd(area, kEps), rden = __frcp_rn(denom);
-        const bool den_ok = exp_safe(denom);
-        const float e0y = fsub(v.y2, v.y1), e0x = fsub(v.x2, v.x1), e1y = fsub(v.y0, v.y2), e1x = fsub(v.x0, v.x2);
-        const float e2y = fsub(v.y1, v.y0), e2x = fsub(v.x1, v.x0);
-        for (int qy = y0; qy <= y1; ++qy)
-            for (int qx = x0; qx <= x1; ++qx)
-                zbuf_test_pixel(__ldg(ndc_x + qx), __ldg(ndc_y + qy), v, denom, rden, den_ok, zpos, persp != 0, e0x, e0y,
-                                e1x, e1y, e2x, e2y, (unsigned)f, zview + (int64_t)qy * W + qx);
+    // small faces: compact the warp's (face, pixel) candidates and test 32 of them per pass
+    const int ncand = small ? bw * bh : 0;
+    int incl = ncand;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int excl = incl - ncand;
+    const int origin = box.x0 | (box.y0 << 16);
+    unsigned long long* zview = zkey + (int64_t)n * H * W;
+    for (int base = 0; base < total; base += 32) {
+        const int idx = base + lane;
+        int s = 0;  // the lane that owns candidate idx: the first one whose inclusive prefix exceeds idx
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const int probe = __shfl_sync(0xffffffffu, incl, s + step - 1);
+            if (probe <= idx) s += step;
+        }
+        FaceVerts u;
+        u.x0 = __shfl_sync(0xffffffffu, v.x0, s); u.y0 = __shfl_sync(0xffffffffu, v.y0, s);
+        u.z0 = __shfl_sync(0xffffffffu, v.z0, s); u.x1 = __shfl_sync(0xffffffffu, v.x1, s);
+        u.y1 = __shfl_sync(0xffffffffu, v.y1, s); u.z1 = __shfl_sync(0xffffffffu, v.z1, s);
+        u.x2 = __shfl_sync(0xffffffffu, v.x2, s); u.y2 = __shfl_sync(0xffffffffu, v.y2, s);
+        u.z2 = __shfl_sync(0xffffffffu, v.z2, s);
+        const float area_s = __shfl_sync(0xffffffffu, box.area, s);
+        const int org = __shfl_sync(0xffffffffu, origin, s), bw_s = __shfl_sync(0xffffffffu, bw, s);
+        const int k = idx - __shfl_sync(0xffffffffu, excl, s);
+        const unsigned fid = (unsigned)__shfl_sync(0xffffffffu, (int)f, s);
+        if (idx < total) {
+            // k < 16 and bw_s <= 16: (k + 0.5) / bw_s stays >= 1/32 away from an integer, the fast quotient is safe
+            const int ry = __float2int_rz(__fdividef((float)k + 0.5f, (float)bw_s));
+            const int qx = (org & 0xffff) + (k - ry * bw_s), qy = (org >> 16) + ry;
+            const bool zpos = u.z0 > 0.0f && u.z1 > 0.0f && u.z2 > 0.0f;
+            const float denom = fadd(area_s, kEps);
+            const float e0y = fsub(u.y2, u.y1), e0x = fsub(u.x2, u.x1), e1y = fsub(u.y0, u.y2), e1x = fsub(u.x0, u.x2);
+            const float e2y = fsub(u.y1, u.y0), e2x = fsub(u.x1, u.x0);
+            zbuf_test_pixel(__ldg(ndc_x + qx), __ldg(ndc_y + qy), u, denom, __frcp_rn(denom), exp_safe(denom), zpos,
+                            persp != 0, e0x, e0y, e1x, e1y, e2x, e2y, fid, zview + (int64_t)qy * W + qx);
+        }
     }
 }
 
@@ -579,21 +709,31 @@ k_face_zbuf(const float* __restrict__ face_verts, const int64_t* __restrict__ fi
 // can stall the pass.
 __global__ void __launch_bounds__(256)
 k_sweep_units(const FaceRec* __restrict__ rec, const int* __restrict__ unit_face, const int* __restrict__ unit_block,
-              const int* __restrict__ hdr, int64_t unit_capacity, int H, int W, int persp,
-              const float* __restrict__ ndc_x, const float* __restrict__ ndc_y, unsigned long long* __restrict__ zkey) {
+              const int* __restrict__ hdr, int64_t unit_capacity, int H, int W, float4 est, int cull_backfaces,
+              float z_clip, int persp, const float* __restrict__ ndc_x, const float* __restrict__ ndc_y,
+              unsigned long long* __restrict__ zkey) {
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const int64_t total = min((int64_t)hdr[0], unit_capacity);
     for (int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < total; p += nwarps) {
         const int f = __ldg(unit_face + p), blk = __ldg(unit_block + p);
-        const int n = blk >> 20, uy = (blk >> 10) & 1023, ux = blk & 1023;
+        const int n = (blk >> 20) & 0x7ff, uy = (blk >> 10) & 1023, ux = blk & 1023;
         const float4 ra = __ldg(&rec[f].a), rb = __ldg(&rec[f].b), rc = __ldg(&rec[f].c);
-        const FaceVerts v{ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w, rc.x};
+        FaceVerts v{ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w, rc.x};
         const int xr = __float_as_int(rc.z), yr = __float_as_int(rc.w);
-        const int x0 = (xr & 0xffff) + ux * kUnitSide, x1 = min(xr >> 16, x0 + kUnitSide - 1);
-        const int y0 = (yr & 0xffff) + uy * kUnitSide, y1 = min(yr >> 16, y0 + kUnitSide - 1);
+        int fx0 = xr & 0xffff, fx1 = (xr >> 16) & 0x7fff, fy0 = yr & 0xffff, fy1 = yr >> 16;
+        float area = rc.y;
+        if (xr < 0) {  // near-plane-clipped face: this unit belongs to sub-triangle (blk >> 31)
+            const ClipUnit cu = clipped_unit(v, z_clip, (int)((unsigned)blk >> 31), H, W, est, cull_backfaces, ndc_x, ndc_y);
+            if (!cu.box.valid) continue;
+            v = cu.v;
+            area = cu.box.area;
+            fx0 = cu.box.x0; fx1 = cu.box.x1; fy0 = cu.box.y0; fy1 = cu.box.y1;
+        }
+        const int x0 = fx0 + ux * kUnitSide, x1 = min(fx1, x0 + kUnitSide - 1);
+        const int y0 = fy0 + uy * kUnitSide, y1 = min(fy1, y0 + kUnitSide - 1);
         const bool zpos = v.z0 > 0.0f && v.z1 > 0.0f && v.z2 > 0.0f;
-        const float denom = fadd(rc.y, kEps), rden = __frcp_rn(denom);
+        const float denom = fadd(area, kEps), rden = __frcp_rn(denom);
         const bool den_ok = exp_safe(denom);
         const float e0y = fsub(v.y2, v.y1), e0x = fsub(v.x2, v.x1), e1y = fsub(v.y0, v.y2), e1x = fsub(v.x0, v.x2);
         const float e2y = fsub(v.y1, v.y0), e2x = fsub(v.x1, v.x0);
@@ -618,6 +758,7 @@ struct HardSrc {  // where the faces of the hard path come from
     const float* R = nullptr;
     const float* T = nullptr;
     float k00 = 0, k11 = 0;
+    int64_t V = 0;
     int64_t F_per_mesh = 0;                 // faces per view (SRC 1) or the largest mesh (SRC 0)
     int cull_backfaces = 0;
     float z_clip = -INFINITY;
@@ -627,29 +768,29 @@ template <int MODE>
 static int run_hard(const RasterWs& ws, const HardSrc& h, int N, int H, int W, int persp, const FragOut& fo,
                     const ShadeParams& sp, cudaStream_t s) {
     ST3D_REQUIRE(N < 2048, "hard rasterization packs the view index into 11 bits: at most 2047 views per call (got %d)", N);
-    k_prepare<<<148 * 4, 256, 0, s>>>(ws.zkey, (int64_t)N * H * W, ws.hdr, H, W, ws.ndc_x, ws.ndc_y);
+    k_prepare<<<148 * 4, 256, 0, s>>>(ws.zkey, (int64_t)N * H * W, ws.hdr, H, W, ws.ndc_x, ws.ndc_y, h.verts, h.R, h.T,
+                                      h.k00, h.k11, N, h.V, ws.verts_ndc);
     ST3D_LAUNCH_OK("k_prepare");
     if (h.F_per_mesh > 0) {
         const dim3 grid(cdiv(h.F_per_mesh, 128), N);
         // seeds of the pixel-range search: NDC-ordered pixel index j(v) = a v + b (A.3 PixToNonSquareNdc inverted)
         const double rx = W > H ? 2.0 * W / H : 2.0, ry = H > W ? 2.0 * H / W : 2.0;
-        const float4 est = make_float4((float)(W / rx), (float)(0.5 * rx * (W - 1) / rx), (float)(H / ry),
-                                       (float)(0.5 * ry * (H - 1) / ry));
+        const float4 est = make_float4((float)(W / rx), (float)(0.5 * (W - 1)), (float)(H / ry), (float)(0.5 * (H - 1)));
         if (h.verts)
-            k_face_zbuf<1><<<grid, 128, 0, s>>>(nullptr, nullptr, nullptr, h.verts, h.faces, h.R, h.T, h.k00, h.k11,
+            k_face_zbuf<1><<<grid, 128, 0, s>>>(nullptr, nullptr, nullptr, ws.verts_ndc, h.faces, h.V, h.F_per_mesh, H, W,
+                                                est, h.cull_backfaces, h.z_clip, persp, ws.ndc_x, ws.ndc_y, ws.rec,
+                                                ws.zkey, ws.list, ws.list_tile, ws.capacity, ws.hdr);
+        else
+            k_face_zbuf<0><<<grid, 128, 0, s>>>(h.face_verts, h.first_idx, h.num_faces, nullptr, nullptr, 0,
                                                 h.F_per_mesh, H, W, est, h.cull_backfaces, h.z_clip, persp, ws.ndc_x,
                                                 ws.ndc_y, ws.rec, ws.zkey, ws.list, ws.list_tile, ws.capacity, ws.hdr);
-        else
-            k_face_zbuf<0><<<grid, 128, 0, s>>>(h.face_verts, h.first_idx, h.num_faces, nullptr, nullptr, nullptr, nullptr,
-                                                0.0f, 0.0f, h.F_per_mesh, H, W, est, h.cull_backfaces, h.z_clip, persp,
-                                                ws.ndc_x, ws.ndc_y, ws.rec, ws.zkey, ws.list, ws.list_tile, ws.capacity,
-                                                ws.hdr);
         ST3D_LAUNCH_OK("k_face_zbuf");
-        k_sweep_units<<<148 * 8, 256, 0, s>>>(ws.rec, ws.list, ws.list_tile, ws.hdr, ws.capacity, H, W, persp, ws.ndc_x,
-                                              ws.ndc_y, ws.zkey);
+        k_sweep_units<<<148 * 8, 256, 0, s>>>(ws.rec, ws.list, ws.list_tile, ws.hdr, ws.capacity, H, W, est,
+                                              h.cull_backfaces, h.z_clip, persp, ws.ndc_x, ws.ndc_y, ws.zkey);
         ST3D_LAUNCH_OK("k_sweep_units");
     }
-    k_resolve<MODE><<<dim3(cdiv(W, 256), H, N), 256, 0, s>>>(ws.rec, ws.zkey, H, W, persp, ws.ndc_x, ws.ndc_y, fo, sp);
+    k_resolve<MODE><<<dim3(cdiv(W, 256), H, N), 256, 0, s>>>(ws.rec, ws.zkey, H, W, persp, h.z_clip, ws.ndc_x, ws.ndc_y,
+                                                             fo, sp);
     ST3D_LAUNCH_OK("k_resolve");
     return ST3D_OK;
 }
@@ -797,6 +938,7 @@ extern "C" int st3d_render_forward(const st3d_render_args* a, st3d_stream_t stre
         h.T = a->T;
         h.k00 = a->k00;
         h.k11 = a->k11;
+        h.V = a->V;
         h.F_per_mesh = a->F;
         h.cull_backfaces = a->cull_backfaces;
         h.z_clip = z_clip;

@@ -7,16 +7,69 @@
 // One pass per pixel; barycentrics are recomputed from the per-face records the forward pass left
 // in the workspace (same one-rounding arithmetic, so the texel footprint is identical); vertex
 // gradients are summed across the lanes of a warp that hit the same face before any atomic.
+#include "clip.cuh"
 #include "common.cuh"
 #include "face_grad.cuh"
 #include "shade.cuh"
 
 namespace st3d {
 
+// Winning pixel of a near-plane-clipped face (clip.cuh): which sub-triangle produced the z-buffer key, its
+// barycentrics converted to the unclipped face, depth and signed edge distance.
+struct ClipFrag {
+    float b0, b1, b2, pz, dist;  // b: barycentrics w.r.t. the UNCLIPPED face
+    int t;                       // sub-triangle index, -1 if none matched (cannot happen for a recorded winner)
+};
+
+static __device__ __noinline__ ClipFrag clipped_fragment(FaceVerts v, float z_clip, float px, float py, unsigned depth_bits) {
+    ClipFrag out{0.0f, 0.0f, 0.0f, 0.0f, -1.0f, -1};
+    const int nt = count_behind(v, z_clip) == 2 ? 1 : 2;
+    for (int t = 0; t < nt; ++t) {
+        ClipTri ct;
+        clip_triangle(v, z_clip, t, ct);
+        float b0, b1, b2, pz, dist;
+        face_recompute(px, py, ct.v, true, false, b0, b1, b2, pz, dist);
+        if (!(dist < 0.0f)) continue;  // not strictly inside this sub-triangle
+        const bool exact = __float_as_uint(fadd(pz, 0.0f)) == depth_bits;
+        if (out.t >= 0 && !exact) continue;
+        clip_convert_bary(ct, b0, b1, b2, out.b0, out.b1, out.b2);
+        out.pz = pz;
+        out.dist = dist;
+        out.t = t;
+        if (exact) break;
+    }
+    return out;
+}
+
+// Geometry backward through a clipped face: gradients of the unclipped barycentrics (gb), depth and distance
+// -> sub-triangle (face_backward) -> the nine unclipped NDC coordinates (clip_triangle_backward).
+static __device__ __noinline__ FaceGrad clipped_face_backward(FaceVerts v, float z_clip, int t, float px, float py, float gb0,
+                                                       float gb1, float gb2, float g_pz, float g_dist) {
+    ClipTri ct;
+    clip_triangle(v, z_clip, t, ct);
+    float b0, b1, b2, pz, dist;
+    face_recompute(px, py, ct.v, true, false, b0, b1, b2, pz, dist);
+    const float gb[3] = {gb0, gb1, gb2}, bc[3] = {b0, b1, b2};
+    float gc[3], gcv[9];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        gc[k] = gb[0] * ct.cv[3 * k] + gb[1] * ct.cv[3 * k + 1] + gb[2] * ct.cv[3 * k + 2];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) gcv[3 * k + j] = gb[j] * bc[k];
+    }
+    const FaceGrad ft = face_backward(px, py, ct.v, true, false, gc[0], gc[1], gc[2], g_pz, g_dist);
+    FaceGrad out;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) out.g[i] = 0.0f;
+    clip_triangle_backward(v, z_clip, t, ft.g, gcv, out.g);
+    return out;
+}
+
 template <int TEX_MODE, bool NEED_GEOM>
-__global__ void __launch_bounds__(256)
-k_render_bwd(const FaceRec* __restrict__ rec, const float* __restrict__ grad_image, int N, int H, int W, int TX,
-             int TY, int clip, ShadeParams sp, float* __restrict__ grad_texture, float* __restrict__ grad_ndc,
+__global__ void __launch_bounds__(256, NEED_GEOM ? (TEX_MODE == ST3D_TEX_UV ? 3 : 4) : 5)
+k_render_bwd(const FaceRec* __restrict__ rec, const unsigned long long* __restrict__ zkey,
+             const float* __restrict__ grad_image, int N, int H, int W, int TX, int TY, int clip, float z_clip,
+             ShadeParams sp, float* __restrict__ grad_texture, float* __restrict__ grad_ndc,
              float* __restrict__ grad_verts_rgb) {
     const int t = blockIdx.x;
     const int n = t / (TX * TY);
@@ -37,12 +90,19 @@ k_render_bwd(const FaceRec* __restrict__ rec, const float* __restrict__ grad_ima
 
     if (hit) {
         const float px = pix_to_ndc(W - 1 - xi, W, H), py = pix_to_ndc(H - 1 - yi, H, W);
-        const FaceVerts v = unpack(rec[f]);
+        const FaceRec fr = rec[f];
+        const FaceVerts v = unpack(fr);
+        const bool near_clipped = __float_as_int(fr.c.z) < 0;  // face crossing the near plane (hard path only)
+        int sub = 0;
         float b0, b1, b2, pz, dist;
         // planar layout + hard rasterization: no alpha gradient comes in and d(rgb)/d(dist) is ~1e-10 relative,
         // so the edge distance (three point-segment distances) is neither recomputed nor differentiated
         const bool skip_dist = sp.out_layout == ST3D_LAYOUT_PLANAR && clip == 0;
-        if (skip_dist) {
+        if (near_clipped) {
+            const ClipFrag cf = clipped_fragment(v, z_clip, px, py, (unsigned)(zkey[pix] >> 32));
+            b0 = cf.b0; b1 = cf.b1; b2 = cf.b2; pz = cf.pz; dist = skip_dist ? -1.0f : cf.dist;
+            sub = cf.t;
+        } else if (skip_dist) {
             face_bary(px, py, v, edge_fn(v.x2, v.y2, v.x0, v.y0, v.x1, v.y1), true, b0, b1, b2, pz);
             dist = -1.0f;
         } else {
@@ -148,7 +208,9 @@ k_render_bwd(const FaceRec* __restrict__ rec, const float* __restrict__ grad_ima
             }
         }
         if (NEED_GEOM) {
-            const FaceGrad fg = face_backward(px, py, v, true, clip != 0, gb0, gb1, gb2, g_pz, g_dist);
+            const FaceGrad fg = (near_clipped && sub >= 0)
+                                    ? clipped_face_backward(v, z_clip, sub, px, py, gb0, gb1, gb2, g_pz, g_dist)
+                                    : face_backward(px, py, v, true, clip != 0, gb0, gb1, gb2, g_pz, g_dist);
 #pragma unroll
             for (int i = 0; i < 9; ++i) gv[i] = fg.g[i];
         }
@@ -192,13 +254,14 @@ extern "C" int st3d_render_backward(const st3d_render_args* a, const float* grad
                                          (int64_t)a->N * a->V);
     const ShadeParams sp = make_shade_params(*a);
     const int clip = a->blur_radius > 0.0f ? 1 : 0;
+    const float z_clip = a->z_clip > 0.0f ? a->z_clip : -INFINITY;
     const bool geom = grad_verts != nullptr;
     if (geom) ST3D_CUDA_OK(cudaMemsetAsync(ws.grad_ndc, 0, (size_t)a->N * a->V * 3 * sizeof(float), s));
     float* g_tex = a->tex_mode == ST3D_TEX_UV ? grad_texture : nullptr;
     float* g_rgb = a->tex_mode == ST3D_TEX_VERTEX ? grad_verts_rgb : nullptr;
 #define ST3D_BWD(MODE, GEOM)                                                                                   \
-    k_render_bwd<MODE, GEOM><<<ws.NT, 256, 0, s>>>(ws.rec, grad_image, a->N, a->H, a->W, ws.TX, ws.TY, clip, sp, \
-                                                   g_tex, ws.grad_ndc, g_rgb)
+    k_render_bwd<MODE, GEOM><<<ws.NT, 256, 0, s>>>(ws.rec, ws.zkey, grad_image, a->N, a->H, a->W, ws.TX, ws.TY, clip, \
+                                                   z_clip, sp, g_tex, ws.grad_ndc, g_rgb)
     if (a->tex_mode == ST3D_TEX_UV) {
         if (geom) ST3D_BWD(ST3D_TEX_UV, true); else ST3D_BWD(ST3D_TEX_UV, false);
     } else {

@@ -120,9 +120,10 @@ def poll_overflow(block: bool = False) -> None:
             _capacity_hint[key] = max(_capacity_hint.get(key, 0), needed)
             if clip:
                 _pending.clear()
-                raise NotImplementedError("a face has a vertex in front of the near clipping plane (z < z_clip): "
-                                          "near-plane face clipping (PyTorch3D clip_faces) is not implemented; the "
-                                          "images of that render call must not be used")
+                raise NotImplementedError("a face has a vertex in front of the near clipping plane (z < z_clip) and "
+                                          "blur_radius > 0: the fused renderer clips faces only when blur_radius == 0; "
+                                          "the images of that render call must not be used (MeshRasterizer + shader, "
+                                          "the Fragments path, clips for any blur_radius)")
             if overflow:
                 _pending.clear()
                 raise St3dError(f"tile bins overflowed: {needed} (face,tile) pairs needed; results of that call are "

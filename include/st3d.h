@@ -66,9 +66,11 @@ size_t st3d_raster_workspace_size(int N, int64_t F_total, int H, int W, int64_t 
 /* Workspace header, readable by the host AFTER the stream has been synchronised:
  * [0] = work-list entries needed by the last call ((face,tile) pairs of the binned path, face units of the
  * hard path), [1] = 1 if that list overflowed (results invalid, re-run with a larger list_capacity),
- * [2] = capacity in entries, [4] = 1 if some face has a vertex nearer
- * than st3d_render_args.z_clip (PyTorch3D would clip such faces against the near plane, clip.py; that
- * path is not implemented, so the caller must treat the render as unsupported rather than trust it). */
+ * [2] = capacity in entries, [5] = 1 if the call clipped faces against the near plane (informational),
+ * [4] = 1 if some face has a vertex nearer than st3d_render_args.z_clip on a path that does not clip: the fused
+ * renderer clips such faces inside its kernels (PyTorch3D clip_faces semantics, csrc/clip.cuh) when blur_radius
+ * is 0 -- the reference's configuration; with blur_radius > 0 it only reports them here and the caller must treat
+ * the render as unsupported (use the operator-boundary path, which clips around st3d_rasterize_meshes_forward). */
 #define ST3D_WS_HEADER_INTS 16
 
 /* _C.rasterize_meshes: face_verts (F_total,3,3) in NDC (z = view depth); mesh n owns faces
@@ -145,7 +147,8 @@ typedef struct st3d_render_args {
     void* workspace;        /* >= st3d_render_workspace_size(...) bytes; forward fills it, backward reads it */
     size_t workspace_bytes;
     int64_t list_capacity;  /* must match the value given to st3d_render_workspace_size */
-    float z_clip;           /* near-plane clip depth (PyTorch3D: znear / 2); <= 0 disables the check */
+    float z_clip;           /* near-plane clip depth (PyTorch3D: znear / 2): faces crossing z = z_clip are clipped,
+                               faces behind it dropped; <= 0 disables clipping */
 } st3d_render_args;
 
 size_t st3d_render_workspace_size(int N, int64_t V, int64_t F, int H, int W, int64_t list_capacity);

@@ -186,16 +186,25 @@ def test_first_approach_mse_fit_matches_oracle(scene, target):
     assert ((got.double() - ref).abs().max() / ref.abs().max()).item() <= 2e-4
 
 
-def test_near_plane_violation_is_reported(scene):
-    """A camera inside the mesh needs near-plane clipping, which is not implemented: fail loudly."""
+def test_camera_inside_the_mesh_is_clipped_like_the_oracle(scene):
+    """A camera inside the mesh: faces crossing z = znear / 2 are clipped (SURVEY A.2 clip_faces), in the fused
+    renderer and in the Fragments path alike."""
     from pytorch3d.renderer import FoVPerspectiveCameras
     from st3d import ops
     sc = scene
-    inside = FoVPerspectiveCameras(R=torch.eye(3)[None], T=torch.tensor([[0.0, 0.0, 0.2]]), device=sc["dev"])
-    sc["renderer"](meshes_world=sc["mesh"], cameras=inside)
+    R, T = torch.eye(3)[None], torch.tensor([[0.0, 0.0, 0.2]])
+    inside = FoVPerspectiveCameras(R=R, T=T, device=sc["dev"])
+    rgba = sc["renderer"](meshes_world=sc["mesh"], cameras=inside)
     torch.cuda.synchronize()
-    with pytest.raises(NotImplementedError):
-        ops.poll_overflow(block=True)
+    ops.poll_overflow(block=True)
+    want, frag = ro.render_views(sc["verts"], sc["faces"], R, T, S, texture=sc["tex"][0], verts_uvs=sc["verts_uvs"],
+                                 faces_uvs=sc["faces_uvs"], nthreads=8, return_fragments=True)
+    assert (frag["pix_to_face"] >= 0).float().mean() > 0.5
+    assert (rgba.cpu() - want).abs().max().item() <= 1e-4
+    fragments = sc["renderer"].rasterizer(sc["mesh"], cameras=inside)
+    assert torch.equal(fragments.pix_to_face.cpu(), frag["pix_to_face"])
+    hit = frag["pix_to_face"] >= 0
+    assert (fragments.bary_coords.cpu()[hit] - frag["bary_exact"][hit]).abs().max().item() <= 1e-4
 
 
 def test_runner_resolves_modules_to_compat(tmp_path):

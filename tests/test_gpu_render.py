@@ -342,3 +342,104 @@ def test_random_triangle_soups_bit_exact(seed):
         m = want[0] >= 0
         assert torch.allclose(got[1].cpu()[m], want[1][m], rtol=1e-5, atol=1e-6)
         assert torch.allclose(got[2].cpu()[m], want[2][m], rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# near-plane clipping: cameras so close that the z = znear / 2 plane cuts the mesh
+# ------------------------------------------------------------------------------------------------
+def _close_cameras():
+    return ro.look_at_view_transform(1.0, [10.0, 40.0, -25.0], [20.0, 200.0, 95.0], at=((0, 0.1, 0.25),))
+
+
+@pytest.mark.parametrize("layout", ["nhwc", "planar"])
+@pytest.mark.parametrize("mode", ["uv", "vertex"])
+def test_near_plane_clipping_fused_matches_oracle(cow, layout, mode):
+    """Fused renderer with faces crossing the clip plane: pix_to_face bit-exact, image and all gradients
+    (through the clipped sub-triangles back to the unclipped vertices) against float64 autograd of the oracle."""
+    ops = _ops()
+    S, gen = 80, torch.Generator().manual_seed(5)
+    R, T = _close_cameras()
+    N = R.shape[0]
+    k00, k11 = ro.fov_scales(60.0)
+    fv, _, _, _ = _face_verts(cow, R, T)
+    behind = (fv[:, :, 2] < 0.5).sum(1)
+    assert (behind == 1).sum() > 20 and (behind == 2).sum() > 20 and (behind == 3).sum() > 20   # all cases present
+    verts64 = cow["verts"].double().requires_grad_(True)
+    tex = torch.rand(40, 56, 3, generator=gen)
+    vrgb = torch.rand(cow["verts"].shape[0], 3, generator=gen)
+    tex64, vrgb64 = tex.double().requires_grad_(True), vrgb.double().requires_grad_(True)
+    kw = dict(texture=tex64, verts_uvs=cow["verts_uvs"].double(), faces_uvs=cow["faces_uvs"]) if mode == "uv" \
+        else dict(verts_rgb=vrgb64)
+    rgba, frag = ro.render_views(verts64, cow["faces"], R, T, S, nthreads=8, return_fragments=True, **kw)
+    wgt = torch.randn(N, S, S, 4, generator=gen).double()
+    if layout == "planar":
+        wgt[..., 3] = 0.0
+    (rgba * wgt).sum().backward()
+
+    lay = ops.LAYOUT_NHWC_RGBA if layout == "nhwc" else ops.LAYOUT_PLANAR
+    spec = ops.RenderSpec(image_size=(S, S), k00=k00, k11=k11, layout=lay)
+    gkw = dict(face_uvs=cow["verts_uvs"][cow["faces_uvs"]].cuda(), texture=tex.cuda()) if mode == "uv" \
+        else dict(verts_rgb=vrgb.cuda())
+    img, mask, p2f, state = ops.render_forward(spec, cow["verts"].cuda(), cow["faces"].cuda(), R.cuda(), T.cuda(), **gkw)
+    torch.cuda.synchronize()
+    ops.poll_overflow(block=True)
+    want_p2f = frag["pix_to_face"][..., 0]
+    assert (want_p2f >= 0).float().mean() > 0.3
+    assert torch.equal(p2f.cpu().long(), want_p2f), "pix_to_face differs from the oracle on a clipped scene"
+    if layout == "planar":
+        want_img, want_mask = ro.images_and_masks(rgba.detach())
+        _close(img, want_img, what="planar image")
+        assert torch.equal(mask.cpu().double(), want_mask)
+        gimg = wgt[..., :3].permute(0, 3, 1, 2).contiguous().float().cuda()
+    else:
+        _close(img, rgba, what="rgba")
+        gimg = wgt.float().cuda()
+    g_tex, g_verts, g_rgb = ops.render_backward(state, gimg, need_texture=True, need_verts=True, need_verts_rgb=True)
+    torch.cuda.synchronize()
+    if mode == "uv":
+        _close(g_tex, tex64.grad, what="grad_texture")
+    else:
+        _close(g_rgb, vrgb64.grad, what="grad_verts_rgb")
+    _close(g_verts, verts64.grad, tol=2e-4, what="grad_verts")
+
+
+@pytest.mark.parametrize("K", [1, 2])
+def test_near_plane_clipping_fragments_match_oracle(cow, K):
+    """Operator-boundary path: torch-level clip_faces around st3d_rasterize_meshes_forward, as upstream does."""
+    import st3d.functional as Fn
+    from st3d import clip as cl
+    S = 64
+    R, T = _close_cameras()
+    fv, first, num, _ = _face_verts(cow, R, T)
+    want_cl = ro.clip_faces(fv, first, num, 0.5)
+    got_cl = cl.clip_faces(fv.cuda(), first.cuda(), num.cuda(), 0.5)
+    assert torch.equal(got_cl.face_verts.cpu(), want_cl["face_verts"]), "clipped faces differ bit-wise"
+    assert torch.equal(got_cl.faces_clipped_to_unclipped_idx.cpu(), want_cl["to_unclipped"])
+    assert torch.equal(got_cl.clipped_faces_neighbor_idx.cpu(), want_cl["neighbor"])
+    assert torch.equal(got_cl.barycentric_conversion.cpu(), want_cl["conversion"])
+
+    w_p2f, w_z, w_b, w_d = ro.rasterize_naive(want_cl["face_verts"], want_cl["first"], want_cl["num"], S, 0.0, K, True,
+                                              False, False, 8)
+    w_p2f, w_b = ro.convert_clipped_to_unclipped(w_p2f, w_b, want_cl)
+    fvg = fv.cuda().requires_grad_(True)
+    p2f, zbuf, bary, dists = Fn.rasterize_meshes(fvg, first.cuda(), num.cuda(), S, 0.0, K, True, False, False,
+                                                 z_clip_value=0.5)
+    torch.cuda.synchronize()
+    assert torch.equal(p2f.cpu(), w_p2f)
+    hit = w_p2f >= 0
+    _close(zbuf.cpu()[hit], w_z[hit], what="zbuf")
+    _close(bary.cpu()[hit], w_b[hit], what="bary")
+    _close(dists.cpu()[hit], w_d[hit], what="dists")
+    # gradient through rasterize + conversion + clip, against float64 autograd of the oracle restatement
+    gen = torch.Generator().manual_seed(2)
+    gz, gb = torch.randn(zbuf.shape, generator=gen), torch.randn(bary.shape, generator=gen)
+    ((zbuf * gz.cuda()).sum() + (bary * gb.cuda()).sum()).backward()
+    fv64 = fv.double().requires_grad_(True)
+    c64 = ro.clip_faces(fv64, first, num, 0.5)
+    z64, b64, _ = ro.fragments_from_faces(c64["face_verts"], ro.rasterize_naive(
+        want_cl["face_verts"], want_cl["first"], want_cl["num"], S, 0.0, K, True, False, False, 8)[0])
+    _, b64 = ro.convert_clipped_to_unclipped(ro.rasterize_naive(
+        want_cl["face_verts"], want_cl["first"], want_cl["num"], S, 0.0, K, True, False, False, 8)[0], b64, c64)
+    hit64 = hit.double()
+    ((z64 * gz.double() * hit64).sum() + (b64 * gb.double() * hit64[..., None]).sum()).backward()
+    _close(fvg.grad, fv64.grad, tol=2e-4, what="grad_face_verts through clipping")

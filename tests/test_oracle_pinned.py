@@ -152,3 +152,106 @@ def test_regularisers_simple_mesh():
     assert lo.mesh_laplacian_smoothing(verts, faces).item() > 0
     n = lo.mesh_normal_consistency(verts, faces)
     assert 0.0 < n.item() < 2.0
+
+
+# ------------------------------------------------------------------------------------------------
+# near-plane clipping (SURVEY A.2 clip_faces): hand-checkable geometry + a consistency property on the cow
+# ------------------------------------------------------------------------------------------------
+def _ndc(view):
+    view = torch.as_tensor(view, dtype=torch.float64)
+    return torch.cat([view[..., :2] / view[..., 2:3], view[..., 2:3]], dim=-1)
+
+
+def test_clip_faces_cases_by_hand():
+    zc = 0.5
+    tris_view = torch.tensor([
+        [[0.0, 0.0, 2.0], [1.0, 0.0, 2.0], [0.0, 1.0, 3.0]],      # in front: kept
+        [[0.0, 0.0, 0.1], [1.0, 0.0, 0.2], [0.0, 1.0, 0.3]],      # behind: removed
+        [[0.0, 0.0, 0.25], [2.0, 0.0, 1.0], [0.0, 2.0, 1.5]],     # vertex 0 behind: quad -> two triangles
+        [[0.0, 0.0, 0.25], [2.0, 0.0, 0.3], [0.0, 2.0, 1.5]],     # vertices 0, 1 behind: one smaller triangle
+    ], dtype=torch.float64)
+    fv = _ndc(tris_view)
+    out = ro.clip_faces(fv, torch.tensor([0]), torch.tensor([4]), zc)
+    assert out["to_unclipped"].tolist() == [0, 2, 2, 3]
+    assert out["neighbor"].tolist() == [-1, 2, 1, -1]
+    assert out["num"].tolist() == [4] and out["was_clipped"].tolist() == [False, True, True, True]
+    assert torch.equal(out["face_verts"][0], fv[0])
+    # every vertex of a clipped triangle = its conversion column applied to the unclipped VIEW-space vertices
+    for k, f in enumerate(out["to_unclipped"].tolist()):
+        cols = out["conversion"][k]                                   # (3 unclipped, 3 clipped vertices)
+        assert torch.allclose(cols.sum(0), torch.ones(3, dtype=torch.float64), atol=1e-12)
+        assert (cols >= -1e-12).all()
+        recon = _ndc(cols.t() @ tris_view[f])
+        assert torch.allclose(recon, out["face_verts"][k], atol=1e-12)
+        assert (out["face_verts"][k][:, 2] >= zc - 1e-12).all()
+    # the quad case: p4 = crossing of v0-v2 (previous vertex), p5 = crossing of v0-v1 (next vertex)
+    t1, t2 = out["face_verts"][1], out["face_verts"][2]
+    assert torch.allclose(t1[0, 2], torch.tensor(zc, dtype=torch.float64)) and torch.allclose(t1[2, 2], t1[0, 2])
+    assert torch.equal(t1[1], fv[2][2]) and torch.equal(t2[1], fv[2][2]) and torch.equal(t2[2], fv[2][1])
+    assert torch.equal(t2[0], t1[2])                                   # shared crossing p5
+    # areas: the two pieces of the quad and the cut-off corner add up to the original triangle (view-space x, y at
+    # constant-z slices differ, so compare via conversion-matrix determinants: |det| = area ratio in barycentric space)
+    d1, d2 = out["conversion"][1].det().abs(), out["conversion"][2].det().abs()
+    w2, w3 = (0.25 - zc) / (0.25 - 1.5), (0.25 - zc) / (0.25 - 1.0)
+    assert torch.allclose(d1 + d2, torch.tensor(1.0 - w2 * w3, dtype=torch.float64), atol=1e-12)
+    assert torch.allclose(out["conversion"][3].det().abs(),
+                          torch.tensor(((1.5 - zc) / (1.5 - 0.25)) * ((1.5 - zc) / (1.5 - 0.3)), dtype=torch.float64),
+                          atol=1e-12)
+
+
+def test_clipped_render_barycentrics_reproject_to_the_pixel(cow):
+    """On a scene cut by the clip plane, the barycentrics reported w.r.t. the UNCLIPPED faces must interpolate the
+    view-space vertices to a point that projects onto the pixel centre, at the reported depth."""
+    R, T = ro.look_at_view_transform(1.0, [10.0, 40.0], [20.0, 200.0], at=((0, 0.1, 0.25),))
+    S = 48
+    k00, k11 = ro.fov_scales(60.0)
+    rgba, fr = ro.render_views(cow["verts"], cow["faces"], R, T, S, verts_rgb=torch.rand(cow["verts"].shape[0], 3),
+                               nthreads=8, return_fragments=True)
+    ndc = ro.transform_verts_exact(cow["verts"], R, T, k00, k11).double()
+    Fn = cow["faces"].shape[0]
+    fv = ndc[:, cow["faces"]].reshape(-1, 3, 3)
+    p2f = fr["pix_to_face"][..., 0]
+    hit = p2f >= 0
+    behind = (fv[:, :, 2] < 0.5).sum(1)
+    assert (behind[p2f[hit]] > 0).sum() > 50, "the scene must show clipped faces"
+    assert (behind[p2f[hit]] == 3).sum() == 0, "a face entirely behind the plane can never be visible"
+    tri = fv[p2f[hit]]                                                   # (P,3,3) ndc x, y + view z
+    view = torch.cat([tri[..., :2] * tri[..., 2:3], tri[..., 2:3]], dim=-1)
+    b = fr["bary_exact"][..., 0, :][hit].double()
+    pt = (b[:, :, None] * view).sum(1)
+    xs, ys = ro.pixel_ndc_grid(S, S, torch.float64)
+    px = xs.view(1, 1, S).expand(R.shape[0], S, S)[hit]
+    py = ys.view(1, S, 1).expand(R.shape[0], S, S)[hit]
+    assert (pt[:, 0] / pt[:, 2] - px).abs().max() < 1e-4
+    assert (pt[:, 1] / pt[:, 2] - py).abs().max() < 1e-4
+    assert (pt[:, 2] - fr["zbuf_exact"][..., 0][hit].double()).abs().max() < 1e-4
+    assert (pt[:, 2] >= 0.5 - 1e-5).all()                                # nothing nearer than the plane is drawn
+
+
+def test_product_clip_faces_equals_oracle_on_cpu_tensors(cow):
+    """st3d.clip (batched torch ops, the operator-boundary path) against the per-face oracle loop: bit-identical
+    outputs in fp32, matching float64 gradients."""
+    from st3d import clip as cl
+    R, T = ro.look_at_view_transform(1.0, [10.0, 40.0], [20.0, 200.0], at=((0, 0.1, 0.25),))
+    k00, k11 = ro.fov_scales(60.0)
+    ndc = ro.transform_verts_exact(cow["verts"], R, T, k00, k11)
+    Fn = cow["faces"].shape[0]
+    fv = ndc[:, cow["faces"]].reshape(-1, 3, 3)
+    first, num = torch.arange(2) * Fn, torch.full((2,), Fn)
+    a, b = ro.clip_faces(fv, first, num, 0.5), cl.clip_faces(fv, first, num, 0.5)
+    assert torch.equal(a["face_verts"], b.face_verts) and torch.equal(a["conversion"], b.barycentric_conversion)
+    assert torch.equal(a["to_unclipped"], b.faces_clipped_to_unclipped_idx)
+    assert torch.equal(a["neighbor"], b.clipped_faces_neighbor_idx)
+    assert torch.equal(a["first"], b.mesh_to_face_first_idx) and torch.equal(a["num"], b.num_faces_per_mesh)
+    x = fv.double().requires_grad_(True)
+    oa = ro.clip_faces(x, first, num, 0.5)
+    ga, = torch.autograd.grad((oa["face_verts"] ** 2).sum() + (oa["conversion"] ** 3).sum(), x)
+    y = fv.double().requires_grad_(True)
+    ob = cl.clip_faces(y, first, num, 0.5)
+    gb, = torch.autograd.grad((ob.face_verts ** 2).sum() + (ob.barycentric_conversion ** 3).sum(), y)
+    assert torch.allclose(ga, gb, rtol=1e-12, atol=1e-12)
+    # nothing behind the plane: the inputs come back untouched (upstream's early return, SURVEY section 8 row a5)
+    far = fv.clone()
+    far[:, :, 2] += 5.0
+    same = cl.clip_faces(far, first, num, 0.5)
+    assert same.face_verts is far and same.faces_clipped_to_unclipped_idx is None
