@@ -91,6 +91,61 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// ---- CTA-pair (cta_group::2) variants: two CTAs of a cluster on one TPC share every MMA ----------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// the box lands in THIS CTA's shared memory; the bytes are counted on the mbarrier at `bar_cluster` (the leader's)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int x, int y,
+                                                 int z) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(x), "r"(y), "r"(z)
+        : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t slot_smem) {  // one warp of EACH CTA of the pair, same warp id
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "n"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+// M = 256 across the pair: each CTA supplies its 128 rows of A and half of the N rows of B from the same
+// shared-memory offsets, and receives its 128 rows of D in its own TMEM.  Issued by the leader CTA only.
+__device__ __forceinline__ void mma_tf32_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_pair(uint32_t bar, uint16_t mask) {  // arrives in every CTA of `mask`
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "n"(COLS)
@@ -522,6 +577,178 @@ k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__
     if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
+// =====================================================================================================
+// backward at C = 512 on CTA pairs (cta_group::2)
+// =====================================================================================================
+// One CTA streams 80 KB per k-block for C = 512 (16 KB of F, 64 KB of S): two stages fit, and two stages cannot
+// cover the TMA round trip (tensor pipe 38-44 % active).  A CTA PAIR shares the S slab: each CTA holds its own
+// 128 pixel rows of F and HALF of the S rows of every N = 256 MMA, 48 KB per k-block, four stages deep, and the
+// slab leaves L2 once per 256 pixels instead of once per 128.  Item = (image, two consecutive 128-pixel chunks).
+struct BwdPairCfg {
+    static constexpr int C = 512;
+    static constexpr int STAGES = 4;
+    static constexpr int F_BYTES = 4 * 4096;         // this CTA's [128 x][32 j] tile of F
+    static constexpr int S_HALF_BYTES = 128 * 128;   // [128 rows c][32 j] of S for one N = 256 MMA
+    static constexpr int STAGE_BYTES = F_BYTES + 2 * S_HALF_BYTES;  // 48 KB per CTA
+    static constexpr int KB = C / 32;
+    static constexpr int TR_FLOATS = 4 * 32 * 36;
+    static constexpr int NBARS = 2 * STAGES + 2;     // full[], empty[], acc_full, acc_empty
+    static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + TR_FLOATS * 4 + NBARS * 8 + 16;
+};
+
+template <bool NHWC>
+__global__ void __launch_bounds__(kThreads, 1)
+k_gram_tc_bwd_pair(const __grid_constant__ CUtensorMap map_f, const __grid_constant__ CUtensorMap map_s,
+                   float* __restrict__ grad_feat, int B, int64_t HW, int accumulate) {
+    using Cfg = BwdPairCfg;
+    constexpr int C = Cfg::C;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* stages = smem;
+    float* tr_scratch = reinterpret_cast<float*>(smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tr_scratch + Cfg::TR_FLOATS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NBARS);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + Cfg::STAGES),
+                   accf = smem_u32(bars + 2 * Cfg::STAGES), acce = smem_u32(bars + 2 * Cfg::STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();  // 0 = leader: issues every MMA and owns the full / acc_empty barriers
+    const int64_t chunks = (HW + 127) / 128, pairs = (chunks + 1) / 2, items = (int64_t)B * pairs;
+    const int64_t cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < Cfg::STAGES; ++i) {
+            mbar_init(full0 + 8 * i, 1);   // leader's copy is used: one arrive.expect_tx + the bytes of both CTAs
+            mbar_init(empty0 + 8 * i, 1);  // one multicast commit per use, in each CTA
+        }
+        mbar_init(accf, 1);
+        mbar_init(acce, 8);                // four epilogue warps of each CTA (leader's copy is used)
+        fence_barrier_init();
+        tma_prefetch_desc(&map_f);
+        tma_prefetch_desc(&map_s);
+    }
+    if (warp == 1) tmem_alloc_pair<512>(smem_u32(tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // the peer's barriers exist before anything can arrive on them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t item = cluster_id; item < items; item += nclusters) {
+                const int b = (int)(item / pairs);
+                const int x0 = (int)((item % pairs) * 2 + rank) * 128;  // a chunk past HW reads zeros
+                for (int kb = 0; kb < Cfg::KB; ++kb, ++it) {
+                    const int st = it % Cfg::STAGES;
+                    const uint32_t ph = (it / Cfg::STAGES) & 1;
+                    mbar_wait(empty0 + 8 * st, ph ^ 1);
+                    if (rank == 0) mbar_arrive_expect_tx(full0 + 8 * st, 2 * Cfg::STAGE_BYTES);
+                    const uint32_t lead_full = mapa_shared(full0 + 8 * st, 0);
+                    const uint32_t dst = smem_u32(stages + (size_t)st * Cfg::STAGE_BYTES);
+                    if (NHWC) {
+                        tma_load_3d_pair(dst, &map_f, lead_full, kb * 32, x0, b);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            tma_load_2d_pair(dst + i * 4096, &map_f, lead_full, x0 + 32 * i, b * C + kb * 32);
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)  // this CTA's half of the S rows of MMA h
+                        tma_load_2d_pair(dst + Cfg::F_BYTES + h * Cfg::S_HALF_BYTES, &map_s, lead_full, kb * 32,
+                                         b * C + h * 256 + (int)rank * 128);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = instr_desc(256, 256, NHWC ? 0 : 1, 0);
+            uint32_t it = 0, li = 0;
+            for (int64_t item = cluster_id; item < items; item += nclusters, ++li) {
+                mbar_wait(acce, (li & 1) ^ 1);  // both epilogues have drained the accumulator
+                tc_fence_after();
+                for (int kb = 0; kb < Cfg::KB; ++kb, ++it) {
+                    const int st = it % Cfg::STAGES;
+                    const uint32_t ph = (it / Cfg::STAGES) & 1;
+                    mbar_wait(full0 + 8 * st, ph);
+                    tc_fence_after();
+                    const uint32_t sF = smem_u32(stages + (size_t)st * Cfg::STAGE_BYTES), sS = sF + Cfg::F_BYTES;
+#pragma unroll
+                    for (int kg = 0; kg < 4; ++kg) {
+                        const uint64_t ad = NHWC ? smem_desc(sF + kg * 32, 16, 1024) : smem_desc(sF + kg * 1024, 4096, 512, 1);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const uint64_t bd = smem_desc(sS + h * Cfg::S_HALF_BYTES + kg * 32, 16, 1024);
+                            mma_tf32_pair(tmem_base + h * 256, ad, bd, idesc, (kb > 0 || kg > 0) ? 1u : 0u);
+                        }
+                    }
+                    mma_commit_pair(empty0 + 8 * st, 0x3);  // frees the slot in both CTAs
+                }
+                mma_commit_pair(accf, 0x3);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        const uint32_t lead_acce = mapa_shared(acce, 0);
+        uint32_t li = 0;
+        float r[32];
+        for (int64_t item = cluster_id; item < items; item += nclusters, ++li) {
+            const int b = (int)(item / pairs);
+            const int64_t xc = ((item % pairs) * 2 + rank) * 128;  // first pixel of this CTA's chunk
+            const int64_t x = xc + q * 32 + lane;
+            mbar_wait(accf, li & 1);
+            tc_fence_after();
+            float* out = grad_feat + (int64_t)b * C * HW + x;  // NCHW
+#pragma unroll 1
+            for (int c0 = 0; c0 < C; c0 += 32) {
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+                if (NHWC) {
+                    float* sc = tr_scratch + q * 32 * 36;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(sc + lane * 36 + 4 * j) =
+                            make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                    __syncwarp();
+                    const int64_t xw = xc + q * 32;
+                    float* ow = grad_feat + ((int64_t)b * HW + xw) * C + c0 + 4 * (lane & 7);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int t = 4 * i + (lane >> 3);
+                        if (xw + t < HW) {
+                            float4 v = *reinterpret_cast<const float4*>(sc + t * 36 + 4 * (lane & 7));
+                            float4* o = reinterpret_cast<float4*>(ow + (int64_t)t * C);
+                            if (accumulate) {
+                                const float4 old = *o;
+                                v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+                            }
+                            *o = v;
+                        }
+                    }
+                    __syncwarp();
+                } else if (x < HW) {
+                    if (accumulate) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) out[(int64_t)(c0 + j) * HW] += r[j];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) out[(int64_t)(c0 + j) * HW] = r[j];
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(lead_acce);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // neither CTA frees tensor memory or exits while the other may still use the pair
+    if (warp == 1) tmem_dealloc_pair<512>(tmem_base);
+}
+
 // ---- host side -----------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -629,8 +856,48 @@ static int launch_fwd(const float* feat, const GramPlan& p, cudaStream_t s) {
     return ST3D_OK;
 }
 
+template <bool NHWC>
+static int launch_bwd_pair(const float* feat, const GramPlan& p, int accumulate, float* grad_feat, cudaStream_t s) {
+    using Cfg = BwdPairCfg;
+    constexpr int C = Cfg::C;
+    CUtensorMap map_f, map_s;
+    int rc = NHWC ? make_map_nhwc(&map_f, feat, p.B, p.HW, C, 128, CU_TENSOR_MAP_SWIZZLE_128B)
+                  : make_map(&map_f, feat, (uint64_t)p.B * C, (uint64_t)p.HW, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc != ST3D_OK) return rc;
+    rc = make_map(&map_s, p.sym, (uint64_t)p.B * C, (uint64_t)C, 128);
+    if (rc != ST3D_OK) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        ST3D_CUDA_OK(cudaFuncSetAttribute(k_gram_tc_bwd_pair<NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)Cfg::SMEM));
+        attr_done = true;
+    }
+    const int64_t chunks = (p.HW + 127) / 128, items = (int64_t)p.B * ((chunks + 1) / 2);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * (unsigned)std::min<int64_t>(items, 74));  // one CTA pair per TPC
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int B = p.B;
+    int64_t HW = p.HW;
+    ST3D_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gram_tc_bwd_pair<NHWC>, map_f, map_s, grad_feat, B, HW, accumulate));
+    ST3D_LAUNCH_OK("k_gram_tc_bwd_pair");
+    return ST3D_OK;
+}
+
 template <int C, bool NHWC>
 static int launch_bwd(const float* feat, const GramPlan& p, int accumulate, float* grad_feat, cudaStream_t s) {
+    if (C == 512) {  // CTA pairs (cta_group::2); ST3D_GRAM_BWD512_SINGLE=1 keeps the one-CTA kernel for comparison
+        static const bool single = [] { const char* e = getenv("ST3D_GRAM_BWD512_SINGLE"); return e && e[0] == '1'; }();
+        if (!single) return launch_bwd_pair<NHWC>(feat, p, accumulate, grad_feat, s);
+    }
     using Cfg = BwdCfg<C>;
     CUtensorMap map_f, map_s;
     int rc = NHWC ? make_map_nhwc(&map_f, feat, p.B, p.HW, C, 128, CU_TENSOR_MAP_SWIZZLE_128B)

@@ -74,10 +74,19 @@ __device__ __forceinline__ void table_pixel_range(const float* __restrict__ tab,
     const int jlo = (int)fminf(fmaxf(ceilf(fmaf(lo_v, a, b)), 0.0f), (float)S);
     i0 = S - 1 - jhi;  // first i with tab[i] <= hi_v
     i1 = S - 1 - jlo;  // last i with tab[i] >= lo_v
-    while (i0 > 0 && __ldg(tab + i0 - 1) <= hi_v) --i0;
-    while (i0 < S && __ldg(tab + i0) > hi_v) ++i0;
-    while (i1 < S - 1 && __ldg(tab + i1 + 1) >= lo_v) ++i1;
-    while (i1 >= 0 && __ldg(tab + i1) < lo_v) --i1;
+    // confirm both seeds with four independent loads (one L1 latency); walk only when a seed is off by a pixel
+    const float a0 = __ldg(tab + max(i0 - 1, 0)), b0 = __ldg(tab + min(i0, S - 1));
+    const float a1 = __ldg(tab + max(i1, 0)), b1 = __ldg(tab + min(i1 + 1, S - 1));
+    const bool ok0 = (i0 == 0 || a0 > hi_v) && (i0 == S || b0 <= hi_v);
+    const bool ok1 = (i1 < 0 || a1 >= lo_v) && (i1 == S - 1 || b1 < lo_v);
+    if (!ok0) {
+        while (i0 > 0 && __ldg(tab + i0 - 1) <= hi_v) --i0;
+        while (i0 < S && __ldg(tab + i0) > hi_v) ++i0;
+    }
+    if (!ok1) {
+        while (i1 < S - 1 && __ldg(tab + i1 + 1) >= lo_v) ++i1;
+        while (i1 >= 0 && __ldg(tab + i1) < lo_v) --i1;
+    }
 }
 
 template <bool GATHER>
