@@ -54,6 +54,8 @@ SIGNATURES = {
     "st3d_gram_mse_forward": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i64, c_f, c_p, c_p, c_p, c_p, c_sz, c_i, c_i, c_p]),
     "st3d_gram_backward": (c_i, [c_p, c_p, c_i, c_i, c_i64, c_f, c_p, c_i, c_p, c_p, c_sz, c_i, c_i, c_p]),
     "st3d_mse_forward": (c_i, [c_p, c_p, c_p, c_i64, c_i64, c_i, c_f, c_p, c_p, c_p]),
+    "st3d_maxpool2x2_forward": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
+    "st3d_maxpool2x2_backward": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
 }
 
 

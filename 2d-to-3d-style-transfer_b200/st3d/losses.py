@@ -28,7 +28,12 @@ def get_features(image: torch.Tensor, model, layers=None, stop_after_last_tap: b
     for name, module in model._modules.items():
         if done and not ((isinstance(module, torch.nn.ReLU) and module.inplace) or isinstance(module, torch.nn.Identity)):
             break
-        x = module(x)
+        if hasattr(module, "tapped"):       # FusedConvReLU: a tapped activation has a second consumer (st3d/vgg.py)
+            module.tapped = name in layers
+            x = module(x)
+            module.tapped = True
+        else:
+            x = module(x)
         if done:
             break
         if name in layers:

@@ -462,3 +462,38 @@ def mse_forward(a, b, scale: float, loss_out, mask=None, want_grad=True):
         check(lib().st3d_mse_forward(_p(a), _p(b), _p(mask), a.numel(), inner, mask_ch, float(scale), _p(loss_out),
                                      _p(grad), _stream()), "st3d_mse_forward")
     return grad
+
+
+# ------------------------------------------------------------------------------------------------
+# 2x2 max pooling of channels_last feature maps (VGG-19 pools; the convolutions stay on cuDNN)
+# ------------------------------------------------------------------------------------------------
+def maxpool_supported(x: torch.Tensor) -> bool:
+    """Shapes / layouts the libst3d pooling kernels accept: CUDA fp32 (B,C,H,W) in channels_last storage,
+    even H and W, C a multiple of 4."""
+    return (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+            and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0 and x.shape[1] % 4 == 0 and x.shape[1] > 1
+            and x.is_contiguous(memory_format=torch.channels_last))
+
+
+def maxpool2x2_forward(x: torch.Tensor) -> torch.Tensor:
+    if not maxpool_supported(x):
+        raise ValueError("maxpool2x2_forward: expected a CUDA float32 channels_last (B,C,H,W) tensor with even H, W "
+                         "and C % 4 == 0")
+    B, C, H, W = x.shape
+    y = torch.empty((B, C, H // 2, W // 2), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+    with _timed("maxpool_forward", (B, C, H, W)):
+        check(lib().st3d_maxpool2x2_forward(_p(x), B, H, W, C, _p(y), _stream()), "st3d_maxpool2x2_forward")
+    return y
+
+
+def maxpool2x2_backward(x: torch.Tensor, grad_y: torch.Tensor, relu_mask: bool = False) -> torch.Tensor:
+    """Gradient w.r.t. x; with relu_mask also through the ReLU that produced x (zero where x <= 0)."""
+    B, C, H, W = x.shape
+    if not maxpool_supported(x) or grad_y.shape != (B, C, H // 2, W // 2):
+        raise ValueError("maxpool2x2_backward: x / grad_y do not match the forward call")
+    grad_y = grad_y.contiguous(memory_format=torch.channels_last)
+    gx = torch.empty_like(x)
+    with _timed("maxpool_backward", (B, C, H, W)):
+        check(lib().st3d_maxpool2x2_backward(_p(x), _p(grad_y), B, H, W, C, int(relu_mask), _p(gx), _stream()),
+              "st3d_maxpool2x2_backward")
+    return gx

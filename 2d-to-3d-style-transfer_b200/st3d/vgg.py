@@ -7,6 +7,10 @@ in this repo, BASELINE.json); this module only picks cuDNN's better entry points
   cudnnConvolutionBiasActivationForward) instead of convolution, broadcast bias add and in-place ReLU as
   three kernels: bit-identical output, 2.55 ms instead of 4.85 ms per forward of 8 x 512^2 images.
 
+* the four MaxPool2d(2, 2) modules run libst3d's NHWC pooling kernels (csrc/pool.cu): no int64 argmax indices
+  written forward and read backward, and the backward also applies the ReLU mask of the layer in front of the
+  pool, so that layer's separate ReLU-backward pass disappears (bit-identical gradients).
+
 `fuse_vgg_features` keeps the module NAMES of `torchvision.models.vgg19().features`, so the reference's
 `get_features` (style_transfer.py:10-27), which taps modules '0', '5', '10', '19', '21', '28', works unchanged:
 module i (Conv2d) becomes the fused op and module i+1 (ReLU(inplace=True)) becomes an identity -- the tapped
@@ -22,9 +26,11 @@ import torch.nn as nn
 
 class _ConvBiasReLUFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, padding, dilation, groups):
+    def forward(ctx, x, weight, bias, stride, padding, dilation, groups, premasked):
         y = torch.cudnn_convolution_relu(x, weight, bias, stride, padding, dilation, groups)
         ctx.conf = (stride, padding, dilation, groups)
+        # the only consumer is a libst3d pool whose backward already applies this layer's ReLU mask
+        ctx.premasked = bool(premasked) and _ops().maxpool_supported(y)
         ctx.save_for_backward(x, weight, y)
         return y
 
@@ -32,11 +38,53 @@ class _ConvBiasReLUFn(torch.autograd.Function):
     def backward(ctx, grad_y):
         x, weight, y = ctx.saved_tensors
         stride, padding, dilation, groups = ctx.conf
-        g = torch.ops.aten.threshold_backward(grad_y, y, 0.0)          # ReLU backward from the saved output
+        # ReLU backward from the saved output (skipped when the pool behind this layer has done it already)
+        g = grad_y if ctx.premasked else torch.ops.aten.threshold_backward(grad_y, y, 0.0)
         need = [ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]]
         gx, gw, gb = torch.ops.aten.convolution_backward(g, x, weight, [weight.shape[0]], list(stride), list(padding),
                                                          list(dilation), False, [0, 0], groups, need)
-        return gx, gw, gb, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None
+
+
+def _ops():
+    from . import ops
+    return ops
+
+
+class _MaxPool2x2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, relu_mask):
+        ctx.save_for_backward(x)
+        ctx.relu_mask = relu_mask
+        return _ops().maxpool2x2_forward(x)
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        (x,) = ctx.saved_tensors
+        return _ops().maxpool2x2_backward(x, grad_y, ctx.relu_mask), None
+
+
+class FusedMaxPool(nn.Module):
+    """MaxPool2d(2, 2) on libst3d's NHWC kernels when the input allows it (CUDA fp32 channels_last, even sides,
+    C % 4 == 0), torch's pooling otherwise.  `after_relu`: the input is a post-ReLU activation, so the backward may
+    apply that ReLU's mask in the same pass (idempotent with a ReLU backward done elsewhere)."""
+
+    def __init__(self, pool: nn.MaxPool2d, after_relu: bool = False):
+        super().__init__()
+        self.pool, self.after_relu = pool, bool(after_relu)
+
+    @staticmethod
+    def accepts(pool) -> bool:
+        def pair(v):
+            return (v, v) if isinstance(v, int) else tuple(v)
+        return (isinstance(pool, nn.MaxPool2d) and pair(pool.kernel_size) == (2, 2) and pair(pool.stride) == (2, 2)
+                and pair(pool.padding) == (0, 0) and pair(pool.dilation) == (1, 1) and not pool.ceil_mode
+                and not pool.return_indices)
+
+    def forward(self, x):
+        if _ops().maxpool_supported(x):
+            return _MaxPool2x2Fn.apply(x, self.after_relu)
+        return self.pool(x)
 
 
 class FusedConvReLU(nn.Module):
@@ -47,20 +95,27 @@ class FusedConvReLU(nn.Module):
         if conv.padding_mode != "zeros" or isinstance(conv.padding, str):
             raise ValueError("FusedConvReLU supports zero padding given as integers")
         self.conv = conv
+        self.feeds_masking_pool = False   # set by fuse_vgg_features: next real module is a FusedMaxPool(after_relu)
+        # cleared by st3d.losses.get_features around the call when it knows nothing else reads this activation; any
+        # other caller keeps the conservative default (this layer's ReLU backward is always applied)
+        self.tapped = True
 
     def forward(self, x):
         c = self.conv
         if not x.is_cuda:
             return torch.relu_(c(x))
         bias = c.bias if c.bias is not None else torch.zeros(c.out_channels, device=x.device, dtype=x.dtype)
-        return _ConvBiasReLUFn.apply(x, c.weight, bias, tuple(c.stride), tuple(c.padding), tuple(c.dilation), c.groups)
+        return _ConvBiasReLUFn.apply(x, c.weight, bias, tuple(c.stride), tuple(c.padding), tuple(c.dilation), c.groups,
+                                     self.feeds_masking_pool and not self.tapped)
 
 
-def fuse_vgg_features(features: nn.Sequential, channels_last: bool = True) -> nn.Sequential:
-    """Same module names as `features`; every Conv2d followed by a ReLU becomes one FusedConvReLU + Identity."""
+def fuse_vgg_features(features: nn.Sequential, channels_last: bool = True, fuse_pool: bool = True) -> nn.Sequential:
+    """Same module names as `features`; every Conv2d followed by a ReLU becomes one FusedConvReLU + Identity, every
+    MaxPool2d(2, 2) a FusedMaxPool (libst3d kernels) that also carries the ReLU mask of a FusedConvReLU before it."""
     items = list(features._modules.items())
     out = OrderedDict()
     skip = False
+    last_fused = None       # the FusedConvReLU whose activation is the current tensor, if any
     for i, (name, m) in enumerate(items):
         if skip:
             out[name] = nn.Identity()
@@ -68,10 +123,16 @@ def fuse_vgg_features(features: nn.Sequential, channels_last: bool = True) -> nn
             continue
         nxt = items[i + 1][1] if i + 1 < len(items) else None
         if isinstance(m, nn.Conv2d) and isinstance(nxt, nn.ReLU):
-            out[name] = FusedConvReLU(m)
+            out[name] = last_fused = FusedConvReLU(m)
             skip = True
+            continue
+        if fuse_pool and channels_last and FusedMaxPool.accepts(m):
+            out[name] = FusedMaxPool(m, after_relu=last_fused is not None)
+            if last_fused is not None:
+                last_fused.feeds_masking_pool = True
         else:
             out[name] = m
+        last_fused = None
     fused = nn.Sequential(out).eval()
     if channels_last:
         fused = fused.to(memory_format=torch.channels_last)

@@ -206,6 +206,19 @@ int st3d_gram_backward(const float* feat, const float* dgram, int B, int C, int6
 int st3d_mse_forward(const float* a, const float* b, const float* mask, int64_t n, int64_t inner, int mask_ch,
                      float scale, float* loss_out, float* grad_a, st3d_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * 2x2 / stride-2 max pooling of channels_last feature maps: the four MaxPool2d(2, 2) modules of the VGG-19
+ * `.features` that utils.py:49 builds and get_features (style_transfer.py:21-26) walks.  The convolutions
+ * around them stay on cuDNN; the pools are pure HBM traffic.
+ * x (B,H,W,C) NHWC storage (torch channels_last), H and W even, C % 4 == 0; y (B,H/2,W/2,C).
+ * Backward: grad_x (B,H,W,C) is fully overwritten; the argmax is recomputed from x (first maximum in scan
+ * order, NaN wins -- ATen's rule, so results are bit-identical to torch's); relu_mask != 0 additionally zeroes
+ * the gradient where the winning input is <= 0, i.e. fuses the backward of the ReLU that produced x.
+ * ---------------------------------------------------------------------------------------------- */
+int st3d_maxpool2x2_forward(const float* x, int B, int H, int W, int C, float* y, st3d_stream_t stream);
+int st3d_maxpool2x2_backward(const float* x, const float* grad_y, int B, int H, int W, int C, int relu_mask,
+                             float* grad_x, st3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -263,3 +263,69 @@ def test_fused_vgg_forward_backward_equal_unfused():
     for k in fb:
         assert torch.allclose(fa[k], fb[k], rtol=1e-4, atol=1e-6), k
     assert _relerr(xa.grad, xb.grad) <= 1e-3
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 32, 48), (1, 128, 16, 16), (3, 4, 2, 2), (2, 512, 8, 4)])
+def test_maxpool2x2_kernels_bit_identical_to_torch(B, C, H, W):
+    """libst3d's NHWC 2x2 max pooling (csrc/pool.cu; the VGG-19 MaxPool2d modules of style_transfer.py:21-26):
+    forward, backward, and backward with the fused ReLU mask, against torch's pooling + threshold_backward.
+    Ties (the zeros a ReLU leaves) and NaNs must route exactly as ATen routes them."""
+    import torch.nn.functional as F
+    ops = _ops()
+    gen = torch.Generator(device="cuda").manual_seed(B * 1000 + C)
+    x = torch.relu(torch.randn(B, C, H, W, device="cuda", generator=gen))            # plenty of tied zeros
+    x[0, 0, 0, 1] = float("nan")
+    x = x.contiguous(memory_format=torch.channels_last)
+    g = torch.randn(B, C, H // 2, W // 2, device="cuda", generator=gen).contiguous(memory_format=torch.channels_last)
+    xr = x.clone().requires_grad_(True)
+    yr = F.max_pool2d(xr, 2, 2)
+    y = ops.maxpool2x2_forward(x)
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(torch.nan_to_num(y, nan=-7.0), torch.nan_to_num(yr.detach(), nan=-7.0))
+    (gr,) = torch.autograd.grad(yr, xr, g)
+    assert torch.equal(ops.maxpool2x2_backward(x, g, relu_mask=False), gr)
+    want = torch.ops.aten.threshold_backward(gr, x, 0.0)                                # the ReLU in front of the pool
+    got = ops.maxpool2x2_backward(x, g, relu_mask=True)
+    assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(want, nan=-7.0))
+
+
+def test_maxpool2x2_rejects_unsupported_inputs():
+    ops = _ops()
+    with pytest.raises(ValueError):
+        ops.maxpool2x2_forward(torch.rand(1, 8, 5, 6, device="cuda").contiguous(memory_format=torch.channels_last))
+    with pytest.raises(ValueError):
+        ops.maxpool2x2_forward(torch.rand(1, 8, 4, 4, device="cuda"))                  # NCHW storage
+    from st3d.vgg import FusedMaxPool
+    pool = FusedMaxPool(torch.nn.MaxPool2d(2, 2), after_relu=True)
+    x = torch.rand(1, 8, 5, 6, device="cuda")
+    assert torch.equal(pool(x), torch.nn.functional.max_pool2d(x, 2, 2))               # torch's pooling takes over
+
+
+def test_fused_vgg_pools_give_bit_identical_gradients():
+    """Fused pools (+ the ReLU mask they carry) against the same VGG with torch's pooling and ReLU backward."""
+    import torchvision
+    from st3d import losses
+    from st3d.vgg import FusedMaxPool, fuse_vgg_features
+    torch.manual_seed(1)
+    vgg = torchvision.models.vgg19(weights=None).features.eval().cuda()
+    for p in vgg.parameters():
+        p.requires_grad_(False)
+    a = fuse_vgg_features(vgg, channels_last=True, fuse_pool=True)
+    b = fuse_vgg_features(vgg, channels_last=True, fuse_pool=False)
+    assert sum(isinstance(m, FusedMaxPool) for m in a) == 5 and not any(isinstance(m, FusedMaxPool) for m in b)
+    assert [n for n, m in a._modules.items() if getattr(m, "feeds_masking_pool", False)] == ["2", "7", "16", "25", "34"]
+    x = torch.rand(2, 3, 64, 96, device="cuda").contiguous(memory_format=torch.channels_last)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    fa, fb = losses.get_features(xa, a), losses.get_features(xb, b)
+    for k in fb:
+        assert torch.equal(fa[k], fb[k]), k
+    sum((f ** 2).mean() for f in fa.values()).backward()
+    sum((f ** 2).mean() for f in fb.values()).backward()
+    assert torch.equal(xa.grad, xb.grad)
+    # a pre-pool activation that is ALSO tapped keeps its own ReLU backward (second consumer): still identical
+    taps = {"2": "conv1_2", "7": "conv2_2"}
+    xa2, xb2 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ga, gb = losses.get_features(xa2, a, taps), losses.get_features(xb2, b, taps)
+    sum((f ** 3).mean() for f in ga.values()).backward()
+    sum((f ** 3).mean() for f in gb.values()).backward()
+    assert torch.equal(xa2.grad, xb2.grad)
