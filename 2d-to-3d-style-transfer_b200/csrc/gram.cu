@@ -225,7 +225,9 @@ k_gram_bwd_simt(const float* __restrict__ feat, const float* __restrict__ sym, i
             const int64_t x = x0 + tx * 4 + j;
             if (c < C && x < HW) {
                 const int64_t o = (int64_t)c * sc + x * sx;
-                G[o] = accumulate ? G[o] + acc[i][j] : acc[i][j];
+                float v = (accumulate & 1) ? G[o] + acc[i][j] : acc[i][j];
+                if ((accumulate & 2) && F[o] <= 0.0f) v = 0.0f;  // ReLU backward of the layer that produced feat
+                G[o] = v;
             }
         }
 }

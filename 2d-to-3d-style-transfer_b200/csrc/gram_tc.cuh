@@ -427,7 +427,7 @@ struct BwdCfg {
 template <int C, bool NHWC>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__ CUtensorMap map_s,
-              float* __restrict__ grad_feat, int B, int64_t HW, int accumulate) {
+              const float* __restrict__ feat, float* __restrict__ grad_feat, int B, int64_t HW, int accumulate) {
     using Cfg = BwdCfg<C>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -543,27 +543,55 @@ k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__
                     __syncwarp();
                     const int64_t xw = (item % chunks) * 128 + q * 32;  // first pixel row of this warp
                     float* ow = grad_feat + ((int64_t)b * HW + xw) * C + c0 + 4 * (lane & 7);
+                    if (accumulate == 0) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int t = 4 * i + (lane >> 3);
-                        if (xw + t < HW) {
-                            float4 v = *reinterpret_cast<const float4*>(sc + t * 36 + 4 * (lane & 7));
-                            float4* o = reinterpret_cast<float4*>(ow + (int64_t)t * C);
-                            if (accumulate) {
-                                const float4 old = *o;
-                                v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+                        for (int i = 0; i < 8; ++i) {
+                            const int t = 4 * i + (lane >> 3);
+                            if (xw + t < HW)
+                                *reinterpret_cast<float4*>(ow + (int64_t)t * C) =
+                                    *reinterpret_cast<const float4*>(sc + t * 36 + 4 * (lane & 7));
+                        }
+                    } else {
+                        // fused elementwise tail: all global loads of the eight row groups are issued before the
+                        // first store, so one memory round trip covers them (a load after a store to the same
+                        // array could not be hoisted over it)
+                        float4 oldv[8], fv[8];
+                        const float* fw = feat + (ow - grad_feat);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int t = 4 * i + (lane >> 3);
+                            const bool ok = xw + t < HW;
+                            oldv[i] = (ok && (accumulate & 1)) ? *reinterpret_cast<const float4*>(ow + (int64_t)t * C)
+                                                               : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                            fv[i] = (ok && (accumulate & 2)) ? __ldg(reinterpret_cast<const float4*>(fw + (int64_t)t * C))
+                                                             : make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int t = 4 * i + (lane >> 3);
+                            if (xw + t < HW) {
+                                float4 v = *reinterpret_cast<const float4*>(sc + t * 36 + 4 * (lane & 7));
+                                if (accumulate & 1) {
+                                    v.x += oldv[i].x; v.y += oldv[i].y; v.z += oldv[i].z; v.w += oldv[i].w;
+                                }
+                                // ReLU backward of the layer that produced feat: zero where feat <= 0
+                                if (fv[i].x <= 0.0f) v.x = 0.0f;
+                                if (fv[i].y <= 0.0f) v.y = 0.0f;
+                                if (fv[i].z <= 0.0f) v.z = 0.0f;
+                                if (fv[i].w <= 0.0f) v.w = 0.0f;
+                                *reinterpret_cast<float4*>(ow + (int64_t)t * C) = v;
                             }
-                            *o = v;
                         }
                     }
                     __syncwarp();
                 } else if (x < HW) {
-                    if (accumulate) {
+                    const float* fin = feat + (out - grad_feat);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) out[(int64_t)(c0 + j) * HW] += r[j];
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) out[(int64_t)(c0 + j) * HW] = r[j];
+                    for (int j = 0; j < 32; ++j) {
+                        const int64_t o = (int64_t)(c0 + j) * HW;
+                        float v = (accumulate & 1) ? out[o] + r[j] : r[j];
+                        if ((accumulate & 2) && __ldg(fin + o) <= 0.0f) v = 0.0f;
+                        out[o] = v;
                     }
                 }
             }
@@ -599,7 +627,7 @@ struct BwdPairCfg {
 template <bool NHWC>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gram_tc_bwd_pair(const __grid_constant__ CUtensorMap map_f, const __grid_constant__ CUtensorMap map_s,
-                   float* __restrict__ grad_feat, int B, int64_t HW, int accumulate) {
+                   const float* __restrict__ feat, float* __restrict__ grad_feat, int B, int64_t HW, int accumulate) {
     using Cfg = BwdPairCfg;
     constexpr int C = Cfg::C;
     extern __shared__ uint8_t smem_raw[];
@@ -714,27 +742,55 @@ k_gram_tc_bwd_pair(const __grid_constant__ CUtensorMap map_f, const __grid_const
                     __syncwarp();
                     const int64_t xw = xc + q * 32;
                     float* ow = grad_feat + ((int64_t)b * HW + xw) * C + c0 + 4 * (lane & 7);
+                    if (accumulate == 0) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int t = 4 * i + (lane >> 3);
-                        if (xw + t < HW) {
-                            float4 v = *reinterpret_cast<const float4*>(sc + t * 36 + 4 * (lane & 7));
-                            float4* o = reinterpret_cast<float4*>(ow + (int64_t)t * C);
-                            if (accumulate) {
-                                const float4 old = *o;
-                                v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+                        for (int i = 0; i < 8; ++i) {
+                            const int t = 4 * i + (lane >> 3);
+                            if (xw + t < HW)
+                                *reinterpret_cast<float4*>(ow + (int64_t)t * C) =
+                                    *reinterpret_cast<const float4*>(sc + t * 36 + 4 * (lane & 7));
+                        }
+                    } else {
+                        // fused elementwise tail: all global loads of the eight row groups are issued before the
+                        // first store, so one memory round trip covers them (a load after a store to the same
+                        // array could not be hoisted over it)
+                        float4 oldv[8], fv[8];
+                        const float* fw = feat + (ow - grad_feat);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int t = 4 * i + (lane >> 3);
+                            const bool ok = xw + t < HW;
+                            oldv[i] = (ok && (accumulate & 1)) ? *reinterpret_cast<const float4*>(ow + (int64_t)t * C)
+                                                               : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                            fv[i] = (ok && (accumulate & 2)) ? __ldg(reinterpret_cast<const float4*>(fw + (int64_t)t * C))
+                                                             : make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int t = 4 * i + (lane >> 3);
+                            if (xw + t < HW) {
+                                float4 v = *reinterpret_cast<const float4*>(sc + t * 36 + 4 * (lane & 7));
+                                if (accumulate & 1) {
+                                    v.x += oldv[i].x; v.y += oldv[i].y; v.z += oldv[i].z; v.w += oldv[i].w;
+                                }
+                                // ReLU backward of the layer that produced feat: zero where feat <= 0
+                                if (fv[i].x <= 0.0f) v.x = 0.0f;
+                                if (fv[i].y <= 0.0f) v.y = 0.0f;
+                                if (fv[i].z <= 0.0f) v.z = 0.0f;
+                                if (fv[i].w <= 0.0f) v.w = 0.0f;
+                                *reinterpret_cast<float4*>(ow + (int64_t)t * C) = v;
                             }
-                            *o = v;
                         }
                     }
                     __syncwarp();
                 } else if (x < HW) {
-                    if (accumulate) {
+                    const float* fin = feat + (out - grad_feat);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) out[(int64_t)(c0 + j) * HW] += r[j];
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) out[(int64_t)(c0 + j) * HW] = r[j];
+                    for (int j = 0; j < 32; ++j) {
+                        const int64_t o = (int64_t)(c0 + j) * HW;
+                        float v = (accumulate & 1) ? out[o] + r[j] : r[j];
+                        if ((accumulate & 2) && __ldg(fin + o) <= 0.0f) v = 0.0f;
+                        out[o] = v;
                     }
                 }
             }
@@ -887,7 +943,7 @@ static int launch_bwd_pair(const float* feat, const GramPlan& p, int accumulate,
     cfg.numAttrs = 1;
     int B = p.B;
     int64_t HW = p.HW;
-    ST3D_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gram_tc_bwd_pair<NHWC>, map_f, map_s, grad_feat, B, HW, accumulate));
+    ST3D_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gram_tc_bwd_pair<NHWC>, map_f, map_s, feat, grad_feat, B, HW, accumulate));
     ST3D_LAUNCH_OK("k_gram_tc_bwd_pair");
     return ST3D_OK;
 }
@@ -913,7 +969,7 @@ static int launch_bwd(const float* feat, const GramPlan& p, int accumulate, floa
     }
     const int64_t items = (int64_t)p.B * ((p.HW + 127) / 128);
     const int grid = (int)std::min<int64_t>(items, 148);
-    k_gram_tc_bwd<C, NHWC><<<grid, kThreads, Cfg::SMEM, s>>>(map_f, map_s, grad_feat, p.B, p.HW, accumulate);
+    k_gram_tc_bwd<C, NHWC><<<grid, kThreads, Cfg::SMEM, s>>>(map_f, map_s, feat, grad_feat, p.B, p.HW, accumulate);
     ST3D_LAUNCH_OK("k_gram_tc_bwd");
     return ST3D_OK;
 }

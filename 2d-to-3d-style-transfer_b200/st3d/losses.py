@@ -70,6 +70,44 @@ def perceptual_loss_from_features(cur_feats, content_feat, style_grams, style_we
     return content_weight * content_loss + style_weight * style_loss
 
 
+def perceptual_loss_of_images(current_imgs, model, content_feat, style_grams, style_weight=1e6, content_weight=1.0,
+                              precision=None):
+    """losses.py:26-42 from the images on: walks `model` like get_features and evaluates the loss on the way.
+    With a fused model (st3d.vgg.fuse_vgg_features) every style tap is evaluated INSIDE its conv + ReLU layer, so
+    the layer's backward adds the Gram gradient to the gradient arriving from deeper layers and applies the ReLU
+    mask in the Gram kernel's epilogue; values and gradients equal get_features + perceptual_loss_from_features."""
+    from .vgg import FusedConvReLU
+    fused_taps = current_imgs.is_cuda and all(isinstance(model._modules.get(n), FusedConvReLU)
+                                              for n, l in VGG_TAPS.items() if l in style_grams)
+    if not fused_taps:
+        return perceptual_loss_from_features(get_features(current_imgs, model), content_feat, style_grams, style_weight,
+                                             content_weight, precision)
+    x = current_imgs
+    if getattr(model, "_st3d_channels_last", False) and x.dim() == 4:
+        x = x.contiguous(memory_format=torch.channels_last)
+    content_loss, style_loss, done = None, None, False
+    for name, module in model._modules.items():
+        if done and not ((isinstance(module, torch.nn.ReLU) and module.inplace) or isinstance(module, torch.nn.Identity)):
+            break
+        layer = VGG_TAPS.get(name)
+        if layer in style_grams:
+            x, term = module.forward_with_style_tap(x, style_grams[layer], precision)
+            style_loss = term if style_loss is None else style_loss + term
+        else:
+            if hasattr(module, "tapped"):
+                module.tapped = layer is not None
+                x = module(x)
+                module.tapped = True
+            else:
+                x = module(x)
+            if layer == CONTENT_LAYER:
+                content_loss = Fn.mse_loss(x, content_feat)
+        if done:
+            break
+        done = name == str(LAST_TAP)
+    return content_weight * content_loss + style_weight * style_loss
+
+
 def compute_perceptual_loss(current_imgs, content_imgs, style_imgs, model, style_weight=1e6, content_weight=1,
                             precision=None):
     """losses.py:12-44.  `style_imgs` may have batch 1 (the reference repeats one image B times,
@@ -79,8 +117,7 @@ def compute_perceptual_loss(current_imgs, content_imgs, style_imgs, model, style
     with torch.no_grad():
         content_feat = get_features(content_imgs, model, {"21": CONTENT_LAYER})[CONTENT_LAYER]
     grams = style_targets(style_imgs, model, precision)
-    cur = get_features(current_imgs, model)
-    return perceptual_loss_from_features(cur, content_feat, grams, style_weight, content_weight, precision)
+    return perceptual_loss_of_images(current_imgs, model, content_feat, grams, style_weight, content_weight, precision)
 
 
 def compute_first_approach_image_loss(rendered, masks, target_rendered):

@@ -141,9 +141,8 @@ class StyleOptimizer:
             if self.cache_constants:
                 self._cache = dict(key=key, content_feat=content_feat, grams=grams)
         current_imgs, _ = self._render(self.verts, self.colour, R, T)                           # :165
-        cur = losses.get_features(self._nn_input(current_imgs), self.vgg)
-        loss = losses.perceptual_loss_from_features(cur, content_feat, grams, self.style_weight, self.content_weight,
-                                                    self.precision)
+        loss = losses.perceptual_loss_of_images(self._nn_input(current_imgs), self.vgg, content_feat, grams,
+                                                self.style_weight, self.content_weight, self.precision)
         if self.target != "texture":                                                            # losses.py:108-124
             # the perceptual term is a mean over views (sharded: scale by 1/world); the regularisers are
             # view-independent and identical on every rank, so they are added once, after the all-reduce

@@ -51,6 +51,52 @@ def _ops():
     return ops
 
 
+class _ConvReLUStyleTapFn(torch.autograd.Function):
+    """A FusedConvReLU whose activation is a style tap (style_transfer.py:21-26 + losses.py:35-39 for that layer):
+    returns (y, layer_loss) with y = relu(conv(x) + b) and layer_loss = mean((y y^T - target)^2) / (C^2 H^2).
+
+    Keeping the tap inside the layer's Function lets the backward do in ONE kernel what autograd spreads over
+    three: the Gram backward dF = (dG + dG^T) y, its addition to the gradient that reaches y through the rest of
+    the network, and the ReLU backward of the sum -- st3d_gram_backward with ST3D_GRAM_ACCUMULATE | ST3D_GRAM_RELU_MASK."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, target, stride, padding, dilation, groups, precision):
+        ops = _ops()
+        y = torch.cudnn_convolution_relu(x, weight, bias, stride, padding, dilation, groups)
+        B, C, H, W = y.shape
+        scale = 1.0 / (B * C * C) / (float(C) ** 2 * float(H) ** 2)
+        loss = torch.zeros(1, device=y.device, dtype=torch.float32)
+        dgram, _ = ops.gram_mse_forward(y, target.detach(), scale, loss, precision=precision)
+        ctx.conf = (stride, padding, dilation, groups, precision)
+        ctx.save_for_backward(x, weight, y, dgram)
+        ctx.set_materialize_grads(False)
+        return y, loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_y, grad_loss):
+        ops = _ops()
+        x, weight, y, dgram = ctx.saved_tensors
+        stride, padding, dilation, groups, precision = ctx.conf
+        if grad_loss is None and grad_y is None:
+            return (None,) * 9
+        if grad_loss is None:                       # the tap's loss term is unused: plain ReLU backward
+            g = torch.ops.aten.threshold_backward(grad_y, y, 0.0)
+        else:
+            out = None
+            if grad_y is not None:                  # accumulate into the incoming gradient when its layout allows it
+                if grad_y.stride() == y.stride() and grad_y.dtype == torch.float32:
+                    out = grad_y
+                else:
+                    out = torch.empty_like(y)
+                    out.copy_(grad_y)
+            g = ops.gram_backward(y, dgram, 1.0, out=out, accumulate=out is not None, precision=precision,
+                                  scale_tensor=grad_loss, relu_mask=True)
+        need = [ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]]
+        gx, gw, gb = torch.ops.aten.convolution_backward(g, x, weight, [weight.shape[0]], list(stride), list(padding),
+                                                         list(dilation), False, [0, 0], groups, need)
+        return gx, gw, gb, None, None, None, None, None, None
+
+
 class _MaxPool2x2Fn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, relu_mask):
@@ -107,6 +153,13 @@ class FusedConvReLU(nn.Module):
         bias = c.bias if c.bias is not None else torch.zeros(c.out_channels, device=x.device, dtype=x.dtype)
         return _ConvBiasReLUFn.apply(x, c.weight, bias, tuple(c.stride), tuple(c.padding), tuple(c.dilation), c.groups,
                                      self.feeds_masking_pool and not self.tapped)
+
+    def forward_with_style_tap(self, x, target_gram, precision=None):
+        """(activation, style-loss term of this layer against `target_gram` (1|B,C,C)); CUDA only."""
+        c = self.conv
+        bias = c.bias if c.bias is not None else torch.zeros(c.out_channels, device=x.device, dtype=x.dtype)
+        return _ConvReLUStyleTapFn.apply(x, c.weight, bias, target_gram, tuple(c.stride), tuple(c.padding),
+                                         tuple(c.dilation), c.groups, precision)
 
 
 def fuse_vgg_features(features: nn.Sequential, channels_last: bool = True, fuse_pool: bool = True) -> nn.Sequential:

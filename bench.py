@@ -95,7 +95,8 @@ def workload_config(args, world):
         "style_weight": 1e6, "content_weight": 1, "lr": 0.01, "parallelism": f"view-sharded dp{world}",
         "vgg": "torchvision VGG-19 .features, seeded random init (ImageNet weights unavailable offline), fp32 cuDNN "
                "(torch default allow_tf32), activations " + ("NCHW" if args.nchw else "channels_last (NHWC)") +
-               (", conv+bias+ReLU as cuDNN's fused call" if not args.unfused_vgg else "") + ", inside the timed step",
+               (", conv+bias+ReLU as cuDNN's fused call, 2x2 max pools on libst3d's NHWC kernels"
+                if not args.unfused_vgg else "") + ", inside the timed step",
         "l2": "per-step working set (VGG activations of 8 x 512^2 images, > 4 GB) exceeds the 126 MB L2; no explicit flush",
     }
 
@@ -209,6 +210,10 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+# filled from the round's ncu capture (profiles/): (bytes per launch, source) of the fused Gram backward at conv1_1
+TRAFFIC_FUSED_BWD64 = (None, None)
+
+
 def algorithmic_bytes(op, key, tex=512):
     """SURVEY.md section 8(d) / DESIGN.md: bytes one call of `op` must move."""
     if op == "render_forward":      # face records + (pix_to_face i32, rgb, mask) per pixel + texture once
@@ -217,14 +222,20 @@ def algorithmic_bytes(op, key, tex=512):
     if op == "render_backward":     # grad rgb + saved pix_to_face per pixel + face records + grad_texture
         N, H, W, F = key
         return N * H * W * (12 + 4) + N * F * 48 + tex * tex * 12
-    if op == "gram_backward":       # read F, write dF
+    if op.startswith("gram_backward"):   # read F, write dF; fused tail: + read the incoming gradient, + read F for the mask
         B, C, HW = key
-        return 2 * B * C * HW * 4
+        return (2 + ("_acc" in op) + ("_relu" in op)) * B * C * HW * 4
     if op in ("gram_forward", "gram_mse_forward"):   # read F, write G (+dG)
         B, C, HW = key
         return B * C * HW * 4 + B * C * C * 4
     if op == "mse_forward":         # read a, b, write grad
         return 3 * key[0] * 4
+    if op == "maxpool_forward":     # read x, write x / 4
+        B, C, H, W = key
+        return B * C * H * W * 5
+    if op == "maxpool_backward":    # read x and grad_y (x / 4), write grad_x
+        B, C, H, W = key
+        return B * C * H * W * 9
     return None
 
 
@@ -354,15 +365,19 @@ def run_st3d(args):
     final_loss = float(loss)
 
     # per-op breakdown (rank 0)
-    stages, mine_ms = {}, 0.0
+    stages, mine_ms, pool_ms = {}, 0.0, 0.0
     for (op, key), v in sorted(prof.items()):
         per_step = sum(v) / args.steps
-        mine_ms += per_step
+        if op.startswith("maxpool"):    # VGG-side kernels of this library: reported apart from the render + loss path
+            pool_ms += per_step
+        else:
+            mine_ms += per_step
         name = op + ("" if key is None else "_" + "x".join(str(k) for k in key))
         stages[name] = round(per_step, 4)
     # dominant KERNEL -> roofline.  gram_* / mse ops are one hot kernel each (plus a <5 us symmetrise/finalize);
     # render_forward is a sequence of 7 launches (bins, z-buffer, resolve) and is reported per op below.
-    single_kernel_ops = ("gram_backward", "gram_mse_forward", "gram_forward", "mse_forward")
+    single_kernel_ops = ("gram_backward", "gram_backward_acc", "gram_backward_relu", "gram_backward_acc_relu",
+                         "gram_mse_forward", "gram_forward", "mse_forward")
     dom = max(((op, key, sum(v) / len(v)) for (op, key), v in prof.items() if op in single_kernel_ops),
               key=lambda t: t[2], default=None)
     peaks = {}
@@ -377,11 +392,18 @@ def run_st3d(args):
         op, key, avg_ms = dom
         nbytes = algorithmic_bytes(op, key)
         ach = nbytes / (avg_ms * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the committed `ncu --set full` captures
+        traffic = {
+            ("gram_backward", (8, 64, 262144)): (1024600000, "profiles/r1b_ncu_full.csv: k_gram_tc_bwd<64, NHWC> read 537.0 MB + "
+                                                             "write 487.6 MB"),
+            ("gram_backward_acc_relu", (8, 64, 262144)): TRAFFIC_FUSED_BWD64,
+        }.get((op, key), (None, None))
         roofline = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": 1026100000 if (op, key) == ("gram_backward", (8, 64, 262144)) else None,
-                    "traffic_source": "ncu --set full, profiles/r1_ncu_full_final.csv: dram read 537.0 MB + write 489.1 MB of "
-                                      "k_gram_tc_bwd<64, NHWC> (per launch)",
-                    "kernel": f"{op} {key}: " + ("k_gram_tc_bwd<C> (tcgen05 kind::tf32, TMA, TMEM)" if op == "gram_backward"
+                    "traffic": traffic[0], "traffic_source": traffic[1],
+                    "kernel": f"{op} {key}: " + ("k_gram_tc_bwd<C, NHWC> (tcgen05 kind::tf32, TMA, TMEM; epilogue fused with the "
+                                                 "gradient accumulation and the ReLU backward of the tapped layer)"
+                                                 if op == "gram_backward_acc_relu"
+                                                 else "k_gram_tc_bwd<C> (tcgen05 kind::tf32, TMA, TMEM)" if op.startswith("gram_backward")
                                                  else "k_gram_tc_fwd<C> (tcgen05 kind::tf32, TMA, TMEM)" if op.startswith("gram")
                                                  else "k_mse"),
                     "algorithmic_bytes": nbytes, "avg_ms": avg_ms,
@@ -404,7 +426,9 @@ def run_st3d(args):
         "roofline": roofline, "final_loss": final_loss,
         "stages_ms_per_step": stages, "ops_vs_hbm_roofline": op_table,
         "render_loss_only": {"ms_per_step": mine_ms, "it_per_s": (world / (mine_ms * 1e-3)) if mine_ms > 0 else None,
-                             "note": "sum of libst3d op times (CUDA events) per step; VGG-19 / Adam / autograd glue excluded"},
+                             "note": "sum of libst3d render / Gram / MSE op times (CUDA events) per step; VGG-19 / Adam / "
+                                     "autograd glue excluded"},
+        "vgg_pool_ms_per_step": pool_ms,
     }
 
     if not args.no_extras:

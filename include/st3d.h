@@ -193,8 +193,14 @@ int st3d_gram_mse_forward(const float* feat, const float* target, int B, int Bt,
 
 /* Backward of gram_matrix: grad_feat (B,C,HW) = s * (dG + dG^T) F with s = grad_scale, times the device
  * scalar *grad_scale_dev when that pointer is not NULL (autograd's upstream gradient, applied without
- * a host read); when accumulate != 0 the result is added to grad_feat.  The workspace is the one sized
+ * a host read).  `accumulate` is a set of flags: ST3D_GRAM_ACCUMULATE adds the result to what grad_feat holds
+ * (the gradient that reached this activation through the rest of the network); ST3D_GRAM_RELU_MASK then zeroes
+ * every element whose feat value is <= 0, i.e. applies the backward of the ReLU that produced feat (ATen
+ * threshold_backward) to the sum -- the two elementwise passes autograd would run around the Gram backward
+ * of a tapped VGG activation (style_transfer.py:21-26), fused into its epilogue.  The workspace is the one sized
  * by st3d_gram_workspace_size. */
+#define ST3D_GRAM_ACCUMULATE 1
+#define ST3D_GRAM_RELU_MASK 2
 int st3d_gram_backward(const float* feat, const float* dgram, int B, int C, int64_t HW, float grad_scale,
                        const float* grad_scale_dev, int accumulate, float* grad_feat, void* workspace,
                        size_t workspace_bytes, int precision, int layout, st3d_stream_t stream);

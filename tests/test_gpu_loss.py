@@ -329,3 +329,55 @@ def test_fused_vgg_pools_give_bit_identical_gradients():
     sum((f ** 3).mean() for f in ga.values()).backward()
     sum((f ** 3).mean() for f in gb.values()).backward()
     assert torch.equal(xa2.grad, xb2.grad)
+
+
+@pytest.mark.parametrize("precision", [None, "fp32"])     # None: tcgen05 where the shape allows it (conv5_1 of 64^2 does not)
+def test_style_taps_inside_the_conv_layers_equal_the_feature_walk(precision):
+    """perceptual_loss_of_images evaluates every style tap inside its conv + ReLU layer (Gram backward + gradient
+    accumulation + ReLU mask in one kernel epilogue, ST3D_GRAM_ACCUMULATE | ST3D_GRAM_RELU_MASK); loss and image
+    gradient must be bit-identical to get_features + perceptual_loss_from_features (losses.py:26-42)."""
+    import torchvision
+    from st3d import losses
+    from st3d.vgg import fuse_vgg_features
+    torch.manual_seed(2)
+    vgg = torchvision.models.vgg19(weights=None).features.eval().cuda()
+    for p in vgg.parameters():
+        p.requires_grad_(False)
+    model = fuse_vgg_features(vgg, channels_last=True)
+    x = torch.rand(2, 3, 64, 64, device="cuda").contiguous(memory_format=torch.channels_last)
+    style = torch.rand(1, 3, 64, 64, device="cuda").contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        content = losses.get_features(torch.rand_like(x), model, {"21": losses.CONTENT_LAYER})[losses.CONTENT_LAYER]
+    grams = losses.style_targets(style, model, precision)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    la = losses.perceptual_loss_of_images(xa, model, content, grams, 1e6, 1.0, precision)
+    lb = losses.perceptual_loss_from_features(losses.get_features(xb, model), content, grams, 1e6, 1.0, precision)
+    assert torch.equal(la, lb)
+    la.backward()
+    lb.backward()
+    assert torch.equal(xa.grad, xb.grad)
+    # an unfused model takes the feature-walk route and still agrees to rounding
+    xc = x.clone().requires_grad_(True)
+    lc = losses.perceptual_loss_of_images(xc, vgg.to(memory_format=torch.channels_last), content, grams, 1e6, 1.0, precision)
+    lc.backward()
+    assert _relerr(lc, lb) <= 1e-5 and _relerr(xc.grad, xb.grad) <= 1e-3
+
+
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+@pytest.mark.parametrize("precision", ["tf32", "fp32"])
+@pytest.mark.parametrize("C,H,W", [(64, 24, 20), (256, 16, 8), (512, 16, 16)])
+def test_gram_backward_accumulate_and_relu_mask_flags(layout, precision, C, H, W):
+    ops = _ops()
+    gen = torch.Generator(device="cuda").manual_seed(C + H)
+    f = torch.relu(torch.randn(2, C, H, W, device="cuda", generator=gen))
+    chain = torch.randn(2, C, H, W, device="cuda", generator=gen)
+    if layout == "nhwc":
+        f, chain = f.contiguous(memory_format=torch.channels_last), chain.contiguous(memory_format=torch.channels_last)
+    dg = torch.randn(2, C, C, device="cuda", generator=gen) * 1e-2
+    plain = ops.gram_backward(f, dg, 0.5, precision=precision)
+    want = torch.ops.aten.threshold_backward(chain + plain, f, 0.0)
+    got = ops.gram_backward(f, dg, 0.5, out=chain.clone(memory_format=torch.preserve_format), accumulate=True,
+                            precision=precision, relu_mask=True)
+    assert torch.equal(got, want)
+    assert torch.equal(ops.gram_backward(f, dg, 0.5, precision=precision, relu_mask=True),
+                       torch.ops.aten.threshold_backward(plain, f, 0.0))
