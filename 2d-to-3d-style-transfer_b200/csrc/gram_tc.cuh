@@ -91,6 +91,14 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// per-thread asynchronous 16-byte copies global -> shared (the fused backward epilogue prefetches with them)
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---- CTA-pair (cta_group::2) variants: two CTAs of a cluster on one TPC share every MMA ----------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -413,12 +421,17 @@ struct BwdCfg {
     static constexpr int F_BYTES = 4 * 4096;      // four [32 j][32 x] boxes = 128 x's
     static constexpr int S_BYTES = C * 128;       // [C rows c][32 j]
     static constexpr int STAGE_BYTES = F_BYTES + S_BYTES;
-    static constexpr int STAGES = C == 64 ? 8 : (C == 128 ? 6 : (C == 256 ? 4 : 2));
+    // C <= 128 (the HBM-bound layers): the fused epilogue (ST3D_GRAM_ACCUMULATE / ST3D_GRAM_RELU_MASK) prefetches the
+    // incoming gradient and the mask values through a per-warp cp.async ring, RING_SLOTS batches of 8 KB deep
+    static constexpr int RING_SLOTS = C <= 128 ? 3 : 0;
+    static constexpr int RING_BYTES = 4 * RING_SLOTS * 8192;
+    static constexpr int STAGES = C == 64 ? 4 : (C == 128 ? 3 : (C == 256 ? 4 : 2));
     static constexpr int KB = C / 32;             // k-blocks (32 channels j each) per chunk
     static constexpr int S_BOX_ROWS = C < 256 ? C : 256;
     static constexpr int S_BOXES = C / S_BOX_ROWS;
     static constexpr int TR_FLOATS = 4 * 32 * 36;  // NHWC epilogue transpose tiles (one per epilogue warp)
-    static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + TR_FLOATS * 4 + (2 * STAGES + 2 * ACC) * 8 + 16;
+    static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + TR_FLOATS * 4 + RING_BYTES +
+                                   (2 * STAGES + 2 * ACC) * 8 + 16;
 };
 
 // NHWC = false: A = F^T tile from rows j of (B, C, HW): MN-major, 32-byte-atom swizzle, four [32 j][32 x] boxes.
@@ -433,7 +446,8 @@ k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* stages = smem;
     float* tr_scratch = reinterpret_cast<float*>(smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tr_scratch + Cfg::TR_FLOATS);
+    uint8_t* ring = reinterpret_cast<uint8_t*>(tr_scratch + Cfg::TR_FLOATS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + Cfg::RING_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 2 * Cfg::ACC);
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + Cfg::STAGES),
                    accf0 = smem_u32(bars + 2 * Cfg::STAGES), acce0 = smem_u32(bars + 2 * Cfg::STAGES + Cfg::ACC);
@@ -522,6 +536,37 @@ k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__
         const int q = warp & 3;
         uint32_t li = 0;
         float r[32];
+        // Fused tail, C <= 128: batch k = (k / G)-th item of this CTA, channel group k % G.  The warp keeps
+        // RING_SLOTS - 1 batches of its own operands (old gradient, mask values: 8 x 16 B of each per lane) in
+        // flight with cp.async, so the HBM round trip of the read-modify-write is paid once, not per batch.
+        constexpr int G = C / 32;
+        constexpr bool kRing = NHWC && Cfg::RING_SLOTS > 0;
+        const bool use_ring = kRing && accumulate != 0;
+        const uint32_t ring_q = smem_u32(ring) + (uint32_t)q * (Cfg::RING_SLOTS * 8192);
+        const uint32_t my_items = blockIdx.x < items ? (uint32_t)((items - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+        const uint32_t total_k = my_items * G;
+        auto prefetch = [&](uint32_t k) {
+            if (k < total_k) {
+                const int64_t it2 = blockIdx.x + (int64_t)(k / G) * gridDim.x;
+                const int64_t xw2 = (it2 % chunks) * 128 + q * 32;
+                const int64_t off = ((it2 / chunks) * HW + xw2) * C + (int)(k % G) * 32 + 4 * (lane & 7);
+                const uint32_t slot = ring_q + (k % (Cfg::RING_SLOTS > 0 ? Cfg::RING_SLOTS : 1)) * 8192 + lane * 16;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int t = 4 * i + (lane >> 3);
+                    if (xw2 + t < HW) {
+                        if (accumulate & 1) cp_async16(slot + i * 512, grad_feat + off + (int64_t)t * C);
+                        if (accumulate & 2) cp_async16(slot + 4096 + i * 512, feat + off + (int64_t)t * C);
+                    }
+                }
+            }
+            cp_async_commit();  // an empty group keeps the group count in step with k
+        };
+        uint32_t kbatch = 0;
+        if (use_ring) {
+#pragma unroll
+            for (int d = 0; d < Cfg::RING_SLOTS - 1; ++d) prefetch((uint32_t)d);
+        }
         for (int64_t item = blockIdx.x; item < items; item += gridDim.x, ++li) {
             const uint32_t a = li % Cfg::ACC, aph = (li / Cfg::ACC) & 1;
             const int b = (int)(item / chunks);
@@ -531,6 +576,10 @@ k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__
             float* out = NHWC ? grad_feat + ((int64_t)b * HW + x) * C : grad_feat + (int64_t)b * C * HW + x;
 #pragma unroll 1
             for (int c0 = 0; c0 < C; c0 += 32) {
+                if (use_ring) {  // batch kbatch is the oldest of the RING_SLOTS - 1 groups in flight once this one is queued
+                    prefetch(kbatch + Cfg::RING_SLOTS - 1);
+                    cp_async_wait<(Cfg::RING_SLOTS > 0 ? Cfg::RING_SLOTS - 1 : 0)>();
+                }
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * C + c0), r);
                 if (NHWC) {
                     // r[j] = D[pixel row = lane][channel c0 + j].  Transpose through padded shared memory so that
@@ -557,14 +606,23 @@ k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__
                         // array could not be hoisted over it)
                         float4 oldv[8], fv[8];
                         const float* fw = feat + (ow - grad_feat);
+                        const uint8_t* slot = ring + ((size_t)q * (kRing ? Cfg::RING_SLOTS : 1) +
+                                                      kbatch % (kRing ? Cfg::RING_SLOTS : 1)) * 8192 + lane * 16;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int t = 4 * i + (lane >> 3);
                             const bool ok = xw + t < HW;
-                            oldv[i] = (ok && (accumulate & 1)) ? *reinterpret_cast<const float4*>(ow + (int64_t)t * C)
-                                                               : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                            fv[i] = (ok && (accumulate & 2)) ? __ldg(reinterpret_cast<const float4*>(fw + (int64_t)t * C))
-                                                             : make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+                            if (use_ring) {  // this lane's own copies, complete after cp_async_wait above
+                                oldv[i] = (ok && (accumulate & 1)) ? *reinterpret_cast<const float4*>(slot + i * 512)
+                                                                   : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                                fv[i] = (ok && (accumulate & 2)) ? *reinterpret_cast<const float4*>(slot + 4096 + i * 512)
+                                                                 : make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+                            } else {
+                                oldv[i] = (ok && (accumulate & 1)) ? *reinterpret_cast<const float4*>(ow + (int64_t)t * C)
+                                                                   : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                                fv[i] = (ok && (accumulate & 2)) ? __ldg(reinterpret_cast<const float4*>(fw + (int64_t)t * C))
+                                                                 : make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+                            }
                         }
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -583,6 +641,7 @@ k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__
                             }
                         }
                     }
+                    ++kbatch;
                     __syncwarp();
                 } else if (x < HW) {
                     const float* fin = feat + (out - grad_feat);

@@ -432,6 +432,8 @@ def gram_backward(feat, dgram, grad_scale: float = 1.0, out=None, accumulate=Fal
         out = torch.empty_like(f)           # preserve_format: channels_last stays channels_last
         accumulate = False
     else:
+        if layout == FEAT_NCHW and out.dim() == 4 and out.is_contiguous() and out.shape == feat.shape:
+            out = out.view(B, C, HW)        # same storage: the kernel reads and writes (B, C, HW)
         if out.shape != f.shape or out.stride() != f.stride() or out.dtype != torch.float32 or not out.is_cuda:
             raise ValueError("gram_backward: `out` must match the (normalised) feature tensor in shape and strides")
     ws, nbytes = _gram_ws(B, C, HW, f.device)

@@ -211,7 +211,8 @@ def run_reference(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 # filled from the round's ncu capture (profiles/): (bytes per launch, source) of the fused Gram backward at conv1_1
-TRAFFIC_FUSED_BWD64 = (None, None)
+TRAFFIC_FUSED_BWD64 = (1587200000, "profiles/r1b_ncu_full_gram_bwd_fused.csv: k_gram_tc_bwd<64, NHWC> with ST3D_GRAM_ACCUMULATE | "
+                                   "ST3D_GRAM_RELU_MASK, dram read 1092.5 MB + write 494.7 MB (the mask's second read of F hits L2)")
 
 
 def algorithmic_bytes(op, key, tex=512):
@@ -222,9 +223,9 @@ def algorithmic_bytes(op, key, tex=512):
     if op == "render_backward":     # grad rgb + saved pix_to_face per pixel + face records + grad_texture
         N, H, W, F = key
         return N * H * W * (12 + 4) + N * F * 48 + tex * tex * 12
-    if op.startswith("gram_backward"):   # read F, write dF; fused tail: + read the incoming gradient, + read F for the mask
-        B, C, HW = key
-        return (2 + ("_acc" in op) + ("_relu" in op)) * B * C * HW * 4
+    if op.startswith("gram_backward"):   # read F, write dF; fused tail: + read the incoming gradient (the ReLU mask re-reads
+        B, C, HW = key                   # F, which an ideal kernel would still hold: no extra algorithmic bytes)
+        return (2 + ("_acc" in op)) * B * C * HW * 4
     if op in ("gram_forward", "gram_mse_forward"):   # read F, write G (+dG)
         B, C, HW = key
         return B * C * HW * 4 + B * C * C * 4

@@ -352,7 +352,7 @@ def test_style_taps_inside_the_conv_layers_equal_the_feature_walk(precision):
     xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
     la = losses.perceptual_loss_of_images(xa, model, content, grams, 1e6, 1.0, precision)
     lb = losses.perceptual_loss_from_features(losses.get_features(xb, model), content, grams, 1e6, 1.0, precision)
-    assert torch.equal(la, lb)
+    assert _relerr(la, lb) <= 1e-6          # the per-layer MSE sums use float atomics: equal up to summation order
     la.backward()
     lb.backward()
     assert torch.equal(xa.grad, xb.grad)
