@@ -545,18 +545,30 @@ k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__
         const uint32_t ring_q = smem_u32(ring) + (uint32_t)q * (Cfg::RING_SLOTS * 8192);
         const uint32_t my_items = blockIdx.x < items ? (uint32_t)((items - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
         const uint32_t total_k = my_items * G;
+        const uint32_t chunks32 = (uint32_t)chunks;  // items = B * chunks < 2^31 (checked by the launcher)
         auto prefetch = [&](uint32_t k) {
             if (k < total_k) {
-                const int64_t it2 = blockIdx.x + (int64_t)(k / G) * gridDim.x;
-                const int64_t xw2 = (it2 % chunks) * 128 + q * 32;
-                const int64_t off = ((it2 / chunks) * HW + xw2) * C + (int)(k % G) * 32 + 4 * (lane & 7);
+                const uint32_t it2 = blockIdx.x + (k / G) * gridDim.x;
+                const uint32_t b2 = it2 / chunks32;
+                const int64_t xw2 = (int64_t)(it2 - b2 * chunks32) * 128 + q * 32;
+                // this lane's first row (lane >> 3) and 16-byte column (lane & 7); the eight copies are 4 rows apart
+                const int64_t off = ((int64_t)b2 * HW + xw2 + (lane >> 3)) * C + (int)(k % G) * 32 + 4 * (lane & 7);
                 const uint32_t slot = ring_q + (k % (Cfg::RING_SLOTS > 0 ? Cfg::RING_SLOTS : 1)) * 8192 + lane * 16;
+                const float* po = grad_feat + off;
+                const float* pf = feat + off;
+                if (accumulate == 3 && xw2 + 32 <= HW) {  // the common case: both operands, no ragged last chunk
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int t = 4 * i + (lane >> 3);
-                    if (xw2 + t < HW) {
-                        if (accumulate & 1) cp_async16(slot + i * 512, grad_feat + off + (int64_t)t * C);
-                        if (accumulate & 2) cp_async16(slot + 4096 + i * 512, feat + off + (int64_t)t * C);
+                    for (int i = 0; i < 8; ++i) {
+                        cp_async16(slot + i * 512, po + i * 4 * C);
+                        cp_async16(slot + 4096 + i * 512, pf + i * 4 * C);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (xw2 + 4 * i + (lane >> 3) < HW) {
+                            if (accumulate & 1) cp_async16(slot + i * 512, po + i * 4 * C);
+                            if (accumulate & 2) cp_async16(slot + 4096 + i * 512, pf + i * 4 * C);
+                        }
                     }
                 }
             }
@@ -569,8 +581,9 @@ k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__
         }
         for (int64_t item = blockIdx.x; item < items; item += gridDim.x, ++li) {
             const uint32_t a = li % Cfg::ACC, aph = (li / Cfg::ACC) & 1;
-            const int b = (int)(item / chunks);
-            const int64_t x = (item % chunks) * 128 + q * 32 + lane;
+            const int b = (int)((uint32_t)item / chunks32);
+            const int64_t xchunk = (int64_t)((uint32_t)item - (uint32_t)b * chunks32) * 128;
+            const int64_t x = xchunk + q * 32 + lane;
             mbar_wait(accf0 + 8 * a, aph);
             tc_fence_after();
             float* out = NHWC ? grad_feat + ((int64_t)b * HW + x) * C : grad_feat + (int64_t)b * C * HW + x;
@@ -590,7 +603,7 @@ k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__
                         *reinterpret_cast<float4*>(sc + lane * 36 + 4 * j) =
                             make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
                     __syncwarp();
-                    const int64_t xw = (item % chunks) * 128 + q * 32;  // first pixel row of this warp
+                    const int64_t xw = xchunk + q * 32;  // first pixel row of this warp
                     float* ow = grad_feat + ((int64_t)b * HW + xw) * C + c0 + 4 * (lane & 7);
                     if (accumulate == 0) {
 #pragma unroll
@@ -599,6 +612,23 @@ k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__
                             if (xw + t < HW)
                                 *reinterpret_cast<float4*>(ow + (int64_t)t * C) =
                                     *reinterpret_cast<const float4*>(sc + t * 36 + 4 * (lane & 7));
+                        }
+                    } else if (use_ring && accumulate == 3 && xw + 32 <= HW) {
+                        // fused tail, common case: operands from this lane's ring slot, constant offsets throughout
+                        const float4* so = reinterpret_cast<const float4*>(
+                            ring + ((size_t)q * (kRing ? Cfg::RING_SLOTS : 1) + kbatch % (kRing ? Cfg::RING_SLOTS : 1)) * 8192 +
+                            lane * 16);
+                        const float* st = sc + (lane >> 3) * 36 + 4 * (lane & 7);
+                        float* og = ow + (int64_t)(lane >> 3) * C;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float4 v = *reinterpret_cast<const float4*>(st + i * 4 * 36);
+                            const float4 o = so[i * 32], f = so[256 + i * 32];
+                            v.x = f.x <= 0.0f ? 0.0f : v.x + o.x;  // ReLU backward of (incoming gradient + dF)
+                            v.y = f.y <= 0.0f ? 0.0f : v.y + o.y;
+                            v.z = f.z <= 0.0f ? 0.0f : v.z + o.z;
+                            v.w = f.w <= 0.0f ? 0.0f : v.w + o.w;
+                            *reinterpret_cast<float4*>(og + i * 4 * C) = v;
                         }
                     } else {
                         // fused elementwise tail: all global loads of the eight row groups are issued before the
@@ -1027,6 +1057,7 @@ static int launch_bwd(const float* feat, const GramPlan& p, int accumulate, floa
         attr_done = true;
     }
     const int64_t items = (int64_t)p.B * ((p.HW + 127) / 128);
+    ST3D_REQUIRE(items < (1ll << 31), "gram_backward: B * ceil(HW / 128) = %lld work items exceed 2^31", (long long)items);
     const int grid = (int)std::min<int64_t>(items, 148);
     k_gram_tc_bwd<C, NHWC><<<grid, kThreads, Cfg::SMEM, s>>>(map_f, map_s, feat, grad_feat, p.B, p.HW, accumulate);
     ST3D_LAUNCH_OK("k_gram_tc_bwd");
