@@ -32,8 +32,8 @@ def style_transfer(initial_optimized_imgs, content_imgs, style_imgs, model, step
     images = initial_optimized_imgs.clone().detach().to(device).requires_grad_(True)
     optimizer = torch.optim.Adam([images], lr=lr)
     for _ in tqdm(range(steps), desc="2D Style Transfer"):
-        feats = _losses.get_features(images, model)
-        loss = _losses.perceptual_loss_from_features(feats, content_feat, grams, style_weight, content_weight)
+        # features + loss in one walk: style taps are evaluated inside their conv layers on a fused model (st3d.vgg)
+        loss = _losses.perceptual_loss_of_images(images, model, content_feat, grams, style_weight, content_weight)
         optimizer.zero_grad()
         loss.backward()
         optimizer.step()

@@ -1,12 +1,16 @@
-// raster.cu -- tile-binned multi-view rasterizer with fused texture / shade / blend epilogue.
+// raster.cu -- multi-view rasterizer with fused texture / shade / blend epilogue.
 //
-// Replaces PyTorch3D's MeshRasterizer.transform, rasterize_meshes
+// Replaces PyTorch3D's MeshRasterizer.transform, clip_faces, rasterize_meshes
 // (coarse + fine kernels), interpolate_face_attributes, TexturesUV/TexturesVertex.sample_textures,
 // phong_shading with AmbientLights and softmax_rgb_blend as reached from the reference through
-// utils.py:65-77 (render_meshes) / first_approach.py:106-114.  Not a port: one setup pass builds a
-// 48-byte record per (view, face) and exact-size 16x16-pixel tile bins; one fine pass stages each
-// tile's faces in shared memory, tests them with one-rounding fp32 edge functions (bit-identical to
-// oracle/raster_oracle.c) and shades the winning face in the same kernel.
+// utils.py:65-77 (render_meshes) / first_approach.py:106-114.  Not a port.  Two paths share the per-face record
+// (48 bytes: projected coordinates, area, exact integer pixel ranges) and the one-rounding fp32 arithmetic that
+// makes pix_to_face bit-identical to oracle/raster_oracle.c:
+//   * hard rasterization (blur_radius == 0, faces_per_pixel == 1 -- the reference's configuration), section 5b:
+//     no bins; every (face, pixel) candidate goes straight to a global 64-bit z-buffer with atomicMin on
+//     (depth bits, face id), then one thread per pixel resolves its winner and shades it;
+//   * the general path (blur > 0 or K <= 8), sections 2-5: exact-size 16x16-pixel tile bins, a fine pass that
+//     stages each tile's faces in shared memory and keeps the K best fragments in registers.
 #include <float.h>
 
 #include <type_traits>
