@@ -330,3 +330,35 @@ def test_loss_trajectory_matches_oracle_loop(cow):
             assert abs(g - w) <= 5e-3 * abs(w), (got, want)
     finally:
         torch.backends.cudnn.allow_tf32 = prev
+
+
+def test_2d_style_transfer_loop_follows_the_oracle():
+    """`style_transfer()` (style_transfer.py:38-84) through compat/: three Adam steps on a small
+    batch end at the images the reference's loop body (oracle: torch autograd on the CPU, same VGG weights) produces."""
+    import style_transfer as st
+    from st3d.vgg import fuse_vgg_features
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(4)
+    init, content, style = (torch.rand(2, 3, 64, 64, generator=gen) for _ in range(3))
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        model = fuse_vgg_features(_vgg(dev), channels_last=True)
+        got = st.style_transfer(init.to(dev), content.to(dev), style.to(dev), model, steps=3, style_weight=1e6,
+                                content_weight=1, lr=0.003)
+        assert got.requires_grad and got.shape == init.shape
+        vgg_cpu = _vgg("cpu")
+        imgs = init.clone().requires_grad_(True)
+        adam = torch.optim.Adam([imgs], lr=0.003)
+        losses = []
+        for _ in range(3):
+            loss = lo.perceptual_loss(imgs, content, style, vgg_cpu, 1e6, 1.0)
+            adam.zero_grad()
+            loss.backward()
+            adam.step()
+            losses.append(loss.item())
+        # Adam's first steps move every pixel by ~lr whatever the gradient's size: positions agree to a fraction of a step
+        assert (got.detach().cpu() - imgs.detach()).abs().max().item() <= 0.2 * 0.003 * 3
+        assert (got.detach().cpu() - init).abs().max().item() >= 0.003          # and the loop did move the images
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
