@@ -96,6 +96,8 @@ class StyleOptimizer:
         # spends 7 launches / 0.19 ms per step on a 512^2 texture
         self.optimizer = torch.optim.Adam(params, lr=lr, fused=True)
         self._cache = {}
+        self._copy_stream = None
+        self.images_ready: Optional[torch.cuda.Event] = None
         self._edges = None
         self.last_images: Optional[torch.Tensor] = None
 
@@ -128,8 +130,25 @@ class StyleOptimizer:
                 + w["mesh_laplacian_smoothing_weight"] * ml.laplacian_smoothing(self.verts, self.faces, edges=self._edges)
                 + w["mesh_normal_consistency_weight"] * ml.normal_consistency(self.verts, self.faces))
 
-    def step(self, R: torch.Tensor, T: torch.Tensor, style_img: torch.Tensor) -> torch.Tensor:
-        """One optimisation iteration over the views (R, T) held by this rank; returns the loss (device scalar)."""
+    def _export_images(self, images: torch.Tensor, images_out: torch.Tensor) -> None:
+        """Device -> pinned-host copy of this step's renders on a side stream, so that it overlaps the VGG passes
+        that follow instead of trailing the step (the reference dumps every view every step,
+        second_approach.py:183-185).  `self.images_ready` is the event to wait on before reading `images_out`."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=images.device)
+        cur = torch.cuda.current_stream(images.device)
+        self._copy_stream.wait_stream(cur)
+        with torch.cuda.stream(self._copy_stream):
+            images_out.copy_(images, non_blocking=True)
+            self.images_ready = torch.cuda.Event()
+            self.images_ready.record(self._copy_stream)
+        images.record_stream(self._copy_stream)
+
+    def step(self, R: torch.Tensor, T: torch.Tensor, style_img: torch.Tensor,
+             images_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One optimisation iteration over the views (R, T) held by this rank; returns the loss (device scalar).
+        images_out: optional pinned host tensor (B,3,H,W) that receives this step's rendered views asynchronously
+        (wait on `self.images_ready` before reading it)."""
         self.optimizer.zero_grad(set_to_none=True)
         key = (R.data_ptr(), T.data_ptr(), style_img.data_ptr())
         if self.cache_constants and self._cache.get("key") == key:
@@ -143,6 +162,8 @@ class StyleOptimizer:
             if self.cache_constants:
                 self._cache = dict(key=key, content_feat=content_feat, grams=grams)
         current_imgs, _ = self._render(self.verts, self.colour, R, T)                           # :165
+        if images_out is not None:
+            self._export_images(current_imgs.detach(), images_out)
         loss = losses.perceptual_loss_of_images(self._nn_input(current_imgs), self.vgg, content_feat, grams,
                                                 self.style_weight, self.content_weight, self.precision)
         if self.target != "texture":                                                            # losses.py:108-124

@@ -445,9 +445,10 @@ def run_st3d(args):
             d_style.copy_(h_style, non_blocking=True)
             d_R.copy_(h_R, non_blocking=True)
             d_T.copy_(h_T, non_blocking=True)
-            l = opt2.step(d_R, d_T, d_style)
-            h_img.copy_(opt2.last_images, non_blocking=True)     # the reference dumps every view every step
-            return float(l)                                      # loss.item(): second_approach.py:190
+            l = opt2.step(d_R, d_T, d_style, images_out=h_img)   # the reference dumps every view every step; the
+            loss = float(l)                                      # device->host copy runs beside the VGG passes
+            opt2.images_ready.synchronize()                      # loss.item(): second_approach.py:190
+            return loss
 
         for _ in range(3):
             e2e_step()
@@ -461,7 +462,8 @@ def run_st3d(args):
         d2h = h_img.numel() * 4 + 4
         out["e2e"] = {"value": world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                       "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
-                      "api": "st3d.optimize.TextureStyleOptimizer.step(R, T, style) with pinned host inputs"}
+                      "api": "st3d.optimize.TextureStyleOptimizer.step(R, T, style, images_out=pinned) with pinned host inputs; "
+                             "the loss is read on the host every step"}
         # ---- variant: constant content/style features cached (loop hygiene the reference lacks) ---------
         opt3 = make(True)
         for _ in range(3):

@@ -362,3 +362,22 @@ def test_2d_style_transfer_loop_follows_the_oracle():
         assert (got.detach().cpu() - init).abs().max().item() >= 0.003          # and the loop did move the images
     finally:
         torch.backends.cudnn.allow_tf32 = prev
+
+
+def test_step_exports_rendered_views_asynchronously(cow):
+    """`step(..., images_out=pinned)` copies the step's renders to the host on a side stream: after `images_ready`
+    the host buffer holds exactly `last_images`."""
+    from st3d.optimize import TextureStyleOptimizer
+    dev = torch.device("cuda:0")
+    R, T = ro.random_cameras(2, generator=torch.Generator().manual_seed(3))
+    style = torch.rand(1, 3, S, S, generator=torch.Generator().manual_seed(4))
+    tex0 = torch.rand(S, S, 3, generator=torch.Generator().manual_seed(5))
+    opt = TextureStyleOptimizer(cow["verts"].to(dev), cow["faces"].to(dev), cow["verts_uvs"].to(dev),
+                                cow["faces_uvs"].to(dev), tex0.to(dev), _vgg(dev), S, lr=0.01)
+    host = torch.zeros(2, 3, S, S).pin_memory()
+    for _ in range(2):
+        loss = opt.step(R.to(dev), T.to(dev), style.to(dev), images_out=host)
+        opt.images_ready.synchronize()
+        assert torch.isfinite(loss).item()
+        torch.cuda.synchronize()
+        assert torch.equal(host, opt.last_images.cpu())
