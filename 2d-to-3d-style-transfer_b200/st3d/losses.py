@@ -59,6 +59,44 @@ def blended_style_targets(style_imgs, weights, model, precision=None):
     return {k: (g * w).sum(dim=0, keepdim=True) for k, g in grams.items()}
 
 
+def content_and_style_constants(content_imgs, style_imgs, model, precision=None, style_weights=None):
+    """The two constant branches of losses.py:18-25 in ONE walk of the VGG: the content images and the style image(s)
+    share a batch up to conv4_2 (a one-image pass leaves most of the GPU idle), the style image(s) continue alone to
+    conv5_1.  Returns (content feature conv4_2 of the content images, {layer: style Gram (J|1,C,C)}).
+    style_weights: blend the J style Grams into one target per layer (BASELINE configs[3])."""
+    if content_imgs.shape[1:] != style_imgs.shape[1:]:
+        with torch.no_grad():
+            content = get_features(content_imgs, model, {"21": CONTENT_LAYER})[CONTENT_LAYER]
+        grams = (blended_style_targets(style_imgs, style_weights, model, precision) if style_weights is not None
+                 else style_targets(style_imgs, model, precision))
+        return content, grams
+    B = content_imgs.shape[0]
+    with torch.no_grad():
+        x = torch.cat([content_imgs, style_imgs], dim=0)
+        if getattr(model, "_st3d_channels_last", False) and x.is_cuda:
+            x = x.contiguous(memory_format=torch.channels_last)
+        content, grams, done = None, {}, False
+        for name, module in model._modules.items():
+            if done and not ((isinstance(module, torch.nn.ReLU) and module.inplace) or isinstance(module, torch.nn.Identity)):
+                break
+            x = module(x)
+            if done:
+                break
+            layer = VGG_TAPS.get(name)
+            if layer == CONTENT_LAYER:
+                content = x[:B]
+                x = x[B:]                       # only the style image(s) go on to conv5_1
+            elif layer is not None:
+                grams[layer] = Fn.gram_matrix(x[B:] if content is None else x, precision)
+            done = name == str(LAST_TAP)
+        if style_weights is not None:
+            w = torch.as_tensor(style_weights, dtype=torch.float32, device=style_imgs.device).reshape(-1, 1, 1)
+            if w.shape[0] != style_imgs.shape[0]:
+                raise ValueError("one weight per style image")
+            grams = {k: (g * w).sum(dim=0, keepdim=True) for k, g in grams.items()}
+    return content, grams
+
+
 def perceptual_loss_from_features(cur_feats, content_feat, style_grams, style_weight=1e6, content_weight=1.0,
                                   precision=None):
     """losses.py:28-42 given the three sets of features."""

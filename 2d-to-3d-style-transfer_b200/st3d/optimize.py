@@ -156,9 +156,9 @@ class StyleOptimizer:
         else:
             with torch.no_grad():
                 content_imgs, _ = self._render(self.verts0, self.content_colour, R, T)         # second_approach.py:160
-                content_feat = losses.get_features(self._nn_input(content_imgs), self.vgg,
-                                                   {"21": losses.CONTENT_LAYER})[losses.CONTENT_LAYER]
-            grams = self._style_targets(style_img)                                              # losses.py:19-25
+            # losses.py:18-25: content features + style Grams, one VGG walk for both constant branches
+            content_feat, grams = losses.content_and_style_constants(content_imgs, style_img, self.vgg, self.precision,
+                                                                     self.style_weights)
             if self.cache_constants:
                 self._cache = dict(key=key, content_feat=content_feat, grams=grams)
         current_imgs, _ = self._render(self.verts, self.colour, R, T)                           # :165
