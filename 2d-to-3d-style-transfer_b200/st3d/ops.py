@@ -98,7 +98,20 @@ _capacity_hint: dict = {}
 _free_hosts: list = []      # recycled pinned header buffers (cudaHostAlloc costs milliseconds; never allocate per call)
 
 
+def _capturing() -> bool:
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
+
+def read_header(ws: torch.Tensor):
+    """Synchronous read of a raster workspace header (for callers that replay captured graphs and therefore own
+    the workspace): (entries needed, overflow flag, unsupported-clip flag)."""
+    h = ws[: WS_HEADER_INTS * 4].view(torch.int32).cpu()
+    return int(h[0]), int(h[1]), int(h[4])
+
+
 def _watch_header(ws: torch.Tensor, key) -> None:
+    if _capturing():        # a captured call is replayed without Python: its owner checks the header (read_header)
+        return
     host = _free_hosts.pop() if _free_hosts else torch.empty(WS_HEADER_INTS, dtype=torch.int32, pin_memory=True)
     host.copy_(ws[: WS_HEADER_INTS * 4].view(torch.int32), non_blocking=True)
     ev = torch.cuda.Event()
@@ -110,6 +123,8 @@ def _watch_header(ws: torch.Tensor, key) -> None:
 
 def poll_overflow(block: bool = False) -> None:
     """Raise if an earlier raster call overflowed its tile-bin pair buffer."""
+    if _capturing():
+        return
     keep = []
     for ev, host, key in _pending:
         if block:

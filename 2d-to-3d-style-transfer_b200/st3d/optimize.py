@@ -191,3 +191,59 @@ class TextureStyleOptimizer(StyleOptimizer):
                          target="texture", lr=lr, style_weight=style_weight, content_weight=content_weight,
                          precision=precision, cache_constants=cache_constants, world_size=world_size, group=group,
                          channels_last=channels_last, fuse_conv_relu=fuse_conv_relu)
+
+
+class GraphedTextureFit:
+    """The texture-fit loop of "approach 1" (first_approach.py:191-213, `texture` target: render -> masked MSE against
+    the target renders -> backward -> Adam) with the whole iteration captured in ONE CUDA graph.
+
+    At the reference's own size (1 view x 256^2, BASELINE configs[0]) an iteration is ~10 short kernels: launched
+    one by one from Python the loop is bound by the host (~1 ms / iteration); replayed as a graph it costs the
+    kernels' own time.  Cameras and target images are fixed for the life of the object (the reference re-uses the
+    same views every epoch); `step()` replays the graph and returns the loss tensor of that iteration."""
+
+    def __init__(self, verts, faces, verts_uvs, faces_uvs, texture, R, T, target_images, image_size, lr: float = 0.01,
+                 warmup: int = 3):
+        from . import ops
+        dev = verts.device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedTextureFit needs CUDA tensors: libst3d has no CPU path")
+        self.verts = verts.detach().float().contiguous()
+        self.faces = faces.to(torch.int32).contiguous()
+        self.face_uvs = verts_uvs.float()[faces_uvs.long()].contiguous()
+        self.texture = texture.detach().clone().float().contiguous().requires_grad_(True)
+        self.R, self.T = R.detach().float().contiguous().to(dev), T.detach().float().contiguous().to(dev)
+        self.target = target_images.detach().float().contiguous().to(dev)
+        self.image_size = image_size
+        # capturable: the step counter lives on the device, so the update can be replayed
+        self.optimizer = torch.optim.Adam([self.texture], lr=lr, capturable=True, fused=True)
+        self._workspaces = []
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):               # warm-up outside the capture (lazy initialisation, autotuning)
+            for _ in range(max(1, warmup)):
+                self._iteration()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        ops.poll_overflow(block=True)
+        self.graph = torch.cuda.CUDAGraph()
+        self.optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self.loss = self._iteration()
+        self.iterations = max(1, warmup)
+
+    def _iteration(self):
+        self.optimizer.zero_grad(set_to_none=True)
+        images, masks, _ = Fn.render_views(self.verts, self.faces, self.R, self.T, self.image_size,
+                                           texture=self.texture, face_uvs=self.face_uvs)
+        loss = Fn.masked_mse_loss(images, self.target, masks)                       # losses.py:71-75
+        loss.backward()
+        self.optimizer.step()
+        self.images = images.detach()
+        return loss.detach()
+
+    def step(self) -> torch.Tensor:
+        """Replays one iteration; the returned tensor (and `self.images`) are overwritten by the next replay."""
+        self.graph.replay()
+        self.iterations += 1
+        return self.loss

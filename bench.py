@@ -275,6 +275,20 @@ def c1_first_approach(dev, steps=200, size=256, run_cpu=True):
     gpu_ms = e0.elapsed_time(e1) / steps
     res = {"workload": "cow texture fit, 1 view x 256^2, masked-MSE loop (first_approach.py:191-213), 200 timed Adam steps",
            "gpu_ms_per_step": gpu_ms, "gpu_it_per_s": 1e3 / gpu_ms, "final_loss": float(loss.detach())}
+    # the same loop with the iteration captured in one CUDA graph (st3d.optimize.GraphedTextureFit): at this size the
+    # eager loop is bound by the host's launch rate, the replayed graph by the kernels
+    from st3d.optimize import GraphedTextureFit
+    fit = GraphedTextureFit(verts, faces, w["verts_uvs"].to(dev), w["faces_uvs"].to(dev), w["texture"].to(dev), Rd, Td, tgt,
+                            size, lr=0.01, warmup=20)
+    torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(steps):
+        gl = fit.step()
+    g1.record()
+    torch.cuda.synchronize()
+    graph_ms = g0.elapsed_time(g1) / steps
+    res.update({"graph_ms_per_step": graph_ms, "graph_it_per_s": 1e3 / graph_ms, "graph_final_loss": float(gl)})
     if run_cpu:
         from oracle import loss_oracle as lo
         from oracle import render_oracle as ro
@@ -296,7 +310,7 @@ def c1_first_approach(dev, steps=200, size=256, run_cpu=True):
                 ts.append(time.perf_counter() - t0)
         cpu_ms = 1e3 * sum(ts) / len(ts)
         res.update({"cpu_ms_per_step": cpu_ms, "cpu_it_per_s": 1e3 / cpu_ms, "cpu_threads": threads,
-                    "speedup": cpu_ms / gpu_ms})
+                    "speedup": cpu_ms / gpu_ms, "graph_speedup": cpu_ms / graph_ms})
     return res
 
 

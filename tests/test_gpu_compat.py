@@ -381,3 +381,35 @@ def test_step_exports_rendered_views_asynchronously(cow):
         assert torch.isfinite(loss).item()
         torch.cuda.synchronize()
         assert torch.equal(host, opt.last_images.cpu())
+
+
+def test_graphed_texture_fit_equals_the_eager_loop(cow):
+    """first_approach.py:191-213 (`texture` target) captured as one CUDA graph per iteration: after ten replays the
+    texture equals the one the eager loop (same kernels launched one by one) produces."""
+    from st3d import functional as Fn
+    from st3d.optimize import GraphedTextureFit
+    dev = torch.device("cuda:0")
+    size = 96
+    R, T = ro.random_cameras(2, generator=torch.Generator().manual_seed(8))
+    target = torch.rand(2, 3, size, size, generator=torch.Generator().manual_seed(9))
+    tex0 = torch.rand(64, 64, 3, generator=torch.Generator().manual_seed(10))
+    verts, faces = cow["verts"].to(dev), cow["faces"].to(dev)
+    fit = GraphedTextureFit(verts, faces, cow["verts_uvs"].to(dev), cow["faces_uvs"].to(dev), tex0.to(dev), R, T, target,
+                            size, lr=0.01, warmup=3)
+    for _ in range(7):
+        loss_g = fit.step().clone()
+    torch.cuda.synchronize()
+    assert fit.iterations == 10
+    tex = tex0.to(dev).clone().requires_grad_(True)
+    adam = torch.optim.Adam([tex], lr=0.01)
+    fuv = cow["verts_uvs"].to(dev)[cow["faces_uvs"].to(dev)]
+    for _ in range(10):
+        adam.zero_grad(set_to_none=True)
+        img, mask, _ = Fn.render_views(verts, faces.int(), R.to(dev), T.to(dev), size, texture=tex, face_uvs=fuv)
+        loss_e = Fn.masked_mse_loss(img, target.to(dev), mask)
+        loss_e.backward()
+        adam.step()
+    torch.cuda.synchronize()
+    assert abs(loss_g.item() - loss_e.item()) <= 1e-5 * abs(loss_e.item()) + 1e-8
+    assert (fit.texture.detach() - tex.detach()).abs().max().item() <= 1e-5
+    assert (fit.texture.detach() - tex0.to(dev)).abs().max().item() >= 0.05      # ten Adam steps of 0.01 did happen
