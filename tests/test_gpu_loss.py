@@ -381,3 +381,33 @@ def test_gram_backward_accumulate_and_relu_mask_flags(layout, precision, C, H, W
     assert torch.equal(got, want)
     assert torch.equal(ops.gram_backward(f, dg, 0.5, precision=precision, relu_mask=True),
                        torch.ops.aten.threshold_backward(plain, f, 0.0))
+
+
+def test_full_size_pool_and_fused_tail_bit_identical_to_torch():
+    """BASELINE configs[1] sizes (8 views x 512^2): the pooling kernels and the fused accumulate + ReLU tail of the
+    Gram backward at conv1_1 / conv2_1 size against torch's own elementwise kernels on the same GPU (selection /
+    one addition per element: bit-identical)."""
+    import torch.nn.functional as F
+    ops = _ops()
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for C, side in ((64, 512), (128, 256)):
+        f = torch.relu(torch.randn(8, C, side, side, device="cuda", generator=gen)).contiguous(memory_format=torch.channels_last)
+        chain = torch.randn(8, C, side, side, device="cuda", generator=gen).contiguous(memory_format=torch.channels_last)
+        dg = torch.randn(8, C, C, device="cuda", generator=gen) * 1e-3
+        plain = ops.gram_backward(f, dg, 1.0)
+        want = torch.ops.aten.threshold_backward(chain + plain, f, 0.0)
+        got = ops.gram_backward(f, dg, 1.0, out=chain, accumulate=True, relu_mask=True)      # in place on `chain`
+        assert got.data_ptr() == chain.data_ptr() and torch.equal(got, want)
+        del plain, want, got, chain
+        xr = f.clone().requires_grad_(True)
+        yr = F.max_pool2d(xr, 2, 2)
+        y = ops.maxpool2x2_forward(f)
+        assert torch.equal(y, yr.detach())
+        g = torch.randn_like(y)
+        (gr,) = torch.autograd.grad(yr, xr, g)
+        assert torch.equal(ops.maxpool2x2_backward(f, g, relu_mask=False), gr)
+        assert torch.equal(ops.maxpool2x2_backward(f, g, relu_mask=True), torch.ops.aten.threshold_backward(gr, f, 0.0))
+        # conservation: every upstream value lands on exactly one input element
+        assert abs(gr.double().sum().item() - g.double().sum().item()) <= 1e-6 * g.double().abs().sum().item()
+        del xr, yr, y, g, gr, f
+        torch.cuda.empty_cache()

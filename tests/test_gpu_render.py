@@ -443,3 +443,50 @@ def test_near_plane_clipping_fragments_match_oracle(cow, K):
     hit64 = hit.double()
     ((z64 * gz.double() * hit64).sum() + (b64 * gb.double() * hit64[..., None]).sum()).backward()
     _close(fvg.grad, fv64.grad, tol=2e-4, what="grad_face_verts through clipping")
+
+
+def test_full_size_clipped_scene_two_paths_agree(cow):
+    """BASELINE configs[1] size with the near plane cutting the mesh: the fused renderer (clipping inside the
+    kernels) and the Fragments path (torch clip_faces around the operator-boundary rasterizer) must produce the same
+    pix_to_face, and the fused barycentric conversion must put every clipped pixel at a depth >= z_clip."""
+    import st3d.functional as Fn
+    ops = _ops()
+    S = 512
+    R, T = ro.look_at_view_transform(1.0, [10.0, 40.0, -25.0, 70.0, 0.0, -60.0, 25.0, 5.0],
+                                     [20.0, 200.0, 95.0, -130.0, 0.0, 45.0, -45.0, 170.0], at=((0, 0.1, 0.25),))
+    N, Fc = R.shape[0], cow["faces"].shape[0]
+    k00, k11 = ro.fov_scales(60.0)
+    spec = ops.RenderSpec(image_size=(S, S), k00=k00, k11=k11)
+    fuv = cow["verts_uvs"][cow["faces_uvs"]].cuda()
+    tex = torch.rand(128, 128, 3, device="cuda")
+    img, _, p2f, state = ops.render_forward(spec, cow["verts"].cuda(), cow["faces"].cuda(), R.cuda(), T.cuda(),
+                                            face_uvs=fuv, texture=tex)
+    img2, _, p2f2, _ = ops.render_forward(spec, cow["verts"].cuda(), cow["faces"].cuda(), R.cuda(), T.cuda(),
+                                          face_uvs=fuv, texture=tex)
+    torch.cuda.synchronize()
+    ops.poll_overflow(block=True)
+    assert torch.equal(p2f, p2f2) and torch.equal(img, img2), "clipped forward is not deterministic"
+    ndc = ops.transform_verts(cow["verts"].cuda(), R.cuda(), T.cuda(), k00, k11)
+    fv = ndc[:, cow["faces"].cuda()].reshape(N * Fc, 3, 3)
+    behind = (fv[:, :, 2] < 0.5).sum(1)
+    assert (behind == 1).sum() > 100 and (behind == 2).sum() > 100
+    first = torch.arange(N, device="cuda") * Fc
+    frag = Fn.rasterize_meshes(fv, first, torch.full((N,), Fc, device="cuda"), S, 0.0, 1, True, False, False,
+                               z_clip_value=0.5)
+    torch.cuda.synchronize()
+    assert torch.equal(frag[0][..., 0], p2f.long())
+    cov = p2f >= 0
+    assert cov.float().mean().item() > 0.3
+    assert (behind[p2f[cov].long()] == 3).sum().item() == 0           # faces behind the plane are never visible
+    clipped_px = cov & (behind[p2f.clamp(min=0).long()] > 0)
+    assert clipped_px.sum().item() > 1000
+    assert (frag[1][..., 0][clipped_px] >= 0.5 - 1e-4).all()          # nothing nearer than the plane is drawn
+    b = frag[2][..., 0, :][clipped_px]
+    assert (b.sum(-1) - 1).abs().max().item() <= 1e-4
+    # the fused backward through clipped faces is linear in the upstream gradient (texture and vertex gradients)
+    g1, g2 = torch.randn_like(img), torch.randn_like(img)
+    t1, v1, _ = ops.render_backward(state, g1, need_verts=True)
+    t2, v2, _ = ops.render_backward(state, g2, need_verts=True)
+    t12, v12, _ = ops.render_backward(state, g1 + 2 * g2, need_verts=True)
+    _close(t12, t1 + 2 * t2, tol=1e-4, what="clipped backward linearity (texture)")
+    _close(v12, v1 + 2 * v2, tol=2e-3, what="clipped backward linearity (vertices)")
