@@ -192,6 +192,25 @@ __global__ void k_fill(const FaceRec* __restrict__ rec, const int64_t* __restric
         }
 }
 
+// 4b. (clipped scenes of the Fragments path only) order every tile's list by face index.  k_fill claims slots with
+// atomics, so a list comes out in arbitrary order; the K-best result does not care -- except for upstream's
+// de-duplication of the two halves of a clipped quad, which looks at the list built SO FAR and is therefore
+// defined by the order the CPU rasterizer visits faces in (ascending index).  Rank sort, one CTA per tile: a rare
+// path, lists of a few hundred entries.
+__global__ void __launch_bounds__(256)
+k_sort_tile_lists(const int* __restrict__ tile_count, const int* __restrict__ tile_offset, const int* __restrict__ list,
+                  int64_t capacity, int* __restrict__ sorted) {
+    const int t = blockIdx.x;
+    const int base = tile_offset[t];
+    const int n = (int)max((int64_t)0, min((int64_t)tile_count[t], capacity - base));
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int v = list[base + i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += __ldg(list + base + j) < v ? 1 : 0;  // a face appears once per tile
+        sorted[base + rank] = v;
+    }
+}
+
 // -------------------------------------------------------------------------------------------------
 // 5. fine raster (+ fused shade)
 // -------------------------------------------------------------------------------------------------
@@ -212,6 +231,17 @@ struct KBest1 {  // K = 1: everything in registers
         if (h.z < z || (h.z == z && face < f)) {
             z = h.z; f = face; b0 = h.b0; b1 = h.b1; b2 = h.b2; dist = h.dist;
         }
+    }
+    // nb = the other half of a clipped quad (-1: none): a pixel keeps the closer of the two
+    __device__ __forceinline__ void offer(const Hit& h, int face, int nb) {
+        if (nb >= 0 && f == nb) {
+            const float dn = fabsf(h.dist), dk = fabsf(dist);
+            if (dn < dk || (dn == dk && face < nb)) {
+                z = h.z; f = face; b0 = h.b0; b1 = h.b1; b2 = h.b2; dist = h.dist;
+            }
+            return;
+        }
+        offer(h, face);
     }
 };
 
@@ -243,6 +273,42 @@ struct KBest {  // ascending (z, face); empty slots hold (FLT_MAX, INT_MAX)
             }
         }
     }
+    __device__ __forceinline__ void swap_slots(int a, int b) {
+        float t;
+        int ti;
+        t = z[a]; z[a] = z[b]; z[b] = t;
+        ti = f[a]; f[a] = f[b]; f[b] = ti;
+        t = b0[a]; b0[a] = b0[b]; b0[b] = t;
+        t = b1[a]; b1[a] = b1[b]; b1[b] = t;
+        t = b2[a]; b2[a] = b2[b]; b2[b] = t;
+        t = dist[a]; dist[a] = dist[b]; dist[b] = t;
+    }
+    // nb = the other half of a clipped quad (-1: none).  Upstream: if the other half is in the list built so far, the
+    // closer of the two (smaller edge distance; ties: the one met first = lower index) keeps that slot, otherwise the
+    // face is inserted normally.  "So far" makes the rule order-dependent: the tile lists are sorted by face index
+    // for such scenes (k_sort_tile_lists), the order the CPU rasterizer of upstream visits faces in.
+    __device__ __forceinline__ void offer(const Hit& h, int face, int nb) {
+        if (nb >= 0) {
+#pragma unroll
+            for (int s = 0; s < K; ++s) {
+                if (f[s] == nb) {
+                    const float dn = fabsf(h.dist), dk = fabsf(dist[s]);
+                    if (dn < dk || (dn == dk && face < nb)) {
+                        z[s] = h.z; f[s] = face; b0[s] = h.b0; b1[s] = h.b1; b2[s] = h.b2; dist[s] = h.dist;
+                        // one changed key: bubble it to its place in the ascending (z, face) order
+#pragma unroll
+                        for (int i = 0; i < K - 1; ++i) {
+#pragma unroll
+                            for (int j = K - 1; j > 0; --j)
+                                if (less(z[j], f[j], z[j - 1], f[j - 1])) swap_slots(j, j - 1);
+                        }
+                    }
+                    return;
+                }
+            }
+        }
+        offer(h, face);
+    }
 };
 
 // MODE 0: fragments out (K >= 1).  MODE 1: fused shade (K == 1).
@@ -250,9 +316,10 @@ template <int MODE, int K>
 __global__ void __launch_bounds__(256)
 k_fine(const FaceRec* __restrict__ rec, const int* __restrict__ tile_count, const int* __restrict__ tile_offset,
        const int* __restrict__ list, int64_t capacity, int H, int W, int TX, int TY, float blur_radius, int persp,
-       int clip, FragOut fo, ShadeParams sp) {
+       int clip, const int64_t* __restrict__ neighbor, FragOut fo, ShadeParams sp) {
     __shared__ float4 s_e0[kChunk], s_e1[kChunk], s_e2[kChunk];
     __shared__ int4 s_misc[kChunk];
+    __shared__ int s_nb[kChunk];  // clipped_faces_neighbor_idx of the staged faces (-1: none)
 
     const int t = blockIdx.x;
     const int n = t / (TX * TY);
@@ -283,6 +350,7 @@ k_fine(const FaceRec* __restrict__ rec, const int* __restrict__ tile_count, cons
             s_e2[threadIdx.x] = make_float4(v.x0, v.y0, fsub(v.y1, v.y0), fsub(v.x1, v.x0));
             const int zpos = (v.z0 > 0.0f && v.z1 > 0.0f && v.z2 > 0.0f) ? 1 : 0;
             s_misc[threadIdx.x] = make_int4(f, __float_as_int(r.c.z), __float_as_int(r.c.w), zpos);
+            s_nb[threadIdx.x] = neighbor ? (int)neighbor[f] : -1;
         }
         __syncthreads();
         for (int j = 0; j < nc; ++j) {
@@ -303,7 +371,7 @@ k_fine(const FaceRec* __restrict__ rec, const int* __restrict__ tile_count, cons
             if (cand) {
                 const FaceRec r = rec[m.x];
                 Hit h;
-                if (eval_face(px, py, unpack(r), r.c.y, blur_radius, persp != 0, clip != 0, h)) best.offer(h, m.x);
+                if (eval_face(px, py, unpack(r), r.c.y, blur_radius, persp != 0, clip != 0, h)) best.offer(h, m.x, s_nb[j]);
             }
         }
     }
@@ -855,7 +923,8 @@ extern "C" int st3d_transform_verts_forward(const float* verts, const float* R, 
 }
 
 extern "C" int st3d_rasterize_meshes_forward(const float* face_verts, const int64_t* mesh_to_face_first_idx,
-                                             const int64_t* num_faces_per_mesh, int N, int64_t F_total,
+                                             const int64_t* num_faces_per_mesh,
+                                             const int64_t* clipped_faces_neighbor_idx, int N, int64_t F_total,
                                              int64_t max_faces_in_mesh, int H, int W, float blur_radius,
                                              int faces_per_pixel, int bin_size, int max_faces_per_bin,
                                              int perspective_correct, int clip_barycentric_coords, int cull_backfaces,
@@ -897,9 +966,16 @@ extern "C" int st3d_rasterize_meshes_forward(const float* face_verts, const int6
     int rc = run_bins(ws, face_verts, nullptr, mesh_to_face_first_idx, num_faces_per_mesh, N, max_faces_in_mesh, 0, H, W,
                       blur_radius, cull_backfaces, false, -INFINITY, s);
     if (rc != ST3D_OK) return rc;
+    const int* tile_list = ws.list;
+    if (clipped_faces_neighbor_idx) {  // the pair de-duplication is defined by ascending face order (see k_sort_tile_lists)
+        k_sort_tile_lists<<<ws.NT, 256, 0, s>>>(ws.tile_count, ws.tile_offset, ws.list, ws.capacity, ws.list_tile);
+        ST3D_LAUNCH_OK("k_sort_tile_lists");
+        tile_list = ws.list_tile;
+    }
 #define ST3D_FINE(KK)                                                                                            \
-    k_fine<0, KK><<<ws.NT, 256, 0, s>>>(ws.rec, ws.tile_count, ws.tile_offset, ws.list, ws.capacity, H, W, ws.TX,  \
-                                        ws.TY, blur_radius, perspective_correct, clip_barycentric_coords, fo, sp)
+    k_fine<0, KK><<<ws.NT, 256, 0, s>>>(ws.rec, ws.tile_count, ws.tile_offset, tile_list, ws.capacity, H, W, ws.TX, \
+                                        ws.TY, blur_radius, perspective_correct, clip_barycentric_coords,           \
+                                        clipped_faces_neighbor_idx, fo, sp)
     if (K == 1) ST3D_FINE(1);
     else if (K == 2) ST3D_FINE(2);
     else if (K <= 4) {
@@ -964,7 +1040,7 @@ extern "C" int st3d_render_forward(const st3d_render_args* a, st3d_stream_t stre
                       a->cull_backfaces, true, z_clip, s);
     if (rc != ST3D_OK) return rc;
     k_fine<1, 1><<<ws.NT, 256, 0, s>>>(ws.rec, ws.tile_count, ws.tile_offset, ws.list, ws.capacity, a->H, a->W,
-                                           ws.TX, ws.TY, a->blur_radius, 1, 1, fo, sp);
+                                           ws.TX, ws.TY, a->blur_radius, 1, 1, nullptr, fo, sp);
     ST3D_LAUNCH_OK("k_fine");
     return ST3D_OK;
 }

@@ -41,7 +41,7 @@ SIGNATURES = {
     "st3d_transform_verts_forward": (c_i, [c_p, c_p, c_p, c_f, c_f, c_i, c_i64, c_p, c_p]),
     "st3d_transform_verts_backward": (c_i, [c_p, c_p, c_p, c_f, c_f, c_i, c_i64, c_p, c_p, c_p]),
     "st3d_raster_workspace_size": (c_sz, [c_i, c_i64, c_i, c_i, c_i64]),
-    "st3d_rasterize_meshes_forward": (c_i, [c_p, c_p, c_p, c_i, c_i64, c_i64, c_i, c_i, c_f, c_i, c_i, c_i, c_i, c_i,
+    "st3d_rasterize_meshes_forward": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i64, c_i64, c_i, c_i, c_f, c_i, c_i, c_i, c_i, c_i,
                                             c_i, c_p, c_sz, c_p, c_p, c_p, c_p, c_p]),
     "st3d_rasterize_meshes_backward": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i64, c_i, c_i, c_p, c_p]),
     "st3d_interp_face_attrs_forward": (c_i, [c_p, c_p, c_p, c_i64, c_i64, c_i, c_p, c_p]),

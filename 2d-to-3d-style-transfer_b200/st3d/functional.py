@@ -94,9 +94,9 @@ def render_views(verts: torch.Tensor, faces: torch.Tensor, R: torch.Tensor, T: t
 # ------------------------------------------------------------------------------------------------
 class _RasterizeFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, face_verts, first, num, image_size, blur_radius, K, persp, clip, cull):
+    def forward(ctx, face_verts, first, num, image_size, blur_radius, K, persp, clip, cull, neighbor=None):
         p2f, zbuf, bary, dists = ops.rasterize_meshes(face_verts.detach(), first, num, image_size, blur_radius, K, 0, 0,
-                                                      persp, clip, cull)
+                                                      persp, clip, cull, clipped_faces_neighbor_idx=neighbor)
         ctx.save_for_backward(face_verts.detach(), p2f)
         ctx.flags = (persp, clip)
         ctx.mark_non_differentiable(p2f)
@@ -107,7 +107,7 @@ class _RasterizeFn(torch.autograd.Function):
         face_verts, p2f = ctx.saved_tensors
         g = ops.rasterize_meshes_backward(face_verts, p2f, g_zbuf.contiguous(), g_bary.contiguous(),
                                           g_dists.contiguous(), *ctx.flags)
-        return g, None, None, None, None, None, None, None, None
+        return g, None, None, None, None, None, None, None, None, None
 
 
 def rasterize_meshes(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, image_size, blur_radius=0.0,
@@ -123,7 +123,8 @@ def rasterize_meshes(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, ima
     from . import clip as _clip
     cl = _clip.clip_faces(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, float(z_clip_value),
                           bool(perspective_correct))
-    p2f, zbuf, bary, dists = _RasterizeFn.apply(cl.face_verts, cl.mesh_to_face_first_idx, cl.num_faces_per_mesh, *args)
+    p2f, zbuf, bary, dists = _RasterizeFn.apply(cl.face_verts, cl.mesh_to_face_first_idx, cl.num_faces_per_mesh, *args,
+                                                cl.clipped_faces_neighbor_idx)
     p2f, bary = _clip.convert_clipped_rasterization_to_original_faces(p2f, bary, cl)
     return p2f, zbuf, bary, dists
 

@@ -182,7 +182,7 @@ def transform_verts_backward(verts, R, T, k00, k11, grad_ndc):
 
 def rasterize_meshes(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, image_size, blur_radius=0.0,
                      faces_per_pixel=1, bin_size=0, max_faces_per_bin=0, perspective_correct=False,
-                     clip_barycentric_coords=False, cull_backfaces=False):
+                     clip_barycentric_coords=False, cull_backfaces=False, clipped_faces_neighbor_idx=None):
     """Signature of pytorch3d._C.rasterize_meshes.  Returns (pix_to_face i64, zbuf, bary, dists)."""
     poll_overflow()
     face_verts = _cuda_f32("face_verts", face_verts, 3, 3)
@@ -203,7 +203,12 @@ def rasterize_meshes(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, ima
     key = ("raster", N, Ft, H, W)
     nbytes = lib().st3d_raster_workspace_size(N, Ft, H, W, _capacity(key, Ft))
     ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
-    check(lib().st3d_rasterize_meshes_forward(_p(face_verts), _p(first), _p(num), N, Ft, max_f, H, W, float(blur_radius),
+    nbi = None
+    if clipped_faces_neighbor_idx is not None:
+        nbi = _cuda_int("clipped_faces_neighbor_idx", clipped_faces_neighbor_idx, torch.int64)
+        if nbi.numel() != Ft:
+            raise ValueError("clipped_faces_neighbor_idx must hold one entry per face")
+    check(lib().st3d_rasterize_meshes_forward(_p(face_verts), _p(first), _p(num), _p(nbi), N, Ft, max_f, H, W, float(blur_radius),
                                               K, int(bin_size or 0), int(max_faces_per_bin or 0), int(perspective_correct),
                                               int(clip_barycentric_coords), int(cull_backfaces), _p(ws), nbytes,
                                               _p(p2f), _p(zbuf), _p(bary), _p(dists), _stream()),

@@ -79,9 +79,12 @@ size_t st3d_raster_workspace_size(int N, int64_t F_total, int H, int W, int64_t 
  * max_faces_per_bin are accepted for signature parity and ignored: hard rasterization (blur 0, K = 1)
  * uses no bins at all (faces go straight to a 64-bit z-buffer), the general path bins into 16x16-pixel
  * tiles with exact-size face lists -- no silent face drop either way (SURVEY section 7
- * "max_faces_per_bin overflow"). */
+ * "max_faces_per_bin overflow").  clipped_faces_neighbor_idx (F_total) int64 or NULL: as produced by clip_faces
+ * (-1 = none); the two halves of a clipped quad de-duplicate per pixel, the one with the smaller edge distance
+ * stays (only reachable with K > 1 or blur_radius > 0; the hard path cannot hold both). */
 int st3d_rasterize_meshes_forward(const float* face_verts, const int64_t* mesh_to_face_first_idx,
-                                  const int64_t* num_faces_per_mesh, int N, int64_t F_total, int64_t max_faces_in_mesh,
+                                  const int64_t* num_faces_per_mesh, const int64_t* clipped_faces_neighbor_idx,
+                                  int N, int64_t F_total, int64_t max_faces_in_mesh,
                                   int H, int W, float blur_radius, int faces_per_pixel, int bin_size,
                                   int max_faces_per_bin, int perspective_correct, int clip_barycentric_coords,
                                   int cull_backfaces, void* workspace, size_t workspace_bytes,

@@ -95,11 +95,16 @@ static inline int hit_less(const hit_t* a, const hit_t* b) {
  * z = view depth.  Outputs are (N,H,W,K) / (N,H,W,K,3), initialised to -1.
  * Returns 0, or -1 on bad arguments.
  */
-int oracle_rasterize_naive(const float* face_verts, const int64_t* mesh_to_face_first_idx,
-                           const int64_t* num_faces_per_mesh, int N, int H, int W,
-                           float blur_radius, int K, int perspective_correct,
-                           int clip_barycentric_coords, int cull_backfaces, int nthreads,
-                           int64_t* pix_to_face, float* zbuf, float* bary, float* dists) {
+/* clipped_faces_neighbor_idx (F_total, or NULL): upstream's clip_faces splits a face with one vertex behind the
+ * near plane into two triangles t1, t2 and records each as the other's neighbour; the shared edge is not an edge of
+ * the original face, so a pixel keeps at most ONE of the pair in its K-best list -- the one whose edge distance is
+ * smaller (upstream rasterize_meshes_cpu.cpp "Handle the case where a face (f) partially behind the
+ * image plane is clipped to a quadrilateral and then split into two faces"). */
+int oracle_rasterize_naive_nb(const float* face_verts, const int64_t* mesh_to_face_first_idx,
+                              const int64_t* num_faces_per_mesh, const int64_t* clipped_faces_neighbor_idx, int N,
+                              int H, int W, float blur_radius, int K, int perspective_correct,
+                              int clip_barycentric_coords, int cull_backfaces, int nthreads,
+                              int64_t* pix_to_face, float* zbuf, float* bary, float* dists) {
     if (K < 1 || K > ORACLE_MAX_K || N < 0 || H < 1 || W < 1) return -1;
     const int64_t npix = (int64_t)N * H * W;
     for (int64_t i = 0; i < npix * K; ++i) {
@@ -175,6 +180,24 @@ int oracle_rasterize_naive(const float* face_verts, const int64_t* mesh_to_face_
                     hit_t h;
                     h.z = pz; h.f = f; h.dist = inside ? -dist : dist;
                     h.b0 = c0; h.b1 = c1; h.b2 = c2;
+                    /* the other half of a clipped quad already in the list: keep the closer of the two */
+                    const int64_t nb = clipped_faces_neighbor_idx ? clipped_faces_neighbor_idx[f] : -1;
+                    int at = -1;
+                    if (nb != -1)
+                        for (int i = 0; i < nq; ++i)
+                            if (q[i].f == nb) { at = i; break; }
+                    if (at != -1) {
+                        if (dist < fabsf(q[at].dist)) {
+                            q[at] = h;
+                            for (int i = 1; i < nq; ++i) {      /* restore the (z, face) order */
+                                const hit_t t = q[i];
+                                int j = i;
+                                while (j > 0 && hit_less(&t, &q[j - 1])) { q[j] = q[j - 1]; --j; }
+                                q[j] = t;
+                            }
+                        }
+                        continue;
+                    }
                     /* step 9: insertion into the K-best list */
                     if (nq < K) {
                         int j = nq++;
@@ -199,6 +222,16 @@ int oracle_rasterize_naive(const float* face_verts, const int64_t* mesh_to_face_
         }
     }
     return 0;
+}
+
+int oracle_rasterize_naive(const float* face_verts, const int64_t* mesh_to_face_first_idx,
+                           const int64_t* num_faces_per_mesh, int N, int H, int W,
+                           float blur_radius, int K, int perspective_correct,
+                           int clip_barycentric_coords, int cull_backfaces, int nthreads,
+                           int64_t* pix_to_face, float* zbuf, float* bary, float* dists) {
+    return oracle_rasterize_naive_nb(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, NULL, N, H, W, blur_radius, K,
+                                     perspective_correct, clip_barycentric_coords, cull_backfaces, nthreads, pix_to_face,
+                                     zbuf, bary, dists);
 }
 
 int oracle_num_threads(void) {

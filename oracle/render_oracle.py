@@ -48,6 +48,9 @@ def lib():
         L.oracle_rasterize_naive.argtypes = [fp, ip, ip] + [ctypes.c_int] * 3 + [ctypes.c_float] + \
             [ctypes.c_int] * 5 + [ip, fp, fp, fp]
         L.oracle_rasterize_naive.restype = ctypes.c_int
+        L.oracle_rasterize_naive_nb.argtypes = [fp, ip, ip, ip] + [ctypes.c_int] * 3 + [ctypes.c_float] + \
+            [ctypes.c_int] * 5 + [ip, fp, fp, fp]
+        L.oracle_rasterize_naive_nb.restype = ctypes.c_int
         L.oracle_pix_to_ndc.argtypes = [ctypes.c_int] * 3
         L.oracle_pix_to_ndc.restype = ctypes.c_float
         L.oracle_num_threads.restype = ctypes.c_int
@@ -161,8 +164,9 @@ def transform_verts_torch(verts, R, T, k00, k11):
 # --------------------------------------------------------------------------------------------
 def rasterize_naive(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, image_size,
                     blur_radius=0.0, faces_per_pixel=1, perspective_correct=True,
-                    clip_barycentric_coords=False, cull_backfaces=False, nthreads=1):
-    """Mirrors pytorch3d._C.rasterize_meshes (naive path).  Returns pix_to_face i64, zbuf, bary, dists."""
+                    clip_barycentric_coords=False, cull_backfaces=False, nthreads=1, clipped_faces_neighbor_idx=None):
+    """Mirrors pytorch3d._C.rasterize_meshes (naive path).  Returns pix_to_face i64, zbuf, bary, dists.
+    clipped_faces_neighbor_idx (F,) int64 or None: the two halves of a clipped quad de-duplicate per pixel (A.2)."""
     H, W = (image_size, image_size) if isinstance(image_size, int) else image_size
     fv = face_verts.detach().to(torch.float32).contiguous().cpu()
     first = mesh_to_face_first_idx.to(torch.int64).contiguous().cpu()
@@ -172,10 +176,17 @@ def rasterize_naive(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, imag
     zbuf = torch.empty((N, H, W, K), dtype=torch.float32)
     bary = torch.empty((N, H, W, K, 3), dtype=torch.float32)
     dists = torch.empty((N, H, W, K), dtype=torch.float32)
-    rc = lib().oracle_rasterize_naive(_fp(fv), _ip(first), _ip(num), N, H, W, float(blur_radius), K,
-                                      int(perspective_correct), int(clip_barycentric_coords),
-                                      int(cull_backfaces), int(nthreads), _ip(p2f), _fp(zbuf),
-                                      _fp(bary), _fp(dists))
+    if clipped_faces_neighbor_idx is None:
+        rc = lib().oracle_rasterize_naive(_fp(fv), _ip(first), _ip(num), N, H, W, float(blur_radius), K,
+                                          int(perspective_correct), int(clip_barycentric_coords),
+                                          int(cull_backfaces), int(nthreads), _ip(p2f), _fp(zbuf),
+                                          _fp(bary), _fp(dists))
+    else:
+        nbi = clipped_faces_neighbor_idx.to(torch.int64).contiguous().cpu()
+        rc = lib().oracle_rasterize_naive_nb(_fp(fv), _ip(first), _ip(num), _ip(nbi), N, H, W, float(blur_radius), K,
+                                             int(perspective_correct), int(clip_barycentric_coords),
+                                             int(cull_backfaces), int(nthreads), _ip(p2f), _fp(zbuf),
+                                             _fp(bary), _fp(dists))
     if rc != 0:
         raise ValueError("oracle_rasterize_naive: bad arguments")
     return p2f, zbuf, bary, dists
@@ -466,7 +477,7 @@ def render_views(verts, faces, R, T, image_size, texture=None, verts_uvs=None, f
         cl_x = clip_faces(fv_exact, first, num, np.float32(z_clip).item(), True)
         p2f_c, zbuf_x, bary_x, dists_x = rasterize_naive(cl_x["face_verts"], cl_x["first"], cl_x["num"], (H, W),
                                                           blur_radius, faces_per_pixel, True, blur_radius > 0, False,
-                                                          nthreads)
+                                                          nthreads, clipped_faces_neighbor_idx=cl_x["neighbor"])
         cl = clip_faces(fv, first, num, z_clip, True)
         assert torch.equal(cl["to_unclipped"], cl_x["to_unclipped"])
         zbuf, bary_c, dists = fragments_from_faces(cl["face_verts"], p2f_c, True, blur_radius > 0)

@@ -403,12 +403,14 @@ def test_near_plane_clipping_fused_matches_oracle(cow, layout, mode):
     _close(g_verts, verts64.grad, tol=2e-4, what="grad_verts")
 
 
-@pytest.mark.parametrize("K", [1, 2])
-def test_near_plane_clipping_fragments_match_oracle(cow, K):
-    """Operator-boundary path: torch-level clip_faces around st3d_rasterize_meshes_forward, as upstream does."""
+@pytest.mark.parametrize("K,blur", [(1, 0.0), (2, 0.0), (3, 1e-3), (8, 4e-4)])
+def test_near_plane_clipping_fragments_match_oracle(cow, K, blur):
+    """Operator-boundary path: torch-level clip_faces around st3d_rasterize_meshes_forward, as upstream does, incl.
+    the per-pixel de-duplication of the two halves of a clipped quad (clipped_faces_neighbor_idx) when blur > 0."""
     import st3d.functional as Fn
     from st3d import clip as cl
     S = 64
+    cb = blur > 0
     R, T = _close_cameras()
     fv, first, num, _ = _face_verts(cow, R, T)
     want_cl = ro.clip_faces(fv, first, num, 0.5)
@@ -418,11 +420,15 @@ def test_near_plane_clipping_fragments_match_oracle(cow, K):
     assert torch.equal(got_cl.clipped_faces_neighbor_idx.cpu(), want_cl["neighbor"])
     assert torch.equal(got_cl.barycentric_conversion.cpu(), want_cl["conversion"])
 
-    w_p2f, w_z, w_b, w_d = ro.rasterize_naive(want_cl["face_verts"], want_cl["first"], want_cl["num"], S, 0.0, K, True,
-                                              False, False, 8)
-    w_p2f, w_b = ro.convert_clipped_to_unclipped(w_p2f, w_b, want_cl)
+    def oracle_raster(neighbor):
+        return ro.rasterize_naive(want_cl["face_verts"], want_cl["first"], want_cl["num"], S, blur, K, True, cb, False, 8,
+                                  clipped_faces_neighbor_idx=neighbor)
+    c_p2f, w_z, w_b, w_d = oracle_raster(want_cl["neighbor"])
+    if cb:      # the de-duplication must matter on this scene, or the test proves nothing
+        assert (oracle_raster(None)[0] != c_p2f).sum().item() > 50
+    w_p2f, w_b = ro.convert_clipped_to_unclipped(c_p2f, w_b, want_cl)
     fvg = fv.cuda().requires_grad_(True)
-    p2f, zbuf, bary, dists = Fn.rasterize_meshes(fvg, first.cuda(), num.cuda(), S, 0.0, K, True, False, False,
+    p2f, zbuf, bary, dists = Fn.rasterize_meshes(fvg, first.cuda(), num.cuda(), S, blur, K, True, cb, False,
                                                  z_clip_value=0.5)
     torch.cuda.synchronize()
     assert torch.equal(p2f.cpu(), w_p2f)
@@ -436,10 +442,8 @@ def test_near_plane_clipping_fragments_match_oracle(cow, K):
     ((zbuf * gz.cuda()).sum() + (bary * gb.cuda()).sum()).backward()
     fv64 = fv.double().requires_grad_(True)
     c64 = ro.clip_faces(fv64, first, num, 0.5)
-    z64, b64, _ = ro.fragments_from_faces(c64["face_verts"], ro.rasterize_naive(
-        want_cl["face_verts"], want_cl["first"], want_cl["num"], S, 0.0, K, True, False, False, 8)[0])
-    _, b64 = ro.convert_clipped_to_unclipped(ro.rasterize_naive(
-        want_cl["face_verts"], want_cl["first"], want_cl["num"], S, 0.0, K, True, False, False, 8)[0], b64, c64)
+    z64, b64, _ = ro.fragments_from_faces(c64["face_verts"], c_p2f, True, cb)
+    _, b64 = ro.convert_clipped_to_unclipped(c_p2f, b64, c64)
     hit64 = hit.double()
     ((z64 * gz.double() * hit64).sum() + (b64 * gb.double() * hit64[..., None]).sum()).backward()
     _close(fvg.grad, fv64.grad, tol=2e-4, what="grad_face_verts through clipping")
