@@ -326,8 +326,11 @@ class MeshRenderer(torch.nn.Module):
     def _can_fuse(self, kwargs):
         rs = kwargs.get("raster_settings", self.rasterizer.raster_settings)
         lights = kwargs.get("lights", self.shader.lights)
+        # blur_radius > 0 goes through Fragments + shader: that path clips faces at the near plane for any blur,
+        # the fused kernels only for the hard rasterization the reference uses
         return (isinstance(lights, AmbientLights) and rs.faces_per_pixel == 1 and not rs.cull_to_frustum
-                and rs.perspective_correct is not False and rs.clip_barycentric_coords in (None, rs.blur_radius > 0.0))
+                and rs.blur_radius == 0.0 and rs.perspective_correct is not False
+                and rs.clip_barycentric_coords in (None, False))
 
     def forward(self, meshes_world, **kwargs):
         if not self._can_fuse(kwargs):       # Phong lights / K > 1: Fragments + general shader
