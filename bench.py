@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
     ap.add_argument("--nchw", action="store_true", help="keep VGG activations NCHW (torch default) instead of channels_last")
     ap.add_argument("--unfused-vgg", action="store_true", help="conv, bias add and ReLU as separate torch kernels")
+    ap.add_argument("--cudnn-benchmark", action="store_true",
+                    help="let cuDNN time its convolution algorithms per shape (torch.backends.cudnn.benchmark)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the e2e / cached-constants legs")
     ap.add_argument("--profile-run", action="store_true",
@@ -324,6 +326,8 @@ def run_st3d(args):
         raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if args.cudnn_benchmark:
+        torch.backends.cudnn.benchmark = True
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     import st3d
