@@ -494,3 +494,49 @@ def test_full_size_clipped_scene_two_paths_agree(cow):
     t12, v12, _ = ops.render_backward(state, g1 + 2 * g2, need_verts=True)
     _close(t12, t1 + 2 * t2, tol=1e-4, what="clipped backward linearity (texture)")
     _close(v12, v1 + 2 * v2, tol=2e-3, what="clipped backward linearity (vertices)")
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_soups_cut_by_the_near_plane_bit_exact(seed):
+    """Random world-space triangle soups whose depths straddle z = z_clip, z = 0 and the camera itself, rendered by
+    the fused path (clipping inside the kernels) and by the Fragments path (torch clip_faces): pix_to_face must match
+    the oracle bit for bit, including faces with a vertex exactly on the plane or almost at z = 0 (huge NDC coordinates)."""
+    import st3d.functional as Fn
+    ops = _ops()
+    g = torch.Generator().manual_seed(500 + seed)
+    n = 240
+    centre = torch.cat([torch.rand(n, 1, 2, generator=g) * 1.6 - 0.8, torch.rand(n, 1, 1, generator=g) * 3.0 - 0.6], dim=-1)
+    size = torch.rand(n, 1, 1, generator=g) ** 2 * 1.2 + 0.02
+    tris = centre + (torch.rand(n, 3, 3, generator=g) - 0.5) * size
+    tris[0, 0, 2] = 0.5            # a vertex exactly on the clip plane (not "behind": the test is z < z_clip)
+    tris[1, 1, 2] = 1e-4           # a vertex almost at z = 0: huge but finite NDC coordinates
+    tris[2, :, 2] = -0.3           # entirely behind the camera
+    tris[3, :, 2] = torch.tensor([0.2, 0.3, 0.4])   # entirely between the camera and the plane: removed
+    verts = tris.reshape(-1, 3).contiguous()
+    faces = torch.arange(3 * n).reshape(n, 3)
+    R = torch.eye(3)[None].repeat(2, 1, 1)
+    T = torch.tensor([[0.0, 0.0, 0.0], [0.1, -0.05, 0.35]])
+    vrgb = torch.rand(3 * n, 3, generator=g)
+    S = (48, 64)
+    k00, k11 = ro.fov_scales(60.0)
+    rgba, frag = ro.render_views(verts, faces, R, T, S, verts_rgb=vrgb, nthreads=8, return_fragments=True)
+    want = frag["pix_to_face"][..., 0]
+    behind = (ro.transform_verts_exact(verts, R, T, k00, k11)[:, faces].reshape(-1, 3, 3)[:, :, 2] < 0.5).sum(1)
+    assert (behind == 1).sum() > 10 and (behind == 2).sum() > 10
+    spec = ops.RenderSpec(image_size=S, k00=k00, k11=k11)
+    img, _, p2f, _ = ops.render_forward(spec, verts.cuda(), faces.cuda(), R.cuda(), T.cuda(), verts_rgb=vrgb.cuda())
+    torch.cuda.synchronize()
+    ops.poll_overflow(block=True)
+    assert torch.equal(p2f.cpu().long(), want), f"fused path, seed {seed}: {(p2f.cpu().long() != want).sum().item()} pixels differ"
+    _close(img, rgba, what="rgba of the clipped soup")
+    ndc = ops.transform_verts(verts.cuda(), R.cuda(), T.cuda(), k00, k11)
+    fv = ndc[:, faces.cuda()].reshape(2 * n, 3, 3)
+    first = torch.arange(2, device="cuda") * n
+    for K, blur in ((1, 0.0), (4, 0.0), (3, 5e-4)):
+        rg, fg = ro.render_views(verts, faces, R, T, S, verts_rgb=vrgb, nthreads=8, return_fragments=True,
+                                 faces_per_pixel=K, blur_radius=blur)
+        got = Fn.rasterize_meshes(fv, first, torch.full((2,), n, device="cuda"), S, blur, K, True, blur > 0, False,
+                                  z_clip_value=0.5)
+        torch.cuda.synchronize()
+        nbad = (got[0].cpu() != fg["pix_to_face"]).sum().item()
+        assert nbad == 0, f"Fragments path, seed {seed}, K={K}, blur={blur}: {nbad} entries differ"
