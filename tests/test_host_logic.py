@@ -106,3 +106,39 @@ def test_fused_vgg_keeps_names_and_values_on_cpu():
         a, b = losses.get_features(x, fused), lo.get_features(x.clone(), vgg)
     for k in b:
         assert torch.equal(a[k], b[k])
+
+
+def test_fused_vgg_pool_wiring_and_cpu_walk():
+    """Structure of the fused VGG with libst3d pools: every MaxPool2d(2, 2) becomes a FusedMaxPool that carries the
+    ReLU mask of the conv layer in front of it, that layer is told so, and the flags that guard the skipped ReLU
+    backward behave (conservative default, cleared only inside get_features for untapped layers).  On CPU tensors
+    the pools hand over to torch's pooling, so the walk still equals the plain model."""
+    import torchvision
+    from st3d import losses
+    from st3d.vgg import FusedConvReLU, FusedMaxPool, fuse_vgg_features
+    torch.manual_seed(0)
+    vgg = torchvision.models.vgg19(weights=None).features.eval()
+    fused = fuse_vgg_features(vgg, channels_last=True, fuse_pool=True)
+    pools = [n for n, m in fused._modules.items() if isinstance(m, FusedMaxPool)]
+    assert pools == ["4", "9", "18", "27", "36"] and all(fused._modules[n].after_relu for n in pools)
+    feeding = [n for n, m in fused._modules.items() if isinstance(m, FusedConvReLU) and m.feeds_masking_pool]
+    assert feeding == ["2", "7", "16", "25", "34"]
+    assert all(m.tapped for m in fused if isinstance(m, FusedConvReLU))          # conservative default
+    seen = {}
+    for name in ("0", "2"):
+        mod = fused._modules[name]
+        orig = mod.forward
+        mod.forward = (lambda x, _o=orig, _m=mod, _n=name: (seen.__setitem__(_n, _m.tapped), _o(x))[1])
+    x = torch.rand(1, 3, 32, 32)
+    with torch.no_grad():
+        a = losses.get_features(x, fused)
+        b = lo.get_features(x.clone(), vgg)
+    assert seen == {"0": True, "2": False}      # conv1_1 is a tap, conv1_2 is not: only the latter may skip its ReLU backward
+    assert all(m.tapped for m in fused if isinstance(m, FusedConvReLU))          # and the default is restored
+    for k in b:
+        assert torch.equal(a[k], b[k])
+    no_pool = fuse_vgg_features(vgg, channels_last=True, fuse_pool=False)
+    assert not any(isinstance(m, FusedMaxPool) for m in no_pool)
+    assert not any(getattr(m, "feeds_masking_pool", False) for m in no_pool)
+    # an odd-sized or NCHW input is not for the libst3d pooling kernels
+    assert not FusedMaxPool.accepts(torch.nn.MaxPool2d(3, 2)) and FusedMaxPool.accepts(torch.nn.MaxPool2d(2, 2))
