@@ -1,4 +1,4 @@
-"""One GPU's share of BASELINE configs[4] (GPU box only): a ~1.5 M-face mesh (cow subdivided 4x, UVs interpolated at the
+"""BASELINE configs[4] scale (GPU box only; one process, or one rank per GPU under torchrun): a ~1.5 M-face mesh (cow subdivided 4x, UVs interpolated at the
 midpoints), 16 views x 1024^2 per GPU (128 views over 8 GPUs), texture + vertex optimisation (`both`), VGG-19 on cuDNN.
 Prints one JSON line: iterations / s, per-op CUDA-event times, peak memory."""
 import json, os, sys, time
@@ -31,18 +31,26 @@ tex = torch.from_numpy(d["texture"]).float() / 255.0
 tex = F.interpolate(tex.permute(2, 0, 1)[None], size=(size, size), mode="bilinear", align_corners=False)[0].permute(1, 2, 0).contiguous()
 style = F.interpolate(torch.rand(1, 3, size // 16, size // 16, generator=torch.Generator().manual_seed(0)), size=(size, size),
                       mode="bicubic", align_corners=False).clamp(0, 1).contiguous()
-dev = torch.device("cuda:0")
+import torch.distributed as dist
+world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:       # views shard over the ranks (weak scaling: `views` per GPU), gradients all-reduced by NCCL
+    dist.init_process_group("nccl", device_id=dev)
 torch.manual_seed(0)
 vgg = torchvision.models.vgg19(weights=None).features.eval().to(dev)
 for p in vgg.parameters():
     p.requires_grad_(False)
-R, T = cm.random_view_cameras(views, generator=torch.Generator().manual_seed(0))
+R, T = cm.random_view_cameras(views * world, generator=torch.Generator().manual_seed(0))
+R, T = R[rank * views:(rank + 1) * views], T[rank * views:(rank + 1) * views]
 opt = StyleOptimizer(verts.to(dev), faces.to(dev), vgg, size, verts_uvs=uvs.to(dev), faces_uvs=fuvs.to(dev), texture=tex.to(dev),
-                     target=target, lr=0.01)
+                     target=target, lr=0.01, world_size=world)
 R, T, style = R.to(dev), T.to(dev), style.to(dev)
 for _ in range(2):
     loss = opt.step(R, T, style)
 torch.cuda.synchronize(); ops.poll_overflow(block=True)
+if world > 1:
+    dist.barrier()
 ops.start_profile()
 e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True); e0.record()
 for _ in range(steps):
@@ -50,8 +58,16 @@ for _ in range(steps):
 e1.record(); torch.cuda.synchronize()
 prof = ops.stop_profile()
 ms = e0.elapsed_time(e1) / steps
+if world > 1:       # device time, max over ranks
+    t = torch.tensor([ms], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    dist.barrier()
+    dist.destroy_process_group()
+if rank != 0:
+    sys.exit(0)
 stages = {op + "_" + "x".join(map(str, key)): round(sum(v) / steps, 3) for (op, key), v in sorted(prof.items())}
 print(json.dumps({"workload": f"cow subdivided {levels}x ({faces.shape[0]} faces, {verts.shape[0]} verts), {views} views x {size}^2 "
-                              f"on one GPU, target={target}", "ms_per_step": ms, "it_per_s": 1e3 / ms,
-                  "views_per_s": views * 1e3 / ms, "loss": float(loss), "peak_mem_GB": torch.cuda.max_memory_allocated() / 2**30,
+                              f"per GPU on {world} GPU(s), target={target}", "n_gpus": world, "ms_per_step": ms, "it_per_s": 1e3 / ms,
+                  "views_per_s": views * world * 1e3 / ms, "loss": float(loss), "peak_mem_GB": torch.cuda.max_memory_allocated() / 2**30,
                   "stages_ms_per_step": stages}))
