@@ -8,6 +8,7 @@
 // 128-byte swizzled exactly as TMA writes them, consumed by tcgen05.mma kind::tf32; accumulation is
 // fp32 in TMEM.  Every mbarrier wait is bounded: a protocol bug traps instead of hanging the GPU.
 #pragma once
+#include <atomic>
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -963,6 +964,20 @@ static inline int make_map_nhwc(CUtensorMap* m, const float* base, uint64_t B, u
     return ST3D_OK;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: remember it per device (bit = device ordinal),
+// not per process, so that a second GPU driven from the same process can launch the > 48 KB kernels too
+template <typename K>
+static int ensure_smem_attr(K kernel, int bytes, std::atomic<uint64_t>& done) {
+    int dev = 0;
+    ST3D_CUDA_OK(cudaGetDevice(&dev));
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(done.load(std::memory_order_acquire) & bit)) {
+        ST3D_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        done.fetch_or(bit, std::memory_order_release);
+    }
+    return ST3D_OK;
+}
+
 template <int C, bool NHWC>
 static int launch_fwd(const float* feat, const GramPlan& p, cudaStream_t s) {
     using Cfg = FwdCfg<C>;
@@ -970,12 +985,9 @@ static int launch_fwd(const float* feat, const GramPlan& p, cudaStream_t s) {
     int rc = NHWC ? make_map_nhwc(&map, feat, p.B, p.HW, C, 32 * Cfg::KPS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
                   : make_map(&map, feat, (uint64_t)p.B * C, (uint64_t)p.HW, Cfg::BOX_ROWS);
     if (rc != ST3D_OK) return rc;
-    static bool attr_done = false;
-    if (!attr_done) {
-        ST3D_CUDA_OK(cudaFuncSetAttribute(k_gram_tc_fwd<C, NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)Cfg::SMEM));
-        attr_done = true;
-    }
+    static std::atomic<uint64_t> attr_done{0};
+    rc = ensure_smem_attr(k_gram_tc_fwd<C, NHWC>, (int)Cfg::SMEM, attr_done);
+    if (rc != ST3D_OK) return rc;
     if (Cfg::CLUSTER) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(Cfg::GROUPS, p.splits, p.B);
@@ -1011,12 +1023,9 @@ static int launch_bwd_pair(const float* feat, const GramPlan& p, int accumulate,
     if (rc != ST3D_OK) return rc;
     rc = make_map(&map_s, p.sym, (uint64_t)p.B * C, (uint64_t)C, 128);
     if (rc != ST3D_OK) return rc;
-    static bool attr_done = false;
-    if (!attr_done) {
-        ST3D_CUDA_OK(cudaFuncSetAttribute(k_gram_tc_bwd_pair<NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)Cfg::SMEM));
-        attr_done = true;
-    }
+    static std::atomic<uint64_t> attr_done{0};
+    rc = ensure_smem_attr(k_gram_tc_bwd_pair<NHWC>, (int)Cfg::SMEM, attr_done);
+    if (rc != ST3D_OK) return rc;
     const int64_t chunks = (p.HW + 127) / 128, items = (int64_t)p.B * ((chunks + 1) / 2);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * (unsigned)std::min<int64_t>(items, 74));  // one CTA pair per TPC
@@ -1050,12 +1059,9 @@ static int launch_bwd(const float* feat, const GramPlan& p, int accumulate, floa
     if (rc != ST3D_OK) return rc;
     rc = make_map(&map_s, p.sym, (uint64_t)p.B * C, (uint64_t)C, Cfg::S_BOX_ROWS);
     if (rc != ST3D_OK) return rc;
-    static bool attr_done = false;
-    if (!attr_done) {
-        ST3D_CUDA_OK(cudaFuncSetAttribute(k_gram_tc_bwd<C, NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)Cfg::SMEM));
-        attr_done = true;
-    }
+    static std::atomic<uint64_t> attr_done{0};
+    rc = ensure_smem_attr(k_gram_tc_bwd<C, NHWC>, (int)Cfg::SMEM, attr_done);
+    if (rc != ST3D_OK) return rc;
     const int64_t items = (int64_t)p.B * ((p.HW + 127) / 128);
     ST3D_REQUIRE(items < (1ll << 31), "gram_backward: B * ceil(HW / 128) = %lld work items exceed 2^31", (long long)items);
     const int grid = (int)std::min<int64_t>(items, 148);

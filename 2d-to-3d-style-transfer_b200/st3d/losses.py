@@ -26,7 +26,7 @@ def get_features(image: torch.Tensor, model, layers=None, stop_after_last_tap: b
         image = image.contiguous(memory_format=torch.channels_last)
     feats, x, done = {}, image, False
     for name, module in model._modules.items():
-        if done and not ((isinstance(module, torch.nn.ReLU) and module.inplace) or isinstance(module, torch.nn.Identity)):
+        if done and not _rewrites_the_tap(module):
             break
         if hasattr(module, "tapped"):       # FusedConvReLU: a tapped activation has a second consumer (st3d/vgg.py)
             module.tapped = name in layers
@@ -40,6 +40,12 @@ def get_features(image: torch.Tensor, model, layers=None, stop_after_last_tap: b
             feats[layers[name]] = x
         done = stop_after_last_tap and last is not None and name == str(last)
     return feats
+
+
+def _rewrites_the_tap(module) -> bool:
+    """Modules that leave the tapped tensor's identity intact: the in-place ReLU behind a tapped convolution
+    (it overwrites the stored tensor, style_transfer.py:21-26) and the Identity a fused model keeps in its place."""
+    return (isinstance(module, torch.nn.ReLU) and module.inplace) or isinstance(module, torch.nn.Identity)
 
 
 def style_targets(style_imgs: torch.Tensor, model, precision=None):
@@ -75,20 +81,38 @@ def content_and_style_constants(content_imgs, style_imgs, model, precision=None,
         x = torch.cat([content_imgs, style_imgs], dim=0)
         if getattr(model, "_st3d_channels_last", False) and x.is_cuda:
             x = x.contiguous(memory_format=torch.channels_last)
-        content, grams, done = None, {}, False
-        for name, module in model._modules.items():
-            if done and not ((isinstance(module, torch.nn.ReLU) and module.inplace) or isinstance(module, torch.nn.Identity)):
+        state = {"content": None, "grams": {}}
+
+        def take(layer, x):
+            """Records the tap `layer` from the activation x and returns what continues down the network."""
+            if layer == CONTENT_LAYER:
+                state["content"] = x[:B]
+                return x[B:]                    # only the style image(s) go on to conv5_1
+            state["grams"][layer] = Fn.gram_matrix(x[B:] if state["content"] is None else x, precision)
+            return x
+
+        modules = list(model._modules.items())
+        pending, done = None, False
+        for i, (name, module) in enumerate(modules):
+            if done and not _rewrites_the_tap(module):
                 break
             x = module(x)
+            if pending is not None:             # the in-place ReLU behind a tapped Conv2d has run: NOW it is the tap
+                x, pending = take(pending, x), None
             if done:
                 break
             layer = VGG_TAPS.get(name)
-            if layer == CONTENT_LAYER:
-                content = x[:B]
-                x = x[B:]                       # only the style image(s) go on to conv5_1
-            elif layer is not None:
-                grams[layer] = Fn.gram_matrix(x[B:] if content is None else x, precision)
+            if layer is not None:
+                # style_transfer.py:21-26 stores the tensor a tapped module returns, and the in-place ReLU that
+                # follows rewrites that very tensor: every tap is the POST-ReLU activation (SURVEY section 8 row
+                # a10).  A FusedConvReLU already returns it; behind a plain Conv2d the tap waits for the ReLU.
+                nxt = modules[i + 1][1] if i + 1 < len(modules) else None
+                if nxt is not None and _rewrites_the_tap(nxt) and not isinstance(nxt, torch.nn.Identity):
+                    pending = layer
+                else:
+                    x = take(layer, x)
             done = name == str(LAST_TAP)
+        content, grams = state["content"], state["grams"]
         if style_weights is not None:
             w = torch.as_tensor(style_weights, dtype=torch.float32, device=style_imgs.device).reshape(-1, 1, 1)
             if w.shape[0] != style_imgs.shape[0]:
@@ -125,7 +149,7 @@ def perceptual_loss_of_images(current_imgs, model, content_feat, style_grams, st
         x = x.contiguous(memory_format=torch.channels_last)
     content_loss, style_loss, done = None, None, False
     for name, module in model._modules.items():
-        if done and not ((isinstance(module, torch.nn.ReLU) and module.inplace) or isinstance(module, torch.nn.Identity)):
+        if done and not _rewrites_the_tap(module):
             break
         layer = VGG_TAPS.get(name)
         if layer in style_grams:

@@ -6,6 +6,7 @@ and raises on a non-zero return code.  Nothing here computes on the CPU.
 from __future__ import annotations
 
 import ctypes
+import functools
 from dataclasses import dataclass, field
 from typing import Optional
 
@@ -69,12 +70,44 @@ def _p(t: Optional[torch.Tensor]):
 
 
 def _stream():
+    """The current torch stream of the CURRENT device; every op runs under `_on_device_of`, which makes the device
+    of its tensors current for the duration of the call (the library launches on the current device)."""
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _first_tensor(args, kwargs):
+    for a in list(args) + list(kwargs.values()):
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            return a
+        if isinstance(a, RenderState):
+            return a.keep[0]
+    return None
+
+
+def _on_device_of(fn):
+    """Runs `fn` with the device of its first CUDA tensor argument current (what a CUDAGuard does in upstream's
+    `_C` ops): kernels, workspace allocations and the stream all belong to that device even when the caller's current
+    device is another one.  `_cuda_f32` / `_cuda_int` / `_feat3` then reject tensors that live elsewhere."""
+    @functools.wraps(fn)
+    def guarded(*args, **kwargs):
+        t = _first_tensor(args, kwargs)
+        if t is None or t.device.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(t.device):
+            return fn(*args, **kwargs)
+    return guarded
+
+
+def _same_device(name: str, t: torch.Tensor) -> None:
+    if t.device.index != torch.cuda.current_device():
+        raise ValueError(f"{name}: tensor is on {t.device} but the call runs on cuda:{torch.cuda.current_device()} "
+                         "(all tensor arguments of one call must share a device)")
 
 
 def _cuda_f32(name: str, t: torch.Tensor, *shape_tail):
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise St3dError(f"{name}: expected a CUDA tensor (st3d has no CPU path; the CPU oracle is test-only)")
+    _same_device(name, t)
     if t.dtype != torch.float32:
         raise ValueError(f"{name}: expected float32, got {t.dtype}")
     if shape_tail and tuple(t.shape[-len(shape_tail):]) != tuple(shape_tail):
@@ -85,6 +118,7 @@ def _cuda_f32(name: str, t: torch.Tensor, *shape_tail):
 def _cuda_int(name: str, t: torch.Tensor, dtype):
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise St3dError(f"{name}: expected a CUDA tensor (st3d has no CPU path)")
+    _same_device(name, t)
     return t.to(dtype).contiguous()
 
 
@@ -158,6 +192,7 @@ def _capacity(key, total_faces: int) -> int:
 # ------------------------------------------------------------------------------------------------
 # operator boundary (mirrors pytorch3d._C)
 # ------------------------------------------------------------------------------------------------
+@_on_device_of
 def transform_verts(verts, R, T, k00: float, k11: float):
     verts = _cuda_f32("verts", verts, 3)
     R = _cuda_f32("R", R, 3, 3).reshape(-1, 3, 3)
@@ -169,6 +204,7 @@ def transform_verts(verts, R, T, k00: float, k11: float):
     return out
 
 
+@_on_device_of
 def transform_verts_backward(verts, R, T, k00, k11, grad_ndc):
     verts = _cuda_f32("verts", verts, 3)
     R = _cuda_f32("R", R, 3, 3).reshape(-1, 3, 3)
@@ -180,6 +216,7 @@ def transform_verts_backward(verts, R, T, k00, k11, grad_ndc):
     return g
 
 
+@_on_device_of
 def rasterize_meshes(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, image_size, blur_radius=0.0,
                      faces_per_pixel=1, bin_size=0, max_faces_per_bin=0, perspective_correct=False,
                      clip_barycentric_coords=False, cull_backfaces=False, clipped_faces_neighbor_idx=None):
@@ -217,6 +254,7 @@ def rasterize_meshes(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, ima
     return p2f, zbuf, bary, dists
 
 
+@_on_device_of
 def rasterize_meshes_backward(face_verts, pix_to_face, grad_zbuf, grad_bary, grad_dists, perspective_correct,
                               clip_barycentric_coords):
     face_verts = _cuda_f32("face_verts", face_verts, 3, 3)
@@ -233,6 +271,7 @@ def rasterize_meshes_backward(face_verts, pix_to_face, grad_zbuf, grad_bary, gra
     return out
 
 
+@_on_device_of
 def interp_face_attrs_forward(pix_to_face, bary, face_attrs):
     p2f = _cuda_int("pix_to_face", pix_to_face, torch.int64).reshape(-1)
     bary = _cuda_f32("bary", bary, 3).reshape(-1, 3)
@@ -246,6 +285,7 @@ def interp_face_attrs_forward(pix_to_face, bary, face_attrs):
     return out
 
 
+@_on_device_of
 def interp_face_attrs_backward(pix_to_face, bary, face_attrs, grad_out):
     p2f = _cuda_int("pix_to_face", pix_to_face, torch.int64).reshape(-1)
     bary = _cuda_f32("bary", bary, 3).reshape(-1, 3)
@@ -288,6 +328,7 @@ class RenderState:
     workspace: Optional[torch.Tensor] = None
 
 
+@_on_device_of
 def render_forward(spec: RenderSpec, verts, faces, R, T, *, face_uvs=None, texture=None, verts_rgb=None):
     """One launch sequence for N views of one mesh.  Returns (image, mask|None, pix_to_face i32, state)."""
     poll_overflow()
@@ -349,6 +390,7 @@ def render_forward(spec: RenderSpec, verts, faces, R, T, *, face_uvs=None, textu
     return image, mask, p2f, RenderState(args=a, keep=keep + [image, mask, p2f], workspace=ws)
 
 
+@_on_device_of
 def render_backward(state: RenderState, grad_image, need_texture=True, need_verts=False, need_verts_rgb=False):
     """Returns (grad_texture|None, grad_verts|None, grad_verts_rgb|None)."""
     a = state.args
@@ -394,6 +436,7 @@ def _feat3(name, feat):
         raise St3dError(f"{name}: expected a CUDA tensor (st3d has no CPU path; the CPU oracle is test-only)")
     if feat.dtype != torch.float32:
         raise ValueError(f"{name}: expected float32, got {feat.dtype}")
+    _same_device(name, feat)
     if feat.dim() == 4:
         B, C, H, W = feat.shape
         if C > 1 and H * W > 1 and feat.is_contiguous(memory_format=torch.channels_last) and not feat.is_contiguous():
@@ -409,6 +452,7 @@ def _gram_ws(B, C, HW, device):
     return torch.empty(nbytes, device=device, dtype=torch.uint8), nbytes
 
 
+@_on_device_of
 def gram_forward(feat, precision=None):
     """(B,C,H,W) -> (B,C,C) = F F^T.  NCHW-contiguous and channels_last inputs are both read in place."""
     f, layout, (B, C, HW) = _feat3("feat", feat)
@@ -422,6 +466,7 @@ def gram_forward(feat, precision=None):
     return out
 
 
+@_on_device_of
 def gram_mse_forward(feat, target, scale: float, loss_out, want_gram=False, precision=None):
     """loss_out[0] += scale * sum((F F^T - target)^2); returns (dgram, gram|None)."""
     f, layout, (B, C, HW) = _feat3("feat", feat)
@@ -440,6 +485,7 @@ def gram_mse_forward(feat, target, scale: float, loss_out, want_gram=False, prec
     return dgram, gram
 
 
+@_on_device_of
 def gram_backward(feat, dgram, grad_scale: float = 1.0, out=None, accumulate=False, precision=None, scale_tensor=None,
                   relu_mask=False):
     """grad_feat = grad_scale * [scale_tensor] * (dG + dG^T) F, with the shape AND memory layout of feat
@@ -467,6 +513,7 @@ def gram_backward(feat, dgram, grad_scale: float = 1.0, out=None, accumulate=Fal
     return out if layout == FEAT_NHWC else out.reshape(feat.shape)
 
 
+@_on_device_of
 def mse_forward(a, b, scale: float, loss_out, mask=None, want_grad=True):
     """loss_out[0] += scale * sum(m (a-b)^2); returns grad wrt a (or None).  mask: (B,1,H,W) for a (B,Cm,H,W)."""
     if a.shape != b.shape:
@@ -501,6 +548,7 @@ def maxpool_supported(x: torch.Tensor) -> bool:
             and x.is_contiguous(memory_format=torch.channels_last))
 
 
+@_on_device_of
 def maxpool2x2_forward(x: torch.Tensor) -> torch.Tensor:
     if not maxpool_supported(x):
         raise ValueError("maxpool2x2_forward: expected a CUDA float32 channels_last (B,C,H,W) tensor with even H, W "
@@ -512,6 +560,7 @@ def maxpool2x2_forward(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+@_on_device_of
 def maxpool2x2_backward(x: torch.Tensor, grad_y: torch.Tensor, relu_mask: bool = False) -> torch.Tensor:
     """Gradient w.r.t. x; with relu_mask also through the ReLU that produced x (zero where x <= 0)."""
     B, C, H, W = x.shape

@@ -17,21 +17,21 @@ from . import functional as Fn
 from . import losses
 
 
-def allreduce_gradients(params, group=None) -> None:
-    """SUM all-reduce of the gradients over the view-sharding ranks as ONE flat fp32 buffer
-    (texture S*S*3 [+ verts V*3]); NCCL over NVLink when the process group is NCCL."""
+def allreduce_gradients(params, group=None, flat: Optional[torch.Tensor] = None, async_op: bool = False):
+    """SUM all-reduce of the gradients over the view-sharding ranks; NCCL over NVLink when the process group is NCCL.
+
+    flat: the ONE fp32 buffer [texture S*S*3 | verts V*3] the gradients are views of (StyleOptimizer keeps one):
+    reduced in place as a single collective, no gather / scatter passes around it.  Without it every gradient is
+    reduced in place on its own.  async_op=True returns the work handle(s) to `.wait()` on, so the caller can run
+    view-independent work (the mesh regularisers) while the collective is in flight."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return
-    grads = [p.grad for p in params if p.grad is not None]
-    if not grads:
-        return
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    off = 0
-    for g in grads:
-        n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
-        off += n
+        return []
+    if flat is not None:
+        bufs = [flat]
+    else:
+        bufs = [p.grad for p in params if p.grad is not None]
+    works = [dist.all_reduce(b, op=dist.ReduceOp.SUM, group=group, async_op=async_op) for b in bufs]
+    return [w for w in works if w is not None]
 
 
 DEFAULT_WEIGHTS = {"main_loss_weight": 3.0, "mesh_verts_weight": 1.0, "mesh_edge_loss_weight": 1.0,
@@ -77,6 +77,16 @@ class StyleOptimizer:
         if target in ("texture", "both"):
             params.append(self.colour.requires_grad_(True))
         self.params = params
+        # ONE flat fp32 gradient buffer; every parameter's .grad is a view of it for the life of the optimiser:
+        # zeroed with one fill, all-reduced in place as one collective, read by Adam where it lies
+        # (each parameter starts on a 256-byte boundary so vectorised kernels keep their fast path)
+        starts, off = [], 0
+        for p in params:
+            starts.append(off)
+            off += -(-p.numel() // 64) * 64
+        self._flat_grad = torch.zeros(off, device=dev, dtype=torch.float32)
+        for p, o in zip(params, starts):
+            p.grad = self._flat_grad[o:o + p.numel()].view_as(p)
         self.weights = dict(DEFAULT_WEIGHTS, **(weights or {}))
         # cuDNN's tensor-core convolutions are NHWC kernels: with NCHW tensors torch wraps every conv in
         # nchw<->nhwc transposes (~20 % of a step).  channels_last keeps activations NHWC end to end.
@@ -130,6 +140,33 @@ class StyleOptimizer:
                 + w["mesh_laplacian_smoothing_weight"] * ml.laplacian_smoothing(self.verts, self.faces, edges=self._edges)
                 + w["mesh_normal_consistency_weight"] * ml.normal_consistency(self.verts, self.faces))
 
+    # ---- cache of the loop constants (content feature, style Grams): keyed on CONTENT, never on addresses ----------
+    # The caching allocator hands the address of a freed per-batch temporary (R[idx].to(dev), the reference's own
+    # batching loop) to the next one, and an in-place edit keeps the address: a data_ptr key would return the
+    # constants of other cameras or another style image without an error.
+    def _remember_constants(self, slot, R, T, style_img, content_feat, grams) -> None:
+        inputs = (R, T, style_img)
+        self._cache[slot] = dict(inputs=inputs, versions=tuple(t._version for t in inputs),
+                                 copies=tuple(t.detach().clone() for t in inputs), content_feat=content_feat,
+                                 grams=grams)
+
+    def _constants_cached_for(self, slot, R, T, style_img) -> bool:
+        """slot: which micro-batch of the step (its first view); every slot keeps its own constants."""
+        c = self._cache.get(slot)
+        if not c:
+            return False
+        inputs = (R, T, style_img)
+        # fast path, no device work: the very tensor objects of the cached call (the cache keeps them alive, so their
+        # storage cannot have been recycled) and no in-place write since (tensor._version)
+        if all(a is b for a, b in zip(inputs, c["inputs"])) and tuple(t._version for t in inputs) == c["versions"]:
+            return True
+        # otherwise compare the values with the private copies (one small device reduction + host read per call)
+        same = all(a.shape == b.shape and a.device == b.device and a.dtype == b.dtype and bool(torch.equal(a, b))
+                   for a, b in zip(inputs, c["copies"]))
+        if same:        # re-arm the fast path for these objects
+            c["inputs"], c["versions"] = inputs, tuple(t._version for t in inputs)
+        return same
+
     def _export_images(self, images: torch.Tensor, images_out: torch.Tensor) -> None:
         """Device -> pinned-host copy of this step's renders on a side stream, so that it overlaps the VGG passes
         that follow instead of trailing the step (the reference dumps every view every step,
@@ -144,15 +181,11 @@ class StyleOptimizer:
             self.images_ready.record(self._copy_stream)
         images.record_stream(self._copy_stream)
 
-    def step(self, R: torch.Tensor, T: torch.Tensor, style_img: torch.Tensor,
-             images_out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """One optimisation iteration over the views (R, T) held by this rank; returns the loss (device scalar).
-        images_out: optional pinned host tensor (B,3,H,W) that receives this step's rendered views asynchronously
-        (wait on `self.images_ready` before reading it)."""
-        self.optimizer.zero_grad(set_to_none=True)
-        key = (R.data_ptr(), T.data_ptr(), style_img.data_ptr())
-        if self.cache_constants and self._cache.get("key") == key:
-            content_feat, grams = self._cache["content_feat"], self._cache["grams"]
+    def _views_loss(self, R, T, style_img, images_out, cache_slot):
+        """Perceptual loss (losses.py:12-44) of the views (R, T): content render + constants, current render, VGG walk."""
+        if self.cache_constants and self._constants_cached_for(cache_slot, R, T, style_img):
+            c = self._cache[cache_slot]
+            content_feat, grams = c["content_feat"], c["grams"]
         else:
             with torch.no_grad():
                 content_imgs, _ = self._render(self.verts0, self.content_colour, R, T)         # second_approach.py:160
@@ -160,25 +193,48 @@ class StyleOptimizer:
             content_feat, grams = losses.content_and_style_constants(content_imgs, style_img, self.vgg, self.precision,
                                                                      self.style_weights)
             if self.cache_constants:
-                self._cache = dict(key=key, content_feat=content_feat, grams=grams)
+                self._remember_constants(cache_slot, R, T, style_img, content_feat, grams)
         current_imgs, _ = self._render(self.verts, self.colour, R, T)                           # :165
         if images_out is not None:
             self._export_images(current_imgs.detach(), images_out)
-        loss = losses.perceptual_loss_of_images(self._nn_input(current_imgs), self.vgg, content_feat, grams,
+        self.last_images = current_imgs.detach()
+        return losses.perceptual_loss_of_images(self._nn_input(current_imgs), self.vgg, content_feat, grams,
                                                 self.style_weight, self.content_weight, self.precision)
-        if self.target != "texture":                                                            # losses.py:108-124
-            # the perceptual term is a mean over views (sharded: scale by 1/world); the regularisers are
-            # view-independent and identical on every rank, so they are added once, after the all-reduce
-            loss = self.weights["main_loss_weight"] * loss
-        (loss / self.world_size).backward()                                                     # :188
-        allreduce_gradients(self.params, self.group)
+
+    def step(self, R: torch.Tensor, T: torch.Tensor, style_img: torch.Tensor,
+             images_out: Optional[torch.Tensor] = None, micro_batch: Optional[int] = None) -> torch.Tensor:
+        """One optimisation iteration over the views (R, T) held by this rank; returns the loss (device scalar).
+        images_out: optional pinned host tensor (B,3,H,W) that receives this step's rendered views asynchronously
+        (wait on `self.images_ready` before reading it).
+        micro_batch: render / walk the VGG over this many views at a time and ACCUMULATE their gradients into the one
+        Adam step (the loss is a mean over views, losses.py:31,38, so a chunk of b of the B views weighs b / B): the
+        same iteration as one B-view batch with the activations of only `micro_batch` views alive."""
+        B = R.shape[0]
+        mb = B if not micro_batch else max(1, min(int(micro_batch), B))
+        self._flat_grad.zero_()         # the .grad views stay in place (optimizer.zero_grad(set_to_none=False) as one fill)
+        main_w = self.weights["main_loss_weight"] if self.target != "texture" else 1.0          # losses.py:108-124
+        loss = None
+        for s in range(0, B, mb):
+            Rm, Tm = (R, T) if mb == B else (R[s:s + mb], T[s:s + mb])
+            out_m = None if images_out is None else (images_out if mb == B else images_out[s:s + mb])
+            part = main_w * self._views_loss(Rm, Tm, style_img, out_m, s) * (Rm.shape[0] / B)
+            (part / self.world_size).backward()                                                 # :188
+            loss = part.detach() if loss is None else loss + part.detach()
+        # ONE collective per iteration, issued asynchronously: the regularisers are view-independent and identical on
+        # every rank, so their forward + backward run while the reduce is in flight and are added once, after it
+        works = allreduce_gradients(self.params, self.group, flat=self._flat_grad, async_op=True)
         if self.target != "texture":
             reg = self._regularisers()
-            reg.backward()
-            loss = loss + reg
+            (g_verts,) = torch.autograd.grad(reg, self.verts)
+            for w in works:
+                w.wait()
+            self.verts.grad.add_(g_verts)
+            loss = loss + reg.detach()
+        else:
+            for w in works:
+                w.wait()
         self.optimizer.step()                                                                   # :189
-        self.last_images = current_imgs.detach()
-        return loss.detach()
+        return loss
 
 
 class TextureStyleOptimizer(StyleOptimizer):

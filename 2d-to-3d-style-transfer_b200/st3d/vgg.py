@@ -112,7 +112,7 @@ class _MaxPool2x2Fn(torch.autograd.Function):
 
 class FusedMaxPool(nn.Module):
     """MaxPool2d(2, 2) on libst3d's NHWC kernels when the input allows it (CUDA fp32 channels_last, even sides,
-    C % 4 == 0), torch's pooling otherwise.  `after_relu`: the input is a post-ReLU activation, so the backward may
+    C % 4 == 0), torch's CUDA pooling for other CUDA shapes; CPU tensors raise.  `after_relu`: the input is a post-ReLU activation, so the backward may
     apply that ReLU's mask in the same pass (idempotent with a ReLU backward done elsewhere)."""
 
     def __init__(self, pool: nn.MaxPool2d, after_relu: bool = False):
@@ -130,7 +130,9 @@ class FusedMaxPool(nn.Module):
     def forward(self, x):
         if _ops().maxpool_supported(x):
             return _MaxPool2x2Fn.apply(x, self.after_relu)
-        return self.pool(x)
+        if not x.is_cuda:
+            raise RuntimeError("FusedMaxPool: CPU tensor -- the fused VGG runs on CUDA only (libst3d has no CPU path)")
+        return self.pool(x)     # CUDA tensor of a shape / layout the NHWC kernels do not take: torch's CUDA pooling
 
 
 class FusedConvReLU(nn.Module):
@@ -149,7 +151,8 @@ class FusedConvReLU(nn.Module):
     def forward(self, x):
         c = self.conv
         if not x.is_cuda:
-            return torch.relu_(c(x))
+            raise RuntimeError("FusedConvReLU: CPU tensor -- the fused VGG runs on CUDA only (cuDNN's fused entry point; "
+                               "libst3d has no CPU path)")
         bias = c.bias if c.bias is not None else torch.zeros(c.out_channels, device=x.device, dtype=x.dtype)
         return _ConvBiasReLUFn.apply(x, c.weight, bias, tuple(c.stride), tuple(c.padding), tuple(c.dilation), c.groups,
                                      self.feeds_masking_pool and not self.tapped)

@@ -2,7 +2,8 @@
 """bench.py -- style-optimisation iterations/sec on B200 (BASELINE.json metric, configs[1]).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (libst3d kernels)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port), real N-view steps
+    python bench.py --impl torch_unfused --steps K ...       # GPU stand-in for the reference's PyTorch3D-CUDA path
 
 One step = one optimisation iteration of second_approach.py:147-190 (`texture` target) over the views a
 rank holds: render content mesh -> render current mesh -> VGG-19 features (torch/cuDNN, out of scope but
@@ -36,7 +37,7 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="st3d", choices=["st3d", "reference"])
+    ap.add_argument("--impl", default="st3d", choices=["st3d", "reference", "torch_unfused"])
     ap.add_argument("--views", type=int, default=8, help="views per GPU")
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
@@ -46,13 +47,15 @@ def parse_args():
                     help="let cuDNN time its convolution algorithms per shape (torch.backends.cudnn.benchmark)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the e2e / cached-constants legs")
+    ap.add_argument("--no-standin", action="store_true", help="skip the unfused-torch GPU stand-in and the cuBLAS Gram A/B")
+    ap.add_argument("--no-scaling-128v", action="store_true", help="skip the fixed-128-view strong-scaling record")
     ap.add_argument("--profile-run", action="store_true",
                     help="for ncu captures only: honour --warmup < 3 (a number from such a run is never reported)")
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------------------------
-# workload (shared by both arms): cow mesh, synthetic style image, seeded random-init VGG-19
+# workload (shared by all arms): cow mesh, Style_1, seeded random-init VGG-19
 # ------------------------------------------------------------------------------------------------
 def load_workload(size):
     import numpy as np
@@ -67,10 +70,24 @@ def load_workload(size):
     # first_approach.py:90-100 / second_approach.py: the texture is resized to size x size (bilinear)
     tex = F.interpolate(tex.permute(2, 0, 1)[None], size=(size, size), mode="bilinear", align_corners=False)[0]
     tex = tex.permute(1, 2, 0).contiguous()
-    g = torch.Generator().manual_seed(0)
-    low = torch.rand(1, 3, size // 16, size // 16, generator=g)
-    style = F.interpolate(low, size=(size, size), mode="bicubic", align_corners=False).clamp(0, 1).contiguous()
-    return dict(verts=verts, faces=faces, verts_uvs=uvs, faces_uvs=fuvs, texture=tex, style=style)
+    return dict(verts=verts, faces=faces, verts_uvs=uvs, faces_uvs=fuvs, texture=tex, style=style_image(size))
+
+
+def style_image(size, name="style_1"):
+    """The reference's imgs/Style_1.jpg (second_approach.py:26), from the committed 512^2 copy in
+    tests/golden/styles.npz, resized to size x size as utils.py:34-44 does: (1,3,size,size) in [0,1]."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    a = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "styles.npz"))[name]).float() / 255.0
+    x = a.permute(2, 0, 1)[None]
+    if x.shape[-1] != size:
+        x = F.interpolate(x, size=(size, size), mode="bilinear", align_corners=False)
+    return x.contiguous()
+
+
+DATA = ("cow mesh + Style_1 image from the reference's own assets (tests/golden fixtures; Style_1 stored at 512^2) + "
+        "seeded random-init VGG-19 (ImageNet weights unavailable offline)")
 
 
 def seeded_vgg():
@@ -151,62 +168,108 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's CPU path (oracle port; PyTorch3D itself is not installable here)
 # ------------------------------------------------------------------------------------------------
-def cpu_one_view_iterations(args, n_timed, n_warm):
-    """Times `n_timed` one-view optimisation iterations on the host cores; returns seconds per one-view step."""
+def cpu_iterations(args, total_views, views_per_step, n_timed, n_warm, budget_s=None):
+    """Times optimisation iterations of second_approach.py:147-190 on the host cores, `views_per_step` views each
+    out of `total_views` cameras (views_per_step == total_views is the real iteration of the job; 1 is the bounded
+    sample of the GPU arm's cpu_baseline).
+    Every iteration does what the reference does: content render, style image repeated to the batch size, three VGG
+    walks, loss, backward, Adam.  Returns (seconds per step, threads, steps actually timed, warm-up steps run).
+    budget_s: if the first step shows that n_warm + n_timed steps would not fit, fewer are run (never fewer than
+    1 + 3) and the caller reports the count it got."""
     import torch
     from oracle import loss_oracle as lo
     from oracle import render_oracle as ro
     # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
-    torch.set_num_threads(os.cpu_count() or 1)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
     w = load_workload(args.size)
     vgg = seeded_vgg()
-    R, T = cameras(args.views)
+    R, T = cameras(total_views)
     tex0 = w["texture"]
     tex = tex0.clone().requires_grad_(True)
     opt = torch.optim.Adam([tex], lr=0.01)
-    threads = os.cpu_count() or 1
     kw = dict(verts_uvs=w["verts_uvs"], faces_uvs=w["faces_uvs"], nthreads=threads)
-    times = []
-    for i in range(n_warm + n_timed):
-        v = i % args.views
+    B = views_per_step
+    times, i, warm_run = [], 0, 0
+    while len(times) < n_timed:
+        lo_v = (i * B) % total_views
+        idx = [(lo_v + j) % total_views for j in range(B)]
+        Rb, Tb = R[idx], T[idx]
         t0 = time.perf_counter()
         opt.zero_grad()
+        style = w["style"].repeat(B, 1, 1, 1)                                               # second_approach.py:157
         with torch.no_grad():
-            content, _ = ro.images_and_masks(ro.render_views(w["verts"], w["faces"], R[v:v + 1], T[v:v + 1], args.size,
-                                                             texture=tex0, **kw))
-        current, _ = ro.images_and_masks(ro.render_views(w["verts"], w["faces"], R[v:v + 1], T[v:v + 1], args.size,
-                                                         texture=tex, **kw))
-        loss = lo.perceptual_loss(current, content, w["style"], vgg, 1e6, 1.0)
+            content, _ = ro.images_and_masks(ro.render_views(w["verts"], w["faces"], Rb, Tb, args.size, texture=tex0, **kw))
+        current, _ = ro.images_and_masks(ro.render_views(w["verts"], w["faces"], Rb, Tb, args.size, texture=tex, **kw))
+        loss = lo.perceptual_loss(current, content, style, vgg, 1e6, 1.0)
         loss.backward()
         opt.step()
         float(loss.detach())
+        dt = time.perf_counter() - t0
+        if i == 0 and budget_s is not None and dt * (n_warm + n_timed) > budget_s:
+            n_warm = 1
+            n_timed = max(3, min(n_timed, int(budget_s / dt) - 1))
         if i >= n_warm:
-            times.append(time.perf_counter() - t0)
-    return sum(times) / len(times), threads
+            times.append(dt)
+        else:
+            warm_run += 1
+        i += 1
+    return sum(times) / len(times), threads, len(times), warm_run
 
 
-def cpu_baseline_dict(args, sec_per_view, threads, n_timed):
-    return {"value": 1.0 / (sec_per_view * args.views), "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{n_timed} one-view iterations at {args.size}^2 (1 of {args.views} views per step); an "
-                      f"{args.views}-view iteration costs {args.views}x (every stage is per-view); CPU restatement of the "
-                      "PyTorch3D path (library unavailable) + the reference's loss arithmetic, all host threads",
-            "sec_per_view_iteration": sec_per_view}
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_baseline_dict(args, sec_per_step, views_per_step, threads, n_timed, n_warm):
+    """value: 8-view-iteration equivalents per second (the unit of the GPU arm's `value`)."""
+    import torch
+    sec_iter = sec_per_step * args.views / views_per_step
+    if views_per_step >= args.views:
+        sample = f"{n_timed} timed + {n_warm} warm-up FULL iterations ({views_per_step} views x {args.size}^2 each)"
+    else:
+        sample = (f"{n_timed} timed + {n_warm} warm-up iterations of {views_per_step} of the {args.views} views at {args.size}^2 "
+                  f"(bounded sample; every stage of the iteration is per-view, so a full iteration costs "
+                  f"{args.views // views_per_step}x; --impl reference times full iterations)")
+    return {"value": 1.0 / sec_iter, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": sample + "; CPU restatement of the PyTorch3D path (library unavailable) + the reference's loss "
+                               "arithmetic, compute only (no PNG / log writes), all host threads",
+            "sec_per_step": sec_per_step, "views_per_step": views_per_step, "cpu_model": cpu_model(),
+            "os_cpu_count": os.cpu_count(), "torch_threads": torch.get_num_threads()}
 
 
 def run_reference(args):
+    """The reference's CPU path on the box's host cores: every step is a REAL iteration over all args.views views
+    (ms_per_step x steps is the time this arm actually spent in its timed region)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
-    sec, threads = cpu_one_view_iterations(args, max(args.steps, 1), max(args.warmup, 0))
-    value = 1.0 / (sec * args.views)
-    cb = cpu_baseline_dict(args, sec, threads, args.steps)
-    return json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * args.views * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "cow mesh fixture + synthetic style image + random-init VGG-19",
-        "config": workload_config(args, 1), "cpu_baseline": cb,
+    budget = float(os.environ.get("ST3D_REF_BUDGET_S", "240"))
+    # the GPU arm's job at --gpus N is N x args.views views per iteration (weak scaling): the same job here
+    world = max(1, args.gpus)
+    total = args.views * world
+    sec, threads, n_timed, n_warm = cpu_iterations(args, total, total, max(args.steps, 1), max(args.warmup, 0), budget)
+    value = world / sec                 # args.views-view-iteration equivalents per second, like the GPU arm
+    cb = cpu_baseline_dict(args, sec, total, threads, n_timed, n_warm)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": n_timed,
+        "warmup": n_warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": DATA,
+        "config": workload_config(args, world), "cpu_baseline": cb,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    })
+    }
+    if n_timed != args.steps or n_warm != args.warmup:
+        out["steps_requested"], out["warmup_requested"] = args.steps, args.warmup
+        out["note"] = (f"the first iteration showed that {args.warmup}+{args.steps} full iterations would exceed the "
+                       f"{budget:.0f} s budget of this arm (ST3D_REF_BUDGET_S): `steps`/`warmup` are what was run")
+    return json.dumps(out)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -241,6 +304,269 @@ def algorithmic_bytes(op, key, tex=512):
         B, C, H, W = key
         return B * C * H * W * 9
     return None
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU stand-in for the reference's PyTorch3D-CUDA path: the reference's own loop structure
+# on the GPU with NOTHING fused -- one renderer call per view (utils.py:68-76), Fragments -> interpolation ->
+# grid_sample -> elementwise blend as separate launches, stock torchvision VGG (NCHW, separate ReLUs), torch.bmm
+# Gram + sub / pow / mean, autograd backward, stock Adam.  PyTorch3D itself cannot be installed here, so the
+# Fragments come from this library's operator-boundary kernel (the `_C.rasterize_meshes` equivalent) -- which is
+# generous to the comparator; everything after it is stock torch / cuBLAS / cuDNN.
+# ------------------------------------------------------------------------------------------------
+def _torch_features(x, vgg):
+    taps = {"0": "conv1_1", "5": "conv2_1", "10": "conv3_1", "19": "conv4_1", "21": "conv4_2", "28": "conv5_1"}
+    out = {}
+    for name, layer in vgg._modules.items():        # all 37 modules, as style_transfer.py:21-26 does
+        x = layer(x)
+        if name in taps:
+            out[taps[name]] = x
+    return out
+
+
+def _torch_gram(t):
+    import torch
+    b, c, h, w = t.shape
+    f = t.view(b, c, h * w)
+    return torch.bmm(f, f.transpose(1, 2))
+
+
+def _torch_perceptual(current, content, style, vgg, style_weight=1e6, content_weight=1.0):
+    """losses.py:12-44 in stock torch ops."""
+    import torch
+    content_f = _torch_features(content, vgg)["conv4_2"]
+    style_f = _torch_features(style, vgg)
+    grams = {k: _torch_gram(v) for k, v in style_f.items() if k != "conv4_2"}
+    cur = _torch_features(current, vgg)
+    loss = content_weight * torch.mean((cur["conv4_2"] - content_f) ** 2)
+    s = 0
+    for k, g in grams.items():
+        f = cur[k]
+        s = s + torch.mean((_torch_gram(f) - g) ** 2) / (f.shape[1] ** 2 * f.shape[2] ** 2)
+    return loss + style_weight * s
+
+
+def torch_unfused_arm(args, dev, n_timed, n_warm=3):
+    """-> dict(ms_per_step, it_per_s, ...) of the unfused stand-in on configs[1]."""
+    import torch
+    compat = os.path.join(PKG, "compat")
+    if compat not in sys.path:
+        sys.path.insert(0, compat)
+    from pytorch3d.renderer import (AmbientLights, FoVPerspectiveCameras, MeshRasterizer, RasterizationSettings,
+                                    SoftPhongShader, TexturesUV)
+    from pytorch3d.structures import Meshes
+    w = load_workload(args.size)
+    vgg = seeded_vgg().to(dev)                      # stock module: NCHW, Conv2d / ReLU(inplace) / MaxPool2d
+    R, T = cameras(args.views)
+    cams = FoVPerspectiveCameras(R=R.to(dev), T=T.to(dev), device=dev)
+    cam_list = [cams[i] for i in range(args.views)]
+    rasterizer = MeshRasterizer(cameras=FoVPerspectiveCameras(device=dev),
+                                raster_settings=RasterizationSettings(image_size=args.size, blur_radius=0.0, faces_per_pixel=1))
+    shader = SoftPhongShader(device=dev, lights=AmbientLights(device=dev))
+    verts, faces = w["verts"].to(dev), w["faces"].to(dev)
+    uvs, fuvs = w["verts_uvs"][None].to(dev), w["faces_uvs"][None].to(dev)
+    tex0 = w["texture"][None].to(dev)
+    tex = tex0.clone().requires_grad_(True)
+    style1 = w["style"].to(dev)
+    opt = torch.optim.Adam([tex], lr=0.01)
+
+    def render(texture):
+        mesh = Meshes(verts=[verts], faces=[faces], textures=TexturesUV(verts_uvs=uvs, faces_uvs=fuvs, maps=texture))
+        imgs, masks = [], []
+        for cam in cam_list:                         # utils.py:68-76: one renderer call per view
+            frags = rasterizer(mesh, cameras=cam)
+            rgba = shader(frags, mesh, cameras=cam)  # Fragments -> interp -> grid_sample -> blend, unfused
+            imgs.append(rgba[0, ..., :3].permute(2, 0, 1))
+            masks.append((rgba[0, ..., 3] > 0).float().unsqueeze(0))
+        return torch.stack(imgs, dim=0), torch.stack(masks, dim=0)
+
+    def step():
+        opt.zero_grad()
+        style = style1.repeat(args.views, 1, 1, 1)                      # second_approach.py:157
+        with torch.no_grad():
+            content, _ = render(tex0)
+        current, _ = render(tex)
+        loss = _torch_perceptual(current, content, style, vgg)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(n_warm):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n_timed):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n_timed
+    return {"ms_per_step": ms, "it_per_s": 1e3 / ms, "steps": n_timed, "warmup": n_warm, "final_loss": float(loss),
+            "label": "STAND-IN for the reference's PyTorch3D-CUDA path (PyTorch3D is not installable here): per-view renderer "
+                     "calls, Fragments from libst3d's operator-boundary rasterizer, then unfused torch ops (interpolation, "
+                     "grid_sample, elementwise blend), stock torchvision VGG-19 (NCHW), torch.bmm Gram + sub/pow/mean, "
+                     "autograd backward, stock Adam; device-resident, torch default precision (fp32 matmul, cuDNN TF32 allowed)"}
+
+
+def run_torch_unfused(args):
+    import torch
+    if int(os.environ.get("RANK", "0")) != 0:
+        return None
+    if not torch.cuda.is_available():
+        raise RuntimeError("--impl torch_unfused needs a CUDA device")
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    r = torch_unfused_arm(args, dev, max(args.steps, 1), max(args.warmup, 3))
+    return json.dumps({"impl": "torch_unfused", "metric": METRIC, "value": r["it_per_s"], "unit": UNIT, "n_gpus": 1,
+                       "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": DATA,
+                       "config": workload_config(args, 1), "label": r["label"], "final_loss": r["final_loss"]})
+
+
+def gram_vs_cublas(args, dev, reps=20):
+    """Per style layer at the bench's shapes: this library's Gram + MSE forward and Gram backward (tcgen05 kind::tf32,
+    channels_last features read in place) against what the reference runs -- torch.bmm + sub/pow/mean forward,
+    autograd (two more cuBLAS GEMMs + elementwise) backward -- in fp32 and with allow_tf32."""
+    import torch
+    from st3d import ops
+    B, S = args.views, args.size
+    shapes = [("conv1_1", 64, S), ("conv2_1", 128, S // 2), ("conv3_1", 256, S // 4), ("conv4_1", 512, S // 8),
+              ("conv5_1", 512, S // 16)]
+    out = {}
+    prev = torch.backends.cuda.matmul.allow_tf32
+    gen = torch.Generator(device=dev).manual_seed(0)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    try:
+        for name, C, H in shapes:
+            feat = torch.relu(torch.randn(B, C, H, H, device=dev, generator=gen))
+            target = torch.randn(1, C, C, device=dev, generator=gen)
+            f_cl = feat.contiguous(memory_format=torch.channels_last)
+            scale = 1.0 / (B * C * C) / (float(C) ** 2 * float(H) ** 2)
+            loss = torch.zeros(1, device=dev)
+            grad_out = torch.empty_like(f_cl)
+
+            def ours():
+                dgram, _ = ops.gram_mse_forward(f_cl, target, scale, loss, precision=args.precision)
+                ops.gram_backward(f_cl, dgram, 1.0, out=grad_out, precision=args.precision)
+
+            leaf = feat.clone().requires_grad_(True)
+
+            def theirs():
+                leaf.grad = None
+                g = _torch_gram(leaf)
+                l = torch.mean((g - target) ** 2) / (C ** 2 * H ** 2)
+                l.backward()
+
+            row = {"B": B, "C": C, "HW": H * H, "st3d_ms": round(timed(ours), 4)}
+            torch.backends.cuda.matmul.allow_tf32 = False
+            row["torch_fp32_ms"] = round(timed(theirs), 4)
+            torch.backends.cuda.matmul.allow_tf32 = True
+            row["torch_tf32_ms"] = round(timed(theirs), 4)
+            row["speedup_vs_fp32"] = round(row["torch_fp32_ms"] / row["st3d_ms"], 2)
+            row["speedup_vs_tf32"] = round(row["torch_tf32_ms"] / row["st3d_ms"], 2)
+            out[name] = row
+            del feat, f_cl, leaf, grad_out
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    tot = {k: round(sum(r[k] for r in out.values()), 4) for k in ("st3d_ms", "torch_fp32_ms", "torch_tf32_ms")}
+    out["all_layers"] = dict(tot, speedup_vs_fp32=round(tot["torch_fp32_ms"] / tot["st3d_ms"], 2),
+                             speedup_vs_tf32=round(tot["torch_tf32_ms"] / tot["st3d_ms"], 2))
+    out["what"] = ("style-loss body of one layer, forward + backward into the feature map: st3d_gram_mse_forward + "
+                   "st3d_gram_backward (" + args.precision + ") vs torch.bmm + sub/pow/mean + autograd (style_transfer.py:31-35, "
+                   "losses.py:35-39); CUDA events, " + str(reps) + " repetitions after 3 warm-ups")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs[4]: ~1.5 M faces, a FIXED total of 128 views x 1024^2 split over the ranks (strong scaling)
+# ------------------------------------------------------------------------------------------------
+def scaling_128v(dev, world, rank, vgg, precision, total_views=128, size=1024, levels=4, micro_batch=16, steps=3, warm=2):
+    """One optimisation iteration = all 128 views into ONE Adam step: every rank renders its 128 / world views in
+    micro-batches of 16 (gradients accumulate), then one NCCL all-reduce of the flat texture gradient.  At world = 1
+    that is 8 micro-batches on one GPU; at world = 8 one micro-batch per GPU: the same job, so the per-N times give
+    strong-scaling efficiency directly."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from st3d import meshgen, ops
+    from st3d.optimize import StyleOptimizer
+    if total_views % world:
+        return {"skipped": f"{total_views} views do not split over {world} ranks"}
+    d = np.load(os.path.join(ROOT, "tests", "golden", "cow_mesh.npz"))
+    verts, faces, uvs, fuvs = meshgen.subdivided_uv_mesh(torch.from_numpy(d["verts"]), torch.from_numpy(d["faces"]).long(),
+                                                         torch.from_numpy(d["verts_uvs"]),
+                                                         torch.from_numpy(d["faces_uvs"]).long(), levels)
+    tex = torch.from_numpy(d["texture"]).float() / 255.0
+    tex = F.interpolate(tex.permute(2, 0, 1)[None], size=(size, size), mode="bilinear", align_corners=False)[0]
+    tex = tex.permute(1, 2, 0).contiguous()
+    style = style_image(size).to(dev)
+    per_rank = total_views // world
+    R, T = cameras(total_views)
+    sl = slice(rank * per_rank, (rank + 1) * per_rank)
+    R, T = R[sl].contiguous().to(dev), T[sl].contiguous().to(dev)
+    opt = StyleOptimizer(verts.to(dev), faces.to(dev), vgg, size, verts_uvs=uvs.to(dev), faces_uvs=fuvs.to(dev),
+                         texture=tex.to(dev), target="texture", lr=0.01, precision=precision, world_size=world)
+    mb = min(micro_batch, per_rank)
+    for _ in range(warm):
+        opt.step(R, T, style, micro_batch=mb)
+    torch.cuda.synchronize()
+    ops.poll_overflow(block=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = opt.step(R, T, style, micro_batch=mb)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    ar_ms = None
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        # the collective alone (the flat texture gradient, in place), CUDA events, max over ranks
+        buf = torch.zeros_like(opt._flat_grad)
+        for _ in range(3):
+            dist.all_reduce(buf)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(10):
+            dist.all_reduce(buf)
+        a1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a0.elapsed_time(a1) / 10], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ar_ms = float(t.item())
+    peak = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    out = {"workload": f"cow subdivided {levels}x ({faces.shape[0]} faces, {verts.shape[0]} verts), {total_views} views x "
+                       f"{size}^2 in total, texture {size}^2, Style_1, texture target, one Adam step per iteration",
+           "scaling": "strong", "n_gpus": world, "views_total": total_views, "views_per_gpu": per_rank, "micro_batch": mb,
+           "micro_batches_per_gpu": -(-per_rank // mb), "steps": steps, "warmup": warm,
+           "ms_per_iteration": ms, "it_per_s": 1e3 / ms, "views_per_s": total_views * 1e3 / ms,
+           "allreduce_ms": ar_ms, "allreduce_bytes": int(opt._flat_grad.numel() * 4), "peak_mem_GB": round(peak, 2),
+           "final_loss": float(loss),
+           "note": "strong-scaling efficiency at N = ms_per_iteration(N=1) / (N * ms_per_iteration(N)); the only collective "
+                   "is the in-place all-reduce of the flat texture gradient (allreduce_ms: that collective alone)"}
+    del opt
+    return out
 
 
 def c1_first_approach(dev, steps=200, size=256, run_cpu=True):
@@ -316,6 +642,19 @@ def c1_first_approach(dev, steps=200, size=256, run_cpu=True):
     return res
 
 
+def bind_to_gpu_numa_node(index):
+    """One process per GPU: keep the rank's host threads (Python launch loop, pinned-buffer copies) on the CPUs NVML
+    names as local to its GPU, so that 8 ranks do not share one NUMA node's cores and memory."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception:       # no NVML / not permitted: run unbound
+        return None
+
+
 def run_st3d(args):
     import torch
     import torch.distributed as dist
@@ -326,6 +665,7 @@ def run_st3d(args):
         raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = bind_to_gpu_numa_node(local) if world > 1 else None
     if args.cudnn_benchmark:
         torch.backends.cudnn.benchmark = True
     if world > 1:
@@ -441,7 +781,7 @@ def run_st3d(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (Gram products tf32 on tcgen05, fp32 accumulate)" if args.precision == "tf32" else "f32",
-        "data": "cow mesh fixture (reference objects/cow_mesh) + synthetic style image + seeded random-init VGG-19",
+        "data": DATA,
         "config": workload_config(args, world), "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roofline, "final_loss": final_loss,
         "stages_ms_per_step": stages, "ops_vs_hbm_roofline": op_table,
@@ -498,16 +838,32 @@ def run_st3d(args):
                                    "note": "content render + content/style VGG features computed once (they are "
                                            "constants of the loop); not the headline"}
 
-    if rank == 0 and world == 1 and not args.no_extras:
-        import gc
-        opt = opt2 = opt3 = None          # release the 8 x 512^2 iteration state before the small workload
+    import gc
+    opt = opt2 = opt3 = None              # release the 8 x 512^2 iteration state before the other workloads
+    gc.collect()
+    torch.cuda.empty_cache()
+    if affinity is not None:
+        out["host_cpus_per_rank"] = affinity
+    if not args.no_scaling_128v:
+        # BASELINE configs[4] / north_star "scaling efficiency from 1 to 8 GPUs at 128 views": every rank takes part
+        rec = scaling_128v(dev, world, rank, vgg, args.precision)
+        out["scaling_128v"] = rec
         gc.collect()
         torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_standin:
+        out["gpu_standin"] = torch_unfused_arm(args, dev, min(max(args.steps, 1), 10))
+        out["gpu_standin"]["st3d_speedup"] = out["gpu_standin"]["ms_per_step"] / ms_step
+        gc.collect()
+        torch.cuda.empty_cache()
+        out["gram_vs_cublas"] = gram_vs_cublas(args, dev)
+        gc.collect()
+        torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_extras:
         out["c1_first_approach"] = c1_first_approach(dev, run_cpu=not args.no_cpu_baseline)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n = 2
-        sec, threads = cpu_one_view_iterations(args, n, 1)
-        out["cpu_baseline"] = cpu_baseline_dict(args, sec, threads, n)
+        # >= 3 warm-up + >= 10 timed iterations; one view each keeps it to ~30 s of CPU work
+        sec, threads, n_timed, n_warm = cpu_iterations(args, args.views, 1, 10, 3)
+        out["cpu_baseline"] = cpu_baseline_dict(args, sec, 1, threads, n_timed, n_warm)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -537,7 +893,7 @@ class _QuietStdout:
 def main():
     args = parse_args()
     with _QuietStdout():
-        line = run_reference(args) if args.impl == "reference" else run_st3d(args)
+        line = {"reference": run_reference, "torch_unfused": run_torch_unfused, "st3d": run_st3d}[args.impl](args)
     if line is not None:
         print(line, flush=True)
 

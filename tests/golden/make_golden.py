@@ -7,6 +7,10 @@
    with the three regulariser names is registered in sys.modules so the file imports unmodified.
 2. cow_mesh.npz      -- geometry of the reference fixture objects/cow_mesh/cow.obj (+ its texture,
    bilinearly reduced to 256x256 uint8) so GPU-box tests/bench have the mesh BASELINE.json names.
+2b. bob_mesh.npz (objects/bob_mesh/bob.obj: quads, fan-triangulated; stands in for the missing bunny.obj of
+   BASELINE configs[2]), teapot_mesh.npz (objects/teapot_mesh/teapot.obj: no UVs -> per-vertex colours, configs[3]) and
+   styles.npz (imgs/Style_1.jpg at 512x512, Style_3/4/5 at 256x256, uint8, resized the way utils.py:34-44 does:
+   PIL bilinear to a square) so the GPU box can run configs 2-4 on the reference's own assets.
 3. render_golden.npz -- oracle renders (pix_to_face, rgba) of that mesh; NOT upstream PyTorch3D output
    (parity unpinned at that boundary), they freeze the oracle so regressions in it are caught.
 """
@@ -92,6 +96,27 @@ def make_cow():
     print("cow:", v.shape, f.shape, uv.shape)
 
 
+def make_bob_teapot_styles():
+    from PIL import Image
+    from oracle import render_oracle as ro
+    v, f, uv, fuv = ro.read_obj(os.path.join(REF, "objects/bob_mesh/bob.obj"))
+    img = Image.open(os.path.join(REF, "objects/bob_mesh/bob.png")).convert("RGB").resize((256, 256), Image.BILINEAR)
+    np.savez_compressed(os.path.join(HERE, "bob_mesh.npz"), verts=v.numpy(), faces=f.numpy().astype(np.int32),
+                        verts_uvs=uv.numpy(), faces_uvs=fuv.numpy().astype(np.int32), texture=np.asarray(img))
+    print("bob:", v.shape, f.shape, uv.shape)
+    v, f, uv, fuv = ro.read_obj(os.path.join(REF, "objects/teapot_mesh/teapot.obj"))
+    assert uv.numel() == 0
+    np.savez_compressed(os.path.join(HERE, "teapot_mesh.npz"), verts=v.numpy(), faces=f.numpy().astype(np.int32))
+    print("teapot:", v.shape, f.shape)
+    styles = {}
+    for name, file, size in (("style_1", "Style_1.jpg", 512), ("style_3", "Style_3.png", 256),
+                             ("style_4", "Style_4.jpeg", 256), ("style_5", "Style_5.png", 256)):
+        im = Image.open(os.path.join(REF, "imgs", file)).convert("RGB").resize((size, size), Image.BILINEAR)
+        styles[name] = np.asarray(im)
+    np.savez_compressed(os.path.join(HERE, "styles.npz"), **styles)
+    print("styles:", {k: v.shape for k, v in styles.items()})
+
+
 def make_render_golden():
     from oracle import render_oracle as ro
     d = np.load(os.path.join(HERE, "cow_mesh.npz"))
@@ -113,4 +138,5 @@ def make_render_golden():
 if __name__ == "__main__":
     make_loss_golden()
     make_cow()
+    make_bob_teapot_styles()
     make_render_golden()

@@ -141,9 +141,9 @@ def test_second_approach_iteration_matches_oracle(scene, target):
         want.backward()
         assert abs(first - want.item()) <= 2e-3 * abs(want.item()), (first, want.item())
         rel = lambda a, b: ((a - b).abs().max() / b.abs().max()).item()
-        assert rel(g_tex[0], tex_o.grad) <= 5e-3, rel(g_tex[0], tex_o.grad)
+        assert rel(g_tex[0], tex_o.grad) <= 2e-3, rel(g_tex[0], tex_o.grad)
         if target == "both":
-            assert rel(g_verts, verts_o.grad) <= 5e-3, rel(g_verts, verts_o.grad)
+            assert rel(g_verts, verts_o.grad) <= 2e-3, rel(g_verts, verts_o.grad)
     finally:
         torch.backends.cudnn.allow_tf32 = prev
 
@@ -292,7 +292,7 @@ def test_style_optimizer_targets(cow, target, mode):
         # content term is zero at the first iteration (current == content); regularisers at the initial mesh
         if target != "texture":
             want = WEIGHTS["main_loss_weight"] * want + lo._regularisers(cow["verts"], cow["verts"], cow["faces"], WEIGHTS)
-        assert abs(hist[0] - want.item()) <= 3e-3 * abs(want.item()), (hist[0], want.item())
+        assert abs(hist[0] - want.item()) <= 2e-3 * abs(want.item()), (hist[0], want.item())
     finally:
         torch.backends.cudnn.allow_tf32 = prev
 
@@ -327,7 +327,7 @@ def test_loss_trajectory_matches_oracle_loop(cow):
             want.append(loss.item())
         assert want[-1] < want[0]
         for g, w in zip(got, want):
-            assert abs(g - w) <= 5e-3 * abs(w), (got, want)
+            assert abs(g - w) <= 2e-3 * abs(w), (got, want)
     finally:
         torch.backends.cudnn.allow_tf32 = prev
 
@@ -413,3 +413,100 @@ def test_graphed_texture_fit_equals_the_eager_loop(cow):
     assert abs(loss_g.item() - loss_e.item()) <= 1e-5 * abs(loss_e.item()) + 1e-8
     assert (fit.texture.detach() - tex.detach()).abs().max().item() <= 1e-5
     assert (fit.texture.detach() - tex0.to(dev)).abs().max().item() >= 0.05      # ten Adam steps of 0.01 did happen
+
+
+def test_micro_batched_step_accumulates_the_same_gradient(cow):
+    """`step(..., micro_batch=b)` (the 128-view iteration of BASELINE configs[4] on one GPU) renders b views at a time and
+    accumulates into ONE Adam step: gradient, loss and updated texture equal those of the single-batch step."""
+    from st3d.optimize import TextureStyleOptimizer
+    dev = torch.device("cuda:0")
+    R, T = ro.random_cameras(4, generator=torch.Generator().manual_seed(21))
+    style = torch.rand(1, 3, S, S, generator=torch.Generator().manual_seed(22))
+    tex0 = torch.rand(S, S, 3, generator=torch.Generator().manual_seed(23))
+    vgg = _vgg(dev)
+    res = []
+    for mb in (None, 2, 3):
+        opt = TextureStyleOptimizer(cow["verts"].to(dev), cow["faces"].to(dev), cow["verts_uvs"].to(dev),
+                                    cow["faces_uvs"].to(dev), tex0.to(dev), vgg, S, lr=0.01, cache_constants=mb == 2)
+        for _ in range(2):
+            loss = opt.step(R.to(dev), T.to(dev), style.to(dev), micro_batch=mb)
+        res.append((loss.item(), opt._flat_grad.clone(), opt.texture.detach().clone()))
+    rel = lambda a, b: ((a - b).abs().max() / b.abs().max()).item()
+    for loss, grad, tex in res[1:]:
+        assert abs(loss - res[0][0]) <= 1e-3 * abs(res[0][0]), (loss, res[0][0])
+        assert rel(grad, res[0][1]) <= 1e-3, rel(grad, res[0][1])
+    assert (res[0][2] - tex0.to(dev)).abs().max().item() >= 0.005         # the two Adam steps did move the texture
+
+
+def test_constants_cache_is_keyed_on_content_not_addresses(cow):
+    """cache_constants=True: a new camera batch that lands on the address of a freed one, or an in-place edit of the
+    style image, must not return the stale content feature / style Grams."""
+    from st3d.optimize import TextureStyleOptimizer
+    dev = torch.device("cuda:0")
+    R, T = ro.random_cameras(4, generator=torch.Generator().manual_seed(31))
+    style = torch.rand(1, 3, S, S, generator=torch.Generator().manual_seed(32)).to(dev)
+    tex0 = torch.rand(S, S, 3, generator=torch.Generator().manual_seed(33))
+    vgg = _vgg(dev)
+
+    def fresh(cache):
+        return TextureStyleOptimizer(cow["verts"].to(dev), cow["faces"].to(dev), cow["verts_uvs"].to(dev),
+                                     cow["faces_uvs"].to(dev), tex0.to(dev), vgg, S, lr=0.0, cache_constants=cache)
+    cached, plain = fresh(True), fresh(False)
+    for idx in ([0, 1], [2, 3], [0, 1]):                # per-batch temporaries, as the reference's batching loop makes them
+        Rb, Tb = R[idx].to(dev), T[idx].to(dev)
+        a, b = cached.step(Rb, Tb, style).item(), plain.step(Rb, Tb, style).item()
+        assert abs(a - b) <= 1e-5 * abs(b), (idx, a, b)
+        del Rb, Tb
+    Rb, Tb = R[[0, 1]].to(dev), T[[0, 1]].to(dev)
+    a0 = cached.step(Rb, Tb, style).item()
+    assert cached._constants_cached_for(0, Rb, Tb, style)
+    style.mul_(0.5)                                     # in place: same address, new values
+    assert not cached._constants_cached_for(0, Rb, Tb, style)
+    a1, b1 = cached.step(Rb, Tb, style).item(), plain.step(Rb, Tb, style).item()
+    assert abs(a1 - b1) <= 1e-5 * abs(b1) and abs(a1 - a0) > 1e-3 * abs(a0)
+
+
+def test_constants_walk_equals_the_feature_walk_fused_and_unfused():
+    """content_and_style_constants (one VGG walk for both constant branches) against get_features + gram_matrix, for the
+    fused model AND the stock torchvision module whose ReLUs are separate in-place modules (the taps
+    must be the post-ReLU activations in both)."""
+    from st3d import functional as Fn
+    from st3d import losses
+    from st3d.vgg import fuse_vgg_features
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(41)
+    content, style = torch.rand(2, 3, S, S, generator=gen).to(dev), torch.rand(1, 3, S, S, generator=gen).to(dev)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        plain = _vgg(dev)
+        for model in (plain, fuse_vgg_features(_vgg(dev), channels_last=True)):
+            c, grams = losses.content_and_style_constants(content, style, model, "fp32")
+            with torch.no_grad():
+                want_c = losses.get_features(content, model)["conv4_2"]
+                want_g = {k: Fn.gram_matrix(v, "fp32") for k, v in losses.get_features(style, model).items() if k != "conv4_2"}
+            assert (c >= 0).all() and (c - want_c).abs().max().item() <= 1e-4 * want_c.abs().max().item()
+            assert set(grams) == set(want_g)
+            for k in want_g:
+                assert (grams[k] - want_g[k]).abs().max().item() <= 1e-4 * want_g[k].abs().max().item(), k
+        # and both agree with the oracle's walk on the host
+        vgg_cpu = _vgg("cpu")
+        want = lo.get_features(content.cpu(), vgg_cpu)["conv4_2"]
+        assert (c.cpu() - want).abs().max().item() <= 1e-3 * want.abs().max().item()
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_ops_run_on_the_device_of_their_tensors():
+    """Tensors on cuda:1 while cuda:0 is current: every op must launch on cuda:1."""
+    from st3d import ops
+    torch.cuda.set_device(0)
+    f = torch.relu(torch.randn(2, 64, 16, 16, device="cuda:1"))
+    G = ops.gram_forward(f, precision="tf32")
+    want = lo.gram_matrix(f.double().cpu())
+    assert G.device == f.device
+    assert ((G.double().cpu() - want).abs().max() / want.abs().max()).item() <= 2e-3
+    with pytest.raises(ValueError, match="share a device"):
+        ops.gram_mse_forward(f, torch.zeros(1, 64, 64, device="cuda:0"), 1.0, torch.zeros(1, device="cuda:1"))
+    assert torch.cuda.current_device() == 0

@@ -83,9 +83,9 @@ def test_gram_mse_and_backward(precision, tol, B, Bt, C, H, W):
     grad = ops.gram_backward(f.cuda(), dgram, 1.0, precision=precision)
     torch.cuda.synchronize()
     assert _relerr(gram, lo.gram_matrix(f.double())) <= tol
-    assert abs(loss.item() - want.item()) <= 2 * tol * abs(want.item()), (loss.item(), want.item())
+    assert abs(loss.item() - want.item()) <= tol * abs(want.item()), (loss.item(), want.item())
     assert grad.shape == f.shape
-    assert _relerr(grad, f64.grad) <= 2 * tol, f"grad error {_relerr(grad, f64.grad):.3e}"
+    assert _relerr(grad, f64.grad) <= tol, f"grad error {_relerr(grad, f64.grad):.3e}"
 
 
 @pytest.mark.parametrize("C,H,W", [(64, 40, 40), (128, 12, 20), (256, 16, 8), (512, 8, 12)])
@@ -181,17 +181,17 @@ def test_gram_channels_last_features(precision, tol, B, C, H, W):
     assert torch.equal(G, ops.gram_forward(fcl, precision=precision))            # deterministic
     loss = torch.zeros(1, device="cuda")
     dgram, _ = ops.gram_mse_forward(fcl, style.float().cuda(), scale, loss, precision=precision)
-    assert abs(loss.item() - want.item()) <= 2 * tol * abs(want.item())
+    assert abs(loss.item() - want.item()) <= tol * abs(want.item())
     grad = ops.gram_backward(fcl, dgram, 1.0, precision=precision)
     assert grad.shape == f.shape and grad.is_contiguous(memory_format=torch.channels_last)
-    assert _relerr(grad, f64.grad) <= 2 * tol, _relerr(grad, f64.grad)
+    assert _relerr(grad, f64.grad) <= tol, _relerr(grad, f64.grad)
     # same numbers as the NCHW path up to the arithmetic mode
     grad_nchw = ops.gram_backward(f.cuda(), dgram, 1.0, precision=precision)
-    assert _relerr(grad, grad_nchw.double()) <= 2 * tol
+    assert _relerr(grad, grad_nchw.double()) <= tol
     # accumulate into an existing channels_last buffer
     base = torch.ones_like(fcl)
     got = ops.gram_backward(fcl, dgram, 0.5, out=base, accumulate=True, precision=precision)
-    assert _relerr(got, 0.5 * f64.grad + 1.0) <= 2 * tol
+    assert _relerr(got, 0.5 * f64.grad + 1.0) <= tol
 
 
 def test_channels_last_autograd_and_mse():
@@ -207,8 +207,8 @@ def test_channels_last_autograd_and_mse():
     f64 = f.double().requires_grad_(True)
     want = 1e6 * lo.style_layer_loss(f64, tgt) + 3.0 * ((f64 - other.cpu().double()) ** 2).mean()
     want.backward()
-    assert abs(loss.item() - want.item()) <= 4e-3 * abs(want.item())
-    assert _relerr(fcl.grad, f64.grad) <= 4e-3
+    assert abs(loss.item() - want.item()) <= TOL_TC * abs(want.item())
+    assert _relerr(fcl.grad, f64.grad) <= TOL_TC, _relerr(fcl.grad, f64.grad)
 
 
 def test_blended_multi_style_targets():
@@ -236,7 +236,7 @@ def test_blended_multi_style_targets():
         for k in lo.STYLE_LAYERS:
             tgt = (lo.gram_matrix(sf[k]) * torch.tensor(wts).reshape(-1, 1, 1)).sum(0, keepdim=True)
             want = want + lo.style_layer_loss(cf[k], tgt)
-        assert abs(got.item() - want.item()) <= 3e-3 * abs(want.item()), (got.item(), want.item())
+        assert abs(got.item() - want.item()) <= TOL_TC * abs(want.item()), (got.item(), want.item())
     finally:
         torch.backends.cudnn.allow_tf32 = prev
 

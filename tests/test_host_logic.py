@@ -47,6 +47,35 @@ def test_get_features_walk():
         assert (a[k] >= 0).all()                 # in-place ReLU: every tap is post-ReLU
 
 
+def test_constants_walk_taps_post_relu_on_a_plain_vgg(monkeypatch):
+    """content_and_style_constants on a torchvision VGG whose ReLUs are separate in-place modules: the content feature
+    and the style Grams must be those of the POST-ReLU activations, as get_features (and the reference,
+    style_transfer.py:21-26) give them.  The Gram product is stood in by the oracle's on the CPU."""
+    import torchvision
+    from st3d import functional as Fn
+    from st3d import losses
+    monkeypatch.setattr(Fn, "gram_matrix", lambda t, precision=None: lo.gram_matrix(t))
+    torch.manual_seed(0)
+    vgg = torchvision.models.vgg19(weights=None).features.eval()
+    content, style = torch.rand(2, 3, 32, 32), torch.rand(1, 3, 32, 32)
+    with torch.no_grad():
+        want_c = lo.get_features(content.clone(), vgg)["conv4_2"]
+        want_s = {k: lo.gram_matrix(v) for k, v in lo.get_features(style.clone(), vgg).items() if k != "conv4_2"}
+    got_c, got_g = losses.content_and_style_constants(content, style, vgg)
+    assert (got_c >= 0).all() and torch.allclose(got_c, want_c, atol=1e-6)
+    assert set(got_g) == set(want_s)
+    for k in want_s:
+        assert torch.allclose(got_g[k], want_s[k], rtol=1e-5, atol=1e-6 * float(want_s[k].abs().max()))
+    # blended targets (BASELINE configs[3]) and the different-size branch go through the same taps
+    styles = torch.rand(2, 3, 32, 32)
+    _, blended = losses.content_and_style_constants(content, styles, vgg, style_weights=[0.25, 0.75])
+    with torch.no_grad():
+        each = [{k: lo.gram_matrix(v) for k, v in lo.get_features(styles[j:j + 1].clone(), vgg).items()} for j in range(2)]
+    for k in want_s:
+        want = 0.25 * each[0][k] + 0.75 * each[1][k]
+        assert torch.allclose(blended[k], want, rtol=1e-5, atol=1e-6 * float(want.abs().max()))
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -89,12 +118,31 @@ def test_allreduce_is_noop_single_process():
     assert torch.equal(p.grad, torch.full((3,), 2.0))
 
 
-def test_fused_vgg_keeps_names_and_values_on_cpu():
-    """fuse_vgg_features keeps the module names get_features taps; on CPU the fused module falls back to
-    conv + relu_ (the cuDNN entry point is CUDA-only), so values must be identical to the plain walk."""
+def _cpu_stand_ins(monkeypatch):
+    """The fused VGG modules are CUDA-only and raise on CPU tensors.  The wiring tests below walk the fused model
+    on the CPU, so they stand in for the two device calls (cuDNN's fused conv+bias+ReLU, libst3d's pooling) here,
+    in the test, with torch's CPU ops."""
+    from st3d import vgg as V
+    monkeypatch.setattr(V.FusedConvReLU, "forward", lambda self, x: torch.relu_(self.conv(x)))
+    monkeypatch.setattr(V.FusedMaxPool, "forward", lambda self, x: self.pool(x))
+
+
+def test_fused_vgg_raises_on_cpu_tensors():
+    import torchvision
+    from st3d.vgg import fuse_vgg_features
+    fused = fuse_vgg_features(torchvision.models.vgg19(weights=None).features.eval(), channels_last=True)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        fused(torch.rand(1, 3, 16, 16))
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        fused._modules["4"](torch.rand(1, 64, 16, 16))
+
+
+def test_fused_vgg_keeps_names_and_values_on_cpu(monkeypatch):
+    """fuse_vgg_features keeps the module names get_features taps, and the values of the plain walk."""
     import torchvision
     from st3d import losses
     from st3d.vgg import FusedConvReLU, fuse_vgg_features
+    _cpu_stand_ins(monkeypatch)
     torch.manual_seed(0)
     vgg = torchvision.models.vgg19(weights=None).features.eval()
     fused = fuse_vgg_features(vgg, channels_last=False)
@@ -108,14 +156,14 @@ def test_fused_vgg_keeps_names_and_values_on_cpu():
         assert torch.equal(a[k], b[k])
 
 
-def test_fused_vgg_pool_wiring_and_cpu_walk():
+def test_fused_vgg_pool_wiring_and_cpu_walk(monkeypatch):
     """Structure of the fused VGG with libst3d pools: every MaxPool2d(2, 2) becomes a FusedMaxPool that carries the
     ReLU mask of the conv layer in front of it, that layer is told so, and the flags that guard the skipped ReLU
-    backward behave (conservative default, cleared only inside get_features for untapped layers).  On CPU tensors
-    the pools hand over to torch's pooling, so the walk still equals the plain model."""
+    backward behave (conservative default, cleared only inside get_features for untapped layers)."""
     import torchvision
     from st3d import losses
     from st3d.vgg import FusedConvReLU, FusedMaxPool, fuse_vgg_features
+    _cpu_stand_ins(monkeypatch)
     torch.manual_seed(0)
     vgg = torchvision.models.vgg19(weights=None).features.eval()
     fused = fuse_vgg_features(vgg, channels_last=True, fuse_pool=True)
