@@ -297,8 +297,6 @@ class MeshRenderer(torch.nn.Module):
         lights = kwargs.get("lights", self.shader.lights)
         materials = kwargs.get("materials", self.shader.materials)
         blend = kwargs.get("blend_params", self.shader.blend_params)
-        if not isinstance(lights, AmbientLights):
-            raise NotImplementedError("only AmbientLights is implemented by the fused shader")
         if rs.faces_per_pixel != 1:
             raise NotImplementedError("the fused renderer implements faces_per_pixel=1 (what the reference uses); "
                                       "use MeshRasterizer for K > 1 fragments")
@@ -307,7 +305,14 @@ class MeshRenderer(torch.nn.Module):
         verts, faces = _one_mesh(meshes_world)
         tex = meshes_world.textures
         ambient = tuple(l * m for l, m in zip(lights.ambient_color, materials.ambient_color))
-        common = dict(fov=fov, aspect=aspect, znear=znear, zfar=zfar, blur_radius=rs.blur_radius,
+        phong = None
+        if not isinstance(lights, AmbientLights):       # Point / Directional: phong_shading in the same epilogue
+            kind = lights.kind
+            phong = dict(kind=kind, diffuse=tuple(l * m for l, m in zip(lights.diffuse_color, materials.diffuse_color)),
+                         specular=tuple(l * m for l, m in zip(lights.specular_color, materials.specular_color)),
+                         shininess=materials.shininess)
+            phong["location" if kind == "point" else "direction"] = lights.location if kind == "point" else lights.direction
+        common = dict(fov=fov, aspect=aspect, znear=znear, zfar=zfar, blur_radius=rs.blur_radius, lights=phong,
                       cull_backfaces=rs.cull_backfaces, ambient=ambient, background=_color(blend.background_color),
                       sigma=blend.sigma, gamma=blend.gamma,
                       z_clip=rs.z_clip_value if rs.z_clip_value is not None else znear / 2.0)
@@ -323,17 +328,22 @@ class MeshRenderer(torch.nn.Module):
             raise ValueError("meshes_world.textures must be TexturesUV or TexturesVertex")
         return verts, faces, R, T, _image_hw(rs.image_size), tex_kw, common
 
-    def _can_fuse(self, kwargs):
+    def _can_fuse(self, meshes_world, kwargs):
         rs = kwargs.get("raster_settings", self.rasterizer.raster_settings)
         lights = kwargs.get("lights", self.shader.lights)
+        # Point / Directional lights are shaded in the fused epilogue too; their backward reaches the texture / vertex
+        # colours only, so a mesh whose vertices are being optimised under such lights takes the general path
+        lit_ok = isinstance(lights, AmbientLights) or (isinstance(lights, (PointLights, DirectionalLights))
+                                                       and not (torch.is_grad_enabled()
+                                                                and meshes_world.verts_packed().requires_grad))
         # blur_radius > 0 goes through Fragments + shader: that path clips faces at the near plane for any blur,
         # the fused kernels only for the hard rasterization the reference uses
-        return (isinstance(lights, AmbientLights) and rs.faces_per_pixel == 1 and not rs.cull_to_frustum
+        return (lit_ok and rs.faces_per_pixel == 1 and not rs.cull_to_frustum
                 and rs.blur_radius == 0.0 and rs.perspective_correct is not False
                 and rs.clip_barycentric_coords in (None, False))
 
     def forward(self, meshes_world, **kwargs):
-        if not self._can_fuse(kwargs):       # Phong lights / K > 1: Fragments + general shader
+        if not self._can_fuse(meshes_world, kwargs):       # K > 1, blur, lit geometry gradients: Fragments + general shader
             fragments = self.rasterizer(meshes_world, **kwargs)
             return self.shader(fragments, meshes_world, **kwargs)
         verts, faces, R, T, size, tex_kw, common = self._fused_args(meshes_world, kwargs)
@@ -343,7 +353,7 @@ class MeshRenderer(torch.nn.Module):
     def render_planar(self, meshes_world, **kwargs):
         """Batched fast path used by this repo's `utils.render_meshes`: ((N,3,H,W) images, (N,1,H,W) masks)
         straight from the kernel epilogue -- no permute / compare / stack passes."""
-        if not self._can_fuse(kwargs):
+        if not self._can_fuse(meshes_world, kwargs):
             rgba = self.forward(meshes_world, **kwargs)
             return rgba[..., :3].permute(0, 3, 1, 2).contiguous(), (rgba[..., 3:4] > 0).to(rgba.dtype).permute(0, 3, 1, 2)
         verts, faces, R, T, size, tex_kw, common = self._fused_args(meshes_world, kwargs)

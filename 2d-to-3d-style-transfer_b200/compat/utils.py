@@ -22,11 +22,14 @@ def apply_background(tensors, masks, background_type="noise", background=None):
     if background_type == "white":
         return tensors                      # the shader's background is already white
     if background_type == "noise":
-        fill = torch.rand(tensors.shape, device=tensors.device)
+        fill = torch.rand(tensors.shape, device=tensors.device)     # torch's generator, as the reference draws it
     elif background_type == "style":
         fill = background
     else:
         return None
+    if tensors.is_cuda and tensors.dtype == torch.float32 and tensors.dim() == 4 and masks.shape[1] == 1:
+        from st3d import functional as _fn
+        return _fn.composite_background(tensors, masks, fill)       # one libst3d kernel (+ one in the backward)
     return tensors * masks + fill * (1 - masks)
 
 
@@ -41,7 +44,14 @@ def load_as_tensor(image_path, size=512):
 def get_vgg():
     """utils.py:48-52: frozen VGG-19 `.features` with ImageNet weights.  On CUDA the module is returned with
     cuDNN's fused conv+bias+ReLU calls and channels_last weights (same module names, same tapped values)."""
-    vgg = models.vgg19(weights=models.VGG19_Weights.IMAGENET1K_V1).features.to(device)
+    if os.environ.get("ST3D_VGG_RANDOM_INIT") == "1":
+        # offline boxes (no ImageNet checkpoint): the same architecture with seeded random weights; the global RNG
+        # stream is left as it was, so the cameras drawn after this call do not depend on the switch
+        with torch.random.fork_rng(devices=[]):
+            torch.manual_seed(int(os.environ.get("ST3D_VGG_SEED", "0")))
+            vgg = models.vgg19(weights=None).features.eval().to(device)
+    else:
+        vgg = models.vgg19(weights=models.VGG19_Weights.IMAGENET1K_V1).features.to(device)
     for p in vgg.parameters():
         p.requires_grad_(False)
     if device.type == "cuda":

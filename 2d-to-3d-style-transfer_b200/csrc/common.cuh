@@ -242,6 +242,7 @@ struct RasterWs {
     float* ndc_y;      // H
     float4* verts_ndc; // N*V (render only)
     float* grad_ndc;   // N*V*3 (render backward scratch)
+    float* vnormals;   // V*3 unit vertex normals (render with Point / Directional lights)
     size_t zero_bytes; // hdr + tile_count + tile_cursor (contiguous) cleared every call
     size_t total_bytes;
     int TX, TY, NT;
@@ -291,6 +292,9 @@ static inline RasterWs raster_ws_layout(void* base, int N, int64_t F_total, int 
     off = align_up(off, 256);
     w.grad_ndc = (float*)(p + off);
     off += (size_t)NV * 3 * sizeof(float);
+    off = align_up(off, 256);
+    w.vnormals = (float*)(p + off);
+    off += (size_t)(N > 0 ? NV / N : 0) * 3 * sizeof(float);
     w.total_bytes = align_up(off, 256);
     return w;
 }

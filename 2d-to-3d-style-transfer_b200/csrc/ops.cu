@@ -167,9 +167,51 @@ k_mse(const float* __restrict__ a, const float* __restrict__ b, const float* __r
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// apply_background (utils.py:19-30) in one pass: out = mask ? image : fill; backward: grad_image = grad_out * mask
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_composite(const float* __restrict__ image, const float* __restrict__ mask, const float* __restrict__ fill, int64_t n,
+            int64_t inner, int ch, int64_t fill_elems, float* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float m = mask[(i / (inner * ch)) * inner + i % inner];
+        // tensors * m + fill * (1 - m), the reference's expression, so a soft mask composites as it does there
+        const float v = fill ? __ldg(fill + i % fill_elems) : 0.0f;
+        out[i] = image ? image[i] * m + v * (1.0f - m) : v * m;     // image == NULL: backward (v = grad_out)
+    }
+}
+
 }  // namespace st3d
 
 using namespace st3d;
+
+extern "C" int st3d_composite_forward(const float* image, const float* mask, const float* fill, int64_t n, int64_t inner,
+                                      int ch, int fill_batch, float* out, st3d_stream_t stream) {
+    ST3D_REQUIRE(n >= 0 && inner > 0 && ch > 0, "composite_forward: bad sizes");
+    if (n == 0) return ST3D_OK;
+    ST3D_REQUIRE(image && mask && fill && out, "composite_forward: null pointer");
+    ST3D_REQUIRE(n % (inner * ch) == 0, "composite_forward: n is not a multiple of C*H*W");
+    const int64_t B = n / (inner * ch);
+    ST3D_REQUIRE(fill_batch == 1 || fill_batch == B, "composite_forward: fill batch %d is neither 1 nor %lld", fill_batch,
+                 (long long)B);
+    const int grid = (int)std::min<int64_t>(cdiv(n, 256), 148 * 8);
+    k_composite<<<grid, 256, 0, (cudaStream_t)stream>>>(image, mask, fill, n, inner, ch, (int64_t)fill_batch * inner * ch, out);
+    ST3D_LAUNCH_OK("k_composite");
+    return ST3D_OK;
+}
+
+extern "C" int st3d_composite_backward(const float* grad_out, const float* mask, int64_t n, int64_t inner, int ch,
+                                       float* grad_image, st3d_stream_t stream) {
+    ST3D_REQUIRE(n >= 0 && inner > 0 && ch > 0, "composite_backward: bad sizes");
+    if (n == 0) return ST3D_OK;
+    ST3D_REQUIRE(grad_out && mask && grad_image, "composite_backward: null pointer");
+    ST3D_REQUIRE(n % (inner * ch) == 0, "composite_backward: n is not a multiple of C*H*W");
+    const int grid = (int)std::min<int64_t>(cdiv(n, 256), 148 * 8);
+    k_composite<<<grid, 256, 0, (cudaStream_t)stream>>>(nullptr, mask, grad_out, n, inner, ch, n, grad_image);
+    ST3D_LAUNCH_OK("k_composite");
+    return ST3D_OK;
+}
 
 extern "C" int st3d_rasterize_meshes_backward(const float* face_verts, const int64_t* pix_to_face,
                                               const float* grad_zbuf, const float* grad_bary, const float* grad_dists,

@@ -404,12 +404,10 @@ k_fine(const FaceRec* __restrict__ rec, const int* __restrict__ tile_count, cons
             const bool hit = best.f != 0x7fffffff;
             float rgba[4];
             if (hit) {
-                const int fl = best.f - n * (int)sp.F;
-                float texel[3];
-                sample_texel(sp, fl, best.b0, best.b1, best.b2, texel);
-                blend_k1(sp, texel, best.dist, best.z, rgba);
+                shade_pixel(sp, n, best.f - n * (int)sp.F, best.b0, best.b1, best.b2, best.dist, best.z, rgba);
             } else {
-                rgba[0] = sp.bg[0]; rgba[1] = sp.bg[1]; rgba[2] = sp.bg[2]; rgba[3] = 0.0f;
+                background_pixel(sp, n, yi, xi, H, W, rgba);
+                rgba[3] = 0.0f;
             }
             sp.pix_to_face[pix] = hit ? best.f : -1;
             if (sp.out_layout == ST3D_LAYOUT_NHWC_RGBA) {
@@ -542,11 +540,10 @@ k_resolve(const FaceRec* __restrict__ rec, const unsigned long long* __restrict_
     } else {
         float rgba[4];
         if (hit) {
-            float texel[3];
-            sample_texel(sp, f - n * (int)sp.F, h.b0, h.b1, h.b2, texel);
-            blend_k1(sp, texel, h.dist, h.z, rgba);
+            shade_pixel(sp, n, f - n * (int)sp.F, h.b0, h.b1, h.b2, h.dist, h.z, rgba);
         } else {
-            rgba[0] = sp.bg[0]; rgba[1] = sp.bg[1]; rgba[2] = sp.bg[2]; rgba[3] = 0.0f;
+            background_pixel(sp, n, yi, xi, H, W, rgba);
+            rgba[3] = 0.0f;
         }
         sp.pix_to_face[pix] = hit ? f : -1;
         if (sp.out_layout == ST3D_LAYOUT_NHWC_RGBA) {
@@ -830,6 +827,35 @@ k_sweep_units(const FaceRec* __restrict__ rec, const int* __restrict__ unit_face
     }
 }
 
+// Unit vertex normals for Phong shading (Meshes.verts_normals_packed): the sum over incident faces of
+// (v2 - v1) x (v0 - v1) (area-weighted), normalised with eps 1e-6.  vn must be zero on entry.
+__global__ void k_face_normals_to_verts(const float* __restrict__ verts, const int32_t* __restrict__ faces, int64_t F,
+                                        float* __restrict__ vn) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
+    const float ax = verts[3 * i2] - verts[3 * i1], ay = verts[3 * i2 + 1] - verts[3 * i1 + 1], az = verts[3 * i2 + 2] - verts[3 * i1 + 2];
+    const float bx = verts[3 * i0] - verts[3 * i1], by = verts[3 * i0 + 1] - verts[3 * i1 + 1], bz = verts[3 * i0 + 2] - verts[3 * i1 + 2];
+    const float nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+    const int idx[3] = {i0, i1, i2};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        atomicAdd(vn + 3 * (int64_t)idx[k], nx);
+        atomicAdd(vn + 3 * (int64_t)idx[k] + 1, ny);
+        atomicAdd(vn + 3 * (int64_t)idx[k] + 2, nz);
+    }
+}
+
+__global__ void k_normalize_rows3(float* __restrict__ v, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = v[3 * i], y = v[3 * i + 1], z = v[3 * i + 2];
+    const float inv = 1.0f / fmaxf(sqrtf(x * x + y * y + z * z), 1e-6f);
+    v[3 * i] = x * inv;
+    v[3 * i + 1] = y * inv;
+    v[3 * i + 2] = z * inv;
+}
+
 struct HardSrc {  // where the faces of the hard path come from
     const float* face_verts = nullptr;      // SRC 0
     const int64_t* first_idx = nullptr;
@@ -1007,6 +1033,10 @@ extern "C" int st3d_render_forward(const st3d_render_args* a, st3d_stream_t stre
         ST3D_REQUIRE(false, "render_forward: unknown tex_mode %d", a->tex_mode);
     ST3D_REQUIRE(a->out_layout == ST3D_LAYOUT_NHWC_RGBA || a->out_layout == ST3D_LAYOUT_PLANAR,
                  "render_forward: unknown out_layout %d", a->out_layout);
+    ST3D_REQUIRE(a->light_kind == ST3D_LIGHT_AMBIENT || a->light_kind == ST3D_LIGHT_POINT ||
+                     a->light_kind == ST3D_LIGHT_DIRECTIONAL, "render_forward: unknown light_kind %d", a->light_kind);
+    ST3D_REQUIRE(a->background_image == nullptr || a->background_batch == 1 || a->background_batch == a->N,
+                 "render_forward: background_batch %d is neither 1 nor N = %d", a->background_batch, a->N);
     const size_t need = st3d_render_workspace_size(a->N, a->V, a->F, a->H, a->W, a->list_capacity);
     if (a->workspace_bytes < need) {
         st3d_set_error("render_forward: workspace %zu < required %zu bytes", a->workspace_bytes, need);
@@ -1016,9 +1046,19 @@ extern "C" int st3d_render_forward(const st3d_render_args* a, st3d_stream_t stre
     cudaStream_t s = (cudaStream_t)stream;
     const RasterWs ws = raster_ws_layout(a->workspace, a->N, (int64_t)a->N * a->F, a->H, a->W, a->list_capacity,
                                          (int64_t)a->N * a->V);
-    const ShadeParams sp = make_shade_params(*a);
+    ShadeParams sp = make_shade_params(*a);
     FragOut fo{};
     const float z_clip = a->z_clip > 0.0f ? a->z_clip : -INFINITY;
+    if (a->light_kind != ST3D_LIGHT_AMBIENT) {
+        ST3D_CUDA_OK(cudaMemsetAsync(ws.vnormals, 0, (size_t)a->V * 3 * sizeof(float), s));
+        if (a->F > 0) {
+            k_face_normals_to_verts<<<cdiv(a->F, 256), 256, 0, s>>>(a->verts, a->faces, a->F, ws.vnormals);
+            ST3D_LAUNCH_OK("k_face_normals_to_verts");
+        }
+        k_normalize_rows3<<<cdiv(a->V, 256), 256, 0, s>>>(ws.vnormals, a->V);
+        ST3D_LAUNCH_OK("k_normalize_rows3");
+        sp.vert_normals = ws.vnormals;
+    }
     if (a->blur_radius == 0.0f) {  // the reference's configuration: no bins, faces go straight to the z-buffer
         HardSrc h;
         h.verts = a->verts;

@@ -156,14 +156,15 @@ k_render_bwd(const FaceRec* __restrict__ rec, const unsigned long long* __restri
             }
         }
         const BlendK1 bl = blend_terms(sp, dist, pz);
-        float g_w = 0.0f, g_delta = 0.0f, g_texel[3];
+        float g_w = 0.0f, g_delta = 0.0f, g_texel[3], shade[3], spec[3];
+        shade_terms(sp, n, fl, b0, b1, b2, shade, spec);     // colour = shade * texel + spec (ambient: shade = ambient)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const float color = sp.ambient[c] * texel[c];
+            const float color = shade[c] * texel[c] + spec[c];
             const float rgb = (bl.w * color + bl.delta * sp.bg[c]) / bl.denom;
             g_w += g_rgb[c] * (color - rgb) / bl.denom;
             g_delta += g_rgb[c] * (sp.bg[c] - rgb) / bl.denom;
-            g_texel[c] = g_rgb[c] * (bl.w / bl.denom) * sp.ambient[c];
+            g_texel[c] = g_rgb[c] * (bl.w / bl.denom) * shade[c];
         }
         // w = prob * e ; alpha = prob
         const float e = bl.prob > 0.0f ? bl.w / bl.prob : 0.0f;
@@ -252,7 +253,13 @@ extern "C" int st3d_render_backward(const st3d_render_args* a, const float* grad
     cudaStream_t s = (cudaStream_t)stream;
     const RasterWs ws = raster_ws_layout(a->workspace, a->N, (int64_t)a->N * a->F, a->H, a->W, a->list_capacity,
                                          (int64_t)a->N * a->V);
-    const ShadeParams sp = make_shade_params(*a);
+    ShadeParams sp = make_shade_params(*a);
+    sp.vert_normals = ws.vnormals;          // left there by the forward call when light_kind != ambient
+    if (a->light_kind != ST3D_LIGHT_AMBIENT && grad_verts != nullptr) {
+        st3d_set_error("render_backward: vertex gradients under Point / Directional lights are not implemented by the "
+                       "fused renderer (the lighting terms depend on positions and normals); use the operator-boundary path");
+        return ST3D_ERR_UNSUPPORTED;
+    }
     const int clip = a->blur_radius > 0.0f ? 1 : 0;
     const float z_clip = a->z_clip > 0.0f ? a->z_clip : -INFINITY;
     const bool geom = grad_verts != nullptr;

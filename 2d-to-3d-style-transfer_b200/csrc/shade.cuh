@@ -23,6 +23,18 @@ struct ShadeParams {
     float* out_image;
     float* out_mask;
     int32_t* pix_to_face;
+    // Point / Directional lights; light_kind == ST3D_LIGHT_AMBIENT leaves all of this unused
+    int light_kind;
+    float light_vec[3];            // location (point) or direction (directional), world space
+    float diffuse[3], specular[3]; // material colour x light colour
+    float shininess;
+    const float* verts;            // (V,3) world space
+    const float* vert_normals;     // (V,3) unit vertex normals (k_vertex_normals, workspace)
+    const float* R;                // (N,3,3), (N,3): the camera centre is -T R^T
+    const float* T;
+    // apply_background (utils.py:19-30) fused: pixels no face covers take their colour from this image
+    const float* bg_image;         // (bg_batch,3,H,W) planar, bg_batch in {1, N}; NULL: the constant bg
+    int bg_batch;
 };
 
 static inline ShadeParams make_shade_params(const st3d_render_args& a) {
@@ -48,7 +60,80 @@ static inline ShadeParams make_shade_params(const st3d_render_args& a) {
     sp.out_image = a.out_image;
     sp.out_mask = a.out_mask;
     sp.pix_to_face = a.pix_to_face;
+    sp.light_kind = a.light_kind;
+    for (int i = 0; i < 3; ++i) {
+        sp.light_vec[i] = a.light_vec[i];
+        sp.diffuse[i] = a.light_diffuse[i];
+        sp.specular[i] = a.light_specular[i];
+    }
+    sp.shininess = a.shininess;
+    sp.verts = a.verts;
+    sp.vert_normals = nullptr;  // set by the caller from the workspace when light_kind != ambient
+    sp.R = a.R;
+    sp.T = a.T;
+    sp.bg_image = a.background_image;
+    sp.bg_batch = a.background_batch;
     return sp;
+}
+
+// Colour of an uncovered pixel: the constant background of BlendParams, or -- apply_background fused -- the pixel of
+// the caller's background image (noise / style image, utils.py:19-30: tensors * mask + fill * (1 - mask), mask = 0 here).
+__device__ __forceinline__ void background_pixel(const ShadeParams& sp, int n, int yi, int xi, int H, int W, float rgb[3]) {
+    if (sp.bg_image == nullptr) {
+        rgb[0] = sp.bg[0]; rgb[1] = sp.bg[1]; rgb[2] = sp.bg[2];
+        return;
+    }
+    const int64_t hw = (int64_t)H * W;
+    const float* p = sp.bg_image + (int64_t)(sp.bg_batch == 1 ? 0 : n) * 3 * hw + (int64_t)yi * W + xi;
+    rgb[0] = __ldg(p); rgb[1] = __ldg(p + hw); rgb[2] = __ldg(p + 2 * hw);
+}
+
+__device__ __forceinline__ void normalize3(float v[3], float eps) {
+    const float inv = 1.0f / fmaxf(sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]), eps);
+    v[0] *= inv; v[1] *= inv; v[2] *= inv;
+}
+
+// phong_shading: colour = shade * texel + spec with shade = ambient + diffuse.  AmbientLights (what the
+// reference uses, first_approach.py:108) gives shade = ambient, spec = 0 without touching memory; Point / Directional
+// lights interpolate the world position and the unit vertex normals of local face fl with the barycentrics.
+__device__ __forceinline__ void shade_terms(const ShadeParams& sp, int n, int fl, float b0, float b1, float b2,
+                                            float shade[3], float spec[3]) {
+    shade[0] = sp.ambient[0]; shade[1] = sp.ambient[1]; shade[2] = sp.ambient[2];
+    spec[0] = spec[1] = spec[2] = 0.0f;
+    if (sp.light_kind == ST3D_LIGHT_AMBIENT) return;
+    const int32_t* fi = sp.faces + 3 * (int64_t)fl;
+    const int i0 = __ldg(fi), i1 = __ldg(fi + 1), i2 = __ldg(fi + 2);
+    float pos[3], nrm[3], dir[3], view[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        pos[k] = b0 * __ldg(sp.verts + 3 * (int64_t)i0 + k) + b1 * __ldg(sp.verts + 3 * (int64_t)i1 + k) +
+                 b2 * __ldg(sp.verts + 3 * (int64_t)i2 + k);
+        nrm[k] = b0 * __ldg(sp.vert_normals + 3 * (int64_t)i0 + k) + b1 * __ldg(sp.vert_normals + 3 * (int64_t)i1 + k) +
+                 b2 * __ldg(sp.vert_normals + 3 * (int64_t)i2 + k);
+    }
+    const float* R = sp.R + 9 * n;
+    const float* T = sp.T + 3 * n;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        dir[k] = sp.light_kind == ST3D_LIGHT_POINT ? sp.light_vec[k] - pos[k] : sp.light_vec[k];
+        const float centre = -(__ldg(T) * __ldg(R + 3 * k) + __ldg(T + 1) * __ldg(R + 3 * k + 1) + __ldg(T + 2) * __ldg(R + 3 * k + 2));
+        view[k] = centre - pos[k];
+    }
+    normalize3(nrm, 1e-6f);
+    normalize3(dir, 1e-6f);
+    normalize3(view, 1e-6f);
+    const float cosang = nrm[0] * dir[0] + nrm[1] * dir[1] + nrm[2] * dir[2];
+    const float lambert = fmaxf(cosang, 0.0f);
+    float vr = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) vr += view[k] * (2.0f * cosang * nrm[k] - dir[k]);
+    const float alpha = cosang > 0.0f ? fmaxf(vr, 0.0f) : 0.0f;
+    const float gloss = powf(alpha, sp.shininess);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        shade[k] += sp.diffuse[k] * lambert;
+        spec[k] = sp.specular[k] * gloss;
+    }
 }
 
 // Bilinear footprint of one UV sample (ATen grid_sampler_2d semantics: align_corners=True,
@@ -137,12 +222,24 @@ __device__ __forceinline__ BlendK1 blend_terms(const ShadeParams& sp, float dist
     return b;
 }
 
-__device__ __forceinline__ void blend_k1(const ShadeParams& sp, const float texel[3], float dist, float z,
+// color = shade * texel + spec (shade_terms); the blend's background is BlendParams' constant colour
+__device__ __forceinline__ void blend_k1(const ShadeParams& sp, const float color[3], float dist, float z,
                                          float rgba[4]) {
     const BlendK1 b = blend_terms(sp, dist, z);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) rgba[c] = (b.w * (sp.ambient[c] * texel[c]) + b.delta * sp.bg[c]) / b.denom;
+    for (int c = 0; c < 3; ++c) rgba[c] = (b.w * color[c] + b.delta * sp.bg[c]) / b.denom;
     rgba[3] = 1.0f - (1.0f - b.prob);
+}
+
+// covered pixel: sample + shade + blend
+__device__ __forceinline__ void shade_pixel(const ShadeParams& sp, int n, int fl, float b0, float b1, float b2, float dist,
+                                            float z, float rgba[4]) {
+    float texel[3], shade[3], spec[3], color[3];
+    sample_texel(sp, fl, b0, b1, b2, texel);
+    shade_terms(sp, n, fl, b0, b1, b2, shade, spec);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) color[c] = shade[c] * texel[c] + spec[c];
+    blend_k1(sp, color, dist, z, rgba);
 }
 
 }  // namespace st3d

@@ -30,6 +30,8 @@ class RenderArgs(ctypes.Structure):
         ("ambient", c_f * 3), ("background", c_f * 3), ("sigma", c_f), ("gamma", c_f),
         ("out_layout", c_i), ("out_image", c_p), ("out_mask", c_p), ("pix_to_face", c_p),
         ("workspace", c_p), ("workspace_bytes", c_sz), ("list_capacity", c_i64), ("z_clip", c_f),
+        ("light_kind", c_i), ("light_vec", c_f * 3), ("light_diffuse", c_f * 3), ("light_specular", c_f * 3),
+        ("shininess", c_f), ("background_image", c_p), ("background_batch", c_i),
     ]
 
 
@@ -53,6 +55,8 @@ SIGNATURES = {
     "st3d_gram_forward": (c_i, [c_p, c_i, c_i, c_i64, c_p, c_p, c_sz, c_i, c_i, c_p]),
     "st3d_gram_mse_forward": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i64, c_f, c_p, c_p, c_p, c_p, c_sz, c_i, c_i, c_p]),
     "st3d_gram_backward": (c_i, [c_p, c_p, c_i, c_i, c_i64, c_f, c_p, c_i, c_p, c_p, c_sz, c_i, c_i, c_p]),
+    "st3d_composite_forward": (c_i, [c_p, c_p, c_p, c_i64, c_i64, c_i, c_i, c_p, c_p]),
+    "st3d_composite_backward": (c_i, [c_p, c_p, c_i64, c_i64, c_i, c_p, c_p]),
     "st3d_mse_forward": (c_i, [c_p, c_p, c_p, c_i64, c_i64, c_i, c_f, c_p, c_p, c_p]),
     "st3d_maxpool2x2_forward": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
     "st3d_maxpool2x2_backward": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),

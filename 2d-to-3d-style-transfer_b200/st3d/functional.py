@@ -36,8 +36,10 @@ def fov_scales(fov_deg: float = 60.0, aspect: float = 1.0, znear: float = 1.0):
 # ------------------------------------------------------------------------------------------------
 class _RenderFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, verts, tex_param, faces, R, T, face_uvs, spec, mode):
+    def forward(ctx, verts, tex_param, faces, R, T, face_uvs, spec, mode, background_image=None):
         kw = dict(face_uvs=face_uvs, texture=tex_param) if mode == ops.TEX_UV else dict(verts_rgb=tex_param)
+        if background_image is not None:
+            kw["background_image"] = background_image
         image, mask, p2f, state = ops.render_forward(spec, verts.detach(), faces, R, T,
                                                      **{k: (v.detach() if isinstance(v, torch.Tensor) else v)
                                                         for k, v in kw.items()})
@@ -58,7 +60,7 @@ class _RenderFn(torch.autograd.Function):
         g_param = g_tex if uv else g_rgb
         if g_param is not None:
             g_param = g_param.reshape(ctx.tex_shape)
-        return g_verts, g_param, None, None, None, None, None, None
+        return g_verts, g_param, None, None, None, None, None, None, None
 
 
 def render_views(verts: torch.Tensor, faces: torch.Tensor, R: torch.Tensor, T: torch.Tensor, image_size,
@@ -66,8 +68,14 @@ def render_views(verts: torch.Tensor, faces: torch.Tensor, R: torch.Tensor, T: t
                  verts_rgb: Optional[torch.Tensor] = None, fov: float = 60.0, aspect: float = 1.0,
                  znear: float = 1.0, zfar: float = 100.0, blur_radius: float = 0.0, cull_backfaces: bool = False,
                  ambient: Sequence[float] = (1.0, 1.0, 1.0), background: Sequence[float] = (1.0, 1.0, 1.0),
-                 sigma: float = 1e-4, gamma: float = 1e-4, planar: bool = True, z_clip: Optional[float] = None):
-    """Render N camera views of one mesh in one launch sequence (faces_per_pixel = 1, ambient light).
+                 sigma: float = 1e-4, gamma: float = 1e-4, planar: bool = True, z_clip: Optional[float] = None,
+                 lights: Optional[dict] = None, background_image: Optional[torch.Tensor] = None):
+    """Render N camera views of one mesh in one launch sequence (faces_per_pixel = 1).
+
+    lights: None = AmbientLights with the colour `ambient` (what the reference uses); or a dict(kind='point' |
+            'directional', location= | direction=, diffuse=, specular= (light colour x material colour), shininess=)
+            for phong_shading in the same epilogue -- differentiable w.r.t. the texture / vertex colours, not `verts`.
+    background_image: (1|N,3,H,W); uncovered pixels take its colour (apply_background of utils.py:19-30, fused).
 
     planar=True  -> (images (N,3,H,W), masks (N,1,H,W), pix_to_face (N,H,W) int32): what
                     `render_meshes` (utils.py:65-77) returns, without the per-view Python loop.
@@ -80,13 +88,42 @@ def render_views(verts: torch.Tensor, faces: torch.Tensor, R: torch.Tensor, T: t
                           cull_backfaces=cull_backfaces, ambient=tuple(ambient), background=tuple(background),
                           sigma=sigma, gamma=gamma, z_clip=z_clip,
                           layout=ops.LAYOUT_PLANAR if planar else ops.LAYOUT_NHWC_RGBA)
+    if lights is not None and lights.get("kind", "ambient") != "ambient":
+        kind = lights["kind"]
+        if kind not in ("point", "directional"):
+            raise ValueError(f"unknown light kind {kind!r}")
+        spec.light_kind = ops.LIGHT_POINT if kind == "point" else ops.LIGHT_DIRECTIONAL
+        spec.light_vec = tuple(float(v) for v in lights["location" if kind == "point" else "direction"])
+        spec.light_diffuse = tuple(float(v) for v in lights.get("diffuse", (0.0, 0.0, 0.0)))
+        spec.light_specular = tuple(float(v) for v in lights.get("specular", (0.0, 0.0, 0.0)))
+        spec.shininess = float(lights.get("shininess", 64.0))
+    if background_image is not None:
+        background_image = background_image.detach()
     if texture is not None:
         if face_uvs is None:
             raise ValueError("texture needs face_uvs (F,3,2) = verts_uvs[faces_uvs]")
-        return _RenderFn.apply(verts, texture, faces, R, T, face_uvs, spec, ops.TEX_UV)
+        return _RenderFn.apply(verts, texture, faces, R, T, face_uvs, spec, ops.TEX_UV, background_image)
     if verts_rgb is None:
         raise ValueError("render_views needs either texture+face_uvs or verts_rgb")
-    return _RenderFn.apply(verts, verts_rgb, faces, R, T, None, spec, ops.TEX_VERTEX)
+    return _RenderFn.apply(verts, verts_rgb, faces, R, T, None, spec, ops.TEX_VERTEX, background_image)
+
+
+class _CompositeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, mask, fill):
+        ctx.save_for_backward(mask)
+        return ops.composite_forward(image.detach(), mask, fill.detach())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (mask,) = ctx.saved_tensors
+        return ops.composite_backward(grad_out.contiguous(), mask), None, None
+
+
+def composite_background(images: torch.Tensor, masks: torch.Tensor, fill: torch.Tensor) -> torch.Tensor:
+    """utils.py:19-30 (`apply_background`, 'noise' / 'style'): images * masks + fill * (1 - masks) as one kernel;
+    differentiable w.r.t. `images` (the fill is a constant of the step)."""
+    return _CompositeFn.apply(images, masks, fill)
 
 
 # ------------------------------------------------------------------------------------------------

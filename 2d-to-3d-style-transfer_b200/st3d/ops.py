@@ -15,6 +15,7 @@ import torch
 from ._lib import RenderArgs, St3dError, check, lib
 
 TEX_UV, TEX_VERTEX = 0, 1
+LIGHT_AMBIENT, LIGHT_POINT, LIGHT_DIRECTIONAL = 0, 1, 2
 LAYOUT_NHWC_RGBA, LAYOUT_PLANAR = 0, 1
 MAX_FACES_PER_PIXEL = 8
 WS_HEADER_INTS = 16
@@ -318,6 +319,13 @@ class RenderSpec:
     gamma: float = 1e-4
     layout: int = LAYOUT_NHWC_RGBA
     z_clip: Optional[float] = None      # None -> znear / 2 (PyTorch3D's default for perspective cameras)
+    # Point / Directional lights (phong_shading) evaluated in the same epilogue; `ambient` above is
+    # light.ambient x material.ambient, light_diffuse / light_specular are light colour x material colour
+    light_kind: int = LIGHT_AMBIENT
+    light_vec: tuple = (0.0, 1.0, 0.0)
+    light_diffuse: tuple = (0.0, 0.0, 0.0)
+    light_specular: tuple = (0.0, 0.0, 0.0)
+    shininess: float = 64.0
 
 
 @dataclass
@@ -329,8 +337,11 @@ class RenderState:
 
 
 @_on_device_of
-def render_forward(spec: RenderSpec, verts, faces, R, T, *, face_uvs=None, texture=None, verts_rgb=None):
-    """One launch sequence for N views of one mesh.  Returns (image, mask|None, pix_to_face i32, state)."""
+def render_forward(spec: RenderSpec, verts, faces, R, T, *, face_uvs=None, texture=None, verts_rgb=None,
+                   background_image=None):
+    """One launch sequence for N views of one mesh.  Returns (image, mask|None, pix_to_face i32, state).
+    background_image (1|N,3,H,W): pixels no face covers take their colour from it (apply_background of utils.py:19-30
+    fused into the epilogue) instead of spec.background."""
     poll_overflow()
     verts = _cuda_f32("verts", verts, 3)
     faces = _cuda_int("faces", faces, torch.int32)
@@ -369,6 +380,17 @@ def render_forward(spec: RenderSpec, verts, faces, R, T, *, face_uvs=None, textu
     a.ambient = (ctypes.c_float * 3)(*spec.ambient)
     a.background = (ctypes.c_float * 3)(*spec.background)
     a.sigma, a.gamma, a.out_layout = spec.sigma, spec.gamma, spec.layout
+    a.light_kind = int(spec.light_kind)
+    a.light_vec = (ctypes.c_float * 3)(*spec.light_vec)
+    a.light_diffuse = (ctypes.c_float * 3)(*spec.light_diffuse)
+    a.light_specular = (ctypes.c_float * 3)(*spec.light_specular)
+    a.shininess = float(spec.shininess)
+    if background_image is not None:
+        background_image = _cuda_f32("background_image", background_image, 3, H, W).reshape(-1, 3, H, W)
+        if background_image.shape[0] not in (1, N):
+            raise ValueError(f"background_image batch {background_image.shape[0]} is neither 1 nor {N}")
+        a.background_image, a.background_batch = _p(background_image), background_image.shape[0]
+        keep.append(background_image)
     if spec.layout == LAYOUT_NHWC_RGBA:
         image = torch.empty((N, H, W, 4), device=dev, dtype=torch.float32)
         mask = None
@@ -397,6 +419,10 @@ def render_backward(state: RenderState, grad_image, need_texture=True, need_vert
     grad_image = _cuda_f32("grad_image", grad_image)
     dev = grad_image.device
     g_tex = torch.zeros((a.Ht, a.Wt, 3), device=dev, dtype=torch.float32) if (need_texture and a.tex_mode == TEX_UV) else None
+    if need_verts and a.light_kind != LIGHT_AMBIENT:
+        raise NotImplementedError("vertex gradients under Point / Directional lights: use MeshRasterizer + SoftPhongShader "
+                                  "(the operator-boundary path); the fused renderer differentiates lit renders w.r.t. "
+                                  "the texture / vertex colours only")
     g_verts = torch.zeros((a.V, 3), device=dev, dtype=torch.float32) if need_verts else None
     g_rgb = torch.zeros((a.V, 3), device=dev, dtype=torch.float32) if (need_verts_rgb and a.tex_mode == TEX_VERTEX) else None
     with _timed("render_backward", (a.N, a.H, a.W, a.F)):
@@ -511,6 +537,36 @@ def gram_backward(feat, dgram, grad_scale: float = 1.0, out=None, accumulate=Fal
                                        _p(out), _p(ws), nbytes, _precision(precision, C, HW), layout, _stream()),
               "st3d_gram_backward")
     return out if layout == FEAT_NHWC else out.reshape(feat.shape)
+
+
+@_on_device_of
+def composite_forward(image, mask, fill):
+    """apply_background (utils.py:19-30) in one pass: image * mask + fill * (1 - mask); image (B,C,H,W), mask (B,1,H,W),
+    fill (1|B,C,H,W)."""
+    image = _cuda_f32("image", image)
+    if image.dim() != 4:
+        raise ValueError("composite_forward: image must be (B,C,H,W)")
+    B, C, H, W = image.shape
+    mask = _cuda_f32("mask", mask, 1, H, W)
+    fill = _cuda_f32("fill", fill, C, H, W).reshape(-1, C, H, W)
+    if mask.shape[0] != B or fill.shape[0] not in (1, B):
+        raise ValueError("composite_forward: mask / fill batch does not match the image")
+    out = torch.empty_like(image)
+    with _timed("composite_forward", (image.numel(),)):
+        check(lib().st3d_composite_forward(_p(image), _p(mask), _p(fill), image.numel(), H * W, C, fill.shape[0], _p(out),
+                                           _stream()), "st3d_composite_forward")
+    return out
+
+
+@_on_device_of
+def composite_backward(grad_out, mask):
+    grad_out = _cuda_f32("grad_out", grad_out)
+    B, C, H, W = grad_out.shape
+    mask = _cuda_f32("mask", mask, 1, H, W)
+    g = torch.empty_like(grad_out)
+    check(lib().st3d_composite_backward(_p(grad_out), _p(mask), grad_out.numel(), H * W, C, _p(g), _stream()),
+          "st3d_composite_backward")
+    return g
 
 
 @_on_device_of

@@ -34,6 +34,39 @@ def allreduce_gradients(params, group=None, flat: Optional[torch.Tensor] = None,
     return [w for w in works if w is not None]
 
 
+class CapturedIteration:
+    """`fn()` recorded ONCE into a CUDA graph and replayed: the loop body costs its kernels, not the host's launch rate
+    (a step of the 2D style-transfer loop or of the style optimisation is ~150 launches of 5-300 us).
+
+    `fn` must be capture-safe: static input / output tensors, no host reads, optimiser state on the device
+    (`capturable=True`).  `warmup` eager calls run first on a side stream (lazy initialisation, cuDNN algorithm
+    selection, allocator warm-up) -- they are REAL iterations, the caller counts them.  libst3d ops are capture-safe:
+    their deferred workspace-header checks are skipped under capture, the owner of the graph calls `check()`."""
+
+    def __init__(self, fn, device, warmup: int = 3):
+        from . import ops
+        self.device = torch.device(device)
+        cur = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(0, warmup)):
+                self.out = fn()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        ops.poll_overflow(block=True)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = fn()
+        self.replays = 0
+
+    def replay(self):
+        """Runs the recorded iteration; returns fn's (static) outputs, overwritten by the next replay."""
+        self.graph.replay()
+        self.replays += 1
+        return self.out
+
+
 DEFAULT_WEIGHTS = {"main_loss_weight": 3.0, "mesh_verts_weight": 1.0, "mesh_edge_loss_weight": 1.0,
                    "mesh_laplacian_smoothing_weight": 1.0, "mesh_normal_consistency_weight": 1.0}
 
@@ -50,10 +83,16 @@ class StyleOptimizer:
     def __init__(self, verts, faces, vgg, image_size, *, verts_uvs=None, faces_uvs=None, texture=None, verts_rgb=None,
                  target: str = "texture", lr: float = 0.01, style_weight: float = 1e6, content_weight: float = 1.0,
                  weights=None, style_weights=None, precision=None, cache_constants: bool = False, world_size: int = 1,
-                 group=None, channels_last: bool = True, fuse_conv_relu: bool = True):
+                 group=None, channels_last: bool = True, fuse_conv_relu: bool = True, content_background: str = "white",
+                 current_background: str = "white"):
         dev = verts.device
         if dev.type != "cuda":
             raise RuntimeError("StyleOptimizer needs CUDA tensors: libst3d has no CPU path")
+        for b in (content_background, current_background):
+            if b not in ("white", "noise", "style"):
+                raise ValueError(f"unknown background type {b!r} (utils.py:19-30: 'white', 'noise' or 'style')")
+        # apply_background of second_approach.py:161,166, composited inside the render epilogue
+        self.content_background, self.current_background = content_background, current_background
         if target not in ("texture", "mesh", "both"):
             raise ValueError(f"unknown optimisation target {target!r}")
         if (texture is None) == (verts_rgb is None):
@@ -119,9 +158,22 @@ class StyleOptimizer:
     def _nn_input(self, images):
         return images.contiguous(memory_format=torch.channels_last) if self.channels_last else images
 
-    def _render(self, verts, colour, R, T):
+    def _background(self, kind, n_views, style_img):
+        """utils.py:19-30: None for 'white' (the shader's own background), fresh uniform noise per call for 'noise'
+        (torch's generator, as the reference draws it), the style image for 'style'."""
+        if kind == "white":
+            return None
+        S = self.image_size
+        H, W = (S, S) if isinstance(S, int) else tuple(S)
+        if kind == "noise":
+            return torch.rand((n_views, 3, H, W), device=self.verts0.device)
+        if style_img.shape[0] != 1 or tuple(style_img.shape[-2:]) != (H, W):
+            raise ValueError("background 'style' needs ONE style image of the render size")
+        return style_img
+
+    def _render(self, verts, colour, R, T, background_image=None):
         kw = dict(texture=colour, face_uvs=self.face_uvs) if self.uv_mode else dict(verts_rgb=colour)
-        images, masks, _ = Fn.render_views(verts, self.faces, R, T, self.image_size, **kw)
+        images, masks, _ = Fn.render_views(verts, self.faces, R, T, self.image_size, background_image=background_image, **kw)
         return images, masks
 
     def _style_targets(self, style_img):
@@ -179,36 +231,35 @@ class StyleOptimizer:
             images_out.copy_(images, non_blocking=True)
             self.images_ready = torch.cuda.Event()
             self.images_ready.record(self._copy_stream)
-        images.record_stream(self._copy_stream)
+        if not torch.cuda.is_current_stream_capturing():    # (a captured copy stream joins back before the graph ends)
+            images.record_stream(self._copy_stream)
 
     def _views_loss(self, R, T, style_img, images_out, cache_slot):
         """Perceptual loss (losses.py:12-44) of the views (R, T): content render + constants, current render, VGG walk."""
-        if self.cache_constants and self._constants_cached_for(cache_slot, R, T, style_img):
+        cacheable = self.cache_constants and self.content_background != "noise"     # fresh noise: nothing is constant
+        if cacheable and self._constants_cached_for(cache_slot, R, T, style_img):
             c = self._cache[cache_slot]
             content_feat, grams = c["content_feat"], c["grams"]
         else:
             with torch.no_grad():
-                content_imgs, _ = self._render(self.verts0, self.content_colour, R, T)         # second_approach.py:160
+                content_imgs, _ = self._render(self.verts0, self.content_colour, R, T,          # second_approach.py:160-161
+                                               self._background(self.content_background, R.shape[0], style_img))
             # losses.py:18-25: content features + style Grams, one VGG walk for both constant branches
             content_feat, grams = losses.content_and_style_constants(content_imgs, style_img, self.vgg, self.precision,
                                                                      self.style_weights)
-            if self.cache_constants:
+            if cacheable:
                 self._remember_constants(cache_slot, R, T, style_img, content_feat, grams)
-        current_imgs, _ = self._render(self.verts, self.colour, R, T)                           # :165
+        current_imgs, _ = self._render(self.verts, self.colour, R, T,                           # :165-166
+                                       self._background(self.current_background, R.shape[0], style_img))
         if images_out is not None:
             self._export_images(current_imgs.detach(), images_out)
         self.last_images = current_imgs.detach()
         return losses.perceptual_loss_of_images(self._nn_input(current_imgs), self.vgg, content_feat, grams,
                                                 self.style_weight, self.content_weight, self.precision)
 
-    def step(self, R: torch.Tensor, T: torch.Tensor, style_img: torch.Tensor,
-             images_out: Optional[torch.Tensor] = None, micro_batch: Optional[int] = None) -> torch.Tensor:
-        """One optimisation iteration over the views (R, T) held by this rank; returns the loss (device scalar).
-        images_out: optional pinned host tensor (B,3,H,W) that receives this step's rendered views asynchronously
-        (wait on `self.images_ready` before reading it).
-        micro_batch: render / walk the VGG over this many views at a time and ACCUMULATE their gradients into the one
-        Adam step (the loss is a mean over views, losses.py:31,38, so a chunk of b of the B views weighs b / B): the
-        same iteration as one B-view batch with the activations of only `micro_batch` views alive."""
+    def _accumulate_gradients(self, R, T, style_img, images_out=None, micro_batch=None) -> torch.Tensor:
+        """Everything of an iteration that depends on this rank's views: zero the flat gradient, then per micro-batch
+        render -> VGG walk -> loss -> backward (gradients accumulate).  Returns the perceptual part of the loss."""
         B = R.shape[0]
         mb = B if not micro_batch else max(1, min(int(micro_batch), B))
         self._flat_grad.zero_()         # the .grad views stay in place (optimizer.zero_grad(set_to_none=False) as one fill)
@@ -220,8 +271,14 @@ class StyleOptimizer:
             part = main_w * self._views_loss(Rm, Tm, style_img, out_m, s) * (Rm.shape[0] / B)
             (part / self.world_size).backward()                                                 # :188
             loss = part.detach() if loss is None else loss + part.detach()
-        # ONE collective per iteration, issued asynchronously: the regularisers are view-independent and identical on
-        # every rank, so their forward + backward run while the reduce is in flight and are added once, after it
+        if self._copy_stream is not None and torch.cuda.is_current_stream_capturing():
+            torch.cuda.current_stream().wait_stream(self._copy_stream)      # a captured side stream must join back
+        return loss
+
+    def _reduce_and_update(self, loss: torch.Tensor) -> torch.Tensor:
+        """The part of an iteration that involves every rank: ONE collective, issued asynchronously -- the regularisers
+        are view-independent and identical on every rank, so their forward + backward run while the reduce is in
+        flight and are added once, after it -- then the Adam step."""
         works = allreduce_gradients(self.params, self.group, flat=self._flat_grad, async_op=True)
         if self.target != "texture":
             reg = self._regularisers()
@@ -235,6 +292,52 @@ class StyleOptimizer:
                 w.wait()
         self.optimizer.step()                                                                   # :189
         return loss
+
+    def step(self, R: torch.Tensor, T: torch.Tensor, style_img: torch.Tensor,
+             images_out: Optional[torch.Tensor] = None, micro_batch: Optional[int] = None) -> torch.Tensor:
+        """One optimisation iteration over the views (R, T) held by this rank; returns the loss (device scalar).
+        images_out: optional pinned host tensor (B,3,H,W) that receives this step's rendered views asynchronously
+        (wait on `self.images_ready` before reading it).
+        micro_batch: render / walk the VGG over this many views at a time and ACCUMULATE their gradients into the one
+        Adam step (the loss is a mean over views, losses.py:31,38, so a chunk of b of the B views weighs b / B): the
+        same iteration as one B-view batch with the activations of only `micro_batch` views alive."""
+        return self._reduce_and_update(self._accumulate_gradients(R, T, style_img, images_out, micro_batch))
+
+    def capture(self, R: torch.Tensor, T: torch.Tensor, style_img: torch.Tensor,
+                images_out: Optional[torch.Tensor] = None, micro_batch: Optional[int] = None, warmup: int = 3) -> None:
+        """Records this rank's share of the iteration (renders, VGG walks, losses, backward, the copy of the rendered
+        views to `images_out`) as ONE CUDA graph over the STATIC tensors R, T, style_img: new cameras or a new style
+        image are copied INTO them before `step_captured()`.  The warm-up runs `warmup` real iterations.  What stays
+        outside the graph is what involves other ranks or the host: the NCCL all-reduce, the regularisers that overlap
+        it, and the Adam step."""
+        if self.target != "texture":
+            # a moving mesh changes the sizes of the rasterizer's work lists from step to step; their overflow check is
+            # a host read the replayed graph cannot make.  With fixed geometry the sizes seen in the warm-up hold.
+            raise NotImplementedError("capture() records the `texture` target only (fixed geometry)")
+
+        def grads():
+            return self._accumulate_gradients(R, T, style_img, images_out, micro_batch)
+
+        def whole():
+            return self._reduce_and_update(grads())
+
+        dev = self.verts0.device
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                whole()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self._captured = CapturedIteration(grads, dev, warmup=0)
+
+    def step_captured(self) -> torch.Tensor:
+        """Replays the captured gradient computation, then all-reduce / regularisers / Adam; returns the loss."""
+        if getattr(self, "_captured", None) is None:
+            raise RuntimeError("call capture(R, T, style_img) first")
+        loss = self._captured.replay()
+        return self._reduce_and_update(loss)
 
 
 class TextureStyleOptimizer(StyleOptimizer):

@@ -6,7 +6,9 @@ The script's `from pytorch3d... import ...`, `from utils import *`, `from losses
 `from style_transfer import *` then resolve to the modules under `compat/` (same names, same call
 surface) instead of the third-party library and the reference's torch-only helpers.
 Set ST3D_KEEP_REFERENCE_HELPERS=1 to keep the script's own utils/losses/style_transfer modules and swap
-only the `pytorch3d` package.
+only the `pytorch3d` package.  ST3D_SEED=<int> seeds torch / random / numpy before the script starts (the scripts
+draw their cameras from the global generators and never seed them); ST3D_VGG_RANDOM_INIT=1 makes `get_vgg()` build
+the VGG-19 with seeded random weights instead of downloading the ImageNet checkpoint (offline boxes).
 """
 import os
 import runpy
@@ -22,6 +24,15 @@ def main(argv=None):
         raise SystemExit(__doc__)
     script = os.path.abspath(argv[0])
     sys.argv = [script] + argv[1:]
+    if os.environ.get("ST3D_SEED") is not None:
+        import random
+
+        import numpy as np
+        import torch
+        seed = int(os.environ["ST3D_SEED"])
+        torch.manual_seed(seed)
+        random.seed(seed)
+        np.random.seed(seed)
     for p in (PKG,):
         if p not in sys.path:
             sys.path.insert(0, p)

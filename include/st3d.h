@@ -116,6 +116,9 @@ int st3d_interp_face_attrs_backward(const int64_t* pix_to_face, const float* bar
 #define ST3D_TEX_VERTEX 1
 #define ST3D_LAYOUT_NHWC_RGBA 0 /* (N,H,W,4), what renderer(...) returns (utils.py:69)              */
 #define ST3D_LAYOUT_PLANAR 1    /* (N,3,H,W) image + (N,1,H,W) mask, what render_meshes returns     */
+#define ST3D_LIGHT_AMBIENT 0     /* AmbientLights (first_approach.py:108): colour = ambient * texel          */
+#define ST3D_LIGHT_POINT 1       /* PointLights: light_vec = location                                       */
+#define ST3D_LIGHT_DIRECTIONAL 2 /* DirectionalLights: light_vec = direction                                */
 
 typedef struct st3d_render_args {
     /* mesh */
@@ -152,6 +155,21 @@ typedef struct st3d_render_args {
     int64_t list_capacity;  /* must match the value given to st3d_render_workspace_size */
     float z_clip;           /* near-plane clip depth (PyTorch3D: znear / 2): faces crossing z = z_clip are clipped,
                                faces behind it dropped; <= 0 disables clipping */
+    /* SoftPhongShader with Point / Directional lights (phong_shading), evaluated in the same epilogue:
+     * colour = (ambient + diffuse) * texel + specular from the interpolated world position and vertex normal.
+     * `ambient` above stays light.ambient x material.ambient; light_diffuse / light_specular are the products
+     * light colour x material colour.  Backward: into the texture / vertex colours only (grad_verts must be NULL
+     * unless light_kind == ST3D_LIGHT_AMBIENT; the operator-boundary path differentiates lit geometry). */
+    int light_kind;         /* ST3D_LIGHT_* */
+    float light_vec[3];
+    float light_diffuse[3];
+    float light_specular[3];
+    float shininess;
+    /* apply_background (utils.py:19-30) fused into the epilogue: where no face covers a pixel (mask = 0) the output
+     * takes background_image's pixel instead of the constant `background`: exactly tensors * mask + fill * (1 - mask).
+     * (Nb,3,H,W) planar with Nb = background_batch in {1, N}; NULL keeps the constant colour. */
+    const float* background_image;
+    int background_batch;
 } st3d_render_args;
 
 size_t st3d_render_workspace_size(int N, int64_t V, int64_t F, int H, int W, int64_t list_capacity);
@@ -207,6 +225,14 @@ int st3d_gram_mse_forward(const float* feat, const float* target, int B, int Bt,
 int st3d_gram_backward(const float* feat, const float* dgram, int B, int C, int64_t HW, float grad_scale,
                        const float* grad_scale_dev, int accumulate, float* grad_feat, void* workspace,
                        size_t workspace_bytes, int precision, int layout, st3d_stream_t stream);
+
+/* apply_background (utils.py:19-30) as ONE pass, for callers that composite after the render:
+ * out[i] = mask ? image[i] : fill[i] (= image * mask + fill * (1 - mask) for a 0/1 mask), image / fill / out (B,C,H,W),
+ * mask (B,1,H,W), inner = H*W, ch = C; fill_batch in {1,B}.  Backward: grad_image = grad_out * mask (the fill is a constant). */
+int st3d_composite_forward(const float* image, const float* mask, const float* fill, int64_t n, int64_t inner, int ch,
+                           int fill_batch, float* out, st3d_stream_t stream);
+int st3d_composite_backward(const float* grad_out, const float* mask, int64_t n, int64_t inner, int ch, float* grad_image,
+                            st3d_stream_t stream);
 
 /* mean((a-b)^2) family (losses.py:31 content loss; losses.py:71-75 masked MSE):
  * loss_out[0] += scale * sum(m*(a-b)^2); grad_a = 2*scale*m*(a-b) (NULL to skip).

@@ -510,3 +510,88 @@ def test_ops_run_on_the_device_of_their_tensors():
     with pytest.raises(ValueError, match="share a device"):
         ops.gram_mse_forward(f, torch.zeros(1, 64, 64, device="cuda:0"), 1.0, torch.zeros(1, device="cuda:1"))
     assert torch.cuda.current_device() == 0
+
+
+def test_style_optimizer_backgrounds_equal_the_reference_composition(cow):
+    """content_background / current_background = 'style' | 'noise' (second_approach.py:161,166) composited in the render
+    epilogue: the first loss equals the oracle iteration over the same composited images."""
+    from st3d.optimize import TextureStyleOptimizer
+    dev = torch.device("cuda:0")
+    R, T = ro.random_cameras(2, generator=torch.Generator().manual_seed(51))
+    style = torch.rand(1, 3, S, S, generator=torch.Generator().manual_seed(52))
+    tex0 = F.interpolate(cow["texture"].permute(2, 0, 1)[None], size=S, mode="bilinear", align_corners=False)[0].permute(1, 2, 0).contiguous()
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        opt = TextureStyleOptimizer(cow["verts"].to(dev), cow["faces"].to(dev), cow["verts_uvs"].to(dev),
+                                    cow["faces_uvs"].to(dev), tex0.to(dev), _vgg(dev), S, lr=0.01)
+        opt.content_background, opt.current_background = "style", "noise"
+        torch.manual_seed(99)
+        got = opt.step(R.to(dev), T.to(dev), style.to(dev)).item()
+        torch.manual_seed(99)
+        noise = torch.rand((2, 3, S, S), device=dev).cpu()        # the one draw of the step (content is 'style')
+        kw = dict(verts_uvs=cow["verts_uvs"], faces_uvs=cow["faces_uvs"], nthreads=8)
+        img, mask = ro.images_and_masks(ro.render_views(cow["verts"], cow["faces"], R, T, S, texture=tex0, **kw))
+        content = img * mask + style * (1 - mask)
+        current = img * mask + noise * (1 - mask)
+        want = lo.perceptual_loss(current, content, style.repeat(2, 1, 1, 1), _vgg("cpu"), 1e6, 1.0).item()
+        assert abs(got - want) <= 2e-3 * abs(want), (got, want)
+        assert (opt.last_images.cpu() - current).abs().max().item() <= 1e-5
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+
+
+def test_2d_style_transfer_graphed_steps_equal_the_eager_loop(monkeypatch):
+    """style_transfer() replays one CUDA graph per step after three eager steps: ten steps end at
+    the images the all-eager loop produces (ST3D_NST_GRAPH=0)."""
+    import style_transfer as st
+    from st3d.vgg import fuse_vgg_features
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(14)
+    init, content, style = (torch.rand(2, 3, 64, 64, generator=gen).to(dev) for _ in range(3))
+    model = fuse_vgg_features(_vgg(dev), channels_last=True)
+    from st3d import ops
+    before = ops.launch_count()
+    graphed = st.style_transfer(init, content, style, model, steps=10, lr=0.003)
+    launched_graphed = ops.launch_count() - before
+    monkeypatch.setenv("ST3D_NST_GRAPH", "0")
+    before = ops.launch_count()
+    eager = st.style_transfer(init, content, style, model, steps=10, lr=0.003)
+    launched_eager = ops.launch_count() - before
+    assert graphed.requires_grad and graphed.shape == init.shape
+    assert (graphed.detach() - eager.detach()).abs().max().item() <= 2e-5
+    assert (graphed.detach() - init).abs().max().item() >= 0.01        # ten Adam steps of 0.003 did happen
+    # the replayed steps launch nothing through the C ABI: 3 eager steps + 1 capture against 10 eager steps
+    assert launched_graphed < 0.6 * launched_eager, (launched_graphed, launched_eager)
+
+
+def test_captured_style_step_equals_the_eager_step(cow):
+    """StyleOptimizer.capture + step_captured (gradient computation replayed from one CUDA graph, all-reduce and Adam
+    eager) follows the eager step: same losses, same texture, rendered views exported to the pinned buffer."""
+    from st3d.optimize import TextureStyleOptimizer
+    dev = torch.device("cuda:0")
+    R, T = ro.random_cameras(2, generator=torch.Generator().manual_seed(91))
+    style = torch.rand(1, 3, S, S, generator=torch.Generator().manual_seed(92)).to(dev)
+    tex0 = torch.rand(S, S, 3, generator=torch.Generator().manual_seed(93))
+    vgg = _vgg(dev)
+
+    def fresh():
+        return TextureStyleOptimizer(cow["verts"].to(dev), cow["faces"].to(dev), cow["verts_uvs"].to(dev),
+                                     cow["faces_uvs"].to(dev), tex0.to(dev), vgg, S, lr=0.01)
+    Rd, Td = R.to(dev), T.to(dev)
+    eager = fresh()
+    want = [eager.step(Rd, Td, style).item() for _ in range(6)]
+    host = torch.zeros(2, 3, S, S).pin_memory()
+    cap = fresh()
+    cap.capture(Rd, Td, style, images_out=host, warmup=3)         # three real iterations
+    got = [cap.step_captured().item() for _ in range(3)]
+    torch.cuda.synchronize()
+    for g, w in zip(got, want[3:]):
+        assert abs(g - w) <= 1e-4 * abs(w), (got, want)
+    assert (cap.texture.detach() - eager.texture.detach()).abs().max().item() <= 1e-4
+    assert torch.equal(host, cap.last_images.cpu())
+    # new cameras go INTO the static tensors
+    R2, T2 = ro.random_cameras(2, generator=torch.Generator().manual_seed(94))
+    Rd.copy_(R2.to(dev)); Td.copy_(T2.to(dev))
+    a, b = cap.step_captured().item(), eager.step(Rd, Td, style).item()
+    assert abs(a - b) <= 1e-3 * abs(b), (a, b)

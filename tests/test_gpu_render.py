@@ -4,6 +4,7 @@ Bar (BASELINE.json north_star): pix_to_face bit-exact; images / fragments / grad
 relative (fp32).  Gradients are compared against float64 autograd through the oracle restatement.
 """
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -540,3 +541,111 @@ def test_random_soups_cut_by_the_near_plane_bit_exact(seed):
         torch.cuda.synchronize()
         nbad = (got[0].cpu() != fg["pix_to_face"]).sum().item()
         assert nbad == 0, f"Fragments path, seed {seed}, K={K}, blur={blur}: {nbad} entries differ"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# round 2: Point / Directional lights and apply_background in the fused epilogue
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["point", "directional"])
+@pytest.mark.parametrize("mode", ["uv", "vertex"])
+def test_fused_phong_lights_match_oracle(cow, kind, mode):
+    """phong_shading evaluated inside k_resolve: image and texture / vertex-colour gradients against
+    float64 autograd through the oracle's phong_colors."""
+    import st3d.functional as Fn
+    S, N = 80, 3
+    gen = torch.Generator().manual_seed(61)
+    R, T = ro.random_cameras(N, generator=gen)
+    tex = torch.rand(48, 40, 3, generator=gen)
+    vrgb = torch.rand(cow["verts"].shape[0], 3, generator=gen)
+    where = dict(location=(1.0, 2.0, -2.0)) if kind == "point" else dict(direction=(0.3, 1.0, -0.5))
+    amb, dif, spc, shin = (0.45, 0.5, 0.55), (0.3, 0.35, 0.25), (0.2, 0.15, 0.25), 12.0
+    o_lights = dict(kind=kind, ambient=amb, diffuse=dif, specular=spc, **where)
+    o_mats = dict(ambient=(1.0,) * 3, diffuse=(1.0,) * 3, specular=(1.0,) * 3, shininess=shin)
+    lights = dict(kind=kind, diffuse=dif, specular=spc, shininess=shin, **where)
+    tex64, vrgb64 = tex.double().requires_grad_(True), vrgb.double().requires_grad_(True)
+    okw = dict(texture=tex64, verts_uvs=cow["verts_uvs"].double(), faces_uvs=cow["faces_uvs"]) if mode == "uv" \
+        else dict(verts_rgb=vrgb64)
+    want = ro.render_views(cow["verts"].double(), cow["faces"], R, T, S, lights=o_lights, materials=o_mats, nthreads=8,
+                           background=(0.1, 0.2, 0.3), **okw)
+    param = (tex if mode == "uv" else vrgb).cuda().requires_grad_(True)
+    kw = dict(texture=param, face_uvs=cow["verts_uvs"][cow["faces_uvs"]].cuda()) if mode == "uv" else dict(verts_rgb=param)
+    rgba, _ = Fn.render_views(cow["verts"].cuda(), cow["faces"].cuda(), R.cuda(), T.cuda(), S, planar=False, ambient=amb,
+                              background=(0.1, 0.2, 0.3), lights=lights, **kw)
+    _close(rgba, want, what=f"{kind}-lit rgba")
+    lit = (want[..., :3] - ro.render_views(cow["verts"].double(), cow["faces"], R, T, S, nthreads=8,
+                                           background=(0.1, 0.2, 0.3), **okw)[..., :3]).abs().max()
+    assert lit > 0.05                                    # the lights do change the picture
+    cot = torch.rand(N, S, S, 4, generator=gen)
+    (rgba * cot.cuda()).sum().backward()
+    (want * cot.double()).sum().backward()
+    _close(param.grad, (tex64 if mode == "uv" else vrgb64).grad, what=f"{kind}-lit gradient")
+    # vertex gradients under such lights are refused loudly, never silently wrong
+    verts = cow["verts"].cuda().requires_grad_(True)
+    out, _ = Fn.render_views(verts, cow["faces"].cuda(), R.cuda(), T.cuda(), S, planar=False, lights=lights,
+                             **{k: v.detach() for k, v in kw.items()})
+    with pytest.raises(NotImplementedError):
+        out.sum().backward()
+
+
+def test_compat_renderer_fuses_point_lights_and_matches_the_general_path(cow):
+    """MeshRenderer with PointLights: the fused epilogue when only the texture is optimised, Fragments + shading.py
+    (autograd through positions and normals) when the vertices are -- same picture either way."""
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "2d-to-3d-style-transfer_b200", "compat")
+    if compat not in sys.path:
+        sys.path.insert(0, compat)
+    from pytorch3d.renderer import (FoVPerspectiveCameras, Materials, MeshRasterizer, MeshRenderer, PointLights,
+                                    RasterizationSettings, SoftPhongShader, TexturesUV)
+    from pytorch3d.structures import Meshes
+    dev = torch.device("cuda:0")
+    R, T = ro.random_cameras(2, generator=torch.Generator().manual_seed(71))
+    cams = FoVPerspectiveCameras(R=R.to(dev), T=T.to(dev), device=dev)
+    lights = PointLights(location=((0.5, 2.0, -1.5),), device=dev)
+    renderer = MeshRenderer(MeshRasterizer(cameras=cams, raster_settings=RasterizationSettings(image_size=64)),
+                            SoftPhongShader(device=dev, cameras=cams, lights=lights, materials=Materials(shininess=20)))
+    tex = torch.rand(1, 32, 32, 3, generator=torch.Generator().manual_seed(72)).to(dev).requires_grad_(True)
+
+    def mesh(verts):
+        return Meshes(verts=[verts], faces=[cow["faces"].to(dev)],
+                      textures=TexturesUV(verts_uvs=cow["verts_uvs"][None].to(dev), faces_uvs=cow["faces_uvs"][None].to(dev),
+                                          maps=tex))
+    m_fixed = mesh(cow["verts"].to(dev))
+    assert renderer._can_fuse(m_fixed, {})
+    fused = renderer(m_fixed)
+    m_opt = mesh(cow["verts"].to(dev).requires_grad_(True))
+    assert not renderer._can_fuse(m_opt, {})
+    general = renderer(m_opt)
+    _close(fused, general, what="fused vs general lit render")
+    g_f, = torch.autograd.grad(fused[..., :3].square().sum(), tex)
+    g_g, = torch.autograd.grad(general[..., :3].square().sum(), tex)
+    _close(g_f, g_g, what="fused vs general lit texture gradient")
+
+
+def test_background_image_in_the_epilogue_equals_apply_background(cow):
+    """utils.py:19-30 fused: rendering over a background image == render, then tensors * masks + fill * (1 - masks);
+    bit-identical values, identical texture gradient (the gradient passes only where the mask is 1)."""
+    import st3d.functional as Fn
+    S, N = 96, 3
+    gen = torch.Generator().manual_seed(81)
+    R, T = ro.random_cameras(N, generator=gen)
+    tex = torch.rand(64, 64, 3, generator=gen)
+    fuv = cow["verts_uvs"][cow["faces_uvs"]].cuda()
+    args = (cow["verts"].cuda(), cow["faces"].cuda(), R.cuda(), T.cuda(), S)
+    for fill in (torch.rand(N, 3, S, S, generator=gen), torch.rand(1, 3, S, S, generator=gen)):   # 'noise', 'style'
+        t1 = tex.cuda().requires_grad_(True)
+        img, mask, _ = Fn.render_views(*args, texture=t1, face_uvs=fuv, background_image=fill.cuda())
+        t2 = tex.cuda().requires_grad_(True)
+        plain, mask2, _ = Fn.render_views(*args, texture=t2, face_uvs=fuv)
+        want = plain * mask2 + fill.cuda() * (1 - mask2)
+        assert torch.equal(mask, mask2) and torch.equal(img, want)
+        assert 0.1 < mask.mean().item() < 0.6
+        cot = torch.rand(N, 3, S, S, generator=gen).cuda()
+        (img * cot).sum().backward()
+        (want * cot).sum().backward()
+        _close(t1.grad, t2.grad, tol=1e-6, what="texture gradient under a background image")
+        # the composite as its own kernel (what the drop-in utils.apply_background runs after render_meshes)
+        t3 = tex.cuda().requires_grad_(True)
+        plain3, mask3, _ = Fn.render_views(*args, texture=t3, face_uvs=fuv)
+        comp = Fn.composite_background(plain3, mask3, fill.cuda())
+        assert torch.equal(comp, want)
+        (comp * cot).sum().backward()
+        _close(t3.grad, t2.grad, tol=1e-6, what="texture gradient through the composite kernel")

@@ -255,3 +255,24 @@ def test_product_clip_faces_equals_oracle_on_cpu_tensors(cow):
     far[:, :, 2] += 5.0
     same = cl.clip_faces(far, first, num, 0.5)
     assert same.face_verts is far and same.faces_clipped_to_unclipped_idx is None
+
+
+REFERENCE_SCRIPT_SHA256 = {
+    "first_approach.py": "60ac2dbecfe10e5b191160e7b2f6a327e7eaad982e909c71080909794c2a4edf",
+    "second_approach.py": "f4f45f59c93b893868ba8335b0564c1b77c18ed5b0650d00c0f8c7fbb98487b7",
+}
+
+
+def test_reference_script_fixtures_are_byte_identical(golden_dir):
+    """tests/golden/reference_scripts/ holds the reference's two driver scripts UNCHANGED (the GPU box has no
+    /root/reference; tests/test_gpu_scripts.py runs them through st3d.run): digests always, and a byte comparison
+    with the live tree when it is there."""
+    import hashlib
+    for name, digest in REFERENCE_SCRIPT_SHA256.items():
+        with open(os.path.join(golden_dir, "reference_scripts", name), "rb") as fh:
+            data = fh.read()
+        assert hashlib.sha256(data).hexdigest() == digest, name
+        live = os.path.join("/root/reference", name)
+        if os.path.exists(live):
+            with open(live, "rb") as fh:
+                assert fh.read() == data, f"{name} differs from {live}"
