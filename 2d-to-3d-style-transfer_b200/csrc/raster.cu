@@ -12,6 +12,7 @@
 //   * the general path (blur > 0 or K <= 8), sections 2-5: exact-size 16x16-pixel tile bins, a fine pass that
 //     stages each tile's faces in shared memory and keeps the K best fragments in registers.
 #include <float.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -592,13 +593,19 @@ k_prepare(unsigned long long* __restrict__ zkey, int64_t nkeys, int* __restrict_
 // Exact depth test of one pixel against one face + z-buffer update (the oracle's arithmetic).
 // rden = __frcp_rn(denom), den_ok = exp_safe(denom): per face, computed by the caller.
 __device__ __forceinline__ void zbuf_test_pixel(float px, float py, const FaceVerts& v, float denom, float rden, bool den_ok,
-                                                bool zpos, bool persp, float e0x, float e0y, float e1x, float e1y,
-                                                float e2x, float e2y, unsigned fid, unsigned long long* slot) {
+                                                bool zpos, unsigned zlow_bits, bool persp, float e0x, float e0y, float e1x,
+                                                float e1y, float e2x, float e2y, unsigned fid, unsigned long long* slot) {
     const float w0 = fsub(fmul(fsub(px, v.x1), e0y), fmul(fsub(py, v.y1), e0x));
     const float w1 = fsub(fmul(fsub(px, v.x2), e1y), fmul(fsub(py, v.y2), e1x));
     const float w2 = fsub(fmul(fsub(px, v.x0), e2y), fmul(fsub(py, v.y0), e2x));
     // necessary for "inside" when every z > 0: the three edge values share one strict sign
     if (zpos && !((w0 > 0.0f && w1 > 0.0f && w2 > 0.0f) || (w0 < 0.0f && w1 < 0.0f && w2 < 0.0f))) return;
+    // early z: the depth of this face at any pixel is a convex combination of its vertex depths (barycentrics > 0,
+    // summing to 1 within a few ulp), so it cannot beat a key whose depth is below zlow = 0.999996 min(z): skip the six
+    // exact quotients.  A stale read only lets a doomed candidate through to the atomicMin, never the reverse (keys
+    // only decrease); zlow < pz strictly, so a tie on depth (lower face id wins) is never skipped.  zlow_bits = 0 for
+    // faces with a vertex behind the camera: never skipped.
+    if (zlow_bits > (unsigned)(__ldcg(slot) >> 32)) return;
     float b0 = w0, b1 = w1, b2 = w2;
     fdiv3_r(b0, b1, b2, denom, rden, den_ok);
     if (persp) {
@@ -615,6 +622,11 @@ __device__ __forceinline__ void zbuf_test_pixel(float px, float py, const FaceVe
     const float pz = fadd(fadd(fmul(b0, v.z0), fmul(b1, v.z1)), fmul(b2, v.z2));
     if (!(pz >= 0.0f)) return;
     atomicMin(slot, ((unsigned long long)__float_as_uint(fadd(pz, 0.0f)) << 32) | (unsigned long long)fid);
+}
+
+// bits of 0.999996 * min(z0, z1, z2) for a face entirely in front of the camera, else 0 (see zbuf_test_pixel)
+__device__ __forceinline__ unsigned zlow_key(const FaceVerts& v, bool zpos) {
+    return zpos ? __float_as_uint(fminf(v.z0, fminf(v.z1, v.z2)) * 0.999996f) : 0u;
 }
 
 constexpr int kUnitSide = 64;   // work units of the sweep pass cover at most 64 x 64 pixels
@@ -777,7 +789,7 @@ k_face_zbuf(const float* __restrict__ face_verts, const int64_t* __restrict__ fi
             const float e0y = fsub(u.y2, u.y1), e0x = fsub(u.x2, u.x1), e1y = fsub(u.y0, u.y2), e1x = fsub(u.x0, u.x2);
             const float e2y = fsub(u.y1, u.y0), e2x = fsub(u.x1, u.x0);
             zbuf_test_pixel(__ldg(ndc_x + qx), __ldg(ndc_y + qy), u, denom, __frcp_rn(denom), exp_safe(denom), zpos,
-                            persp != 0, e0x, e0y, e1x, e1y, e2x, e2y, fid, zview + (int64_t)qy * W + qx);
+                            zlow_key(u, zpos), persp != 0, e0x, e0y, e1x, e1y, e2x, e2y, fid, zview + (int64_t)qy * W + qx);
         }
     }
 }
@@ -793,35 +805,45 @@ k_sweep_units(const FaceRec* __restrict__ rec, const int* __restrict__ unit_face
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const int64_t total = min((int64_t)hdr[0], unit_capacity);
-    for (int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < total; p += nwarps) {
-        const int f = __ldg(unit_face + p), blk = __ldg(unit_block + p);
-        const int n = (blk >> 20) & 0x7ff, uy = (blk >> 10) & 1023, ux = blk & 1023;
-        const float4 ra = __ldg(&rec[f].a), rb = __ldg(&rec[f].b), rc = __ldg(&rec[f].c);
-        FaceVerts v{ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w, rc.x};
-        const int xr = __float_as_int(rc.z), yr = __float_as_int(rc.w);
-        int fx0 = xr & 0xffff, fx1 = (xr >> 16) & 0x7fff, fy0 = yr & 0xffff, fy1 = yr >> 16;
-        float area = rc.y;
-        if (xr < 0) {  // near-plane-clipped face: this unit belongs to sub-triangle (blk >> 31)
-            const ClipUnit cu = clipped_unit(v, z_clip, (int)((unsigned)blk >> 31), H, W, est, cull_backfaces, ndc_x, ndc_y);
-            if (!cu.box.valid) continue;
-            v = cu.v;
-            area = cu.box.area;
-            fx0 = cu.box.x0; fx1 = cu.box.x1; fy0 = cu.box.y0; fy1 = cu.box.y1;
-        }
-        const int x0 = fx0 + ux * kUnitSide, x1 = min(fx1, x0 + kUnitSide - 1);
-        const int y0 = fy0 + uy * kUnitSide, y1 = min(fy1, y0 + kUnitSide - 1);
-        const bool zpos = v.z0 > 0.0f && v.z1 > 0.0f && v.z2 > 0.0f;
-        const float denom = fadd(area, kEps), rden = __frcp_rn(denom);
-        const bool den_ok = exp_safe(denom);
-        const float e0y = fsub(v.y2, v.y1), e0x = fsub(v.x2, v.x1), e1y = fsub(v.y0, v.y2), e1x = fsub(v.x0, v.x2);
-        const float e2y = fsub(v.y1, v.y0), e2x = fsub(v.x1, v.x0);
-        unsigned long long* zview = zkey + (int64_t)n * H * W;
-        for (int by = y0; by <= y1; by += 4) {
-            for (int bx = x0; bx <= x1; bx += 8) {
-                const int qx = bx + (lane & 7), qy = by + (lane >> 3);
-                if (qx > x1 || qy > y1) continue;
-                zbuf_test_pixel(__ldg(ndc_x + qx), __ldg(ndc_y + qy), v, denom, rden, den_ok, zpos, persp != 0, e0x, e0y,
-                                e1x, e1y, e2x, e2y, (unsigned)f, zview + (int64_t)qy * W + qx);
+    // Two passes over the queue: faces of positive area (front-facing in the rasterizer's convention) first, the rest
+    // after.  On a closed, consistently oriented mesh the first pass writes the visible surface, and the early-z test of
+    // zbuf_test_pixel then rejects nearly every candidate of the second before its exact depth is computed.  Only the
+    // amount of work depends on the order (and on how far the warps drift apart), never the result.
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < total; p += nwarps) {
+            const int f = __ldg(unit_face + p), blk = __ldg(unit_block + p);
+            const float4 rc = __ldg(&rec[f].c);
+            const int xr = __float_as_int(rc.z), yr = __float_as_int(rc.w);
+            // (a near-plane-clipped face keeps area 0 in its record: second pass)
+            if ((rc.y > 0.0f) != (pass == 0)) continue;
+            const int n = (blk >> 20) & 0x7ff, uy = (blk >> 10) & 1023, ux = blk & 1023;
+            const float4 ra = __ldg(&rec[f].a), rb = __ldg(&rec[f].b);
+            FaceVerts v{ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w, rc.x};
+            int fx0 = xr & 0xffff, fx1 = (xr >> 16) & 0x7fff, fy0 = yr & 0xffff, fy1 = yr >> 16;
+            float area = rc.y;
+            if (xr < 0) {  // near-plane-clipped face: this unit belongs to sub-triangle (blk >> 31)
+                const ClipUnit cu = clipped_unit(v, z_clip, (int)((unsigned)blk >> 31), H, W, est, cull_backfaces, ndc_x, ndc_y);
+                if (!cu.box.valid) continue;
+                v = cu.v;
+                area = cu.box.area;
+                fx0 = cu.box.x0; fx1 = cu.box.x1; fy0 = cu.box.y0; fy1 = cu.box.y1;
+            }
+            const int x0 = fx0 + ux * kUnitSide, x1 = min(fx1, x0 + kUnitSide - 1);
+            const int y0 = fy0 + uy * kUnitSide, y1 = min(fy1, y0 + kUnitSide - 1);
+            const bool zpos = v.z0 > 0.0f && v.z1 > 0.0f && v.z2 > 0.0f;
+            const unsigned zlow = zlow_key(v, zpos);
+            const float denom = fadd(area, kEps), rden = __frcp_rn(denom);
+            const bool den_ok = exp_safe(denom);
+            const float e0y = fsub(v.y2, v.y1), e0x = fsub(v.x2, v.x1), e1y = fsub(v.y0, v.y2), e1x = fsub(v.x0, v.x2);
+            const float e2y = fsub(v.y1, v.y0), e2x = fsub(v.x1, v.x0);
+            unsigned long long* zview = zkey + (int64_t)n * H * W;
+            for (int by = y0; by <= y1; by += 4) {
+                for (int bx = x0; bx <= x1; bx += 8) {
+                    const int qx = bx + (lane & 7), qy = by + (lane >> 3);
+                    if (qx > x1 || qy > y1) continue;
+                    zbuf_test_pixel(__ldg(ndc_x + qx), __ldg(ndc_y + qy), v, denom, rden, den_ok, zpos, zlow, persp != 0, e0x,
+                                    e0y, e1x, e1y, e2x, e2y, (unsigned)f, zview + (int64_t)qy * W + qx);
+                }
             }
         }
     }
@@ -1059,7 +1081,11 @@ extern "C" int st3d_render_forward(const st3d_render_args* a, st3d_stream_t stre
         ST3D_LAUNCH_OK("k_normalize_rows3");
         sp.vert_normals = ws.vnormals;
     }
-    if (a->blur_radius == 0.0f) {  // the reference's configuration: no bins, faces go straight to the z-buffer
+    // ST3D_RASTER_BINS=1: measurement switch -- send hard rasterization through the tile-bin path (exact per-tile
+    // face lists staged in shared memory, K-best in registers) instead of the bin-free z-buffer path, for A/B timing
+    // of the two designs on the same scenes (same pix_to_face; no near-plane clipping on that path)
+    static const bool force_bins = [] { const char* e = getenv("ST3D_RASTER_BINS"); return e && e[0] == '1'; }();
+    if (a->blur_radius == 0.0f && !force_bins) {  // the reference's configuration: no bins, faces go straight to the z-buffer
         HardSrc h;
         h.verts = a->verts;
         h.faces = a->faces;
@@ -1080,7 +1106,7 @@ extern "C" int st3d_render_forward(const st3d_render_args* a, st3d_stream_t stre
                       a->cull_backfaces, true, z_clip, s);
     if (rc != ST3D_OK) return rc;
     k_fine<1, 1><<<ws.NT, 256, 0, s>>>(ws.rec, ws.tile_count, ws.tile_offset, ws.list, ws.capacity, a->H, a->W,
-                                           ws.TX, ws.TY, a->blur_radius, 1, 1, nullptr, fo, sp);
+                                           ws.TX, ws.TY, a->blur_radius, 1, a->blur_radius > 0.0f ? 1 : 0, nullptr, fo, sp);
     ST3D_LAUNCH_OK("k_fine");
     return ST3D_OK;
 }

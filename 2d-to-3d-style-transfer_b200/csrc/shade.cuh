@@ -203,8 +203,20 @@ struct BlendK1 {
 
 __device__ __forceinline__ BlendK1 blend_terms(const ShadeParams& sp, float dist, float z) {
     BlendK1 b;
-    b.prob = 1.0f / (1.0f + expf(dist / sp.sigma));  // sigmoid(-dist / sigma)
     const float z_inv = (sp.zfar - z) / (sp.zfar - sp.znear);
+    // Hard rasterization (sigma = gamma = 1e-4, the reference's BlendParams): a covered pixel sits >= 20 sigma inside
+    // its face and >= 24 gamma in front of the far plane, where the formulas below give exactly prob = 1 (the exp is
+    // below half an ulp of 1), e = exp(0) = 1 and delta = its 1e-10 floor.  Same values, no exp / division.
+    if (dist * (-1.0f / sp.sigma) > 20.0f && z_inv > 24.0f * sp.gamma + 1e-10f) {
+        b.prob = 1.0f;
+        b.w = 1.0f;
+        b.dw_dzinv = 0.0f;
+        b.delta = 1e-10f;
+        b.ddelta_dzinv = 0.0f;
+        b.denom = 1.0f + 1e-10f;
+        return b;
+    }
+    b.prob = 1.0f / (1.0f + expf(dist / sp.sigma));  // sigmoid(-dist / sigma)
     const bool zmax_is_zinv = z_inv > 1e-10f;
     const float z_max = zmax_is_zinv ? z_inv : 1e-10f;
     const float e = expf((z_inv - z_max) / sp.gamma);
@@ -227,7 +239,10 @@ __device__ __forceinline__ void blend_k1(const ShadeParams& sp, const float colo
                                          float rgba[4]) {
     const BlendK1 b = blend_terms(sp, dist, z);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) rgba[c] = (b.w * color[c] + b.delta * sp.bg[c]) / b.denom;
+    for (int c = 0; c < 3; ++c) {
+        const float num = b.w * color[c] + b.delta * sp.bg[c];
+        rgba[c] = b.denom == 1.0f ? num : num / b.denom;     // (x / 1 = x exactly: the hard-raster case skips the division)
+    }
     rgba[3] = 1.0f - (1.0f - b.prob);
 }
 

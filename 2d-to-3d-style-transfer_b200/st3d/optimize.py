@@ -301,6 +301,7 @@ class StyleOptimizer:
         micro_batch: render / walk the VGG over this many views at a time and ACCUMULATE their gradients into the one
         Adam step (the loss is a mean over views, losses.py:31,38, so a chunk of b of the B views weighs b / B): the
         same iteration as one B-view batch with the activations of only `micro_batch` views alive."""
+        self._eager_steps = getattr(self, "_eager_steps", 0) + 1
         return self._reduce_and_update(self._accumulate_gradients(R, T, style_img, images_out, micro_batch))
 
     def capture(self, R: torch.Tensor, T: torch.Tensor, style_img: torch.Tensor,
@@ -310,6 +311,10 @@ class StyleOptimizer:
         image are copied INTO them before `step_captured()`.  The warm-up runs `warmup` real iterations.  What stays
         outside the graph is what involves other ranks or the host: the NCCL all-reduce, the regularisers that overlap
         it, and the Adam step."""
+        if getattr(self, "_eager_steps", 0):
+            # the leaves' gradient accumulators were bound to the stream the eager steps ran on (normally the legacy
+            # default stream); autograd would make that stream wait on the capturing one, which CUDA refuses
+            raise RuntimeError("capture() must be called before any eager step(): build a fresh optimiser for the captured loop")
         if self.target != "texture":
             # a moving mesh changes the sizes of the rasterizer's work lists from step to step; their overflow check is
             # a host read the replayed graph cannot make.  With fixed geometry the sizes seen in the warm-up hold.

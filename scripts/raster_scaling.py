@@ -6,16 +6,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "2d-to-3d-style-transfer_b200")]
 import numpy as np, torch
 from st3d import ops, functional as Fn, cameras as cm
 
-def subdivide(verts, faces):
-    e = torch.cat([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]], dim=0)
-    uniq, inv = torch.unique(torch.sort(e, dim=1).values, dim=0, return_inverse=True)
-    mid = 0.5 * (verts[uniq[:, 0]] + verts[uniq[:, 1]])
-    V, Fn_ = verts.shape[0], faces.shape[0]
-    m01, m12, m20 = V + inv[:Fn_], V + inv[Fn_:2 * Fn_], V + inv[2 * Fn_:]
-    a, b, c = faces[:, 0], faces[:, 1], faces[:, 2]
-    nf = torch.cat([torch.stack([a, m01, m20], 1), torch.stack([m01, b, m12], 1), torch.stack([m20, m12, c], 1),
-                    torch.stack([m01, m12, m20], 1)], dim=0)
-    return torch.cat([verts, mid], dim=0), nf
+from st3d.meshgen import subdivide
 
 def timeit(fn, reps=10, warm=3):
     for _ in range(warm): fn()
@@ -53,4 +44,4 @@ for level in range(5):
                          fwd_GBs=round(fb / t_f / 1e3, 1), bwd_GBs=round(bb / t_b / 1e3, 1),
                          coverage=round(float((st["o"][2] >= 0).float().mean()), 3)))
         print(rows[-1], flush=True)
-json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "raster_scaling.json"), "w"), indent=1)
+json.dump(rows, open(os.path.join(ROOT, "gpurun_out", os.environ.get("OUT", "raster_scaling.json")), "w"), indent=1)

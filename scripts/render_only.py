@@ -8,16 +8,7 @@ d = np.load(os.path.join(ROOT, "tests/golden/cow_mesh.npz"))
 dev = "cuda"
 verts, faces = torch.from_numpy(d["verts"]), torch.from_numpy(d["faces"]).long()
 uvs, fuvs = torch.from_numpy(d["verts_uvs"]), torch.from_numpy(d["faces_uvs"]).long()
-def subdivide(verts, faces):
-    e = torch.cat([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]], dim=0)
-    uniq, inv = torch.unique(torch.sort(e, dim=1).values, dim=0, return_inverse=True)
-    mid = 0.5 * (verts[uniq[:, 0]] + verts[uniq[:, 1]])
-    V, F_ = verts.shape[0], faces.shape[0]
-    m01, m12, m20 = V + inv[:F_], V + inv[F_:2 * F_], V + inv[2 * F_:]
-    a, b, c = faces[:, 0], faces[:, 1], faces[:, 2]
-    nf = torch.cat([torch.stack([a, m01, m20], 1), torch.stack([m01, b, m12], 1), torch.stack([m20, m12, c], 1),
-                    torch.stack([m01, m12, m20], 1)], dim=0)
-    return torch.cat([verts, mid], dim=0), nf
+from st3d.meshgen import subdivide
 for _ in range(int(os.environ.get("SUBDIV", 0))):      # SUBDIV=4: 1.5 M faces (BASELINE configs[4] scale)
     verts, faces = subdivide(verts, faces); uvs, fuvs = subdivide(uvs, fuvs)
 fuv = uvs[fuvs].to(dev); verts = verts.to(dev); faces = faces.int().to(dev)

