@@ -246,9 +246,12 @@ static int check_common(const char* what, const float* feat, int B, int C, int64
     return ST3D_OK;
 }
 
-static int gram_partials(const float* feat, const GramPlan& p, int precision, int layout, cudaStream_t s) {
+// *fused_out = 1 when the GEMM kernel itself reduced the split-K partials and applied `ep` (tcgen05 path)
+static int gram_partials(const float* feat, const GramPlan& p, int precision, int layout, const GramEpilogue& ep,
+                         int* fused_out, cudaStream_t s) {
     const bool nhwc = layout == ST3D_FEAT_NHWC;
-    if (precision == ST3D_GRAM_TF32) return gram_tc_forward(feat, p, nhwc, s);
+    *fused_out = 0;
+    if (precision == ST3D_GRAM_TF32) return gram_tc_forward(feat, p, nhwc, ep, fused_out, s);
     const int T = cdiv(p.C, kST);
     k_gram_simt<<<dim3(T * (T + 1) / 2, p.splits, p.B), 256, 0, s>>>(feat, p.C, p.HW, nhwc ? 1 : p.HW, nhwc ? p.C : 1,
                                                                      p.splits, p.k_chunk, p.partials);
@@ -280,8 +283,13 @@ extern "C" int st3d_gram_mse_forward(const float* feat, const float* target, int
         return ST3D_ERR_WORKSPACE;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    rc = gram_partials(feat, p, precision, layout, s);
+    // ST3D_GRAM_SEPARATE_FINALIZE=1 keeps the round-1 two-kernel form (GEMM, then k_gram_finalize) for A/B timing
+    static const bool separate = [] { const char* e = getenv("ST3D_GRAM_SEPARATE_FINALIZE"); return e && e[0] == '1'; }();
+    GramEpilogue ep{target, gram, target ? dgram : nullptr, target ? loss_out : nullptr, p.counters, Bt, scale, separate ? 0 : 1};
+    int fused = 0;
+    rc = gram_partials(feat, p, precision, layout, ep, &fused, s);
     if (rc != ST3D_OK) return rc;
+    if (fused) return ST3D_OK;
     const int64_t total = (int64_t)B * C * C;
     const int sp = p.splits >= 8 ? 8 : (p.splits >= 4 ? 4 : (p.splits >= 2 ? 2 : 1));
     const int lanes = 256 / sp;

@@ -13,7 +13,22 @@ struct GramPlan {
     int64_t k_chunk;   // columns of F per split (multiple of 32)
     float* partials;   // [B][splits][C][C]
     float* sym;        // [B][C][C] scratch for dG + dG^T (backward)
+    unsigned* counters;  // [B] arrival counters of the fused split-K reduction (zeroed by the launcher)
     size_t bytes;
+};
+
+// What the forward GEMM does with its split-K partial sums once every split of an image has landed
+// (losses.py:35-39 fused into the GEMM kernel): G = sum of the partials in split order, loss += scale * sum((G - Gs)^2),
+// dG = 2 scale (G - Gs).  fused == 0 leaves the partials to k_gram_finalize.
+struct GramEpilogue {
+    const float* target;  // (Bt,C,C) or NULL
+    float* gram;          // (B,C,C) or NULL
+    float* dgram;         // (B,C,C) or NULL
+    float* loss_out;      // 1 float or NULL
+    unsigned* counters;   // [B], zero on entry
+    int Bt;
+    float scale;
+    int fused;
 };
 
 // Split K so that one wave of CTAs (<= 148, one per SM) covers the launch: every CTA then pays the
@@ -40,6 +55,9 @@ static inline GramPlan gram_plan(void* base, int B, int C, int64_t HW, int ctas_
     off = align_up(off, 256);
     p.sym = (float*)(c + off);
     off += (size_t)B * C * C * sizeof(float);
+    off = align_up(off, 256);
+    p.counters = (unsigned*)(c + off);
+    off += (size_t)B * sizeof(unsigned);
     p.bytes = align_up(off, 256);
     return p;
 }

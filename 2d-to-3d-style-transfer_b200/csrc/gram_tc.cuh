@@ -247,7 +247,7 @@ struct FwdCfg {
 template <int C, bool NHWC>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gram_tc_fwd(const __grid_constant__ CUtensorMap map, float* __restrict__ partials, int splits, int64_t k_chunk,
-              int64_t HW) {
+              int64_t HW, const GramEpilogue ep) {
     using Cfg = FwdCfg<C>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -403,11 +403,69 @@ k_gram_tc_fwd(const __grid_constant__ CUtensorMap map, float* __restrict__ parti
                 __syncwarp();
             }
         }
+        if (ep.fused) __threadfence();  // this CTA's partial tile is visible device-wide before its arrival is counted
     }
     tc_fence_before();
     __syncthreads();
     if (Cfg::CLUSTER) cluster_sync_all();  // no CTA leaves while peers may still multicast into it / arrive on its barriers
     if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (!ep.fused) return;
+
+    // ---- split-K reduction + style-loss epilogue, inside the GEMM kernel --------------------------------------------
+    // The n = splits * GROUPS CTAs of image b are all resident (the launcher sizes the grid to at most one CTA per SM),
+    // so each one counts its arrival, waits for the others, and then reduces ITS 1/n slice of the C x C tile over the
+    // splits in a fixed order (deterministic sum): no second kernel, no host-visible seam between GEMM and loss.
+    const int n = splits * Cfg::GROUPS;
+    if (n > 1) {
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(ep.counters + b, 1u);
+            long long start = 0;
+            while (*reinterpret_cast<volatile unsigned*>(ep.counters + b) < (unsigned)n) {
+                __nanosleep(40);
+                const long long now = clock64();
+                if (start == 0) start = now;
+                if (now - start > 4000000000ll) __trap();  // ~2 s: a CTA of this image never ran, fail loudly
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+    constexpr int64_t CC = (int64_t)C * C;
+    const int j = s * Cfg::GROUPS + g;
+    const int64_t per = ((CC / 4 + n - 1) / n) * 4;  // elements per CTA, whole float4s
+    const int64_t e_lo = min(CC, (int64_t)j * per), e_hi = min(CC, e_lo + per);
+    const float* P0 = partials + (int64_t)b * splits * CC;
+    const float* tg = ep.target ? ep.target + (ep.Bt == 1 ? 0 : (int64_t)b * CC) : nullptr;
+    float lsum = 0.0f;
+    for (int64_t e = e_lo + 4 * (int64_t)threadIdx.x; e < e_hi; e += 4 * kThreads) {
+        float4 acc = __ldcg(reinterpret_cast<const float4*>(P0 + e));
+        for (int sp = 1; sp < splits; ++sp) {
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(P0 + (int64_t)sp * CC + e));
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+        if (ep.gram) *reinterpret_cast<float4*>(ep.gram + (int64_t)b * CC + e) = acc;
+        if (tg) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(tg + e));
+            float4 d = make_float4(acc.x - t.x, acc.y - t.y, acc.z - t.z, acc.w - t.w);
+            lsum += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
+            const float s2 = 2.0f * ep.scale;
+            d.x *= s2; d.y *= s2; d.z *= s2; d.w *= s2;
+            if (ep.dgram) *reinterpret_cast<float4*>(ep.dgram + (int64_t)b * CC + e) = d;
+        }
+    }
+    if (tg && ep.loss_out) {
+        lsum = warp_sum(lsum);
+        float* red = scratch;  // the transpose scratch is free by now
+        if (lane == 0) red[warp] = lsum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float v = 0.0f;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) v += red[w];
+            if (v != 0.0f) atomicAdd(ep.loss_out, v * ep.scale);
+        }
+    }
 }
 
 // =====================================================================================================
@@ -978,8 +1036,21 @@ static int ensure_smem_attr(K kernel, int bytes, std::atomic<uint64_t>& done) {
     return ST3D_OK;
 }
 
+// SMs of the current device (cached per device ordinal)
+static int sm_count() {
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    int v = cached[dev & 63].load(std::memory_order_relaxed);
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+        cached[dev & 63].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
 template <int C, bool NHWC>
-static int launch_fwd(const float* feat, const GramPlan& p, cudaStream_t s) {
+static int launch_fwd(const float* feat, const GramPlan& p, GramEpilogue ep, int* fused_out, cudaStream_t s) {
     using Cfg = FwdCfg<C>;
     CUtensorMap map;
     int rc = NHWC ? make_map_nhwc(&map, feat, p.B, p.HW, C, 32 * Cfg::KPS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
@@ -988,6 +1059,17 @@ static int launch_fwd(const float* feat, const GramPlan& p, cudaStream_t s) {
     static std::atomic<uint64_t> attr_done{0};
     rc = ensure_smem_attr(k_gram_tc_fwd<C, NHWC>, (int)Cfg::SMEM, attr_done);
     if (rc != ST3D_OK) return rc;
+    // The in-kernel reduction waits for the other CTAs of its image: only when they are certain to be resident --
+    // one CTA per SM (the kernel's shared memory allows no more), the whole grid within the SM count (gram_plan sizes
+    // it for 148), or no cross-CTA wait at all beyond a hardware-co-scheduled cluster (splits == 1).
+    if (ep.fused) {
+        const int64_t grid = (int64_t)Cfg::GROUPS * p.splits * p.B;
+        if (p.splits > 1 && grid > sm_count()) ep.fused = 0;
+        const uintptr_t bits = (uintptr_t)ep.target | (uintptr_t)ep.gram | (uintptr_t)ep.dgram | (uintptr_t)p.partials;
+        if (bits & 15) ep.fused = 0;
+    }
+    if (ep.fused && p.splits * Cfg::GROUPS > 1) ST3D_CUDA_OK(cudaMemsetAsync(p.counters, 0, (size_t)p.B * sizeof(unsigned), s));
+    *fused_out = ep.fused;
     if (Cfg::CLUSTER) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(Cfg::GROUPS, p.splits, p.B);
@@ -1004,10 +1086,10 @@ static int launch_fwd(const float* feat, const GramPlan& p, cudaStream_t s) {
         float* partials = p.partials;
         int splits = p.splits;
         int64_t k_chunk = p.k_chunk, HW = p.HW;
-        ST3D_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gram_tc_fwd<C, NHWC>, map, partials, splits, k_chunk, HW));
+        ST3D_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gram_tc_fwd<C, NHWC>, map, partials, splits, k_chunk, HW, ep));
     } else {
         k_gram_tc_fwd<C, NHWC><<<dim3(Cfg::GROUPS, p.splits, p.B), kThreads, Cfg::SMEM, s>>>(map, p.partials, p.splits,
-                                                                                            p.k_chunk, p.HW);
+                                                                                            p.k_chunk, p.HW, ep);
     }
     ST3D_LAUNCH_OK("k_gram_tc_fwd");
     return ST3D_OK;
@@ -1076,8 +1158,11 @@ static inline bool gram_tc_supported(int C, int64_t HW) {
     return (C == 64 || C == 128 || C == 256 || C == 512) && HW % 4 == 0 && HW >= 32;
 }
 
-static inline int gram_tc_forward(const float* feat, const GramPlan& p, bool nhwc, cudaStream_t s) {
-#define ST3D_FWD(CC) return nhwc ? tc::launch_fwd<CC, true>(feat, p, s) : tc::launch_fwd<CC, false>(feat, p, s)
+// *fused_out: whether the kernel also reduced the split-K partials and applied `ep` (else k_gram_finalize must run)
+static inline int gram_tc_forward(const float* feat, const GramPlan& p, bool nhwc, GramEpilogue ep, int* fused_out,
+                                  cudaStream_t s) {
+#define ST3D_FWD(CC) \
+    return nhwc ? tc::launch_fwd<CC, true>(feat, p, ep, fused_out, s) : tc::launch_fwd<CC, false>(feat, p, ep, fused_out, s)
     switch (p.C) {
         case 64: ST3D_FWD(64);
         case 128: ST3D_FWD(128);

@@ -573,20 +573,19 @@ k_prepare(unsigned long long* __restrict__ zkey, int64_t nkeys, int* __restrict_
     if (tid < ST3D_WS_HEADER_INTS) hdr[tid] = 0;
     for (int64_t i = tid; i < W; i += nth) ndc_x[i] = pix_to_ndc(W - 1 - (int)i, W, H);
     for (int64_t i = tid; i < H; i += nth) ndc_y[i] = pix_to_ndc(H - 1 - (int)i, H, W);
-    if (verts == nullptr || tid >= V) return;
-    for (int n = 0; n < N; ++n) {  // same operation order as k_transform / oracle_transform_verts
+    if (verts == nullptr) return;
+    // one (view, vertex) pair per thread, all threads of the grid (same operation order as k_transform /
+    // oracle_transform_verts)
+    for (int64_t idx = tid; idx < (int64_t)N * V; idx += nth) {
+        const int n = (int)(idx / V);
+        const int64_t i = idx - (int64_t)n * V;
         const float* R = Rm + 9 * n;
         const float* T = Tv + 3 * n;
-        const float r0 = __ldg(R), r1 = __ldg(R + 1), r2 = __ldg(R + 2), r3 = __ldg(R + 3), r4 = __ldg(R + 4);
-        const float r5 = __ldg(R + 5), r6 = __ldg(R + 6), r7 = __ldg(R + 7), r8 = __ldg(R + 8);
-        const float t0 = __ldg(T), t1 = __ldg(T + 1), t2 = __ldg(T + 2);
-        for (int64_t i = tid; i < V; i += nth) {
-            const float x = __ldg(verts + 3 * i), y = __ldg(verts + 3 * i + 1), z = __ldg(verts + 3 * i + 2);
-            const float xv = fadd(fadd(fadd(fmul(x, r0), fmul(y, r3)), fmul(z, r6)), t0);
-            const float yv = fadd(fadd(fadd(fmul(x, r1), fmul(y, r4)), fmul(z, r7)), t1);
-            const float zv = fadd(fadd(fadd(fmul(x, r2), fmul(y, r5)), fmul(z, r8)), t2);
-            verts_ndc[(int64_t)n * V + i] = make_float4(fdiv(fmul(xv, k00), zv), fdiv(fmul(yv, k11), zv), zv, 0.0f);
-        }
+        const float x = __ldg(verts + 3 * i), y = __ldg(verts + 3 * i + 1), z = __ldg(verts + 3 * i + 2);
+        const float xv = fadd(fadd(fadd(fmul(x, __ldg(R)), fmul(y, __ldg(R + 3))), fmul(z, __ldg(R + 6))), __ldg(T));
+        const float yv = fadd(fadd(fadd(fmul(x, __ldg(R + 1)), fmul(y, __ldg(R + 4))), fmul(z, __ldg(R + 7))), __ldg(T + 1));
+        const float zv = fadd(fadd(fadd(fmul(x, __ldg(R + 2)), fmul(y, __ldg(R + 5))), fmul(z, __ldg(R + 8))), __ldg(T + 2));
+        verts_ndc[idx] = make_float4(fdiv(fmul(xv, k00), zv), fdiv(fmul(yv, k11), zv), zv, 0.0f);
     }
 }
 
@@ -605,7 +604,7 @@ __device__ __forceinline__ void zbuf_test_pixel(float px, float py, const FaceVe
     // exact quotients.  A stale read only lets a doomed candidate through to the atomicMin, never the reverse (keys
     // only decrease); zlow < pz strictly, so a tie on depth (lower face id wins) is never skipped.  zlow_bits = 0 for
     // faces with a vertex behind the camera: never skipped.
-    if (zlow_bits > (unsigned)(__ldcg(slot) >> 32)) return;
+    if (zlow_bits != 0u && zlow_bits > (unsigned)(__ldcg(slot) >> 32)) return;
     float b0 = w0, b1 = w1, b2 = w2;
     fdiv3_r(b0, b1, b2, denom, rden, den_ok);
     if (persp) {
@@ -684,7 +683,7 @@ __global__ void __launch_bounds__(128, 10)
 k_face_zbuf(const float* __restrict__ face_verts, const int64_t* __restrict__ first_idx,
             const int64_t* __restrict__ num_faces, const float4* __restrict__ verts_ndc,
             const int32_t* __restrict__ faces, int64_t V, int64_t F_per_mesh, int H, int W, float4 est,
-            int cull_backfaces, float z_clip, int persp, const float* __restrict__ ndc_x,
+            int cull_backfaces, float z_clip, int persp, int early_z, const float* __restrict__ ndc_x,
             const float* __restrict__ ndc_y, FaceRec* __restrict__ rec, unsigned long long* __restrict__ zkey,
             int* __restrict__ unit_face, int* __restrict__ unit_block, int64_t unit_capacity, int* __restrict__ hdr) {
     const int n = blockIdx.y;
@@ -725,25 +724,34 @@ k_face_zbuf(const float* __restrict__ face_verts, const int64_t* __restrict__ fi
     const bool small = box.valid && bw * bh <= kSmallBox;
     {
         // queue the face as ceil(bw/64) x ceil(bh/64) work units of at most 64 x 64 pixels for k_sweep_units;
-        // one atomicAdd per WARP (prefix sum over the lanes' unit counts), not one per face
+        // one atomicAdd per WARP and side (prefix sums over the lanes' unit counts), not one per face.  Faces of
+        // positive area fill the queue from slot 0 upwards (counter hdr[0]), the others from the last slot downwards
+        // (counter hdr[6]): the sweep then meets the front-facing surface first (see k_sweep_units).
         const int ux = (box.valid && !small) ? (bw + kUnitSide - 1) / kUnitSide : 0;
         const int nu = (box.valid && !small) ? ux * ((bh + kUnitSide - 1) / kUnitSide) : 0;
         if (__any_sync(0xffffffffu, nu > 0)) {  // (on meshes denser than the pixel grid most warps queue nothing)
-            int incl = nu;
+            const bool front = box.area > 0.0f;
+            int incl_f = front ? nu : 0, incl_b = front ? 0 : nu;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
+                const int tf = __shfl_up_sync(0xffffffffu, incl_f, o), tb = __shfl_up_sync(0xffffffffu, incl_b, o);
+                if (lane >= o) { incl_f += tf; incl_b += tb; }
             }
-            const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
-            int base = 0;
-            if (lane == 31) base = atomicAdd(&hdr[0], warp_total);  // hdr[0] = units needed
-            base = __shfl_sync(0xffffffffu, base, 31);
-            const int slot0 = base + incl - nu;
+            const int tot_f = __shfl_sync(0xffffffffu, incl_f, 31), tot_b = __shfl_sync(0xffffffffu, incl_b, 31);
+            int base_f = 0, base_b = 0;
+            if (lane == 31) {
+                if (tot_f) base_f = atomicAdd(&hdr[0], tot_f);
+                if (tot_b) base_b = atomicAdd(&hdr[6], tot_b);
+            }
+            base_f = __shfl_sync(0xffffffffu, base_f, 31);
+            base_b = __shfl_sync(0xffffffffu, base_b, 31);
+            const int64_t first = front ? (int64_t)base_f + incl_f - nu : (int64_t)base_b + incl_b - nu;
             for (int u = 0; u < nu; ++u) {
-                if (slot0 + u < unit_capacity) {
-                    unit_face[slot0 + u] = (int)f;
-                    unit_block[slot0 + u] = (n << 20) | ((u / ux) << 10) | (u % ux);
+                // (the two ends meeting is detected by k_sweep_units: hdr[0] + hdr[6] > capacity sets the overflow flag)
+                if (first + u < unit_capacity) {
+                    const int64_t slot = front ? first + u : unit_capacity - 1 - (first + u);
+                    unit_face[slot] = (int)f;
+                    unit_block[slot] = (n << 20) | ((u / ux) << 10) | (u % ux);
                 } else {
                     hdr[1] = 1;
                 }
@@ -789,7 +797,8 @@ k_face_zbuf(const float* __restrict__ face_verts, const int64_t* __restrict__ fi
             const float e0y = fsub(u.y2, u.y1), e0x = fsub(u.x2, u.x1), e1y = fsub(u.y0, u.y2), e1x = fsub(u.x0, u.x2);
             const float e2y = fsub(u.y1, u.y0), e2x = fsub(u.x1, u.x0);
             zbuf_test_pixel(__ldg(ndc_x + qx), __ldg(ndc_y + qy), u, denom, __frcp_rn(denom), exp_safe(denom), zpos,
-                            zlow_key(u, zpos), persp != 0, e0x, e0y, e1x, e1y, e2x, e2y, fid, zview + (int64_t)qy * W + qx);
+                            early_z ? zlow_key(u, zpos) : 0u, persp != 0, e0x, e0y, e1x, e1y, e2x, e2y, fid,
+                            zview + (int64_t)qy * W + qx);
         }
     }
 }
@@ -799,51 +808,49 @@ k_face_zbuf(const float* __restrict__ face_verts, const int64_t* __restrict__ fi
 // can stall the pass.
 __global__ void __launch_bounds__(256)
 k_sweep_units(const FaceRec* __restrict__ rec, const int* __restrict__ unit_face, const int* __restrict__ unit_block,
-              const int* __restrict__ hdr, int64_t unit_capacity, int H, int W, float4 est, int cull_backfaces,
-              float z_clip, int persp, const float* __restrict__ ndc_x, const float* __restrict__ ndc_y,
+              int* __restrict__ hdr, int64_t unit_capacity, int H, int W, float4 est, int cull_backfaces,
+              float z_clip, int persp, int early_z, const float* __restrict__ ndc_x, const float* __restrict__ ndc_y,
               unsigned long long* __restrict__ zkey) {
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    const int64_t total = min((int64_t)hdr[0], unit_capacity);
-    // Two passes over the queue: faces of positive area (front-facing in the rasterizer's convention) first, the rest
-    // after.  On a closed, consistently oriented mesh the first pass writes the visible surface, and the early-z test of
-    // zbuf_test_pixel then rejects nearly every candidate of the second before its exact depth is computed.  Only the
-    // amount of work depends on the order (and on how far the warps drift apart), never the result.
-    for (int pass = 0; pass < 2; ++pass) {
-        for (int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < total; p += nwarps) {
-            const int f = __ldg(unit_face + p), blk = __ldg(unit_block + p);
-            const float4 rc = __ldg(&rec[f].c);
-            const int xr = __float_as_int(rc.z), yr = __float_as_int(rc.w);
-            // (a near-plane-clipped face keeps area 0 in its record: second pass)
-            if ((rc.y > 0.0f) != (pass == 0)) continue;
-            const int n = (blk >> 20) & 0x7ff, uy = (blk >> 10) & 1023, ux = blk & 1023;
-            const float4 ra = __ldg(&rec[f].a), rb = __ldg(&rec[f].b);
-            FaceVerts v{ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w, rc.x};
-            int fx0 = xr & 0xffff, fx1 = (xr >> 16) & 0x7fff, fy0 = yr & 0xffff, fy1 = yr >> 16;
-            float area = rc.y;
-            if (xr < 0) {  // near-plane-clipped face: this unit belongs to sub-triangle (blk >> 31)
-                const ClipUnit cu = clipped_unit(v, z_clip, (int)((unsigned)blk >> 31), H, W, est, cull_backfaces, ndc_x, ndc_y);
-                if (!cu.box.valid) continue;
-                v = cu.v;
-                area = cu.box.area;
-                fx0 = cu.box.x0; fx1 = cu.box.x1; fy0 = cu.box.y0; fy1 = cu.box.y1;
-            }
-            const int x0 = fx0 + ux * kUnitSide, x1 = min(fx1, x0 + kUnitSide - 1);
-            const int y0 = fy0 + uy * kUnitSide, y1 = min(fy1, y0 + kUnitSide - 1);
-            const bool zpos = v.z0 > 0.0f && v.z1 > 0.0f && v.z2 > 0.0f;
-            const unsigned zlow = zlow_key(v, zpos);
-            const float denom = fadd(area, kEps), rden = __frcp_rn(denom);
-            const bool den_ok = exp_safe(denom);
-            const float e0y = fsub(v.y2, v.y1), e0x = fsub(v.x2, v.x1), e1y = fsub(v.y0, v.y2), e1x = fsub(v.x0, v.x2);
-            const float e2y = fsub(v.y1, v.y0), e2x = fsub(v.x1, v.x0);
-            unsigned long long* zview = zkey + (int64_t)n * H * W;
-            for (int by = y0; by <= y1; by += 4) {
-                for (int bx = x0; bx <= x1; bx += 8) {
-                    const int qx = bx + (lane & 7), qy = by + (lane >> 3);
-                    if (qx > x1 || qy > y1) continue;
-                    zbuf_test_pixel(__ldg(ndc_x + qx), __ldg(ndc_y + qy), v, denom, rden, den_ok, zpos, zlow, persp != 0, e0x,
-                                    e0y, e1x, e1y, e2x, e2y, (unsigned)f, zview + (int64_t)qy * W + qx);
-                }
+    // The queue is ordered by k_face_zbuf: faces of positive area (front-facing in the rasterizer's convention) from
+    // slot 0 upwards, the rest from the last slot downwards.  On a closed, consistently oriented mesh the first waves
+    // therefore write the visible surface, and the early-z test of zbuf_test_pixel rejects most candidates of the later
+    // ones before their exact depth is computed.  Only the amount of work depends on the order, never the result.
+    const int64_t nfront = min((int64_t)hdr[0], unit_capacity), nback = min((int64_t)hdr[6], unit_capacity - nfront);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (int64_t)hdr[0] + hdr[6] > unit_capacity) hdr[1] = 1;  // the two ends met
+    const int64_t total = nfront + nback;
+    for (int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < total; q += nwarps) {
+        const int64_t p = q < nfront ? q : unit_capacity - 1 - (q - nfront);
+        const int f = __ldg(unit_face + p), blk = __ldg(unit_block + p);
+        const int n = (blk >> 20) & 0x7ff, uy = (blk >> 10) & 1023, ux = blk & 1023;
+        const float4 ra = __ldg(&rec[f].a), rb = __ldg(&rec[f].b), rc = __ldg(&rec[f].c);
+        FaceVerts v{ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w, rc.x};
+        const int xr = __float_as_int(rc.z), yr = __float_as_int(rc.w);
+        int fx0 = xr & 0xffff, fx1 = (xr >> 16) & 0x7fff, fy0 = yr & 0xffff, fy1 = yr >> 16;
+        float area = rc.y;
+        if (xr < 0) {  // near-plane-clipped face: this unit belongs to sub-triangle (blk >> 31)
+            const ClipUnit cu = clipped_unit(v, z_clip, (int)((unsigned)blk >> 31), H, W, est, cull_backfaces, ndc_x, ndc_y);
+            if (!cu.box.valid) continue;
+            v = cu.v;
+            area = cu.box.area;
+            fx0 = cu.box.x0; fx1 = cu.box.x1; fy0 = cu.box.y0; fy1 = cu.box.y1;
+        }
+        const int x0 = fx0 + ux * kUnitSide, x1 = min(fx1, x0 + kUnitSide - 1);
+        const int y0 = fy0 + uy * kUnitSide, y1 = min(fy1, y0 + kUnitSide - 1);
+        const bool zpos = v.z0 > 0.0f && v.z1 > 0.0f && v.z2 > 0.0f;
+        const unsigned zlow = early_z ? zlow_key(v, zpos) : 0u;
+        const float denom = fadd(area, kEps), rden = __frcp_rn(denom);
+        const bool den_ok = exp_safe(denom);
+        const float e0y = fsub(v.y2, v.y1), e0x = fsub(v.x2, v.x1), e1y = fsub(v.y0, v.y2), e1x = fsub(v.x0, v.x2);
+        const float e2y = fsub(v.y1, v.y0), e2x = fsub(v.x1, v.x0);
+        unsigned long long* zview = zkey + (int64_t)n * H * W;
+        for (int by = y0; by <= y1; by += 4) {
+            for (int bx = x0; bx <= x1; bx += 8) {
+                const int qx = bx + (lane & 7), qy = by + (lane >> 3);
+                if (qx > x1 || qy > y1) continue;
+                zbuf_test_pixel(__ldg(ndc_x + qx), __ldg(ndc_y + qy), v, denom, rden, den_ok, zpos, zlow, persp != 0, e0x,
+                                e0y, e1x, e1y, e2x, e2y, (unsigned)f, zview + (int64_t)qy * W + qx);
             }
         }
     }
@@ -905,17 +912,22 @@ static int run_hard(const RasterWs& ws, const HardSrc& h, int N, int H, int W, i
         // seeds of the pixel-range search: NDC-ordered pixel index j(v) = a v + b (A.3 PixToNonSquareNdc inverted)
         const double rx = W > H ? 2.0 * W / H : 2.0, ry = H > W ? 2.0 * H / W : 2.0;
         const float4 est = make_float4((float)(W / rx), (float)(0.5 * (W - 1)), (float)(H / ry), (float)(0.5 * (H - 1)));
+        // ST3D_EARLY_Z: bit 0 = early-z test in the sweep of queued units, bit 1 = in the small-face pass (default 1;
+        // measurement switch, the result does not depend on it)
+        static const int ez = [] { const char* e = getenv("ST3D_EARLY_Z"); return e ? atoi(e) : 1; }();
+        const int ez_sweep = ez & 1, ez_small = (ez >> 1) & 1;
         if (h.verts)
             k_face_zbuf<1><<<grid, 128, 0, s>>>(nullptr, nullptr, nullptr, ws.verts_ndc, h.faces, h.V, h.F_per_mesh, H, W,
-                                                est, h.cull_backfaces, h.z_clip, persp, ws.ndc_x, ws.ndc_y, ws.rec,
+                                                est, h.cull_backfaces, h.z_clip, persp, ez_small, ws.ndc_x, ws.ndc_y, ws.rec,
                                                 ws.zkey, ws.list, ws.list_tile, ws.capacity, ws.hdr);
         else
             k_face_zbuf<0><<<grid, 128, 0, s>>>(h.face_verts, h.first_idx, h.num_faces, nullptr, nullptr, 0,
-                                                h.F_per_mesh, H, W, est, h.cull_backfaces, h.z_clip, persp, ws.ndc_x,
-                                                ws.ndc_y, ws.rec, ws.zkey, ws.list, ws.list_tile, ws.capacity, ws.hdr);
+                                                h.F_per_mesh, H, W, est, h.cull_backfaces, h.z_clip, persp, ez_small,
+                                                ws.ndc_x, ws.ndc_y, ws.rec, ws.zkey, ws.list, ws.list_tile, ws.capacity,
+                                                ws.hdr);
         ST3D_LAUNCH_OK("k_face_zbuf");
         k_sweep_units<<<148 * 8, 256, 0, s>>>(ws.rec, ws.list, ws.list_tile, ws.hdr, ws.capacity, H, W, est,
-                                              h.cull_backfaces, h.z_clip, persp, ws.ndc_x, ws.ndc_y, ws.zkey);
+                                              h.cull_backfaces, h.z_clip, persp, ez_sweep, ws.ndc_x, ws.ndc_y, ws.zkey);
         ST3D_LAUNCH_OK("k_sweep_units");
     }
     k_resolve<MODE><<<dim3(cdiv(W, 256), H, N), 256, 0, s>>>(ws.rec, ws.zkey, H, W, persp, h.z_clip, ws.ndc_x, ws.ndc_y,

@@ -141,7 +141,7 @@ def read_header(ws: torch.Tensor):
     """Synchronous read of a raster workspace header (for callers that replay captured graphs and therefore own
     the workspace): (entries needed, overflow flag, unsupported-clip flag)."""
     h = ws[: WS_HEADER_INTS * 4].view(torch.int32).cpu()
-    return int(h[0]), int(h[1]), int(h[4])
+    return int(h[0]) + int(h[6]), int(h[1]), int(h[4])
 
 
 def _watch_header(ws: torch.Tensor, key) -> None:
@@ -165,7 +165,7 @@ def poll_overflow(block: bool = False) -> None:
         if block:
             ev.synchronize()
         if ev.query():
-            needed, overflow, clip = int(host[0]), int(host[1]), int(host[4])
+            needed, overflow, clip = int(host[0]) + int(host[6]), int(host[1]), int(host[4])   # [6]: back-facing units
             _free_hosts.append(host)
             _capacity_hint[key] = max(_capacity_hint.get(key, 0), needed)
             if clip:

@@ -64,8 +64,9 @@ int st3d_transform_verts_backward(const float* verts, const float* R, const floa
 size_t st3d_raster_workspace_size(int N, int64_t F_total, int H, int W, int64_t list_capacity);
 
 /* Workspace header, readable by the host AFTER the stream has been synchronised:
- * [0] = work-list entries needed by the last call ((face,tile) pairs of the binned path, face units of the
- * hard path), [1] = 1 if that list overflowed (results invalid, re-run with a larger list_capacity),
+ * [0] (+ [6]) = work-list entries needed by the last call ((face,tile) pairs of the binned path; face units of the
+ * hard path, [0] the front-facing ones queued from the first slot up, [6] the others queued from the last slot down),
+ * [1] = 1 if that list overflowed (results invalid, re-run with a larger list_capacity),
  * [2] = capacity in entries, [5] = 1 if the call clipped faces against the near plane (informational),
  * [4] = 1 if some face has a vertex nearer than st3d_render_args.z_clip on a path that does not clip: the fused
  * renderer clips such faces inside its kernels (PyTorch3D clip_faces semantics, csrc/clip.cuh) when blur_radius

@@ -21,9 +21,12 @@ N = 8
 R, T = cm.random_view_cameras(N, generator=torch.Generator().manual_seed(0)); R, T = R.cuda(), T.cuda()
 k00, k11 = Fn.fov_scales(60.0)
 rows = []
+levels = [int(t) for t in os.environ.get("LEVELS", "0,1,2,3,4").split(",")]
 for level in range(5):
     if level:
         verts, faces = subdivide(verts, faces); uvs, fuvs = subdivide(uvs, fuvs)
+    if level not in levels:
+        continue
     v, f, fuv = verts.cuda(), faces.int().cuda(), uvs[fuvs].cuda()
     for S in (512, 1024):
         tex = torch.rand(S, S, 3, device="cuda")
