@@ -230,8 +230,6 @@ class MeshRasterizer(torch.nn.Module):
     def forward(self, meshes_world, **kwargs) -> Fragments:
         cams, (fov, aspect, znear, zfar) = _camera_params(kwargs.get("cameras", self.cameras))
         rs = self._settings(kwargs)
-        if rs.cull_to_frustum:
-            raise NotImplementedError("cull_to_frustum is not implemented")
         verts, faces = _one_mesh(meshes_world)
         R, T = cams.R.to(verts.device), cams.T.to(verts.device)
         N, Fn = R.shape[0], faces.shape[0]
@@ -245,7 +243,7 @@ class MeshRasterizer(torch.nn.Module):
         z_clip = rs.z_clip_value if rs.z_clip_value is not None else (znear / 2.0 if persp else None)
         p2f, zbuf, bary, dists = _fn.rasterize_meshes(face_verts, first, num, _image_hw(rs.image_size), rs.blur_radius,
                                                       rs.faces_per_pixel, persp, clip_bary, rs.cull_backfaces,
-                                                      z_clip_value=z_clip)
+                                                      z_clip_value=z_clip, cull_to_frustum=rs.cull_to_frustum)
         return Fragments(p2f, zbuf, bary, dists)
 
 
@@ -300,8 +298,8 @@ class MeshRenderer(torch.nn.Module):
         if rs.faces_per_pixel != 1:
             raise NotImplementedError("the fused renderer implements faces_per_pixel=1 (what the reference uses); "
                                       "use MeshRasterizer for K > 1 fragments")
-        if rs.cull_to_frustum or (rs.perspective_correct is False):
-            raise NotImplementedError("cull_to_frustum / perspective_correct=False are not implemented in the fused path")
+        if rs.perspective_correct is False:
+            raise NotImplementedError("perspective_correct=False is not implemented in the fused path")
         verts, faces = _one_mesh(meshes_world)
         tex = meshes_world.textures
         ambient = tuple(l * m for l, m in zip(lights.ambient_color, materials.ambient_color))
@@ -313,6 +311,7 @@ class MeshRenderer(torch.nn.Module):
                          shininess=materials.shininess)
             phong["location" if kind == "point" else "direction"] = lights.location if kind == "point" else lights.direction
         common = dict(fov=fov, aspect=aspect, znear=znear, zfar=zfar, blur_radius=rs.blur_radius, lights=phong,
+                      cull_to_frustum=rs.cull_to_frustum,
                       cull_backfaces=rs.cull_backfaces, ambient=ambient, background=_color(blend.background_color),
                       sigma=blend.sigma, gamma=blend.gamma,
                       z_clip=rs.z_clip_value if rs.z_clip_value is not None else znear / 2.0)
@@ -338,7 +337,7 @@ class MeshRenderer(torch.nn.Module):
                                                                 and meshes_world.verts_packed().requires_grad))
         # blur_radius > 0 goes through Fragments + shader: that path clips faces at the near plane for any blur,
         # the fused kernels only for the hard rasterization the reference uses
-        return (lit_ok and rs.faces_per_pixel == 1 and not rs.cull_to_frustum
+        return (lit_ok and rs.faces_per_pixel == 1
                 and rs.blur_radius == 0.0 and rs.perspective_correct is not False
                 and rs.clip_barycentric_coords in (None, False))
 

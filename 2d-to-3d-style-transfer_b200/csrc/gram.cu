@@ -285,7 +285,10 @@ extern "C" int st3d_gram_mse_forward(const float* feat, const float* target, int
     cudaStream_t s = (cudaStream_t)stream;
     // ST3D_GRAM_SEPARATE_FINALIZE=1 keeps the round-1 two-kernel form (GEMM, then k_gram_finalize) for A/B timing
     static const bool separate = [] { const char* e = getenv("ST3D_GRAM_SEPARATE_FINALIZE"); return e && e[0] == '1'; }();
-    GramEpilogue ep{target, gram, target ? dgram : nullptr, target ? loss_out : nullptr, p.counters, Bt, scale, separate ? 0 : 1};
+    // ST3D_GRAM_FUSE_MAXC=<C>: fuse only for layers of at most C channels (measurement switch; default: all)
+    static const int fuse_maxc = [] { const char* e = getenv("ST3D_GRAM_FUSE_MAXC"); return e ? atoi(e) : 1 << 30; }();
+    GramEpilogue ep{target, gram, target ? dgram : nullptr, target ? loss_out : nullptr, p.counters, Bt, scale,
+                    (separate || C > fuse_maxc) ? 0 : 1};
     int fused = 0;
     rc = gram_partials(feat, p, precision, layout, ep, &fused, s);
     if (rc != ST3D_OK) return rc;

@@ -438,20 +438,40 @@ k_gram_tc_fwd(const __grid_constant__ CUtensorMap map, float* __restrict__ parti
     const float* P0 = partials + (int64_t)b * splits * CC;
     const float* tg = ep.target ? ep.target + (ep.Bt == 1 ? 0 : (int64_t)b * CC) : nullptr;
     float lsum = 0.0f;
-    for (int64_t e = e_lo + 4 * (int64_t)threadIdx.x; e < e_hi; e += 4 * kThreads) {
-        float4 acc = __ldcg(reinterpret_cast<const float4*>(P0 + e));
-        for (int sp = 1; sp < splits; ++sp) {
-            const float4 t = __ldcg(reinterpret_cast<const float4*>(P0 + (int64_t)sp * CC + e));
-            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    // U independent float4 columns per thread and round: U x splits loads in flight (the partials sit in L2; one
+    // column at a time would pay one L2 round trip per split and column, the whole tail latency-bound)
+    constexpr int U = 4;
+    for (int64_t e = e_lo + 4 * (int64_t)threadIdx.x; e < e_hi; e += 4 * kThreads * U) {
+        float4 acc[U], tv[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t ee = e + (int64_t)u * 4 * kThreads;
+            ok[u] = ee < e_hi;
+            acc[u] = ok[u] ? __ldcg(reinterpret_cast<const float4*>(P0 + ee)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            tv[u] = (ok[u] && tg) ? __ldg(reinterpret_cast<const float4*>(tg + ee)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (ep.gram) *reinterpret_cast<float4*>(ep.gram + (int64_t)b * CC + e) = acc;
-        if (tg) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(tg + e));
-            float4 d = make_float4(acc.x - t.x, acc.y - t.y, acc.z - t.z, acc.w - t.w);
-            lsum += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
-            const float s2 = 2.0f * ep.scale;
-            d.x *= s2; d.y *= s2; d.z *= s2; d.w *= s2;
-            if (ep.dgram) *reinterpret_cast<float4*>(ep.dgram + (int64_t)b * CC + e) = d;
+        for (int sp = 1; sp < splits; ++sp) {
+            float4 t[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                t[u] = ok[u] ? __ldcg(reinterpret_cast<const float4*>(P0 + (int64_t)sp * CC + e + (int64_t)u * 4 * kThreads))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < U; ++u) { acc[u].x += t[u].x; acc[u].y += t[u].y; acc[u].z += t[u].z; acc[u].w += t[u].w; }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!ok[u]) continue;
+            const int64_t ee = e + (int64_t)u * 4 * kThreads;
+            if (ep.gram) *reinterpret_cast<float4*>(ep.gram + (int64_t)b * CC + ee) = acc[u];
+            if (tg) {
+                float4 d = make_float4(acc[u].x - tv[u].x, acc[u].y - tv[u].y, acc[u].z - tv[u].z, acc[u].w - tv[u].w);
+                lsum += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
+                const float s2 = 2.0f * ep.scale;
+                d.x *= s2; d.y *= s2; d.z *= s2; d.w *= s2;
+                if (ep.dgram) *reinterpret_cast<float4*>(ep.dgram + (int64_t)b * CC + ee) = d;
+            }
         }
     }
     if (tg && ep.loss_out) {

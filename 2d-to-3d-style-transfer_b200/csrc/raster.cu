@@ -94,6 +94,14 @@ __device__ __forceinline__ void table_pixel_range(const float* __restrict__ tab,
     }
 }
 
+// cull_to_frustum (upstream clip_faces with ClipFrustum(left=-1, right=1, top=-1, bottom=1, cull=True)): a
+// face is dropped when all three of its vertices lie beyond ONE side plane of the NDC frustum.  Evaluated on the
+// unclipped face.  In the kernels the switch travels as bit 1 of the `cull_backfaces` word (bit 0: back faces).
+__device__ __forceinline__ bool frustum_culled(const FaceVerts& v) {
+    return fmaxf(v.x0, fmaxf(v.x1, v.x2)) < -1.0f || fminf(v.x0, fminf(v.x1, v.x2)) > 1.0f ||
+           fmaxf(v.y0, fmaxf(v.y1, v.y2)) < -1.0f || fminf(v.y0, fminf(v.y1, v.y2)) > 1.0f;
+}
+
 template <bool GATHER>
 __global__ void k_setup(const float* __restrict__ face_verts, const float4* __restrict__ verts_ndc,
                         const int32_t* __restrict__ faces, const int64_t* __restrict__ first_idx,
@@ -120,7 +128,8 @@ __global__ void k_setup(const float* __restrict__ face_verts, const float4* __re
     if (fminf(v.z0, fminf(v.z1, v.z2)) < z_clip) hdr[4] = 1;  // would need near-plane clipping (A.2 clip_faces)
     const float area = edge_fn(v.x2, v.y2, v.x0, v.y0, v.x1, v.y1);
     bool valid = fabsf(area) > kEps;                       // also false for NaN
-    if (cull_backfaces && area < 0.0f) valid = false;
+    if ((cull_backfaces & 1) && area < 0.0f) valid = false;
+    if ((cull_backfaces & 2) && frustum_culled(v)) valid = false;
     if (fmaxf(v.z0, fmaxf(v.z1, v.z2)) < 0.0f) valid = false;
     const float radius = __fsqrt_rn(blur_radius);
     const float xmin = fsub(fminf(v.x0, fminf(v.x1, v.x2)), radius);
@@ -447,7 +456,7 @@ __device__ __forceinline__ TriBox tri_box(const FaceVerts& v, int H, int W, floa
     TriBox b{1, 0, 1, 0, 0.0f, false};
     b.area = edge_fn(v.x2, v.y2, v.x0, v.y0, v.x1, v.y1);
     bool valid = fabsf(b.area) > kEps;  // also false for NaN
-    if (cull_backfaces && b.area < 0.0f) valid = false;
+    if ((cull_backfaces & 1) && b.area < 0.0f) valid = false;
     if (fmaxf(v.z0, fmaxf(v.z1, v.z2)) < 0.0f) valid = false;
     const float xmin = fminf(v.x0, fminf(v.x1, v.x2)), xmax = fmaxf(v.x0, fmaxf(v.x1, v.x2));
     const float ymin = fminf(v.y0, fminf(v.y1, v.y2)), ymax = fmaxf(v.y0, fmaxf(v.y1, v.y2));
@@ -705,7 +714,9 @@ k_face_zbuf(const float* __restrict__ face_verts, const int64_t* __restrict__ fi
             const float* p = face_verts + 9 * f;
             v = FaceVerts{p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8]};
         }
-        const int nb = count_behind(v, z_clip);  // z_clip = -inf: clipping off (operator boundary: done upstream)
+        // z_clip = -inf: clipping off (operator boundary: done upstream); a frustum-culled face goes the way of one
+        // that lies entirely behind the plane
+        const int nb = ((cull_backfaces & 2) && frustum_culled(v)) ? 3 : count_behind(v, z_clip);
         if (nb == 0)
             box = tri_box(v, H, W, est, cull_backfaces, ndc_x, ndc_y);
         else if (nb < 3)
@@ -912,9 +923,11 @@ static int run_hard(const RasterWs& ws, const HardSrc& h, int N, int H, int W, i
         // seeds of the pixel-range search: NDC-ordered pixel index j(v) = a v + b (A.3 PixToNonSquareNdc inverted)
         const double rx = W > H ? 2.0 * W / H : 2.0, ry = H > W ? 2.0 * H / W : 2.0;
         const float4 est = make_float4((float)(W / rx), (float)(0.5 * (W - 1)), (float)(H / ry), (float)(0.5 * (H - 1)));
-        // ST3D_EARLY_Z: bit 0 = early-z test in the sweep of queued units, bit 1 = in the small-face pass (default 1;
-        // measurement switch, the result does not depend on it)
-        static const int ez = [] { const char* e = getenv("ST3D_EARLY_Z"); return e ? atoi(e) : 1; }();
+        // ST3D_EARLY_Z: bit 0 = early-z test in the sweep of queued units, bit 1 = in the small-face pass.  A
+        // measurement switch (the result does not depend on it), OFF by default: on B200 the dependent z-buffer read in
+        // front of every exact test costs more than the tests it saves (8 views x 1024^2, cow: 246.8 us without, 271.6
+        // with it in the sweep, 277.6 in both passes)
+        static const int ez = [] { const char* e = getenv("ST3D_EARLY_Z"); return e ? atoi(e) : 0; }();
         const int ez_sweep = ez & 1, ez_small = (ez >> 1) & 1;
         if (h.verts)
             k_face_zbuf<1><<<grid, 128, 0, s>>>(nullptr, nullptr, nullptr, ws.verts_ndc, h.faces, h.V, h.F_per_mesh, H, W,
@@ -1020,11 +1033,11 @@ extern "C" int st3d_rasterize_meshes_forward(const float* face_verts, const int6
         h.first_idx = mesh_to_face_first_idx;
         h.num_faces = num_faces_per_mesh;
         h.F_per_mesh = max_faces_in_mesh;
-        h.cull_backfaces = cull_backfaces;
+        h.cull_backfaces = cull_backfaces ? 1 : 0;
         return run_hard<0>(ws, h, N, H, W, perspective_correct, fo, sp, s);
     }
     int rc = run_bins(ws, face_verts, nullptr, mesh_to_face_first_idx, num_faces_per_mesh, N, max_faces_in_mesh, 0, H, W,
-                      blur_radius, cull_backfaces, false, -INFINITY, s);
+                      blur_radius, cull_backfaces ? 1 : 0, false, -INFINITY, s);
     if (rc != ST3D_OK) return rc;
     const int* tile_list = ws.list;
     if (clipped_faces_neighbor_idx) {  // the pair de-duplication is defined by ascending face order (see k_sort_tile_lists)
@@ -1107,7 +1120,7 @@ extern "C" int st3d_render_forward(const st3d_render_args* a, st3d_stream_t stre
         h.k11 = a->k11;
         h.V = a->V;
         h.F_per_mesh = a->F;
-        h.cull_backfaces = a->cull_backfaces;
+        h.cull_backfaces = (a->cull_backfaces ? 1 : 0) | (a->cull_to_frustum ? 2 : 0);
         h.z_clip = z_clip;
         return run_hard<1>(ws, h, a->N, a->H, a->W, 1, fo, sp, s);
     }
@@ -1115,7 +1128,7 @@ extern "C" int st3d_render_forward(const st3d_render_args* a, st3d_stream_t stre
                                                             nullptr);
     ST3D_LAUNCH_OK("k_transform");
     int rc = run_bins(ws, nullptr, a->faces, nullptr, nullptr, a->N, a->F, a->V, a->H, a->W, a->blur_radius,
-                      a->cull_backfaces, true, z_clip, s);
+                      (a->cull_backfaces ? 1 : 0) | (a->cull_to_frustum ? 2 : 0), true, z_clip, s);
     if (rc != ST3D_OK) return rc;
     k_fine<1, 1><<<ws.NT, 256, 0, s>>>(ws.rec, ws.tile_count, ws.tile_offset, ws.list, ws.capacity, a->H, a->W,
                                            ws.TX, ws.TY, a->blur_radius, 1, a->blur_radius > 0.0f ? 1 : 0, nullptr, fo, sp);

@@ -31,7 +31,7 @@ class RenderArgs(ctypes.Structure):
         ("out_layout", c_i), ("out_image", c_p), ("out_mask", c_p), ("pix_to_face", c_p),
         ("workspace", c_p), ("workspace_bytes", c_sz), ("list_capacity", c_i64), ("z_clip", c_f),
         ("light_kind", c_i), ("light_vec", c_f * 3), ("light_diffuse", c_f * 3), ("light_specular", c_f * 3),
-        ("shininess", c_f), ("background_image", c_p), ("background_batch", c_i),
+        ("shininess", c_f), ("background_image", c_p), ("background_batch", c_i), ("cull_to_frustum", c_i),
     ]
 
 

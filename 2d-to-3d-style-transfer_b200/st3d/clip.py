@@ -58,14 +58,29 @@ def _crossings(tris: torch.Tensor, i1: torch.Tensor, z_clip: float, perspective_
     return (p1, p2, p3, p4, p5), (e1, e2, e3, b4, b5)
 
 
+def frustum_culled(face_verts: torch.Tensor) -> torch.Tensor:
+    """(F,) bool: faces that upstream's `cull_to_frustum=True` removes -- all three vertices beyond ONE of the side
+    planes x = -1, x = 1, y = -1, y = 1 of the NDC frustum (ClipFrustum(left=-1, right=1, top=-1, bottom=1): the z
+    planes are not set by the rasterizer)."""
+    x, y = face_verts[:, :, 0].detach(), face_verts[:, :, 1].detach()
+    return ((x < -1.0).all(dim=1) | (x > 1.0).all(dim=1) | (y < -1.0).all(dim=1) | (y > 1.0).all(dim=1))
+
+
 def clip_faces(face_verts: torch.Tensor, mesh_to_face_first_idx: torch.Tensor, num_faces_per_mesh: torch.Tensor,
-               z_clip: float, perspective_correct: bool = True) -> ClippedFaces:
-    """Returns the inputs unchanged (conversion fields None) when no vertex lies behind the plane --
-    the case of every scene of the reference."""
-    behind = face_verts[:, :, 2].detach() < z_clip
+               z_clip: Optional[float], perspective_correct: bool = True, cull_to_frustum: bool = False) -> ClippedFaces:
+    """Returns the inputs unchanged (conversion fields None) when no vertex lies behind the plane and nothing is
+    culled -- the case of every scene of the reference.  z_clip None: culling only."""
+    if z_clip is None:
+        behind = torch.zeros(face_verts.shape[:2], dtype=torch.bool, device=face_verts.device)
+        z_clip = 0.0
+    else:
+        behind = face_verts[:, :, 2].detach() < z_clip
     nb = behind.sum(dim=1)
-    if not bool(nb.any()):          # one host read, as upstream's early return
+    culled = frustum_culled(face_verts) if cull_to_frustum else None
+    if not bool(nb.any()) and not (culled is not None and bool(culled.any())):   # host read, as upstream's early return
         return ClippedFaces(face_verts, mesh_to_face_first_idx, num_faces_per_mesh)
+    if culled is not None:
+        nb = torch.where(culled, torch.full_like(nb, 3), nb)        # a culled face goes the way of one behind the plane
     dev, dt, Fu = face_verts.device, face_verts.dtype, face_verts.shape[0]
     count = torch.where(nb == 1, 2, torch.where(nb == 3, 0, 1))
     csum = torch.cat([count.new_zeros(1), count.cumsum(0)])

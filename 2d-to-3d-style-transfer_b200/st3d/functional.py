@@ -69,7 +69,8 @@ def render_views(verts: torch.Tensor, faces: torch.Tensor, R: torch.Tensor, T: t
                  znear: float = 1.0, zfar: float = 100.0, blur_radius: float = 0.0, cull_backfaces: bool = False,
                  ambient: Sequence[float] = (1.0, 1.0, 1.0), background: Sequence[float] = (1.0, 1.0, 1.0),
                  sigma: float = 1e-4, gamma: float = 1e-4, planar: bool = True, z_clip: Optional[float] = None,
-                 lights: Optional[dict] = None, background_image: Optional[torch.Tensor] = None):
+                 lights: Optional[dict] = None, background_image: Optional[torch.Tensor] = None,
+                 cull_to_frustum: bool = False):
     """Render N camera views of one mesh in one launch sequence (faces_per_pixel = 1).
 
     lights: None = AmbientLights with the colour `ambient` (what the reference uses); or a dict(kind='point' |
@@ -85,8 +86,8 @@ def render_views(verts: torch.Tensor, faces: torch.Tensor, R: torch.Tensor, T: t
     H, W = (image_size, image_size) if isinstance(image_size, int) else tuple(image_size)
     k00, k11 = fov_scales(fov, aspect, znear)
     spec = ops.RenderSpec(image_size=(H, W), k00=k00, k11=k11, znear=znear, zfar=zfar, blur_radius=blur_radius,
-                          cull_backfaces=cull_backfaces, ambient=tuple(ambient), background=tuple(background),
-                          sigma=sigma, gamma=gamma, z_clip=z_clip,
+                          cull_backfaces=cull_backfaces, cull_to_frustum=cull_to_frustum, ambient=tuple(ambient),
+                          background=tuple(background), sigma=sigma, gamma=gamma, z_clip=z_clip,
                           layout=ops.LAYOUT_PLANAR if planar else ops.LAYOUT_NHWC_RGBA)
     if lights is not None and lights.get("kind", "ambient") != "ambient":
         kind = lights["kind"]
@@ -149,17 +150,18 @@ class _RasterizeFn(torch.autograd.Function):
 
 def rasterize_meshes(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, image_size, blur_radius=0.0,
                      faces_per_pixel=1, perspective_correct=True, clip_barycentric_coords=False, cull_backfaces=False,
-                     z_clip_value: Optional[float] = None):
+                     z_clip_value: Optional[float] = None, cull_to_frustum: bool = False):
     """Upstream `rasterize_meshes` from packed face vertices on: optional near-plane clipping (torch ops, as
     upstream's clip.py) -> `_C.rasterize_meshes` (libst3d kernels) -> indices / barycentrics mapped back to the
     unclipped faces.  Differentiable w.r.t. face_verts."""
     args = (image_size, float(blur_radius), int(faces_per_pixel), bool(perspective_correct),
             bool(clip_barycentric_coords), bool(cull_backfaces))
-    if z_clip_value is None:
+    if z_clip_value is None and not cull_to_frustum:
         return _RasterizeFn.apply(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, *args)
     from . import clip as _clip
-    cl = _clip.clip_faces(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, float(z_clip_value),
-                          bool(perspective_correct))
+    cl = _clip.clip_faces(face_verts, mesh_to_face_first_idx, num_faces_per_mesh,
+                          None if z_clip_value is None else float(z_clip_value), bool(perspective_correct),
+                          bool(cull_to_frustum))
     p2f, zbuf, bary, dists = _RasterizeFn.apply(cl.face_verts, cl.mesh_to_face_first_idx, cl.num_faces_per_mesh, *args,
                                                 cl.clipped_faces_neighbor_idx)
     p2f, bary = _clip.convert_clipped_rasterization_to_original_faces(p2f, bary, cl)

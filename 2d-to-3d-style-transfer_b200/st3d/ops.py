@@ -313,6 +313,7 @@ class RenderSpec:
     zfar: float = 100.0
     blur_radius: float = 0.0
     cull_backfaces: bool = False
+    cull_to_frustum: bool = False
     ambient: tuple = (1.0, 1.0, 1.0)
     background: tuple = (1.0, 1.0, 1.0)
     sigma: float = 1e-4
@@ -359,6 +360,7 @@ def render_forward(spec: RenderSpec, verts, faces, R, T, *, face_uvs=None, textu
     a.R, a.T, a.N = _p(R), _p(T), N
     a.k00, a.k11, a.znear, a.zfar = spec.k00, spec.k11, spec.znear, spec.zfar
     a.H, a.W, a.blur_radius, a.cull_backfaces = H, W, spec.blur_radius, int(spec.cull_backfaces)
+    a.cull_to_frustum = int(spec.cull_to_frustum)
     keep = [verts, faces, R, T]
     if texture is not None:
         texture = _cuda_f32("texture", texture, 3)

@@ -171,6 +171,9 @@ typedef struct st3d_render_args {
      * (Nb,3,H,W) planar with Nb = background_batch in {1, N}; NULL keeps the constant colour. */
     const float* background_image;
     int background_batch;
+    /* RasterizationSettings.cull_to_frustum: drop the faces whose three vertices all lie beyond one side plane
+     * (x = -1, x = 1, y = -1, y = 1) of the NDC frustum, as upstream's clip_faces does before rasterizing */
+    int cull_to_frustum;
 } st3d_render_args;
 
 size_t st3d_render_workspace_size(int N, int64_t V, int64_t F, int H, int W, int64_t list_capacity);

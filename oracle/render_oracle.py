@@ -287,7 +287,27 @@ def _plane_crossings(tri, i1, z_clip, perspective_correct):
     return p4, p5, torch.stack(b4), torch.stack(b5), i2, i3
 
 
-def clip_faces(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, z_clip, perspective_correct=True):
+def frustum_culled(face_verts):
+    """cull_to_frustum (upstream clip_faces with ClipFrustum(left=-1, right=1, top=-1, bottom=1, cull=True)):
+    faces whose three vertices all lie beyond ONE of the planes x = -1, x = 1, y = -1, y = 1."""
+    x, y = face_verts[:, :, 0].detach(), face_verts[:, :, 1].detach()
+    return (x < -1).all(1) | (x > 1).all(1) | (y < -1).all(1) | (y > 1).all(1)
+
+
+def _with_cull_of(fv, fv_exact):
+    """fv (differentiable, any dtype) with the faces the EXACT fp32 coordinates cull pushed far outside the frustum, so
+    that the differentiable clip removes the same faces whatever the rounding of fv (a face the exact coordinates keep
+    but fv would cull trips the to_unclipped assert in render_views)."""
+    culled = frustum_culled(fv_exact)
+    if not bool(culled.any()):
+        return fv
+    shift = torch.zeros_like(fv)
+    shift[culled, :, 0] = 1e6
+    return fv + shift
+
+
+def clip_faces(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, z_clip, perspective_correct=True,
+               cull_to_frustum=False):
     """Clip every face against the plane z = z_clip.  Per face, by the number of vertices
     with z < z_clip:  0 -> kept;  3 -> removed;  2 (p1 in front) -> the triangle (p4, p5, p1);
     1 (p1 behind) -> the quad split into (p4, p2, p5) and (p5, p2, p3), linked as neighbours.
@@ -299,12 +319,13 @@ def clip_faces(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, z_clip, p
     first = mesh_to_face_first_idx.tolist()
     num = num_faces_per_mesh.tolist()
     behind = (face_verts[:, :, 2].detach() < z_clip)
+    culled = frustum_culled(face_verts) if cull_to_frustum else torch.zeros(face_verts.shape[0], dtype=torch.bool)
     out_fv, to_unc, conv, was, neigh, new_first, new_num = [], [], [], [], [], [], []
     eye = torch.eye(3, dtype=dt)
     for n in range(len(first)):
         new_first.append(len(out_fv))
         for f in range(first[n], first[n] + num[n]):
-            nb = int(behind[f].sum())
+            nb = 3 if bool(culled[f]) else int(behind[f].sum())     # a culled face is removed like one behind the plane
             tri = face_verts[f]
             if nb == 0:
                 out_fv.append(tri); to_unc.append(f); conv.append(eye); was.append(False); neigh.append(-1)
@@ -452,7 +473,7 @@ DEFAULT_MATERIALS = dict(ambient=(1.0, 1.0, 1.0), diffuse=(1.0, 1.0, 1.0), specu
 def render_views(verts, faces, R, T, image_size, texture=None, verts_uvs=None, faces_uvs=None,
                  verts_rgb=None, blur_radius=0.0, faces_per_pixel=1, fov=60.0, znear=1.0, zfar=100.0,
                  sigma=1e-4, gamma=1e-4, background=(1.0, 1.0, 1.0), lights=None, materials=None,
-                 nthreads=1, return_fragments=False, z_clip=None):
+                 nthreads=1, return_fragments=False, z_clip=None, cull_to_frustum=False):
     """Render N views of one mesh.  Differentiable w.r.t. verts / texture / verts_rgb.
     z_clip: near-plane clip depth (None = znear / 2, what MeshRasterizer infers for perspective cameras).
 
@@ -473,12 +494,13 @@ def render_views(verts, faces, R, T, image_size, texture=None, verts_uvs=None, f
     z_clip = znear / 2.0 if z_clip is None else z_clip
     ndc = transform_verts_torch(verts, R, T, k00, k11)
     fv = ndc[:, faces].reshape(N * Fn, 3, 3)
-    if bool((fv_exact[:, :, 2] < z_clip).any()):    # A.2: some face crosses (or lies behind) the clip plane
-        cl_x = clip_faces(fv_exact, first, num, np.float32(z_clip).item(), True)
+    if bool((fv_exact[:, :, 2] < z_clip).any()) or (cull_to_frustum and bool(frustum_culled(fv_exact).any())):
+        # A.2: some face crosses (or lies behind) the clip plane, or is culled
+        cl_x = clip_faces(fv_exact, first, num, np.float32(z_clip).item(), True, cull_to_frustum)
         p2f_c, zbuf_x, bary_x, dists_x = rasterize_naive(cl_x["face_verts"], cl_x["first"], cl_x["num"], (H, W),
                                                           blur_radius, faces_per_pixel, True, blur_radius > 0, False,
                                                           nthreads, clipped_faces_neighbor_idx=cl_x["neighbor"])
-        cl = clip_faces(fv, first, num, z_clip, True)
+        cl = clip_faces(_with_cull_of(fv, fv_exact) if cull_to_frustum else fv, first, num, z_clip, True, cull_to_frustum)
         assert torch.equal(cl["to_unclipped"], cl_x["to_unclipped"])
         zbuf, bary_c, dists = fragments_from_faces(cl["face_verts"], p2f_c, True, blur_radius > 0)
         p2f, bary = convert_clipped_to_unclipped(p2f_c, bary_c, cl)

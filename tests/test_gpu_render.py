@@ -649,3 +649,36 @@ def test_background_image_in_the_epilogue_equals_apply_background(cow):
         assert torch.equal(comp, want)
         (comp * cot).sum().backward()
         _close(t3.grad, t2.grad, tol=1e-6, what="texture gradient through the composite kernel")
+
+
+def test_cull_to_frustum_matches_oracle_in_both_paths(cow):
+    """RasterizationSettings.cull_to_frustum: faces entirely beyond one side plane x, y = +-1 of the NDC
+    frustum are dropped -- visible on a non-square image, whose long axis spans more than [-1, 1].  The fused kernels
+    and the Fragments path (torch clip around the operator-boundary rasterizer) both follow the oracle bit for bit."""
+    import st3d.functional as Fn
+    H, W = 48, 96
+    R, T = ro.look_at_view_transform(1.7, [10.0, 30.0], [20.0, 200.0], at=((0.9, 0.1, 0.25),))
+    vrgb = torch.rand(cow["verts"].shape[0], 3, generator=torch.Generator().manual_seed(5))
+    kw = dict(verts_rgb=vrgb, return_fragments=True, nthreads=8)
+    plain, fp = ro.render_views(cow["verts"], cow["faces"], R, T, (H, W), **kw)
+    want, fw = ro.render_views(cow["verts"], cow["faces"], R, T, (H, W), cull_to_frustum=True, **kw)
+    assert (fp["pix_to_face"] != fw["pix_to_face"]).float().mean().item() > 0.05     # culling does change this picture
+    args = (cow["verts"].cuda(), cow["faces"].cuda(), R.cuda(), T.cuda(), (H, W))
+    rgba, p2f = Fn.render_views(*args, verts_rgb=vrgb.cuda(), planar=False, cull_to_frustum=True)
+    assert torch.equal(p2f.cpu().long(), fw["pix_to_face"][..., 0])
+    _close(rgba, want, what="culled rgba")
+    rgba0, p2f0 = Fn.render_views(*args, verts_rgb=vrgb.cuda(), planar=False)
+    assert torch.equal(p2f0.cpu().long(), fp["pix_to_face"][..., 0])
+    # Fragments path, K = 2 with blur (tile bins), culled
+    k00, k11 = ro.fov_scales(60.0)
+    ndc = Fn.transform_verts(cow["verts"].cuda(), R.cuda(), T.cuda())
+    Fc = cow["faces"].shape[0]
+    fv = ndc[:, cow["faces"].cuda()].reshape(2 * Fc, 3, 3)
+    first = torch.arange(2, device="cuda") * Fc
+    num = torch.full((2,), Fc, device="cuda")
+    got = Fn.rasterize_meshes(fv, first, num, (H, W), blur_radius=1e-3, faces_per_pixel=2, clip_barycentric_coords=True,
+                              z_clip_value=0.5, cull_to_frustum=True)
+    _, fo = ro.render_views(cow["verts"], cow["faces"], R, T, (H, W), cull_to_frustum=True, blur_radius=1e-3,
+                            faces_per_pixel=2, **kw)
+    assert torch.equal(got[0].cpu(), fo["pix_to_face"])
+    _close(got[1], fo["zbuf_exact"], what="culled zbuf")
