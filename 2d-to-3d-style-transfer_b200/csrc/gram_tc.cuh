@@ -500,11 +500,13 @@ struct BwdCfg {
     static constexpr int F_BYTES = 4 * 4096;      // four [32 j][32 x] boxes = 128 x's
     static constexpr int S_BYTES = C * 128;       // [C rows c][32 j]
     static constexpr int STAGE_BYTES = F_BYTES + S_BYTES;
-    // C <= 128 (the HBM-bound layers): the fused epilogue (ST3D_GRAM_ACCUMULATE / ST3D_GRAM_RELU_MASK) prefetches the
-    // incoming gradient and the mask values through a per-warp cp.async ring, RING_SLOTS batches of 8 KB deep
-    static constexpr int RING_SLOTS = C <= 128 ? 3 : 0;
+    // C <= 256: the fused epilogue (ST3D_GRAM_ACCUMULATE / ST3D_GRAM_RELU_MASK) prefetches the incoming gradient and
+    // the mask values through a per-warp cp.async ring, RING_SLOTS batches of 8 KB deep.  At C = 256 the ring takes
+    // the place of two of the four TMA stages: an item's epilogue (eight 32-channel groups, each a read-modify-write
+    // of global memory) is what bounds that kernel, its 2 us of MMAs are fed well enough by two stages.
+    static constexpr int RING_SLOTS = C <= 256 ? 3 : 0;
     static constexpr int RING_BYTES = 4 * RING_SLOTS * 8192;
-    static constexpr int STAGES = C == 64 ? 4 : (C == 128 ? 3 : (C == 256 ? 4 : 2));
+    static constexpr int STAGES = C == 64 ? 4 : (C == 128 ? 3 : 2);
     static constexpr int KB = C / 32;             // k-blocks (32 channels j each) per chunk
     static constexpr int S_BOX_ROWS = C < 256 ? C : 256;
     static constexpr int S_BOXES = C / S_BOX_ROWS;
@@ -1088,29 +1090,46 @@ static int launch_fwd(const float* feat, const GramPlan& p, GramEpilogue ep, int
         const uintptr_t bits = (uintptr_t)ep.target | (uintptr_t)ep.gram | (uintptr_t)ep.dgram | (uintptr_t)p.partials;
         if (bits & 15) ep.fused = 0;
     }
-    if (ep.fused && p.splits * Cfg::GROUPS > 1) ST3D_CUDA_OK(cudaMemsetAsync(p.counters, 0, (size_t)p.B * sizeof(unsigned), s));
-    *fused_out = ep.fused;
-    if (Cfg::CLUSTER) {
+    const bool waits = ep.fused && p.splits * Cfg::GROUPS > 1;  // CTAs of an image wait for one another
+    if (waits) ST3D_CUDA_OK(cudaMemsetAsync(p.counters, 0, (size_t)p.B * sizeof(unsigned), s));
+    float* partials = p.partials;
+    int splits = p.splits;
+    int64_t k_chunk = p.k_chunk, HW = p.HW;
+    for (int attempt = 0; attempt < 2; ++attempt) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(Cfg::GROUPS, p.splits, p.B);
         cfg.blockDim = dim3(kThreads);
         cfg.dynamicSmemBytes = Cfg::SMEM;
         cfg.stream = s;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = Cfg::GROUPS;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
+        cudaLaunchAttribute attr[2];
+        int na = 0;
+        if (Cfg::CLUSTER) {
+            attr[na].id = cudaLaunchAttributeClusterDimension;
+            attr[na].val.clusterDim.x = Cfg::GROUPS;
+            attr[na].val.clusterDim.y = 1;
+            attr[na].val.clusterDim.z = 1;
+            ++na;
+        }
+        if (waits && ep.fused) {
+            // a COOPERATIVE launch: the driver places the whole grid at once or refuses, so the in-kernel wait can
+            // neither starve behind another kernel nor deadlock against a second instance of itself on another stream
+            attr[na].id = cudaLaunchAttributeCooperative;
+            attr[na].val.cooperative = 1;
+            ++na;
+        }
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        float* partials = p.partials;
-        int splits = p.splits;
-        int64_t k_chunk = p.k_chunk, HW = p.HW;
-        ST3D_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gram_tc_fwd<C, NHWC>, map, partials, splits, k_chunk, HW, ep));
-    } else {
-        k_gram_tc_fwd<C, NHWC><<<dim3(Cfg::GROUPS, p.splits, p.B), kThreads, Cfg::SMEM, s>>>(map, p.partials, p.splits,
-                                                                                            p.k_chunk, p.HW, ep);
+        cfg.numAttrs = na;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, k_gram_tc_fwd<C, NHWC>, map, partials, splits, k_chunk, HW, ep);
+        if (e == cudaSuccess) break;
+        if (attempt == 0 && waits && ep.fused) {  // co-residency refused: two-kernel form (GEMM, then k_gram_finalize)
+            (void)cudaGetLastError();
+            ep.fused = 0;
+            continue;
+        }
+        st3d_set_error("launch of k_gram_tc_fwd: %s", cudaGetErrorString(e));
+        return ST3D_ERR_CUDA;
     }
+    *fused_out = ep.fused;
     ST3D_LAUNCH_OK("k_gram_tc_fwd");
     return ST3D_OK;
 }

@@ -83,6 +83,12 @@ class _ConvReLUStyleTapFn(torch.autograd.Function):
             g = torch.ops.aten.threshold_backward(grad_y, y, 0.0)
         else:
             out = None
+            # The Gram kernel's epilogue adds into the INCOMING gradient buffer (no third pass over the largest tensors of
+            # the step).  Autograd does not in general allow a backward to write its grad input: the buffer could be
+            # shared with y.retain_grad(), a tensor hook, or another consumer's accumulation.  Here y's only other
+            # consumer is the next VGG module, whose backward (cuDNN dgrad / k_maxpool_bwd) returns a fresh tensor that
+            # nothing else holds, and perceptual_loss_of_images never exposes y -- callers that do hold y (get_features)
+            # go through _StyleLayerFn, which allocates.
             if grad_y is not None:                  # accumulate into the incoming gradient when its layout allows it
                 if grad_y.stride() == y.stride() and grad_y.dtype == torch.float32:
                     out = grad_y

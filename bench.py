@@ -251,7 +251,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
-    budget = float(os.environ.get("ST3D_REF_BUDGET_S", "240"))
+    budget = float(os.environ.get("ST3D_REF_BUDGET_S", "400"))
     # the GPU arm's job at --gpus N is N x args.views views per iteration (weak scaling): the same job here
     world = max(1, args.gpus)
     total = args.views * world
