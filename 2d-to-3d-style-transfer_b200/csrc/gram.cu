@@ -287,8 +287,12 @@ extern "C" int st3d_gram_mse_forward(const float* feat, const float* target, int
     static const bool separate = [] { const char* e = getenv("ST3D_GRAM_SEPARATE_FINALIZE"); return e && e[0] == '1'; }();
     // ST3D_GRAM_FUSE_MAXC=<C>: fuse only for layers of at most C channels (measurement switch; default: all)
     static const int fuse_maxc = [] { const char* e = getenv("ST3D_GRAM_FUSE_MAXC"); return e ? atoi(e) : 1 << 30; }();
+    // The loss epilogue is what gets fused (losses.py:35-39: Gram, MSE against the style Gram and dG in one kernel).  A bare
+    // Gram product (the style image's targets, B = 1) keeps the two-kernel form: with one image every CTA of the launch
+    // waits for all the others before a reduction of a few dozen elements each, and the cooperative launch cannot
+    // overlap the tail of the kernel in front of it -- measured 31-36 us against 21-27 us per layer on B200.
     GramEpilogue ep{target, gram, target ? dgram : nullptr, target ? loss_out : nullptr, p.counters, Bt, scale,
-                    (separate || C > fuse_maxc) ? 0 : 1};
+                    (separate || C > fuse_maxc || target == nullptr) ? 0 : 1};
     int fused = 0;
     rc = gram_partials(feat, p, precision, layout, ep, &fused, s);
     if (rc != ST3D_OK) return rc;

@@ -491,8 +491,11 @@ k_gram_tc_fwd(const __grid_constant__ CUtensorMap map, float* __restrict__ parti
 // =====================================================================================================
 // backward: D[x (128 lanes)][c (C columns)] = sum_j F[j][x] S[c][j]
 // =====================================================================================================
-template <int C>
+// RING: the epilogue owns a cp.async prefetch ring (fused accumulate / ReLU-mask tail).  Always at C <= 128; at C = 256
+// the ring takes the place of two of the four TMA stages, so the launcher picks it only when the tail is requested.
+template <int C, bool RING = (C <= 128)>
 struct BwdCfg {
+    static_assert(!RING || C <= 256, "no shared memory left for a prefetch ring at C = 512");
     static constexpr int NHALF = C == 512 ? 2 : 1;
     static constexpr int NMMA = C / NHALF;
     static constexpr int ACC = C <= 256 ? 2 : 1;  // TMEM accumulator buffers (epilogue overlaps the next chunk)
@@ -500,13 +503,14 @@ struct BwdCfg {
     static constexpr int F_BYTES = 4 * 4096;      // four [32 j][32 x] boxes = 128 x's
     static constexpr int S_BYTES = C * 128;       // [C rows c][32 j]
     static constexpr int STAGE_BYTES = F_BYTES + S_BYTES;
-    // C <= 256: the fused epilogue (ST3D_GRAM_ACCUMULATE / ST3D_GRAM_RELU_MASK) prefetches the incoming gradient and
-    // the mask values through a per-warp cp.async ring, RING_SLOTS batches of 8 KB deep.  At C = 256 the ring takes
-    // the place of two of the four TMA stages: an item's epilogue (eight 32-channel groups, each a read-modify-write
-    // of global memory) is what bounds that kernel, its 2 us of MMAs are fed well enough by two stages.
-    static constexpr int RING_SLOTS = C <= 256 ? 3 : 0;
+    // The fused epilogue (ST3D_GRAM_ACCUMULATE / ST3D_GRAM_RELU_MASK) prefetches the incoming gradient and the mask
+    // values through a per-warp cp.async ring, RING_SLOTS batches of 8 KB deep.  At C = 256 the ring costs two TMA
+    // stages: with the tail an item's epilogue (eight 32-channel groups, each a read-modify-write of global memory)
+    // bounds the kernel and its 2 us of MMAs are fed well enough by two stages (0.128 -> 0.083 ms at 8 x 256 x 16384);
+    // without the tail four stages are faster (58 vs 73 us), hence the second configuration.
+    static constexpr int RING_SLOTS = RING ? 3 : 0;
     static constexpr int RING_BYTES = 4 * RING_SLOTS * 8192;
-    static constexpr int STAGES = C == 64 ? 4 : (C == 128 ? 3 : 2);
+    static constexpr int STAGES = C == 64 ? 4 : (C == 128 ? 3 : (C == 256 ? (RING ? 2 : 4) : 2));
     static constexpr int KB = C / 32;             // k-blocks (32 channels j each) per chunk
     static constexpr int S_BOX_ROWS = C < 256 ? C : 256;
     static constexpr int S_BOXES = C / S_BOX_ROWS;
@@ -518,11 +522,11 @@ struct BwdCfg {
 // NHWC = false: A = F^T tile from rows j of (B, C, HW): MN-major, 32-byte-atom swizzle, four [32 j][32 x] boxes.
 // NHWC = true : A = F tile [128 x rows][32 j] of (B, HW, C): K-major, plain 128-byte swizzle, one box; the
 //               epilogue thread owns one pixel row and stores 32 consecutive channels (128 contiguous bytes).
-template <int C, bool NHWC>
+template <int C, bool NHWC, bool RING>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__ CUtensorMap map_s,
               const float* __restrict__ feat, float* __restrict__ grad_feat, int B, int64_t HW, int accumulate) {
-    using Cfg = BwdCfg<C>;
+    using Cfg = BwdCfg<C, RING>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* stages = smem;
@@ -1167,13 +1171,9 @@ static int launch_bwd_pair(const float* feat, const GramPlan& p, int accumulate,
     return ST3D_OK;
 }
 
-template <int C, bool NHWC>
-static int launch_bwd(const float* feat, const GramPlan& p, int accumulate, float* grad_feat, cudaStream_t s) {
-    if (C == 512) {  // CTA pairs (cta_group::2); ST3D_GRAM_BWD512_SINGLE=1 keeps the one-CTA kernel for comparison
-        static const bool single = [] { const char* e = getenv("ST3D_GRAM_BWD512_SINGLE"); return e && e[0] == '1'; }();
-        if (!single) return launch_bwd_pair<NHWC>(feat, p, accumulate, grad_feat, s);
-    }
-    using Cfg = BwdCfg<C>;
+template <int C, bool NHWC, bool RING>
+static int launch_bwd_cfg(const float* feat, const GramPlan& p, int accumulate, float* grad_feat, cudaStream_t s) {
+    using Cfg = BwdCfg<C, RING>;
     CUtensorMap map_f, map_s;
     int rc = NHWC ? make_map_nhwc(&map_f, feat, p.B, p.HW, C, 128, CU_TENSOR_MAP_SWIZZLE_128B)
                   : make_map(&map_f, feat, (uint64_t)p.B * C, (uint64_t)p.HW, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
@@ -1181,14 +1181,26 @@ static int launch_bwd(const float* feat, const GramPlan& p, int accumulate, floa
     rc = make_map(&map_s, p.sym, (uint64_t)p.B * C, (uint64_t)C, Cfg::S_BOX_ROWS);
     if (rc != ST3D_OK) return rc;
     static std::atomic<uint64_t> attr_done{0};
-    rc = ensure_smem_attr(k_gram_tc_bwd<C, NHWC>, (int)Cfg::SMEM, attr_done);
+    rc = ensure_smem_attr(k_gram_tc_bwd<C, NHWC, RING>, (int)Cfg::SMEM, attr_done);
     if (rc != ST3D_OK) return rc;
     const int64_t items = (int64_t)p.B * ((p.HW + 127) / 128);
     ST3D_REQUIRE(items < (1ll << 31), "gram_backward: B * ceil(HW / 128) = %lld work items exceed 2^31", (long long)items);
     const int grid = (int)std::min<int64_t>(items, 148);
-    k_gram_tc_bwd<C, NHWC><<<grid, kThreads, Cfg::SMEM, s>>>(map_f, map_s, feat, grad_feat, p.B, p.HW, accumulate);
+    k_gram_tc_bwd<C, NHWC, RING><<<grid, kThreads, Cfg::SMEM, s>>>(map_f, map_s, feat, grad_feat, p.B, p.HW, accumulate);
     ST3D_LAUNCH_OK("k_gram_tc_bwd");
     return ST3D_OK;
+}
+
+template <int C, bool NHWC>
+static int launch_bwd(const float* feat, const GramPlan& p, int accumulate, float* grad_feat, cudaStream_t s) {
+    if (C == 512) {  // CTA pairs (cta_group::2); ST3D_GRAM_BWD512_SINGLE=1 keeps the one-CTA kernel for comparison
+        static const bool single = [] { const char* e = getenv("ST3D_GRAM_BWD512_SINGLE"); return e && e[0] == '1'; }();
+        if (!single) return launch_bwd_pair<NHWC>(feat, p, accumulate, grad_feat, s);
+    }
+    // C = 256: the prefetch-ring configuration when the fused tail is requested on channels_last features (the only
+    // layout the ring serves), the four-stage one otherwise
+    if (C == 256 && NHWC && accumulate != 0) return launch_bwd_cfg<C, NHWC, (C <= 256)>(feat, p, accumulate, grad_feat, s);
+    return launch_bwd_cfg<C, NHWC, (C <= 128)>(feat, p, accumulate, grad_feat, s);
 }
 
 }  // namespace tc

@@ -1,0 +1,22 @@
+#!/bin/bash
+# Round-2 ncu captures (GPU box, one GPU).  Every profiled command first runs plain and must exit 0.
+# Numbers printed by runs under ncu are never bench values.
+set -u
+OUT=gpurun_out
+BENCH="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extras --no-standin --no-scaling-128v --profile-run"
+K='regex:k_gram|k_resolve|k_sweep_units|k_face_zbuf|k_render_bwd|k_prepare|k_mse|k_maxpool|k_transform|k_composite'
+
+$BENCH > $OUT/r2_prof_plain.log 2>&1 || { echo "plain bench failed"; exit 1; }
+# 1. every launch of one warm-up + one timed step with its device time
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/r2_launches_ncu.csv $BENCH \
+    > $OUT/r2_prof_launches.log 2>&1
+# 2. --set full over the libst3d launches of the timed step (42 per step; the first 42 belong to the warm-up step)
+ncu --set full --clock-control none -k "$K" -s 42 -c 42 -o $OUT/r2_full $BENCH > $OUT/r2_prof_full.log 2>&1
+ncu -i $OUT/r2_full.ncu-rep --page raw --csv > $OUT/r2_ncu_full_raw.csv 2> /dev/null
+# 3. dense mesh: 1.5 M faces, 8 views x 1024^2, forward + texture backward
+DENSE="env SUBDIV=4 SIZE=1024 REPS=2 NEED_VERTS=0 python scripts/render_only.py"
+$DENSE > $OUT/r2_prof_dense_plain.log 2>&1 || { echo "plain dense render failed"; exit 1; }
+ncu --set full --clock-control none -k "$K" -s 5 -c 5 -o $OUT/r2_full_dense $DENSE > $OUT/r2_prof_dense.log 2>&1
+ncu -i $OUT/r2_full_dense.ncu-rep --page raw --csv > $OUT/r2_ncu_full_dense_raw.csv 2> /dev/null
+rm -f $OUT/r2_full.ncu-rep $OUT/r2_full_dense.ncu-rep
+ls -la $OUT | tail -12

@@ -276,3 +276,49 @@ def test_reference_script_fixtures_are_byte_identical(golden_dir):
         if os.path.exists(live):
             with open(live, "rb") as fh:
                 assert fh.read() == data, f"{name} differs from {live}"
+
+
+def test_mesh_regularisers_known_answers():
+    """SURVEY A.7 regularisers (pytorch3d.loss is absent, so neither the oracle nor st3d.mesh_losses can be checked
+    against it): closed-form values derived by hand on meshes small enough to do so, for BOTH implementations.
+
+    Regular tetrahedron, vertices (+-1,+-1,+-1) with an even number of minus signs, edge length 2 sqrt 2:
+      edge loss (target 0) = mean |e|^2 = 8;
+      uniform Laplacian: the three neighbours of v average to -v / 3 (the four vertices sum to 0), so
+        |L v| = |-(4/3) v| = 4 sqrt(3) / 3 for every vertex;
+      normal consistency: for the edge (v0, v1) = ((1,1,1), (1,-1,-1)) with opposite vertices a = (-1,1,-1),
+        b = (-1,-1,1):  n0 = (v1 - v0) x (a - v0) = (4,4,-4),  n1 = -(v1 - v0) x (b - v0) = (4,-4,4),
+        cos = (16 - 16 - 16) / 48 = -1/3, so 1 - cos = 4/3 on every edge by symmetry.
+    Unit square split along its diagonal (0,0)-(1,1): five edges of squared length 1,1,1,1,2 -> 6/5; coplanar faces ->
+      normal consistency 0; |L v| = 2 sqrt(2)/3, sqrt(2)/2, 2 sqrt(2)/3, sqrt(2)/2 -> mean (4 sqrt(2)/3 + sqrt(2)) / 4.
+    The same square folded by 90 degrees about the diagonal (fourth vertex at (1/2, 1/2, h)) -> normal consistency 1."""
+    from st3d import mesh_losses as ml
+    s2, s3 = 2.0 ** 0.5, 3.0 ** 0.5
+    tet_v = torch.tensor([[1.0, 1, 1], [1, -1, -1], [-1, 1, -1], [-1, -1, 1]], dtype=torch.float64)
+    tet_f = torch.tensor([[0, 1, 2], [0, 3, 1], [0, 2, 3], [1, 3, 2]])
+    sq_v = torch.tensor([[0.0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]], dtype=torch.float64)
+    sq_f = torch.tensor([[0, 1, 2], [0, 2, 3]])
+    fold_v = sq_v.clone()
+    fold_v[3] = torch.tensor([0.5, 0.5, 0.7])
+    cases = [
+        (tet_v, tet_f, 8.0, 4 * s3 / 3, 4.0 / 3),
+        (sq_v, sq_f, 6.0 / 5, (4 * s2 / 3 + s2) / 4, 0.0),
+        (fold_v, sq_f, None, None, 1.0),
+    ]
+    impls = [("oracle", lo.mesh_edge_loss, lo.mesh_laplacian_smoothing, lo.mesh_normal_consistency),
+             ("st3d", ml.edge_loss, ml.laplacian_smoothing, ml.normal_consistency)]
+    for name, edge, lap, ncons in impls:
+        for v, f, want_e, want_l, want_n in cases:
+            if want_e is not None:
+                assert abs(float(edge(v, f)) - want_e) < 1e-12, (name, "edge")
+                assert abs(float(lap(v, f)) - want_l) < 1e-12, (name, "laplacian")
+            assert abs(float(ncons(v, f)) - want_n) < 1e-12, (name, "normal consistency")
+    # gradients of the two implementations agree on a perturbed tetrahedron (double precision)
+    g = torch.Generator().manual_seed(0)
+    base = tet_v + 0.1 * torch.rand(tet_v.shape, generator=g, dtype=torch.float64)
+    grads = []
+    for _, edge, lap, ncons in impls:
+        v = base.clone().requires_grad_(True)
+        (edge(v, tet_f) + 2 * lap(v, tet_f) + 3 * ncons(v, tet_f)).backward()
+        grads.append(v.grad)
+    assert torch.allclose(grads[0], grads[1], rtol=1e-10, atol=1e-12)
