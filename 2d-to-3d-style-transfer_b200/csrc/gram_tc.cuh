@@ -1088,6 +1088,10 @@ static int launch_fwd(const float* feat, const GramPlan& p, GramEpilogue ep, int
     // The in-kernel reduction waits for the other CTAs of its image: only when they are certain to be resident --
     // one CTA per SM (the kernel's shared memory allows no more), the whole grid within the SM count (gram_plan sizes
     // it for 148), or no cross-CTA wait at all beyond a hardware-co-scheduled cluster (splits == 1).
+    // C = 512 (the 4-CTA cluster) keeps the two-kernel form: a launch that is cooperative AND clustered runs on its own
+    // but fails under Nsight Compute's kernel replay (LaunchFailed, CUDA 12.9 / driver 580), and a kernel that cannot be
+    // profiled is not worth the 5-10 us the fusion saves on the two smallest layers
+    if (Cfg::CLUSTER) ep.fused = 0;
     if (ep.fused) {
         const int64_t grid = (int64_t)Cfg::GROUPS * p.splits * p.B;
         if (p.splits > 1 && grid > sm_count()) ep.fused = 0;

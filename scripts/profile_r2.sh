@@ -10,8 +10,8 @@ $BENCH > $OUT/r2_prof_plain.log 2>&1 || { echo "plain bench failed"; exit 1; }
 # 1. every launch of one warm-up + one timed step with its device time
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/r2_launches_ncu.csv $BENCH \
     > $OUT/r2_prof_launches.log 2>&1
-# 2. --set full over the libst3d launches of the timed step (42 per step; the first 42 belong to the warm-up step)
-ncu --set full --clock-control none -k "$K" -s 42 -c 42 -o $OUT/r2_full $BENCH > $OUT/r2_prof_full.log 2>&1
+# 2. --set full over the libst3d launches of the warm-up step and of the timed step (~50 each)
+ncu --set full --clock-control none -k "$K" -c 110 -o $OUT/r2_full $BENCH > $OUT/r2_prof_full.log 2>&1
 ncu -i $OUT/r2_full.ncu-rep --page raw --csv > $OUT/r2_ncu_full_raw.csv 2> /dev/null
 # 3. dense mesh: 1.5 M faces, 8 views x 1024^2, forward + texture backward
 DENSE="env SUBDIV=4 SIZE=1024 REPS=2 NEED_VERTS=0 python scripts/render_only.py"
