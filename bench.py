@@ -276,8 +276,8 @@ def run_reference(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 # filled from the round's ncu capture (profiles/): (bytes per launch, source) of the fused Gram backward at conv1_1
-TRAFFIC_FUSED_BWD64 = (1570500000, "profiles/r1b_ncu_full_gram_bwd_fused.csv: k_gram_tc_bwd<64, NHWC> with ST3D_GRAM_ACCUMULATE | "
-                                   "ST3D_GRAM_RELU_MASK, dram read 1074.7 MB + write 495.8 MB per launch (the mask's second read "
+TRAFFIC_FUSED_BWD64 = (1568011000, "profiles/r2_ncu_full.csv: k_gram_tc_bwd<64, NHWC, RING> with ST3D_GRAM_ACCUMULATE | "
+                                   "ST3D_GRAM_RELU_MASK, dram read 1075.4 MB + write 492.6 MB per launch (the mask's second read "
                                    "of F hits L2)")
 
 
