@@ -251,7 +251,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
-    budget = float(os.environ.get("ST3D_REF_BUDGET_S", "400"))
+    budget = float(os.environ.get("ST3D_REF_BUDGET_S", "480"))
     # the GPU arm's job at --gpus N is N x args.views views per iteration (weak scaling): the same job here
     world = max(1, args.gpus)
     total = args.views * world
@@ -566,6 +566,41 @@ def scaling_128v(dev, world, rank, vgg, precision, total_views=128, size=1024, l
            "note": "strong-scaling efficiency at N = ms_per_iteration(N=1) / (N * ms_per_iteration(N)); the only collective "
                    "is the in-place all-reduce of the flat texture gradient (allreduce_ms: that collective alone)"}
     del opt
+    return out
+
+
+def nst_2d_loop(dev, vgg, size=512, batch=4, steps=103):
+    """The 2D neural-style-transfer loop of first_approach.py:171-179 (`style_transfer()`, style_transfer.py:38-84) through
+    the drop-in module: every step launched from Python against three eager steps + one CUDA-graph replay per step."""
+    import torch
+    compat = os.path.join(PKG, "compat")
+    if compat not in sys.path:
+        sys.path.insert(0, compat)
+    import style_transfer as st
+    from st3d.vgg import fuse_vgg_features
+    model = fuse_vgg_features(vgg, channels_last=True)
+    g = torch.Generator().manual_seed(5)
+    content = torch.rand(batch, 3, size, size, generator=g).to(dev)
+    style = style_image(size).to(dev).repeat(batch, 1, 1, 1)
+    out = {}
+    prev = os.environ.get("ST3D_NST_GRAPH")
+    try:
+        for label, flag in (("eager", "0"), ("graphed", "1")):
+            os.environ["ST3D_NST_GRAPH"] = flag
+            st.style_transfer(content, content, style, model, steps=5, lr=0.01)        # warm-up of this variant
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            st.style_transfer(content, content, style, model, steps=steps, lr=0.01)
+            torch.cuda.synchronize()
+            out[label + "_ms_per_step"] = (time.perf_counter() - t0) * 1e3 / steps
+    finally:
+        if prev is None:
+            os.environ.pop("ST3D_NST_GRAPH", None)
+        else:
+            os.environ["ST3D_NST_GRAPH"] = prev
+    out["workload"] = (f"style_transfer() of {batch} images x {size}^2, {steps} Adam steps per call (wall clock of the whole call incl. "
+                       "the constant features, the 3 eager steps and the capture)")
+    out["graph_speedup"] = out["eager_ms_per_step"] / out["graphed_ms_per_step"]
     return out
 
 
@@ -890,6 +925,7 @@ def run_st3d(args):
         torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_extras:
         out["c1_first_approach"] = c1_first_approach(dev, run_cpu=not args.no_cpu_baseline)
+        out["nst_2d_loop"] = nst_2d_loop(dev, vgg)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # >= 3 warm-up + >= 10 timed iterations; one view each keeps it to ~30 s of CPU work
         sec, threads, n_timed, n_warm = cpu_iterations(args, args.views, 1, 10, 3)
