@@ -786,29 +786,39 @@ k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__
 // cover the TMA round trip (tensor pipe 38-44 % active).  A CTA PAIR shares the S slab: each CTA holds its own
 // 128 pixel rows of F and HALF of the S rows of every N = 256 MMA, 48 KB per k-block, four stages deep, and the
 // slab leaves L2 once per 256 pixels instead of once per 128.  Item = (image, two consecutive 128-pixel chunks).
-struct BwdPairCfg {
+// RING: the epilogue warps own a cp.async prefetch ring for the fused accumulate / ReLU-mask tail (as BwdCfg at C <= 256),
+// paid for with two of the four TMA stages.  With the tail an item's epilogue -- sixteen 32-channel groups, each a
+// read-modify-write of global memory -- is 3/4 of the item's time (the single 512-column accumulator serialises MMAs and
+// epilogue), so that is where the shared memory earns more; without the tail the four-stage configuration stays.
+template <bool RING>
+struct BwdPairCfgT {
     static constexpr int C = 512;
-    static constexpr int STAGES = 4;
+    static constexpr int STAGES = RING ? 2 : 4;
     static constexpr int F_BYTES = 4 * 4096;         // this CTA's [128 x][32 j] tile of F
     static constexpr int S_HALF_BYTES = 128 * 128;   // [128 rows c][32 j] of S for one N = 256 MMA
     static constexpr int STAGE_BYTES = F_BYTES + 2 * S_HALF_BYTES;  // 48 KB per CTA
     static constexpr int KB = C / 32;
     static constexpr int TR_FLOATS = 4 * 32 * 36;
+    static constexpr int RING_SLOTS = RING ? 3 : 0;
+    static constexpr int RING_BYTES = 4 * RING_SLOTS * 8192;
     static constexpr int NBARS = 2 * STAGES + 2;     // full[], empty[], acc_full, acc_empty
-    static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + TR_FLOATS * 4 + NBARS * 8 + 16;
+    static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + TR_FLOATS * 4 + RING_BYTES + NBARS * 8 + 16;
 };
+using BwdPairCfg = BwdPairCfgT<false>;
 
-template <bool NHWC>
+template <bool NHWC, bool RING>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gram_tc_bwd_pair(const __grid_constant__ CUtensorMap map_f, const __grid_constant__ CUtensorMap map_s,
                    const float* __restrict__ feat, float* __restrict__ grad_feat, int B, int64_t HW, int accumulate) {
-    using Cfg = BwdPairCfg;
+    using Cfg = BwdPairCfgT<RING>;
+    static_assert(!RING || NHWC, "the prefetch ring serves channels_last features only");
     constexpr int C = Cfg::C;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* stages = smem;
     float* tr_scratch = reinterpret_cast<float*>(smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tr_scratch + Cfg::TR_FLOATS);
+    uint8_t* ring = reinterpret_cast<uint8_t*>(tr_scratch + Cfg::TR_FLOATS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + Cfg::RING_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NBARS);
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + Cfg::STAGES),
                    accf = smem_u32(bars + 2 * Cfg::STAGES), acce = smem_u32(bars + 2 * Cfg::STAGES + 1);
@@ -897,6 +907,48 @@ k_gram_tc_bwd_pair(const __grid_constant__ CUtensorMap map_f, const __grid_const
         const uint32_t lead_acce = mapa_shared(acce, 0);
         uint32_t li = 0;
         float r[32];
+        // Fused tail with a ring (RING): batch k = (k / G)-th item of this CTA pair, channel group k % G.  Each warp keeps
+        // RING_SLOTS - 1 batches of its own operands (old gradient, mask values: 8 x 16 B of each per lane) in flight with
+        // cp.async -- also across the MMA phase of the next item, during which the epilogue warps would otherwise idle.
+        constexpr int G = C / 32;
+        constexpr int kSlots = RING ? Cfg::RING_SLOTS : 1;
+        const bool use_ring = RING && accumulate != 0;
+        const uint32_t ring_q = smem_u32(ring) + (uint32_t)q * (kSlots * 8192);
+        const int64_t my_items = cluster_id < items ? (items - cluster_id + nclusters - 1) / nclusters : 0;
+        const uint32_t total_k = (uint32_t)(my_items * G);
+        auto prefetch = [&](uint32_t k) {
+            if (RING && k < total_k) {
+                const int64_t it2 = cluster_id + (int64_t)(k / G) * nclusters;
+                const int64_t b2 = it2 / pairs;
+                const int64_t xw2 = ((it2 % pairs) * 2 + rank) * 128 + q * 32;
+                // this lane's first row (lane >> 3) and 16-byte column (lane & 7); the eight copies are 4 rows apart
+                const int64_t off = (b2 * HW + xw2 + (lane >> 3)) * C + (int)(k % G) * 32 + 4 * (lane & 7);
+                const uint32_t slot = ring_q + (k % kSlots) * 8192 + lane * 16;
+                const float* po = grad_feat + off;
+                const float* pf = feat + off;
+                if (accumulate == 3 && xw2 + 32 <= HW) {  // the common case: both operands, no ragged last chunk
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        cp_async16(slot + i * 512, po + i * 4 * C);
+                        cp_async16(slot + 4096 + i * 512, pf + i * 4 * C);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (xw2 + 4 * i + (lane >> 3) < HW) {
+                            if (accumulate & 1) cp_async16(slot + i * 512, po + i * 4 * C);
+                            if (accumulate & 2) cp_async16(slot + 4096 + i * 512, pf + i * 4 * C);
+                        }
+                    }
+                }
+            }
+            cp_async_commit();  // an empty group keeps the group count in step with k
+        };
+        uint32_t kbatch = 0;
+        if (use_ring) {
+#pragma unroll
+            for (int d = 0; d < kSlots - 1; ++d) prefetch((uint32_t)d);
+        }
         for (int64_t item = cluster_id; item < items; item += nclusters, ++li) {
             const int b = (int)(item / pairs);
             const int64_t xc = ((item % pairs) * 2 + rank) * 128;  // first pixel of this CTA's chunk
@@ -906,6 +958,10 @@ k_gram_tc_bwd_pair(const __grid_constant__ CUtensorMap map_f, const __grid_const
             float* out = grad_feat + (int64_t)b * C * HW + x;  // NCHW
 #pragma unroll 1
             for (int c0 = 0; c0 < C; c0 += 32) {
+                if (use_ring) {  // batch kbatch is the oldest of the kSlots - 1 groups in flight once this one is queued
+                    prefetch(kbatch + kSlots - 1);
+                    cp_async_wait<(RING ? Cfg::RING_SLOTS - 1 : 0)>();
+                }
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
                 if (NHWC) {
                     float* sc = tr_scratch + q * 32 * 36;
@@ -924,20 +980,44 @@ k_gram_tc_bwd_pair(const __grid_constant__ CUtensorMap map_f, const __grid_const
                                 *reinterpret_cast<float4*>(ow + (int64_t)t * C) =
                                     *reinterpret_cast<const float4*>(sc + t * 36 + 4 * (lane & 7));
                         }
+                    } else if (use_ring && accumulate == 3 && xw + 32 <= HW) {
+                        // fused tail, common case: operands from this lane's ring slot, constant offsets throughout
+                        const float4* so = reinterpret_cast<const float4*>(
+                            ring + ((size_t)q * kSlots + kbatch % kSlots) * 8192 + lane * 16);
+                        const float* st = sc + (lane >> 3) * 36 + 4 * (lane & 7);
+                        float* og = ow + (int64_t)(lane >> 3) * C;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float4 v = *reinterpret_cast<const float4*>(st + i * 4 * 36);
+                            const float4 o = so[i * 32], f = so[256 + i * 32];
+                            v.x = f.x <= 0.0f ? 0.0f : v.x + o.x;  // ReLU backward of (incoming gradient + dF)
+                            v.y = f.y <= 0.0f ? 0.0f : v.y + o.y;
+                            v.z = f.z <= 0.0f ? 0.0f : v.z + o.z;
+                            v.w = f.w <= 0.0f ? 0.0f : v.w + o.w;
+                            *reinterpret_cast<float4*>(og + i * 4 * C) = v;
+                        }
                     } else {
-                        // fused elementwise tail: all global loads of the eight row groups are issued before the
-                        // first store, so one memory round trip covers them (a load after a store to the same
-                        // array could not be hoisted over it)
+                        // fused elementwise tail: all loads of the eight row groups are issued before the first store,
+                        // so one memory round trip covers them (a load after a store to the same array could not be
+                        // hoisted over it); with the ring they are this lane's own copies, complete after the wait above
                         float4 oldv[8], fv[8];
                         const float* fw = feat + (ow - grad_feat);
+                        const uint8_t* slot = ring + ((size_t)q * kSlots + kbatch % kSlots) * 8192 + lane * 16;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int t = 4 * i + (lane >> 3);
                             const bool ok = xw + t < HW;
-                            oldv[i] = (ok && (accumulate & 1)) ? *reinterpret_cast<const float4*>(ow + (int64_t)t * C)
-                                                               : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                            fv[i] = (ok && (accumulate & 2)) ? __ldg(reinterpret_cast<const float4*>(fw + (int64_t)t * C))
-                                                             : make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+                            if (use_ring) {
+                                oldv[i] = (ok && (accumulate & 1)) ? *reinterpret_cast<const float4*>(slot + i * 512)
+                                                                   : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                                fv[i] = (ok && (accumulate & 2)) ? *reinterpret_cast<const float4*>(slot + 4096 + i * 512)
+                                                                 : make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+                            } else {
+                                oldv[i] = (ok && (accumulate & 1)) ? *reinterpret_cast<const float4*>(ow + (int64_t)t * C)
+                                                                   : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                                fv[i] = (ok && (accumulate & 2)) ? __ldg(reinterpret_cast<const float4*>(fw + (int64_t)t * C))
+                                                                 : make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+                            }
                         }
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -956,6 +1036,7 @@ k_gram_tc_bwd_pair(const __grid_constant__ CUtensorMap map_f, const __grid_const
                             }
                         }
                     }
+                    ++kbatch;
                     __syncwarp();
                 } else if (x < HW) {
                     const float* fin = feat + (out - grad_feat);
@@ -1142,9 +1223,9 @@ static int launch_fwd(const float* feat, const GramPlan& p, GramEpilogue ep, int
     return ST3D_OK;
 }
 
-template <bool NHWC>
-static int launch_bwd_pair(const float* feat, const GramPlan& p, int accumulate, float* grad_feat, cudaStream_t s) {
-    using Cfg = BwdPairCfg;
+template <bool NHWC, bool RING>
+static int launch_bwd_pair_cfg(const float* feat, const GramPlan& p, int accumulate, float* grad_feat, cudaStream_t s) {
+    using Cfg = BwdPairCfgT<RING>;
     constexpr int C = Cfg::C;
     CUtensorMap map_f, map_s;
     int rc = NHWC ? make_map_nhwc(&map_f, feat, p.B, p.HW, C, 128, CU_TENSOR_MAP_SWIZZLE_128B)
@@ -1153,7 +1234,7 @@ static int launch_bwd_pair(const float* feat, const GramPlan& p, int accumulate,
     rc = make_map(&map_s, p.sym, (uint64_t)p.B * C, (uint64_t)C, 128);
     if (rc != ST3D_OK) return rc;
     static std::atomic<uint64_t> attr_done{0};
-    rc = ensure_smem_attr(k_gram_tc_bwd_pair<NHWC>, (int)Cfg::SMEM, attr_done);
+    rc = ensure_smem_attr(k_gram_tc_bwd_pair<NHWC, RING>, (int)Cfg::SMEM, attr_done);
     if (rc != ST3D_OK) return rc;
     const int64_t chunks = (p.HW + 127) / 128, items = (int64_t)p.B * ((chunks + 1) / 2);
     cudaLaunchConfig_t cfg{};
@@ -1170,9 +1251,18 @@ static int launch_bwd_pair(const float* feat, const GramPlan& p, int accumulate,
     cfg.numAttrs = 1;
     int B = p.B;
     int64_t HW = p.HW;
-    ST3D_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gram_tc_bwd_pair<NHWC>, map_f, map_s, feat, grad_feat, B, HW, accumulate));
+    ST3D_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gram_tc_bwd_pair<NHWC, RING>, map_f, map_s, feat, grad_feat, B, HW, accumulate));
     ST3D_LAUNCH_OK("k_gram_tc_bwd_pair");
     return ST3D_OK;
+}
+
+template <bool NHWC>
+static int launch_bwd_pair(const float* feat, const GramPlan& p, int accumulate, float* grad_feat, cudaStream_t s) {
+    // the prefetch-ring configuration when the fused tail is requested on channels_last features; ST3D_GRAM_BWD512_NO_RING=1
+    // keeps the four-stage one for A/B timing
+    static const bool no_ring = [] { const char* e = getenv("ST3D_GRAM_BWD512_NO_RING"); return e && e[0] == '1'; }();
+    if (NHWC && accumulate != 0 && !no_ring) return launch_bwd_pair_cfg<NHWC, NHWC>(feat, p, accumulate, grad_feat, s);
+    return launch_bwd_pair_cfg<NHWC, false>(feat, p, accumulate, grad_feat, s);
 }
 
 template <int C, bool NHWC, bool RING>
