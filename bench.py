@@ -569,9 +569,11 @@ def scaling_128v(dev, world, rank, vgg, precision, total_views=128, size=1024, l
     return out
 
 
-def nst_2d_loop(dev, vgg, size=512, batch=4, steps=103):
+def nst_2d_loop(dev, vgg, size=512, batch=4, short=53, long=253):
     """The 2D neural-style-transfer loop of first_approach.py:171-179 (`style_transfer()`, style_transfer.py:38-84) through
-    the drop-in module: every step launched from Python against three eager steps + one CUDA-graph replay per step."""
+    the drop-in module: every step launched from Python against three eager steps + one CUDA-graph replay per step.
+    Steady-state cost per step = (time of a `long`-step call - time of a `short`-step call) / (long - short): the constant
+    features, the eager warm-up steps and the capture are paid once per call (the reference's default is 3000 steps)."""
     import torch
     compat = os.path.join(PKG, "compat")
     if compat not in sys.path:
@@ -584,22 +586,28 @@ def nst_2d_loop(dev, vgg, size=512, batch=4, steps=103):
     style = style_image(size).to(dev).repeat(batch, 1, 1, 1)
     out = {}
     prev = os.environ.get("ST3D_NST_GRAPH")
+
+    def call(steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        st.style_transfer(content, content, style, model, steps=steps, lr=0.01)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e3
+
     try:
         for label, flag in (("eager", "0"), ("graphed", "1")):
             os.environ["ST3D_NST_GRAPH"] = flag
-            st.style_transfer(content, content, style, model, steps=5, lr=0.01)        # warm-up of this variant
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            st.style_transfer(content, content, style, model, steps=steps, lr=0.01)
-            torch.cuda.synchronize()
-            out[label + "_ms_per_step"] = (time.perf_counter() - t0) * 1e3 / steps
+            call(8)                                                                     # warm-up of this variant
+            t_short, t_long = call(short), call(long)
+            out[label + "_ms_per_step"] = (t_long - t_short) / (long - short)
+            out[label + "_call_overhead_ms"] = t_short - short * out[label + "_ms_per_step"]
     finally:
         if prev is None:
             os.environ.pop("ST3D_NST_GRAPH", None)
         else:
             os.environ["ST3D_NST_GRAPH"] = prev
-    out["workload"] = (f"style_transfer() of {batch} images x {size}^2, {steps} Adam steps per call (wall clock of the whole call incl. "
-                       "the constant features, the 3 eager steps and the capture)")
+    out["workload"] = (f"style_transfer() of {batch} images x {size}^2 (VGG-19 on cuDNN inside every step); steady-state ms per "
+                       f"Adam step from calls of {short} and {long} steps, wall clock")
     out["graph_speedup"] = out["eager_ms_per_step"] / out["graphed_ms_per_step"]
     return out
 
@@ -925,7 +933,8 @@ def run_st3d(args):
         torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_extras:
         out["c1_first_approach"] = c1_first_approach(dev, run_cpu=not args.no_cpu_baseline)
-        out["nst_2d_loop"] = nst_2d_loop(dev, vgg)
+        # BASELINE configs[0] is first_approach.py at 1 view x 256^2: its 2D style-transfer stage, and a 4 x 512^2 batch
+        out["nst_2d_loop"] = {"1x256": nst_2d_loop(dev, vgg, size=256, batch=1), "4x512": nst_2d_loop(dev, vgg, size=512, batch=4)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # >= 3 warm-up + >= 10 timed iterations; one view each keeps it to ~30 s of CPU work
         sec, threads, n_timed, n_warm = cpu_iterations(args, args.views, 1, 10, 3)
