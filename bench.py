@@ -569,45 +569,47 @@ def scaling_128v(dev, world, rank, vgg, precision, total_views=128, size=1024, l
     return out
 
 
-def nst_2d_loop(dev, vgg, size=512, batch=4, short=53, long=253):
-    """The 2D neural-style-transfer loop of first_approach.py:171-179 (`style_transfer()`, style_transfer.py:38-84) through
-    the drop-in module: every step launched from Python against three eager steps + one CUDA-graph replay per step.
-    Steady-state cost per step = (time of a `long`-step call - time of a `short`-step call) / (long - short): the constant
-    features, the eager warm-up steps and the capture are paid once per call (the reference's default is 3000 steps)."""
+def nst_2d_loop(dev, vgg, size=512, batch=4, steps=50):
+    """One step of the 2D neural-style-transfer loop (`style_transfer()`, style_transfer.py:59-83; first stage of
+    first_approach.py:171-179) exactly as the drop-in compat/style_transfer.py runs it -- fused loss walk, Adam -- launched
+    from Python every step against replayed from one CUDA graph (st3d.optimize.CapturedIteration); CUDA events."""
     import torch
-    compat = os.path.join(PKG, "compat")
-    if compat not in sys.path:
-        sys.path.insert(0, compat)
-    import style_transfer as st
+    from st3d import losses
+    from st3d.optimize import CapturedIteration
     from st3d.vgg import fuse_vgg_features
     model = fuse_vgg_features(vgg, channels_last=True)
     g = torch.Generator().manual_seed(5)
     content = torch.rand(batch, 3, size, size, generator=g).to(dev)
     style = style_image(size).to(dev).repeat(batch, 1, 1, 1)
+    with torch.no_grad():
+        content_feat = losses.get_features(content, model, {"21": losses.CONTENT_LAYER})[losses.CONTENT_LAYER]
+    grams = losses.style_targets(style, model)
     out = {}
-    prev = os.environ.get("ST3D_NST_GRAPH")
+    for label in ("eager", "graphed"):
+        images = content.clone().requires_grad_(True)
+        optimizer = torch.optim.Adam([images], lr=0.01, capturable=True, fused=True)
 
-    def call(steps):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        st.style_transfer(content, content, style, model, steps=steps, lr=0.01)
-        torch.cuda.synchronize()
-        return (time.perf_counter() - t0) * 1e3
+        def iteration():
+            loss = losses.perceptual_loss_of_images(images, model, content_feat, grams, 1e6, 1.0)
+            optimizer.zero_grad()
+            loss.backward()
+            optimizer.step()
 
-    try:
-        for label, flag in (("eager", "0"), ("graphed", "1")):
-            os.environ["ST3D_NST_GRAPH"] = flag
-            call(8)                                                                     # warm-up of this variant
-            t_short, t_long = call(short), call(long)
-            out[label + "_ms_per_step"] = (t_long - t_short) / (long - short)
-            out[label + "_call_overhead_ms"] = t_short - short * out[label + "_ms_per_step"]
-    finally:
-        if prev is None:
-            os.environ.pop("ST3D_NST_GRAPH", None)
+        if label == "graphed":
+            step = CapturedIteration(iteration, dev, warmup=3).replay
         else:
-            os.environ["ST3D_NST_GRAPH"] = prev
-    out["workload"] = (f"style_transfer() of {batch} images x {size}^2 (VGG-19 on cuDNN inside every step); steady-state ms per "
-                       f"Adam step from calls of {short} and {long} steps, wall clock")
+            for _ in range(3):
+                iteration()
+            step = iteration
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        out[label + "_ms_per_step"] = e0.elapsed_time(e1) / steps
+    out["workload"] = f"2D NST step on {batch} image(s) x {size}^2 (VGG-19 forward + backward on cuDNN inside the step), {steps} steps"
     out["graph_speedup"] = out["eager_ms_per_step"] / out["graphed_ms_per_step"]
     return out
 
