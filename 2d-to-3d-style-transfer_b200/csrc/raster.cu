@@ -637,7 +637,8 @@ __device__ __forceinline__ unsigned zlow_key(const FaceVerts& v, bool zpos) {
     return zpos ? __float_as_uint(fminf(v.z0, fminf(v.z1, v.z2)) * 0.999996f) : 0u;
 }
 
-constexpr int kUnitSide = 64;   // work units of the sweep pass cover at most 64 x 64 pixels
+constexpr int kUnitW = 64;      // work units of the sweep pass cover at most 64 x 32 pixels:
+constexpr int kUnitH = 32;      // one lane of the sweeping warp per pixel row
 constexpr int kSmallBox = 16;   // faces whose pixel box holds at most this many centres never reach the queue
 
 // A face crossing the near plane (1 or 2 vertices with z < z_clip): its one or two sub-triangles are queued as
@@ -653,8 +654,8 @@ static __device__ __noinline__ void setup_clipped_face(FaceVerts v, float z_clip
     for (int t = 0; t < nt; ++t) {
         const ClipUnit u = clipped_unit(v, z_clip, t, H, W, est, cull_backfaces, ndc_x, ndc_y);
         if (!u.box.valid) continue;
-        ux[t] = (u.box.x1 - u.box.x0 + kUnitSide) / kUnitSide;
-        nu[t] = ux[t] * ((u.box.y1 - u.box.y0 + kUnitSide) / kUnitSide);
+        ux[t] = (u.box.x1 - u.box.x0 + kUnitW) / kUnitW;
+        nu[t] = ux[t] * ((u.box.y1 - u.box.y0 + kUnitH) / kUnitH);
         X0 = min(X0, u.box.x0); X1 = max(X1, u.box.x1); Y0 = min(Y0, u.box.y0); Y1 = max(Y1, u.box.y1);
     }
     const int total = nu[0] + nu[1];
@@ -734,12 +735,12 @@ k_face_zbuf(const float* __restrict__ face_verts, const int64_t* __restrict__ fi
     const int bw = box.x1 - box.x0 + 1, bh = box.y1 - box.y0 + 1;
     const bool small = box.valid && bw * bh <= kSmallBox;
     {
-        // queue the face as ceil(bw/64) x ceil(bh/64) work units of at most 64 x 64 pixels for k_sweep_units;
+        // queue the face as ceil(bw/64) x ceil(bh/32) work units of at most 64 x 32 pixels for k_sweep_units;
         // one atomicAdd per WARP and side (prefix sums over the lanes' unit counts), not one per face.  Faces of
         // positive area fill the queue from slot 0 upwards (counter hdr[0]), the others from the last slot downwards
         // (counter hdr[6]): the sweep then meets the front-facing surface first (see k_sweep_units).
-        const int ux = (box.valid && !small) ? (bw + kUnitSide - 1) / kUnitSide : 0;
-        const int nu = (box.valid && !small) ? ux * ((bh + kUnitSide - 1) / kUnitSide) : 0;
+        const int ux = (box.valid && !small) ? (bw + kUnitW - 1) / kUnitW : 0;
+        const int nu = (box.valid && !small) ? ux * ((bh + kUnitH - 1) / kUnitH) : 0;
         if (__any_sync(0xffffffffu, nu > 0)) {  // (on meshes denser than the pixel grid most warps queue nothing)
             const bool front = box.area > 0.0f;
             int incl_f = front ? nu : 0, incl_b = front ? 0 : nu;
@@ -820,8 +821,8 @@ k_face_zbuf(const float* __restrict__ face_verts, const int64_t* __restrict__ fi
 __global__ void __launch_bounds__(256)
 k_sweep_units(const FaceRec* __restrict__ rec, const int* __restrict__ unit_face, const int* __restrict__ unit_block,
               int* __restrict__ hdr, int64_t unit_capacity, int H, int W, float4 est, int cull_backfaces,
-              float z_clip, int persp, int early_z, const float* __restrict__ ndc_x, const float* __restrict__ ndc_y,
-              unsigned long long* __restrict__ zkey) {
+              float z_clip, int persp, int early_z, int spans, const float* __restrict__ ndc_x,
+              const float* __restrict__ ndc_y, unsigned long long* __restrict__ zkey) {
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     // The queue is ordered by k_face_zbuf: faces of positive area (front-facing in the rasterizer's convention) from
@@ -847,8 +848,8 @@ k_sweep_units(const FaceRec* __restrict__ rec, const int* __restrict__ unit_face
             area = cu.box.area;
             fx0 = cu.box.x0; fx1 = cu.box.x1; fy0 = cu.box.y0; fy1 = cu.box.y1;
         }
-        const int x0 = fx0 + ux * kUnitSide, x1 = min(fx1, x0 + kUnitSide - 1);
-        const int y0 = fy0 + uy * kUnitSide, y1 = min(fy1, y0 + kUnitSide - 1);
+        const int x0 = fx0 + ux * kUnitW, x1 = min(fx1, x0 + kUnitW - 1);
+        const int y0 = fy0 + uy * kUnitH, y1 = min(fy1, y0 + kUnitH - 1);
         const bool zpos = v.z0 > 0.0f && v.z1 > 0.0f && v.z2 > 0.0f;
         const unsigned zlow = early_z ? zlow_key(v, zpos) : 0u;
         const float denom = fadd(area, kEps), rden = __frcp_rn(denom);
@@ -856,10 +857,73 @@ k_sweep_units(const FaceRec* __restrict__ rec, const int* __restrict__ unit_face
         const float e0y = fsub(v.y2, v.y1), e0x = fsub(v.x2, v.x1), e1y = fsub(v.y0, v.y2), e1x = fsub(v.x0, v.x2);
         const float e2y = fsub(v.y1, v.y0), e2x = fsub(v.x1, v.x0);
         unsigned long long* zview = zkey + (int64_t)n * H * W;
-        for (int by = y0; by <= y1; by += 4) {
-            for (int bx = x0; bx <= x1; bx += 8) {
-                const int qx = bx + (lane & 7), qy = by + (lane >> 3);
-                if (qx > x1 || qy > y1) continue;
+        if (!spans) {  // (measurement switch ST3D_SWEEP_SPANS=0) every pixel of the unit's box, in 8 x 4 steps
+            for (int by = y0; by <= y1; by += 4) {
+                for (int bx = x0; bx <= x1; bx += 8) {
+                    const int qx = bx + (lane & 7), qy = by + (lane >> 3);
+                    if (qx > x1 || qy > y1) continue;
+                    zbuf_test_pixel(__ldg(ndc_x + qx), __ldg(ndc_y + qy), v, denom, rden, den_ok, zpos, zlow, persp != 0, e0x,
+                                    e0y, e1x, e1y, e2x, e2y, (unsigned)f, zview + (int64_t)qy * W + qx);
+                }
+            }
+            continue;
+        }
+        // Span compaction.  Lane r owns pixel row y0 + r and solves the three edge inequalities for that row: every w_i
+        // is linear in the pixel's x, so "all three share the sign of the area" is an interval of x, mapped to pixel
+        // columns with the estimate j = a x + b and WIDENED by a twentieth of a pixel on both sides (the fp32 error of
+        // this arithmetic is below a thousandth of a pixel).  The spans only select CANDIDATES -- every candidate still
+        // takes the exact test of zbuf_test_pixel, so a conservative span cannot change the result, while a triangle
+        // fills half of its box and a thin one far less.  The warp then walks the concatenated spans 32 candidates at a
+        // time: all lanes busy, nearly all of them on pixels that are inside.
+        int s_lo = x0, s_len = 0;
+        {
+            const int qy = y0 + lane;
+            if (qy <= y1) {
+                int lo = x0, hi = x1;
+                if (zpos) {
+                    const float py = __ldg(ndc_y + qy);
+                    const float sgn = area > 0.0f ? 1.0f : -1.0f;
+                    // w_i(px) = (px - xa) dy - (py - ya) dx; s w_i > 0  <=>  px > / < xa + (py - ya) dx / dy by the sign of s dy
+                    float Lb = -FLT_MAX, Ub = FLT_MAX;
+                    const float xa[3] = {v.x1, v.x2, v.x0}, ya[3] = {v.y1, v.y2, v.y0};
+                    const float dxs[3] = {e0x, e1x, e2x}, dys[3] = {e0y, e1y, e2y};
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const float sd = sgn * dys[i];
+                        if (sd != 0.0f) {
+                            const float cross = xa[i] + __fdividef((py - ya[i]) * dxs[i], dys[i]);
+                            if (sd > 0.0f) Lb = fmaxf(Lb, cross); else Ub = fminf(Ub, cross);
+                        }
+                    }
+                    // NDC x -> image column: column i has NDC-ordered index j = W - 1 - i = est.x * x + est.y
+                    const float i_first = (float)(W - 1) - fmaf(Ub, est.x, est.y);   // px < Ub  <=>  i > i_first
+                    const float i_last = (float)(W - 1) - fmaf(Lb, est.x, est.y);    // px > Lb  <=>  i < i_last
+                    lo = max(lo, (int)fminf(fmaxf(ceilf(i_first - 0.05f), (float)x0), (float)x1 + 1.0f));
+                    hi = min(hi, (int)fmaxf(fminf(floorf(i_last + 0.05f), (float)x1), (float)x0 - 1.0f));
+                }
+                s_lo = lo;
+                s_len = max(hi - lo + 1, 0);
+            }
+        }
+        int incl = s_len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int ncand = __shfl_sync(0xffffffffu, incl, 31);
+        const int excl = incl - s_len;
+        for (int base = 0; base < ncand; base += 32) {
+            const int idx = base + lane;
+            int r = 0;  // the row that owns candidate idx: the first lane whose inclusive prefix exceeds idx
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int probe = __shfl_sync(0xffffffffu, incl, r + step - 1);
+                if (probe <= idx) r += step;
+            }
+            const int r_excl = __shfl_sync(0xffffffffu, excl, r), r_lo = __shfl_sync(0xffffffffu, s_lo, r);
+            if (idx < ncand) {
+                const int qx = r_lo + (idx - r_excl), qy = y0 + r;
                 zbuf_test_pixel(__ldg(ndc_x + qx), __ldg(ndc_y + qy), v, denom, rden, den_ok, zpos, zlow, persp != 0, e0x,
                                 e0y, e1x, e1y, e2x, e2y, (unsigned)f, zview + (int64_t)qy * W + qx);
             }
@@ -929,6 +993,8 @@ static int run_hard(const RasterWs& ws, const HardSrc& h, int N, int H, int W, i
         // with it in the sweep, 277.6 in both passes)
         static const int ez = [] { const char* e = getenv("ST3D_EARLY_Z"); return e ? atoi(e) : 0; }();
         const int ez_sweep = ez & 1, ez_small = (ez >> 1) & 1;
+        // ST3D_SWEEP_SPANS=0: sweep every pixel of a unit's box instead of the per-row spans of its triangle (A/B)
+        static const int sweep_spans = [] { const char* e = getenv("ST3D_SWEEP_SPANS"); return e ? atoi(e) : 1; }();
         if (h.verts)
             k_face_zbuf<1><<<grid, 128, 0, s>>>(nullptr, nullptr, nullptr, ws.verts_ndc, h.faces, h.V, h.F_per_mesh, H, W,
                                                 est, h.cull_backfaces, h.z_clip, persp, ez_small, ws.ndc_x, ws.ndc_y, ws.rec,
@@ -940,7 +1006,8 @@ static int run_hard(const RasterWs& ws, const HardSrc& h, int N, int H, int W, i
                                                 ws.hdr);
         ST3D_LAUNCH_OK("k_face_zbuf");
         k_sweep_units<<<148 * 8, 256, 0, s>>>(ws.rec, ws.list, ws.list_tile, ws.hdr, ws.capacity, H, W, est,
-                                              h.cull_backfaces, h.z_clip, persp, ez_sweep, ws.ndc_x, ws.ndc_y, ws.zkey);
+                                              h.cull_backfaces, h.z_clip, persp, ez_sweep, sweep_spans, ws.ndc_x, ws.ndc_y,
+                                              ws.zkey);
         ST3D_LAUNCH_OK("k_sweep_units");
     }
     k_resolve<MODE><<<dim3(cdiv(W, 256), H, N), 256, 0, s>>>(ws.rec, ws.zkey, H, W, persp, h.z_clip, ws.ndc_x, ws.ndc_y,
