@@ -26,9 +26,11 @@ from .cameras import FoVPerspectiveCameras, look_at_view_transform  # noqa: F401
 # ------------------------------------------------------------------------------------------------
 def _stack(x, name):
     if isinstance(x, (list, tuple)):
-        if len(x) != 1:
-            raise NotImplementedError(f"{name}: one mesh per batch (views are batched, not meshes)")
-        return x[0][None]
+        if len(x) == 1:
+            return x[0][None]           # a view: a leaf passed in a one-element list stays reachable
+        if any(t.shape != x[0].shape for t in x):
+            raise NotImplementedError(f"{name}: the meshes of a batch must share their texture shapes")
+        return torch.stack(list(x), dim=0)
     return x
 
 
@@ -66,6 +68,12 @@ class TexturesUV:
         """(F,3,2) per-face UVs of mesh 0."""
         return self._verts_uvs[0][self._faces_uvs[0].long()]
 
+    def __len__(self):
+        return self._maps.shape[0]
+
+    def __getitem__(self, index):
+        return TexturesUV(self._maps[index:index + 1], self._faces_uvs[index:index + 1], self._verts_uvs[index:index + 1])
+
     def clone(self):
         return TexturesUV(self._maps.clone(), self._faces_uvs.clone(), self._verts_uvs.clone())
 
@@ -90,6 +98,12 @@ class TexturesVertex:
 
     def verts_features_packed(self):
         return self._feats[0]
+
+    def __len__(self):
+        return self._feats.shape[0]
+
+    def __getitem__(self, index):
+        return TexturesVertex(self._feats[index:index + 1])
 
     def clone(self):
         return TexturesVertex(self._feats.clone())
@@ -203,6 +217,18 @@ def _one_mesh(meshes: Meshes):
     return verts, faces
 
 
+def _per_mesh(meshes: Meshes, cameras):
+    """A batch of M > 1 meshes renders mesh i with camera i (or the one camera given), as upstream pairs them; this layer
+    batches VIEWS inside one launch sequence, so meshes are walked one launch sequence each."""
+    if isinstance(cameras, (list, tuple)):
+        cameras = FoVPerspectiveCameras.join(cameras)
+    M = len(meshes)
+    if cameras is not None and len(cameras) not in (1, M):
+        raise ValueError(f"{M} meshes need {M} cameras (or one), got {len(cameras)}")
+    for i in range(M):
+        yield meshes[i], (cameras if cameras is None or len(cameras) == 1 else cameras[i])
+
+
 def _camera_params(cameras):
     if cameras is None:
         raise ValueError("cameras must be given to the rasterizer / renderer, at construction or per call")
@@ -228,6 +254,14 @@ class MeshRasterizer(torch.nn.Module):
         return kwargs.get("raster_settings", self.raster_settings)
 
     def forward(self, meshes_world, **kwargs) -> Fragments:
+        if isinstance(meshes_world, Meshes) and len(meshes_world) > 1:
+            parts, offset, out = [], 0, []
+            for mesh, cam in _per_mesh(meshes_world, kwargs.get("cameras", self.cameras)):
+                fr = self.forward(mesh, **dict(kwargs, cameras=cam))
+                # pix_to_face indexes the PACKED faces of the whole batch
+                out.append(fr._replace(pix_to_face=torch.where(fr.pix_to_face >= 0, fr.pix_to_face + offset, fr.pix_to_face)))
+                offset += mesh.faces_packed().shape[0]
+            return Fragments(*(torch.cat([getattr(f, name) for f in out], dim=0) for name in Fragments._fields))
         cams, (fov, aspect, znear, zfar) = _camera_params(kwargs.get("cameras", self.cameras))
         rs = self._settings(kwargs)
         verts, faces = _one_mesh(meshes_world)
@@ -342,6 +376,10 @@ class MeshRenderer(torch.nn.Module):
                 and rs.clip_barycentric_coords in (None, False))
 
     def forward(self, meshes_world, **kwargs):
+        if isinstance(meshes_world, Meshes) and len(meshes_world) > 1:
+            cams = kwargs.get("cameras", self.rasterizer.cameras)
+            return torch.cat([self.forward(mesh, **dict(kwargs, cameras=cam)) for mesh, cam in _per_mesh(meshes_world, cams)],
+                             dim=0)
         if not self._can_fuse(meshes_world, kwargs):       # K > 1, blur, lit geometry gradients: Fragments + general shader
             fragments = self.rasterizer(meshes_world, **kwargs)
             return self.shader(fragments, meshes_world, **kwargs)
@@ -352,7 +390,7 @@ class MeshRenderer(torch.nn.Module):
     def render_planar(self, meshes_world, **kwargs):
         """Batched fast path used by this repo's `utils.render_meshes`: ((N,3,H,W) images, (N,1,H,W) masks)
         straight from the kernel epilogue -- no permute / compare / stack passes."""
-        if not self._can_fuse(meshes_world, kwargs):
+        if (isinstance(meshes_world, Meshes) and len(meshes_world) > 1) or not self._can_fuse(meshes_world, kwargs):
             rgba = self.forward(meshes_world, **kwargs)
             return rgba[..., :3].permute(0, 3, 1, 2).contiguous(), (rgba[..., 3:4] > 0).to(rgba.dtype).permute(0, 3, 1, 2)
         verts, faces, R, T, size, tex_kw, common = self._fused_args(meshes_world, kwargs)

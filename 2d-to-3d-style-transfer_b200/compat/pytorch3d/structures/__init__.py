@@ -32,6 +32,16 @@ class Meshes:
     def __len__(self):
         return len(self._verts_list)
 
+    def __getitem__(self, index):
+        """Mesh `index` (an int) as a one-mesh Meshes that shares the vertex / face / texture tensors."""
+        if not isinstance(index, int):
+            raise IndexError("Meshes supports integer indexing")
+        if not -len(self) <= index < len(self):
+            raise IndexError(f"mesh index {index} out of range for {len(self)} meshes")
+        index %= len(self)
+        tex = self.textures[index] if self.textures is not None else None
+        return Meshes([self._verts_list[index]], [self._faces_list[index]], tex)
+
     def verts_list(self):
         return self._verts_list
 

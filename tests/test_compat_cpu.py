@@ -153,3 +153,25 @@ def test_renderer_fails_loudly_on_cpu():
     with pytest.raises(RuntimeError):
         renderer(meshes_world=mesh, cameras=cams)
     assert PointLights().kind == "point"
+
+
+def test_meshes_and_textures_index_into_a_batch():
+    """Meshes[i] / TexturesUV[i] / TexturesVertex[i] of a batch share the tensors of entry i; a list of maps stacks."""
+    from pytorch3d.renderer import TexturesUV, TexturesVertex
+    from pytorch3d.structures import Meshes
+    v = [torch.rand(4, 3), torch.rand(5, 3)]
+    f = [torch.tensor([[0, 1, 2]]), torch.tensor([[0, 1, 2], [2, 3, 4]])]
+    feats = TexturesVertex(verts_features=torch.rand(2, 5, 3))
+    m = Meshes(verts=v, faces=f, textures=feats)
+    assert len(m) == 2 and len(m[1]) == 1 and m[1].verts_packed() is v[1] and m[-1].faces_packed() is f[1]
+    assert torch.equal(m[1].textures.verts_features_packed(), feats.verts_features_padded()[1])
+    assert torch.equal(m.faces_packed(), torch.cat([f[0], f[1] + 4]))
+    with pytest.raises(IndexError):
+        m[2]
+    maps = [torch.rand(4, 4, 3), torch.rand(4, 4, 3)]
+    t = TexturesUV(maps=maps, faces_uvs=torch.zeros(2, 1, 3, dtype=torch.int64), verts_uvs=torch.rand(2, 3, 2))
+    assert len(t) == 2 and torch.equal(t[1].maps_padded()[0], maps[1])
+    one = torch.rand(4, 4, 3, requires_grad=True)          # a one-element list stays a view of the leaf
+    single = TexturesUV(maps=[one], faces_uvs=torch.zeros(1, 1, 3, dtype=torch.int64), verts_uvs=torch.rand(1, 3, 2))
+    single.maps_padded().sum().backward()
+    assert torch.equal(one.grad, torch.ones_like(one))

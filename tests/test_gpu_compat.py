@@ -596,3 +596,34 @@ def test_captured_style_step_equals_the_eager_step(cow):
     Rd.copy_(R2.to(dev)); Td.copy_(T2.to(dev))
     a, b = cap.step_captured().item(), eager.step(Rd, Td, style).item()
     assert abs(a - b) <= 1e-3 * abs(b), (a, b)
+
+
+def test_batch_of_meshes_renders_mesh_i_with_camera_i(cow):
+    """Meshes with M > 1 entries (upstream pairs mesh i with camera i): the renderer walks the meshes, one launch sequence
+    each; RGBA equals the per-mesh renders, and the rasterizer's pix_to_face indexes the PACKED faces of the batch."""
+    from pytorch3d.renderer import (AmbientLights, FoVPerspectiveCameras, MeshRasterizer, MeshRenderer,
+                                    RasterizationSettings, SoftPhongShader, TexturesUV)
+    from pytorch3d.structures import Meshes
+    dev = torch.device("cuda:0")
+    R, T = ro.random_cameras(2, generator=torch.Generator().manual_seed(101))
+    cams = FoVPerspectiveCameras(R=R.to(dev), T=T.to(dev), device=dev)
+    gen = torch.Generator().manual_seed(102)
+    maps = [torch.rand(32, 32, 3, generator=gen).to(dev) for _ in range(2)]
+    uvs = cow["verts_uvs"].to(dev)
+    # the second mesh: the cow scaled down, its own texture map
+    fuv = cow["faces_uvs"].to(dev)
+    tex = TexturesUV(maps=torch.stack(maps), faces_uvs=torch.stack([fuv, fuv]), verts_uvs=torch.stack([uvs, uvs]))
+    both = Meshes(verts=[cow["verts"].to(dev), 0.8 * cow["verts"].to(dev)], faces=[cow["faces"].to(dev), cow["faces"].to(dev)],
+                  textures=tex)
+    assert len(both) == 2 and len(both[1]) == 1
+    renderer = MeshRenderer(MeshRasterizer(cameras=cams, raster_settings=RasterizationSettings(image_size=S)),
+                            SoftPhongShader(device=dev, cameras=cams, lights=AmbientLights(device=dev)))
+    rgba = renderer(both)
+    assert rgba.shape == (2, S, S, 4)
+    for i in range(2):
+        one = renderer(both[i], cameras=cams[i])
+        assert torch.equal(rgba[i:i + 1], one)
+    frags = renderer.rasterizer(both)
+    Fc = cow["faces"].shape[0]
+    p0, p1 = frags.pix_to_face[0], frags.pix_to_face[1]
+    assert p0.max().item() < Fc and p1[p1 >= 0].min().item() >= Fc and p1.max().item() < 2 * Fc
