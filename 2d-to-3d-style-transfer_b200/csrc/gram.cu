@@ -332,10 +332,17 @@ extern "C" int st3d_gram_backward(const float* feat, const float* dgram, int B, 
         return ST3D_ERR_WORKSPACE;
     }
     cudaStream_t s = (cudaStream_t)stream;
+    const bool nhwc = layout == ST3D_FEAT_NHWC;
+    const int tail = accumulate & (ST3D_GRAM_ACCUMULATE | ST3D_GRAM_RELU_MASK);
+    if ((accumulate & ST3D_GRAM_DGRAM_SYMMETRIC) && precision == ST3D_GRAM_TF32 && (((uintptr_t)dgram) & 15) == 0) {
+        // dG = dG^T (it is 2 scale (G - Gs) of two Gram matrices): S = 2 s dG, the factor applied to the accumulator --
+        // no symmetrise pass, the GEMM reads dG where st3d_gram_mse_forward left it
+        return gram_tc_backward(feat, p, nhwc, tc::GramS{dgram, 2.0f * grad_scale, grad_scale_dev}, tail, grad_feat, s);
+    }
     k_gram_symmetrize<<<dim3(cdiv(C, 32), cdiv(C, 32), B), 256, 0, s>>>(dgram, B, C, grad_scale, grad_scale_dev, p.sym);
     ST3D_LAUNCH_OK("k_gram_symmetrize");
-    const bool nhwc = layout == ST3D_FEAT_NHWC;
-    if (precision == ST3D_GRAM_TF32) return gram_tc_backward(feat, p, nhwc, accumulate, grad_feat, s);
+    accumulate = tail;
+    if (precision == ST3D_GRAM_TF32) return gram_tc_backward(feat, p, nhwc, tc::GramS{p.sym, 1.0f, nullptr}, accumulate, grad_feat, s);
     k_gram_bwd_simt<<<dim3(cdiv(HW, kST), cdiv(C, kST), B), 256, 0, s>>>(feat, p.sym, C, HW, nhwc ? 1 : HW, nhwc ? C : 1,
                                                                          accumulate, grad_feat);
     ST3D_LAUNCH_OK("k_gram_bwd_simt");

@@ -525,7 +525,8 @@ struct BwdCfg {
 template <int C, bool NHWC, bool RING>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__ CUtensorMap map_s,
-              const float* __restrict__ feat, float* __restrict__ grad_feat, int B, int64_t HW, int accumulate) {
+              const float* __restrict__ feat, float* __restrict__ grad_feat, int B, int64_t HW, int accumulate,
+              float out_scale, const float* __restrict__ out_scale_dev) {
     using Cfg = BwdCfg<C, RING>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -621,6 +622,7 @@ k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__
         const int q = warp & 3;
         uint32_t li = 0;
         float r[32];
+        const float osc = out_scale * (out_scale_dev ? __ldg(out_scale_dev) : 1.0f);
         // Fused tail, C <= 128: batch k = (k / G)-th item of this CTA, channel group k % G.  The warp keeps
         // RING_SLOTS - 1 batches of its own operands (old gradient, mask values: 8 x 16 B of each per lane) in
         // flight with cp.async, so the HBM round trip of the read-modify-write is paid once, not per batch.
@@ -679,6 +681,8 @@ k_gram_tc_bwd(const __grid_constant__ CUtensorMap map_f, const __grid_constant__
                     cp_async_wait<(Cfg::RING_SLOTS > 0 ? Cfg::RING_SLOTS - 1 : 0)>();
                 }
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * C + c0), r);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] *= osc;  // 1 unless S is the raw, symmetric dG (ST3D_GRAM_DGRAM_SYMMETRIC)
                 if (NHWC) {
                     // r[j] = D[pixel row = lane][channel c0 + j].  Transpose through padded shared memory so that
                     // one warp store covers 4 pixel rows x 128 contiguous bytes instead of 32 rows x 16 bytes.
@@ -809,7 +813,8 @@ using BwdPairCfg = BwdPairCfgT<false>;
 template <bool NHWC, bool RING>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gram_tc_bwd_pair(const __grid_constant__ CUtensorMap map_f, const __grid_constant__ CUtensorMap map_s,
-                   const float* __restrict__ feat, float* __restrict__ grad_feat, int B, int64_t HW, int accumulate) {
+                   const float* __restrict__ feat, float* __restrict__ grad_feat, int B, int64_t HW, int accumulate,
+                   float out_scale, const float* __restrict__ out_scale_dev) {
     using Cfg = BwdPairCfgT<RING>;
     static_assert(!RING || NHWC, "the prefetch ring serves channels_last features only");
     constexpr int C = Cfg::C;
@@ -907,6 +912,7 @@ k_gram_tc_bwd_pair(const __grid_constant__ CUtensorMap map_f, const __grid_const
         const uint32_t lead_acce = mapa_shared(acce, 0);
         uint32_t li = 0;
         float r[32];
+        const float osc = out_scale * (out_scale_dev ? __ldg(out_scale_dev) : 1.0f);
         // Fused tail with a ring (RING): batch k = (k / G)-th item of this CTA pair, channel group k % G.  Each warp keeps
         // RING_SLOTS - 1 batches of its own operands (old gradient, mask values: 8 x 16 B of each per lane) in flight with
         // cp.async -- also across the MMA phase of the next item, during which the epilogue warps would otherwise idle.
@@ -963,6 +969,8 @@ k_gram_tc_bwd_pair(const __grid_constant__ CUtensorMap map_f, const __grid_const
                     cp_async_wait<(RING ? Cfg::RING_SLOTS - 1 : 0)>();
                 }
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] *= osc;  // 1 unless S is the raw, symmetric dG (ST3D_GRAM_DGRAM_SYMMETRIC)
                 if (NHWC) {
                     float* sc = tr_scratch + q * 32 * 36;
 #pragma unroll
@@ -1223,15 +1231,23 @@ static int launch_fwd(const float* feat, const GramPlan& p, GramEpilogue ep, int
     return ST3D_OK;
 }
 
+// The B operand of the backward GEMM: S = s (dG + dG^T) from k_gram_symmetrize (scale 1), or -- when the caller vouches
+// that dG is symmetric, ST3D_GRAM_DGRAM_SYMMETRIC -- dG itself, with 2 s [* *scale_dev] applied to the accumulator
+struct GramS {
+    const float* s;
+    float scale;
+    const float* scale_dev;
+};
+
 template <bool NHWC, bool RING>
-static int launch_bwd_pair_cfg(const float* feat, const GramPlan& p, int accumulate, float* grad_feat, cudaStream_t s) {
+static int launch_bwd_pair_cfg(const float* feat, const GramPlan& p, GramS S, int accumulate, float* grad_feat, cudaStream_t s) {
     using Cfg = BwdPairCfgT<RING>;
     constexpr int C = Cfg::C;
     CUtensorMap map_f, map_s;
     int rc = NHWC ? make_map_nhwc(&map_f, feat, p.B, p.HW, C, 128, CU_TENSOR_MAP_SWIZZLE_128B)
                   : make_map(&map_f, feat, (uint64_t)p.B * C, (uint64_t)p.HW, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc != ST3D_OK) return rc;
-    rc = make_map(&map_s, p.sym, (uint64_t)p.B * C, (uint64_t)C, 128);
+    rc = make_map(&map_s, S.s, (uint64_t)p.B * C, (uint64_t)C, 128);
     if (rc != ST3D_OK) return rc;
     static std::atomic<uint64_t> attr_done{0};
     rc = ensure_smem_attr(k_gram_tc_bwd_pair<NHWC, RING>, (int)Cfg::SMEM, attr_done);
@@ -1251,30 +1267,33 @@ static int launch_bwd_pair_cfg(const float* feat, const GramPlan& p, int accumul
     cfg.numAttrs = 1;
     int B = p.B;
     int64_t HW = p.HW;
-    ST3D_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gram_tc_bwd_pair<NHWC, RING>, map_f, map_s, feat, grad_feat, B, HW, accumulate));
+    float out_scale = S.scale;
+    const float* out_scale_dev = S.scale_dev;
+    ST3D_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gram_tc_bwd_pair<NHWC, RING>, map_f, map_s, feat, grad_feat, B, HW, accumulate,
+                                    out_scale, out_scale_dev));
     ST3D_LAUNCH_OK("k_gram_tc_bwd_pair");
     return ST3D_OK;
 }
 
 template <bool NHWC>
-static int launch_bwd_pair(const float* feat, const GramPlan& p, int accumulate, float* grad_feat, cudaStream_t s) {
+static int launch_bwd_pair(const float* feat, const GramPlan& p, GramS S, int accumulate, float* grad_feat, cudaStream_t s) {
     // the prefetch-ring configuration when the fused tail is requested on channels_last features (0.090 -> 0.078 ms at
     // 8 x 512 x 4096); ST3D_GRAM_BWD512_NO_RING=1 keeps the four-stage one for A/B timing
     static const bool no_ring = [] { const char* e = getenv("ST3D_GRAM_BWD512_NO_RING"); return e && e[0] == '1'; }();
     // (only for the full tail, accumulate + mask, which has the constant-offset fast path: with the mask alone -- conv5_1,
     // nothing arrives from deeper layers -- the ring configuration measured 0.055 ms against 0.040 ms)
-    if (NHWC && accumulate == 3 && !no_ring) return launch_bwd_pair_cfg<NHWC, NHWC>(feat, p, accumulate, grad_feat, s);
-    return launch_bwd_pair_cfg<NHWC, false>(feat, p, accumulate, grad_feat, s);
+    if (NHWC && accumulate == 3 && !no_ring) return launch_bwd_pair_cfg<NHWC, NHWC>(feat, p, S, accumulate, grad_feat, s);
+    return launch_bwd_pair_cfg<NHWC, false>(feat, p, S, accumulate, grad_feat, s);
 }
 
 template <int C, bool NHWC, bool RING>
-static int launch_bwd_cfg(const float* feat, const GramPlan& p, int accumulate, float* grad_feat, cudaStream_t s) {
+static int launch_bwd_cfg(const float* feat, const GramPlan& p, GramS S, int accumulate, float* grad_feat, cudaStream_t s) {
     using Cfg = BwdCfg<C, RING>;
     CUtensorMap map_f, map_s;
     int rc = NHWC ? make_map_nhwc(&map_f, feat, p.B, p.HW, C, 128, CU_TENSOR_MAP_SWIZZLE_128B)
                   : make_map(&map_f, feat, (uint64_t)p.B * C, (uint64_t)p.HW, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc != ST3D_OK) return rc;
-    rc = make_map(&map_s, p.sym, (uint64_t)p.B * C, (uint64_t)C, Cfg::S_BOX_ROWS);
+    rc = make_map(&map_s, S.s, (uint64_t)p.B * C, (uint64_t)C, Cfg::S_BOX_ROWS);
     if (rc != ST3D_OK) return rc;
     static std::atomic<uint64_t> attr_done{0};
     rc = ensure_smem_attr(k_gram_tc_bwd<C, NHWC, RING>, (int)Cfg::SMEM, attr_done);
@@ -1282,21 +1301,22 @@ static int launch_bwd_cfg(const float* feat, const GramPlan& p, int accumulate, 
     const int64_t items = (int64_t)p.B * ((p.HW + 127) / 128);
     ST3D_REQUIRE(items < (1ll << 31), "gram_backward: B * ceil(HW / 128) = %lld work items exceed 2^31", (long long)items);
     const int grid = (int)std::min<int64_t>(items, 148);
-    k_gram_tc_bwd<C, NHWC, RING><<<grid, kThreads, Cfg::SMEM, s>>>(map_f, map_s, feat, grad_feat, p.B, p.HW, accumulate);
+    k_gram_tc_bwd<C, NHWC, RING><<<grid, kThreads, Cfg::SMEM, s>>>(map_f, map_s, feat, grad_feat, p.B, p.HW, accumulate, S.scale,
+                                                                   S.scale_dev);
     ST3D_LAUNCH_OK("k_gram_tc_bwd");
     return ST3D_OK;
 }
 
 template <int C, bool NHWC>
-static int launch_bwd(const float* feat, const GramPlan& p, int accumulate, float* grad_feat, cudaStream_t s) {
+static int launch_bwd(const float* feat, const GramPlan& p, GramS S, int accumulate, float* grad_feat, cudaStream_t s) {
     if (C == 512) {  // CTA pairs (cta_group::2); ST3D_GRAM_BWD512_SINGLE=1 keeps the one-CTA kernel for comparison
         static const bool single = [] { const char* e = getenv("ST3D_GRAM_BWD512_SINGLE"); return e && e[0] == '1'; }();
-        if (!single) return launch_bwd_pair<NHWC>(feat, p, accumulate, grad_feat, s);
+        if (!single) return launch_bwd_pair<NHWC>(feat, p, S, accumulate, grad_feat, s);
     }
     // C = 256: the prefetch-ring configuration when the fused tail is requested on channels_last features (the only
     // layout the ring serves), the four-stage one otherwise
-    if (C == 256 && NHWC && accumulate != 0) return launch_bwd_cfg<C, NHWC, (C <= 256)>(feat, p, accumulate, grad_feat, s);
-    return launch_bwd_cfg<C, NHWC, (C <= 128)>(feat, p, accumulate, grad_feat, s);
+    if (C == 256 && NHWC && accumulate != 0) return launch_bwd_cfg<C, NHWC, (C <= 256)>(feat, p, S, accumulate, grad_feat, s);
+    return launch_bwd_cfg<C, NHWC, (C <= 128)>(feat, p, S, accumulate, grad_feat, s);
 }
 
 }  // namespace tc
@@ -1320,10 +1340,11 @@ static inline int gram_tc_forward(const float* feat, const GramPlan& p, bool nhw
     return ST3D_ERR_UNSUPPORTED;
 }
 
-static inline int gram_tc_backward(const float* feat, const GramPlan& p, bool nhwc, int accumulate, float* grad_feat,
-                                   cudaStream_t s) {
-#define ST3D_BWD(CC) \
-    return nhwc ? tc::launch_bwd<CC, true>(feat, p, accumulate, grad_feat, s) : tc::launch_bwd<CC, false>(feat, p, accumulate, grad_feat, s)
+static inline int gram_tc_backward(const float* feat, const GramPlan& p, bool nhwc, tc::GramS S, int accumulate,
+                                   float* grad_feat, cudaStream_t s) {
+#define ST3D_BWD(CC)                                                                          \
+    return nhwc ? tc::launch_bwd<CC, true>(feat, p, S, accumulate, grad_feat, s)              \
+                : tc::launch_bwd<CC, false>(feat, p, S, accumulate, grad_feat, s)
     switch (p.C) {
         case 64: ST3D_BWD(64);
         case 128: ST3D_BWD(128);

@@ -225,6 +225,8 @@ class _StyleLayerFn(torch.autograd.Function):
     def backward(ctx, grad_out):
         feat, dgram = ctx.saved_tensors
         # dgram = dL/dG for grad_out == 1; the upstream scalar is applied on the device without a host sync
+        # (general in the target: an arbitrary (C,C) target gives a non-symmetric dG, so the dG + dG^T pass stays; the
+        # fused VGG taps, whose targets are Gram matrices by construction, skip it -- st3d/vgg.py)
         g = ops.gram_backward(feat, dgram, 1.0, precision=ctx.precision, scale_tensor=grad_out)
         return g, None, None, None
 

@@ -515,11 +515,12 @@ def gram_mse_forward(feat, target, scale: float, loss_out, want_gram=False, prec
 
 @_on_device_of
 def gram_backward(feat, dgram, grad_scale: float = 1.0, out=None, accumulate=False, precision=None, scale_tensor=None,
-                  relu_mask=False):
+                  relu_mask=False, symmetric_dgram=False):
     """grad_feat = grad_scale * [scale_tensor] * (dG + dG^T) F, with the shape AND memory layout of feat
     (scale_tensor: 1-element CUDA tensor).  `out`, when given, must have feat's layout; with `accumulate` the
     result is added to it.  `relu_mask` then zeroes the elements whose feat value is <= 0 (the backward of the
-    ReLU that produced feat, applied to the sum) -- both fused into the kernel's epilogue."""
+    ReLU that produced feat, applied to the sum) -- both fused into the kernel's epilogue.  `symmetric_dgram`: dgram is
+    symmetric (what gram_mse_forward returns), so the dG + dG^T pass is skipped."""
     f, layout, (B, C, HW) = _feat3("feat", feat)
     dgram = _cuda_f32("dgram", dgram, C, C).reshape(B, C, C)
     if out is None:
@@ -535,6 +536,7 @@ def gram_backward(feat, dgram, grad_scale: float = 1.0, out=None, accumulate=Fal
         scale_tensor = _cuda_f32("scale_tensor", scale_tensor).reshape(1)
     flags = (1 if accumulate else 0) | (2 if relu_mask else 0)
     with _timed("gram_backward" + ("", "_acc", "_relu", "_acc_relu")[flags], (B, C, HW)):
+        flags |= 4 if symmetric_dgram else 0
         check(lib().st3d_gram_backward(_p(f), _p(dgram), B, C, HW, float(grad_scale), _p(scale_tensor), flags,
                                        _p(out), _p(ws), nbytes, _precision(precision, C, HW), layout, _stream()),
               "st3d_gram_backward")

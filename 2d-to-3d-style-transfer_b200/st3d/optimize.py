@@ -149,6 +149,8 @@ class StyleOptimizer:
         self.images_ready: Optional[torch.cuda.Event] = None
         self._edges = None
         self.last_images: Optional[torch.Tensor] = None
+        self._eager_steps = 0
+        self._captured: Optional[CapturedIteration] = None
 
     # kept for the first API of this module
     @property
@@ -175,12 +177,6 @@ class StyleOptimizer:
         kw = dict(texture=colour, face_uvs=self.face_uvs) if self.uv_mode else dict(verts_rgb=colour)
         images, masks, _ = Fn.render_views(verts, self.faces, R, T, self.image_size, background_image=background_image, **kw)
         return images, masks
-
-    def _style_targets(self, style_img):
-        x = self._nn_input(style_img)
-        if self.style_weights is not None:
-            return losses.blended_style_targets(x, self.style_weights, self.vgg, self.precision)
-        return losses.style_targets(x, self.vgg, self.precision)
 
     def _regularisers(self):
         from . import mesh_losses as ml
@@ -301,7 +297,7 @@ class StyleOptimizer:
         micro_batch: render / walk the VGG over this many views at a time and ACCUMULATE their gradients into the one
         Adam step (the loss is a mean over views, losses.py:31,38, so a chunk of b of the B views weighs b / B): the
         same iteration as one B-view batch with the activations of only `micro_batch` views alive."""
-        self._eager_steps = getattr(self, "_eager_steps", 0) + 1
+        self._eager_steps += 1
         return self._reduce_and_update(self._accumulate_gradients(R, T, style_img, images_out, micro_batch))
 
     def capture(self, R: torch.Tensor, T: torch.Tensor, style_img: torch.Tensor,
@@ -311,10 +307,15 @@ class StyleOptimizer:
         image are copied INTO them before `step_captured()`.  The warm-up runs `warmup` real iterations.  What stays
         outside the graph is what involves other ranks or the host: the NCCL all-reduce, the regularisers that overlap
         it, and the Adam step."""
-        if getattr(self, "_eager_steps", 0):
+        if self._eager_steps:
             # the leaves' gradient accumulators were bound to the stream the eager steps ran on (normally the legacy
             # default stream); autograd would make that stream wait on the capturing one, which CUDA refuses
             raise RuntimeError("capture() must be called before any eager step(): build a fresh optimiser for the captured loop")
+        if self.cache_constants:
+            # the constants would be computed in the warm-up and left OUT of the recorded iteration: new cameras copied
+            # into the static tensors would then meet the old content feature without any error
+            raise ValueError("capture() records the whole iteration, constants included: build the optimiser with "
+                             "cache_constants=False")
         if self.target != "texture":
             # a moving mesh changes the sizes of the rasterizer's work lists from step to step; their overflow check is
             # a host read the replayed graph cannot make.  With fixed geometry the sizes seen in the warm-up hold.
@@ -339,7 +340,7 @@ class StyleOptimizer:
 
     def step_captured(self) -> torch.Tensor:
         """Replays the captured gradient computation, then all-reduce / regularisers / Adam; returns the loss."""
-        if getattr(self, "_captured", None) is None:
+        if self._captured is None:
             raise RuntimeError("call capture(R, T, style_img) first")
         loss = self._captured.replay()
         return self._reduce_and_update(loss)

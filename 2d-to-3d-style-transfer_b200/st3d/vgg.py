@@ -96,7 +96,7 @@ class _ConvReLUStyleTapFn(torch.autograd.Function):
                     out = torch.empty_like(y)
                     out.copy_(grad_y)
             g = ops.gram_backward(y, dgram, 1.0, out=out, accumulate=out is not None, precision=precision,
-                                  scale_tensor=grad_loss, relu_mask=True)
+                                  scale_tensor=grad_loss, relu_mask=True, symmetric_dgram=True)
         need = [ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]]
         gx, gw, gb = torch.ops.aten.convolution_backward(g, x, weight, [weight.shape[0]], list(stride), list(padding),
                                                          list(dilation), False, [0, 0], groups, need)
@@ -164,7 +164,10 @@ class FusedConvReLU(nn.Module):
                                      self.feeds_masking_pool and not self.tapped)
 
     def forward_with_style_tap(self, x, target_gram, precision=None):
-        """(activation, style-loss term of this layer against `target_gram` (1|B,C,C)); CUDA only."""
+        """(activation, style-loss term of this layer against `target_gram` (1|B,C,C)); CUDA only.
+        `target_gram` must be SYMMETRIC -- a Gram matrix or a blend of Gram matrices, what losses.py:24 builds: the
+        backward then reads dG = 2 scale (G - target) as the symmetric matrix it is and skips the dG + dG^T pass
+        (st3d.functional.style_layer_loss is the entry point for arbitrary targets)."""
         c = self.conv
         bias = c.bias if c.bias is not None else torch.zeros(c.out_channels, device=x.device, dtype=x.dtype)
         return _ConvReLUStyleTapFn.apply(x, c.weight, bias, target_gram, tuple(c.stride), tuple(c.padding),

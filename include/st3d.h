@@ -226,6 +226,9 @@ int st3d_gram_mse_forward(const float* feat, const float* target, int B, int Bt,
  * by st3d_gram_workspace_size. */
 #define ST3D_GRAM_ACCUMULATE 1
 #define ST3D_GRAM_RELU_MASK 2
+/* The caller vouches that dgram is symmetric -- true of what st3d_gram_mse_forward writes, 2 scale (G - G_target) of two
+ * Gram matrices: the dG + dG^T pass is skipped, the GEMM reads dgram directly and 2 s is applied to its accumulator. */
+#define ST3D_GRAM_DGRAM_SYMMETRIC 4
 int st3d_gram_backward(const float* feat, const float* dgram, int B, int C, int64_t HW, float grad_scale,
                        const float* grad_scale_dev, int accumulate, float* grad_feat, void* workspace,
                        size_t workspace_bytes, int precision, int layout, st3d_stream_t stream);

@@ -411,3 +411,32 @@ def test_full_size_pool_and_fused_tail_bit_identical_to_torch():
         assert abs(gr.double().sum().item() - g.double().sum().item()) <= 1e-6 * g.double().abs().sum().item()
         del xr, yr, y, g, gr, f
         torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("C,H,W", [(64, 24, 20), (256, 16, 16), (512, 16, 8)])
+def test_gram_backward_symmetric_dgram_skips_the_symmetrise_pass(C, H, W):
+    """ST3D_GRAM_DGRAM_SYMMETRIC: for a symmetric dG (what gram_mse_forward returns for Gram-matrix targets) the GEMM reads
+    dG directly and applies 2 s to its accumulator -- same gradient as the general dG + dG^T path, one launch fewer."""
+    ops = _ops()
+    B = 3
+    f = _features(B, C, H, W, 31).cuda().contiguous(memory_format=torch.channels_last)
+    target = lo.gram_matrix(_features(1, C, H, W, 32).double()).float().cuda()
+    loss = torch.zeros(1, device="cuda")
+    dgram, _ = ops.gram_mse_forward(f, target, 1e-3, loss, precision="tf32")
+    assert (dgram - dgram.transpose(1, 2)).abs().max().item() <= 1e-6 * dgram.abs().max().item()
+    scale_t = torch.tensor([0.37], device="cuda")
+    chain = torch.randn_like(f)
+    before = ops.launch_count()
+    fast = ops.gram_backward(f, dgram, 1.5, out=chain.clone(memory_format=torch.preserve_format), accumulate=True,
+                             precision="tf32", scale_tensor=scale_t, relu_mask=True, symmetric_dgram=True)
+    n_fast = ops.launch_count() - before
+    before = ops.launch_count()
+    general = ops.gram_backward(f, dgram, 1.5, out=chain.clone(memory_format=torch.preserve_format), accumulate=True,
+                                precision="tf32", scale_tensor=scale_t, relu_mask=True)
+    n_general = ops.launch_count() - before
+    assert n_fast == n_general - 1
+    f64 = f.double().cpu()
+    want = 1.5 * 0.37 * 2.0 * torch.einsum("bij,bjhw->bihw", dgram.double().cpu(), f64) + chain.double().cpu()
+    want = torch.where(f64 > 0, want, torch.zeros_like(want))
+    assert _relerr(fast, want) <= TOL_TC, _relerr(fast, want)
+    assert _relerr(fast, general.double()) <= TOL_TC
