@@ -335,7 +335,9 @@ def test_fused_vgg_pools_give_bit_identical_gradients():
 def test_style_taps_inside_the_conv_layers_equal_the_feature_walk(precision):
     """perceptual_loss_of_images evaluates every style tap inside its conv + ReLU layer (Gram backward + gradient
     accumulation + ReLU mask in one kernel epilogue, ST3D_GRAM_ACCUMULATE | ST3D_GRAM_RELU_MASK); loss and image
-    gradient must be bit-identical to get_features + perceptual_loss_from_features (losses.py:26-42)."""
+    gradient must equal get_features + perceptual_loss_from_features (losses.py:26-42): bit for bit with fp32 Gram
+    products; with tf32 the taps read the symmetric dG directly (ST3D_GRAM_DGRAM_SYMMETRIC) while the feature walk rounds
+    s (dG + dG^T) to tf32 -- two roundings of the same operand, 1e-4 apart."""
     import torchvision
     from st3d import losses
     from st3d.vgg import fuse_vgg_features
@@ -355,7 +357,10 @@ def test_style_taps_inside_the_conv_layers_equal_the_feature_walk(precision):
     assert _relerr(la, lb) <= 1e-6          # the per-layer MSE sums use float atomics: equal up to summation order
     la.backward()
     lb.backward()
-    assert torch.equal(xa.grad, xb.grad)
+    if precision == "fp32":
+        assert torch.equal(xa.grad, xb.grad)
+    else:
+        assert _relerr(xa.grad, xb.grad) <= 5e-4, _relerr(xa.grad, xb.grad)
     # an unfused model takes the feature-walk route and still agrees to rounding
     xc = x.clone().requires_grad_(True)
     lc = losses.perceptual_loss_of_images(xc, vgg.to(memory_format=torch.channels_last), content, grams, 1e6, 1.0, precision)
