@@ -88,13 +88,28 @@ def _worker(rank, world, port, q):
     tex.grad = torch.rand(4, 4, 3, generator=g)
     verts.grad = torch.rand(5, 3, generator=g)
     allreduce_gradients([tex, verts, unused])
-    q.put((rank, tex.grad.clone(), verts.grad.clone(), unused.grad is None))
+    # StyleOptimizer's form: the gradients are views of ONE flat buffer, reduced in place, asynchronously
+    flat = torch.zeros(64 + 15)
+    a, b = torch.zeros(4, 4, 3, requires_grad=True), torch.zeros(5, 3, requires_grad=True)
+    a.grad, b.grad = flat[:48].view(4, 4, 3), flat[64:79].view(5, 3)
+    a.grad.copy_(torch.rand(4, 4, 3, generator=g))
+    b.grad.copy_(torch.rand(5, 3, generator=g))
+    works = allreduce_gradients([a, b], flat=flat, async_op=True)
+    assert len(works) == 1
+    for w in works:
+        w.wait()
+    assert a.grad.data_ptr() == flat.data_ptr()         # still views: reduced where they lie
+    q.put((rank, tex.grad.clone(), verts.grad.clone(), unused.grad is None, a.grad.clone(), b.grad.clone()))
     dist.barrier()
     dist.destroy_process_group()
 
 
 def test_view_sharded_gradient_allreduce_gloo():
-    world, port = 2, 29641
+    import socket
+    world = 2
+    with socket.socket() as sock:           # a free rendezvous port (a fixed one can linger in TIME_WAIT between runs)
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
@@ -105,8 +120,16 @@ def test_view_sharded_gradient_allreduce_gloo():
         p.join(60)
         assert p.exitcode == 0
     want_tex = sum(torch.rand(4, 4, 3, generator=torch.Generator().manual_seed(100 + r)) for r in range(world))
-    for rank, tex, verts, unused_none in out:
+
+    def third_and_fourth_draws(r):
+        gen = torch.Generator().manual_seed(100 + r)
+        torch.rand(4, 4, 3, generator=gen), torch.rand(5, 3, generator=gen)
+        return torch.rand(4, 4, 3, generator=gen), torch.rand(5, 3, generator=gen)
+    want_a = sum(third_and_fourth_draws(r)[0] for r in range(world))
+    want_b = sum(third_and_fourth_draws(r)[1] for r in range(world))
+    for rank, tex, verts, unused_none, a, b in out:
         assert torch.allclose(tex, want_tex) and unused_none
+        assert torch.allclose(a, want_a) and torch.allclose(b, want_b)
     assert torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
 
 
@@ -190,3 +213,24 @@ def test_fused_vgg_pool_wiring_and_cpu_walk(monkeypatch):
     assert not any(getattr(m, "feeds_masking_pool", False) for m in no_pool)
     # an odd-sized or NCHW input is not for the libst3d pooling kernels
     assert not FusedMaxPool.accepts(torch.nn.MaxPool2d(3, 2)) and FusedMaxPool.accepts(torch.nn.MaxPool2d(2, 2))
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) on a tiny job: ONE JSON line on stdout
+    with the contract's keys, real full iterations (ms_per_step x steps is what the run spent), no GPU needed."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                        "--views", "2", "--size", "64", "--gpus", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    out = json.loads(lines[0])
+    assert out["impl"] == "reference" and out["higher_is_better"] is True and out["unit"] == "it/s"
+    assert out["steps"] == 2 and out["warmup"] == 1 and out["n_gpus"] == 1
+    assert abs(out["value"] - 1e3 / out["ms_per_step"]) <= 1e-9 * out["value"]          # a step IS a full iteration
+    cb = out["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["views_per_step"] == 2 and "FULL iterations" in cb["sample"]
+    assert out["e2e"] == {"value": out["value"], "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert out["config"]["global_views"] == 2 and out["config"]["workload"].startswith("cow_mesh")
