@@ -32,6 +32,7 @@ class RenderArgs(ctypes.Structure):
         ("workspace", c_p), ("workspace_bytes", c_sz), ("list_capacity", c_i64), ("z_clip", c_f),
         ("light_kind", c_i), ("light_vec", c_f * 3), ("light_diffuse", c_f * 3), ("light_specular", c_f * 3),
         ("shininess", c_f), ("background_image", c_p), ("background_batch", c_i), ("cull_to_frustum", c_i),
+        ("grad_texture_scratch", c_p),
     ]
 
 

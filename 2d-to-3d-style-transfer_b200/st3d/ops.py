@@ -427,9 +427,13 @@ def render_backward(state: RenderState, grad_image, need_texture=True, need_vert
                                   "the texture / vertex colours only")
     g_verts = torch.zeros((a.V, 3), device=dev, dtype=torch.float32) if need_verts else None
     g_rgb = torch.zeros((a.V, 3), device=dev, dtype=torch.float32) if (need_verts_rgb and a.tex_mode == TEX_VERTEX) else None
+    # texel-padded zero scratch: the kernel scatters with 16-byte vector reductions, a second kernel folds it into g_tex
+    scratch = torch.zeros((a.Ht, a.Wt, 4), device=dev, dtype=torch.float32) if g_tex is not None else None
+    a.grad_texture_scratch = _p(scratch)
     with _timed("render_backward", (a.N, a.H, a.W, a.F)):
         check(lib().st3d_render_backward(ctypes.byref(a), _p(grad_image), _p(g_tex), _p(g_verts), _p(g_rgb), _stream()),
               "st3d_render_backward")
+    a.grad_texture_scratch = None
     return g_tex, g_verts, g_rgb
 
 

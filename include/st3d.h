@@ -174,6 +174,10 @@ typedef struct st3d_render_args {
     /* RasterizationSettings.cull_to_frustum: drop the faces whose three vertices all lie beyond one side plane
      * (x = -1, x = 1, y = -1, y = 1) of the NDC frustum, as upstream's clip_faces does before rasterizing */
     int cull_to_frustum;
+    /* st3d_render_backward only, optional: (Ht,Wt,4) floats, 16-byte aligned, ZERO-FILLED by the caller.  When given, the
+     * bilinear texel scatter goes into it as 16-byte vector reductions (one per tap instead of three scalar ones -- the
+     * scatter is what bounds the backward kernel) and is folded into grad_texture by a second small kernel. */
+    float* grad_texture_scratch;
 } st3d_render_args;
 
 size_t st3d_render_workspace_size(int N, int64_t V, int64_t F, int H, int W, int64_t list_capacity);
