@@ -116,6 +116,40 @@ __device__ __forceinline__ void warp_aggregate_add(bool valid, int key, const fl
     }
 }
 
+// The same for the nine NDC-coordinate gradients of a face when the destination keeps one float4 per vertex: three
+// 16-byte vector reductions (red.global.add.v4.f32) per face group instead of nine scalar ones.  dst(key, k) is the
+// float4 slot of vertex k of face `key`; the fourth component receives 0.
+template <class DstFn>
+__device__ __forceinline__ void warp_aggregate_add_verts_v4(bool valid, int key, const float (&vals)[9], DstFn dst) {
+    const unsigned lane = threadIdx.x & 31;
+    if (!__any_sync(0xffffffffu, valid)) return;
+    const unsigned grp = __match_any_sync(0xffffffffu, valid ? key : (int)(0x80000000u | lane));
+    const bool shared_key = valid && (grp & (grp - 1)) != 0;
+    if (valid && !shared_key) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (vals[3 * k] != 0.0f || vals[3 * k + 1] != 0.0f || vals[3 * k + 2] != 0.0f)
+                atomicAdd(dst(key, k), make_float4(vals[3 * k], vals[3 * k + 1], vals[3 * k + 2], 0.0f));
+    }
+    unsigned remaining = __ballot_sync(0xffffffffu, shared_key && lane == (unsigned)(__ffs(grp) - 1));  // group leaders
+    while (remaining) {
+        const int leader = __ffs(remaining) - 1;
+        const unsigned g = __shfl_sync(0xffffffffu, grp, leader);
+        const int lk = __shfl_sync(0xffffffffu, key, leader);
+        const bool mine = (g >> lane) & 1u;
+        float sum[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) sum[i] = warp_sum(mine ? vals[i] : 0.0f);
+        if (lane == (unsigned)leader) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (sum[3 * k] != 0.0f || sum[3 * k + 1] != 0.0f || sum[3 * k + 2] != 0.0f)
+                    atomicAdd(dst(lk, k), make_float4(sum[3 * k], sum[3 * k + 1], sum[3 * k + 2], 0.0f));
+        }
+        remaining &= remaining - 1;
+    }
+}
+
 // SURVEY A.3 PixToNonSquareNdc
 __device__ __forceinline__ float pix_to_ndc(int i, int S1, int S2) {
     float range = 2.0f;
@@ -241,7 +275,7 @@ struct RasterWs {
     float* ndc_x;      // W: NDC x of every pixel column (exact oracle arithmetic)
     float* ndc_y;      // H
     float4* verts_ndc; // N*V (render only)
-    float* grad_ndc;   // N*V*3 (render backward scratch)
+    float* grad_ndc;   // N*V*4 (render backward scratch: one float4 per (view, vertex), xyz used)
     float* vnormals;   // V*3 unit vertex normals (render with Point / Directional lights)
     size_t zero_bytes; // hdr + tile_count + tile_cursor (contiguous) cleared every call
     size_t total_bytes;
@@ -291,7 +325,7 @@ static inline RasterWs raster_ws_layout(void* base, int N, int64_t F_total, int 
     off += (size_t)NV * sizeof(float4);
     off = align_up(off, 256);
     w.grad_ndc = (float*)(p + off);
-    off += (size_t)NV * 3 * sizeof(float);
+    off += (size_t)NV * 4 * sizeof(float);
     off = align_up(off, 256);
     w.vnormals = (float*)(p + off);
     off += (size_t)(N > 0 ? NV / N : 0) * 3 * sizeof(float);

@@ -92,7 +92,7 @@ __global__ void k_interp_bwd(const int64_t* __restrict__ pix_to_face, const floa
 // -------------------------------------------------------------------------------------------------
 __global__ void k_transform_bwd(const float* __restrict__ verts, const float* __restrict__ R,
                                 const float* __restrict__ T, float k00, float k11, int N, int64_t V,
-                                const float* __restrict__ grad_ndc, float* __restrict__ grad_verts) {
+                                const float* __restrict__ grad_ndc, int gstride, float* __restrict__ grad_verts) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= V) return;
     const float x = verts[3 * i], y = verts[3 * i + 1], z = verts[3 * i + 2];
@@ -100,7 +100,7 @@ __global__ void k_transform_bwd(const float* __restrict__ verts, const float* __
     for (int n = 0; n < N; ++n) {
         const float* r = R + 9 * n;
         const float* t = T + 3 * n;
-        const float* g = grad_ndc + 3 * ((int64_t)n * V + i);
+        const float* g = grad_ndc + (int64_t)gstride * ((int64_t)n * V + i);
         const float gx = g[0], gy = g[1], gz = g[2];
         if (gx == 0.0f && gy == 0.0f && gz == 0.0f) continue;
         const float xv = x * r[0] + y * r[3] + z * r[6] + t[0];
@@ -182,6 +182,14 @@ k_composite(const float* __restrict__ image, const float* __restrict__ mask, con
     }
 }
 
+int transform_verts_backward_strided(const float* verts, const float* R, const float* T, float k00, float k11, int N,
+                                     int64_t V, const float* grad_ndc, int gstride, float* grad_verts, cudaStream_t s) {
+    if (N == 0 || V == 0) return ST3D_OK;
+    k_transform_bwd<<<cdiv(V, 128), 128, 0, s>>>(verts, R, T, k00, k11, N, V, grad_ndc, gstride, grad_verts);
+    ST3D_LAUNCH_OK("k_transform_bwd");
+    return ST3D_OK;
+}
+
 }  // namespace st3d
 
 using namespace st3d;
@@ -260,7 +268,7 @@ extern "C" int st3d_transform_verts_backward(const float* verts, const float* R,
     ST3D_REQUIRE(N >= 0 && V >= 0, "transform_verts_backward: negative size");
     if (N == 0 || V == 0) return ST3D_OK;
     ST3D_REQUIRE(verts && R && T && grad_ndc && grad_verts, "transform_verts_backward: null pointer");
-    k_transform_bwd<<<cdiv(V, 128), 128, 0, (cudaStream_t)stream>>>(verts, R, T, k00, k11, N, V, grad_ndc, grad_verts);
+    k_transform_bwd<<<cdiv(V, 128), 128, 0, (cudaStream_t)stream>>>(verts, R, T, k00, k11, N, V, grad_ndc, 3, grad_verts);
     ST3D_LAUNCH_OK("k_transform_bwd");
     return ST3D_OK;
 }

@@ -18,6 +18,10 @@
 
 namespace st3d {
 
+// ops.cu: camera-chain backward over grad_ndc rows of `gstride` floats
+int transform_verts_backward_strided(const float* verts, const float* R, const float* T, float k00, float k11, int N,
+                                     int64_t V, const float* grad_ndc, int gstride, float* grad_verts, cudaStream_t s);
+
 // Winning pixel of a near-plane-clipped face (clip.cuh): which sub-triangle produced the z-buffer key, its
 // barycentrics converted to the unclipped face, depth and signed edge distance.
 struct ClipFrag {
@@ -238,9 +242,10 @@ k_render_bwd(const FaceRec* __restrict__ rec, const unsigned long long* __restri
         // per-face accumulation: lanes that hit the same face are summed before the atomics
         const int32_t* faces = sp.faces;
         const int64_t nV = (int64_t)n * sp.V;
-        warp_aggregate_add<9>(hit, fl, gv, [&](int key, int i) {
-            const int vert = __ldg(faces + 3 * (int64_t)key + i / 3);
-            return grad_ndc + 3 * (nV + vert) + i % 3;
+        float4* gn4 = reinterpret_cast<float4*>(grad_ndc);  // one float4 per (view, vertex): three vector reductions per face
+        warp_aggregate_add_verts_v4(hit, fl, gv, [&](int key, int k) {
+            const int vert = __ldg(faces + 3 * (int64_t)key + k);
+            return gn4 + (nV + vert);
         });
     }
     if (TEX_MODE == ST3D_TEX_VERTEX && grad_verts_rgb) {
@@ -293,7 +298,7 @@ extern "C" int st3d_render_backward(const st3d_render_args* a, const float* grad
     const int clip = a->blur_radius > 0.0f ? 1 : 0;
     const float z_clip = a->z_clip > 0.0f ? a->z_clip : -INFINITY;
     const bool geom = grad_verts != nullptr;
-    if (geom) ST3D_CUDA_OK(cudaMemsetAsync(ws.grad_ndc, 0, (size_t)a->N * a->V * 3 * sizeof(float), s));
+    if (geom) ST3D_CUDA_OK(cudaMemsetAsync(ws.grad_ndc, 0, (size_t)a->N * a->V * 4 * sizeof(float), s));
     float* g_tex = a->tex_mode == ST3D_TEX_UV ? grad_texture : nullptr;
     // texel-padded scratch for vector reductions (optional, caller-provided and zero-filled; NULL: scalar atomics)
     float4* tex4 = (g_tex && a->grad_texture_scratch && (((uintptr_t)a->grad_texture_scratch) & 15) == 0)
@@ -315,8 +320,8 @@ extern "C" int st3d_render_backward(const st3d_render_args* a, const float* grad
         ST3D_LAUNCH_OK("k_tex4_accumulate");
     }
     if (geom) {
-        const int rc = st3d_transform_verts_backward(a->verts, a->R, a->T, a->k00, a->k11, a->N, a->V, ws.grad_ndc,
-                                                     grad_verts, stream);
+        const int rc = st3d::transform_verts_backward_strided(a->verts, a->R, a->T, a->k00, a->k11, a->N, a->V, ws.grad_ndc, 4,
+                                                              grad_verts, s);
         if (rc != ST3D_OK) return rc;
     }
     return ST3D_OK;
