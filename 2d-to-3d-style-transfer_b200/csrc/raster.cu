@@ -75,18 +75,8 @@ __device__ __forceinline__ void ndc_pixel_range(float lo_v, float hi_v, int S1, 
 // is decided by comparisons against the exact table values, so the result equals ndc_pixel_range's.
 __device__ __forceinline__ void table_pixel_range(const float* __restrict__ tab, int S, float a, float b, float lo_v,
                                                   float hi_v, int& i0, int& i1) {
-    const float fh = fmaf(hi_v, a, b), fl = fmaf(lo_v, a, b);
-    // Sure reject without touching the table: the estimate is within delta of the exact pixel coordinate (fp32 error of
-    // a v + b plus one ulp of the table value: < 1e-4 pixel at a = 512), so if even [fl - delta, fh + delta] holds no
-    // integer, no pixel centre lies in [lo_v, hi_v].  On a mesh denser than the pixel grid that is most faces.
-    const float delta = 1e-3f + 4e-7f * a;
-    if (floorf(fh + delta) < ceilf(fl - delta)) {
-        i0 = 1;
-        i1 = 0;
-        return;
-    }
-    const int jhi = (int)fminf(fmaxf(floorf(fh), -1.0f), (float)(S - 1));
-    const int jlo = (int)fminf(fmaxf(ceilf(fl), 0.0f), (float)S);
+    const int jhi = (int)fminf(fmaxf(floorf(fmaf(hi_v, a, b)), -1.0f), (float)(S - 1));
+    const int jlo = (int)fminf(fmaxf(ceilf(fmaf(lo_v, a, b)), 0.0f), (float)S);
     i0 = S - 1 - jhi;  // first i with tab[i] <= hi_v
     i1 = S - 1 - jlo;  // last i with tab[i] >= lo_v
     // confirm both seeds with four independent loads (one L1 latency); walk only when a seed is off by a pixel
@@ -473,7 +463,7 @@ __device__ __forceinline__ TriBox tri_box(const FaceVerts& v, int H, int W, floa
     if (!(isfinite(xmin) && isfinite(xmax) && isfinite(ymin) && isfinite(ymax))) valid = false;
     if (valid) {
         table_pixel_range(ndc_x, W, est.x, est.y, xmin, xmax, b.x0, b.x1);  // image x runs opposite to NDC x (A.3)
-        if (b.x0 <= b.x1) table_pixel_range(ndc_y, H, est.z, est.w, ymin, ymax, b.y0, b.y1);
+        table_pixel_range(ndc_y, H, est.z, est.w, ymin, ymax, b.y0, b.y1);
         if (b.x0 > b.x1 || b.y0 > b.y1) {
             valid = false;
             b.x0 = b.y0 = 1;
