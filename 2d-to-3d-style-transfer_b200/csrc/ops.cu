@@ -182,6 +182,29 @@ k_composite(const float* __restrict__ image, const float* __restrict__ mask, con
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// backward of a tapped conv + ReLU activation y whose tap is a content MSE against c (losses.py:31):
+//   out = (y > 0) ? grad_in + s (y - c) : 0,   s = 2 scale [* *scale_dev]
+// i.e. the MSE backward, its addition to the gradient that reached y through the rest of the network, and the ReLU
+// backward of the sum (ATen threshold_backward) in ONE pass instead of three (mul, add, threshold).
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_mse_tap_bwd(const float4* __restrict__ y, const float4* __restrict__ c, const float4* __restrict__ grad_in, float s,
+              const float* __restrict__ s_dev, int64_t n4, float4* __restrict__ out) {
+    if (s_dev) s *= __ldg(s_dev);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 yv = y[i], cv = __ldg(c + i);
+        const float4 g = grad_in ? grad_in[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 o;
+        o.x = yv.x > 0.0f ? g.x + s * (yv.x - cv.x) : 0.0f;
+        o.y = yv.y > 0.0f ? g.y + s * (yv.y - cv.y) : 0.0f;
+        o.z = yv.z > 0.0f ? g.z + s * (yv.z - cv.z) : 0.0f;
+        o.w = yv.w > 0.0f ? g.w + s * (yv.w - cv.w) : 0.0f;
+        out[i] = o;
+    }
+}
+
 int transform_verts_backward_strided(const float* verts, const float* R, const float* T, float k00, float k11, int N,
                                      int64_t V, const float* grad_ndc, int gstride, float* grad_verts, cudaStream_t s) {
     if (N == 0 || V == 0) return ST3D_OK;
@@ -193,6 +216,20 @@ int transform_verts_backward_strided(const float* verts, const float* R, const f
 }  // namespace st3d
 
 using namespace st3d;
+
+extern "C" int st3d_mse_tap_backward(const float* y, const float* c, const float* grad_in, int64_t n, float scale,
+                                     const float* scale_dev, float* out, st3d_stream_t stream) {
+    ST3D_REQUIRE(n >= 0, "mse_tap_backward: negative size");
+    if (n == 0) return ST3D_OK;
+    ST3D_REQUIRE(y && c && out, "mse_tap_backward: null pointer");
+    ST3D_REQUIRE(n % 4 == 0 && ((((uintptr_t)y) | ((uintptr_t)c) | ((uintptr_t)grad_in) | ((uintptr_t)out)) & 15) == 0,
+                 "mse_tap_backward: n must be a multiple of 4 and the pointers 16-byte aligned");
+    const int grid = (int)std::min<int64_t>(cdiv(n / 4, 256), 148 * 8);
+    k_mse_tap_bwd<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)y, (const float4*)c, (const float4*)grad_in,
+                                                          2.0f * scale, scale_dev, n / 4, (float4*)out);
+    ST3D_LAUNCH_OK("k_mse_tap_bwd");
+    return ST3D_OK;
+}
 
 extern "C" int st3d_composite_forward(const float* image, const float* mask, const float* fill, int64_t n, int64_t inner,
                                       int ch, int fill_batch, float* out, st3d_stream_t stream) {

@@ -422,6 +422,12 @@ k_fine(const FaceRec* __restrict__ rec, const int* __restrict__ tile_count, cons
             sp.pix_to_face[pix] = hit ? best.f : -1;
             if (sp.out_layout == ST3D_LAYOUT_NHWC_RGBA) {
                 reinterpret_cast<float4*>(sp.out_image)[pix] = make_float4(rgba[0], rgba[1], rgba[2], rgba[3]);
+            } else if (sp.out_layout == ST3D_LAYOUT_NHWC_RGB) {
+                float* o = sp.out_image + 3 * pix;
+                o[0] = rgba[0];
+                o[1] = rgba[1];
+                o[2] = rgba[2];
+                if (sp.out_mask) sp.out_mask[pix] = rgba[3] > 0.0f ? 1.0f : 0.0f;
             } else {
                 const int64_t hw = (int64_t)H * W, o = (int64_t)n * 3 * hw + (int64_t)yi * W + xi;
                 sp.out_image[o] = rgba[0];
@@ -558,6 +564,12 @@ k_resolve(const FaceRec* __restrict__ rec, const unsigned long long* __restrict_
         sp.pix_to_face[pix] = hit ? f : -1;
         if (sp.out_layout == ST3D_LAYOUT_NHWC_RGBA) {
             reinterpret_cast<float4*>(sp.out_image)[pix] = make_float4(rgba[0], rgba[1], rgba[2], rgba[3]);
+        } else if (sp.out_layout == ST3D_LAYOUT_NHWC_RGB) {  // (N,H,W,3): a warp writes 384 contiguous bytes
+            float* o = sp.out_image + 3 * pix;
+            o[0] = rgba[0];
+            o[1] = rgba[1];
+            o[2] = rgba[2];
+            if (sp.out_mask) sp.out_mask[pix] = rgba[3] > 0.0f ? 1.0f : 0.0f;
         } else {
             const int64_t hw = (int64_t)H * W, o = (int64_t)n * 3 * hw + (int64_t)yi * W + xi;
             sp.out_image[o] = rgba[0];
@@ -1145,8 +1157,8 @@ extern "C" int st3d_render_forward(const st3d_render_args* a, st3d_stream_t stre
         ST3D_REQUIRE(a->verts_rgb, "render_forward: verts_rgb missing");
     else
         ST3D_REQUIRE(false, "render_forward: unknown tex_mode %d", a->tex_mode);
-    ST3D_REQUIRE(a->out_layout == ST3D_LAYOUT_NHWC_RGBA || a->out_layout == ST3D_LAYOUT_PLANAR,
-                 "render_forward: unknown out_layout %d", a->out_layout);
+    ST3D_REQUIRE(a->out_layout == ST3D_LAYOUT_NHWC_RGBA || a->out_layout == ST3D_LAYOUT_PLANAR ||
+                     a->out_layout == ST3D_LAYOUT_NHWC_RGB, "render_forward: unknown out_layout %d", a->out_layout);
     ST3D_REQUIRE(a->light_kind == ST3D_LIGHT_AMBIENT || a->light_kind == ST3D_LIGHT_POINT ||
                      a->light_kind == ST3D_LIGHT_DIRECTIONAL, "render_forward: unknown light_kind %d", a->light_kind);
     ST3D_REQUIRE(a->background_image == nullptr || a->background_batch == 1 || a->background_batch == a->N,

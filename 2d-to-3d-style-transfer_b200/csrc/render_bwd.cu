@@ -105,7 +105,7 @@ k_render_bwd(const FaceRec* __restrict__ rec, const unsigned long long* __restri
         float b0, b1, b2, pz, dist;
         // planar layout + hard rasterization: no alpha gradient comes in and d(rgb)/d(dist) is ~1e-10 relative,
         // so the edge distance (three point-segment distances) is neither recomputed nor differentiated
-        const bool skip_dist = sp.out_layout == ST3D_LAYOUT_PLANAR && clip == 0;
+        const bool skip_dist = sp.out_layout != ST3D_LAYOUT_NHWC_RGBA && clip == 0;
         if (near_clipped) {
             const ClipFrag cf = clipped_fragment(v, z_clip, px, py, (unsigned)(zkey[pix] >> 32));
             b0 = cf.b0; b1 = cf.b1; b2 = cf.b2; pz = cf.pz; dist = skip_dist ? -1.0f : cf.dist;
@@ -122,6 +122,9 @@ k_render_bwd(const FaceRec* __restrict__ rec, const unsigned long long* __restri
         if (sp.out_layout == ST3D_LAYOUT_NHWC_RGBA) {
             const float4 g = reinterpret_cast<const float4*>(grad_image)[pix];
             g_rgb[0] = g.x; g_rgb[1] = g.y; g_rgb[2] = g.z; g_alpha = g.w;
+        } else if (sp.out_layout == ST3D_LAYOUT_NHWC_RGB) {
+            const float* g = grad_image + 3 * pix;
+            g_rgb[0] = g[0]; g_rgb[1] = g[1]; g_rgb[2] = g[2];
         } else {
             const int64_t hw = (int64_t)H * W, o = (int64_t)n * 3 * hw + (int64_t)yi * W + xi;
             g_rgb[0] = grad_image[o]; g_rgb[1] = grad_image[o + hw]; g_rgb[2] = grad_image[o + 2 * hw];

@@ -59,6 +59,7 @@ SIGNATURES = {
     "st3d_composite_forward": (c_i, [c_p, c_p, c_p, c_i64, c_i64, c_i, c_i, c_p, c_p]),
     "st3d_composite_backward": (c_i, [c_p, c_p, c_i64, c_i64, c_i, c_p, c_p]),
     "st3d_mse_forward": (c_i, [c_p, c_p, c_p, c_i64, c_i64, c_i, c_f, c_p, c_p, c_p]),
+    "st3d_mse_tap_backward": (c_i, [c_p, c_p, c_p, c_i64, c_f, c_p, c_p, c_p]),
     "st3d_maxpool2x2_forward": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
     "st3d_maxpool2x2_backward": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
 }

@@ -55,7 +55,7 @@ class _RenderFn(torch.autograd.Function):
     def backward(ctx, grad_image, *unused):
         need_verts, need_tex = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         uv = ctx.mode == ops.TEX_UV
-        g_tex, g_verts, g_rgb = ops.render_backward(ctx.state, grad_image.contiguous(), need_texture=need_tex and uv,
+        g_tex, g_verts, g_rgb = ops.render_backward(ctx.state, grad_image, need_texture=need_tex and uv,
                                                     need_verts=need_verts, need_verts_rgb=need_tex and not uv)
         g_param = g_tex if uv else g_rgb
         if g_param is not None:
@@ -70,7 +70,7 @@ def render_views(verts: torch.Tensor, faces: torch.Tensor, R: torch.Tensor, T: t
                  ambient: Sequence[float] = (1.0, 1.0, 1.0), background: Sequence[float] = (1.0, 1.0, 1.0),
                  sigma: float = 1e-4, gamma: float = 1e-4, planar: bool = True, z_clip: Optional[float] = None,
                  lights: Optional[dict] = None, background_image: Optional[torch.Tensor] = None,
-                 cull_to_frustum: bool = False):
+                 cull_to_frustum: bool = False, channels_last: bool = False):
     """Render N camera views of one mesh in one launch sequence (faces_per_pixel = 1).
 
     lights: None = AmbientLights with the colour `ambient` (what the reference uses); or a dict(kind='point' |
@@ -80,6 +80,8 @@ def render_views(verts: torch.Tensor, faces: torch.Tensor, R: torch.Tensor, T: t
 
     planar=True  -> (images (N,3,H,W), masks (N,1,H,W), pix_to_face (N,H,W) int32): what
                     `render_meshes` (utils.py:65-77) returns, without the per-view Python loop.
+                    channels_last=True returns the same (N,3,H,W) images in torch channels_last storage (N,H,W,3) -- what
+                    a channels_last VGG takes without a layout copy -- and reads the image gradient in that storage.
     planar=False -> (rgba (N,H,W,4), pix_to_face): what `renderer(meshes_world=, cameras=)` returns.
     Differentiable w.r.t. `verts` and `texture` (UV mode, any shape ending in (Ht,Wt,3)) or `verts_rgb`.
     """
@@ -88,7 +90,8 @@ def render_views(verts: torch.Tensor, faces: torch.Tensor, R: torch.Tensor, T: t
     spec = ops.RenderSpec(image_size=(H, W), k00=k00, k11=k11, znear=znear, zfar=zfar, blur_radius=blur_radius,
                           cull_backfaces=cull_backfaces, cull_to_frustum=cull_to_frustum, ambient=tuple(ambient),
                           background=tuple(background), sigma=sigma, gamma=gamma, z_clip=z_clip,
-                          layout=ops.LAYOUT_PLANAR if planar else ops.LAYOUT_NHWC_RGBA)
+                          layout=(ops.LAYOUT_NHWC_RGB if channels_last else ops.LAYOUT_PLANAR) if planar
+                          else ops.LAYOUT_NHWC_RGBA)
     if lights is not None and lights.get("kind", "ambient") != "ambient":
         kind = lights["kind"]
         if kind not in ("point", "directional"):

@@ -78,6 +78,11 @@ def content_and_style_constants(content_imgs, style_imgs, model, precision=None,
         return content, grams
     B = content_imgs.shape[0]
     with torch.no_grad():
+        if getattr(model, "_st3d_channels_last", False) and content_imgs.is_cuda:
+            # both channels_last BEFORE the cat (the renderer can deliver its views that way): the cat then writes
+            # channels_last storage directly instead of an NCHW batch that needs a second, full-size layout copy
+            content_imgs = content_imgs.contiguous(memory_format=torch.channels_last)
+            style_imgs = style_imgs.contiguous(memory_format=torch.channels_last)
         x = torch.cat([content_imgs, style_imgs], dim=0)
         if getattr(model, "_st3d_channels_last", False) and x.is_cuda:
             x = x.contiguous(memory_format=torch.channels_last)
@@ -155,6 +160,9 @@ def perceptual_loss_of_images(current_imgs, model, content_feat, style_grams, st
         if layer in style_grams:
             x, term = module.forward_with_style_tap(x, style_grams[layer], precision)
             style_loss = term if style_loss is None else style_loss + term
+        elif layer == CONTENT_LAYER and isinstance(module, FusedConvReLU) and x.shape[0] == content_feat.shape[0]:
+            # the content tap inside its conv + ReLU layer: MSE backward + gradient accumulation + ReLU mask in one kernel
+            x, content_loss = module.forward_with_content_tap(x, content_feat)
         else:
             if hasattr(module, "tapped"):
                 module.tapped = layer is not None

@@ -16,7 +16,7 @@ from ._lib import RenderArgs, St3dError, check, lib
 
 TEX_UV, TEX_VERTEX = 0, 1
 LIGHT_AMBIENT, LIGHT_POINT, LIGHT_DIRECTIONAL = 0, 1, 2
-LAYOUT_NHWC_RGBA, LAYOUT_PLANAR = 0, 1
+LAYOUT_NHWC_RGBA, LAYOUT_PLANAR, LAYOUT_NHWC_RGB = 0, 1, 2
 MAX_FACES_PER_PIXEL = 8
 WS_HEADER_INTS = 16
 
@@ -396,6 +396,9 @@ def render_forward(spec: RenderSpec, verts, faces, R, T, *, face_uvs=None, textu
     if spec.layout == LAYOUT_NHWC_RGBA:
         image = torch.empty((N, H, W, 4), device=dev, dtype=torch.float32)
         mask = None
+    elif spec.layout == LAYOUT_NHWC_RGB:    # an (N,3,H,W) tensor in channels_last storage
+        image = torch.empty((N, H, W, 3), device=dev, dtype=torch.float32).permute(0, 3, 1, 2)
+        mask = torch.empty((N, 1, H, W), device=dev, dtype=torch.float32)
     else:
         image = torch.empty((N, 3, H, W), device=dev, dtype=torch.float32)
         mask = torch.empty((N, 1, H, W), device=dev, dtype=torch.float32)
@@ -418,7 +421,15 @@ def render_forward(spec: RenderSpec, verts, faces, R, T, *, face_uvs=None, textu
 def render_backward(state: RenderState, grad_image, need_texture=True, need_verts=False, need_verts_rgb=False):
     """Returns (grad_texture|None, grad_verts|None, grad_verts_rgb|None)."""
     a = state.args
-    grad_image = _cuda_f32("grad_image", grad_image)
+    if a.out_layout == LAYOUT_NHWC_RGB:     # the gradient in the storage order of the image: (N,H,W,3)
+        if not (isinstance(grad_image, torch.Tensor) and grad_image.is_cuda and grad_image.dtype == torch.float32):
+            raise St3dError("grad_image: expected a CUDA float32 tensor (st3d has no CPU path)")
+        _same_device("grad_image", grad_image)
+        if tuple(grad_image.shape) != (a.N, 3, a.H, a.W):
+            raise ValueError(f"grad_image: expected {(a.N, 3, a.H, a.W)}, got {tuple(grad_image.shape)}")
+        grad_image = grad_image.permute(0, 2, 3, 1).contiguous()        # no copy when it already is channels_last
+    else:
+        grad_image = _cuda_f32("grad_image", grad_image)
     dev = grad_image.device
     g_tex = torch.zeros((a.Ht, a.Wt, 3), device=dev, dtype=torch.float32) if (need_texture and a.tex_mode == TEX_UV) else None
     if need_verts and a.light_kind != LIGHT_AMBIENT:
@@ -599,6 +610,29 @@ def mse_forward(a, b, scale: float, loss_out, mask=None, want_grad=True):
         check(lib().st3d_mse_forward(_p(a), _p(b), _p(mask), a.numel(), inner, mask_ch, float(scale), _p(loss_out),
                                      _p(grad), _stream()), "st3d_mse_forward")
     return grad
+
+
+@_on_device_of
+def mse_tap_backward(y, c, grad_in, scale: float, scale_tensor=None):
+    """(y > 0) ? grad_in + 2 scale [* scale_tensor] (y - c) : 0 in one pass (st3d_mse_tap_backward).  y, c and grad_in
+    must share one dense layout; the result has it too.  grad_in may be None."""
+    if not (isinstance(y, torch.Tensor) and y.is_cuda and y.dtype == torch.float32):
+        raise St3dError("mse_tap_backward: expected CUDA float32 tensors (st3d has no CPU path)")
+    _same_device("y", y)
+    dense = y.is_contiguous() or (y.dim() == 4 and y.is_contiguous(memory_format=torch.channels_last))
+    if not dense or c.shape != y.shape or c.stride() != y.stride() or c.dtype != torch.float32 or not c.is_cuda:
+        raise ValueError("mse_tap_backward: y and c must be dense tensors of one shape and layout")
+    if grad_in is not None and (grad_in.shape != y.shape or grad_in.stride() != y.stride() or grad_in.dtype != torch.float32):
+        raise ValueError("mse_tap_backward: grad_in must match y in shape and layout")
+    if y.numel() % 4:
+        raise ValueError("mse_tap_backward: the number of elements must be a multiple of 4")
+    out = torch.empty_like(y)
+    if scale_tensor is not None:
+        scale_tensor = _cuda_f32("scale_tensor", scale_tensor).reshape(1)
+    with _timed("mse_tap_backward", (y.numel(),)):
+        check(lib().st3d_mse_tap_backward(_p(y), _p(c), _p(grad_in), y.numel(), float(scale), _p(scale_tensor), _p(out),
+                                          _stream()), "st3d_mse_tap_backward")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

@@ -175,7 +175,9 @@ class StyleOptimizer:
 
     def _render(self, verts, colour, R, T, background_image=None):
         kw = dict(texture=colour, face_uvs=self.face_uvs) if self.uv_mode else dict(verts_rgb=colour)
-        images, masks, _ = Fn.render_views(verts, self.faces, R, T, self.image_size, background_image=background_image, **kw)
+        # channels_last VGG: the renderer writes (and its backward reads) the images in that storage, no layout copies
+        images, masks, _ = Fn.render_views(verts, self.faces, R, T, self.image_size, background_image=background_image,
+                                           channels_last=self.channels_last, **kw)
         return images, masks
 
     def _regularisers(self):

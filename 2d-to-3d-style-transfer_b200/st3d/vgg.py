@@ -103,6 +103,45 @@ class _ConvReLUStyleTapFn(torch.autograd.Function):
         return gx, gw, gb, None, None, None, None, None, None
 
 
+class _ConvReLUContentTapFn(torch.autograd.Function):
+    """A FusedConvReLU whose activation is the CONTENT tap (conv4_2; losses.py:31): returns (y, mean((y - c)^2)).
+    The backward is one kernel, st3d_mse_tap_backward: the MSE gradient 2 (y - c) / n, its sum with the gradient arriving
+    from the layers behind y, and the ReLU backward of the sum -- autograd runs a multiply, an add and a threshold pass
+    over the 67 MB activation for the same thing."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, content, stride, padding, dilation, groups):
+        ops = _ops()
+        y = torch.cudnn_convolution_relu(x, weight, bias, stride, padding, dilation, groups)
+        c = content.detach()
+        if c.stride() != y.stride() or c.dtype != torch.float32:       # the kernels walk y and c in one element order
+            c = torch.empty_like(y).copy_(c)
+        loss = torch.zeros(1, device=y.device, dtype=torch.float32)
+        ops.mse_forward(y, c, 1.0 / max(y.numel(), 1), loss, want_grad=False)
+        ctx.conf = (stride, padding, dilation, groups)
+        ctx.save_for_backward(x, weight, y, c)
+        ctx.set_materialize_grads(False)
+        return y, loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_y, grad_loss):
+        ops = _ops()
+        x, weight, y, c = ctx.saved_tensors
+        stride, padding, dilation, groups = ctx.conf
+        if grad_loss is None and grad_y is None:
+            return (None,) * 8
+        if grad_loss is None:                       # the tap's loss term is unused: plain ReLU backward
+            g = torch.ops.aten.threshold_backward(grad_y, y, 0.0)
+        else:
+            if grad_y is not None and (grad_y.stride() != y.stride() or grad_y.dtype != torch.float32):
+                grad_y = torch.empty_like(y).copy_(grad_y)
+            g = ops.mse_tap_backward(y, c, grad_y, 1.0 / max(y.numel(), 1), scale_tensor=grad_loss)
+        need = [ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]]
+        gx, gw, gb = torch.ops.aten.convolution_backward(g, x, weight, [weight.shape[0]], list(stride), list(padding),
+                                                         list(dilation), False, [0, 0], groups, need)
+        return gx, gw, gb, None, None, None, None, None
+
+
 class _MaxPool2x2Fn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, relu_mask):
@@ -172,6 +211,17 @@ class FusedConvReLU(nn.Module):
         bias = c.bias if c.bias is not None else torch.zeros(c.out_channels, device=x.device, dtype=x.dtype)
         return _ConvReLUStyleTapFn.apply(x, c.weight, bias, target_gram, tuple(c.stride), tuple(c.padding),
                                          tuple(c.dilation), c.groups, precision)
+
+
+def _content_tap(self, x, content_feat):
+    """(activation, mean((activation - content_feat)^2)) with the fused one-kernel backward; CUDA only."""
+    c = self.conv
+    bias = c.bias if c.bias is not None else torch.zeros(c.out_channels, device=x.device, dtype=x.dtype)
+    return _ConvReLUContentTapFn.apply(x, c.weight, bias, content_feat, tuple(c.stride), tuple(c.padding),
+                                       tuple(c.dilation), c.groups)
+
+
+FusedConvReLU.forward_with_content_tap = _content_tap
 
 
 def fuse_vgg_features(features: nn.Sequential, channels_last: bool = True, fuse_pool: bool = True) -> nn.Sequential:

@@ -117,6 +117,8 @@ int st3d_interp_face_attrs_backward(const int64_t* pix_to_face, const float* bar
 #define ST3D_TEX_VERTEX 1
 #define ST3D_LAYOUT_NHWC_RGBA 0 /* (N,H,W,4), what renderer(...) returns (utils.py:69)              */
 #define ST3D_LAYOUT_PLANAR 1    /* (N,3,H,W) image + (N,1,H,W) mask, what render_meshes returns     */
+#define ST3D_LAYOUT_NHWC_RGB 2  /* (N,H,W,3) image + (N,1,H,W) mask: the same (N,3,H,W) tensor in torch channels_last
+                                   storage, what cuDNN's NHWC convolutions take without a layout copy        */
 #define ST3D_LIGHT_AMBIENT 0     /* AmbientLights (first_approach.py:108): colour = ambient * texel          */
 #define ST3D_LIGHT_POINT 1       /* PointLights: light_vec = location                                       */
 #define ST3D_LIGHT_DIRECTIONAL 2 /* DirectionalLights: light_vec = direction                                */
@@ -147,8 +149,8 @@ typedef struct st3d_render_args {
     float sigma, gamma;
     /* outputs */
     int out_layout;
-    float* out_image;       /* NHWC_RGBA: (N,H,W,4); PLANAR: (N,3,H,W) */
-    float* out_mask;        /* PLANAR only: (N,1,H,W) = (alpha > 0) */
+    float* out_image;       /* NHWC_RGBA: (N,H,W,4); PLANAR: (N,3,H,W); NHWC_RGB: (N,H,W,3) */
+    float* out_mask;        /* PLANAR / NHWC_RGB: (N,1,H,W) = (alpha > 0) */
     int32_t* pix_to_face;   /* (N,H,W) packed face index n*F+f or -1; saved for backward */
     /* scratch */
     void* workspace;        /* >= st3d_render_workspace_size(...) bytes; forward fills it, backward reads it */
@@ -185,7 +187,7 @@ int st3d_render_forward(const st3d_render_args* args, st3d_stream_t stream);
 
 /* Backward of st3d_render_forward (autograd of loss.backward(), first_approach.py:211 /
  * second_approach.py:188).  grad_image has the layout of out_image
- * (the alpha channel of NHWC_RGBA carries a gradient; the PLANAR mask does not).
+ * (the alpha channel of NHWC_RGBA carries a gradient; the PLANAR / NHWC_RGB mask does not).
  * grad_texture (Ht,Wt,3), grad_verts (V,3), grad_verts_rgb (V,3): accumulated (+=), may be NULL when
  * not required; the caller zero-fills. */
 int st3d_render_backward(const st3d_render_args* args, const float* grad_image, float* grad_texture,
@@ -251,6 +253,14 @@ int st3d_composite_backward(const float* grad_out, const float* mask, int64_t n,
  * elements: m[i] = mask[(i / (inner*mask_ch)) * inner + i % inner]  (mask (B,1,H,W) vs (B,3,H,W)). */
 int st3d_mse_forward(const float* a, const float* b, const float* mask, int64_t n, int64_t inner, int mask_ch,
                      float scale, float* loss_out, float* grad_a, st3d_stream_t stream);
+
+/* Backward of a tapped activation y = relu(conv(x)) whose tap is the content MSE of losses.py:31 against c:
+ * out[i] = y[i] > 0 ? grad_in[i] + 2 scale [* *scale_dev] (y[i] - c[i]) : 0 -- the MSE backward, its sum with the gradient
+ * that reached y through the rest of the network (grad_in, may be NULL) and the ReLU backward of that sum, in one pass.
+ * y, c, grad_in, out: n floats in the SAME element order (any dense layout), n % 4 == 0, 16-byte aligned; out may alias
+ * grad_in. */
+int st3d_mse_tap_backward(const float* y, const float* c, const float* grad_in, int64_t n, float scale,
+                          const float* scale_dev, float* out, st3d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * 2x2 / stride-2 max pooling of channels_last feature maps: the four MaxPool2d(2, 2) modules of the VGG-19

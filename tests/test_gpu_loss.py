@@ -445,3 +445,43 @@ def test_gram_backward_symmetric_dgram_skips_the_symmetrise_pass(C, H, W):
     want = torch.where(f64 > 0, want, torch.zeros_like(want))
     assert _relerr(fast, want) <= TOL_TC, _relerr(fast, want)
     assert _relerr(fast, general.double()) <= TOL_TC
+
+
+def test_content_tap_inside_its_conv_layer_equals_the_separate_passes():
+    """perceptual_loss_of_images evaluates the content tap (conv4_2, losses.py:31) inside its conv + ReLU layer: the MSE
+    backward, its sum with the gradient from deeper layers and the ReLU mask are one kernel (st3d_mse_tap_backward).
+    The op against torch, then the whole walk against get_features + perceptual_loss_from_features."""
+    import torchvision
+    ops = _ops()
+    from st3d import losses
+    from st3d.vgg import fuse_vgg_features
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    y = torch.relu(torch.randn(2, 64, 12, 10, device="cuda", generator=gen)).contiguous(memory_format=torch.channels_last)
+    c = torch.randn(2, 64, 12, 10, device="cuda", generator=gen).contiguous(memory_format=torch.channels_last)
+    g_in = torch.randn(2, 64, 12, 10, device="cuda", generator=gen).contiguous(memory_format=torch.channels_last)
+    s = torch.tensor([0.7], device="cuda")
+    got = ops.mse_tap_backward(y, c, g_in, 0.25, scale_tensor=s)
+    want = torch.ops.aten.threshold_backward(g_in + (2 * 0.25 * 0.7) * (y - c), y, 0.0)
+    assert got.stride() == y.stride() and torch.allclose(got, want, rtol=1e-6, atol=1e-7)
+    got0 = ops.mse_tap_backward(y, c, None, 0.25)
+    assert torch.allclose(got0, torch.ops.aten.threshold_backward(0.5 * (y - c), y, 0.0), rtol=1e-6, atol=1e-7)
+    with pytest.raises(ValueError):
+        ops.mse_tap_backward(y, c.contiguous(), g_in, 0.25)
+    # the walk
+    torch.manual_seed(2)
+    vgg = torchvision.models.vgg19(weights=None).features.eval().cuda()
+    for p in vgg.parameters():
+        p.requires_grad_(False)
+    model = fuse_vgg_features(vgg, channels_last=True)
+    x = torch.rand(2, 3, 64, 64, device="cuda").contiguous(memory_format=torch.channels_last)
+    style = torch.rand(1, 3, 64, 64, device="cuda")
+    with torch.no_grad():
+        content = losses.get_features(torch.rand_like(x), model, {"21": losses.CONTENT_LAYER})[losses.CONTENT_LAYER]
+    grams = losses.style_targets(style, model, "fp32")
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    la = losses.perceptual_loss_of_images(xa, model, content, grams, 1e3, 50.0, "fp32")       # content term dominant
+    lb = losses.perceptual_loss_from_features(losses.get_features(xb, model), content, grams, 1e3, 50.0, "fp32")
+    assert _relerr(la, lb) <= 1e-6
+    la.backward()
+    lb.backward()
+    assert _relerr(xa.grad, xb.grad) <= 1e-5, _relerr(xa.grad, xb.grad)

@@ -104,7 +104,7 @@ def test_render_forward_matches_golden(golden_dir, cow):
         _close(img, want, what="rgba")
 
 
-@pytest.mark.parametrize("layout", ["nhwc", "planar"])
+@pytest.mark.parametrize("layout", ["nhwc", "planar", "nhwc_rgb"])
 @pytest.mark.parametrize("mode", ["uv", "vertex"])
 def test_render_backward_matches_oracle_autograd(cow, layout, mode):
     ops = _ops()
@@ -121,25 +121,36 @@ def test_render_backward_matches_oracle_autograd(cow, layout, mode):
     # coverage must come from the fp32 positions: render_views rasterizes verts.float() exactly
     rgba = ro.render_views(verts64, cow["faces"], R, T, S, nthreads=8, **kw)
     wgt = torch.randn(N, S, S, 4, generator=gen).double()
-    if layout == "planar":
+    if layout != "nhwc":
         wgt[..., 3] = 0.0
     (rgba * wgt).sum().backward()
 
-    lay = ops.LAYOUT_NHWC_RGBA if layout == "nhwc" else ops.LAYOUT_PLANAR
+    lay = dict(nhwc=ops.LAYOUT_NHWC_RGBA, planar=ops.LAYOUT_PLANAR, nhwc_rgb=ops.LAYOUT_NHWC_RGB)[layout]
     spec = ops.RenderSpec(image_size=(S, S), k00=k00, k11=k11, layout=lay)
     gkw = dict(face_uvs=cow["verts_uvs"][cow["faces_uvs"]].cuda(), texture=tex.cuda()) if mode == "uv" \
         else dict(verts_rgb=vrgb.cuda())
     img, mask, p2f, state = ops.render_forward(spec, cow["verts"].cuda(), cow["faces"].cuda(), R.cuda(), T.cuda(), **gkw)
-    if layout == "planar":
+    if layout != "nhwc":
         want_img, want_mask = ro.images_and_masks(rgba.detach())
+        assert tuple(img.shape) == (N, 3, S, S)
         _close(img, want_img, what="planar image")
         assert torch.equal(mask.cpu().double(), want_mask)
         gimg = wgt[..., :3].permute(0, 3, 1, 2).contiguous().float().cuda()
+        if layout == "nhwc_rgb":
+            # the same (N,3,H,W) tensor in channels_last storage, and the gradient is taken in either storage order
+            assert img.is_contiguous(memory_format=torch.channels_last) and not img.is_contiguous()
+            g_nchw = ops.render_backward(state, gimg, need_texture=True, need_verts=True, need_verts_rgb=True)
+            gimg = gimg.contiguous(memory_format=torch.channels_last)
     else:
         _close(img, rgba, what="rgba")
         gimg = wgt.float().cuda()
     g_tex, g_verts, g_rgb = ops.render_backward(state, gimg, need_texture=True, need_verts=True, need_verts_rgb=True)
     torch.cuda.synchronize()
+    if layout == "nhwc_rgb":
+        for a, b in zip(g_nchw, (g_tex, g_verts, g_rgb)):
+            assert (a is None) == (b is None)
+            if a is not None:
+                _close(a, b, tol=1e-5, what="same gradient from an NCHW and a channels_last cotangent")
     if mode == "uv":
         _close(g_tex, tex64.grad, what="grad_texture")
         assert g_rgb is None
@@ -373,11 +384,11 @@ def test_near_plane_clipping_fused_matches_oracle(cow, layout, mode):
         else dict(verts_rgb=vrgb64)
     rgba, frag = ro.render_views(verts64, cow["faces"], R, T, S, nthreads=8, return_fragments=True, **kw)
     wgt = torch.randn(N, S, S, 4, generator=gen).double()
-    if layout == "planar":
+    if layout != "nhwc":
         wgt[..., 3] = 0.0
     (rgba * wgt).sum().backward()
 
-    lay = ops.LAYOUT_NHWC_RGBA if layout == "nhwc" else ops.LAYOUT_PLANAR
+    lay = dict(nhwc=ops.LAYOUT_NHWC_RGBA, planar=ops.LAYOUT_PLANAR, nhwc_rgb=ops.LAYOUT_NHWC_RGB)[layout]
     spec = ops.RenderSpec(image_size=(S, S), k00=k00, k11=k11, layout=lay)
     gkw = dict(face_uvs=cow["verts_uvs"][cow["faces_uvs"]].cuda(), texture=tex.cuda()) if mode == "uv" \
         else dict(verts_rgb=vrgb.cuda())
@@ -387,16 +398,27 @@ def test_near_plane_clipping_fused_matches_oracle(cow, layout, mode):
     want_p2f = frag["pix_to_face"][..., 0]
     assert (want_p2f >= 0).float().mean() > 0.3
     assert torch.equal(p2f.cpu().long(), want_p2f), "pix_to_face differs from the oracle on a clipped scene"
-    if layout == "planar":
+    if layout != "nhwc":
         want_img, want_mask = ro.images_and_masks(rgba.detach())
+        assert tuple(img.shape) == (N, 3, S, S)
         _close(img, want_img, what="planar image")
         assert torch.equal(mask.cpu().double(), want_mask)
         gimg = wgt[..., :3].permute(0, 3, 1, 2).contiguous().float().cuda()
+        if layout == "nhwc_rgb":
+            # the same (N,3,H,W) tensor in channels_last storage, and the gradient is taken in either storage order
+            assert img.is_contiguous(memory_format=torch.channels_last) and not img.is_contiguous()
+            g_nchw = ops.render_backward(state, gimg, need_texture=True, need_verts=True, need_verts_rgb=True)
+            gimg = gimg.contiguous(memory_format=torch.channels_last)
     else:
         _close(img, rgba, what="rgba")
         gimg = wgt.float().cuda()
     g_tex, g_verts, g_rgb = ops.render_backward(state, gimg, need_texture=True, need_verts=True, need_verts_rgb=True)
     torch.cuda.synchronize()
+    if layout == "nhwc_rgb":
+        for a, b in zip(g_nchw, (g_tex, g_verts, g_rgb)):
+            assert (a is None) == (b is None)
+            if a is not None:
+                _close(a, b, tol=1e-5, what="same gradient from an NCHW and a channels_last cotangent")
     if mode == "uv":
         _close(g_tex, tex64.grad, what="grad_texture")
     else:
