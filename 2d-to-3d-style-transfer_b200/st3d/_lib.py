@@ -36,6 +36,14 @@ class RenderArgs(ctypes.Structure):
     ]
 
 
+class MeshRegArgs(ctypes.Structure):
+    """Mirror of `struct st3d_mesh_reg_args` (include/st3d.h)."""
+    _fields_ = [
+        ("verts", c_p), ("V", c_i64), ("edges", c_p), ("E", c_i64), ("adj_ptr", c_p), ("adj_idx", c_p),
+        ("pairs", c_p), ("P", c_i64), ("target_length", c_f), ("which", c_i), ("lap_dir", c_p),
+    ]
+
+
 # name -> (restype, argtypes): every symbol include/st3d.h declares
 SIGNATURES = {
     "st3d_last_error": (ctypes.c_char_p, []),
@@ -60,6 +68,9 @@ SIGNATURES = {
     "st3d_composite_backward": (c_i, [c_p, c_p, c_i64, c_i64, c_i, c_p, c_p]),
     "st3d_mse_forward": (c_i, [c_p, c_p, c_p, c_i64, c_i64, c_i, c_f, c_p, c_p, c_p]),
     "st3d_mse_tap_backward": (c_i, [c_p, c_p, c_p, c_i64, c_f, c_p, c_p, c_p]),
+    "st3d_mesh_regularizers_workspace_size": (c_i64, []),
+    "st3d_mesh_regularizers_forward": (c_i, [c_p, c_p, c_p, c_p]),
+    "st3d_mesh_regularizers_backward": (c_i, [c_p, c_p, c_p, c_p]),
     "st3d_maxpool2x2_forward": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
     "st3d_maxpool2x2_backward": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
 }

@@ -636,6 +636,66 @@ def mse_tap_backward(y, c, grad_in, scale: float, scale_tensor=None):
 
 
 # ------------------------------------------------------------------------------------------------
+# mesh regularisers (losses.py:85-87): one forward and one backward launch over cached topology tables
+# ------------------------------------------------------------------------------------------------
+MESH_EDGE, MESH_LAPLACIAN, MESH_NORMAL = 1, 2, 4
+_mesh_reg_ws: dict = {}
+
+
+def _mesh_reg_args(verts, topo, target_length, which, lap_dir):
+    from ._lib import MeshRegArgs
+    a = MeshRegArgs()
+    a.verts, a.V = verts.data_ptr(), verts.shape[0]
+    a.edges, a.E = topo.edges.data_ptr(), topo.edges.shape[0]
+    a.adj_ptr, a.adj_idx = topo.adj_ptr.data_ptr(), topo.adj_idx.data_ptr()
+    a.pairs, a.P = topo.pairs.data_ptr(), topo.pairs.shape[0]
+    a.target_length, a.which = float(target_length), int(which)
+    a.lap_dir = lap_dir.data_ptr()
+    return a
+
+
+def _check_topology(verts, topo):
+    V, dev = verts.shape[0], verts.device
+    for name in ("edges", "adj_ptr", "adj_idx", "pairs"):
+        t = getattr(topo, name)
+        if not (t.is_cuda and t.device == dev and t.dtype == torch.int32 and t.is_contiguous()):
+            raise ValueError(f"mesh topology: {name} must be a contiguous int32 tensor on {dev}")
+    if topo.num_verts != V or topo.adj_ptr.shape[0] != V + 1 or topo.adj_idx.shape[0] != 2 * topo.edges.shape[0]:
+        raise ValueError("mesh topology: tables were built for another vertex count")
+
+
+@_on_device_of
+def mesh_regularizers_forward(verts, topo, target_length: float = 0.0, which: int = 7):
+    """-> (losses (3,) [edge, laplacian, normal consistency], state for the backward).  `topo`: st3d.mesh_losses.topology."""
+    verts = _cuda_f32("verts", verts, 3)
+    _check_topology(verts, topo)
+    dev = verts.device
+    ws = _mesh_reg_ws.get(dev)
+    if ws is None:      # 32 bytes, zero once: every launch leaves it zero
+        ws = _mesh_reg_ws[dev] = torch.zeros(int(lib().st3d_mesh_regularizers_workspace_size()) // 8, device=dev,
+                                             dtype=torch.float64)
+    losses = torch.empty(3, device=dev, dtype=torch.float32)
+    lap_dir = torch.empty_like(verts)
+    a = _mesh_reg_args(verts, topo, target_length, which, lap_dir)
+    with _timed("mesh_regularizers_forward", (verts.shape[0], topo.edges.shape[0], topo.pairs.shape[0])):
+        check(lib().st3d_mesh_regularizers_forward(ctypes.byref(a), _p(ws), _p(losses), _stream()),
+              "st3d_mesh_regularizers_forward")
+    return losses, (verts, topo, float(target_length), int(which), lap_dir)
+
+
+@_on_device_of
+def mesh_regularizers_backward(state, grad_losses):
+    verts, topo, target_length, which, lap_dir = state
+    grad_losses = _cuda_f32("grad_losses", grad_losses, 3)
+    grad = torch.empty_like(verts)
+    a = _mesh_reg_args(verts, topo, target_length, which, lap_dir)
+    with _timed("mesh_regularizers_backward", (verts.shape[0], topo.edges.shape[0], topo.pairs.shape[0])):
+        check(lib().st3d_mesh_regularizers_backward(ctypes.byref(a), _p(grad_losses), _p(grad), _stream()),
+              "st3d_mesh_regularizers_backward")
+    return grad
+
+
+# ------------------------------------------------------------------------------------------------
 # 2x2 max pooling of channels_last feature maps (VGG-19 pools; the convolutions stay on cuDNN)
 # ------------------------------------------------------------------------------------------------
 def maxpool_supported(x: torch.Tensor) -> bool:

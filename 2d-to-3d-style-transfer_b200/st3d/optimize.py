@@ -147,7 +147,7 @@ class StyleOptimizer:
         self._cache = {}
         self._copy_stream = None
         self.images_ready: Optional[torch.cuda.Event] = None
-        self._edges = None
+        self._mesh_tables = None
         self.last_images: Optional[torch.Tensor] = None
         self._eager_steps = 0
         self._captured: Optional[CapturedIteration] = None
@@ -181,14 +181,17 @@ class StyleOptimizer:
         return images, masks
 
     def _regularisers(self):
+        """losses.py:85-87 / 113-115: the vertex MSE plus the three mesh regularisers -- the latter from ONE libst3d
+        launch (and one for their backward) over topology tables built once (st3d/mesh_losses.py)."""
         from . import mesh_losses as ml
-        if self._edges is None:
-            self._edges = ml.unique_edges(self.faces)
-        w = self.weights
-        return (w["mesh_verts_weight"] * Fn.mse_loss(self.verts, self.verts0)
-                + w["mesh_edge_loss_weight"] * ml.edge_loss(self.verts, self.faces, edges=self._edges)
-                + w["mesh_laplacian_smoothing_weight"] * ml.laplacian_smoothing(self.verts, self.faces, edges=self._edges)
-                + w["mesh_normal_consistency_weight"] * ml.normal_consistency(self.verts, self.faces))
+        if self._mesh_tables is None:
+            w = self.weights
+            self._mesh_tables = (ml.topology(self.faces, self.verts.shape[0]),
+                           torch.tensor([w["mesh_edge_loss_weight"], w["mesh_laplacian_smoothing_weight"],
+                                         w["mesh_normal_consistency_weight"]], device=self.verts.device))
+        topo, w3 = self._mesh_tables
+        return (self.weights["mesh_verts_weight"] * Fn.mse_loss(self.verts, self.verts0)
+                + torch.dot(ml.regularizers(self.verts, self.faces, 0.0, 7, topo=topo), w3))
 
     # ---- cache of the loop constants (content feature, style Grams): keyed on CONTENT, never on addresses ----------
     # The caching allocator hands the address of a freed per-batch temporary (R[idx].to(dev), the reference's own

@@ -263,6 +263,45 @@ int st3d_mse_tap_backward(const float* y, const float* c, const float* grad_in, 
                           const float* scale_dev, float* out, st3d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Mesh regularisers of the `mesh` / `both` targets: pytorch3d.loss.mesh_edge_loss(meshes, target_length),
+ * mesh_laplacian_smoothing(meshes, method="uniform") and mesh_normal_consistency(meshes) as the reference calls them
+ * (losses.py:85-87, 113-115), for ONE mesh, in one forward and one backward
+ * launch.  The topology tables depend on the faces only and are built once by the caller:
+ *   edges   (E,2) int32  unique undirected edges
+ *   adj_ptr (V+1) int32, adj_idx (2E) int32  CSR neighbour lists of the edge graph (deg_i = adj_ptr[i+1] - adj_ptr[i])
+ *   pairs   (P,4) int32  one row (v0, v1, a, b) per unordered pair of faces sharing the edge (v0, v1), a / b the vertex of
+ *                        either face opposite to it; an edge shared by k faces gives k (k-1) / 2 rows; 16-byte aligned
+ * losses[3] = { mean_e (|v_a - v_b| - target_length)^2,  mean_i |sum_{j in N(i)} v_j / deg_i - v_i|,
+ *               mean_p 1 - cos((v1-v0) x (a-v0), -(v1-v0) x (b-v0)) }; entries not selected by `which`, and means over
+ * empty sets, are 0.  workspace: st3d_mesh_regularizers_workspace_size() bytes, zero before the FIRST call (every call
+ * leaves it zero).  lap_dir (V,3) is written by the forward and read by the backward (Laplacian term only).
+ * Backward: grad_verts (V,3) is overwritten with sum_k grad_losses[k] dlosses[k]/dverts (grad_losses: 3 floats on the
+ * device, so an autograd backward needs no host read).
+ * ---------------------------------------------------------------------------------------------- */
+#define ST3D_MESH_EDGE 1
+#define ST3D_MESH_LAPLACIAN 2
+#define ST3D_MESH_NORMAL 4
+
+typedef struct st3d_mesh_reg_args {
+    const float* verts;     /* (V,3) */
+    int64_t V;
+    const int32_t* edges;   /* (E,2) */
+    int64_t E;
+    const int32_t* adj_ptr; /* (V+1) */
+    const int32_t* adj_idx; /* (2E) */
+    const int32_t* pairs;   /* (P,4) */
+    int64_t P;
+    float target_length;    /* mesh_edge_loss's target_length (the reference leaves it at 0) */
+    int which;              /* ST3D_MESH_EDGE | ST3D_MESH_LAPLACIAN | ST3D_MESH_NORMAL */
+    float* lap_dir;         /* (V,3) */
+} st3d_mesh_reg_args;
+
+int64_t st3d_mesh_regularizers_workspace_size(void);
+int st3d_mesh_regularizers_forward(const st3d_mesh_reg_args* args, void* workspace, float* losses, st3d_stream_t stream);
+int st3d_mesh_regularizers_backward(const st3d_mesh_reg_args* args, const float* grad_losses, float* grad_verts,
+                                    st3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * 2x2 / stride-2 max pooling of channels_last feature maps: the four MaxPool2d(2, 2) modules of the VGG-19
  * `.features` that utils.py:49 builds and get_features (style_transfer.py:21-26) walks.  The convolutions
  * around them stay on cuDNN; the pools are pure HBM traffic.

@@ -485,3 +485,81 @@ def test_content_tap_inside_its_conv_layer_equals_the_separate_passes():
     la.backward()
     lb.backward()
     assert _relerr(xa.grad, xb.grad) <= 1e-5, _relerr(xa.grad, xb.grad)
+
+
+def _mesh_npz(golden_dir, name):
+    d = np.load(os.path.join(golden_dir, f"{name}_mesh.npz"))
+    return torch.from_numpy(d["verts"]).float(), torch.from_numpy(d["faces"]).long()
+
+
+@pytest.mark.parametrize("name", ["cow", "bob", "teapot"])
+def test_fused_mesh_regularisers_match_the_oracle(golden_dir, name):
+    """losses.py:85-87 (pytorch3d.loss.mesh_edge_loss / mesh_laplacian_smoothing / mesh_normal_consistency): values and
+    vertex gradients of the one-launch CUDA op against the float64 oracle on the three meshes of the configs, a few
+    steps into an optimisation (perturbed vertices).  fp32 sums of ~10^4 terms: 2e-5 on values, 2e-4 of the largest
+    gradient entry on gradients."""
+    from st3d import mesh_losses as ml
+    verts, faces = _mesh_npz(golden_dir, name)
+    g = torch.Generator().manual_seed(5)
+    verts = verts + 2e-3 * torch.randn(verts.shape, generator=g)
+    w = torch.tensor([1.0, 0.7, 0.3], dtype=torch.float64)
+    v64 = verts.double().requires_grad_(True)
+    want = torch.stack([lo.mesh_edge_loss(v64, faces), lo.mesh_laplacian_smoothing(v64, faces),
+                        lo.mesh_normal_consistency(v64, faces)])
+    (want * w).sum().backward()
+    vc = verts.cuda().requires_grad_(True)
+    fc = faces.cuda()
+    got = ml.regularizers(vc, fc)
+    (got * w.float().cuda()).sum().backward()
+    assert torch.allclose(got.detach().cpu().double(), want.detach(), rtol=2e-5, atol=1e-9), (got, want)
+    err = (vc.grad.cpu().double() - v64.grad).abs().max().item()
+    assert err <= 2e-4 * v64.grad.abs().max().item(), err
+    # the three pytorch3d.loss entry points select one term each, and the target length reaches the kernel
+    for k, fn in enumerate((ml.edge_loss, ml.laplacian_smoothing, ml.normal_consistency)):
+        assert torch.allclose(fn(vc, fc).detach(), got[k].detach(), rtol=1e-6, atol=1e-12)
+    t = 0.01
+    vt = verts.cuda().requires_grad_(True)
+    ml.edge_loss(vt, fc, t).backward()
+    v64b = verts.double().requires_grad_(True)
+    want_t = lo.mesh_edge_loss(v64b, faces, t)
+    want_t.backward()
+    assert abs(ml.edge_loss(vc, fc, t).item() - want_t.item()) <= 2e-5 * abs(want_t.item())
+    assert (vt.grad.cpu().double() - v64b.grad).abs().max().item() <= 2e-4 * v64b.grad.abs().max().item()
+    # the workspace is left zero: a second call gives the same bits
+    assert torch.equal(ml.regularizers(vc, fc).detach(), got.detach())
+
+
+def test_fused_mesh_regularisers_edge_cases():
+    """Empty face list, isolated vertices, an edge shared by three faces (three pairs), a zero-length edge and a
+    zero-area face (clamped cosine, zero sub-gradient of the norm): same values and gradients as the oracle."""
+    from st3d import mesh_losses as ml
+    dev = torch.device("cuda")
+    v = torch.rand(5, 3, device=dev, requires_grad=True)
+    out = ml.regularizers(v, torch.zeros((0, 3), dtype=torch.long, device=dev))
+    assert torch.equal(out.detach().cpu(), torch.zeros(3))
+    out.sum().backward()
+    assert torch.equal(v.grad.cpu(), torch.zeros(5, 3))
+    g = torch.Generator().manual_seed(2)
+    faces = torch.tensor([[0, 1, 2], [0, 1, 3], [1, 0, 4], [0, 5, 1]])   # (0,1) shared by 4 faces; vertex 6 isolated
+    topo = ml.topology(faces.cuda(), 7)
+    assert topo.pairs.shape[0] == 6 and topo.edges.shape[0] == 9 and int(topo.adj_ptr[-1]) == 18
+    assert int(topo.adj_ptr[7] - topo.adj_ptr[6]) == 0
+    w = torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64)
+    for degenerate in (False, True):
+        verts = torch.rand(7, 3, generator=g)
+        if degenerate:
+            verts[5] = verts[0]                                # edge (0,5) has length 0; face (0,5,1) has area 0
+        v64 = verts.double().requires_grad_(True)
+        want = torch.stack([lo.mesh_edge_loss(v64, faces), lo.mesh_laplacian_smoothing(v64, faces),
+                            lo.mesh_normal_consistency(v64, faces)])
+        (want * w).sum().backward()
+        vc = verts.cuda().requires_grad_(True)
+        got = ml.regularizers(vc, faces.cuda())
+        (got * w.float().cuda()).sum().backward()
+        assert torch.allclose(got.detach().cpu().double(), want.detach(), rtol=1e-5, atol=1e-7), (got, want)
+        assert torch.isfinite(vc.grad).all()
+        if not degenerate:      # (a zero normal clamped to eps = 1e-8 makes the reference's own gradient ~1e8: not compared)
+            assert torch.allclose(vc.grad.cpu().double(), v64.grad, rtol=1e-3, atol=1e-5), \
+                (vc.grad.cpu().double() - v64.grad).abs().max()
+    with pytest.raises(ValueError):
+        ml.regularizers(verts, faces)                           # CPU tensors: no library path

@@ -234,3 +234,32 @@ def test_bench_reference_arm_prints_one_json_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["views_per_step"] == 2 and "FULL iterations" in cb["sample"]
     assert out["e2e"] == {"value": out["value"], "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert out["config"]["global_views"] == 2 and out["config"]["workload"].startswith("cow_mesh")
+
+
+def test_mesh_topology_tables():
+    """The tables `st3d_mesh_regularizers_*` walk (include/st3d.h), built by st3d.mesh_losses.topology on the host:
+    unique edges, CSR neighbour lists, one row per pair of faces sharing an edge (k faces -> k (k-1) / 2 rows)."""
+    import torch
+    from st3d import mesh_losses as ml
+    tet = torch.tensor([[0, 1, 2], [0, 3, 1], [0, 2, 3], [1, 3, 2]])
+    t = ml.topology(tet, 4)
+    assert t.edges.dtype == torch.int32 and t.edges.tolist() == [[0, 1], [0, 2], [0, 3], [1, 2], [1, 3], [2, 3]]
+    assert t.adj_ptr.tolist() == [0, 3, 6, 9, 12]
+    assert [sorted(t.adj_idx[3 * i:3 * i + 3].tolist()) for i in range(4)] == [[1, 2, 3], [0, 2, 3], [0, 1, 3], [0, 1, 2]]
+    assert t.pairs.shape == (6, 4)
+    for v0, v1, a, b in t.pairs.tolist():                       # the four vertices of a tetrahedron, edge first
+        assert v0 < v1 and sorted([v0, v1, a, b]) == [0, 1, 2, 3]
+    fan = torch.tensor([[0, 1, 2], [0, 1, 3], [1, 0, 4]])       # three faces around the edge (0, 1); vertex 5 unused
+    t = ml.topology(fan, 6)
+    assert t.pairs.shape == (3, 4) and all(r[:2] == [0, 1] for r in t.pairs.tolist())
+    assert sorted(tuple(sorted(r[2:])) for r in t.pairs.tolist()) == [(2, 3), (2, 4), (3, 4)]
+    assert t.adj_ptr.tolist() == [0, 4, 8, 10, 12, 14, 14] and t.adj_idx.shape[0] == 2 * t.edges.shape[0] == 14
+    empty = ml.topology(torch.zeros((0, 3), dtype=torch.long), 3)
+    assert empty.edges.shape == (0, 2) and empty.pairs.shape == (0, 4) and empty.adj_ptr.tolist() == [0, 0, 0, 0]
+    # the cache follows the storage and the version of the face tensor, not the Python object
+    faces = tet.clone()
+    a = ml._cached(faces, 4)
+    assert ml._cached(faces.detach(), 4) is a
+    faces[0, 0] = 0
+    faces.add_(0)
+    assert ml._cached(faces, 4) is not a
