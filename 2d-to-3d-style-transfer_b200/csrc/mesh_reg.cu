@@ -190,6 +190,9 @@ static int check_tables(const st3d_mesh_reg_args* a, const char* op) {
     return ST3D_OK;
 }
 
+// upstream returns 0 for a mesh without faces before it looks at the vertices: no edges, no Laplacian term
+static int terms_of(const st3d_mesh_reg_args* a) { return a->E == 0 ? (a->which & ~ST3D_MESH_LAPLACIAN) : a->which; }
+
 static int grid_for(const st3d_mesh_reg_args* a) {
     int64_t m = 1;
     if (a->which & ST3D_MESH_EDGE) m = std::max(m, a->E);
@@ -210,7 +213,7 @@ extern "C" int st3d_mesh_regularizers_forward(const st3d_mesh_reg_args* a, void*
     ST3D_REQUIRE(workspace && losses, "mesh_regularizers_forward: null workspace / losses");
     ST3D_REQUIRE((((uintptr_t)workspace) & 7) == 0, "mesh_regularizers_forward: workspace must be 8-byte aligned");
     k_mesh_reg_fwd<<<grid_for(a), 256, 0, (cudaStream_t)stream>>>(a->verts, a->V, a->edges, a->E, a->adj_ptr, a->adj_idx,
-                                                                  a->pairs, a->P, a->target_length, a->which,
+                                                                  a->pairs, a->P, a->target_length, terms_of(a),
                                                                   (MeshRegWs*)workspace, losses, a->lap_dir);
     ST3D_LAUNCH_OK("k_mesh_reg_fwd");
     return ST3D_OK;
@@ -223,7 +226,7 @@ extern "C" int st3d_mesh_regularizers_backward(const st3d_mesh_reg_args* a, cons
     ST3D_REQUIRE(grad_losses && grad_verts, "mesh_regularizers_backward: null pointer");
     ST3D_CUDA_OK(cudaMemsetAsync(grad_verts, 0, sizeof(float) * 3 * (size_t)a->V, (cudaStream_t)stream));
     k_mesh_reg_bwd<<<grid_for(a), 256, 0, (cudaStream_t)stream>>>(a->verts, a->V, a->edges, a->E, a->adj_ptr, a->adj_idx,
-                                                                  a->pairs, a->P, a->target_length, a->which, grad_losses,
+                                                                  a->pairs, a->P, a->target_length, terms_of(a), grad_losses,
                                                                   a->lap_dir, grad_verts);
     ST3D_LAUNCH_OK("k_mesh_reg_bwd");
     return ST3D_OK;

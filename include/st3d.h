@@ -273,7 +273,8 @@ int st3d_mse_tap_backward(const float* y, const float* c, const float* grad_in, 
  *                        either face opposite to it; an edge shared by k faces gives k (k-1) / 2 rows; 16-byte aligned
  * losses[3] = { mean_e (|v_a - v_b| - target_length)^2,  mean_i |sum_{j in N(i)} v_j / deg_i - v_i|,
  *               mean_p 1 - cos((v1-v0) x (a-v0), -(v1-v0) x (b-v0)) }; entries not selected by `which`, and means over
- * empty sets, are 0.  workspace: st3d_mesh_regularizers_workspace_size() bytes, zero before the FIRST call (every call
+ * empty sets, are 0 -- all three for a mesh without faces (E == 0), as upstream's isempty() early return; an isolated
+ * vertex of a mesh WITH faces contributes |v_i| to the Laplacian term (deg^-1 := 0).  workspace: st3d_mesh_regularizers_workspace_size() bytes, zero before the FIRST call (every call
  * leaves it zero).  lap_dir (V,3) is written by the forward and read by the backward (Laplacian term only).
  * Backward: grad_verts (V,3) is overwritten with sum_k grad_losses[k] dlosses[k]/dverts (grad_losses: 3 floats on the
  * device, so an autograd backward needs no host read).
