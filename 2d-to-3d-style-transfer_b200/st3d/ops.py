@@ -144,8 +144,46 @@ def read_header(ws: torch.Tensor):
     return int(h[0]) + int(h[6]), int(h[1]), int(h[4])
 
 
+_captured_headers: Optional[list] = None     # set by `collect_captured_headers` while a graph is being recorded
+
+
+class collect_captured_headers:
+    """Context manager for the owner of a CUDA graph: every raster call recorded inside also records a copy of its
+    workspace header to a pinned host buffer; `.headers` lists them as (host int32 tensor, capacity key).  Each replay
+    refreshes the buffers, `check_captured_headers` reads them (after the replay has finished)."""
+
+    def __enter__(self):
+        global _captured_headers
+        self.headers = _captured_headers = []
+        return self
+
+    def __exit__(self, *exc):
+        global _captured_headers
+        _captured_headers = None
+        return False
+
+
+def check_captured_headers(headers) -> None:
+    """Raise if a raster call of the LAST finished replay overflowed its work lists or met a case it does not handle
+    (the caller has waited for that replay)."""
+    for host, key in headers:
+        needed, overflow, clip = int(host[0]) + int(host[6]), int(host[1]), int(host[4])
+        _capacity_hint[key] = max(_capacity_hint.get(key, 0), needed)
+        if clip:
+            raise NotImplementedError("a replayed render met a face crossing the near clipping plane with blur_radius > 0: "
+                                      "the fused renderer clips faces only when blur_radius == 0")
+        if overflow:
+            raise St3dError(f"a replayed render needed {needed} work-list entries, more than the workspace recorded in "
+                            "the graph holds (the mesh moved too far from the one that was captured); the results of that "
+                            "replay are invalid. Capture again: the capacity hint has been raised.")
+
+
 def _watch_header(ws: torch.Tensor, key) -> None:
-    if _capturing():        # a captured call is replayed without Python: its owner checks the header (read_header)
+    if _capturing():        # a captured call is replayed without Python: its owner checks the header
+        if _captured_headers is not None:
+            host = torch.empty(WS_HEADER_INTS, dtype=torch.int32, pin_memory=True)
+            host.copy_(ws[: WS_HEADER_INTS * 4].view(torch.int32), non_blocking=True)
+            _captured_headers.append((host, key))
         return
     host = _free_hosts.pop() if _free_hosts else torch.empty(WS_HEADER_INTS, dtype=torch.int32, pin_memory=True)
     host.copy_(ws[: WS_HEADER_INTS * 4].view(torch.int32), non_blocking=True)

@@ -56,15 +56,29 @@ class CapturedIteration:
         torch.cuda.synchronize(self.device)
         ops.poll_overflow(block=True)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with ops.collect_captured_headers() as collected, torch.cuda.graph(self.graph):
             self.out = fn()
+        self.headers = collected.headers        # pinned copies of the raster workspace headers, refreshed by every replay
         self.replays = 0
+        self._replayed = None
 
     def replay(self):
         """Runs the recorded iteration; returns fn's (static) outputs, overwritten by the next replay."""
         self.graph.replay()
         self.replays += 1
+        if self.headers:
+            self._replayed = torch.cuda.Event()
+            self._replayed.record(torch.cuda.current_stream(self.device))
         return self.out
+
+    def check(self) -> None:
+        """Waits for the last replay and raises if one of its renders overflowed the work lists recorded in the graph
+        (geometry that moves between replays: the sizes seen when the graph was recorded are not guaranteed)."""
+        if self._replayed is not None:
+            from . import ops
+            self._replayed.synchronize()
+            self._replayed = None
+            ops.check_captured_headers(self.headers)
 
 
 DEFAULT_WEIGHTS = {"main_loss_weight": 3.0, "mesh_verts_weight": 1.0, "mesh_edge_loss_weight": 1.0,
@@ -311,7 +325,7 @@ class StyleOptimizer:
         views to `images_out`) as ONE CUDA graph over the STATIC tensors R, T, style_img: new cameras or a new style
         image are copied INTO them before `step_captured()`.  The warm-up runs `warmup` real iterations.  What stays
         outside the graph is what involves other ranks or the host: the NCCL all-reduce, the regularisers that overlap
-        it, and the Adam step."""
+        it (two launches, csrc/mesh_reg.cu), and the Adam step.  All three targets can be captured."""
         if self._eager_steps:
             # the leaves' gradient accumulators were bound to the stream the eager steps ran on (normally the legacy
             # default stream); autograd would make that stream wait on the capturing one, which CUDA refuses
@@ -321,10 +335,9 @@ class StyleOptimizer:
             # into the static tensors would then meet the old content feature without any error
             raise ValueError("capture() records the whole iteration, constants included: build the optimiser with "
                              "cache_constants=False")
-        if self.target != "texture":
-            # a moving mesh changes the sizes of the rasterizer's work lists from step to step; their overflow check is
-            # a host read the replayed graph cannot make.  With fixed geometry the sizes seen in the warm-up hold.
-            raise NotImplementedError("capture() records the `texture` target only (fixed geometry)")
+        # `mesh` / `both`: a moving mesh changes the sizes of the rasterizer's work lists from step to step.  The graph
+        # records a copy of every workspace header to pinned memory; step_captured() reads the copies of the previous
+        # replay (work lists are sized at twice what the warm-up needed) and raises if one overflowed.
 
         def grads():
             return self._accumulate_gradients(R, T, style_img, images_out, micro_batch)
@@ -347,6 +360,8 @@ class StyleOptimizer:
         """Replays the captured gradient computation, then all-reduce / regularisers / Adam; returns the loss."""
         if self._captured is None:
             raise RuntimeError("call capture(R, T, style_img) first")
+        if self.target != "texture":
+            self._captured.check()      # the previous replay (its regularisers / Adam tail is still queued behind it)
         loss = self._captured.replay()
         return self._reduce_and_update(loss)
 

@@ -598,6 +598,44 @@ def test_captured_style_step_equals_the_eager_step(cow):
     assert abs(a - b) <= 1e-3 * abs(b), (a, b)
 
 
+@pytest.mark.parametrize("target", ["both", "mesh"])
+def test_captured_step_of_a_moving_mesh_equals_the_eager_step(cow, target):
+    """capture() of the `mesh` / `both` targets (second_approach.py:140-190 with a moving mesh): the replayed iteration
+    follows the eager one, and the graph owner sees the rasterizer's work-list headers of every replay."""
+    from st3d.optimize import StyleOptimizer
+    dev = torch.device("cuda:0")
+    R, T = ro.random_cameras(2, generator=torch.Generator().manual_seed(191))
+    style = torch.rand(1, 3, S, S, generator=torch.Generator().manual_seed(192)).to(dev)
+    tex0 = torch.rand(S, S, 3, generator=torch.Generator().manual_seed(193))
+    vgg = _vgg(dev)
+
+    def fresh():
+        return StyleOptimizer(cow["verts"].to(dev), cow["faces"].to(dev), vgg, S, target=target, weights=WEIGHTS, lr=1e-4,
+                              verts_uvs=cow["verts_uvs"].to(dev), faces_uvs=cow["faces_uvs"].to(dev), texture=tex0.to(dev))
+    Rd, Td = R.to(dev), T.to(dev)
+    eager = fresh()
+    want = [eager.step(Rd, Td, style).item() for _ in range(6)]
+    cap = fresh()
+    cap.capture(Rd, Td, style, warmup=3)
+    got = [cap.step_captured().item() for _ in range(3)]
+    cap._captured.check()
+    assert len(cap._captured.headers) == 2                       # content render + current render
+    assert all(int(h[1]) == 0 and int(h[0]) + int(h[6]) > 0 for h, _ in cap._captured.headers)
+    for g, w in zip(got, want[3:]):
+        assert abs(g - w) <= 2e-3 * abs(w), (got, want)
+    # Adam's first steps are +-lr per entry whatever the gradient's size: an entry whose gradient is rounding noise may
+    # step the other way (atomics order), so bound the mean tightly and the maximum by the six steps taken
+    dv = (cap.verts.detach() - eager.verts.detach()).abs()
+    assert dv.mean().item() <= 2e-5 and dv.max().item() <= 1.3e-3, (dv.mean().item(), dv.max().item())
+    assert (cap.verts.detach() - cow["verts"].to(dev)).abs().max().item() > 0      # the mesh did move
+    # an overflow reported by a replay reaches the caller of the next step
+    cap._captured.headers[0][0][1] = 1
+    cap._captured._replayed = torch.cuda.Event()
+    cap._captured._replayed.record()
+    with pytest.raises(RuntimeError, match="work-list"):
+        cap.step_captured()
+
+
 def test_batch_of_meshes_renders_mesh_i_with_camera_i(cow):
     """Meshes with M > 1 entries (upstream pairs mesh i with camera i): the renderer walks the meshes, one launch sequence
     each; RGBA equals the per-mesh renders, and the rasterizer's pix_to_face indexes the PACKED faces of the batch."""
