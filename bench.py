@@ -614,6 +614,75 @@ def nst_2d_loop(dev, vgg, size=512, batch=4, steps=50):
     return out
 
 
+def c3_both_target(dev, vgg, precision, views=4, size=512, steps=20):
+    """BASELINE configs[2], one rank's share: bob (10 688 faces, the stand-in for the missing bunny.obj), target `both`
+    (texture + vertices, second_approach.py:140-190 with losses.py:101-126: perceptual loss x main_loss_weight + vertex MSE
+    + edge / Laplacian / normal-consistency regularisers), `views` views x `size`^2.  One iteration launched from Python
+    against the same iteration with its gradient computation replayed from one CUDA graph; CUDA events.  The regularisers
+    are one libst3d forward and one backward launch (csrc/mesh_reg.cu); `regularisers_torch_ms` times the ~80-launch
+    torch formulation of the same three terms beside them."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    from st3d import mesh_losses as ml
+    from st3d.optimize import StyleOptimizer
+    d = np.load(os.path.join(ROOT, "tests", "golden", "bob_mesh.npz"))
+    verts, faces = torch.from_numpy(d["verts"]).float().to(dev), torch.from_numpy(d["faces"]).long().to(dev)
+    uvs, fuvs = torch.from_numpy(d["verts_uvs"]).float().to(dev), torch.from_numpy(d["faces_uvs"]).long().to(dev)
+    tex = torch.from_numpy(d["texture"]).float() / 255.0
+    tex = F.interpolate(tex.permute(2, 0, 1)[None], size=(size, size), mode="bilinear", align_corners=False)[0]
+    tex = tex.permute(1, 2, 0).contiguous().to(dev)
+    R, T = cameras(views)
+    R, T, style = R.to(dev), T.to(dev), style_image(size).to(dev)
+    out = {"workload": f"bob_mesh `both` target, {views} views x {size}^2 (BASELINE configs[2], one rank of 8), {steps} steps"}
+
+    def fresh():
+        return StyleOptimizer(verts, faces, vgg, size, verts_uvs=uvs, faces_uvs=fuvs, texture=tex, target="both",
+                              precision=precision)
+    for label in ("eager", "captured"):
+        opt = fresh()
+        if label == "captured":
+            opt.capture(R, T, style, warmup=3)
+            step = opt.step_captured
+        else:
+            for _ in range(3):
+                opt.step(R, T, style)
+            step = lambda: opt.step(R, T, style)    # noqa: E731
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+        out[label + "_ms_per_step"] = e0.elapsed_time(e1) / steps
+        out[label + "_it_per_s"] = 1e3 * steps / e0.elapsed_time(e1)
+        out[label + "_final_loss"] = float(loss)
+        del opt
+    v = verts.clone().requires_grad_(True)
+    w3 = torch.ones(3, device=dev)
+
+    def fused():
+        v.grad = None
+        torch.dot(ml.regularizers(v, faces), w3).backward()
+
+    def torch_ops():
+        v.grad = None
+        (ml.edge_loss_torch(v, faces) + ml.laplacian_smoothing_torch(v, faces) + ml.normal_consistency_torch(v, faces)).backward()
+    for label, fn in (("regularisers_fused_ms", fused), ("regularisers_torch_ms", torch_ops)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        out[label] = e0.elapsed_time(e1) / 20
+    return out
+
+
 def c1_first_approach(dev, steps=200, size=256, run_cpu=True):
     """BASELINE configs[0]: cow texture fit, 1 view 256x256, 50 Adam steps of the masked-MSE loop of
     first_approach.py:191-213 (render -> masked MSE -> backward -> Adam; no VGG on this path)."""
@@ -937,6 +1006,12 @@ def run_st3d(args):
         out["c1_first_approach"] = c1_first_approach(dev, run_cpu=not args.no_cpu_baseline)
         # BASELINE configs[0] is first_approach.py at 1 view x 256^2: its 2D style-transfer stage, and a 4 x 512^2 batch
         out["nst_2d_loop"] = {"1x256": nst_2d_loop(dev, vgg, size=256, batch=1), "4x512": nst_2d_loop(dev, vgg, size=512, batch=4)}
+        gc.collect()
+        torch.cuda.empty_cache()
+        try:
+            out["c3_both_target"] = c3_both_target(dev, vgg, args.precision)
+        except Exception as e:      # a side record must not take the headline line down with it
+            out["c3_both_target"] = {"error": repr(e)[:400]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # >= 3 warm-up + >= 10 timed iterations; one view each keeps it to ~30 s of CPU work
         sec, threads, n_timed, n_warm = cpu_iterations(args, args.views, 1, 10, 3)
