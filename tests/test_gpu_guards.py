@@ -82,8 +82,7 @@ class _GuardedTorch:
 def guarded(monkeypatch):
     import st3d
     from st3d import ops
-    if not st3d.available():
-        pytest.fail("libst3d.so not built")
+    st3d.lib()                  # raises when libst3d.so is not built
     g = _GuardedTorch()
     monkeypatch.setattr(ops, "torch", g)
     monkeypatch.setattr(ops, "_mesh_reg_ws", {})
