@@ -219,3 +219,20 @@ def test_loss_and_pool_ops_stay_inside_their_buffers(guarded, golden_dir):
         losses, state = ops.mesh_regularizers_forward(verts, topo, 0.0, which)
         ops.mesh_regularizers_backward(state, torch.ones(3, device=dev))
         g.verify(f"mesh regularisers which={which}")
+
+
+def test_the_guard_bands_do_see_an_overrun(guarded):
+    """The check itself: a kernel told to write 128 floats into a 64-float guarded buffer is caught."""
+    import ctypes
+    from st3d import lib
+    ops, g = guarded
+    out = g.empty(64, dtype=torch.float32, device="cuda")
+    y, c = torch.rand(128, device="cuda"), torch.rand(128, device="cuda")
+    p = lambda t: ctypes.c_void_p(t.data_ptr())     # noqa: E731
+    rc = lib().st3d_mse_tap_backward(p(y), p(c), None, 128, ctypes.c_float(1.0), None, p(out),
+                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    with pytest.raises(AssertionError, match="PAST the end"):
+        g.verify("deliberate overrun")
+    g.records.clear()
+    g.checked += 1
