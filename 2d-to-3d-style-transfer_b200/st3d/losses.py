@@ -138,31 +138,36 @@ def perceptual_loss_from_features(cur_feats, content_feat, style_grams, style_we
 
 
 def perceptual_loss_of_images(current_imgs, model, content_feat, style_grams, style_weight=1e6, content_weight=1.0,
-                              precision=None):
+                              precision=None, loss_scale: float = 1.0):
     """losses.py:26-42 from the images on: walks `model` like get_features and evaluates the loss on the way.
-    With a fused model (st3d.vgg.fuse_vgg_features) every style tap is evaluated INSIDE its conv + ReLU layer, so
-    the layer's backward adds the Gram gradient to the gradient arriving from deeper layers and applies the ReLU
-    mask in the Gram kernel's epilogue; values and gradients equal get_features + perceptual_loss_from_features."""
+    With a fused model (st3d.vgg.fuse_vgg_features) every tap is evaluated INSIDE its conv + ReLU layer, so the layer's
+    backward adds the tap's gradient to the gradient arriving from deeper layers and applies the ReLU mask in one kernel,
+    and every tap ADDS its weighted term to ONE loss accumulator from inside its kernel (content_weight x content +
+    style_weight x sum of the layer terms, losses.py:42, times `loss_scale`): no per-layer loss tensors, no tree of scalar
+    multiply / add kernels in the forward or the backward.  Values and gradients equal get_features +
+    perceptual_loss_from_features."""
     from .vgg import FusedConvReLU
     fused_taps = current_imgs.is_cuda and all(isinstance(model._modules.get(n), FusedConvReLU)
                                               for n, l in VGG_TAPS.items() if l in style_grams)
     if not fused_taps:
-        return perceptual_loss_from_features(get_features(current_imgs, model), content_feat, style_grams, style_weight,
+        loss = perceptual_loss_from_features(get_features(current_imgs, model), content_feat, style_grams, style_weight,
                                              content_weight, precision)
+        return loss if loss_scale == 1.0 else loss_scale * loss
     x = current_imgs
     if getattr(model, "_st3d_channels_last", False) and x.dim() == 4:
         x = x.contiguous(memory_format=torch.channels_last)
-    content_loss, style_loss, done = None, None, False
+    acc = torch.zeros(1, device=x.device, dtype=torch.float32)
+    sw, cw = float(style_weight) * float(loss_scale), float(content_weight) * float(loss_scale)
+    done = False
     for name, module in model._modules.items():
         if done and not _rewrites_the_tap(module):
             break
         layer = VGG_TAPS.get(name)
         if layer in style_grams:
-            x, term = module.forward_with_style_tap(x, style_grams[layer], precision)
-            style_loss = term if style_loss is None else style_loss + term
+            x, acc = module.forward_with_style_tap(x, style_grams[layer], precision, acc=acc, loss_weight=sw)
         elif layer == CONTENT_LAYER and isinstance(module, FusedConvReLU) and x.shape[0] == content_feat.shape[0]:
             # the content tap inside its conv + ReLU layer: MSE backward + gradient accumulation + ReLU mask in one kernel
-            x, content_loss = module.forward_with_content_tap(x, content_feat)
+            x, acc = module.forward_with_content_tap(x, content_feat, acc=acc, loss_weight=cw)
         else:
             if hasattr(module, "tapped"):
                 module.tapped = layer is not None
@@ -171,11 +176,11 @@ def perceptual_loss_of_images(current_imgs, model, content_feat, style_grams, st
             else:
                 x = module(x)
             if layer == CONTENT_LAYER:
-                content_loss = Fn.mse_loss(x, content_feat)
+                acc = acc + cw * Fn.mse_loss(x, content_feat)
         if done:
             break
         done = name == str(LAST_TAP)
-    return content_weight * content_loss + style_weight * style_loss
+    return acc.reshape(())
 
 
 def compute_perceptual_loss(current_imgs, content_imgs, style_imgs, model, style_weight=1e6, content_weight=1,

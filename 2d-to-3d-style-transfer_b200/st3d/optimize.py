@@ -165,6 +165,7 @@ class StyleOptimizer:
         self.last_images: Optional[torch.Tensor] = None
         self._eager_steps = 0
         self._captured: Optional[CapturedIteration] = None
+        self._grad_seed = torch.full((), 1.0 / self.world_size, device=self.verts0.device, dtype=torch.float32)
 
     # kept for the first API of this module
     @property
@@ -249,8 +250,9 @@ class StyleOptimizer:
         if not torch.cuda.is_current_stream_capturing():    # (a captured copy stream joins back before the graph ends)
             images.record_stream(self._copy_stream)
 
-    def _views_loss(self, R, T, style_img, images_out, cache_slot):
-        """Perceptual loss (losses.py:12-44) of the views (R, T): content render + constants, current render, VGG walk."""
+    def _views_loss(self, R, T, style_img, images_out, cache_slot, loss_scale=1.0):
+        """Perceptual loss (losses.py:12-44) of the views (R, T), times `loss_scale`: content render + constants, current
+        render, VGG walk."""
         cacheable = self.cache_constants and self.content_background != "noise"     # fresh noise: nothing is constant
         if cacheable and self._constants_cached_for(cache_slot, R, T, style_img):
             c = self._cache[cache_slot]
@@ -270,7 +272,7 @@ class StyleOptimizer:
             self._export_images(current_imgs.detach(), images_out)
         self.last_images = current_imgs.detach()
         return losses.perceptual_loss_of_images(self._nn_input(current_imgs), self.vgg, content_feat, grams,
-                                                self.style_weight, self.content_weight, self.precision)
+                                                self.style_weight, self.content_weight, self.precision, loss_scale)
 
     def _accumulate_gradients(self, R, T, style_img, images_out=None, micro_batch=None) -> torch.Tensor:
         """Everything of an iteration that depends on this rank's views: zero the flat gradient, then per micro-batch
@@ -283,8 +285,10 @@ class StyleOptimizer:
         for s in range(0, B, mb):
             Rm, Tm = (R, T) if mb == B else (R[s:s + mb], T[s:s + mb])
             out_m = None if images_out is None else (images_out if mb == B else images_out[s:s + mb])
-            part = main_w * self._views_loss(Rm, Tm, style_img, out_m, s) * (Rm.shape[0] / B)
-            (part / self.world_size).backward()                                                 # :188
+            # the weights of this chunk in the iteration's loss go down to the kernels that accumulate it, and the 1 / world
+            # of the gradient average is the seed of the backward: no scalar kernels around the loss
+            part = self._views_loss(Rm, Tm, style_img, out_m, s, loss_scale=main_w * (Rm.shape[0] / B))
+            part.backward(gradient=self._grad_seed)                                             # :188
             loss = part.detach() if loss is None else loss + part.detach()
         if self._copy_stream is not None and torch.cuda.is_current_stream_capturing():
             torch.cuda.current_stream().wait_stream(self._copy_stream)      # a captured side stream must join back

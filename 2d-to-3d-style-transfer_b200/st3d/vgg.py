@@ -60,20 +60,29 @@ class _ConvReLUStyleTapFn(torch.autograd.Function):
     the network, and the ReLU backward of the sum -- st3d_gram_backward with ST3D_GRAM_ACCUMULATE | ST3D_GRAM_RELU_MASK."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, target, stride, padding, dilation, groups, precision):
+    def forward(ctx, x, weight, bias, target, stride, padding, dilation, groups, precision, acc=None, loss_weight=1.0):
+        """acc None: returns (y, this layer's loss term).  acc (1,) float32: the kernel ADDS loss_weight x term to it in
+        place and (y, acc) is returned -- a whole perceptual loss is then one accumulator, not a tree of scalar kernels."""
         ops = _ops()
         y = torch.cudnn_convolution_relu(x, weight, bias, stride, padding, dilation, groups)
         B, C, H, W = y.shape
-        scale = 1.0 / (B * C * C) / (float(C) ** 2 * float(H) ** 2)
-        loss = torch.zeros(1, device=y.device, dtype=torch.float32)
+        scale = float(loss_weight) / (B * C * C) / (float(C) ** 2 * float(H) ** 2)
+        loss = acc if acc is not None else torch.zeros(1, device=y.device, dtype=torch.float32)
         dgram, _ = ops.gram_mse_forward(y, target.detach(), scale, loss, precision=precision)
         ctx.conf = (stride, padding, dilation, groups, precision)
         ctx.save_for_backward(x, weight, y, dgram)
         ctx.set_materialize_grads(False)
+        if acc is not None:
+            ctx.mark_dirty(acc)
+            return y, acc
         return y, loss.reshape(())
 
     @staticmethod
     def backward(ctx, grad_y, grad_loss):
+        return _ConvReLUStyleTapFn._backward(ctx, grad_y, grad_loss) + (grad_loss, None)   # acc: passed through
+
+    @staticmethod
+    def _backward(ctx, grad_y, grad_loss):
         ops = _ops()
         x, weight, y, dgram = ctx.saved_tensors
         stride, padding, dilation, groups, precision = ctx.conf
@@ -110,17 +119,22 @@ class _ConvReLUContentTapFn(torch.autograd.Function):
     over the 67 MB activation for the same thing."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, content, stride, padding, dilation, groups):
+    def forward(ctx, x, weight, bias, content, stride, padding, dilation, groups, acc=None, loss_weight=1.0):
+        """acc: as in _ConvReLUStyleTapFn.forward."""
         ops = _ops()
         y = torch.cudnn_convolution_relu(x, weight, bias, stride, padding, dilation, groups)
         c = content.detach()
         if c.stride() != y.stride() or c.dtype != torch.float32:       # the kernels walk y and c in one element order
             c = torch.empty_like(y).copy_(c)
-        loss = torch.zeros(1, device=y.device, dtype=torch.float32)
-        ops.mse_forward(y, c, 1.0 / max(y.numel(), 1), loss, want_grad=False)
+        loss = acc if acc is not None else torch.zeros(1, device=y.device, dtype=torch.float32)
+        ctx.scale = float(loss_weight) / max(y.numel(), 1)
+        ops.mse_forward(y, c, ctx.scale, loss, want_grad=False)
         ctx.conf = (stride, padding, dilation, groups)
         ctx.save_for_backward(x, weight, y, c)
         ctx.set_materialize_grads(False)
+        if acc is not None:
+            ctx.mark_dirty(acc)
+            return y, acc
         return y, loss.reshape(())
 
     @staticmethod
@@ -129,17 +143,17 @@ class _ConvReLUContentTapFn(torch.autograd.Function):
         x, weight, y, c = ctx.saved_tensors
         stride, padding, dilation, groups = ctx.conf
         if grad_loss is None and grad_y is None:
-            return (None,) * 8
+            return (None,) * 10
         if grad_loss is None:                       # the tap's loss term is unused: plain ReLU backward
             g = torch.ops.aten.threshold_backward(grad_y, y, 0.0)
         else:
             if grad_y is not None and (grad_y.stride() != y.stride() or grad_y.dtype != torch.float32):
                 grad_y = torch.empty_like(y).copy_(grad_y)
-            g = ops.mse_tap_backward(y, c, grad_y, 1.0 / max(y.numel(), 1), scale_tensor=grad_loss)
+            g = ops.mse_tap_backward(y, c, grad_y, ctx.scale, scale_tensor=grad_loss)
         need = [ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]]
         gx, gw, gb = torch.ops.aten.convolution_backward(g, x, weight, [weight.shape[0]], list(stride), list(padding),
                                                          list(dilation), False, [0, 0], groups, need)
-        return gx, gw, gb, None, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None, grad_loss, None     # acc: passed through
 
 
 class _MaxPool2x2Fn(torch.autograd.Function):
@@ -202,23 +216,26 @@ class FusedConvReLU(nn.Module):
         return _ConvBiasReLUFn.apply(x, c.weight, bias, tuple(c.stride), tuple(c.padding), tuple(c.dilation), c.groups,
                                      self.feeds_masking_pool and not self.tapped)
 
-    def forward_with_style_tap(self, x, target_gram, precision=None):
+    def forward_with_style_tap(self, x, target_gram, precision=None, acc=None, loss_weight=1.0):
         """(activation, style-loss term of this layer against `target_gram` (1|B,C,C)); CUDA only.
         `target_gram` must be SYMMETRIC -- a Gram matrix or a blend of Gram matrices, what losses.py:24 builds: the
         backward then reads dG = 2 scale (G - target) as the symmetric matrix it is and skips the dG + dG^T pass
-        (st3d.functional.style_layer_loss is the entry point for arbitrary targets)."""
+        (st3d.functional.style_layer_loss is the entry point for arbitrary targets).
+        acc: a (1,) float32 loss accumulator; the kernel adds `loss_weight` x term to it in place and it is returned in
+        place of the term (see perceptual_loss_of_images)."""
         c = self.conv
         bias = c.bias if c.bias is not None else torch.zeros(c.out_channels, device=x.device, dtype=x.dtype)
         return _ConvReLUStyleTapFn.apply(x, c.weight, bias, target_gram, tuple(c.stride), tuple(c.padding),
-                                         tuple(c.dilation), c.groups, precision)
+                                         tuple(c.dilation), c.groups, precision, acc, loss_weight)
 
 
-def _content_tap(self, x, content_feat):
-    """(activation, mean((activation - content_feat)^2)) with the fused one-kernel backward; CUDA only."""
+def _content_tap(self, x, content_feat, acc=None, loss_weight=1.0):
+    """(activation, mean((activation - content_feat)^2)) with the fused one-kernel backward; CUDA only.  acc / loss_weight as
+    in forward_with_style_tap."""
     c = self.conv
     bias = c.bias if c.bias is not None else torch.zeros(c.out_channels, device=x.device, dtype=x.dtype)
     return _ConvReLUContentTapFn.apply(x, c.weight, bias, content_feat, tuple(c.stride), tuple(c.padding),
-                                       tuple(c.dilation), c.groups)
+                                       tuple(c.dilation), c.groups, acc, loss_weight)
 
 
 FusedConvReLU.forward_with_content_tap = _content_tap
