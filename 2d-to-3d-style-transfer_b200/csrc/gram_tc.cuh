@@ -1073,7 +1073,21 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// cuTensorMapEncodeTiled is a DRIVER entry point: it needs a context current on the calling thread, and unlike a runtime
+// call it does not make one so.  A thread whose first CUDA work is one of these Gram ops -- autograd's backward thread,
+// when the node it starts with is a style tap -- has none yet (CUDA_ERROR_INVALID_CONTEXT, 201): one runtime call per
+// thread and device binds the primary context.
+static inline void bind_primary_context() {
+    thread_local int bound_device = -1;
+    int d = -1;
+    if (cudaGetDevice(&d) == cudaSuccess && d != bound_device) {
+        cudaFree(nullptr);
+        bound_device = d;
+    }
+}
+
 static inline EncodeTiledFn encode_fn() {
+    bind_primary_context();
     static EncodeTiledFn fn = [] {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;

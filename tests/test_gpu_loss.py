@@ -354,7 +354,9 @@ def test_style_taps_inside_the_conv_layers_equal_the_feature_walk(precision):
     xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
     la = losses.perceptual_loss_of_images(xa, model, content, grams, 1e6, 1.0, precision)
     lb = losses.perceptual_loss_from_features(losses.get_features(xb, model), content, grams, 1e6, 1.0, precision)
-    assert _relerr(la, lb) <= 1e-6          # the per-layer MSE sums use float atomics: equal up to summation order
+    # one accumulator fed by float atomics, the weights applied inside the kernels, against per-layer sums weighted
+    # afterwards: equal up to the order and place of a handful of fp32 roundings
+    assert _relerr(la, lb) <= 5e-6
     la.backward()
     lb.backward()
     if precision == "fp32":
@@ -481,7 +483,7 @@ def test_content_tap_inside_its_conv_layer_equals_the_separate_passes():
     xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
     la = losses.perceptual_loss_of_images(xa, model, content, grams, 1e3, 50.0, "fp32")       # content term dominant
     lb = losses.perceptual_loss_from_features(losses.get_features(xb, model), content, grams, 1e3, 50.0, "fp32")
-    assert _relerr(la, lb) <= 1e-6
+    assert _relerr(la, lb) <= 5e-6          # (one accumulator, weights inside the kernels: a few fp32 roundings apart)
     la.backward()
     lb.backward()
     assert _relerr(xa.grad, xb.grad) <= 1e-5, _relerr(xa.grad, xb.grad)
