@@ -39,7 +39,10 @@ for _ in range(4):
     v, f = meshgen.subdivide(v, f)
 meshes["cow_x256"] = (v, f)
 
+only = [m for m in os.environ.get("MESHES", "").split(",") if m]
 for name, (verts, faces) in meshes.items():
+    if only and name not in only:
+        continue
     verts, faces = verts.cuda().requires_grad_(True), faces.cuda()
     t0 = time.perf_counter()
     topo = ml.topology(faces, verts.shape[0])
