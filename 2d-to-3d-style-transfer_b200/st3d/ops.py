@@ -644,7 +644,7 @@ def mse_forward(a, b, scale: float, loss_out, mask=None, want_grad=True):
             raise ValueError("mask must be (B,1,H,W) for a (B,C,H,W) input")
         inner, mask_ch = a.shape[2] * a.shape[3], a.shape[1]
     grad = torch.empty_like(a) if want_grad else None
-    with _timed("mse_forward", (a.numel(),)):
+    with _timed("mse_forward" if want_grad else "mse_value_forward", (a.numel(),)):
         check(lib().st3d_mse_forward(_p(a), _p(b), _p(mask), a.numel(), inner, mask_ch, float(scale), _p(loss_out),
                                      _p(grad), _stream()), "st3d_mse_forward")
     return grad

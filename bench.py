@@ -276,9 +276,9 @@ def run_reference(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 # filled from the round's ncu capture (profiles/): (bytes per launch, source) of the fused Gram backward at conv1_1
-TRAFFIC_FUSED_BWD64 = (1568011000, "profiles/r2_ncu_full.csv: k_gram_tc_bwd<64, NHWC, RING> with ST3D_GRAM_ACCUMULATE | "
-                                   "ST3D_GRAM_RELU_MASK, dram read 1075.4 MB + write 492.6 MB per launch (the mask's second read "
-                                   "of F hits L2)")
+TRAFFIC_FUSED_BWD64 = (1567838400, "profiles/r2_ncu_full.csv (end-of-round capture, timed step): k_gram_tc_bwd<64, NHWC, RING> "
+                                   "with ST3D_GRAM_ACCUMULATE | ST3D_GRAM_RELU_MASK | ST3D_GRAM_DGRAM_SYMMETRIC, dram read 1074.97 MB + "
+                                   "write 492.87 MB per launch (the mask's second read of F hits L2)")
 
 
 def algorithmic_bytes(op, key, tex=512):
@@ -297,6 +297,10 @@ def algorithmic_bytes(op, key, tex=512):
         return B * C * HW * 4 + B * C * C * 4
     if op == "mse_forward":         # read a, b, write grad
         return 3 * key[0] * 4
+    if op == "mse_value_forward":   # the content tap's forward: read a, b; its gradient comes from mse_tap_backward
+        return 2 * key[0] * 4
+    if op == "mse_tap_backward":    # read y, c and the incoming gradient, write the layer's pre-activation gradient
+        return 4 * key[0] * 4
     if op == "maxpool_forward":     # read x, write x / 4
         B, C, H, W = key
         return B * C * H * W * 5
