@@ -322,3 +322,101 @@ def test_mesh_regularisers_known_answers():
         (edge(v, tet_f) + 2 * lap(v, tet_f) + 3 * ncons(v, tet_f)).backward()
         grads.append(v.grad)
     assert torch.allclose(grads[0], grads[1], rtol=1e-10, atol=1e-12)
+
+
+def test_fragments_of_one_triangle_against_closed_forms_in_exact_arithmetic():
+    """An independent pin of the rasterizer semantics of SURVEY Appendix A.3 (PyTorch3D itself is absent): for ONE
+    triangle with vertices at different depths every output of the oracle is recomputed here from the definitions in
+    exact rational arithmetic (fractions.Fraction on the float32 inputs), sharing no code with the oracle:
+      pixel centre i of an S-pixel axis sits at NDC 1 - (2 i + 1) / S (+X left, +Y up);
+      inside  <=>  the three affine barycentrics are > 0;
+      perspective correction  b_i' = (b_i / z_i) / sum_j (b_j / z_j),  zbuf = sum_i b_i' z_i = 1 / sum_j (b_j / z_j);
+      dists = -(squared NDC distance to the nearest edge segment) for a pixel inside."""
+    from fractions import Fraction as Fr
+    S = 16
+    tri = np.array([[-0.71, -0.52, 1.5], [0.83, -0.34, 2.25], [0.12, 0.77, 3.0]], dtype=np.float32)
+    p2f, zbuf, bary, dists = _raster(tri.tolist(), S=S, perspective_correct=True)
+    V = [[Fr(float(c)) for c in v] for v in tri]
+    (x0, y0, z0), (x1, y1, z1), (x2, y2, z2) = V
+
+    def edge(px, py, ax, ay, bx, by):
+        return (px - ax) * (by - ay) - (py - ay) * (bx - ax)
+
+    def seg_d2(px, py, ax, ay, bx, by):
+        dx, dy = bx - ax, by - ay
+        t = ((px - ax) * dx + (py - ay) * dy) / (dx * dx + dy * dy)
+        t = max(Fr(0), min(Fr(1), t))
+        cx, cy = ax + t * dx, ay + t * dy
+        return (px - cx) ** 2 + (py - cy) ** 2
+
+    area = edge(x2, y2, x0, y0, x1, y1)
+    assert area != 0
+    inside_count = 0
+    for yi in range(S):
+        for xi in range(S):
+            px, py = 1 - Fr(2 * xi + 1, S), 1 - Fr(2 * yi + 1, S)
+            b = [edge(px, py, x1, y1, x2, y2) / area, edge(px, py, x2, y2, x0, y0) / area, edge(px, py, x0, y0, x1, y1) / area]
+            margin = min(abs(v) for v in b)
+            if margin < Fr(1, 10 ** 5):
+                continue                        # a centre this close to an edge is decided by fp32 rounding
+            inside = all(v > 0 for v in b)
+            assert (int(p2f[0, yi, xi, 0]) == 0) == inside, (yi, xi)
+            if not inside:
+                assert float(zbuf[0, yi, xi, 0]) == -1.0 and float(dists[0, yi, xi, 0]) == -1.0
+                continue
+            inside_count += 1
+            w = [b[0] / z0, b[1] / z1, b[2] / z2]
+            tot = sum(w)
+            want_b = [float(v / tot) for v in w]
+            want_z = float(1 / tot)
+            want_d = -float(min(seg_d2(px, py, x0, y0, x1, y1), seg_d2(px, py, x1, y1, x2, y2), seg_d2(px, py, x2, y2, x0, y0)))
+            got_b = bary[0, yi, xi, 0].tolist()
+            assert max(abs(g - w_) for g, w_ in zip(got_b, want_b)) < 2e-6, (yi, xi, got_b, want_b)
+            assert abs(float(zbuf[0, yi, xi, 0]) - want_z) < 5e-6 * want_z
+            assert abs(float(dists[0, yi, xi, 0]) - want_d) < 1e-6 + 1e-5 * abs(want_d)
+    assert inside_count > 40
+    # without perspective correction the barycentrics are the affine ones and the depth their plain interpolation
+    p2f_a, zbuf_a, bary_a, _ = _raster(tri.tolist(), S=S, perspective_correct=False)
+    assert torch.equal(p2f_a, p2f)
+    yi, xi = [int(v[0]) for v in torch.nonzero(p2f_a[0, ..., 0] == 0, as_tuple=True)]
+    px, py = 1 - Fr(2 * xi + 1, S), 1 - Fr(2 * yi + 1, S)
+    b = [edge(px, py, x1, y1, x2, y2) / area, edge(px, py, x2, y2, x0, y0) / area, edge(px, py, x0, y0, x1, y1) / area]
+    assert max(abs(g - float(w_)) for g, w_ in zip(bary_a[0, yi, xi, 0].tolist(), b)) < 2e-6
+    assert abs(float(zbuf_a[0, yi, xi, 0]) - float(b[0] * z0 + b[1] * z1 + b[2] * z2)) < 1e-5
+
+
+def test_blend_and_texture_sampling_closed_forms():
+    """softmax_rgb_blend for K = 1 and TexturesUV sampling (A.4) against values written out by hand:
+    covered pixel: alpha = sigmoid(-d / sigma), rgb = (w c + delta bg) / (w + delta) with w = alpha * exp((zinv - zmax) / gamma),
+    zinv = (zfar - z) / (zfar - znear), zmax = max(zinv, eps), delta = max(exp((eps - zmax) / gamma), eps), eps = 1e-10;
+    empty pixel: rgb = background, alpha = 0.  UV (u, v) reads texel column u (W - 1), row (1 - v) (H - 1), bilinear."""
+    import math
+    colors = torch.tensor([0.2, 0.6, 0.9]).reshape(1, 1, 1, 1, 3).repeat(1, 1, 2, 1, 1)
+    p2f = torch.tensor([0, -1]).reshape(1, 1, 2, 1)
+    d, z, sigma, gamma = -3e-5, 2.5, 1e-4, 1e-4
+    dists = torch.tensor([d, -1.0]).reshape(1, 1, 2, 1)
+    zbuf = torch.tensor([z, -1.0]).reshape(1, 1, 2, 1)
+    out = ro.softmax_rgb_blend(colors, p2f, dists, zbuf, sigma=sigma, gamma=gamma, background=(1.0, 0.5, 0.25),
+                               znear=1.0, zfar=100.0)
+    alpha = 1.0 / (1.0 + math.exp(d / sigma))
+    zinv = (100.0 - z) / 99.0
+    w = alpha * math.exp((zinv - max(zinv, 1e-10)) / gamma)
+    delta = max(math.exp((1e-10 - max(zinv, 1e-10)) / gamma), 1e-10)
+    want = [(w * c + delta * b) / (w + delta) for c, b in zip((0.2, 0.6, 0.9), (1.0, 0.5, 0.25))]
+    assert torch.allclose(out[0, 0, 0, :3], torch.tensor(want), atol=1e-6) and abs(float(out[0, 0, 0, 3]) - alpha) < 1e-6
+    assert 0.5 < alpha < 0.6                                    # 0.3 sigma inside the face: a soft edge pixel
+    assert torch.allclose(out[0, 0, 1], torch.tensor([1.0, 0.5, 0.25, 0.0]))
+    # texture: a 3 x 4 map whose texel (row r, column c) holds 10 r + c in channel 0
+    H, W = 3, 4
+    tex = torch.zeros(H, W, 3)
+    tex[..., 0] = 10.0 * torch.arange(H)[:, None] + torch.arange(W)[None, :]
+    fuv = torch.tensor([[[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]]])                  # face 0: uv = (b1, b2)
+    for (u, v) in [(0.0, 0.0), (1.0, 0.0), (0.0, 1.0), (0.5, 0.25), (1.0 / 3.0, 0.5)]:
+        b = torch.tensor([1.0 - u - v, u, v]).reshape(1, 1, 1, 1, 3)
+        got = ro.sample_textures_uv(torch.zeros(1, 1, 1, 1, dtype=torch.int64), b, fuv, tex[None])[0, 0, 0, 0, 0].item()
+        x, y = u * (W - 1), (1.0 - v) * (H - 1)
+        c0, r0 = min(int(math.floor(x)), W - 2), min(int(math.floor(y)), H - 2)
+        fx, fy = x - c0, y - r0
+        want = ((1 - fy) * ((1 - fx) * (10 * r0 + c0) + fx * (10 * r0 + c0 + 1))
+                + fy * ((1 - fx) * (10 * (r0 + 1) + c0) + fx * (10 * (r0 + 1) + c0 + 1)))
+        assert abs(got - want) < 1e-5, ((u, v), got, want)
