@@ -708,9 +708,10 @@ def mesh_regularizers_forward(verts, topo, target_length: float = 0.0, which: in
     verts = _cuda_f32("verts", verts, 3)
     _check_topology(verts, topo)
     dev = verts.device
-    ws = _mesh_reg_ws.get(dev)
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)     # launches on one stream are ordered; two streams must not share
+    ws = _mesh_reg_ws.get(key)
     if ws is None:      # 32 bytes, zero once: every launch leaves it zero
-        ws = _mesh_reg_ws[dev] = torch.zeros(int(lib().st3d_mesh_regularizers_workspace_size()) // 8, device=dev,
+        ws = _mesh_reg_ws[key] = torch.zeros(int(lib().st3d_mesh_regularizers_workspace_size()) // 8, device=dev,
                                              dtype=torch.float64)
     losses = torch.empty(3, device=dev, dtype=torch.float32)
     lap_dir = torch.empty_like(verts)
