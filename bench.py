@@ -15,6 +15,7 @@ Prints ONE JSON line on rank 0.
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -687,6 +688,48 @@ def c3_both_target(dev, vgg, precision, views=4, size=512, steps=20):
     return out
 
 
+def c4_teapot_multi_style(dev, vgg, precision, views=8, size=1024, steps=10):
+    """BASELINE configs[3], one rank's share: teapot (2 464 faces, no UVs -> per-vertex colours initialised at 0.5, the
+    colours are what is optimised), 8 of the 64 views x 1024^2, style target Gs = sum_j 1/4 Gram(style_j) over the four
+    style images the reference ships (Style_1/3/4/5; stored at 512^2 / 256^2 in tests/golden/styles.npz and resized as
+    utils.py:34-44 does).  One iteration, eager and with the captured gradient computation; CUDA events."""
+    import numpy as np
+    import torch
+    from st3d.optimize import StyleOptimizer
+    d = np.load(os.path.join(ROOT, "tests", "golden", "teapot_mesh.npz"))
+    verts, faces = torch.from_numpy(d["verts"]).float().to(dev), torch.from_numpy(d["faces"]).long().to(dev)
+    rgb = torch.full((verts.shape[0], 3), 0.5, device=dev)
+    styles = torch.cat([style_image(size, n) for n in ("style_1", "style_3", "style_4", "style_5")], dim=0).to(dev)
+    R, T = cameras(views)
+    R, T = R.to(dev), T.to(dev)
+    out = {"workload": f"teapot_mesh per-vertex colours, {views} views x {size}^2, four blended style Grams "
+                       f"(BASELINE configs[3], one rank of 8), {steps} steps"}
+    for label in ("eager", "captured"):
+        opt = StyleOptimizer(verts, faces, vgg, size, verts_rgb=rgb, target="texture", precision=precision,
+                             style_weights=[0.25] * 4)
+        if label == "captured":
+            opt.capture(R, T, styles, warmup=3)
+            step = opt.step_captured
+        else:
+            for _ in range(3):
+                opt.step(R, T, styles)
+            step = lambda: opt.step(R, T, styles)    # noqa: E731
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+        out[label + "_ms_per_step"] = e0.elapsed_time(e1) / steps
+        out[label + "_views_per_s"] = 1e3 * steps * views / e0.elapsed_time(e1)
+        out[label + "_final_loss"] = float(loss)
+        del opt
+        gc.collect()
+        torch.cuda.empty_cache()
+    return out
+
+
 def c1_first_approach(dev, steps=200, size=256, run_cpu=True):
     """BASELINE configs[0]: cow texture fit, 1 view 256x256, 50 Adam steps of the masked-MSE loop of
     first_approach.py:191-213 (render -> masked MSE -> backward -> Adam; no VGG on this path)."""
@@ -1012,10 +1055,13 @@ def run_st3d(args):
         out["nst_2d_loop"] = {"1x256": nst_2d_loop(dev, vgg, size=256, batch=1), "4x512": nst_2d_loop(dev, vgg, size=512, batch=4)}
         gc.collect()
         torch.cuda.empty_cache()
-        try:
-            out["c3_both_target"] = c3_both_target(dev, vgg, args.precision)
-        except Exception as e:      # a side record must not take the headline line down with it
-            out["c3_both_target"] = {"error": repr(e)[:400]}
+        for key, fn in (("c3_both_target", c3_both_target), ("c4_teapot_multi_style", c4_teapot_multi_style)):
+            try:
+                out[key] = fn(dev, vgg, args.precision)
+            except Exception as e:      # a side record must not take the headline line down with it
+                out[key] = {"error": repr(e)[:400]}
+            gc.collect()
+            torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # >= 3 warm-up + >= 10 timed iterations; one view each keeps it to ~30 s of CPU work
         sec, threads, n_timed, n_warm = cpu_iterations(args, args.views, 1, 10, 3)
