@@ -151,7 +151,9 @@ class StyleOptimizer:
             self.vgg = vgg.to(memory_format=torch.channels_last) if channels_last else vgg
         self.image_size = image_size
         self.style_weight, self.content_weight = style_weight, content_weight
-        self.style_weights = style_weights
+        # on the device from the start: a captured iteration cannot upload them (no pageable H2D copy under capture)
+        self.style_weights = (None if style_weights is None else
+                              torch.as_tensor(style_weights, dtype=torch.float32, device=verts.device))
         self.precision = precision
         self.cache_constants = cache_constants
         self.world_size, self.group = world_size, group
