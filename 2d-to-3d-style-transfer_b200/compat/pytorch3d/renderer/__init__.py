@@ -369,18 +369,18 @@ class MeshRenderer(torch.nn.Module):
         lit_ok = isinstance(lights, AmbientLights) or (isinstance(lights, (PointLights, DirectionalLights))
                                                        and not (torch.is_grad_enabled()
                                                                 and meshes_world.verts_packed().requires_grad))
-        # blur_radius > 0 goes through Fragments + shader: that path clips faces at the near plane for any blur,
-        # the fused kernels only for the hard rasterization the reference uses
-        return (lit_ok and rs.faces_per_pixel == 1
-                and rs.blur_radius == 0.0 and rs.perspective_correct is not False
-                and rs.clip_barycentric_coords in (None, False))
+        # one face per pixel, hard or soft (blur_radius > 0: tile-bin path, barycentrics clamped as upstream's default
+        # clip_barycentric_coords = blur_radius > 0 does); both clip faces at the near plane inside the kernels
+        clip_bary = rs.clip_barycentric_coords
+        return (lit_ok and rs.faces_per_pixel == 1 and rs.perspective_correct is not False
+                and (clip_bary is None or bool(clip_bary) == (rs.blur_radius > 0.0)))
 
     def forward(self, meshes_world, **kwargs):
         if isinstance(meshes_world, Meshes) and len(meshes_world) > 1:
             cams = kwargs.get("cameras", self.rasterizer.cameras)
             return torch.cat([self.forward(mesh, **dict(kwargs, cameras=cam)) for mesh, cam in _per_mesh(meshes_world, cams)],
                              dim=0)
-        if not self._can_fuse(meshes_world, kwargs):       # K > 1, blur, lit geometry gradients: Fragments + general shader
+        if not self._can_fuse(meshes_world, kwargs):       # K > 1, lit geometry gradients: Fragments + general shader
             fragments = self.rasterizer(meshes_world, **kwargs)
             return self.shader(fragments, meshes_world, **kwargs)
         verts, faces, R, T, size, tex_kw, common = self._fused_args(meshes_world, kwargs)

@@ -125,36 +125,56 @@ __global__ void k_setup(const float* __restrict__ face_verts, const float4* __re
         const float* p = face_verts + 9 * f;
         v = FaceVerts{p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8]};
     }
-    if (fminf(v.z0, fminf(v.z1, v.z2)) < z_clip) hdr[4] = 1;  // would need near-plane clipping (A.2 clip_faces)
+    // z_clip = -inf: no clipping here (operator boundary: the caller clipped the face list).  Fused renderer: a face
+    // with 1 or 2 vertices behind the plane is binned under the union of the pixel ranges of its sub-triangles
+    // (clip.cuh) and flagged in bit 31 of its x range; k_fine recomputes the sub-triangles.  3 behind: removed.
+    const int nb = count_behind(v, z_clip);
     const float area = edge_fn(v.x2, v.y2, v.x0, v.y0, v.x1, v.y1);
-    bool valid = fabsf(area) > kEps;                       // also false for NaN
-    if ((cull_backfaces & 1) && area < 0.0f) valid = false;
-    if ((cull_backfaces & 2) && frustum_culled(v)) valid = false;
-    if (fmaxf(v.z0, fmaxf(v.z1, v.z2)) < 0.0f) valid = false;
     const float radius = __fsqrt_rn(blur_radius);
-    const float xmin = fsub(fminf(v.x0, fminf(v.x1, v.x2)), radius);
-    const float xmax = fadd(fmaxf(v.x0, fmaxf(v.x1, v.x2)), radius);
-    const float ymin = fsub(fminf(v.y0, fminf(v.y1, v.y2)), radius);
-    const float ymax = fadd(fmaxf(v.y0, fmaxf(v.y1, v.y2)), radius);
-    if (!(isfinite(xmin) && isfinite(xmax) && isfinite(ymin) && isfinite(ymax))) valid = false;
     int xi0 = 1, xi1 = 0, yi0 = 1, yi1 = 0;
-    if (valid) {
+    bool valid = nb < 3 && !((cull_backfaces & 2) && frustum_culled(v));
+    const int nsub = nb == 0 ? 1 : (nb == 2 ? 1 : 2);
+    bool any = false;
+    for (int t = 0; t < nsub && valid; ++t) {
+        FaceVerts s = v;
+        float a = area;
+        if (nb != 0) {
+            ClipTri ct;
+            clip_triangle(v, z_clip, t, ct);
+            s = ct.v;
+            a = edge_fn(s.x2, s.y2, s.x0, s.y0, s.x1, s.y1);
+        }
+        bool ok = fabsf(a) > kEps;                         // also false for NaN
+        if ((cull_backfaces & 1) && a < 0.0f) ok = false;
+        if (fmaxf(s.z0, fmaxf(s.z1, s.z2)) < 0.0f) ok = false;
+        const float xmin = fsub(fminf(s.x0, fminf(s.x1, s.x2)), radius);
+        const float xmax = fadd(fmaxf(s.x0, fmaxf(s.x1, s.x2)), radius);
+        const float ymin = fsub(fminf(s.y0, fminf(s.y1, s.y2)), radius);
+        const float ymax = fadd(fmaxf(s.y0, fmaxf(s.y1, s.y2)), radius);
+        if (!(isfinite(xmin) && isfinite(xmax) && isfinite(ymin) && isfinite(ymax))) ok = false;
+        if (!ok) continue;
         int jlo, jhi, klo, khi;
         ndc_pixel_range(xmin, xmax, W, H, jlo, jhi);
         ndc_pixel_range(ymin, ymax, H, W, klo, khi);
-        if (jlo <= jhi && klo <= khi) {
-            xi0 = W - 1 - jhi;  // image x runs opposite to NDC x (A.3)
-            xi1 = W - 1 - jlo;
-            yi0 = H - 1 - khi;
-            yi1 = H - 1 - klo;
-        } else {
-            valid = false;
-        }
+        if (jlo > jhi || klo > khi) continue;
+        const int a0 = W - 1 - jhi, a1 = W - 1 - jlo, c0 = H - 1 - khi, c1 = H - 1 - klo;  // image x / y run opposite to NDC (A.3)
+        xi0 = any ? min(xi0, a0) : a0;
+        xi1 = any ? max(xi1, a1) : a1;
+        yi0 = any ? min(yi0, c0) : c0;
+        yi1 = any ? max(yi1, c1) : c1;
+        any = true;
+    }
+    valid = valid && any;
+    if (!valid) { xi0 = yi0 = 1; xi1 = yi1 = 0; }
+    int xword = xi0 | (xi1 << 16);
+    if (nb == 1 || nb == 2) {
+        xword |= (int)0x80000000u;
+        hdr[5] = 1;  // this call holds clipped faces: k_fine walks the tile lists in face order (k_sort_tile_lists)
     }
     FaceRec r;
     r.a = make_float4(v.x0, v.y0, v.z0, v.x1);
     r.b = make_float4(v.y1, v.z1, v.x2, v.y2);
-    r.c = make_float4(v.z2, area, __int_as_float(xi0 | (xi1 << 16)), __int_as_float(yi0 | (yi1 << 16)));
+    r.c = make_float4(v.z2, area, __int_as_float(xword), __int_as_float(yi0 | (yi1 << 16)));
     rec[f] = r;
     if (!valid) return;
     const int tx0 = xi0 / kTile, tx1 = xi1 / kTile, ty0 = yi0 / kTile, ty1 = yi1 / kTile;
@@ -187,7 +207,7 @@ __global__ void k_fill(const FaceRec* __restrict__ rec, const int64_t* __restric
     const int64_t f = first + i;
     const float4 c = rec[f].c;
     const int xr = __float_as_int(c.z), yr = __float_as_int(c.w);
-    const int xi0 = xr & 0xffff, xi1 = xr >> 16, yi0 = yr & 0xffff, yi1 = yr >> 16;
+    const int xi0 = xr & 0xffff, xi1 = (xr >> 16) & 0x7fff, yi0 = yr & 0xffff, yi1 = yr >> 16;   // bit 31 of xr: clipped flag
     if (xi0 > xi1) return;
     const int tx0 = xi0 / kTile, tx1 = xi1 / kTile, ty0 = yi0 / kTile, ty1 = yi1 / kTile;
     for (int ty = ty0; ty <= ty1; ++ty)
@@ -209,7 +229,8 @@ __global__ void k_fill(const FaceRec* __restrict__ rec, const int64_t* __restric
 // path, lists of a few hundred entries.
 __global__ void __launch_bounds__(256)
 k_sort_tile_lists(const int* __restrict__ tile_count, const int* __restrict__ tile_offset, const int* __restrict__ list,
-                  int64_t capacity, int* __restrict__ sorted) {
+                  int64_t capacity, int* __restrict__ sorted, const int* __restrict__ only_if) {
+    if (only_if && *only_if == 0) return;   // fused renderer: nothing was clipped in this call, the order is irrelevant
     const int t = blockIdx.x;
     const int base = tile_offset[t];
     const int n = (int)max((int64_t)0, min((int64_t)tile_count[t], capacity - base));
@@ -236,6 +257,7 @@ struct FragOut {  // MODE 0: _C.rasterize_meshes outputs
 struct KBest1 {  // K = 1: everything in registers
     float z = FLT_MAX;
     int f = 0x7fffffff;
+    int sub = 0;  // fused renderer: which sub-triangle of a near-plane-clipped face won (read back by the backward)
     float b0, b1, b2, dist;
     __device__ __forceinline__ void offer(const Hit& h, int face) {
         if (h.z < z || (h.z == z && face < f)) {
@@ -326,7 +348,8 @@ template <int MODE, int K>
 __global__ void __launch_bounds__(256)
 k_fine(const FaceRec* __restrict__ rec, const int* __restrict__ tile_count, const int* __restrict__ tile_offset,
        const int* __restrict__ list, int64_t capacity, int H, int W, int TX, int TY, float blur_radius, int persp,
-       int clip, const int64_t* __restrict__ neighbor, FragOut fo, ShadeParams sp) {
+       int clip, const int64_t* __restrict__ neighbor, FragOut fo, ShadeParams sp, const int* __restrict__ sorted_list,
+       const int* __restrict__ use_sorted, float z_clip, int cull_backfaces, unsigned long long* __restrict__ sub_out) {
     __shared__ float4 s_e0[kChunk], s_e1[kChunk], s_e2[kChunk];
     __shared__ int4 s_misc[kChunk];
     __shared__ int s_nb[kChunk];  // clipped_faces_neighbor_idx of the staged faces (-1: none)
@@ -343,6 +366,9 @@ k_fine(const FaceRec* __restrict__ rec, const int* __restrict__ tile_count, cons
     const bool soft = blur_radius > 0.0f;
 
     typename std::conditional<K == 1, KBest1, KBest<K>>::type best;
+    // fused renderer with clipped faces in the call: the lists ordered by face index (see k_sort_tile_lists)
+    if (MODE == 1 && use_sorted && __ldg(use_sorted) != 0) list = sorted_list;
+    const float radius = __fsqrt_rn(blur_radius);
 
     const int base = tile_offset[t];
     // on bin overflow (hdr[1] set, results invalid) never read past the pair buffer
@@ -365,7 +391,8 @@ k_fine(const FaceRec* __restrict__ rec, const int* __restrict__ tile_count, cons
         __syncthreads();
         for (int j = 0; j < nc; ++j) {
             const int4 m = s_misc[j];
-            const int fx0 = m.y & 0xffff, fx1 = m.y >> 16, fy0 = m.z & 0xffff, fy1 = m.z >> 16;
+            const int fx0 = m.y & 0xffff, fx1 = (m.y >> 16) & 0x7fff, fy0 = m.z & 0xffff, fy1 = m.z >> 16;
+            const bool near_clipped = m.y < 0;  // fused renderer: face crossing the near plane (bit 31 of the x range)
             // warp-uniform reject: face's pixel range misses this warp's 8x4 block
             if (fx1 < wx0 || fx0 > wx0 + 7 || fy1 < wy0 || fy0 > wy0 + 3) continue;
             const float4 e0 = s_e0[j], e1 = s_e1[j], e2 = s_e2[j];
@@ -376,12 +403,51 @@ k_fine(const FaceRec* __restrict__ rec, const int* __restrict__ tile_count, cons
             bool cand = active && xi >= fx0 && xi <= fx1 && yi >= fy0 && yi <= fy1;
             // necessary condition for "inside" when all z > 0 and blur == 0: the three edge values
             // share one strict sign (then every barycentric coordinate can be > 0)
-            if (!soft && m.w)
+            if (!soft && m.w && !near_clipped)
                 cand = cand && ((w0 > 0.0f && w1 > 0.0f && w2 > 0.0f) || (w0 < 0.0f && w1 < 0.0f && w2 < 0.0f));
+            if constexpr (MODE == 1 && K == 1) {
+                if (cand && near_clipped) {
+                    // The one or two sub-triangles of the face, in the order upstream's clipped face list holds them
+                    // (consecutive indices), each with the rasterizer's own per-face rejects; barycentrics converted to
+                    // the unclipped face.  The second half of a quad meets the rule of clipped_faces_neighbor_idx: if
+                    // the first half holds the pixel, the closer of the two (smaller edge distance) keeps it.
+                    const FaceVerts v = unpack(rec[m.x]);
+                    const int nt = count_behind(v, z_clip) == 2 ? 1 : 2;
+                    bool first_holds = false;
+                    for (int st = 0; st < nt; ++st) {
+                        ClipTri ct;
+                        clip_triangle(v, z_clip, st, ct);
+                        const FaceVerts& q = ct.v;
+                        if (px > fadd(fmaxf(q.x0, fmaxf(q.x1, q.x2)), radius) || px < fsub(fminf(q.x0, fminf(q.x1, q.x2)), radius) ||
+                            py > fadd(fmaxf(q.y0, fmaxf(q.y1, q.y2)), radius) || py < fsub(fminf(q.y0, fminf(q.y1, q.y2)), radius))
+                            continue;
+                        if (fmaxf(q.z0, fmaxf(q.z1, q.z2)) < 0.0f) continue;
+                        const float a = edge_fn(q.x2, q.y2, q.x0, q.y0, q.x1, q.y1);
+                        if (!(fabsf(a) > kEps) || ((cull_backfaces & 1) && a < 0.0f)) continue;
+                        Hit h;
+                        if (!eval_face(px, py, q, a, blur_radius, persp != 0, clip != 0, h)) continue;
+                        bool take;
+                        if (st == 1 && first_holds)
+                            take = fabsf(h.dist) < fabsf(best.dist);
+                        else
+                            take = h.z < best.z || (h.z == best.z && m.x < best.f);
+                        if (take) {
+                            float u0, u1, u2;
+                            clip_convert_bary(ct, h.b0, h.b1, h.b2, u0, u1, u2);
+                            best.z = h.z; best.f = m.x; best.sub = st; best.b0 = u0; best.b1 = u1; best.b2 = u2; best.dist = h.dist;
+                            first_holds = st == 0;
+                        }
+                    }
+                    cand = false;
+                }
+            }
             if (cand) {
                 const FaceRec r = rec[m.x];
                 Hit h;
-                if (eval_face(px, py, unpack(r), r.c.y, blur_radius, persp != 0, clip != 0, h)) best.offer(h, m.x, s_nb[j]);
+                if (eval_face(px, py, unpack(r), r.c.y, blur_radius, persp != 0, clip != 0, h)) {
+                    best.offer(h, m.x, s_nb[j]);
+                    if constexpr (K == 1) { if (best.f == m.x) best.sub = 0; }
+                }
             }
         }
     }
@@ -420,6 +486,7 @@ k_fine(const FaceRec* __restrict__ rec, const int* __restrict__ tile_count, cons
                 rgba[3] = 0.0f;
             }
             sp.pix_to_face[pix] = hit ? best.f : -1;
+            if (sub_out) sub_out[pix] = (unsigned long long)(hit ? best.sub : 0);
             if (sp.out_layout == ST3D_LAYOUT_NHWC_RGBA) {
                 reinterpret_cast<float4*>(sp.out_image)[pix] = make_float4(rgba[0], rgba[1], rgba[2], rgba[3]);
             } else if (sp.out_layout == ST3D_LAYOUT_NHWC_RGB) {
@@ -1120,14 +1187,14 @@ extern "C" int st3d_rasterize_meshes_forward(const float* face_verts, const int6
     if (rc != ST3D_OK) return rc;
     const int* tile_list = ws.list;
     if (clipped_faces_neighbor_idx) {  // the pair de-duplication is defined by ascending face order (see k_sort_tile_lists)
-        k_sort_tile_lists<<<ws.NT, 256, 0, s>>>(ws.tile_count, ws.tile_offset, ws.list, ws.capacity, ws.list_tile);
+        k_sort_tile_lists<<<ws.NT, 256, 0, s>>>(ws.tile_count, ws.tile_offset, ws.list, ws.capacity, ws.list_tile, nullptr);
         ST3D_LAUNCH_OK("k_sort_tile_lists");
         tile_list = ws.list_tile;
     }
 #define ST3D_FINE(KK)                                                                                            \
     k_fine<0, KK><<<ws.NT, 256, 0, s>>>(ws.rec, ws.tile_count, ws.tile_offset, tile_list, ws.capacity, H, W, ws.TX, \
                                         ws.TY, blur_radius, perspective_correct, clip_barycentric_coords,           \
-                                        clipped_faces_neighbor_idx, fo, sp)
+                                        clipped_faces_neighbor_idx, fo, sp, nullptr, nullptr, -INFINITY, 0, nullptr)
     if (K == 1) ST3D_FINE(1);
     else if (K == 2) ST3D_FINE(2);
     else if (K <= 4) {
@@ -1209,8 +1276,14 @@ extern "C" int st3d_render_forward(const st3d_render_args* a, st3d_stream_t stre
     int rc = run_bins(ws, nullptr, a->faces, nullptr, nullptr, a->N, a->F, a->V, a->H, a->W, a->blur_radius,
                       (a->cull_backfaces ? 1 : 0) | (a->cull_to_frustum ? 2 : 0), true, z_clip, s);
     if (rc != ST3D_OK) return rc;
+    // faces cut by the near plane (hdr[5], set by k_setup): the pair rule of their halves depends on the order faces are
+    // visited in, which upstream defines as ascending -- sort the tile lists, but only when the call has such faces
+    k_sort_tile_lists<<<ws.NT, 256, 0, s>>>(ws.tile_count, ws.tile_offset, ws.list, ws.capacity, ws.list_tile, ws.hdr + 5);
+    ST3D_LAUNCH_OK("k_sort_tile_lists");
     k_fine<1, 1><<<ws.NT, 256, 0, s>>>(ws.rec, ws.tile_count, ws.tile_offset, ws.list, ws.capacity, a->H, a->W,
-                                           ws.TX, ws.TY, a->blur_radius, 1, a->blur_radius > 0.0f ? 1 : 0, nullptr, fo, sp);
+                                           ws.TX, ws.TY, a->blur_radius, 1, a->blur_radius > 0.0f ? 1 : 0, nullptr, fo, sp,
+                                           ws.list_tile, ws.hdr + 5, z_clip,
+                                           (a->cull_backfaces ? 1 : 0) | (a->cull_to_frustum ? 2 : 0), ws.zkey);
     ST3D_LAUNCH_OK("k_fine");
     return ST3D_OK;
 }

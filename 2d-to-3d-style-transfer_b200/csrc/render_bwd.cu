@@ -49,14 +49,27 @@ static __device__ __noinline__ ClipFrag clipped_fragment(FaceVerts v, float z_cl
     return out;
 }
 
+// The same for the binned (blur_radius > 0) path, where the forward recorded WHICH sub-triangle won the pixel (the pair
+// rule of the two halves of a quad depends on what else covered the pixel, so it cannot be re-derived here) and the
+// barycentrics of the sub-triangle are clamped and renormalised before the conversion (clip_barycentric_coords).
+static __device__ __noinline__ ClipFrag clipped_fragment_of(FaceVerts v, float z_clip, float px, float py, int t, bool clip) {
+    ClipFrag out{0.0f, 0.0f, 0.0f, 0.0f, -1.0f, t};
+    ClipTri ct;
+    clip_triangle(v, z_clip, t, ct);
+    float b0, b1, b2;
+    face_recompute(px, py, ct.v, true, clip, b0, b1, b2, out.pz, out.dist);
+    clip_convert_bary(ct, b0, b1, b2, out.b0, out.b1, out.b2);
+    return out;
+}
+
 // Geometry backward through a clipped face: gradients of the unclipped barycentrics (gb), depth and distance
 // -> sub-triangle (face_backward) -> the nine unclipped NDC coordinates (clip_triangle_backward).
 static __device__ __noinline__ FaceGrad clipped_face_backward(FaceVerts v, float z_clip, int t, float px, float py, float gb0,
-                                                       float gb1, float gb2, float g_pz, float g_dist) {
+                                                       float gb1, float gb2, float g_pz, float g_dist, bool clip) {
     ClipTri ct;
     clip_triangle(v, z_clip, t, ct);
     float b0, b1, b2, pz, dist;
-    face_recompute(px, py, ct.v, true, false, b0, b1, b2, pz, dist);
+    face_recompute(px, py, ct.v, true, clip, b0, b1, b2, pz, dist);
     const float gb[3] = {gb0, gb1, gb2}, bc[3] = {b0, b1, b2};
     float gc[3], gcv[9];
 #pragma unroll
@@ -65,7 +78,7 @@ static __device__ __noinline__ FaceGrad clipped_face_backward(FaceVerts v, float
 #pragma unroll
         for (int j = 0; j < 3; ++j) gcv[3 * k + j] = gb[j] * bc[k];
     }
-    const FaceGrad ft = face_backward(px, py, ct.v, true, false, gc[0], gc[1], gc[2], g_pz, g_dist);
+    const FaceGrad ft = face_backward(px, py, ct.v, true, clip, gc[0], gc[1], gc[2], g_pz, g_dist);
     FaceGrad out;
 #pragma unroll
     for (int i = 0; i < 9; ++i) out.g[i] = 0.0f;
@@ -107,7 +120,9 @@ k_render_bwd(const FaceRec* __restrict__ rec, const unsigned long long* __restri
         // so the edge distance (three point-segment distances) is neither recomputed nor differentiated
         const bool skip_dist = sp.out_layout != ST3D_LAYOUT_NHWC_RGBA && clip == 0;
         if (near_clipped) {
-            const ClipFrag cf = clipped_fragment(v, z_clip, px, py, (unsigned)(zkey[pix] >> 32));
+            // hard path: the sub-triangle whose depth is the z-buffer key; binned path: the index k_fine stored
+            const ClipFrag cf = clip != 0 ? clipped_fragment_of(v, z_clip, px, py, (int)(zkey[pix] & 1ull), true)
+                                          : clipped_fragment(v, z_clip, px, py, (unsigned)(zkey[pix] >> 32));
             b0 = cf.b0; b1 = cf.b1; b2 = cf.b2; pz = cf.pz; dist = skip_dist ? -1.0f : cf.dist;
             sub = cf.t;
         } else if (skip_dist) {
@@ -234,7 +249,7 @@ k_render_bwd(const FaceRec* __restrict__ rec, const unsigned long long* __restri
         }
         if (NEED_GEOM) {
             const FaceGrad fg = (near_clipped && sub >= 0)
-                                    ? clipped_face_backward(v, z_clip, sub, px, py, gb0, gb1, gb2, g_pz, g_dist)
+                                    ? clipped_face_backward(v, z_clip, sub, px, py, gb0, gb1, gb2, g_pz, g_dist, clip != 0)
                                     : face_backward(px, py, v, true, clip != 0, gb0, gb1, gb2, g_pz, g_dist);
 #pragma unroll
             for (int i = 0; i < 9; ++i) gv[i] = fg.g[i];

@@ -139,9 +139,9 @@ def _capturing() -> bool:
 
 def read_header(ws: torch.Tensor):
     """Synchronous read of a raster workspace header (for callers that replay captured graphs and therefore own
-    the workspace): (entries needed, overflow flag, unsupported-clip flag)."""
+    the workspace): (entries needed, overflow flag, 1 if the call clipped faces at the near plane)."""
     h = ws[: WS_HEADER_INTS * 4].view(torch.int32).cpu()
-    return int(h[0]) + int(h[6]), int(h[1]), int(h[4])
+    return int(h[0]) + int(h[6]), int(h[1]), int(h[5])
 
 
 _captured_headers: Optional[list] = None     # set by `collect_captured_headers` while a graph is being recorded
@@ -167,11 +167,8 @@ def check_captured_headers(headers) -> None:
     """Raise if a raster call of the LAST finished replay overflowed its work lists or met a case it does not handle
     (the caller has waited for that replay)."""
     for host, key in headers:
-        needed, overflow, clip = int(host[0]) + int(host[6]), int(host[1]), int(host[4])
+        needed, overflow = int(host[0]) + int(host[6]), int(host[1])
         _capacity_hint[key] = max(_capacity_hint.get(key, 0), needed)
-        if clip:
-            raise NotImplementedError("a replayed render met a face crossing the near clipping plane with blur_radius > 0: "
-                                      "the fused renderer clips faces only when blur_radius == 0")
         if overflow:
             raise St3dError(f"a replayed render needed {needed} work-list entries, more than the workspace recorded in "
                             "the graph holds (the mesh moved too far from the one that was captured); the results of that "
@@ -203,15 +200,9 @@ def poll_overflow(block: bool = False) -> None:
         if block:
             ev.synchronize()
         if ev.query():
-            needed, overflow, clip = int(host[0]) + int(host[6]), int(host[1]), int(host[4])   # [6]: back-facing units
+            needed, overflow = int(host[0]) + int(host[6]), int(host[1])   # [6]: back-facing units
             _free_hosts.append(host)
             _capacity_hint[key] = max(_capacity_hint.get(key, 0), needed)
-            if clip:
-                _pending.clear()
-                raise NotImplementedError("a face has a vertex in front of the near clipping plane (z < z_clip) and "
-                                          "blur_radius > 0: the fused renderer clips faces only when blur_radius == 0; "
-                                          "the images of that render call must not be used (MeshRasterizer + shader, "
-                                          "the Fragments path, clips for any blur_radius)")
             if overflow:
                 _pending.clear()
                 raise St3dError(f"tile bins overflowed: {needed} (face,tile) pairs needed; results of that call are "

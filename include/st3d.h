@@ -67,11 +67,10 @@ size_t st3d_raster_workspace_size(int N, int64_t F_total, int H, int W, int64_t 
  * [0] (+ [6]) = work-list entries needed by the last call ((face,tile) pairs of the binned path; face units of the
  * hard path, [0] the front-facing ones queued from the first slot up, [6] the others queued from the last slot down),
  * [1] = 1 if that list overflowed (results invalid, re-run with a larger list_capacity),
- * [2] = capacity in entries, [5] = 1 if the call clipped faces against the near plane (informational),
- * [4] = 1 if some face has a vertex nearer than st3d_render_args.z_clip on a path that does not clip: the fused
- * renderer clips such faces inside its kernels (PyTorch3D clip_faces semantics, csrc/clip.cuh) when blur_radius
- * is 0 -- the reference's configuration; with blur_radius > 0 it only reports them here and the caller must treat
- * the render as unsupported (use the operator-boundary path, which clips around st3d_rasterize_meshes_forward). */
+ * [2] = capacity in entries, [5] = 1 if the call clipped faces against the near plane (PyTorch3D clip_faces semantics,
+ * csrc/clip.cuh: inside the kernels of the fused renderer, for hard and for blur_radius > 0 rasterization alike; the
+ * tile-bin path then walks its lists in face order, which upstream's rule for the two halves of a clipped quad
+ * depends on), [4] reserved (0). */
 #define ST3D_WS_HEADER_INTS 16
 
 /* _C.rasterize_meshes: face_verts (F_total,3,3) in NDC (z = view depth); mesh n owns faces

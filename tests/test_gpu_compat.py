@@ -207,6 +207,32 @@ def test_camera_inside_the_mesh_is_clipped_like_the_oracle(scene):
     assert (fragments.bary_coords.cpu()[hit] - frag["bary_exact"][hit]).abs().max().item() <= 1e-4
 
 
+def test_soft_renderer_one_face_per_pixel_is_fused_and_clips(scene):
+    """RasterizationSettings(blur_radius > 0, faces_per_pixel = 1): the fused tile-bin path (soft edges, clamped
+    barycentrics), near-plane clipping included -- same picture as the oracle, and as the Fragments + shader path."""
+    from pytorch3d.renderer import (AmbientLights, FoVPerspectiveCameras, MeshRasterizer, MeshRenderer,
+                                    RasterizationSettings, SoftPhongShader)
+    from st3d import ops
+    sc, dev = scene, scene["dev"]
+    blur = 4e-4
+    cases = [(sc["cameras"].R.cpu(), sc["cameras"].T.cpu()), (torch.eye(3)[None], torch.tensor([[0.0, 0.0, 0.2]]))]
+    for R, T in cases:                                  # outside views, then a camera inside the mesh
+        cams = FoVPerspectiveCameras(R=R, T=T, device=dev)
+        rs = RasterizationSettings(image_size=S, blur_radius=blur, faces_per_pixel=1)
+        renderer = MeshRenderer(rasterizer=MeshRasterizer(cameras=cams, raster_settings=rs),
+                                shader=SoftPhongShader(device=dev, cameras=cams, lights=AmbientLights(device=dev)))
+        assert renderer._can_fuse(sc["mesh"], {})
+        rgba = renderer(meshes_world=sc["mesh"], cameras=cams)
+        torch.cuda.synchronize()
+        ops.poll_overflow(block=True)
+        want = ro.render_views(sc["verts"], sc["faces"], R, T, S, texture=sc["tex"][0], verts_uvs=sc["verts_uvs"],
+                               faces_uvs=sc["faces_uvs"], nthreads=8, blur_radius=blur)
+        assert (rgba.cpu() - want).abs().max().item() <= 1e-4
+        general = renderer.shader(renderer.rasterizer(sc["mesh"], cameras=cams), sc["mesh"], cameras=cams)
+        assert (general - rgba).abs().max().item() <= 1e-4
+        assert ((want[..., 3] > 0) & (want[..., 3] < 0.999)).sum() > 20      # soft edge pixels are there
+
+
 def test_runner_resolves_modules_to_compat(tmp_path):
     script = tmp_path / "probe.py"
     script.write_text(

@@ -426,6 +426,60 @@ def test_near_plane_clipping_fused_matches_oracle(cow, layout, mode):
     _close(g_verts, verts64.grad, tol=2e-4, what="grad_verts")
 
 
+@pytest.mark.parametrize("scene", ["far", "cut_by_the_near_plane"])
+@pytest.mark.parametrize("mode", ["uv", "vertex"])
+@pytest.mark.parametrize("blur", [2e-4, 1.5e-3])
+def test_fused_soft_rasterization_matches_oracle(cow, scene, mode, blur):
+    """The fused renderer with blur_radius > 0 (K = 1, tile-bin path, clamped barycentrics, soft edge pixels), also on a
+    scene whose faces cross the near clip plane: the halves of a clipped quad follow upstream's pair rule
+    (clipped_faces_neighbor_idx: the closer half keeps the pixel), pix_to_face bit-exact, RGBA and every gradient --
+    through the edge distance, the clamped barycentrics and the clipped sub-triangles back to the unclipped vertices --
+    against float64 autograd of the oracle."""
+    ops = _ops()
+    S, gen = 72, torch.Generator().manual_seed(15)
+    if scene == "far":
+        R, T = ro.random_cameras(3, generator=gen)
+    else:
+        R, T = _close_cameras()
+        fv, _, _, _ = _face_verts(cow, R, T)
+        behind = (fv[:, :, 2] < 0.5).sum(1)
+        assert (behind == 1).sum() > 20 and (behind == 2).sum() > 20
+    N = R.shape[0]
+    k00, k11 = ro.fov_scales(60.0)
+    verts64 = cow["verts"].double().requires_grad_(True)
+    tex = torch.rand(40, 56, 3, generator=gen)
+    vrgb = torch.rand(cow["verts"].shape[0], 3, generator=gen)
+    tex64, vrgb64 = tex.double().requires_grad_(True), vrgb.double().requires_grad_(True)
+    kw = dict(texture=tex64, verts_uvs=cow["verts_uvs"].double(), faces_uvs=cow["faces_uvs"]) if mode == "uv" \
+        else dict(verts_rgb=vrgb64)
+    rgba, frag = ro.render_views(verts64, cow["faces"], R, T, S, nthreads=8, return_fragments=True, blur_radius=blur, **kw)
+    wgt = torch.randn(N, S, S, 4, generator=gen).double()
+    (rgba * wgt).sum().backward()
+
+    spec = ops.RenderSpec(image_size=(S, S), k00=k00, k11=k11, layout=ops.LAYOUT_NHWC_RGBA, blur_radius=blur)
+    gkw = dict(face_uvs=cow["verts_uvs"][cow["faces_uvs"]].cuda(), texture=tex.cuda()) if mode == "uv" \
+        else dict(verts_rgb=vrgb.cuda())
+    img, _, p2f, state = ops.render_forward(spec, cow["verts"].cuda(), cow["faces"].cuda(), R.cuda(), T.cuda(), **gkw)
+    torch.cuda.synchronize()
+    ops.poll_overflow(block=True)
+    want_p2f = frag["pix_to_face"][..., 0]
+    hard = ro.render_views(cow["verts"], cow["faces"], R, T, S, nthreads=8, return_fragments=True, verts_rgb=vrgb)[1]["pix_to_face"]
+    assert ((want_p2f >= 0) & (hard[..., 0] < 0)).sum() > 50         # the blur does add soft pixels outside the faces
+    assert torch.equal(p2f.cpu().long(), want_p2f), "pix_to_face differs from the oracle"
+    _close(img, rgba, what="rgba")
+    g_tex, g_verts, g_rgb = ops.render_backward(state, wgt.float().cuda(), need_texture=True, need_verts=True,
+                                                need_verts_rgb=True)
+    torch.cuda.synchronize()
+    if mode == "uv":
+        _close(g_tex, tex64.grad, what="grad_texture")
+    else:
+        _close(g_rgb, vrgb64.grad, what="grad_verts_rgb")
+    # the alpha / colour of a soft edge pixel is sigmoid(-d / sigma) with sigma = 1e-4 and d a DIFFERENCE of squared NDC
+    # lengths of the same size: its slope amplifies the fp32 rounding of d by 1 / sigma, so the vertex gradient of a soft
+    # render is conditioned ~10x worse than that of a hard one (measured 5e-4 .. 6e-4 of the largest entry)
+    _close(g_verts, verts64.grad, tol=1e-3, what="grad_verts")
+
+
 @pytest.mark.parametrize("K,blur", [(1, 0.0), (2, 0.0), (3, 1e-3), (8, 4e-4)])
 def test_near_plane_clipping_fragments_match_oracle(cow, K, blur):
     """Operator-boundary path: torch-level clip_faces around st3d_rasterize_meshes_forward, as upstream does, incl.
