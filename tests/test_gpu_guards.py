@@ -131,6 +131,10 @@ def test_render_ops_stay_inside_their_buffers(guarded, cow):
     img, mask, p2f, state = ops.render_forward(spec, verts, faces.int(), Rc, Tc, face_uvs=fuv, texture=tex)
     ops.render_backward(state, torch.randn_like(img), need_texture=True, need_verts=True)
     g.verify("render of a near-plane-clipped scene")
+    spec = ops.RenderSpec(image_size=(67, 41), k00=k00, k11=k11, layout=ops.LAYOUT_NHWC_RGBA, blur_radius=6e-4)
+    img, mask, p2f, state = ops.render_forward(spec, verts, faces.int(), Rc, Tc, face_uvs=fuv, texture=tex)
+    ops.render_backward(state, torch.randn_like(img), need_texture=True, need_verts=True)
+    g.verify("soft render (tile bins) of a near-plane-clipped scene")
     ops.poll_overflow(block=True)
 
 

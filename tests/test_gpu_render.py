@@ -617,6 +617,17 @@ def test_random_soups_cut_by_the_near_plane_bit_exact(seed):
         torch.cuda.synchronize()
         nbad = (got[0].cpu() != fg["pix_to_face"]).sum().item()
         assert nbad == 0, f"Fragments path, seed {seed}, K={K}, blur={blur}: {nbad} entries differ"
+    # the fused renderer's soft path (blur_radius > 0, one face per pixel): overlapping clipped quads, whose two halves
+    # compete under upstream's pair rule in face order
+    for blur in (5e-4, 4e-3):
+        rg, fg = ro.render_views(verts, faces, R, T, S, verts_rgb=vrgb, nthreads=8, return_fragments=True, blur_radius=blur)
+        spec = ops.RenderSpec(image_size=S, k00=k00, k11=k11, blur_radius=blur)
+        img, _, p2f, _ = ops.render_forward(spec, verts.cuda(), faces.cuda(), R.cuda(), T.cuda(), verts_rgb=vrgb.cuda())
+        torch.cuda.synchronize()
+        ops.poll_overflow(block=True)
+        nbad = (p2f.cpu().long() != fg["pix_to_face"][..., 0]).sum().item()
+        assert nbad == 0, f"fused soft path, seed {seed}, blur={blur}: {nbad} pixels differ"
+        _close(img, rg, what="rgba of the clipped soup, soft")
 
 
 # ------------------------------------------------------------------------------------------------------------
