@@ -8,6 +8,9 @@ un-pinned third-party dependency that is absent from /root/reference and from th
 functions below restate its published algorithm as recorded in SURVEY.md Appendix A
 (A.1 cameras, A.2 raster settings, A.3 rasterization, A.4 texture sampling, A.5 Phong,
 A.6 softmax_rgb_blend).  PARITY UNPINNED at that boundary (no upstream golden vectors on disk).
+What pins the restatement instead (tests/test_oracle_pinned.py): the definitions of A.3 / A.4 / A.6 recomputed in exact
+rational arithmetic for a triangle with three different depths (inside test, perspective-corrected barycentrics, depth,
+signed edge distance of every pixel), hand-derived clip geometry, and texture sampling through torch's own grid_sample.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 import this module.
