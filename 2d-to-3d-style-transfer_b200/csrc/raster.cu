@@ -229,16 +229,17 @@ __global__ void k_fill(const FaceRec* __restrict__ rec, const int64_t* __restric
 // path, lists of a few hundred entries.
 __global__ void __launch_bounds__(256)
 k_sort_tile_lists(const int* __restrict__ tile_count, const int* __restrict__ tile_offset, const int* __restrict__ list,
-                  int64_t capacity, int* __restrict__ sorted, const int* __restrict__ only_if) {
+                  int64_t capacity, int* __restrict__ sorted, const int* __restrict__ only_if, int NT) {
     if (only_if && *only_if == 0) return;   // fused renderer: nothing was clipped in this call, the order is irrelevant
-    const int t = blockIdx.x;
-    const int base = tile_offset[t];
-    const int n = (int)max((int64_t)0, min((int64_t)tile_count[t], capacity - base));
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int v = list[base + i];
-        int rank = 0;
-        for (int j = 0; j < n; ++j) rank += __ldg(list + base + j) < v ? 1 : 0;  // a face appears once per tile
-        sorted[base + rank] = v;
+    for (int t = blockIdx.x; t < NT; t += gridDim.x) {
+        const int base = tile_offset[t];
+        const int n = (int)max((int64_t)0, min((int64_t)tile_count[t], capacity - base));
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int v = list[base + i];
+            int rank = 0;
+            for (int j = 0; j < n; ++j) rank += __ldg(list + base + j) < v ? 1 : 0;  // a face appears once per tile
+            sorted[base + rank] = v;
+        }
     }
 }
 
@@ -1187,7 +1188,8 @@ extern "C" int st3d_rasterize_meshes_forward(const float* face_verts, const int6
     if (rc != ST3D_OK) return rc;
     const int* tile_list = ws.list;
     if (clipped_faces_neighbor_idx) {  // the pair de-duplication is defined by ascending face order (see k_sort_tile_lists)
-        k_sort_tile_lists<<<ws.NT, 256, 0, s>>>(ws.tile_count, ws.tile_offset, ws.list, ws.capacity, ws.list_tile, nullptr);
+        k_sort_tile_lists<<<std::min(ws.NT, 148 * 8), 256, 0, s>>>(ws.tile_count, ws.tile_offset, ws.list, ws.capacity, ws.list_tile,
+                                                                   nullptr, ws.NT);
         ST3D_LAUNCH_OK("k_sort_tile_lists");
         tile_list = ws.list_tile;
     }
@@ -1278,7 +1280,8 @@ extern "C" int st3d_render_forward(const st3d_render_args* a, st3d_stream_t stre
     if (rc != ST3D_OK) return rc;
     // faces cut by the near plane (hdr[5], set by k_setup): the pair rule of their halves depends on the order faces are
     // visited in, which upstream defines as ascending -- sort the tile lists, but only when the call has such faces
-    k_sort_tile_lists<<<ws.NT, 256, 0, s>>>(ws.tile_count, ws.tile_offset, ws.list, ws.capacity, ws.list_tile, ws.hdr + 5);
+    k_sort_tile_lists<<<std::min(ws.NT, 148 * 8), 256, 0, s>>>(ws.tile_count, ws.tile_offset, ws.list, ws.capacity, ws.list_tile,
+                                                               ws.hdr + 5, ws.NT);
     ST3D_LAUNCH_OK("k_sort_tile_lists");
     k_fine<1, 1><<<ws.NT, 256, 0, s>>>(ws.rec, ws.tile_count, ws.tile_offset, ws.list, ws.capacity, a->H, a->W,
                                            ws.TX, ws.TY, a->blur_radius, 1, a->blur_radius > 0.0f ? 1 : 0, nullptr, fo, sp,
