@@ -33,12 +33,25 @@ def apply_background(tensors, masks, background_type="noise", background=None):
     return tensors * masks + fill * (1 - masks)
 
 
+_decoded = {}       # (path, size, mtime, bytes) -> decoded tensor on `device`
+
+
 def load_as_tensor(image_path, size=512):
-    """utils.py:34-44: RGB image squashed to size x size, (3,size,size) in [0,1]."""
-    with Image.open(image_path) as im:
-        im = im.convert("RGB")
-        tensor = transforms.ToTensor()(transforms.Resize((size, size))(im))
-    return tensor[:3].to(device)
+    """utils.py:34-44: RGB image squashed to size x size, (3,size,size) in [0,1].
+    second_approach.py:157 calls this for the style image in EVERY batch of every epoch (a JPEG decode + resize of
+    10-20 ms on the host): the decoded tensor is kept per (file, size, mtime) and every call
+    returns a fresh copy of it, so callers may still write into what they get."""
+    st = os.stat(image_path)
+    key = (os.path.abspath(image_path), int(size) if isinstance(size, int) else tuple(size), st.st_mtime_ns, st.st_size)
+    cached = _decoded.get(key)
+    if cached is None:
+        with Image.open(image_path) as im:
+            im = im.convert("RGB")
+            tensor = transforms.ToTensor()(transforms.Resize((size, size))(im))
+        if len(_decoded) >= 16:
+            _decoded.pop(next(iter(_decoded)))
+        cached = _decoded[key] = tensor[:3].to(device)
+    return cached.clone()
 
 
 def get_vgg():

@@ -175,3 +175,26 @@ def test_meshes_and_textures_index_into_a_batch():
     single = TexturesUV(maps=[one], faces_uvs=torch.zeros(1, 1, 3, dtype=torch.int64), verts_uvs=torch.rand(1, 3, 2))
     single.maps_padded().sum().backward()
     assert torch.equal(one.grad, torch.ones_like(one))
+
+
+def test_style_image_decode_is_cached_per_file_size_and_mtime(tmp_path):
+    """utils.load_as_tensor (utils.py:34-44) is called for the style image in every batch (second_approach.py:157): the
+    decode happens once per (file, size, mtime), every call returns its own copy, a rewritten file is decoded again."""
+    import os
+    import numpy as np
+    import utils
+    from PIL import Image
+    path = str(tmp_path / "style.png")
+    Image.fromarray((np.arange(24 * 30 * 3) % 251).astype(np.uint8).reshape(24, 30, 3)).save(path)
+    utils._decoded.clear()
+    a = utils.load_as_tensor(path, size=16)
+    assert tuple(a.shape) == (3, 16, 16) and len(utils._decoded) == 1
+    b = utils.load_as_tensor(path, size=16)
+    assert torch.equal(a, b) and a.data_ptr() != b.data_ptr() and len(utils._decoded) == 1
+    a.zero_()                                                   # a caller writing into its copy does not reach the cache
+    assert torch.equal(utils.load_as_tensor(path, size=16), b)
+    assert tuple(utils.load_as_tensor(path, size=8).shape) == (3, 8, 8) and len(utils._decoded) == 2
+    Image.fromarray(np.full((24, 30, 3), 200, dtype=np.uint8)).save(path)
+    os.utime(path, ns=(1, 2_000_000_000_000_000_000))          # a different mtime even on coarse clocks
+    c = utils.load_as_tensor(path, size=16)
+    assert torch.allclose(c, torch.full((3, 16, 16), 200 / 255.0)) and not torch.equal(c, b)

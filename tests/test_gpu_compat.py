@@ -233,6 +233,36 @@ def test_soft_renderer_one_face_per_pixel_is_fused_and_clips(scene):
         assert ((want[..., 3] > 0) & (want[..., 3] < 0.999)).sum() > 20      # soft edge pixels are there
 
 
+def test_repeated_style_image_is_walked_once_with_the_same_loss(scene):
+    """losses.compute_perceptual_loss with the style image repeated batch_size times (second_approach.py:157): the
+    drop-in walks the VGG over one copy; loss and gradient equal those of the B-copy walk, and B different style
+    images are still walked one by one."""
+    import losses
+    from st3d import losses as st_losses
+    dev = scene["dev"]
+    from st3d.vgg import fuse_vgg_features
+    model = fuse_vgg_features(_vgg(dev), channels_last=True)
+    g = torch.Generator().manual_seed(77)
+    cur = torch.rand(3, 3, S, S, generator=g).to(dev)
+    content = torch.rand(3, 3, S, S, generator=g).to(dev)
+    one = torch.rand(1, 3, S, S, generator=g).to(dev)
+    rep = one.repeat(3, 1, 1, 1)
+    assert losses._one_style_image(rep).shape[0] == 1
+    a = cur.clone().requires_grad_(True)
+    la = losses.compute_perceptual_loss(a, content, rep, model)
+    la.backward()
+    b = cur.clone().requires_grad_(True)
+    lb = st_losses.compute_perceptual_loss(b, content, rep, model)      # all three copies through the VGG
+    lb.backward()
+    assert abs(la.item() - lb.item()) <= 1e-5 * abs(lb.item())
+    assert ((a.grad - b.grad).abs().max() / b.grad.abs().max()).item() <= 1e-4
+    different = torch.rand(3, 3, S, S, generator=g).to(dev)
+    assert losses._one_style_image(different).shape[0] == 3
+    c = cur.clone().requires_grad_(True)
+    lc = losses.compute_perceptual_loss(c, content, different, model)
+    assert abs(lc.item() - lb.item()) > 1e-3 * abs(lb.item())
+
+
 def test_runner_resolves_modules_to_compat(tmp_path):
     script = tmp_path / "probe.py"
     script.write_text(
