@@ -73,7 +73,68 @@ def get_vgg():
     return vgg
 
 
+# ---- image dumps (second_approach.py:183-185 writes every view of every batch as a PNG) ----------------
+# A PNG of a 512^2 view costs ~20 ms of host time to encode -- 8 views per step against a 10 ms GPU step.  For CUDA tensors
+# tensor_to_image therefore returns a stand-in for the PIL image: the 8-bit conversion runs on the GPU, the copy to pinned host
+# memory is asynchronous, and `.save(path)` hands the encoding to a worker thread (the same path always to the same worker, so a
+# later dump of a view replaces an earlier one in order).  Everything is written before the interpreter exits, or when
+# flush_image_writes() is called; any other use of the object builds the real PIL image on the spot.
+# ST3D_SYNC_IMAGE_WRITES=1 restores the synchronous behaviour.
+_WRITERS, _PENDING = [], []
+
+
+def _writer_for(path):
+    from concurrent.futures import ThreadPoolExecutor
+    if not _WRITERS:
+        import atexit
+        _WRITERS.extend(ThreadPoolExecutor(max_workers=1, thread_name_prefix="st3d-png") for _ in range(4))
+        atexit.register(flush_image_writes)
+    return _WRITERS[hash(os.path.abspath(path)) % len(_WRITERS)]
+
+
+def flush_image_writes():
+    """Waits for every image handed to `.save()` so far; re-raises the first error a writer met."""
+    pending, _PENDING[:] = list(_PENDING), []
+    errors = [f.exception() for f in pending]
+    for e in errors:
+        if e is not None:
+            raise e
+
+
+class _PendingImage:
+    def __init__(self, tensor):
+        t = tensor.detach().squeeze(0).clamp(0, 1)
+        u8 = t.mul(255).to(torch.uint8)                                # ToPILImage: pic.mul(255).byte()
+        u8 = (u8.permute(1, 2, 0) if u8.dim() == 3 else u8).contiguous()
+        self._host = torch.empty(u8.shape, dtype=torch.uint8, pin_memory=True)
+        self._host.copy_(u8, non_blocking=True)
+        self._ready = torch.cuda.Event()
+        self._ready.record()
+        self._pil = None
+
+    def _image(self):
+        if self._pil is None:
+            self._ready.synchronize()
+            a = self._host.numpy()
+            self._pil = Image.fromarray(a[..., 0] if a.ndim == 3 and a.shape[-1] == 1 else a)
+        return self._pil
+
+    def save(self, path, *args, **kwargs):
+        if isinstance(path, (str, os.PathLike)):
+            _PENDING.append(_writer_for(path).submit(lambda: self._image().save(path, *args, **kwargs)))
+            if len(_PENDING) > 256:                                     # bound the backlog (and surface errors early)
+                flush_image_writes()
+        else:
+            self._image().save(path, *args, **kwargs)                   # a file object: the caller wants it written now
+
+    def __getattr__(self, name):
+        return getattr(self._image(), name)
+
+
 def tensor_to_image(tensor):
+    """utils.py:56-61.  CUDA tensors: see the note on image dumps above."""
+    if tensor.is_cuda and os.environ.get("ST3D_SYNC_IMAGE_WRITES") != "1":
+        return _PendingImage(tensor)
     return transforms.ToPILImage()(tensor.detach().clone().squeeze(0).clamp(0, 1).cpu())
 
 

@@ -263,6 +263,33 @@ def test_repeated_style_image_is_walked_once_with_the_same_loss(scene):
     assert abs(lc.item() - lb.item()) > 1e-3 * abs(lb.item())
 
 
+def test_image_dumps_are_written_by_worker_threads_with_the_same_pixels(tmp_path, monkeypatch):
+    """utils.tensor_to_image(...).save(path) for CUDA tensors (second_approach.py:183-185 dumps every view of every
+    batch): 8-bit conversion on the GPU, encoding on a worker thread -- the same pixels as torchvision's ToPILImage on the
+    host, later dumps of a path replace earlier ones in order, and the object still behaves as a PIL image."""
+    import numpy as np
+    import utils
+    from PIL import Image
+    from torchvision import transforms
+    g = torch.Generator().manual_seed(4)
+    imgs = [(torch.rand(3, 37, 53, generator=g) * 1.4 - 0.2).cuda() for _ in range(6)]     # values outside [0, 1] too
+    for i, t in enumerate(imgs):
+        utils.tensor_to_image(t).save(str(tmp_path / f"view_{i % 2}.png"))                 # two paths, written three times each
+    mono = torch.rand(1, 1, 20, 24, generator=g).cuda()
+    utils.tensor_to_image(mono).save(str(tmp_path / "mono.png"))
+    utils.flush_image_writes()
+    for k in (0, 1):
+        want = np.asarray(transforms.ToPILImage()(imgs[4 + k].clamp(0, 1).cpu()))
+        with Image.open(tmp_path / f"view_{k}.png") as im:
+            assert im.mode == "RGB" and np.array_equal(np.asarray(im), want)
+    with Image.open(tmp_path / "mono.png") as im:
+        assert im.mode == "L" and np.array_equal(np.asarray(im), np.asarray(transforms.ToPILImage()(mono[0].cpu())))
+    pending = utils.tensor_to_image(imgs[0])
+    assert pending.size == (53, 37) and pending.mode == "RGB"                              # any other use: the PIL image itself
+    monkeypatch.setenv("ST3D_SYNC_IMAGE_WRITES", "1")
+    assert isinstance(utils.tensor_to_image(imgs[0]), Image.Image)
+
+
 def test_runner_resolves_modules_to_compat(tmp_path):
     script = tmp_path / "probe.py"
     script.write_text(
