@@ -77,19 +77,23 @@ def get_vgg():
 # A PNG of a 512^2 view costs ~20 ms of host time to encode -- 8 views per step against a 10 ms GPU step.  For CUDA tensors
 # tensor_to_image therefore returns a stand-in for the PIL image: the 8-bit conversion runs on the GPU, the copy to pinned host
 # memory is asynchronous, and `.save(path)` hands the encoding to a worker thread (the same path always to the same worker, so a
-# later dump of a view replaces an earlier one in order).  Everything is written before the interpreter exits, or when
+# later dump of a view replaces an earlier one in order; PNGs at zlib level 1).  Everything is written before the interpreter exits, or when
 # flush_image_writes() is called; any other use of the object builds the real PIL image on the spot.
 # ST3D_SYNC_IMAGE_WRITES=1 restores the synchronous behaviour.
-_WRITERS, _PENDING = [], []
+_WRITERS, _PENDING, _WRITER_OF = [], [], {}
 
 
 def _writer_for(path):
     from concurrent.futures import ThreadPoolExecutor
     if not _WRITERS:
         import atexit
-        _WRITERS.extend(ThreadPoolExecutor(max_workers=1, thread_name_prefix="st3d-png") for _ in range(4))
+        n = max(2, min(16, (os.cpu_count() or 4) - 1))
+        _WRITERS.extend(ThreadPoolExecutor(max_workers=1, thread_name_prefix="st3d-png") for _ in range(n))
         atexit.register(flush_image_writes)
-    return _WRITERS[hash(os.path.abspath(path)) % len(_WRITERS)]
+    key = os.path.abspath(path)
+    if key not in _WRITER_OF:                   # paths are spread evenly; one path stays with one (FIFO) worker
+        _WRITER_OF[key] = len(_WRITER_OF) % len(_WRITERS)
+    return _WRITERS[_WRITER_OF[key]]
 
 
 def flush_image_writes():
@@ -121,6 +125,8 @@ class _PendingImage:
 
     def save(self, path, *args, **kwargs):
         if isinstance(path, (str, os.PathLike)):
+            if str(path).lower().endswith(".png"):
+                kwargs.setdefault("compress_level", 1)                  # same pixels, a third of the encoding time
             _PENDING.append(_writer_for(path).submit(lambda: self._image().save(path, *args, **kwargs)))
             if len(_PENDING) > 256:                                     # bound the backlog (and surface errors early)
                 flush_image_writes()
