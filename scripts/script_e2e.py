@@ -57,4 +57,39 @@ for label, sync in (("png_synchronous", True), ("png_worker_threads", False)):
     ms, lag = run(60, sync)
     res[label] = {"ms_per_epoch": round(ms, 2), "last_log_line_to_exit_s": round(lag, 2)}
 res["speedup"] = round(res["png_synchronous"]["ms_per_epoch"] / res["png_worker_threads"]["ms_per_epoch"], 2)
+
+
+def run_first(steps=400, first=100):
+    """first_approach.py unchanged at BASELINE configs[0] (1 view x 256^2): ms per texture-fit step (first_approach.py:191-217:
+    build_mesh, render_meshes, compute_first_approach_loss, backward, Adam, loss.item(), one log line per step)."""
+    out = tempfile.mkdtemp(prefix="out1_", dir=work)
+    env = dict(os.environ, ST3D_SEED="7", ST3D_VGG_RANDOM_INIT="1", PYTHONPATH=PKG + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    cmd = [sys.executable, "-m", "st3d.run", os.path.join(os.path.dirname(script), "first_approach.py"), "--n_views", "1",
+           "--batch_size", "1", "--size", "256", "--n_style_transfer_steps", "50", "--n_mse_steps", str(steps),
+           "--obj_path", os.path.join(work, "cow.obj"), "--style_path", os.path.join(work, "Style_1.png"), "--output_path", out]
+    p = subprocess.Popen(cmd, env=env, cwd=out, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+    log, stamps = os.path.join(out, "log.txt"), {}
+    while p.poll() is None:
+        try:
+            n = os.path.getsize(log)
+        except OSError:
+            n = 0
+        if n not in stamps:
+            try:
+                with open(log) as fh:
+                    stamps.setdefault(sum(1 for line in fh if line.startswith("Batch 0, Step")), time.perf_counter())
+            except OSError:
+                pass
+            stamps[n] = stamps.get(n, 0.0)
+        time.sleep(0.001)
+    assert p.returncode == 0, p.stderr.read()[-3000:]
+    lines = {k: v for k, v in stamps.items() if k <= steps and v > 0.0}
+    last = max(lines)
+    lo = min(k for k in lines if k >= first)
+    return (lines[last] - lines[lo]) / (last - lo) * 1e3
+
+
+res["first_approach_fit_step"] = {"workload": "first_approach.py unchanged, cow, 1 view x 256^2 (BASELINE configs[0]): one texture-fit step "
+                                              "incl. build_mesh, loss.item() and the log write",
+                                  "ms_per_step": round(run_first(), 3)}
 print(json.dumps(res))
