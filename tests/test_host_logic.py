@@ -99,7 +99,10 @@ def _worker(rank, world, port, q):
     for w in works:
         w.wait()
     assert a.grad.data_ptr() == flat.data_ptr()         # still views: reduced where they lie
-    q.put((rank, tex.grad.clone(), verts.grad.clone(), unused.grad is None, a.grad.clone(), b.grad.clone()))
+    # by value (numpy), not as shared-memory tensors: those are rebuilt in the parent through a socket of THIS process,
+    # which may be gone by the time the parent reads the queue
+    q.put((rank, tex.grad.numpy().copy(), verts.grad.numpy().copy(), unused.grad is None, a.grad.numpy().copy(),
+           b.grad.numpy().copy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -141,7 +144,8 @@ def test_view_sharded_gradient_allreduce_gloo():
         if out is not None:
             break
     assert out is not None, "the gloo ranks did not come up in three attempts"
-    out = sorted(out, key=lambda t: t[0])
+    out = sorted(((r, torch.from_numpy(t), torch.from_numpy(v), u, torch.from_numpy(a), torch.from_numpy(b))
+                  for r, t, v, u, a, b in out), key=lambda t: t[0])
     want_tex = sum(torch.rand(4, 4, 3, generator=torch.Generator().manual_seed(100 + r)) for r in range(world))
 
     def third_and_fourth_draws(r):
