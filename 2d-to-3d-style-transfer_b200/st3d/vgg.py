@@ -24,58 +24,10 @@ import torch
 import torch.nn as nn
 
 
-# ---- the 3-channel first layer ----------------------------------------------------------------------------------------
-# cuDNN's NHWC tensor-core convolutions want a channel count that is a multiple of 8.  Given the 3-channel image of VGG conv1_1
-# it pads the tensor itself (two helper kernels) and then runs an index-based fallback kernel: 253 us forward, 477 us data
-# gradient at 8 x 512^2, against 156 / 359 us for the same convolution on an 8-channel input (scripts/conv1_pad_probe.py).  So
-# the image is zero-padded to 8 channels here and the frozen weights get five zero input channels: the same sums, the data
-# gradient bit-identical, the forward equal to TF32 rounding.  ST3D_VGG_PAD_CONV1=0 turns it off.
-_PAD_TO = 8
-_padded_weights: dict = {}
-
-
-def _pads_first_layer(x, weight, groups) -> bool:
-    import os
-    return (x.is_cuda and x.dim() == 4 and x.shape[1] == 3 and weight.shape[1] == 3 and groups == 1
-            and x.dtype == torch.float32 and not weight.requires_grad
-            and x.is_contiguous(memory_format=torch.channels_last) and os.environ.get("ST3D_VGG_PAD_CONV1", "1") != "0")
-
-
-def _padded_weight(weight):
-    key = (weight.device, weight.data_ptr(), tuple(weight.shape))
-    hit = _padded_weights.get(key)
-    if hit is None or hit[1] != weight._version:
-        w = weight.new_zeros((weight.shape[0], _PAD_TO) + tuple(weight.shape[2:]))
-        w[:, :3] = weight.detach()
-        hit = _padded_weights[key] = (weight, weight._version, w.contiguous(memory_format=torch.channels_last))
-    return hit[2]
-
-
-def _conv_relu(x, weight, bias, stride, padding, dilation, groups):
-    if _pads_first_layer(x, weight, groups):
-        x = torch.nn.functional.pad(x, (0, 0, 0, 0, 0, _PAD_TO - 3))        # channels 3..7 = 0; stays channels_last
-        weight = _padded_weight(weight)
-    return torch.cudnn_convolution_relu(x, weight, bias, stride, padding, dilation, groups)
-
-
-def _conv_backward(g, x, weight, stride, padding, dilation, groups, need):
-    """aten.convolution_backward; for the padded first layer the data gradient comes back as the first three channels (a
-    strided view) of the 8-channel result -- its consumers (render backward, AccumulateGrad) take any strides."""
-    if _pads_first_layer(x, weight, groups) and not need[1]:
-        N, _, H, W = x.shape
-        shape_only = torch.empty((N, _PAD_TO, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
-        gx, _, gb = torch.ops.aten.convolution_backward(g, shape_only, _padded_weight(weight), [weight.shape[0]], list(stride),
-                                                        list(padding), list(dilation), False, [0, 0], groups,
-                                                        [need[0], False, need[2]])    # (the input's VALUES feed wgrad only)
-        return (gx[:, :3] if gx is not None else None), None, gb
-    return torch.ops.aten.convolution_backward(g, x, weight, [weight.shape[0]], list(stride), list(padding), list(dilation),
-                                               False, [0, 0], groups, need)
-
-
 class _ConvBiasReLUFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, stride, padding, dilation, groups, premasked):
-        y = _conv_relu(x, weight, bias, stride, padding, dilation, groups)
+        y = torch.cudnn_convolution_relu(x, weight, bias, stride, padding, dilation, groups)
         ctx.conf = (stride, padding, dilation, groups)
         # the only consumer is a libst3d pool whose backward already applies this layer's ReLU mask
         ctx.premasked = bool(premasked) and _ops().maxpool_supported(y)
@@ -89,7 +41,8 @@ class _ConvBiasReLUFn(torch.autograd.Function):
         # ReLU backward from the saved output (skipped when the pool behind this layer has done it already)
         g = grad_y if ctx.premasked else torch.ops.aten.threshold_backward(grad_y, y, 0.0)
         need = [ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]]
-        gx, gw, gb = _conv_backward(g, x, weight, stride, padding, dilation, groups, need)
+        gx, gw, gb = torch.ops.aten.convolution_backward(g, x, weight, [weight.shape[0]], list(stride), list(padding),
+                                                         list(dilation), False, [0, 0], groups, need)
         return gx, gw, gb, None, None, None, None, None
 
 
@@ -111,7 +64,7 @@ class _ConvReLUStyleTapFn(torch.autograd.Function):
         """acc None: returns (y, this layer's loss term).  acc (1,) float32: the kernel ADDS loss_weight x term to it in
         place and (y, acc) is returned -- a whole perceptual loss is then one accumulator, not a tree of scalar kernels."""
         ops = _ops()
-        y = _conv_relu(x, weight, bias, stride, padding, dilation, groups)
+        y = torch.cudnn_convolution_relu(x, weight, bias, stride, padding, dilation, groups)
         B, C, H, W = y.shape
         scale = float(loss_weight) / (B * C * C) / (float(C) ** 2 * float(H) ** 2)
         loss = acc if acc is not None else torch.zeros(1, device=y.device, dtype=torch.float32)
@@ -154,7 +107,8 @@ class _ConvReLUStyleTapFn(torch.autograd.Function):
             g = ops.gram_backward(y, dgram, 1.0, out=out, accumulate=out is not None, precision=precision,
                                   scale_tensor=grad_loss, relu_mask=True, symmetric_dgram=True)
         need = [ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]]
-        gx, gw, gb = _conv_backward(g, x, weight, stride, padding, dilation, groups, need)
+        gx, gw, gb = torch.ops.aten.convolution_backward(g, x, weight, [weight.shape[0]], list(stride), list(padding),
+                                                         list(dilation), False, [0, 0], groups, need)
         return gx, gw, gb, None, None, None, None, None, None
 
 
@@ -168,7 +122,7 @@ class _ConvReLUContentTapFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, content, stride, padding, dilation, groups, acc=None, loss_weight=1.0):
         """acc: as in _ConvReLUStyleTapFn.forward."""
         ops = _ops()
-        y = _conv_relu(x, weight, bias, stride, padding, dilation, groups)
+        y = torch.cudnn_convolution_relu(x, weight, bias, stride, padding, dilation, groups)
         c = content.detach()
         if c.stride() != y.stride() or c.dtype != torch.float32:       # the kernels walk y and c in one element order
             c = torch.empty_like(y).copy_(c)
@@ -197,7 +151,8 @@ class _ConvReLUContentTapFn(torch.autograd.Function):
                 grad_y = torch.empty_like(y).copy_(grad_y)
             g = ops.mse_tap_backward(y, c, grad_y, ctx.scale, scale_tensor=grad_loss)
         need = [ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]]
-        gx, gw, gb = _conv_backward(g, x, weight, stride, padding, dilation, groups, need)
+        gx, gw, gb = torch.ops.aten.convolution_backward(g, x, weight, [weight.shape[0]], list(stride), list(padding),
+                                                         list(dilation), False, [0, 0], groups, need)
         return gx, gw, gb, None, None, None, None, None, grad_loss, None     # acc: passed through
 
 

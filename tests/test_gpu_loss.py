@@ -565,35 +565,3 @@ def test_fused_mesh_regularisers_edge_cases():
                 (vc.grad.cpu().double() - v64.grad).abs().max()
     with pytest.raises(ValueError):
         ml.regularizers(verts, faces)                           # CPU tensors: no library path
-
-
-def test_first_vgg_layer_padded_to_8_channels_gives_the_same_features_and_gradient(monkeypatch):
-    """st3d.vgg pads the 3-channel image (and conv1_1's frozen weights, with zeros) to 8 channels so that cuDNN runs a
-    tensor-core kernel instead of its 3-channel fallback: same features, same image gradient (fp32 convolutions here, so
-    the comparison is not about TF32 rounding), and the gradient is handed on as a (B,3,H,W) view of the 8-channel result."""
-    import torchvision
-    from st3d import losses, vgg as V
-    from st3d.vgg import fuse_vgg_features
-    torch.manual_seed(4)
-    net = torchvision.models.vgg19(weights=None).features.eval().cuda()
-    for p in net.parameters():
-        p.requires_grad_(False)
-    model = fuse_vgg_features(net, channels_last=True)
-    x = torch.rand(2, 3, 48, 80, device="cuda").contiguous(memory_format=torch.channels_last)
-    prev = torch.backends.cudnn.allow_tf32
-    torch.backends.cudnn.allow_tf32 = False
-    try:
-        out = {}
-        for pad in ("1", "0"):
-            monkeypatch.setenv("ST3D_VGG_PAD_CONV1", pad)
-            xi = x.clone().requires_grad_(True)
-            assert V._pads_first_layer(xi, net[0].weight, 1) == (pad == "1")
-            feats = losses.get_features(xi, model)
-            sum((f ** 2).mean() for f in feats.values()).backward()
-            out[pad] = (feats, xi.grad)
-        for k in out["0"][0]:
-            assert _relerr(out["1"][0][k], out["0"][0][k]) <= 1e-5, k
-        assert _relerr(out["1"][1], out["0"][1]) <= 1e-5
-        assert out["1"][1].shape == x.shape
-    finally:
-        torch.backends.cudnn.allow_tf32 = prev
