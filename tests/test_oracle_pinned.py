@@ -420,3 +420,44 @@ def test_blend_and_texture_sampling_closed_forms():
         want = ((1 - fy) * ((1 - fx) * (10 * r0 + c0) + fx * (10 * r0 + c0 + 1))
                 + fy * ((1 - fx) * (10 * (r0 + 1) + c0) + fx * (10 * (r0 + 1) + c0 + 1)))
         assert abs(got - want) < 1e-5, ((u, v), got, want)
+
+
+def test_phong_shading_closed_form():
+    """SURVEY A.5 (SoftPhongShader with Point / Directional lights) on a configuration worked out by hand.
+    One face in the plane z = 0, counter-clockwise seen from -z ... its vertex normals are (v2 - v1) x (v0 - v1) normalised =
+    (0, 0, -1) here.  Pixel at the face's centroid p = (1/3, 1/3, 0), texel t.
+    Point light at L = (1/3, 1/3, -2): l = (0, 0, -1), n . l = 1 -> diffuse = kd ld; the camera at C = (1/3 + 2, 1/3, -2):
+      v = (2, 0, -2) / sqrt 8 = (s, 0, -s), s = 1 / sqrt 2;  r = 2 (n . l) n - l = (0, 0, -1);  v . r = s
+      -> specular = ks ls s^shininess.
+    Directional light from d = (0, 3, -4) (normalised (0, .6, -.8)): n . l = .8, r = 2 (.8) n - l = (0, -.6, -.8),
+      v . r = .8 s -> specular = ks ls (.8 s)^shininess.  A light behind the face (n . l < 0) adds nothing."""
+    import math
+    verts = torch.tensor([[0.0, 0.0, 0.0], [0.0, 1.0, 0.0], [1.0, 0.0, 0.0]], dtype=torch.float64)
+    faces = torch.tensor([[0, 1, 2]])
+    n = ro.vertex_normals(verts, faces)
+    assert torch.allclose(n, torch.tensor([[0.0, 0.0, -1.0]], dtype=torch.float64).expand(3, 3))
+    texel = torch.tensor([0.2, 0.5, 0.9], dtype=torch.float64).reshape(1, 1, 1, 1, 3)
+    p2f = torch.zeros(1, 1, 1, 1, dtype=torch.int64)
+    bary = torch.full((1, 1, 1, 1, 3), 1.0 / 3.0, dtype=torch.float64)
+    cam = torch.tensor([[1.0 / 3.0 + 2.0, 1.0 / 3.0, -2.0]], dtype=torch.float64)
+    mat = dict(ambient=(0.9, 0.8, 0.7), diffuse=(0.6, 0.5, 0.4), specular=(0.3, 0.2, 0.1), shininess=5.0)
+    la, ld, ls = (0.5, 0.4, 0.3), (0.7, 0.6, 0.5), (0.2, 0.4, 0.6)
+    s = 1.0 / math.sqrt(2.0)
+
+    def expect(cos, vr):
+        return [(mat["ambient"][c] * la[c] + mat["diffuse"][c] * ld[c] * max(cos, 0.0)) * float(texel[0, 0, 0, 0, c])
+                + (mat["specular"][c] * ls[c] * max(vr, 0.0) ** 5.0 if cos > 0 else 0.0) for c in range(3)]
+
+    point = dict(kind="point", ambient=la, diffuse=ld, specular=ls, location=(1.0 / 3.0, 1.0 / 3.0, -2.0))
+    got = ro.phong_colors(texel, p2f, bary, verts, faces, point, mat, cam)[0, 0, 0, 0]
+    assert torch.allclose(got, torch.tensor(expect(1.0, s), dtype=torch.float64), atol=1e-12)
+    direc = dict(kind="directional", ambient=la, diffuse=ld, specular=ls, direction=(0.0, 3.0, -4.0))
+    got = ro.phong_colors(texel, p2f, bary, verts, faces, direc, mat, cam)[0, 0, 0, 0]
+    assert torch.allclose(got, torch.tensor(expect(0.8, 0.8 * s), dtype=torch.float64), atol=1e-12)
+    behind = dict(kind="point", ambient=la, diffuse=ld, specular=ls, location=(1.0 / 3.0, 1.0 / 3.0, 2.0))
+    got = ro.phong_colors(texel, p2f, bary, verts, faces, behind, mat, cam)[0, 0, 0, 0]
+    assert torch.allclose(got, torch.tensor(expect(-1.0, 0.0), dtype=torch.float64), atol=1e-12)
+    amb = dict(kind="ambient", ambient=la, diffuse=(0, 0, 0), specular=(0, 0, 0))
+    got = ro.phong_colors(texel, p2f, bary, verts, faces, amb, mat, cam)[0, 0, 0, 0]
+    assert torch.allclose(got, torch.tensor([mat["ambient"][c] * la[c] * float(texel[0, 0, 0, 0, c]) for c in range(3)],
+                                            dtype=torch.float64), atol=1e-12)
