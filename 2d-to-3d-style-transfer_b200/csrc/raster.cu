@@ -487,7 +487,13 @@ k_fine(const FaceRec* __restrict__ rec, const int* __restrict__ tile_count, cons
                 rgba[3] = 0.0f;
             }
             sp.pix_to_face[pix] = hit ? best.f : -1;
-            if (sub_out) sub_out[pix] = (unsigned long long)(hit ? best.sub : 0);
+            // what the backward needs to find the winning half of a clipped face again: the half itself for a soft render
+            // (its pair rule cannot be re-derived), the z-buffer key of the hard path -- depth bits | face -- when this kernel
+            // stands in for it (blur_radius == 0 through the bins, ST3D_RASTER_BINS=1)
+            if (sub_out)
+                sub_out[pix] = !hit ? ~0ull
+                               : soft ? (unsigned long long)best.sub
+                                      : (((unsigned long long)__float_as_uint(fadd(best.z, 0.0f)) << 32) | (unsigned)best.f);
             if (sp.out_layout == ST3D_LAYOUT_NHWC_RGBA) {
                 reinterpret_cast<float4*>(sp.out_image)[pix] = make_float4(rgba[0], rgba[1], rgba[2], rgba[3]);
             } else if (sp.out_layout == ST3D_LAYOUT_NHWC_RGB) {

@@ -14,6 +14,7 @@ from oracle import render_oracle as ro
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _ops():
@@ -769,3 +770,45 @@ def test_cull_to_frustum_matches_oracle_in_both_paths(cow):
                             faces_per_pixel=2, **kw)
     assert torch.equal(got[0].cpu(), fo["pix_to_face"])
     _close(got[1], fo["zbuf_exact"], what="culled zbuf")
+
+
+def test_tile_bin_stand_in_for_the_hard_path_on_a_clipped_scene(cow, tmp_path):
+    """ST3D_RASTER_BINS=1 (the A/B switch of profiles/r2_raster_ab.md) sends hard rasterization through the tile-bin
+    kernels; on a scene cut by the near plane it must give the z-buffer path's pix_to_face, image and gradients (the
+    switch is read once per process, hence the subprocess)."""
+    import subprocess
+    import sys
+    S = 72
+    R, T = _close_cameras()
+    gen = torch.Generator().manual_seed(31)
+    tex = torch.rand(40, 56, 3, generator=gen)
+    cot = torch.randn(R.shape[0], S, S, 4, generator=gen)
+    torch.save(dict(verts=cow["verts"], faces=cow["faces"], fuv=cow["verts_uvs"][cow["faces_uvs"]], R=R, T=T, tex=tex, cot=cot),
+               tmp_path / "scene.pt")
+    code = f"""
+import sys, torch
+sys.path[:0] = [{ROOT!r}, {os.path.join(ROOT, '2d-to-3d-style-transfer_b200')!r}]
+from st3d import ops
+from oracle import render_oracle as ro
+d = torch.load({str(tmp_path / 'scene.pt')!r})
+k00, k11 = ro.fov_scales(60.0)
+spec = ops.RenderSpec(image_size=({S}, {S}), k00=k00, k11=k11, layout=ops.LAYOUT_NHWC_RGBA)
+img, _, p2f, state = ops.render_forward(spec, d['verts'].cuda(), d['faces'].int().cuda(), d['R'].cuda(), d['T'].cuda(),
+                                        face_uvs=d['fuv'].cuda(), texture=d['tex'].cuda())
+g_tex, g_verts, _ = ops.render_backward(state, d['cot'].cuda(), need_texture=True, need_verts=True)
+torch.cuda.synchronize()
+ops.poll_overflow(block=True)
+torch.save(dict(img=img.cpu(), p2f=p2f.cpu(), g_tex=g_tex.cpu(), g_verts=g_verts.cpu()), sys.argv[1])
+"""
+    outs = {}
+    for bins in ("0", "1"):
+        out = tmp_path / f"out_{bins}.pt"
+        r = subprocess.run([sys.executable, "-c", code, str(out)], env=dict(os.environ, ST3D_RASTER_BINS=bins),
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-3000:]
+        outs[bins] = torch.load(out)
+    a, b = outs["0"], outs["1"]
+    assert (a["p2f"] >= 0).float().mean() > 0.3 and torch.equal(a["p2f"], b["p2f"])
+    _close(b["img"], a["img"].double(), tol=1e-6, what="image through the bins")
+    _close(b["g_tex"], a["g_tex"].double(), tol=1e-5, what="texture gradient through the bins")
+    _close(b["g_verts"], a["g_verts"].double(), tol=1e-5, what="vertex gradient through the bins")
