@@ -461,3 +461,39 @@ def test_phong_shading_closed_form():
     got = ro.phong_colors(texel, p2f, bary, verts, faces, amb, mat, cam)[0, 0, 0, 0]
     assert torch.allclose(got, torch.tensor([mat["ambient"][c] * la[c] * float(texel[0, 0, 0, 0, c]) for c in range(3)],
                                             dtype=torch.float64), atol=1e-12)
+
+
+def test_blend_of_two_fragments_closed_form():
+    """softmax_rgb_blend for K = 2, written out with math.exp: probabilities p_k = sigmoid(-d_k / sigma),
+    alpha = 1 - (1 - p_0)(1 - p_1), weights w_k = p_k exp((zinv_k - zmax) / gamma) with zmax the largest zinv (the NEAREST
+    fragment), delta = max(exp((eps - zmax) / gamma), eps), rgb = (sum_k w_k c_k + delta bg) / (sum_k w_k + delta); an
+    empty second slot (pix_to_face = -1) must drop out of every sum."""
+    import math
+    sigma, gamma, znear, zfar, eps = 2e-3, 5e-2, 1.0, 100.0, 1e-10
+    c = [(0.9, 0.1, 0.3), (0.2, 0.8, 0.5)]
+    d = [-4e-4, 1.5e-3]                  # inside the first face, just outside the second (a soft edge)
+    z = [3.0, 2.0]                       # the second fragment is nearer
+    bg = (1.0, 0.5, 0.25)
+    colors = torch.tensor(c, dtype=torch.float64).reshape(1, 1, 1, 2, 3)
+    dists = torch.tensor(d, dtype=torch.float64).reshape(1, 1, 1, 2)
+    zbuf = torch.tensor(z, dtype=torch.float64).reshape(1, 1, 1, 2)
+    p2f = torch.tensor([4, 9]).reshape(1, 1, 1, 2)
+    out = ro.softmax_rgb_blend(colors, p2f, dists, zbuf, sigma=sigma, gamma=gamma, background=bg, znear=znear, zfar=zfar)[0, 0, 0]
+    p = [1.0 / (1.0 + math.exp(dk / sigma)) for dk in d]
+    zinv = [(zfar - zk) / (zfar - znear) for zk in z]
+    zmax = max(max(zinv), eps)
+    w = [pk * math.exp((zi - zmax) / gamma) for pk, zi in zip(p, zinv)]
+    delta = max(math.exp((eps - zmax) / gamma), eps)
+    want = [(w[0] * c[0][k] + w[1] * c[1][k] + delta * bg[k]) / (w[0] + w[1] + delta) for k in range(3)]
+    assert torch.allclose(out[:3], torch.tensor(want, dtype=torch.float64), atol=1e-12)
+    assert abs(float(out[3]) - (1.0 - (1.0 - p[0]) * (1.0 - p[1]))) < 1e-12
+    assert w[1] > 0 and w[0] < w[1] * 2                     # both fragments matter in this configuration
+    # the second slot empty: the one-fragment formulas
+    p2f1 = torch.tensor([4, -1]).reshape(1, 1, 1, 2)
+    out1 = ro.softmax_rgb_blend(colors, p2f1, dists, zbuf, sigma=sigma, gamma=gamma, background=bg, znear=znear, zfar=zfar)[0, 0, 0]
+    zmax1 = max(zinv[0], eps)
+    w0 = p[0] * math.exp((zinv[0] - zmax1) / gamma)
+    delta1 = max(math.exp((eps - zmax1) / gamma), eps)
+    want1 = [(w0 * c[0][k] + delta1 * bg[k]) / (w0 + delta1) for k in range(3)]
+    assert torch.allclose(out1[:3], torch.tensor(want1, dtype=torch.float64), atol=1e-12)
+    assert abs(float(out1[3]) - p[0]) < 1e-12
